@@ -1,0 +1,45 @@
+// common.cuh -- error plumbing and small device helpers shared by every translation unit.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <string>
+
+#include "../../include/probav_b200.h"
+
+namespace pv {
+
+// thread-local last-error text behind pv_last_error()
+std::string& last_error();
+int set_error(int code, const char* fmt, ...);
+// every kernel launch of this library goes through here so bench.py can report gpu_launches
+void count_launch(int n = 1);
+int64_t launch_count();
+
+#define PV_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return pv::set_error(PV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                \
+                                 cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+    } while (0)
+
+#define PV_LAUNCH_CHECK()                                                                     \
+    do {                                                                                      \
+        pv::count_launch();                                                                   \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess)                                                                \
+            return pv::set_error(PV_ERR_CUDA, "kernel launch failed: %s (%s:%d)",            \
+                                 cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+    } while (0)
+
+#define PV_TRY(expr)                                                                          \
+    do {                                                                                      \
+        int _s = (expr);                                                                      \
+        if (_s != 0) return _s;                                                               \
+    } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace pv

@@ -1,0 +1,864 @@
+// engine.cu -- graph plan, arenas, forward / backward / optimizer sequencing, and the extern "C" ABI
+// declared in include/probav_b200.h.
+//
+// Replaces, behind the C-ABI:
+//   WDSRConv3D.build                     reference models/modelsTF.py:15-43   -> pv_model_create (plan below)
+//   WDSRNetHRResidualPath / ResConv3D    modelsTF.py:55-74, 177-189           -> Model::forward trunk
+//   ConvReduceAndUpscale{,v2,v3,Ex}      modelsTF.py:76-175                   -> reducer plan (T = 9, 7, 13, 19)
+//   WDSRNetLRResidualPath                modelsTF.py:45-53                    -> 2-D skip (conv layers with T = kt = 1)
+//   ModelTrainer.trainStep / testStep    models/trainClass.py:124-143         -> Trainer::forward_backward / apply / eval
+//   tf.keras.optimizers.Nadam/Adam/SGD   train.py:76-83                       -> Trainer::apply (host scalars + one kernel)
+//   resolve / resolveByBatch / reconstruct_from_patches   test.py:114-160     -> pv_resolve*, pv_predict_*
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include <atomic>
+
+#include "kernels.h"
+
+namespace pv {
+
+// ------------------------------------------------------------------------------------------ error plumbing
+std::string& last_error() {
+    static thread_local std::string e;
+    return e;
+}
+int set_error(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error() = buf;
+    return code;
+}
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches += n; }
+int64_t launch_count() { return g_launches.load(); }
+
+static inline int storage_channels(int c) { return c > 16 ? ((c + 31) / 32) * 32 : c; }
+
+struct Layer {
+    std::string name;
+    int k[3];            // kernel (H, W, T)
+    int cin, cout, cin_s, cout_s;
+    int pad[3];          // zero padding per side ('same' = k/2, 'valid' = 0)
+    int relu;
+    int Hi, Wi, Ti, Ho, Wo, To;
+    long long v_off, g_off, b_off, weff_off, bias_s_off, scale_off;
+    int taps() const { return k[0] * k[1] * k[2]; }
+};
+
+struct PInfo { std::string name; int rank; int64_t shape[5]; int64_t off, numel; };
+
+struct Pool {
+    std::map<std::string, float*> ptr;
+    std::vector<std::pair<std::string, size_t>> spec;   // name, floats per sample
+    int cap = 0;
+    void add(const std::string& n, size_t per) {
+        for (auto& s : spec) if (s.first == n) { s.second = std::max(s.second, per); return; }
+        spec.emplace_back(n, per);
+    }
+    int ensure(int B) {
+        if (B <= cap) return 0;
+        release();
+        for (auto& s : spec) {
+            float* d = nullptr;
+            PV_CUDA(cudaMalloc(&d, s.second * (size_t)B * sizeof(float)));
+            ptr[s.first] = d;
+        }
+        cap = B;
+        return 0;
+    }
+    void release() {
+        for (auto& kv : ptr) cudaFree(kv.second);
+        ptr.clear();
+        cap = 0;
+    }
+    float* operator[](const std::string& n) {
+        auto it = ptr.find(n);
+        return it == ptr.end() ? nullptr : it->second;
+    }
+};
+
+}  // namespace pv
+
+using namespace pv;
+
+struct pv_model {
+    pv_cfg cfg;
+    int device = 0;
+    int S = 0, T = 0, P = 0, F = 0, R = 0, nred = 0;
+    std::vector<Layer> layers;
+    std::vector<PInfo> pinfo;
+    std::vector<int> red_pad;          // 3 ints per reducer: reflect pad before it
+    long long nparams = 0, nweff = 0, nbias_s = 0, nscale = 0;
+    float *params = nullptr, *weff = nullptr, *weffT = nullptr, *bias_s = nullptr, *scale = nullptr;
+    WnLayer* wn_tab = nullptr;
+    int wn_blocks = 0;
+    bool weff_dirty = true;
+    Pool pool_infer, pool_train;
+    float *stage_lr = nullptr, *stage_sr = nullptr, *stage_scene = nullptr;   // host-API staging
+    size_t stage_lr_n = 0, stage_sr_n = 0, stage_scene_n = 0;
+
+    int li(const std::string& n) const {
+        for (size_t i = 0; i < layers.size(); ++i) if (layers[i].name == n) return (int)i;
+        return -1;
+    }
+    std::string A(int i, bool tr) const { return tr ? "a" + std::to_string(i) : "a" + std::to_string(i & 1); }
+    std::string E(int i, bool tr) const { return tr ? "E" + std::to_string(i) : "E"; }
+    std::string D(int i, bool tr) const { return tr ? "D" + std::to_string(i) : "D"; }
+};
+
+struct pv_trainer {
+    pv_model* m = nullptr;
+    int opt = PV_OPT_NADAM, loss_kind = PV_LOSS_L1;
+    float lr = 1e-3f;
+    long long iter = 0;
+    double momentum_cache = 1.0;
+    float *grads = nullptr, *dweff = nullptr, *dbias_s = nullptr, *m1 = nullptr, *m2 = nullptr;
+    // per-batch loss workspace
+    int capB = 0;
+    float *sr = nullptr, *dsr = nullptr, *loss_ps = nullptr, *cpsnr_ps = nullptr, *out2 = nullptr;
+    int32_t *best = nullptr, *cnt = nullptr;
+    // host-API staging
+    float *s_lr = nullptr, *s_hr = nullptr;
+    uint8_t* s_mask = nullptr;
+    int s_cap = 0;
+};
+
+namespace pv {
+
+// ------------------------------------------------------------------------------------------ plan
+static int add_layer(pv_model* m, const std::string& name, int kh, int kw, int kt, int cin, int cout, bool same,
+                     int relu, int Hi, int Wi, int Ti) {
+    Layer L;
+    L.name = name;
+    L.k[0] = kh; L.k[1] = kw; L.k[2] = kt;
+    L.cin = cin; L.cout = cout;
+    L.cin_s = storage_channels(cin); L.cout_s = storage_channels(cout);
+    for (int a = 0; a < 3; ++a) L.pad[a] = same ? L.k[a] / 2 : 0;
+    L.relu = relu;
+    L.Hi = Hi; L.Wi = Wi; L.Ti = Ti;
+    L.Ho = Hi + 2 * L.pad[0] - (kh - 1); L.Wo = Wi + 2 * L.pad[1] - (kw - 1); L.To = Ti + 2 * L.pad[2] - (kt - 1);
+    const long long K = (long long)L.taps() * cin;
+    L.v_off = m->nparams; m->nparams += K * cout;
+    L.g_off = m->nparams; m->nparams += cout;
+    L.b_off = m->nparams; m->nparams += cout;
+    L.weff_off = m->nweff; m->nweff += (long long)L.taps() * L.cin_s * L.cout_s;
+    L.bias_s_off = m->nbias_s; m->nbias_s += L.cout_s;
+    L.scale_off = m->nscale; m->nscale += 2 * cout;
+    const bool is2d = (kt == 1 && Ti == 1 && name.rfind("residConv", 0) == 0);
+    PInfo pv_;
+    pv_.name = name + "/v";
+    if (is2d) { pv_.rank = 4; pv_.shape[0] = kh; pv_.shape[1] = kw; pv_.shape[2] = cin; pv_.shape[3] = cout; pv_.shape[4] = 0; }
+    else { pv_.rank = 5; pv_.shape[0] = kh; pv_.shape[1] = kw; pv_.shape[2] = kt; pv_.shape[3] = cin; pv_.shape[4] = cout; }
+    pv_.off = L.v_off; pv_.numel = K * cout;
+    m->pinfo.push_back(pv_);
+    PInfo pg; pg.name = name + "/g"; pg.rank = 1; pg.shape[0] = cout; pg.shape[1] = pg.shape[2] = pg.shape[3] = pg.shape[4] = 0;
+    pg.off = L.g_off; pg.numel = cout;
+    m->pinfo.push_back(pg);
+    PInfo pb = pg; pb.name = name + "/bias"; pb.off = L.b_off;
+    m->pinfo.push_back(pb);
+    m->layers.push_back(L);
+    return (int)m->layers.size() - 1;
+}
+
+static int build_plan(pv_model* m) {
+    const pv_cfg& c = m->cfg;
+    if (c.num_res_blocks < 0 || c.scale < 1 || c.num_filters < 1 || c.exp_rate < 1 || c.patch_size < 1 || c.max_shift < 0)
+        return set_error(PV_ERR_BAD_CONFIG, "bad cfg value");
+    if (c.kernel_size != 3)
+        return set_error(PV_ERR_BAD_CONFIG, "kernel_size=%d: only 3 is supported (cfg/p16t9c85r12.cfg:20)", c.kernel_size);
+    if (!c.is_grayscale)
+        return set_error(PV_ERR_BAD_CONFIG, "is_grayscale=0 (3-channel input) is not built; PROBA-V bands are single-channel");
+    const int ks = c.kernel_size;
+    m->S = c.patch_size + c.max_shift;            // modelsTF.py:19
+    m->T = c.num_low_res_imgs; m->P = c.patch_size; m->F = c.num_filters; m->R = c.num_res_blocks;
+    const int S = m->S, T = m->T, F = m->F;
+    const int dec = (int)(F * c.decay_rate);      // int(numFilters*decayRate), modelsTF.py:182
+    if (dec < 1) return set_error(PV_ERR_BAD_CONFIG, "int(num_filters*decay_rate) = %d", dec);
+    // reducer table per modelsTF.py:62-69
+    struct Red { int k; int p[3]; };
+    std::vector<Red> reds;
+    if (T == 9) { for (int i = 0; i < T / c.scale; ++i) reds.push_back({ks, {i == 0 ? 1 : 0, i == 0 ? 1 : 0, 0}}); }
+    else if (T == 7) { for (int i = 0; i < T / c.scale; ++i) reds.push_back({ks, {0, 0, 0}}); }
+    else if (T == 13) { for (int i = 0; i < 5; ++i) reds.push_back({ks, {i < 3 ? 1 : 0, i < 3 ? 1 : 0, 0}}); }
+    else if (T == 19) {
+        const int pp[10][3] = {{2, 2, 2}, {2, 2, 1}, {2, 2, 0}, {2, 2, 0}, {1, 1, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int i = 0; i < 10; ++i) reds.push_back({i == 0 ? 5 : ks, {pp[i][0], pp[i][1], pp[i][2]}});
+    } else
+        return set_error(PV_ERR_BAD_CONFIG, "num_low_res_imgs=%d: the reference graph only has reducers for 7, 9, 13, 19 "
+                                            "(modelsTF.py:62-69)", T);
+    m->nred = (int)reds.size();
+
+    add_layer(m, "mainConv1", ks, ks, ks, 1, F, true, 1, S, S, T);
+    for (int i = 0; i < m->R; ++i) {
+        add_layer(m, "expConv_" + std::to_string(i), 1, 1, 1, F, F * c.exp_rate, true, 1, S, S, T);
+        add_layer(m, "decConv_" + std::to_string(i), 1, 1, 1, F * c.exp_rate, dec, true, 0, S, S, T);
+        add_layer(m, "normConv_" + std::to_string(i), ks, ks, ks, dec, F, true, 0, S, S, T);
+    }
+    int H = S, W = S, TT = T;
+    for (int i = 0; i < m->nred; ++i) {
+        for (int a = 0; a < 3; ++a) m->red_pad.push_back(reds[i].p[a]);
+        H += 2 * reds[i].p[0]; W += 2 * reds[i].p[1]; TT += 2 * reds[i].p[2];
+        if (H < reds[i].k || W < reds[i].k || TT < reds[i].k) return set_error(PV_ERR_BAD_CONFIG, "reducer %d collapses", i + 1);
+        const int id = add_layer(m, "convReducer_" + std::to_string(i + 1), reds[i].k, reds[i].k, reds[i].k, F, F, false, 1, H, W, TT);
+        H = m->layers[id].Ho; W = m->layers[id].Wo; TT = m->layers[id].To;
+    }
+    if (H < ks || W < ks || TT < ks) return set_error(PV_ERR_BAD_CONFIG, "upscale conv input %dx%dx%d too small", H, W, TT);
+    const int up = add_layer(m, "upscaleConv1", ks, ks, ks, F, c.scale * c.scale, false, 0, H, W, TT);
+    if (m->layers[up].Ho != m->P || m->layers[up].Wo != m->P || m->layers[up].To != 1)
+        return set_error(PV_ERR_BAD_CONFIG, "main path ends at %dx%dx%d but Reshape((patch,patch,scale^2)) needs %dx%dx1 "
+                         "(modelsTF.py:71): max_shift must be 6 for this reducer", m->layers[up].Ho, m->layers[up].Wo,
+                         m->layers[up].To, m->P, m->P);
+    int h2 = S, cin = 1;
+    for (int i = 0; i < c.scale; ++i) {
+        if (h2 < ks) return set_error(PV_ERR_BAD_CONFIG, "2-D skip path collapses");
+        const int id = add_layer(m, "residConv" + std::to_string(i + 1), ks, ks, 1, cin, c.scale * c.scale, false, i == 0, h2, h2, 1);
+        h2 = m->layers[id].Ho; cin = c.scale * c.scale;
+    }
+    if (h2 != m->P)
+        return set_error(PV_ERR_BAD_CONFIG, "2-D skip path ends at %dx%d, main path at %dx%d (Add at modelsTF.py:38 would fail)", h2, h2, m->P, m->P);
+
+    // activation pools
+    for (int tr = 0; tr < 2; ++tr) {
+        Pool& P = tr ? m->pool_train : m->pool_infer;
+        const size_t vox = (size_t)S * S * T;
+        P.add("xn", vox);
+        P.add("mn", (size_t)S * S);
+        for (int i = 0; i <= m->R; ++i) P.add(m->A(i, tr), vox * F);
+        for (int i = 0; i < m->R; ++i) {
+            P.add(m->E(i, tr), vox * F * c.exp_rate);
+            P.add(m->D(i, tr), vox * storage_channels(dec));
+        }
+        for (int i = 0; i < m->nred; ++i) {
+            const Layer& L = m->layers[m->li("convReducer_" + std::to_string(i + 1))];
+            if (reds[i].p[0] || reds[i].p[1] || reds[i].p[2]) P.add("pad" + std::to_string(i + 1), (size_t)L.Hi * L.Wi * L.Ti * F);
+            P.add("r" + std::to_string(i + 1), (size_t)L.Ho * L.Wo * L.To * F);
+        }
+        P.add("U", (size_t)m->P * m->P * c.scale * c.scale);
+        for (int i = 0; i < c.scale; ++i) {
+            const Layer& L = m->layers[m->li("residConv" + std::to_string(i + 1))];
+            P.add("q" + std::to_string(i + 1), (size_t)L.Ho * L.Wo * L.cout_s);
+        }
+        if (tr) {   // gradient buffers
+            P.add("g_a0", vox * F); P.add("g_a1", vox * F);
+            P.add("g_E", vox * F * c.exp_rate);
+            P.add("g_D", vox * storage_channels(dec));
+            for (int i = 0; i < m->nred; ++i) {
+                const Layer& L = m->layers[m->li("convReducer_" + std::to_string(i + 1))];
+                if (reds[i].p[0] || reds[i].p[1] || reds[i].p[2]) P.add("g_pad" + std::to_string(i + 1), (size_t)L.Hi * L.Wi * L.Ti * F);
+                P.add("g_r" + std::to_string(i + 1), (size_t)L.Ho * L.Wo * L.To * F);
+            }
+            P.add("g_tail", (size_t)m->P * m->P * c.scale * c.scale);
+            for (int i = 0; i + 1 < c.scale; ++i) {
+                const Layer& L = m->layers[m->li("residConv" + std::to_string(i + 1))];
+                P.add("g_q" + std::to_string(i + 1), (size_t)L.Ho * L.Wo * L.cout_s);
+            }
+        }
+    }
+    return 0;
+}
+
+static ConvP conv_desc(const Layer& L, const float* w, const float* bias, int B) {
+    ConvP p;
+    p.x = nullptr; p.xmask = nullptr; p.w = w; p.bias = bias; p.residual = nullptr; p.y = nullptr;
+    p.B = B; p.Hi = L.Hi; p.Wi = L.Wi; p.Ti = L.Ti; p.Ho = L.Ho; p.Wo = L.Wo; p.To = L.To;
+    p.cin = L.cin_s; p.cout = L.cout_s; p.kh = L.k[0]; p.kw = L.k[1]; p.kt = L.k[2];
+    p.ph = L.pad[0]; p.pw = L.pad[1]; p.pt = L.pad[2]; p.relu = L.relu;
+    return p;
+}
+
+static int conv_fwd(pv_model* m, int li, const float* in, float* out, const float* res, int B, cudaStream_t st) {
+    const Layer& L = m->layers[li];
+    ConvP p = conv_desc(L, m->weff + L.weff_off, m->bias_s + L.bias_s_off, B);
+    p.x = in; p.y = out; p.residual = res;
+    return launch_conv(p, st);
+}
+
+// data gradient: correlate dy (masked by the layer's ReLU output) with the flipped/transposed kernel, pad' = k-1-pad
+static int conv_dgrad(pv_model* m, int li, const float* gout, const float* relu_ref, float* gin, const float* res, int B, cudaStream_t st) {
+    const Layer& L = m->layers[li];
+    ConvP p;
+    p.x = gout; p.xmask = relu_ref; p.w = m->weffT + L.weff_off; p.bias = nullptr; p.residual = res; p.y = gin;
+    p.B = B; p.Hi = L.Ho; p.Wi = L.Wo; p.Ti = L.To; p.Ho = L.Hi; p.Wo = L.Wi; p.To = L.Ti;
+    p.cin = L.cout_s; p.cout = L.cin_s; p.kh = L.k[0]; p.kw = L.k[1]; p.kt = L.k[2];
+    p.ph = L.k[0] - 1 - L.pad[0]; p.pw = L.k[1] - 1 - L.pad[1]; p.pt = L.k[2] - 1 - L.pad[2];
+    p.relu = 0;
+    return launch_conv(p, st);
+}
+
+static int conv_wgrad(pv_trainer* t, int li, const float* in, const float* gout, const float* relu_ref, int B, cudaStream_t st) {
+    const Layer& L = t->m->layers[li];
+    WgradP p;
+    p.x = in; p.dy = gout; p.ymask = relu_ref; p.dw = t->dweff + L.weff_off; p.db = t->dbias_s + L.bias_s_off;
+    p.B = B; p.Hi = L.Hi; p.Wi = L.Wi; p.Ti = L.Ti; p.Ho = L.Ho; p.Wo = L.Wo; p.To = L.To;
+    p.cin = L.cin_s; p.cout = L.cout_s; p.kh = L.k[0]; p.kw = L.k[1]; p.kt = L.k[2];
+    p.ph = L.pad[0]; p.pw = L.pad[1]; p.pt = L.pad[2];
+    return launch_wgrad(p, st);
+}
+
+static int refresh_weights(pv_model* m, cudaStream_t st) {
+    if (!m->weff_dirty) return 0;
+    PV_TRY(launch_wn_prep(m->wn_tab, (int)m->layers.size(), m->wn_blocks, m->params, m->weff, m->weffT, m->bias_s, m->scale, st));
+    m->weff_dirty = false;
+    return 0;
+}
+
+// model(x): modelsTF.py:15-43
+static int model_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip_round, cudaStream_t st) {
+    if (!lr || !sr || B <= 0) return set_error(PV_ERR_BAD_ARG, "forward: null buffer or B=%d", B);
+    PV_CUDA(cudaSetDevice(m->device));
+    Pool& P = tr ? m->pool_train : m->pool_infer;
+    PV_TRY(P.ensure(B));
+    PV_TRY(refresh_weights(m, st));
+    const pv_cfg& c = m->cfg;
+    PV_TRY(launch_prep(lr, B, m->S * m->S, m->T, c.mean, c.std, P["xn"], P["mn"], st));
+    PV_TRY(conv_fwd(m, m->li("mainConv1"), P["xn"], P[m->A(0, tr)], nullptr, B, st));
+    for (int i = 0; i < m->R; ++i) {                                   // ResConv3D, modelsTF.py:177-189
+        const int e = m->li("expConv_" + std::to_string(i));
+        PV_TRY(conv_fwd(m, e, P[m->A(i, tr)], P[m->E(i, tr)], nullptr, B, st));
+        PV_TRY(conv_fwd(m, e + 1, P[m->E(i, tr)], P[m->D(i, tr)], nullptr, B, st));
+        PV_TRY(conv_fwd(m, e + 2, P[m->D(i, tr)], P[m->A(i + 1, tr)], P[m->A(i, tr)], B, st));
+    }
+    const float* cur = P[m->A(m->R, tr)];
+    for (int i = 0; i < m->nred; ++i) {                                // ConvReduceAndUpscale*, modelsTF.py:76-175
+        const int id = m->li("convReducer_" + std::to_string(i + 1));
+        const Layer& L = m->layers[id];
+        const int* rp = &m->red_pad[3 * i];
+        if (rp[0] || rp[1] || rp[2]) {
+            float* pd = P["pad" + std::to_string(i + 1)];
+            PV_TRY(launch_reflect_pad(cur, pd, B, L.Hi - 2 * rp[0], L.Wi - 2 * rp[1], L.Ti - 2 * rp[2], m->F, rp[0], rp[1], rp[2], st));
+            cur = pd;
+        }
+        float* out = P["r" + std::to_string(i + 1)];
+        PV_TRY(conv_fwd(m, id, cur, out, nullptr, B, st));
+        cur = out;
+    }
+    PV_TRY(conv_fwd(m, m->li("upscaleConv1"), cur, P["U"], nullptr, B, st));
+    const float* q = P["mn"];
+    for (int i = 0; i < c.scale; ++i) {                                // WDSRNetLRResidualPath, modelsTF.py:45-53
+        float* out = P["q" + std::to_string(i + 1)];
+        PV_TRY(conv_fwd(m, m->li("residConv" + std::to_string(i + 1)), q, out, nullptr, B, st));
+        q = out;
+    }
+    PV_TRY(launch_tail(P["U"], q, B, m->P, c.scale, c.mean, c.std, clip_round, sr, st));
+    return 0;
+}
+
+// tape.gradient(loss, trainable_variables): trainClass.py:131.  g_sr = dL/dSR [B, sP, sP].
+static int model_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
+    pv_model* m = t->m;
+    Pool& P = m->pool_train;
+    const pv_cfg& c = m->cfg;
+    PV_CUDA(cudaMemsetAsync(t->dweff, 0, m->nweff * sizeof(float), st));
+    PV_CUDA(cudaMemsetAsync(t->dbias_s, 0, m->nbias_s * sizeof(float), st));
+    PV_TRY(launch_tail_bwd(g_sr, B, m->P, c.scale, c.std, P["g_tail"], st));
+    // ---- 2-D skip path
+    {
+        const float* gout = P["g_tail"];
+        for (int i = c.scale; i >= 1; --i) {
+            const int id = m->li("residConv" + std::to_string(i));
+            const float* in = (i == 1) ? P["mn"] : P["q" + std::to_string(i - 1)];
+            const float* ref = m->layers[id].relu ? P["q" + std::to_string(i)] : nullptr;
+            PV_TRY(conv_wgrad(t, id, in, gout, ref, B, st));
+            if (i > 1) {
+                float* gin = P["g_q" + std::to_string(i - 1)];
+                PV_TRY(conv_dgrad(m, id, gout, ref, gin, nullptr, B, st));
+                gout = gin;
+            }
+        }
+    }
+    // ---- upscale conv + reducers
+    const int R = m->R;
+    {
+        const int up = m->li("upscaleConv1");
+        const float* in = m->nred ? P["r" + std::to_string(m->nred)] : P[m->A(R, true)];
+        float* gin = m->nred ? P["g_r" + std::to_string(m->nred)] : P["g_a" + std::to_string(R & 1)];
+        PV_TRY(conv_wgrad(t, up, in, P["g_tail"], nullptr, B, st));
+        PV_TRY(conv_dgrad(m, up, P["g_tail"], nullptr, gin, nullptr, B, st));
+    }
+    for (int i = m->nred; i >= 1; --i) {
+        const int id = m->li("convReducer_" + std::to_string(i));
+        const Layer& L = m->layers[id];
+        const int* rp = &m->red_pad[3 * (i - 1)];
+        const bool padded = rp[0] || rp[1] || rp[2];
+        const float* prev = (i == 1) ? P[m->A(R, true)] : P["r" + std::to_string(i - 1)];
+        float* gprev = (i == 1) ? P["g_a" + std::to_string(R & 1)] : P["g_r" + std::to_string(i - 1)];
+        const float* in = padded ? P["pad" + std::to_string(i)] : prev;
+        const float* gout = P["g_r" + std::to_string(i)];
+        const float* ref = P["r" + std::to_string(i)];
+        PV_TRY(conv_wgrad(t, id, in, gout, ref, B, st));
+        if (padded) {
+            float* gp = P["g_pad" + std::to_string(i)];
+            PV_TRY(conv_dgrad(m, id, gout, ref, gp, nullptr, B, st));
+            PV_TRY(launch_reflect_pad_bwd(gp, gprev, B, L.Hi - 2 * rp[0], L.Wi - 2 * rp[1], L.Ti - 2 * rp[2], m->F, rp[0], rp[1], rp[2], st));
+        } else {
+            PV_TRY(conv_dgrad(m, id, gout, ref, gprev, nullptr, B, st));
+        }
+    }
+    // ---- residual blocks, last to first
+    for (int i = R - 1; i >= 0; --i) {
+        const int e = m->li("expConv_" + std::to_string(i));
+        const float* gout = P["g_a" + std::to_string((i + 1) & 1)];
+        float* gin = P["g_a" + std::to_string(i & 1)];
+        PV_TRY(conv_wgrad(t, e + 2, P[m->D(i, true)], gout, nullptr, B, st));
+        PV_TRY(conv_dgrad(m, e + 2, gout, nullptr, P["g_D"], nullptr, B, st));
+        PV_TRY(conv_wgrad(t, e + 1, P[m->E(i, true)], P["g_D"], nullptr, B, st));
+        PV_TRY(conv_dgrad(m, e + 1, P["g_D"], nullptr, P["g_E"], nullptr, B, st));
+        PV_TRY(conv_wgrad(t, e, P[m->A(i, true)], P["g_E"], P[m->E(i, true)], B, st));
+        PV_TRY(conv_dgrad(m, e, P["g_E"], P[m->E(i, true)], gin, gout, B, st));      // + skip connection
+    }
+    PV_TRY(conv_wgrad(t, m->li("mainConv1"), P["xn"], P["g_a0"], P[m->A(0, true)], B, st));
+    PV_TRY(launch_wn_bwd(m->wn_tab, (int)m->layers.size(), m->wn_blocks, m->params, m->scale, t->dweff, t->dbias_s, t->grads, st));
+    return 0;
+}
+
+static int trainer_ensure(pv_trainer* t, int B) {
+    if (B <= t->capB) return 0;
+    cudaFree(t->sr); cudaFree(t->dsr); cudaFree(t->loss_ps); cudaFree(t->cpsnr_ps); cudaFree(t->best); cudaFree(t->cnt);
+    const size_t hw = (size_t)t->m->P * t->m->cfg.scale * t->m->P * t->m->cfg.scale;
+    PV_CUDA(cudaMalloc(&t->sr, hw * B * sizeof(float)));
+    PV_CUDA(cudaMalloc(&t->dsr, hw * B * sizeof(float)));
+    PV_CUDA(cudaMalloc(&t->loss_ps, B * sizeof(float)));
+    PV_CUDA(cudaMalloc(&t->cpsnr_ps, B * sizeof(float)));
+    PV_CUDA(cudaMalloc(&t->best, B * sizeof(int32_t)));
+    PV_CUDA(cudaMalloc(&t->cnt, B * sizeof(int32_t)));
+    t->capB = B;
+    return 0;
+}
+
+// fwd -> loss (+ cPSNR metric in the same pass) [-> grads]
+static int trainer_fwd_loss(pv_trainer* t, const float* lr, const float* hr, const uint8_t* mask, int B, float grad_scale,
+                            bool backward, float* out_dev, cudaStream_t st) {
+    if (!lr || !hr || !mask || !out_dev || B <= 0) return set_error(PV_ERR_BAD_ARG, "step: null buffer or B=%d", B);
+    pv_model* m = t->m;
+    PV_TRY(trainer_ensure(t, B));
+    PV_TRY(model_forward(m, lr, B, t->sr, true, 0, st));
+    const int HW = m->P * m->cfg.scale;
+    PV_TRY(shift_loss_device(t->loss_kind, hr, mask, t->sr, B, HW, HW, 3, grad_scale, t->loss_ps, t->best, t->cnt,
+                             t->cpsnr_ps, out_dev, backward ? t->dsr : nullptr, nullptr, st));
+    PV_TRY(launch_mean(t->cpsnr_ps, B, out_dev + 1, st));
+    if (backward) PV_TRY(model_backward(t, t->dsr, B, st));
+    return 0;
+}
+
+// optimizer.apply_gradients: trainClass.py:132 (Keras Nadam per SURVEY Appendix B.7)
+static int trainer_apply(pv_trainer* t, cudaStream_t st) {
+    pv_model* m = t->m;
+    const long long n = m->nparams;
+    const double b1 = 0.9, b2 = 0.999, eps = 1e-7;
+    const long long step = t->iter + 1;
+    if (t->opt == PV_OPT_NADAM) {
+        const double decay = 0.004;
+        const double mu_t = b1 * (1.0 - 0.5 * std::pow(0.96, decay * step));
+        const double mu_t1 = b1 * (1.0 - 0.5 * std::pow(0.96, decay * (step + 1)));
+        const double Pt = t->momentum_cache * mu_t, Pt1 = Pt * mu_t1;
+        t->momentum_cache = Pt;
+        NadamScalars s;
+        s.lr = t->lr; s.b1 = (float)b1; s.b2 = (float)b2; s.eps = (float)eps; s.mu_t = (float)mu_t; s.mu_t1 = (float)mu_t1;
+        s.one_minus_Pt = (float)(1.0 - Pt); s.one_minus_Pt1 = (float)(1.0 - Pt1);
+        s.one_minus_b2t = (float)(1.0 - std::pow(b2, (double)step));
+        PV_TRY(launch_nadam(m->params, t->grads, t->m1, t->m2, n, s, st));
+    } else if (t->opt == PV_OPT_ADAM) {
+        const double lr_t = t->lr * std::sqrt(1.0 - std::pow(b2, (double)step)) / (1.0 - std::pow(b1, (double)step));
+        PV_TRY(launch_adam(m->params, t->grads, t->m1, t->m2, n, (float)lr_t, (float)b1, (float)b2, (float)eps, st));
+    } else {
+        PV_TRY(launch_sgd(m->params, t->grads, n, t->lr, st));
+    }
+    t->iter = step;
+    m->weff_dirty = true;
+    return 0;
+}
+
+static cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace pv
+
+// =========================================================================================== extern "C"
+extern "C" {
+
+int pv_abi_version(void) { return PV_ABI_VERSION; }
+const char* pv_last_error(void) { return pv::last_error().c_str(); }
+int64_t pv_launch_count(void) { return pv::launch_count(); }
+
+int pv_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+int pv_model_create(const pv_cfg* cfg, int device, pv_model** out) {
+    if (!cfg || !out) return set_error(PV_ERR_BAD_ARG, "pv_model_create: null argument");
+    *out = nullptr;
+    pv_model* m = new pv_model();
+    m->cfg = *cfg;
+    m->device = device;
+    int s = build_plan(m);
+    if (s) { delete m; return s; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        delete m;
+        return set_error(PV_ERR_NO_DEVICE, "no CUDA device: libprobav_b200 has no CPU fallback");
+    }
+    cudaDeviceProp prop;
+    if (device < 0 || device >= ndev || cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        delete m;
+        return set_error(PV_ERR_NO_DEVICE, "device %d is not an sm_100 (B200) GPU: this library is built for sm_100a only", device);
+    }
+    auto fail = [&](int code) { pv_model_destroy(m); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return fail(set_error(PV_ERR_CUDA, "cudaSetDevice(%d) failed", device));
+    if (cudaMalloc(&m->params, m->nparams * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&m->weff, m->nweff * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&m->weffT, m->nweff * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&m->bias_s, m->nbias_s * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&m->scale, m->nscale * sizeof(float)) != cudaSuccess)
+        return fail(set_error(PV_ERR_CUDA, "cudaMalloc of the weight arenas failed"));
+    cudaMemset(m->params, 0, m->nparams * sizeof(float));
+    cudaMemset(m->weff, 0, m->nweff * sizeof(float));
+    cudaMemset(m->weffT, 0, m->nweff * sizeof(float));
+    cudaMemset(m->bias_s, 0, m->nbias_s * sizeof(float));
+    std::vector<WnLayer> tab(m->layers.size());
+    int blocks = 0;
+    for (size_t i = 0; i < m->layers.size(); ++i) {
+        const Layer& L = m->layers[i];
+        WnLayer& w = tab[i];
+        w.v_off = L.v_off; w.g_off = L.g_off; w.b_off = L.b_off;
+        w.weff_off = L.weff_off; w.weffT_off = L.weff_off; w.bias_s_off = L.bias_s_off; w.scale_off = L.scale_off;
+        w.taps = L.taps(); w.cin = L.cin; w.cout = L.cout; w.cin_s = L.cin_s; w.cout_s = L.cout_s;
+        w.first_block = blocks;
+        blocks += L.cout;
+    }
+    m->wn_blocks = blocks;
+    if (cudaMalloc(&m->wn_tab, tab.size() * sizeof(WnLayer)) != cudaSuccess ||
+        cudaMemcpy(m->wn_tab, tab.data(), tab.size() * sizeof(WnLayer), cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(set_error(PV_ERR_CUDA, "weight-norm table upload failed"));
+    *out = m;
+    return 0;
+}
+
+void pv_model_destroy(pv_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    m->pool_infer.release();
+    m->pool_train.release();
+    cudaFree(m->params); cudaFree(m->weff); cudaFree(m->weffT); cudaFree(m->bias_s); cudaFree(m->scale); cudaFree(m->wn_tab);
+    cudaFree(m->stage_lr); cudaFree(m->stage_sr); cudaFree(m->stage_scene);
+    delete m;
+}
+
+int pv_model_param_count(const pv_model* m) { return m ? (int)m->pinfo.size() : set_error(PV_ERR_BAD_ARG, "null model"); }
+
+int pv_model_param_info(const pv_model* m, int idx, char* name, int name_cap, int* rank, int64_t shape[5],
+                        int64_t* offset, int64_t* numel) {
+    if (!m || idx < 0 || idx >= (int)m->pinfo.size()) return set_error(PV_ERR_BAD_ARG, "param index %d out of range", idx);
+    const PInfo& p = m->pinfo[idx];
+    if (name && name_cap > 0) { std::strncpy(name, p.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    if (rank) *rank = p.rank;
+    if (shape) for (int i = 0; i < 5; ++i) shape[i] = p.shape[i];
+    if (offset) *offset = p.off;
+    if (numel) *numel = p.numel;
+    return 0;
+}
+
+int64_t pv_model_param_numel(const pv_model* m) { return m ? m->nparams : 0; }
+
+int pv_model_set_params(pv_model* m, const float* flat_host, int64_t n) {
+    if (!m || !flat_host || n != m->nparams) return set_error(PV_ERR_BAD_ARG, "set_params: expected %lld floats", m ? m->nparams : 0LL);
+    PV_CUDA(cudaSetDevice(m->device));
+    PV_CUDA(cudaMemcpy(m->params, flat_host, n * sizeof(float), cudaMemcpyHostToDevice));
+    m->weff_dirty = true;
+    return 0;
+}
+
+int pv_model_get_params(pv_model* m, float* flat_host, int64_t n) {
+    if (!m || !flat_host || n != m->nparams) return set_error(PV_ERR_BAD_ARG, "get_params: expected %lld floats", m ? m->nparams : 0LL);
+    PV_CUDA(cudaSetDevice(m->device));
+    PV_CUDA(cudaDeviceSynchronize());
+    PV_CUDA(cudaMemcpy(flat_host, m->params, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int pv_model_param_arena(pv_model* m, float** dev_ptr, int64_t* n) {
+    if (!m || !dev_ptr || !n) return set_error(PV_ERR_BAD_ARG, "param_arena: null argument");
+    *dev_ptr = m->params; *n = m->nparams;
+    m->weff_dirty = true;       // the caller may write through the pointer (DP broadcast)
+    return 0;
+}
+
+int pv_model_init_g_from_v(pv_model* m) {
+    if (!m) return set_error(PV_ERR_BAD_ARG, "null model");
+    PV_CUDA(cudaSetDevice(m->device));
+    PV_TRY(launch_g_from_v(m->wn_tab, (int)m->layers.size(), m->wn_blocks, m->params, 0));
+    PV_CUDA(cudaDeviceSynchronize());
+    m->weff_dirty = true;
+    return 0;
+}
+
+int pv_forward(pv_model* m, const float* lr_dev, int B, float* sr_dev, void* stream) {
+    if (!m) return set_error(PV_ERR_BAD_ARG, "null model");
+    return model_forward(m, lr_dev, B, sr_dev, false, 0, S_(stream));
+}
+
+int pv_resolve(pv_model* m, const float* lr_dev, int B, float* sr_dev, void* stream) {
+    if (!m) return set_error(PV_ERR_BAD_ARG, "null model");
+    return model_forward(m, lr_dev, B, sr_dev, false, 1, S_(stream));
+}
+
+static int stage_ensure(float** p, size_t* cap, size_t n) {
+    if (n <= *cap) return 0;
+    cudaFree(*p); *p = nullptr; *cap = 0;
+    PV_CUDA(cudaMalloc(p, n * sizeof(float)));
+    *cap = n;
+    return 0;
+}
+
+static int forward_host(pv_model* m, const float* lr_host, int B, float* sr_host, int clip_round) {
+    if (!m || !lr_host || !sr_host || B <= 0) return set_error(PV_ERR_BAD_ARG, "forward_host: null buffer or B=%d", B);
+    PV_CUDA(cudaSetDevice(m->device));
+    const size_t nin = (size_t)m->S * m->S * m->T, nout = (size_t)m->P * m->cfg.scale * m->P * m->cfg.scale;
+    const int chunk = 256;
+    PV_TRY(stage_ensure(&m->stage_lr, &m->stage_lr_n, nin * std::min(B, chunk)));
+    PV_TRY(stage_ensure(&m->stage_sr, &m->stage_sr_n, nout * std::min(B, chunk)));
+    for (int s = 0; s < B; s += chunk) {
+        const int b = std::min(chunk, B - s);
+        PV_CUDA(cudaMemcpyAsync(m->stage_lr, lr_host + nin * s, nin * b * sizeof(float), cudaMemcpyHostToDevice, 0));
+        PV_TRY(model_forward(m, m->stage_lr, b, m->stage_sr, false, clip_round, 0));
+        PV_CUDA(cudaMemcpyAsync(sr_host + nout * s, m->stage_sr, nout * b * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    }
+    PV_CUDA(cudaStreamSynchronize(0));
+    return 0;
+}
+
+int pv_forward_host(pv_model* m, const float* lr_host, int B, float* sr_host) { return forward_host(m, lr_host, B, sr_host, 0); }
+int pv_resolve_host(pv_model* m, const float* lr_host, int B, float* sr_host) { return forward_host(m, lr_host, B, sr_host, 1); }
+
+int pv_predict_scenes_host(pv_model* m, const float* lr_patches_host, int nscenes, int pps, float* sr_scenes_host) {
+    if (!m || !lr_patches_host || !sr_scenes_host || nscenes <= 0 || pps <= 0) return set_error(PV_ERR_BAD_ARG, "predict_scenes: bad argument");
+    const int n = (int)std::lround(std::sqrt((double)pps));
+    if (n * n != pps) return set_error(PV_ERR_BAD_ARG, "predict_scenes: %d patches per scene is not a square (test.py:152)", pps);
+    PV_CUDA(cudaSetDevice(m->device));
+    const size_t nin = (size_t)m->S * m->S * m->T, PP = (size_t)m->P * m->cfg.scale, nout = PP * PP;
+    const int chunk = std::max(1, 256 / pps);          // scenes per launch
+    PV_TRY(stage_ensure(&m->stage_lr, &m->stage_lr_n, nin * pps * chunk));
+    PV_TRY(stage_ensure(&m->stage_sr, &m->stage_sr_n, nout * pps * chunk));
+    PV_TRY(stage_ensure(&m->stage_scene, &m->stage_scene_n, nout * pps * chunk));
+    for (int s = 0; s < nscenes; s += chunk) {
+        const int ns = std::min(chunk, nscenes - s);
+        PV_CUDA(cudaMemcpyAsync(m->stage_lr, lr_patches_host + nin * pps * s, nin * pps * ns * sizeof(float), cudaMemcpyHostToDevice, 0));
+        PV_TRY(model_forward(m, m->stage_lr, ns * pps, m->stage_sr, false, 1, 0));
+        PV_TRY(launch_stitch(m->stage_sr, ns, n, (int)PP, m->stage_scene, 0));
+        PV_CUDA(cudaMemcpyAsync(sr_scenes_host + nout * pps * s, m->stage_scene, nout * pps * ns * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    }
+    PV_CUDA(cudaStreamSynchronize(0));
+    return 0;
+}
+
+int pv_predict_from_scenes_host(pv_model* m, const float* lr_scenes_host, int nscenes, int H, int W, float* sr_scenes_host) {
+    if (!m || !lr_scenes_host || !sr_scenes_host || nscenes <= 0) return set_error(PV_ERR_BAD_ARG, "predict_from_scenes: bad argument");
+    if (H != W || H % m->P) return set_error(PV_ERR_BAD_ARG, "predict_from_scenes: scene %dx%d must be square and a multiple of patch_size", H, W);
+    PV_CUDA(cudaSetDevice(m->device));
+    const int n = H / m->P, pps = n * n;
+    const size_t nin = (size_t)m->S * m->S * m->T, PP = (size_t)m->P * m->cfg.scale, nout = PP * PP, nsc = (size_t)m->T * H * W;
+    const int chunk = std::max(1, 256 / pps);
+    float* scn = nullptr;
+    PV_CUDA(cudaMalloc(&scn, nsc * chunk * sizeof(float)));
+    int rc = 0;
+    do {
+        if ((rc = stage_ensure(&m->stage_lr, &m->stage_lr_n, nin * pps * chunk))) break;
+        if ((rc = stage_ensure(&m->stage_sr, &m->stage_sr_n, nout * pps * chunk))) break;
+        if ((rc = stage_ensure(&m->stage_scene, &m->stage_scene_n, nout * pps * chunk))) break;
+        for (int s = 0; s < nscenes && !rc; s += chunk) {
+            const int ns = std::min(chunk, nscenes - s);
+            if (cudaMemcpyAsync(scn, lr_scenes_host + nsc * s, nsc * ns * sizeof(float), cudaMemcpyHostToDevice, 0) != cudaSuccess) { rc = set_error(PV_ERR_CUDA, "H2D failed"); break; }
+            if ((rc = launch_scene_to_patches(scn, ns, m->T, H, W, m->P, m->cfg.max_shift, m->stage_lr, 0))) break;
+            if ((rc = model_forward(m, m->stage_lr, ns * pps, m->stage_sr, false, 1, 0))) break;
+            if ((rc = launch_stitch(m->stage_sr, ns, n, (int)PP, m->stage_scene, 0))) break;
+            if (cudaMemcpyAsync(sr_scenes_host + nout * pps * s, m->stage_scene, nout * pps * ns * sizeof(float), cudaMemcpyDeviceToHost, 0) != cudaSuccess) { rc = set_error(PV_ERR_CUDA, "D2H failed"); break; }
+        }
+    } while (0);
+    cudaStreamSynchronize(0);
+    cudaFree(scn);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------ losses
+int pv_shift_loss(int kind, const float* hr, const uint8_t* mask, const float* sr, int B, int H, int W, int border,
+                  float grad_scale, float* loss_ps, int32_t* best_shift, int32_t* clear_count, float* cpsnr_ps,
+                  float* mean_loss, float* dsr, float* stack_out, void* stream) {
+    return shift_loss_device(kind, hr, mask, sr, B, H, W, border, grad_scale, loss_ps, best_shift, clear_count, cpsnr_ps,
+                             mean_loss, dsr, stack_out, S_(stream));
+}
+
+int pv_shift_loss_host(int kind, const float* hr, const uint8_t* mask, const float* sr, int B, int H, int W, int border,
+                       float grad_scale, float* loss_ps, int32_t* best_shift, int32_t* clear_count, float* cpsnr_ps,
+                       float* mean_loss, float* dsr, float* stack_out) {
+    if (!hr || !mask || !sr || !loss_ps || !best_shift || !clear_count || B <= 0 || H <= 0 || W <= 0)
+        return set_error(PV_ERR_BAD_ARG, "pv_shift_loss_host: null buffer or bad shape");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_error(PV_ERR_NO_DEVICE, "no CUDA device: no CPU fallback"); }
+    const size_t n = (size_t)B * H * W;
+    float *d_hr = nullptr, *d_sr = nullptr, *d_f = nullptr;
+    uint8_t* d_m = nullptr;
+    int32_t* d_i = nullptr;
+    const size_t nf = (size_t)B * 2 + 1 + (dsr ? n : 0) + (stack_out ? (size_t)B * 49 * 4 : 0);
+    int rc = 0;
+    do {
+        if (cudaMalloc(&d_hr, n * 4) != cudaSuccess || cudaMalloc(&d_sr, n * 4) != cudaSuccess || cudaMalloc(&d_m, n) != cudaSuccess ||
+            cudaMalloc(&d_f, nf * 4) != cudaSuccess || cudaMalloc(&d_i, (size_t)B * 2 * 4) != cudaSuccess) { rc = set_error(PV_ERR_CUDA, "cudaMalloc failed"); break; }
+        cudaMemcpyAsync(d_hr, hr, n * 4, cudaMemcpyHostToDevice, 0);
+        cudaMemcpyAsync(d_sr, sr, n * 4, cudaMemcpyHostToDevice, 0);
+        cudaMemcpyAsync(d_m, mask, n, cudaMemcpyHostToDevice, 0);
+        float* d_loss = d_f; float* d_cp = d_f + B; float* d_mean = d_f + 2 * B;
+        float* d_dsr = dsr ? d_f + 2 * B + 1 : nullptr;
+        float* d_stack = stack_out ? d_f + 2 * B + 1 + (dsr ? n : 0) : nullptr;
+        if ((rc = shift_loss_device(kind, d_hr, d_m, d_sr, B, H, W, border, grad_scale, d_loss, d_i, d_i + B, d_cp, d_mean, d_dsr, d_stack, 0))) break;
+        cudaMemcpyAsync(loss_ps, d_loss, (size_t)B * 4, cudaMemcpyDeviceToHost, 0);
+        cudaMemcpyAsync(best_shift, d_i, (size_t)B * 4, cudaMemcpyDeviceToHost, 0);
+        cudaMemcpyAsync(clear_count, d_i + B, (size_t)B * 4, cudaMemcpyDeviceToHost, 0);
+        if (cpsnr_ps) cudaMemcpyAsync(cpsnr_ps, d_cp, (size_t)B * 4, cudaMemcpyDeviceToHost, 0);
+        if (mean_loss) cudaMemcpyAsync(mean_loss, d_mean, 4, cudaMemcpyDeviceToHost, 0);
+        if (dsr) cudaMemcpyAsync(dsr, d_dsr, n * 4, cudaMemcpyDeviceToHost, 0);
+        if (stack_out) cudaMemcpyAsync(stack_out, d_stack, (size_t)B * 49 * 16, cudaMemcpyDeviceToHost, 0);
+        if (cudaStreamSynchronize(0) != cudaSuccess) rc = set_error(PV_ERR_CUDA, "shift loss failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } while (0);
+    cudaFree(d_hr); cudaFree(d_sr); cudaFree(d_m); cudaFree(d_f); cudaFree(d_i);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------ trainer
+int pv_trainer_create(pv_model* m, int opt_kind, float learning_rate, int loss_kind, pv_trainer** out) {
+    if (!m || !out) return set_error(PV_ERR_BAD_ARG, "pv_trainer_create: null argument");
+    *out = nullptr;
+    if (opt_kind < PV_OPT_SGD || opt_kind > PV_OPT_NADAM) return set_error(PV_ERR_BAD_ARG, "unknown optimizer %d", opt_kind);
+    if (loss_kind != PV_LOSS_L1 && loss_kind != PV_LOSS_L2)
+        return set_error(PV_ERR_BAD_ARG, "loss kind %d is not built yet (l1 and l2 are)", loss_kind);
+    if (m->P * m->cfg.scale != 48)
+        return set_error(PV_ERR_BAD_CONFIG, "training needs scale*patch_size = 48 (fused loss backward); got %d", m->P * m->cfg.scale);
+    PV_CUDA(cudaSetDevice(m->device));
+    pv_trainer* t = new pv_trainer();
+    t->m = m; t->opt = opt_kind; t->lr = learning_rate; t->loss_kind = loss_kind;
+    if (cudaMalloc(&t->grads, m->nparams * 4) != cudaSuccess || cudaMalloc(&t->m1, m->nparams * 4) != cudaSuccess ||
+        cudaMalloc(&t->m2, m->nparams * 4) != cudaSuccess || cudaMalloc(&t->dweff, m->nweff * 4) != cudaSuccess ||
+        cudaMalloc(&t->dbias_s, m->nbias_s * 4) != cudaSuccess || cudaMalloc(&t->out2, 2 * 4) != cudaSuccess) {
+        pv_trainer_destroy(t);
+        return set_error(PV_ERR_CUDA, "cudaMalloc of the trainer arenas failed");
+    }
+    cudaMemset(t->grads, 0, m->nparams * 4);
+    cudaMemset(t->m1, 0, m->nparams * 4);
+    cudaMemset(t->m2, 0, m->nparams * 4);
+    *out = t;
+    return 0;
+}
+
+void pv_trainer_destroy(pv_trainer* t) {
+    if (!t) return;
+    cudaSetDevice(t->m->device);
+    cudaFree(t->grads); cudaFree(t->dweff); cudaFree(t->dbias_s); cudaFree(t->m1); cudaFree(t->m2);
+    cudaFree(t->sr); cudaFree(t->dsr); cudaFree(t->loss_ps); cudaFree(t->cpsnr_ps); cudaFree(t->best); cudaFree(t->cnt);
+    cudaFree(t->out2); cudaFree(t->s_lr); cudaFree(t->s_hr); cudaFree(t->s_mask);
+    delete t;
+}
+
+int pv_train_forward_backward(pv_trainer* t, const float* lr, const float* hr, const uint8_t* mask, int B, float grad_scale,
+                              float* out_dev, void* stream) {
+    if (!t) return set_error(PV_ERR_BAD_ARG, "null trainer");
+    return trainer_fwd_loss(t, lr, hr, mask, B, grad_scale, true, out_dev, S_(stream));
+}
+
+int pv_apply_gradients(pv_trainer* t, void* stream) {
+    if (!t) return set_error(PV_ERR_BAD_ARG, "null trainer");
+    PV_CUDA(cudaSetDevice(t->m->device));
+    return trainer_apply(t, S_(stream));
+}
+
+int pv_train_step(pv_trainer* t, const float* lr, const float* hr, const uint8_t* mask, int B, float* out_dev, void* stream) {
+    if (!t) return set_error(PV_ERR_BAD_ARG, "null trainer");
+    PV_TRY(trainer_fwd_loss(t, lr, hr, mask, B, 1.0f / (float)B, true, out_dev, S_(stream)));
+    return trainer_apply(t, S_(stream));
+}
+
+int pv_eval_step(pv_trainer* t, const float* lr, const float* hr, const uint8_t* mask, int B, float* out_dev, void* stream) {
+    if (!t) return set_error(PV_ERR_BAD_ARG, "null trainer");
+    return trainer_fwd_loss(t, lr, hr, mask, B, 0.f, false, out_dev, S_(stream));
+}
+
+static int step_host(pv_trainer* t, const float* lr, const float* hr, const uint8_t* mask, int B, float* out_host, bool train) {
+    if (!t || !lr || !hr || !mask || !out_host || B <= 0) return set_error(PV_ERR_BAD_ARG, "step_host: null buffer or B=%d", B);
+    pv_model* m = t->m;
+    PV_CUDA(cudaSetDevice(m->device));
+    const size_t nin = (size_t)m->S * m->S * m->T, nhr = (size_t)m->P * m->cfg.scale * m->P * m->cfg.scale;
+    if (B > t->s_cap) {
+        cudaFree(t->s_lr); cudaFree(t->s_hr); cudaFree(t->s_mask);
+        t->s_lr = t->s_hr = nullptr; t->s_mask = nullptr; t->s_cap = 0;
+        PV_CUDA(cudaMalloc(&t->s_lr, nin * B * 4));
+        PV_CUDA(cudaMalloc(&t->s_hr, nhr * B * 4));
+        PV_CUDA(cudaMalloc(&t->s_mask, nhr * B));
+        t->s_cap = B;
+    }
+    PV_CUDA(cudaMemcpyAsync(t->s_lr, lr, nin * B * 4, cudaMemcpyHostToDevice, 0));
+    PV_CUDA(cudaMemcpyAsync(t->s_hr, hr, nhr * B * 4, cudaMemcpyHostToDevice, 0));
+    PV_CUDA(cudaMemcpyAsync(t->s_mask, mask, nhr * B, cudaMemcpyHostToDevice, 0));
+    if (train) PV_TRY(pv_train_step(t, t->s_lr, t->s_hr, t->s_mask, B, t->out2, nullptr));
+    else PV_TRY(pv_eval_step(t, t->s_lr, t->s_hr, t->s_mask, B, t->out2, nullptr));
+    PV_CUDA(cudaMemcpyAsync(out_host, t->out2, 2 * 4, cudaMemcpyDeviceToHost, 0));
+    PV_CUDA(cudaStreamSynchronize(0));
+    return 0;
+}
+
+int pv_train_step_host(pv_trainer* t, const float* lr, const float* hr, const uint8_t* mask, int B, float* out_host) {
+    return step_host(t, lr, hr, mask, B, out_host, true);
+}
+int pv_eval_step_host(pv_trainer* t, const float* lr, const float* hr, const uint8_t* mask, int B, float* out_host) {
+    return step_host(t, lr, hr, mask, B, out_host, false);
+}
+
+int pv_trainer_grad_arena(pv_trainer* t, float** dev_ptr, int64_t* n) {
+    if (!t || !dev_ptr || !n) return set_error(PV_ERR_BAD_ARG, "grad_arena: null argument");
+    *dev_ptr = t->grads; *n = t->m->nparams;
+    return 0;
+}
+
+int pv_trainer_get_state(pv_trainer* t, int64_t* iter, double* momentum_cache, float* m_host, float* v_host, int64_t n) {
+    if (!t) return set_error(PV_ERR_BAD_ARG, "null trainer");
+    PV_CUDA(cudaSetDevice(t->m->device));
+    PV_CUDA(cudaDeviceSynchronize());
+    if (iter) *iter = t->iter;
+    if (momentum_cache) *momentum_cache = t->momentum_cache;
+    if (m_host || v_host) {
+        if (n != t->m->nparams) return set_error(PV_ERR_BAD_ARG, "get_state: expected %lld floats", t->m->nparams);
+        if (m_host) PV_CUDA(cudaMemcpy(m_host, t->m1, n * 4, cudaMemcpyDeviceToHost));
+        if (v_host) PV_CUDA(cudaMemcpy(v_host, t->m2, n * 4, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int pv_trainer_set_state(pv_trainer* t, int64_t iter, double momentum_cache, const float* m_host, const float* v_host, int64_t n) {
+    if (!t) return set_error(PV_ERR_BAD_ARG, "null trainer");
+    PV_CUDA(cudaSetDevice(t->m->device));
+    t->iter = iter; t->momentum_cache = momentum_cache;
+    if (m_host || v_host) {
+        if (n != t->m->nparams) return set_error(PV_ERR_BAD_ARG, "set_state: expected %lld floats", t->m->nparams);
+        if (m_host) PV_CUDA(cudaMemcpy(t->m1, m_host, n * 4, cudaMemcpyHostToDevice));
+        if (v_host) PV_CUDA(cudaMemcpy(t->m2, v_host, n * 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int pv_trainer_set_lr(pv_trainer* t, float learning_rate) {
+    if (!t) return set_error(PV_ERR_BAD_ARG, "null trainer");
+    t->lr = learning_rate;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+"""Predict path with the reference's surface: Enhancer(model, patchLR).enhance() (reference models/testClass.py:11-39)
+and the functions test.py really uses -- evaluate / resolve / resolveByBatch / reconstruct_from_patches
+(reference test.py:103-160).  Clip, round-half-even and the n x n stitch run on the device."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def resolve(model, lr_batch) -> np.ndarray:
+    """test.py:114-122: model -> clip_by_value(0, 2**16) -> round -> numpy."""
+    return model(lr_batch, resolve=True)
+
+
+def resolveByBatch(model, lr_batch, batch_size=16) -> np.ndarray:
+    """test.py:125-134 (patches are independent, so the batch split does not change the result)."""
+    out = [resolve(model, lr_batch[s:s + batch_size]) for s in range(0, lr_batch.shape[0], batch_size)]
+    return np.concatenate(out)
+
+
+def reconstruct_from_patches(images: np.ndarray) -> np.ndarray:
+    """test.py:149-160 host version (the device path is model.predict_scenes)."""
+    n = int(len(images) ** 0.5)
+    P = images.shape[1]
+    rec = np.zeros((n * P, n * P, 1))
+    k = 0
+    for i in range(n):
+        for j in range(n):
+            rec[i * P:(i + 1) * P, j * P:(j + 1) * P] = images[k]
+            k += 1
+    return rec
+
+
+def evaluate(model, X_test_patches):
+    """test.py:103-111: list of stitched [n*P, n*P, 1] predictions, one per scene; one batched device call."""
+    return list(model.predict_scenes(X_test_patches).astype(np.float64))
+
+
+class Enhancer:
+    def __init__(self, model, patchLR):
+        self.model = model
+        self.patchLR = patchLR
+
+    def enhance(self):
+        return evaluate(self.model, np.asarray(self.patchLR))
+
+    def enhancePatch(self, set_):
+        return resolve(self.model, set_)
+
+    def reconstruct(self, patches):
+        return reconstruct_from_patches(np.asarray(patches))

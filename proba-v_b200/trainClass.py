@@ -1,0 +1,311 @@
+"""Step loops with the reference's surface (reference models/trainClass.py:17-143):
+ModelTrainer(model, loss, metric, optimizer, ckptDir, logDir, multiGPU=True, evalStep=1000) with
+.fitTrainData / .trainStep / .testStep / .restore / .model.  One trainStep = pv_train_step (fwd, shift loss +
+cPSNR in one pass, fused loss backward, conv backward, weight-norm backward, fused optimizer); under
+torch.distributed the gradient arena is all-reduced once between backward and apply_gradients."""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import json
+import logging
+import os
+import time
+from typing import List
+
+import numpy as np
+
+from . import _buf, parallel
+from ._lib import PV_LOSS, PV_OPT, check, lib
+from .loss import LOSS_KIND_OF_METHOD
+
+logging.basicConfig(format="%(asctime)s - %(message)s", level=logging.INFO)
+logger = logging.getLogger("probav_b200")
+
+
+class Mean:
+    """tf.keras.metrics.Mean: running mean, count-weighted by update calls (trainClass.py:43-46)."""
+
+    def __init__(self, name=""):
+        self.name = name
+        self.reset_states()
+
+    def reset_states(self):
+        self.total, self.count = 0.0, 0
+
+    def __call__(self, value, weight=1):
+        self.total += float(value) * weight
+        self.count += weight
+
+    def result(self) -> float:
+        return self.total / self.count if self.count else 0.0
+
+
+def shuffled_index_stream(n: int, epochs: int, buffer_size: int, rng: np.random.Generator):
+    """tf.data shuffle(buffer).repeat(epochs): a streaming shuffle buffer refilled in dataset order, reshuffled each epoch."""
+    for _ in range(epochs):
+        buf = list(range(min(buffer_size, n)))
+        nxt = len(buf)
+        while buf:
+            k = int(rng.integers(len(buf)))
+            yield buf[k]
+            if nxt < n:
+                buf[k] = nxt
+                nxt += 1
+            else:
+                buf[k] = buf[-1]
+                buf.pop()
+
+
+def batched(stream, batch_size: int):
+    """.batch(B) without drop_remainder: the final batch may be partial (utils/utils.py:32-34)."""
+    cur = []
+    for i in stream:
+        cur.append(i)
+        if len(cur) == batch_size:
+            yield np.asarray(cur)
+            cur = []
+    if cur:
+        yield np.asarray(cur)
+
+
+class ModelTrainer:
+    def __init__(self, model, loss, metric, optimizer, ckptDir, logDir, multiGPU=True, evalStep=1000, seed=0):
+        os.makedirs(ckptDir, exist_ok=True)
+        os.makedirs(logDir, exist_ok=True)
+        kind = LOSS_KIND_OF_METHOD.get(getattr(loss, "__name__", ""), None)
+        if kind is None:
+            raise ValueError("loss must be one of Losses.shiftCompensated{L1Loss,L2Loss,L1EdgeLoss}")
+        if getattr(metric, "__name__", "") != "shiftCompensatedcPSNR":
+            raise ValueError("metric must be Losses.shiftCompensatedcPSNR (train.py:104)")
+        self._model = model
+        self.loss, self.metric, self.optimizer = loss, metric, optimizer
+        self.loss_kind = kind
+        self.ckptDir, self.logDir = ckptDir, logDir
+        self.trainLoss, self.trainPSNR = Mean("trainLoss"), Mean("trainPSNR")
+        self.testLoss, self.testPSNR = Mean("testLoss"), Mean("testPSNR")
+        self.evalStep = evalStep
+        self.multiGPU = multiGPU
+        self.strategy = None
+        self.step = 0               # ckpt.step
+        self.psnr = 1.0             # ckpt.psnr
+        self.max_to_keep = 5
+        self._rng = np.random.default_rng(seed)
+        h = C.c_void_p()
+        check(lib().pv_trainer_create(model._h, PV_OPT[optimizer.kind], optimizer.learning_rate, PV_LOSS[kind], C.byref(h)))
+        self._h = h
+        self._out = np.zeros(2, np.float32)
+        self._scalars = open(os.path.join(logDir, "scalars.jsonl"), "a") if parallel.world()[0] == 0 else None
+        self._grad_view = None
+        self.restore()
+
+    @property
+    def model(self):
+        return self._model
+
+    # ---- checkpoint (stands in for tf.train.Checkpoint + CheckpointManager(max_to_keep=5), trainClass.py:33-39)
+    def _latest(self):
+        files = sorted(glob.glob(os.path.join(self.ckptDir, "ckpt-*.npz")), key=lambda f: int(f.split("-")[-1][:-4]))
+        return files[-1] if files else None
+
+    def restore(self):
+        f = self._latest()
+        if f:
+            z = np.load(f)
+            self._model.set_flat(z["params"])
+            n = self._model.nparams
+            m1 = np.ascontiguousarray(z["opt_m"], np.float32)
+            m2 = np.ascontiguousarray(z["opt_v"], np.float32)
+            check(lib().pv_trainer_set_state(self._h, int(z["opt_iter"]), float(z["momentum_cache"]), _buf.ptr(m1), _buf.ptr(m2), n))
+            self.step, self.psnr = int(z["step"]), float(z["psnr"])
+            print(f"[ INFO ] Model restored from checkpoint at step {self.step}.")
+
+    def save(self):
+        if parallel.world()[0] != 0:
+            return None
+        n = self._model.nparams
+        it, mc = C.c_int64(), C.c_double()
+        m1, m2 = np.empty(n, np.float32), np.empty(n, np.float32)
+        check(lib().pv_trainer_get_state(self._h, C.byref(it), C.byref(mc), _buf.ptr(m1), _buf.ptr(m2), n))
+        files = sorted(glob.glob(os.path.join(self.ckptDir, "ckpt-*.npz")), key=lambda f: int(f.split("-")[-1][:-4]))
+        k = int(files[-1].split("-")[-1][:-4]) + 1 if files else 1
+        path = os.path.join(self.ckptDir, f"ckpt-{k}.npz")
+        np.savez(path, params=self._model.get_flat(), opt_m=m1, opt_v=m2, opt_iter=it.value, momentum_cache=mc.value,
+                 step=self.step, psnr=self.psnr, names=np.array([v.name for v in self._model.trainable_variables]))
+        for old in files[:max(0, len(files) + 1 - self.max_to_keep)]:
+            os.remove(old)
+        return path
+
+    # ---- steps
+    def _run(self, fn_host, fn_dev, patchLR, patchHR, maskHR):
+        B = int(patchLR.shape[0])
+        if _buf.is_cuda_tensor(patchLR):
+            import torch
+            dev = patchLR.device
+            x = _buf.dev_tensor(patchLR, torch.float32, dev)
+            y = _buf.dev_tensor(patchHR, torch.float32, dev)
+            m = maskHR.to(dev).contiguous().view(torch.uint8) if maskHR.dtype == torch.bool else _buf.dev_tensor(maskHR, torch.uint8, dev)
+            out = torch.empty(2, dtype=torch.float32, device=dev)
+            check(fn_dev(self._h, _buf.ptr(x), _buf.ptr(y), _buf.ptr(m), B, _buf.ptr(out), _buf.current_stream_ptr(dev)))
+            return out
+        x = _buf.host_array(patchLR, np.float32)
+        y = _buf.host_array(patchHR, np.float32)
+        m = _buf.host_array(maskHR, np.uint8)
+        check(fn_host(self._h, _buf.ptr(x), _buf.ptr(y), _buf.ptr(m), B, _buf.ptr(self._out)))
+        return self._out.copy()
+
+    def trainStep(self, patchLR, patchHR, maskHR, global_batch: int = None):
+        """trainClass.py:124-135.  Returns (loss, mean cPSNR) of this rank's shard and updates the running means."""
+        rank, ws = parallel.world()
+        if ws == 1:
+            out = self._run(lib().pv_train_step_host, lib().pv_train_step, patchLR, patchHR, maskHR)
+        else:
+            out = self._dp_step(patchLR, patchHR, maskHR, global_batch)
+        lossv, psnrv = float(out[0]), float(out[1])
+        if ws > 1:
+            lossv, psnrv = parallel.reduce_metrics(lossv, psnrv, int(patchLR.shape[0]),
+                                                   device=patchLR.device if _buf.is_cuda_tensor(patchLR) else None)
+        self.trainLoss(lossv)
+        self.trainPSNR(psnrv)
+        return lossv, psnrv
+
+    def _dp_step(self, patchLR, patchHR, maskHR, global_batch):
+        """fwd/bwd on the local shard -> ONE all-reduce(SUM) of the flat gradient arena -> identical update on every rank."""
+        import torch
+        if not _buf.is_cuda_tensor(patchLR):
+            dev = torch.device(f"cuda:{self._model.device}")
+            patchLR = torch.as_tensor(np.asarray(patchLR, np.float32)).to(dev)
+            patchHR = torch.as_tensor(np.asarray(patchHR, np.float32)).to(dev)
+            maskHR = torch.as_tensor(np.asarray(maskHR).astype(np.uint8)).to(dev)
+        dev = patchLR.device
+        B = int(patchLR.shape[0])
+        ws = parallel.world()[1]
+        gb = global_batch if global_batch else B * ws
+        x = _buf.dev_tensor(patchLR, torch.float32, dev)
+        y = _buf.dev_tensor(patchHR, torch.float32, dev)
+        m = maskHR.contiguous().view(torch.uint8) if maskHR.dtype == torch.bool else _buf.dev_tensor(maskHR, torch.uint8, dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        st = _buf.current_stream_ptr(dev)
+        check(lib().pv_train_forward_backward(self._h, _buf.ptr(x), _buf.ptr(y), _buf.ptr(m), B, parallel.grad_scale(gb), _buf.ptr(out), st))
+        parallel.allreduce_sum_(self.grad_view())
+        check(lib().pv_apply_gradients(self._h, st))
+        return out
+
+    def testStep(self, patchLR, patchHR, maskHR):
+        """trainClass.py:137-143."""
+        out = self._run(lib().pv_eval_step_host, lib().pv_eval_step, patchLR, patchHR, maskHR)
+        lossv, psnrv = float(out[0]), float(out[1])
+        self.testLoss(lossv)
+        self.testPSNR(psnrv)
+        return lossv, psnrv
+
+    # ---- introspection used by the parity tests and the DP path
+    def forward_backward(self, patchLR, patchHR, maskHR, grad_scale: float = None):
+        """tape.gradient only (no optimizer step): returns (loss, mean cPSNR); gradients via get_grads()."""
+        import torch
+        dev = torch.device(f"cuda:{self._model.device}")
+        B = int(patchLR.shape[0])
+        x = _buf.dev_tensor(patchLR, torch.float32, dev)
+        y = _buf.dev_tensor(patchHR, torch.float32, dev)
+        m = _buf.dev_tensor(np.asarray(maskHR).astype(np.uint8) if not isinstance(maskHR, torch.Tensor) else maskHR.to(torch.uint8), torch.uint8, dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        gs = (1.0 / B) if grad_scale is None else float(grad_scale)
+        check(lib().pv_train_forward_backward(self._h, _buf.ptr(x), _buf.ptr(y), _buf.ptr(m), B, gs, _buf.ptr(out),
+                                              _buf.current_stream_ptr(dev)))
+        o = out.cpu().numpy()
+        return float(o[0]), float(o[1])
+
+    def grad_view(self):
+        """torch view (no copy) of the flat gradient arena (same layout as the parameter arena)."""
+        if self._grad_view is None:
+            p, n = C.c_void_p(), C.c_int64()
+            check(lib().pv_trainer_grad_arena(self._h, C.byref(p), C.byref(n)))
+            self._grad_view = _buf.view_device_floats(p.value, n.value, f"cuda:{self._model.device}")
+        return self._grad_view
+
+    def get_grads(self) -> dict:
+        flat = self.grad_view().cpu().numpy()
+        return {v.name: flat[v.offset:v.offset + v.numel].reshape(v.shape).copy() for v in self._model.trainable_variables}
+
+    def apply_gradients(self):
+        import torch
+        check(lib().pv_apply_gradients(self._h, _buf.current_stream_ptr(torch.device(f"cuda:{self._model.device}"))))
+
+    def _scalar(self, tag, value, step):
+        if self._scalars:
+            self._scalars.write(json.dumps({"tag": tag, "value": float(value), "step": int(step), "wall_time": time.time()}) + "\n")
+
+    # ---- fit loop
+    def fitTrainData(self, X, y, globalBatchSize: int, epochs: int, valData: List, bufferSize: int = 256,
+                     valSteps: int = 64, saveBestOnly: bool = True, initEpoch: int = 0, maxSteps: int = None,
+                     logEvery: int = 1):
+        """trainClass.py:61-122.  X [N,S,S,T,1]; y = [HR [N,..,1], mask]; valData = [X_val, y_val, mask_val].
+        Under torch.distributed every rank walks the same index stream and takes its shard of each global batch."""
+        rank, ws = parallel.world()
+        yHR, yMask = y
+        n = len(X)
+        totalSteps = int(n / globalBatchSize)
+        globalStep = self.step
+        step = globalStep % totalSteps if totalSteps else 0
+        epoch = initEpoch
+        stream = batched(shuffled_index_stream(n, epochs, bufferSize, self._rng), globalBatchSize)
+        logger.info("[ INFO ] Begin training...")
+        done = 0
+        for idx in stream:
+            if totalSteps - step == 0:
+                epoch += 1
+                step = self.step % totalSteps
+                logger.info(f"[ ***************  NEW EPOCH  *************** ] Epoch number {epoch}")
+                for mtr in (self.trainLoss, self.trainPSNR, self.testLoss, self.testPSNR):
+                    mtr.reset_states()
+            step += 1
+            globalStep += 1
+            lo, hi = parallel.shard_bounds(len(idx), rank, ws)
+            sel = np.sort(idx[lo:hi]) if hi > lo else idx[:0]
+            self.trainStep(X[sel], yHR[sel], yMask[sel], global_batch=len(idx))
+            self.step += 1
+            if logEvery and (step % logEvery == 0) and rank == 0:
+                logger.info(f"[ EPOCH {epoch}/{epochs} ] - [ STEP {step}/{totalSteps} ] Loss: {self.trainLoss.result():.6f}, "
+                            f"cPSNR: {self.trainPSNR.result():.3f}")
+            self._scalar("Train PSNR", self.trainPSNR.result(), globalStep)
+            self._scalar("Train loss", self.trainLoss.result(), globalStep)
+            if step != 0 and (step % self.evalStep) == 0:
+                self.testLoss.reset_states()
+                self.testPSNR.reset_states()
+                Xv, yv, mv = valData
+                vstream = batched(shuffled_index_stream(len(Xv), 1, bufferSize, self._rng), globalBatchSize)
+                for k, vidx in enumerate(vstream):
+                    if k >= valSteps:
+                        break
+                    vsel = np.sort(vidx)
+                    self.testStep(Xv[vsel], yv[vsel], mv[vsel])
+                self._scalar("Test loss", self.testLoss.result(), globalStep)
+                self._scalar("Test PSNR", self.testPSNR.result(), globalStep)
+                if rank == 0:
+                    logger.info(f"[ *************** VAL INFO *************** ] Validation Loss: {self.testLoss.result():.6f}, "
+                                f"Validation PSNR: {self.testPSNR.result():.3f}")
+                if self._scalars:
+                    self._scalars.flush()
+                if not (saveBestOnly and self.testPSNR.result() <= self.psnr):
+                    logger.info("[ SAVE ] Saving checkpoint...")
+                    self.psnr = self.testPSNR.result()
+                    self.save()
+            done += 1
+            if maxSteps and done >= maxSteps:
+                break
+        if self._scalars:
+            self._scalars.flush()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pv_trainer_destroy(self._h)
+            self._h = None
+        if getattr(self, "_scalars", None):
+            self._scalars.close()
+            self._scalars = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
