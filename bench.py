@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the PROBA-V 3D-WDSR hot path on B200 (BASELINE.json: train patches/s,
+fwd+bwd+shift-L1(+Nadam, +cPSNR metric) on cfg/p16t9c85r12, batch 128 per GPU, synthetic PROBA-V-shaped data).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = ModelTrainer.trainStep (reference models/trainClass.py:124-135) on one batch.  Prints ONE JSON line
+(rank 0).  `value` = whole-job patches/s with the batch resident in HBM; `e2e` = the same through the public API
+with pinned HOST buffers (H2D of the batch + D2H of loss/cPSNR inside the timed region).  `roofline` describes the
+dominant kernel class, timed live with CUDA events through pv_timing_*; `cpu_baseline` is the oracle (a PyTorch-CPU
+restatement of the TF reference, which cannot be installed here) timed on this box's host cores.
+Weak scaling for N > 1: per-rank batch fixed, ONE NCCL all-reduce of the flat gradient arena per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "train patches/s (fwd+bwd+shift-L1+Nadam+cPSNR), cfg/p16t9c85r12"
+UNIT = "patches/s"
+TRAIN_GFLOP_PER_PATCH = 12.443      # 3 x 2 073 878 964 MAC x 2
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        z = json.load(open(p))
+        return dict(hbm=z["hbm_gbs"], tensor_burst=z["bf16_tflops"], tensor_sustained=z.get("bf16_tflops_sustained", z["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_steps(cfg, batch, steps, warmup, seed=0):
+    """The oracle's train step (fwd + shift-L1 + autograd + Nadam + cPSNR) in fp32 on all host threads."""
+    from oracle.losses import OracleLosses
+    from oracle.optim import OracleNadam
+    from oracle.step import train_step
+    from probav_b200 import synth
+    from tests.helpers import oracle_and_params
+    torch.set_num_threads(os.cpu_count() or 1)
+    ocfg = dict(scale=cfg["scale"], numFilters=cfg["num_filters"], kernelSize=(cfg["kernel_size"],) * 3,
+                numResBlocks=cfg["num_res_blocks"], expRate=cfg["exp_rate"], decayRate=cfg["decay_rate"],
+                numImgLR=cfg["num_low_res_imgs"], patchSizeLR=cfg["patch_size"], isGrayScale=cfg["is_grayscale"])
+    om, p = oracle_and_params(ocfg, seed=seed, dtype=torch.float32)
+    ol = OracleLosses((48, 48, 1), dtype=torch.float32)
+    opt = OracleNadam(cfg["learning_rate"])
+    lr, hr, mask = synth.make_batch(batch, T=cfg["num_low_res_imgs"], seed=seed + 1, hr_zero_under_mask=True)
+    lr, hr, mask = torch.from_numpy(lr), torch.from_numpy(hr), torch.from_numpy(mask)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        p, loss, cps, _ = train_step(om, ol, opt, p, lr, hr, mask)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return batch * len(times) / sum(times), sum(times) / len(times), torch.get_num_threads()
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    b = args.ref_batch
+    v, sec, cores = cpu_reference_steps(cfg, b, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg/p16t9c85r12 train step (fwd+shift-L1+bwd+Nadam+cPSNR metric)", "batch_per_step": b,
+                       "note": "TensorFlow/TFA are not installable here (no wheels, no network): the reference arm is the "
+                               "oracle, a PyTorch-CPU restatement of models/modelsTF.py + loss.py + trainClass.py"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} steps of batch {b} (of the 128-patch step), torch CPU fp32"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args, cfg):
+    import torch.distributed as dist
+
+    import probav_b200 as pb
+    from probav_b200 import _lib, parallel, synth
+    rank, ws, local = parallel.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    lib = _lib.lib()
+    B = args.batch
+    model = pb.build_from_config(cfg, band="NIR", device=local, seed=0)
+    L = pb.Losses((cfg["scale"] * cfg["patch_size"],) * 2 + (1,))
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="pv_bench_")
+    trainer = pb.ModelTrainer(model, pb.loss_from_config(L, cfg["loss"]), L.shiftCompensatedcPSNR,
+                              pb.optimizers.from_config(cfg["optimizer"], cfg["learning_rate"]), tmp + "/ckpt", tmp + "/log")
+    if ws > 1:
+        parallel.broadcast_(model.param_arena(), 0)
+    lr, hr, mask = synth.make_batch(B, T=cfg["num_low_res_imgs"], seed=100 + rank, hr_zero_under_mask=True)
+    # pinned host copies (e2e) and device-resident copies (value)
+    h_lr, h_hr = torch.from_numpy(lr).pin_memory(), torch.from_numpy(hr).pin_memory()
+    h_mk = torch.from_numpy(mask.astype(np.uint8)).pin_memory()
+    d_lr, d_hr, d_mk = h_lr.to(dev), h_hr.to(dev), h_mk.to(dev)
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if ws == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        trainer.trainStep(d_lr, d_hr, d_mk, sync=False)
+    barrier()
+    n0 = lib.pv_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            trainer.trainStep(d_lr, d_hr, d_mk, sync=False)
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = int(lib.pv_launch_count() - n0)
+    value = ws * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with pinned host buffers
+    for _ in range(max(1, args.warmup // 2)):
+        trainer.trainStep(h_lr, h_hr, h_mk)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lossv, psnrv = trainer.trainStep(h_lr, h_hr, h_mk)          # returns host floats: D2H + sync every step
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = ws * B * args.steps / e2e_s
+    h2d = ws * (h_lr.numel() * 4 + h_hr.numel() * 4 + h_mk.numel())
+    d2h = ws * 8
+
+    # ---- per-kernel-class timing (CUDA events on the launch stream) for the roofline
+    lib.pv_timing_reset()
+    lib.pv_timing_enable(1)
+    for _ in range(2):
+        trainer.trainStep(d_lr, d_hr, d_mk, sync=False)
+    torch.cuda.synchronize()
+    lib.pv_timing_enable(0)
+    rep = _lib.timing_report()
+    lib.pv_timing_reset()
+    barrier()
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    tot_ms = sum(v["ms"] for v in rep.values()) or 1.0
+    kernels = {k: {"launches_per_step": v["launches"] // 2, "ms_per_step": v["ms"] / 2, "share": v["ms"] / tot_ms,
+                   "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None,
+                   "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] > 0 else None}
+               for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
+    top = max(rep.items(), key=lambda kv: kv[1]["ms"])
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tf):
+        traffic = json.load(open(tf)).get(top[0])
+    ach = top[1]["flops"] / (top[1]["ms"] * 1e-3) / 1e12
+    roofline = {"kernel": top[0], "bound": "tensor", "achieved": ach, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tensor_sustained"], "traffic": traffic, "peak_source": peaks["source"] + ", bf16 sustained",
+                "avg_launch_ms": top[1]["ms"] / top[1]["launches"], "share_of_step": top[1]["ms"] / tot_ms}
+    sl = rep.get("shift_loss_patch")
+    roof_loss = None
+    if sl and sl["ms"] > 0:
+        a = sl["bytes"] / (sl["ms"] * 1e-3) / 1e9
+        roof_loss = {"kernel": "shift_loss_patch", "bound": "hbm", "achieved": a, "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": a / peaks["hbm"], "traffic": None,
+                     "note": f"batch {B}: {sl['bytes'] / sl['launches'] / 1e6:.2f} MB per launch is latency-bound; see bench_loss in DESIGN.md"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if model.cfg.precision == 0 else "bf16", "data": "synthetic",
+            "config": {"workload": "cfg/p16t9c85r12 train step (fwd+shift-L1+bwd+Nadam+cPSNR metric), BASELINE configs[1]",
+                       "batch_per_gpu": B, "global_batch": B * ws, "parallelism": f"dp{ws}",
+                       "l2_policy": "per-step working set (activations ~8 GB) >> 126 MB L2; no explicit flush",
+                       "algorithmic_tflops": value * TRAIN_GFLOP_PER_PATCH / 1e3},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": roofline, "roofline_shift_loss": roof_loss, "kernels": kernels,
+            "last_loss": lossv, "last_cpsnr": psnrv}
+    if ws == 1 and not args.no_cpu_baseline:
+        v, sec, cores = cpu_reference_steps(cfg, args.ref_batch, 2, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"2 steps of batch {args.ref_batch} (of the 128-patch step) after 1 warm-up, torch CPU fp32 oracle"}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: cfg batch_size = 128)")
+    ap.add_argument("--ref-batch", type=int, default=16, help="CPU arm: patches per step (bounded sample)")
+    ap.add_argument("--cfg", default=os.path.join(ROOT, "cfg", "p16t9c85r12.cfg"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    from probav_b200 import parseConfig
+    cfg = parseConfig(args.cfg)
+    if args.batch is None:
+        args.batch = cfg["batch_size"]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_b200(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

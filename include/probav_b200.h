@@ -155,6 +155,13 @@ int  pv_trainer_set_state(pv_trainer* t, int64_t iter, double momentum_cache, co
 int  pv_trainer_set_lr(pv_trainer* t, float learning_rate);
 /* number of kernels of this library launched so far (bench.py's gpu_launches) */
 int64_t pv_launch_count(void);
+/* Per-kernel-class device timing (bench.py's roofline; no reference counterpart).  While enabled every kernel
+ * launch is bracketed by CUDA events on its stream.  pv_timing_report synchronises the device and writes one line
+ * per kernel class: "name launches total_ms algorithmic_flops algorithmic_bytes\n"; returns the number of bytes
+ * written (or needed, if larger than cap). */
+int  pv_timing_enable(int on);
+int  pv_timing_reset(void);
+int  pv_timing_report(char* buf, int cap);
 
 #ifdef __cplusplus
 }

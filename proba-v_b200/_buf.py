@@ -23,9 +23,11 @@ def host_array(x, dtype) -> np.ndarray:
 
 
 def dev_tensor(x, dtype, device):
-    """contiguous torch CUDA tensor of `dtype` on `device` (copies only when needed)."""
+    """contiguous torch CUDA tensor of `dtype` on `device` (copies only when needed; pinned host tensors copy async)."""
     if not isinstance(x, torch.Tensor):
         x = torch.as_tensor(np.asarray(x))
+    if x.dtype == torch.bool:
+        x = x.contiguous().view(torch.uint8)          # bool and uint8 share the byte layout (True = 1)
     return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()
 
 

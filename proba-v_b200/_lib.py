@@ -63,6 +63,9 @@ _SIGS = {
     "pv_trainer_get_state": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_double), _P, _P, C.c_int64]),
     "pv_trainer_set_state": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P, C.c_int64]),
     "pv_trainer_set_lr": (C.c_int, [_P, C.c_float]),
+    "pv_timing_enable": (C.c_int, [C.c_int]),
+    "pv_timing_reset": (C.c_int, []),
+    "pv_timing_report": (C.c_int, [C.c_char_p, C.c_int]),
 }
 
 _lib = None
@@ -92,3 +95,15 @@ def check(status: int):
         if status == -1:
             raise ValueError(msg)          # bad cfg: what Keras would raise while building the graph
         raise PvError(f"[pv_status {status}] {msg}")
+
+
+def timing_report() -> dict:
+    """{kernel class: dict(launches, ms, flops, bytes)} accumulated since pv_timing_reset (device-synchronising)."""
+    n = lib().pv_timing_report(None, 0)
+    buf = C.create_string_buffer(max(n, 1))
+    lib().pv_timing_report(buf, n)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms, fl, by = line.split()
+        out[name] = dict(launches=int(cnt), ms=float(ms), flops=float(fl), bytes=float(by))
+    return out

@@ -42,4 +42,14 @@ int64_t launch_count();
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Per-kernel-class device timing behind pv_timing_* (bench.py's roofline): when enabled, a launch is bracketed by
+// CUDA events on its own stream and tagged with its ALGORITHMIC flops / bytes (unpadded shapes).
+struct KernelTimer {
+    KernelTimer(const char* name, cudaStream_t st, double flops = 0.0, double bytes = 0.0);
+    ~KernelTimer();
+    int slot;
+    cudaStream_t st;
+};
+#define PV_TIMED(name, st, ...) pv::KernelTimer _pv_kt(name, st, ##__VA_ARGS__)
+
 }  // namespace pv

@@ -288,6 +288,9 @@ int launch_conv(const ConvP& p, cudaStream_t st) {
     const long long M = (long long)p.B * p.Ho * p.Wo * p.To;
     if (M <= 0) return set_error(PV_ERR_BAD_ARG, "conv: empty output");
     const bool vec = (p.cin % 16 == 0) && (p.cout % 32 == 0);
+    PV_TIMED(p.tag ? p.tag : (vec ? "conv_vec" : "conv_direct"), st,
+             2.0 * (double)M * p.kh * p.kw * p.kt * p.cin_r * p.cout_r,
+             4.0 * ((double)p.B * p.Hi * p.Wi * p.Ti * p.cin_r + (double)M * p.cout_r));
     if (vec) {
         if (p.cout % 64 == 0) {
             dim3 grid(cdiv(M, 128), p.cout / 64);
@@ -307,6 +310,9 @@ int launch_wgrad(const WgradP& p, cudaStream_t st) {
     const long long M = (long long)p.B * p.Ho * p.Wo * p.To;
     const int Ktot = p.kh * p.kw * p.kt * p.cin;
     const bool vec = (p.cin % 16 == 0) && (p.cout % 32 == 0);
+    PV_TIMED(p.tag ? p.tag : (vec ? "wgrad_vec" : "wgrad_direct"), st,
+             2.0 * (double)M * Ktot / p.cin * p.cin_r * p.cout_r,
+             4.0 * ((double)p.B * p.Hi * p.Wi * p.Ti * p.cin_r + (double)M * p.cout_r));
     if (vec) {
         const int BN = (p.cout % 64 == 0) ? 64 : 32;
         const int kt = cdiv(Ktot, 64), nt = p.cout / BN;

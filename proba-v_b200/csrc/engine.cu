@@ -39,6 +39,25 @@ static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches += n; }
 int64_t launch_count() { return g_launches.load(); }
 
+// ------------------------------------------------------------------------------------------ kernel timing
+namespace {
+struct TimedLaunch { const char* name; cudaEvent_t a, b; double flops, bytes; };
+std::vector<TimedLaunch> g_timed;
+bool g_timing = false;
+}  // namespace
+
+KernelTimer::KernelTimer(const char* name, cudaStream_t s, double flops, double bytes) : slot(-1), st(s) {
+    if (!g_timing) return;
+    TimedLaunch t{name, nullptr, nullptr, flops, bytes};
+    if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return;
+    cudaEventRecord(t.a, st);
+    slot = (int)g_timed.size();
+    g_timed.push_back(t);
+}
+KernelTimer::~KernelTimer() {
+    if (slot >= 0) cudaEventRecord(g_timed[slot].b, st);
+}
+
 static inline int storage_channels(int c) { return c > 16 ? ((c + 31) / 32) * 32 : c; }
 
 struct Layer {
@@ -270,6 +289,7 @@ static ConvP conv_desc(const Layer& L, const float* w, const float* bias, int B)
     p.B = B; p.Hi = L.Hi; p.Wi = L.Wi; p.Ti = L.Ti; p.Ho = L.Ho; p.Wo = L.Wo; p.To = L.To;
     p.cin = L.cin_s; p.cout = L.cout_s; p.kh = L.k[0]; p.kw = L.k[1]; p.kt = L.k[2];
     p.ph = L.pad[0]; p.pw = L.pad[1]; p.pt = L.pad[2]; p.relu = L.relu;
+    p.cin_r = L.cin; p.cout_r = L.cout; p.tag = nullptr;
     return p;
 }
 
@@ -289,6 +309,7 @@ static int conv_dgrad(pv_model* m, int li, const float* gout, const float* relu_
     p.cin = L.cout_s; p.cout = L.cin_s; p.kh = L.k[0]; p.kw = L.k[1]; p.kt = L.k[2];
     p.ph = L.k[0] - 1 - L.pad[0]; p.pw = L.k[1] - 1 - L.pad[1]; p.pt = L.k[2] - 1 - L.pad[2];
     p.relu = 0;
+    p.cin_r = L.cout; p.cout_r = L.cin; p.tag = nullptr;
     return launch_conv(p, st);
 }
 
@@ -299,6 +320,7 @@ static int conv_wgrad(pv_trainer* t, int li, const float* in, const float* gout,
     p.B = B; p.Hi = L.Hi; p.Wi = L.Wi; p.Ti = L.Ti; p.Ho = L.Ho; p.Wo = L.Wo; p.To = L.To;
     p.cin = L.cin_s; p.cout = L.cout_s; p.kh = L.k[0]; p.kw = L.k[1]; p.kt = L.k[2];
     p.ph = L.pad[0]; p.pw = L.pad[1]; p.pt = L.pad[2];
+    p.cin_r = L.cin; p.cout_r = L.cout; p.tag = nullptr;
     return launch_wgrad(p, st);
 }
 
@@ -485,6 +507,34 @@ extern "C" {
 int pv_abi_version(void) { return PV_ABI_VERSION; }
 const char* pv_last_error(void) { return pv::last_error().c_str(); }
 int64_t pv_launch_count(void) { return pv::launch_count(); }
+
+int pv_timing_enable(int on) { pv::g_timing = on != 0; return 0; }
+
+int pv_timing_reset(void) {
+    for (auto& t : pv::g_timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    pv::g_timed.clear();
+    return 0;
+}
+
+int pv_timing_report(char* buf, int cap) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return set_error(PV_ERR_CUDA, "timing_report: device sync failed");
+    struct Acc { long long n = 0; double ms = 0, flops = 0, bytes = 0; };
+    std::map<std::string, Acc> acc;
+    for (auto& t : pv::g_timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) != cudaSuccess) { cudaGetLastError(); continue; }
+        Acc& a = acc[t.name];
+        a.n++; a.ms += ms; a.flops += t.flops; a.bytes += t.bytes;
+    }
+    std::string out;
+    char line[256];
+    for (auto& kv : acc) {
+        snprintf(line, sizeof line, "%s %lld %.6f %.6e %.6e\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops, kv.second.bytes);
+        out += line;
+    }
+    if (buf && cap > 0) { std::strncpy(buf, out.c_str(), cap - 1); buf[cap - 1] = 0; }
+    return (int)out.size() + 1;
+}
 
 int pv_device_count(void) {
     int n = 0;

@@ -253,6 +253,7 @@ __global__ void stitch_kernel(const float* __restrict__ sr, long long ntot, int 
 }  // namespace
 
 int launch_prep(const float* lr, int B, int HW, int T, float mean, float stdv, float* xn, float* mn, cudaStream_t st) {
+    PV_TIMED("prep", st);
     const long long nvox = (long long)B * HW;
     prep_kernel<<<cdiv(nvox, 256), 256, 0, st>>>(lr, nvox, T, mean, 1.0f / stdv, xn, mn);
     PV_LAUNCH_CHECK();
@@ -260,6 +261,7 @@ int launch_prep(const float* lr, int B, int HW, int T, float mean, float stdv, f
 }
 
 int launch_reflect_pad(const float* in, float* out, int B, int H, int W, int T, int C, int ph, int pw, int pt, cudaStream_t st) {
+    PV_TIMED("reflect_pad", st);
     if (C % 4) return set_error(PV_ERR_BAD_ARG, "reflect_pad: C %% 4 != 0");
     const long long n = (long long)B * (H + 2 * ph) * (W + 2 * pw) * (T + 2 * pt) * (C / 4);
     reflect_pad_kernel<<<cdiv(n, 256), 256, 0, st>>>(in, out, B, H, W, T, C / 4, ph, pw, pt);
@@ -268,6 +270,7 @@ int launch_reflect_pad(const float* in, float* out, int B, int H, int W, int T, 
 }
 
 int launch_reflect_pad_bwd(const float* gout, float* gin, int B, int H, int W, int T, int C, int ph, int pw, int pt, cudaStream_t st) {
+    PV_TIMED("reflect_pad_bwd", st);
     if (C % 4) return set_error(PV_ERR_BAD_ARG, "reflect_pad_bwd: C %% 4 != 0");
     const long long n = (long long)B * H * W * T * (C / 4);
     reflect_pad_bwd_kernel<<<cdiv(n, 256), 256, 0, st>>>(gout, gin, B, H, W, T, C / 4, ph, pw, pt);
@@ -277,6 +280,7 @@ int launch_reflect_pad_bwd(const float* gout, float* gin, int B, int H, int W, i
 
 int launch_tail(const float* up, const float* resid, int B, int P, int scale, float mean, float stdv, int clip_round,
                 float* sr, cudaStream_t st) {
+    PV_TIMED("tail", st);
     const long long n = (long long)B * P * scale * P * scale;
     tail_kernel<<<cdiv(n, 256), 256, 0, st>>>(up, resid, n, P, scale, mean, stdv, clip_round, sr);
     PV_LAUNCH_CHECK();
@@ -284,6 +288,7 @@ int launch_tail(const float* up, const float* resid, int B, int P, int scale, fl
 }
 
 int launch_tail_bwd(const float* dsr, int B, int P, int scale, float stdv, float* dtail, cudaStream_t st) {
+    PV_TIMED("tail_bwd", st);
     const long long n = (long long)B * P * P * scale * scale;
     tail_bwd_kernel<<<cdiv(n, 256), 256, 0, st>>>(dsr, n, P, scale, stdv, dtail);
     PV_LAUNCH_CHECK();
@@ -292,6 +297,7 @@ int launch_tail_bwd(const float* dsr, int B, int P, int scale, float stdv, float
 
 int launch_wn_prep(const WnLayer* tab, int nlayers, int nblocks, const float* params, float* weff, float* weffT,
                    float* bias_s, float* scale, cudaStream_t st) {
+    PV_TIMED("wn_prep", st);
     wn_prep_kernel<<<nblocks, 128, 0, st>>>(tab, nlayers, params, weff, weffT, bias_s, scale);
     PV_LAUNCH_CHECK();
     return 0;
@@ -299,36 +305,42 @@ int launch_wn_prep(const WnLayer* tab, int nlayers, int nblocks, const float* pa
 
 int launch_wn_bwd(const WnLayer* tab, int nlayers, int nblocks, const float* params, const float* scale,
                   const float* dweff, const float* dbias_s, float* grads, cudaStream_t st) {
+    PV_TIMED("wn_bwd", st);
     wn_bwd_kernel<<<nblocks, 128, 0, st>>>(tab, nlayers, params, scale, dweff, dbias_s, grads);
     PV_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_g_from_v(const WnLayer* tab, int nlayers, int nblocks, float* params, cudaStream_t st) {
+    PV_TIMED("g_from_v", st);
     g_from_v_kernel<<<nblocks, 128, 0, st>>>(tab, nlayers, params);
     PV_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_nadam(float* p, const float* g, float* m, float* v, long long n, NadamScalars s, cudaStream_t st) {
+    PV_TIMED("nadam", st);
     nadam_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, g, m, v, n, s);
     PV_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2, float eps, cudaStream_t st) {
+    PV_TIMED("adam", st);
     adam_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps);
     PV_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_sgd(float* p, const float* g, long long n, float lr, cudaStream_t st) {
+    PV_TIMED("sgd", st);
     sgd_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, g, n, lr);
     PV_LAUNCH_CHECK();
     return 0;
 }
 
 int launch_scene_to_patches(const float* scenes, int ns, int T, int H, int W, int patch, int max_shift, float* patches, cudaStream_t st) {
+    PV_TIMED("scene_to_patches", st);
     const int n = H / patch, S = patch + max_shift;
     const long long ntot = (long long)ns * n * n * S * S * T;
     scene_to_patches_kernel<<<cdiv(ntot, 256), 256, 0, st>>>(scenes, ntot, T, H, W, patch, max_shift / 2, S, n, patches);
@@ -337,6 +349,7 @@ int launch_scene_to_patches(const float* scenes, int ns, int T, int H, int W, in
 }
 
 int launch_stitch(const float* sr, int ns, int n, int P, float* scenes, cudaStream_t st) {
+    PV_TIMED("stitch", st);
     const long long ntot = (long long)ns * n * P * n * P;
     stitch_kernel<<<cdiv(ntot, 256), 256, 0, st>>>(sr, ntot, n, P, scenes);
     PV_LAUNCH_CHECK();

@@ -18,6 +18,8 @@ struct ConvP {
     int B, Hi, Wi, Ti, Ho, Wo, To;
     int cin, cout, kh, kw, kt, ph, pw, pt;   // zero padding ph/pw/pt on each side
     int relu;
+    int cin_r, cout_r;      // un-padded channel counts (algorithmic flop accounting only)
+    const char* tag;        // kernel-class label for pv_timing_report
 };
 
 // Weight gradient of the same convolution: dw[k][n] += sum_m im2col(x)[m][k] * dy[m][n]; db[n] += sum_m dy[m][n].
@@ -30,6 +32,8 @@ struct WgradP {
     float* db;              // [cout]
     int B, Hi, Wi, Ti, Ho, Wo, To;
     int cin, cout, kh, kw, kt, ph, pw, pt;
+    int cin_r, cout_r;
+    const char* tag;
 };
 
 int launch_conv(const ConvP& p, cudaStream_t st);

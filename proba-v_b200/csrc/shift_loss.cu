@@ -432,6 +432,7 @@ __global__ void mean_kernel(const float* __restrict__ v, int n, float* __restric
 }  // namespace sl
 
 int launch_mean(const float* v, int n, float* out, cudaStream_t st) {
+    PV_TIMED("mean", st);
     sl::mean_kernel<<<1, 256, 0, st>>>(v, n, out);
     PV_LAUNCH_CHECK();
     return 0;
@@ -450,6 +451,9 @@ int shift_loss_device(int kind, const float* hr, const uint8_t* mask, const floa
         return set_error(PV_ERR_BAD_ARG, "pv_shift_loss: loss kind %d not implemented by this kernel", kind);
     if (B <= 0 || H <= 2 * border || W <= 2 * border)
         return set_error(PV_ERR_BAD_ARG, "pv_shift_loss: bad shape B=%d H=%d W=%d", B, H, W);
+    // algorithmic bytes per sample: HR f32 + SR f32 + bool mask read, dSR f32 written when fused
+    PV_TIMED(H == WT && W == WT ? "shift_loss_patch" : "shift_loss_tiled", st, 0.0,
+             (double)B * H * W * (9.0 + (dsr ? 4.0 : 0.0)));
     if (H == WT && W == WT) {
         shift_loss_patch_kernel<<<B, NT, 0, st>>>(kind, hr, mask, sr, grad_scale, loss_ps, best_shift, clear_count,
                                                   cpsnr_ps, dsr, stack_out);

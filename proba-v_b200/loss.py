@@ -42,8 +42,7 @@ class Losses:
             dev = predPatchHR.device
             sr = _buf.dev_tensor(predPatchHR, torch.float32, dev)
             hr = _buf.dev_tensor(patchHR, torch.float32, dev)
-            mk = _buf.dev_tensor(maskHR, torch.uint8, dev) if not (isinstance(maskHR, torch.Tensor) and maskHR.dtype == torch.bool) \
-                else maskHR.to(dev).contiguous().view(torch.uint8)
+            mk = _buf.dev_tensor(maskHR, torch.uint8, dev)
             f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
             out = dict(loss_per_sample=f(B), cpsnr=f(B), mean_loss=f(1),
                        best_shift=torch.empty(B, dtype=torch.int32, device=dev),

@@ -144,7 +144,7 @@ class ModelTrainer:
             dev = patchLR.device
             x = _buf.dev_tensor(patchLR, torch.float32, dev)
             y = _buf.dev_tensor(patchHR, torch.float32, dev)
-            m = maskHR.to(dev).contiguous().view(torch.uint8) if maskHR.dtype == torch.bool else _buf.dev_tensor(maskHR, torch.uint8, dev)
+            m = _buf.dev_tensor(maskHR, torch.uint8, dev)
             out = torch.empty(2, dtype=torch.float32, device=dev)
             check(fn_dev(self._h, _buf.ptr(x), _buf.ptr(y), _buf.ptr(m), B, _buf.ptr(out), _buf.current_stream_ptr(dev)))
             return out
@@ -154,17 +154,20 @@ class ModelTrainer:
         check(fn_host(self._h, _buf.ptr(x), _buf.ptr(y), _buf.ptr(m), B, _buf.ptr(self._out)))
         return self._out.copy()
 
-    def trainStep(self, patchLR, patchHR, maskHR, global_batch: int = None):
-        """trainClass.py:124-135.  Returns (loss, mean cPSNR) of this rank's shard and updates the running means."""
+    def trainStep(self, patchLR, patchHR, maskHR, global_batch: int = None, sync: bool = True):
+        """trainClass.py:124-135.  Returns (loss, mean cPSNR) of the global batch and updates the running means.
+        sync=False (device tensors only) skips the per-step host read the reference's logging forces and returns the
+        device tensor [loss, cPSNR] of this rank's shard instead."""
         rank, ws = parallel.world()
         if ws == 1:
             out = self._run(lib().pv_train_step_host, lib().pv_train_step, patchLR, patchHR, maskHR)
         else:
             out = self._dp_step(patchLR, patchHR, maskHR, global_batch)
+        if not sync and _buf.is_cuda_tensor(out):
+            return out
         lossv, psnrv = float(out[0]), float(out[1])
         if ws > 1:
-            lossv, psnrv = parallel.reduce_metrics(lossv, psnrv, int(patchLR.shape[0]),
-                                                   device=patchLR.device if _buf.is_cuda_tensor(patchLR) else None)
+            lossv, psnrv = parallel.reduce_metrics(lossv, psnrv, int(patchLR.shape[0]), device=out.device)
         self.trainLoss(lossv)
         self.trainPSNR(psnrv)
         return lossv, psnrv
@@ -172,18 +175,13 @@ class ModelTrainer:
     def _dp_step(self, patchLR, patchHR, maskHR, global_batch):
         """fwd/bwd on the local shard -> ONE all-reduce(SUM) of the flat gradient arena -> identical update on every rank."""
         import torch
-        if not _buf.is_cuda_tensor(patchLR):
-            dev = torch.device(f"cuda:{self._model.device}")
-            patchLR = torch.as_tensor(np.asarray(patchLR, np.float32)).to(dev)
-            patchHR = torch.as_tensor(np.asarray(patchHR, np.float32)).to(dev)
-            maskHR = torch.as_tensor(np.asarray(maskHR).astype(np.uint8)).to(dev)
-        dev = patchLR.device
+        dev = patchLR.device if _buf.is_cuda_tensor(patchLR) else torch.device(f"cuda:{self._model.device}")
         B = int(patchLR.shape[0])
         ws = parallel.world()[1]
         gb = global_batch if global_batch else B * ws
         x = _buf.dev_tensor(patchLR, torch.float32, dev)
         y = _buf.dev_tensor(patchHR, torch.float32, dev)
-        m = maskHR.contiguous().view(torch.uint8) if maskHR.dtype == torch.bool else _buf.dev_tensor(maskHR, torch.uint8, dev)
+        m = _buf.dev_tensor(maskHR, torch.uint8, dev)
         out = torch.empty(2, dtype=torch.float32, device=dev)
         st = _buf.current_stream_ptr(dev)
         check(lib().pv_train_forward_backward(self._h, _buf.ptr(x), _buf.ptr(y), _buf.ptr(m), B, parallel.grad_scale(gb), _buf.ptr(out), st))
@@ -207,7 +205,7 @@ class ModelTrainer:
         B = int(patchLR.shape[0])
         x = _buf.dev_tensor(patchLR, torch.float32, dev)
         y = _buf.dev_tensor(patchHR, torch.float32, dev)
-        m = _buf.dev_tensor(np.asarray(maskHR).astype(np.uint8) if not isinstance(maskHR, torch.Tensor) else maskHR.to(torch.uint8), torch.uint8, dev)
+        m = _buf.dev_tensor(maskHR, torch.uint8, dev)
         out = torch.empty(2, dtype=torch.float32, device=dev)
         gs = (1.0 / B) if grad_scale is None else float(grad_scale)
         check(lib().pv_train_forward_backward(self._h, _buf.ptr(x), _buf.ptr(y), _buf.ptr(m), B, gs, _buf.ptr(out),

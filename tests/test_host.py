@@ -1,0 +1,137 @@
+"""CPU: host-side logic -- cfg grammar, input pipeline, data-parallel plumbing (gloo, world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import probav_b200 as pb
+from probav_b200 import parallel
+from probav_b200.trainClass import Mean, batched, shuffled_index_stream
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_parse_config_p16t9c85r12():
+    c = pb.parseConfig(os.path.join(ROOT, "cfg", "p16t9c85r12.cfg"))
+    assert (c["num_res_blocks"], c["num_low_res_imgs"], c["scale"], c["num_filters"], c["kernel_size"], c["exp_rate"]) == (12, 9, 3, 32, 3, 8)
+    assert c["decay_rate"] == 0.8 and c["is_grayscale"] is True
+    assert c["max_shift"] == 6 and c["patch_size"] == 16
+    assert c["optimizer"] == "nadam" and c["loss"] == "l1" and c["batch_size"] == 128 and c["learning_rate"] == 0.0005
+    assert isinstance(c["ckpt"], list) and isinstance(c["raw_data"], str)
+    # '.cfg' appended and cfg/ searched (parseConfig.py:10-13)
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        assert pb.parseConfig("p16t12c85r12")["num_low_res_imgs"] == 9
+    finally:
+        os.chdir(cwd)
+
+
+def test_parse_config_rejects_unknown_field(tmp_path):
+    f = tmp_path / "bad.cfg"
+    f.write_text("[Directories]\nraw_data=x\n[Net]\nnum_filters=32\nbogus_field=3\n")
+    with pytest.raises(AssertionError):
+        pb.parseConfig(str(f))
+    g = tmp_path / "ok.cfg"
+    g.write_text("# comment\n[Directories]\nanything_goes=here\n\n[Train]\nlearning_rate=0.1\nloss=l2\n[Preprocessing]\nto_flip=1\nlow_res_patch_thresholds=0.5,0.6\n")
+    c = pb.parseConfig(str(g))
+    assert c["anything_goes"] == "here" and c["learning_rate"] == 0.1 and c["to_flip"] is True and c["low_res_patch_thresholds"] == [0.5, 0.6]
+
+
+def test_shuffle_stream_is_a_permutation_per_epoch_and_last_batch_is_partial():
+    rng = np.random.default_rng(0)
+    idx = list(shuffled_index_stream(100, 2, 16, rng))
+    assert sorted(idx[:100]) == list(range(100)) and sorted(idx[100:]) == list(range(100))
+    # a shuffle buffer of 16 cannot emit element k before position k-15
+    assert all(v <= pos + 15 for pos, v in enumerate(idx[:100]))
+    b = list(batched(iter(range(10)), 4))
+    assert [len(x) for x in b] == [4, 4, 2]          # no drop_remainder (utils.py:32-34)
+
+
+def test_mean_metric_and_shard_bounds():
+    m = Mean()
+    m(2.0); m(4.0)
+    assert m.result() == 3.0
+    m.reset_states()
+    assert m.result() == 0.0
+    for n in (0, 1, 7, 128, 129):
+        for ws in (1, 2, 3, 8):
+            spans = [parallel.shard_bounds(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_loss_selector_and_optimizer_selector():
+    L = pb.Losses((48, 48, 1))
+    assert pb.loss_from_config(L, "l1").__name__ == "shiftCompensatedL1Loss"
+    assert pb.loss_from_config(L, "sobel_l1_mix").__name__ == "shiftCompensatedL1EdgeLoss"
+    with pytest.raises(ValueError):
+        pb.loss_from_config(L, "nope")
+    assert pb.optimizers.from_config("nadam", 5e-4).kind == "nadam"
+    assert pb.optimizers.from_config("adam", 5e-4).kind == "adam"
+    assert pb.optimizers.from_config("rmsprop", 5e-4).kind == "sgd"      # anything else -> SGD (train.py:82-83)
+    assert L.cropSizeHeight == 42 and L.maxPixelShift == 6
+
+
+# ------------------------------------------------------------------------------------------- gloo, world_size 2
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, ws, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws), LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    r, w, _ = parallel.init_from_env(backend="gloo")
+    assert (r, w) == (rank, ws) and parallel.world() == (rank, ws)
+    # the DP contract on the oracle: per-rank grads of sum_b loss_b / global_batch, SUM all-reduced == full-batch grads
+    from oracle.losses import OracleLosses
+    from oracle.step import loss_and_grads
+    from oracle.wdsr import OracleWDSR, init_params
+    from probav_b200 import synth
+    om = OracleWDSR(8075.2045, 3160.7272, 6, 3, 8, (3, 3, 3), 1, 2, 0.8, 9, 16)
+    p = init_params(om.specs, seed=0)
+    lr, hr, mask = synth.make_batch(5, seed=3, hr_zero_under_mask=True)      # 5 samples -> unequal shards 3 + 2
+    ol = OracleLosses((48, 48, 1))
+    lo, hi = parallel.shard_bounds(5, rank, ws)
+    t = lambda a: torch.from_numpy(a[lo:hi])
+    loss, g, _, cps = loss_and_grads(om, ol, p, t(lr).double(), t(hr).double(), t(mask))
+    n_local = hi - lo
+    flat = torch.cat([v.reshape(-1) for v in g.values()]) * (n_local * parallel.grad_scale(5))   # mean over shard -> sum/global
+    parallel.allreduce_sum_(flat)
+    gl, gc = parallel.reduce_metrics(float(loss), float(cps.mean()), n_local)
+    w0 = torch.zeros(4) + rank
+    parallel.broadcast_(w0, 0)
+    if rank == 0:
+        full_loss, gfull, _, cfull = loss_and_grads(om, ol, p, torch.from_numpy(lr).double(), torch.from_numpy(hr).double(), torch.from_numpy(mask))
+        ref = torch.cat([v.reshape(-1) for v in gfull.values()])
+        q.put((float((flat - ref).abs().max() / ref.abs().max()), abs(gl - float(full_loss)), abs(gc - float(cfull.mean())), float(w0.sum())))
+    else:
+        q.put(("r1", float(w0.sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_contract_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    res = [q.get(timeout=240) for _ in range(2)]
+    for p_ in procs:
+        p_.join(timeout=60)
+        assert p_.exitcode == 0
+    main = [r for r in res if r[0] != "r1"][0]
+    other = [r for r in res if r[0] == "r1"][0]
+    assert main[0] < 1e-10 and main[1] < 1e-9 and main[2] < 1e-9
+    assert main[3] == 0.0 and other[1] == 0.0           # broadcast from rank 0
