@@ -761,7 +761,9 @@ int pv_shift_loss_host(int kind, const float* hr, const uint8_t* mask, const flo
     float *d_hr = nullptr, *d_sr = nullptr, *d_f = nullptr;
     uint8_t* d_m = nullptr;
     int32_t* d_i = nullptr;
-    const size_t nf = (size_t)B * 2 + 1 + (dsr ? n : 0) + (stack_out ? (size_t)B * 49 * 4 : 0);
+    // sub-buffer offsets rounded to 4 floats: the kernel stores dSR as float4
+    const size_t o_mean = ((size_t)B * 2 + 3) & ~(size_t)3, o_dsr = o_mean + 4, o_stack = o_dsr + (dsr ? n : 0);
+    const size_t nf = o_stack + (stack_out ? (size_t)B * 49 * 4 : 0);
     int rc = 0;
     do {
         if (cudaMalloc(&d_hr, n * 4) != cudaSuccess || cudaMalloc(&d_sr, n * 4) != cudaSuccess || cudaMalloc(&d_m, n) != cudaSuccess ||
@@ -769,9 +771,9 @@ int pv_shift_loss_host(int kind, const float* hr, const uint8_t* mask, const flo
         cudaMemcpyAsync(d_hr, hr, n * 4, cudaMemcpyHostToDevice, 0);
         cudaMemcpyAsync(d_sr, sr, n * 4, cudaMemcpyHostToDevice, 0);
         cudaMemcpyAsync(d_m, mask, n, cudaMemcpyHostToDevice, 0);
-        float* d_loss = d_f; float* d_cp = d_f + B; float* d_mean = d_f + 2 * B;
-        float* d_dsr = dsr ? d_f + 2 * B + 1 : nullptr;
-        float* d_stack = stack_out ? d_f + 2 * B + 1 + (dsr ? n : 0) : nullptr;
+        float* d_loss = d_f; float* d_cp = d_f + B; float* d_mean = d_f + o_mean;
+        float* d_dsr = dsr ? d_f + o_dsr : nullptr;
+        float* d_stack = stack_out ? d_f + o_stack : nullptr;
         if ((rc = shift_loss_device(kind, d_hr, d_m, d_sr, B, H, W, border, grad_scale, d_loss, d_i, d_i + B, d_cp, d_mean, d_dsr, d_stack, 0))) break;
         cudaMemcpyAsync(loss_ps, d_loss, (size_t)B * 4, cudaMemcpyDeviceToHost, 0);
         cudaMemcpyAsync(best_shift, d_i, (size_t)B * 4, cudaMemcpyDeviceToHost, 0);

@@ -454,6 +454,10 @@ int shift_loss_device(int kind, const float* hr, const uint8_t* mask, const floa
     // algorithmic bytes per sample: HR f32 + SR f32 + bool mask read, dSR f32 written when fused
     PV_TIMED(H == WT && W == WT ? "shift_loss_patch" : "shift_loss_tiled", st, 0.0,
              (double)B * H * W * (9.0 + (dsr ? 4.0 : 0.0)));
+    if (H == WT && W == WT &&
+        ((reinterpret_cast<uintptr_t>(hr) | reinterpret_cast<uintptr_t>(sr) | reinterpret_cast<uintptr_t>(dsr)) & 15 ||
+         reinterpret_cast<uintptr_t>(mask) & 3))
+        return set_error(PV_ERR_BAD_ARG, "pv_shift_loss: hr/sr/dsr must be 16-byte aligned and mask 4-byte aligned");
     if (H == WT && W == WT) {
         shift_loss_patch_kernel<<<B, NT, 0, st>>>(kind, hr, mask, sr, grad_scale, loss_ps, best_shift, clear_count,
                                                   cpsnr_ps, dsr, stack_out);

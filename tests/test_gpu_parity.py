@@ -84,15 +84,22 @@ def test_shift_loss_known_answer_shift_36():
 @pytest.mark.parametrize("kind", ["l1", "l2"])
 def test_shift_loss_fused_backward_matches_autograd(kind):
     pb = _pb()
-    hr, mask, sr = _loss_inputs(8, seed=21)
     L = OracleLosses((48, 48, 1))
-    srg = sr.clone().requires_grad_(True)
     fn = L.shiftCompensatedL1Loss if kind == "l1" else L.shiftCompensatedL2Loss
-    fn(hr, mask, srg).backward()
-    out = pb.Losses((48, 48, 1)).evaluate(kind, _np(hr), _np(mask, np.uint8), _np(sr), want_grad=True)
-    ref = _np(srg.grad, np.float64)
-    assert rel_err(out["dsr"], ref) < GRAD_TOL
-    assert np.all(out["dsr"][:, :3] == 0) and np.all(out["dsr"][:, :, 45:] == 0)
+    for zero_under_mask in (True, False):
+        hr, mask, sr = _loss_inputs(8, seed=21, zero_under_mask=zero_under_mask)
+        srg = sr.clone().requires_grad_(True)
+        fn(hr, mask, srg).backward()
+        out = pb.Losses((48, 48, 1)).evaluate(kind, _np(hr), _np(mask, np.uint8), _np(sr), want_grad=True)
+        ref = _np(srg.grad, np.float64)
+        if zero_under_mask or kind == "l2":
+            assert rel_err(out["dsr"], ref) < GRAD_TOL
+        else:
+            # reference quirk: with raw HR under unclear pixels the bias is inflated, every clear
+            # residual has the same sign and the L1 gradient collapses to ~0: compare on the scale of a normal gradient
+            assert np.abs(ref).max() < 1e-12
+            assert np.abs(out["dsr"]).max() < 1e-3 / (8 * 1764)
+        assert np.all(out["dsr"][:, :3] == 0) and np.all(out["dsr"][:, :, 45:] == 0)
 
 
 def test_shift_loss_device_pointers_and_large_batch_properties():
@@ -306,7 +313,7 @@ def test_train_steps_match_oracle(small_cfg, opt):
     om, p = oracle_and_params(small_cfg, seed=20)
     m = cuda_model(small_cfg, p)
     from probav_b200 import synth
-    lr_rate = 5e-4 if opt != "sgd" else 1e-6
+    lr_rate = 5e-4 if opt != "sgd" else 1e-4
     t = _trainer(pb, m, opt=opt, lr=lr_rate)
     oopt = make_optimizer(opt, lr_rate)
     ol = OracleLosses((48, 48, 1))
@@ -357,7 +364,8 @@ def test_eval_step_and_checkpoint_roundtrip(small_cfg):
     w2 = m.get_flat()
     t.restore()
     l2b, _ = t.trainStep(lr, hr, mask)
-    assert l2a == l2b and np.array_equal(m.get_flat(), w2)
+    # the weight-gradient kernels reduce with fp32 atomics (order not fixed), so the step repeats to rounding, not bitwise
+    assert l2a == l2b and np.abs(m.get_flat() - w2).max() < 0.02 * 5e-4
 
 
 def test_fit_loop_runs_and_loss_decreases(small_cfg):
@@ -367,7 +375,7 @@ def test_fit_loop_runs_and_loss_decreases(small_cfg):
     X, y, msk = synth.make_batch(64, seed=50, hr_zero_under_mask=True)
     t = _trainer(pb, m, lr=2e-3)
     l_first, _ = t.testStep(X[:32], y[:32], msk[:32])
-    t.evalStep = 8
+    t.evalStep = 2
     t.fitTrainData(X, [y, msk], 16, 6, [X[:32], y[:32], msk[:32]], valSteps=2, saveBestOnly=False, logEvery=0)
     l_last, _ = t.testStep(X[:32], y[:32], msk[:32])
     assert t.step == 24 and l_last < l_first
