@@ -55,7 +55,9 @@ typedef struct pv_cfg {
     int32_t patch_size;
     float   mean;               /* datasetAllMean (train.py:48,51)                             */
     float   std;                /* datasetAllStd  (train.py:49,52)                             */
-    int32_t precision;          /* 0 = fp32 (CUDA-core, exact mode), 1 = bf16 tensor-core mode */
+    int32_t precision;          /* 0 = fp32 on CUDA cores (exact mode); 1 = tf32 on the tcgen05 tensor cores, fp32 accumulate
+                                 * (what TensorFlow itself runs on Ampere-or-newer GPUs by default); 3 = fp32 CUDA-core
+                                 * kernels on the tensor-core engine's row layouts (debug / cross-check) */
 } pv_cfg;
 
 typedef enum pv_loss_kind {     /* cfg [Train] loss (train.py:93-100)                          */
@@ -159,6 +161,9 @@ int64_t pv_launch_count(void);
  * launch is bracketed by CUDA events on its stream.  pv_timing_report synchronises the device and writes one line
  * per kernel class: "name launches total_ms algorithmic_flops algorithmic_bytes\n"; returns the number of bytes
  * written (or needed, if larger than cap). */
+/* Device self-test: every tensor-core kernel configuration against the CUDA-core kernel on the same random buffers.
+ * Returns the number of failing configurations (0 = all agree); the per-configuration report goes to buf. */
+int  pv_selftest(char* buf, int cap);
 int  pv_timing_enable(int on);
 int  pv_timing_reset(void);
 int  pv_timing_report(char* buf, int cap);

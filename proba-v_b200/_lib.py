@@ -63,6 +63,7 @@ _SIGS = {
     "pv_trainer_get_state": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_double), _P, _P, C.c_int64]),
     "pv_trainer_set_state": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P, C.c_int64]),
     "pv_trainer_set_lr": (C.c_int, [_P, C.c_float]),
+    "pv_selftest": (C.c_int, [C.c_char_p, C.c_int]),
     "pv_timing_enable": (C.c_int, [C.c_int]),
     "pv_timing_reset": (C.c_int, []),
     "pv_timing_report": (C.c_int, [C.c_char_p, C.c_int]),
@@ -107,3 +108,10 @@ def timing_report() -> dict:
         name, cnt, ms, fl, by = line.split()
         out[name] = dict(launches=int(cnt), ms=float(ms), flops=float(fl), bytes=float(by))
     return out
+
+
+def selftest():
+    """(number of failing tensor-core kernel configurations, report text)."""
+    buf = C.create_string_buffer(8192)
+    n = lib().pv_selftest(buf, 8192)
+    return n, buf.value.decode()

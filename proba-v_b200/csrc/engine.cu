@@ -58,96 +58,11 @@ KernelTimer::~KernelTimer() {
     if (slot >= 0) cudaEventRecord(g_timed[slot].b, st);
 }
 
-static inline int storage_channels(int c) { return c > 16 ? ((c + 31) / 32) * 32 : c; }
-
-struct Layer {
-    std::string name;
-    int k[3];            // kernel (H, W, T)
-    int cin, cout, cin_s, cout_s;
-    int pad[3];          // zero padding per side ('same' = k/2, 'valid' = 0)
-    int relu;
-    int Hi, Wi, Ti, Ho, Wo, To;
-    long long v_off, g_off, b_off, weff_off, bias_s_off, scale_off;
-    int taps() const { return k[0] * k[1] * k[2]; }
-};
-
-struct PInfo { std::string name; int rank; int64_t shape[5]; int64_t off, numel; };
-
-struct Pool {
-    std::map<std::string, float*> ptr;
-    std::vector<std::pair<std::string, size_t>> spec;   // name, floats per sample
-    int cap = 0;
-    void add(const std::string& n, size_t per) {
-        for (auto& s : spec) if (s.first == n) { s.second = std::max(s.second, per); return; }
-        spec.emplace_back(n, per);
-    }
-    int ensure(int B) {
-        if (B <= cap) return 0;
-        release();
-        for (auto& s : spec) {
-            float* d = nullptr;
-            PV_CUDA(cudaMalloc(&d, s.second * (size_t)B * sizeof(float)));
-            ptr[s.first] = d;
-        }
-        cap = B;
-        return 0;
-    }
-    void release() {
-        for (auto& kv : ptr) cudaFree(kv.second);
-        ptr.clear();
-        cap = 0;
-    }
-    float* operator[](const std::string& n) {
-        auto it = ptr.find(n);
-        return it == ptr.end() ? nullptr : it->second;
-    }
-};
-
 }  // namespace pv
 
+#include "engine.h"
+
 using namespace pv;
-
-struct pv_model {
-    pv_cfg cfg;
-    int device = 0;
-    int S = 0, T = 0, P = 0, F = 0, R = 0, nred = 0;
-    std::vector<Layer> layers;
-    std::vector<PInfo> pinfo;
-    std::vector<int> red_pad;          // 3 ints per reducer: reflect pad before it
-    long long nparams = 0, nweff = 0, nbias_s = 0, nscale = 0;
-    float *params = nullptr, *weff = nullptr, *weffT = nullptr, *bias_s = nullptr, *scale = nullptr;
-    WnLayer* wn_tab = nullptr;
-    int wn_blocks = 0;
-    bool weff_dirty = true;
-    Pool pool_infer, pool_train;
-    float *stage_lr = nullptr, *stage_sr = nullptr, *stage_scene = nullptr;   // host-API staging
-    size_t stage_lr_n = 0, stage_sr_n = 0, stage_scene_n = 0;
-
-    int li(const std::string& n) const {
-        for (size_t i = 0; i < layers.size(); ++i) if (layers[i].name == n) return (int)i;
-        return -1;
-    }
-    std::string A(int i, bool tr) const { return tr ? "a" + std::to_string(i) : "a" + std::to_string(i & 1); }
-    std::string E(int i, bool tr) const { return tr ? "E" + std::to_string(i) : "E"; }
-    std::string D(int i, bool tr) const { return tr ? "D" + std::to_string(i) : "D"; }
-};
-
-struct pv_trainer {
-    pv_model* m = nullptr;
-    int opt = PV_OPT_NADAM, loss_kind = PV_LOSS_L1;
-    float lr = 1e-3f;
-    long long iter = 0;
-    double momentum_cache = 1.0;
-    float *grads = nullptr, *dweff = nullptr, *dbias_s = nullptr, *m1 = nullptr, *m2 = nullptr;
-    // per-batch loss workspace
-    int capB = 0;
-    float *sr = nullptr, *dsr = nullptr, *loss_ps = nullptr, *cpsnr_ps = nullptr, *out2 = nullptr;
-    int32_t *best = nullptr, *cnt = nullptr;
-    // host-API staging
-    float *s_lr = nullptr, *s_hr = nullptr;
-    uint8_t* s_mask = nullptr;
-    int s_cap = 0;
-};
 
 namespace pv {
 
@@ -159,6 +74,11 @@ static int add_layer(pv_model* m, const std::string& name, int kh, int kw, int k
     L.k[0] = kh; L.k[1] = kw; L.k[2] = kt;
     L.cin = cin; L.cout = cout;
     L.cin_s = storage_channels(cin); L.cout_s = storage_channels(cout);
+    const bool is3d = name.rfind("residConv", 0) != 0;
+    if (m->rows && is3d) {              // row engine: every trunk tensor is [rows][32k] and taps run (dt,dh,dw)
+        L.wn_mode = 1;
+        if (cout > 1) L.cout_s = ((cout + 31) / 32) * 32;
+    }
     for (int a = 0; a < 3; ++a) L.pad[a] = same ? L.k[a] / 2 : 0;
     L.relu = relu;
     L.Hi = Hi; L.Wi = Wi; L.Ti = Ti;
@@ -195,6 +115,14 @@ static int build_plan(pv_model* m) {
     if (!c.is_grayscale)
         return set_error(PV_ERR_BAD_CONFIG, "is_grayscale=0 (3-channel input) is not built; PROBA-V bands are single-channel");
     const int ks = c.kernel_size;
+    if (c.precision != 0 && c.precision != 1 && c.precision != 3)
+        return set_error(PV_ERR_BAD_CONFIG, "precision=%d: 0 = fp32 (CUDA cores), 1 = tf32 (tcgen05 tensor cores), 3 = fp32 on the row layouts", c.precision);
+    m->rows = c.precision != 0;
+    m->use_tc = c.precision == 1;
+    if (m->rows && (c.num_low_res_imgs != 9 || c.num_filters != 32 || c.num_filters * c.exp_rate != 256 || c.scale != 3 ||
+                    c.patch_size != 16 || c.max_shift != 6 || (int)(c.num_filters * c.decay_rate) > 32))
+        return set_error(PV_ERR_BAD_CONFIG, "the tensor-core engine is built for the p16t9 family (T=9, 32 filters, exp_rate 8, scale 3, "
+                                            "patch 16, max_shift 6); use precision fp32 for other graphs");
     m->S = c.patch_size + c.max_shift;            // modelsTF.py:19
     m->T = c.num_low_res_imgs; m->P = c.patch_size; m->F = c.num_filters; m->R = c.num_res_blocks;
     const int S = m->S, T = m->T, F = m->F;
@@ -243,6 +171,7 @@ static int build_plan(pv_model* m) {
     if (h2 != m->P)
         return set_error(PV_ERR_BAD_CONFIG, "2-D skip path ends at %dx%d, main path at %dx%d (Add at modelsTF.py:38 would fail)", h2, h2, m->P, m->P);
 
+    if (m->rows) return tc_build_plan(m);
     // activation pools
     for (int tr = 0; tr < 2; ++tr) {
         Pool& P = tr ? m->pool_train : m->pool_infer;
@@ -293,7 +222,7 @@ static ConvP conv_desc(const Layer& L, const float* w, const float* bias, int B)
     return p;
 }
 
-static int conv_fwd(pv_model* m, int li, const float* in, float* out, const float* res, int B, cudaStream_t st) {
+int conv_fwd(pv_model* m, int li, const float* in, float* out, const float* res, int B, cudaStream_t st) {
     const Layer& L = m->layers[li];
     ConvP p = conv_desc(L, m->weff + L.weff_off, m->bias_s + L.bias_s_off, B);
     p.x = in; p.y = out; p.residual = res;
@@ -301,7 +230,7 @@ static int conv_fwd(pv_model* m, int li, const float* in, float* out, const floa
 }
 
 // data gradient: correlate dy (masked by the layer's ReLU output) with the flipped/transposed kernel, pad' = k-1-pad
-static int conv_dgrad(pv_model* m, int li, const float* gout, const float* relu_ref, float* gin, const float* res, int B, cudaStream_t st) {
+int conv_dgrad(pv_model* m, int li, const float* gout, const float* relu_ref, float* gin, const float* res, int B, cudaStream_t st) {
     const Layer& L = m->layers[li];
     ConvP p;
     p.x = gout; p.xmask = relu_ref; p.w = m->weffT + L.weff_off; p.bias = nullptr; p.residual = res; p.y = gin;
@@ -313,7 +242,7 @@ static int conv_dgrad(pv_model* m, int li, const float* gout, const float* relu_
     return launch_conv(p, st);
 }
 
-static int conv_wgrad(pv_trainer* t, int li, const float* in, const float* gout, const float* relu_ref, int B, cudaStream_t st) {
+int conv_wgrad(pv_trainer* t, int li, const float* in, const float* gout, const float* relu_ref, int B, cudaStream_t st) {
     const Layer& L = t->m->layers[li];
     WgradP p;
     p.x = in; p.dy = gout; p.ymask = relu_ref; p.dw = t->dweff + L.weff_off; p.db = t->dbias_s + L.bias_s_off;
@@ -324,7 +253,7 @@ static int conv_wgrad(pv_trainer* t, int li, const float* in, const float* gout,
     return launch_wgrad(p, st);
 }
 
-static int refresh_weights(pv_model* m, cudaStream_t st) {
+int refresh_weights(pv_model* m, cudaStream_t st) {
     if (!m->weff_dirty) return 0;
     PV_TRY(launch_wn_prep(m->wn_tab, (int)m->layers.size(), m->wn_blocks, m->params, m->weff, m->weffT, m->bias_s, m->scale, st));
     m->weff_dirty = false;
@@ -335,6 +264,7 @@ static int refresh_weights(pv_model* m, cudaStream_t st) {
 static int model_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip_round, cudaStream_t st) {
     if (!lr || !sr || B <= 0) return set_error(PV_ERR_BAD_ARG, "forward: null buffer or B=%d", B);
     PV_CUDA(cudaSetDevice(m->device));
+    if (m->rows) return tc_forward(m, lr, B, sr, tr, clip_round, st);
     Pool& P = tr ? m->pool_train : m->pool_infer;
     PV_TRY(P.ensure(B));
     PV_TRY(refresh_weights(m, st));
@@ -375,6 +305,7 @@ static int model_forward(pv_model* m, const float* lr, int B, float* sr, bool tr
 // tape.gradient(loss, trainable_variables): trainClass.py:131.  g_sr = dL/dSR [B, sP, sP].
 static int model_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
     pv_model* m = t->m;
+    if (m->rows) return tc_backward(t, g_sr, B, st);
     Pool& P = m->pool_train;
     const pv_cfg& c = m->cfg;
     PV_CUDA(cudaMemsetAsync(t->dweff, 0, m->nweff * sizeof(float), st));
@@ -508,6 +439,15 @@ int pv_abi_version(void) { return PV_ABI_VERSION; }
 const char* pv_last_error(void) { return pv::last_error().c_str(); }
 int64_t pv_launch_count(void) { return pv::launch_count(); }
 
+int pv_selftest(char* buf, int cap) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return set_error(PV_ERR_NO_DEVICE, "no CUDA device: no CPU fallback"); }
+    std::string rep;
+    const int fails = tc_selftest(rep);
+    if (buf && cap > 0) { std::strncpy(buf, rep.c_str(), cap - 1); buf[cap - 1] = 0; }
+    return fails;
+}
+
 int pv_timing_enable(int on) { pv::g_timing = on != 0; return 0; }
 
 int pv_timing_reset(void) {
@@ -587,6 +527,8 @@ int pv_model_create(const pv_cfg* cfg, int device, pv_model** out) {
         w.weff_off = L.weff_off; w.weffT_off = L.weff_off; w.bias_s_off = L.bias_s_off; w.scale_off = L.scale_off;
         w.taps = L.taps(); w.cin = L.cin; w.cout = L.cout; w.cin_s = L.cin_s; w.cout_s = L.cout_s;
         w.first_block = blocks;
+        w.mode = L.wn_mode;
+        w.round_tf32 = (m->use_tc && L.wn_mode == 1 && L.cin > 1) ? 1 : 0;
         blocks += L.cout;
     }
     m->wn_blocks = blocks;
@@ -818,7 +760,7 @@ void pv_trainer_destroy(pv_trainer* t) {
     cudaSetDevice(t->m->device);
     cudaFree(t->grads); cudaFree(t->dweff); cudaFree(t->dbias_s); cudaFree(t->m1); cudaFree(t->m2);
     cudaFree(t->sr); cudaFree(t->dsr); cudaFree(t->loss_ps); cudaFree(t->cpsnr_ps); cudaFree(t->best); cudaFree(t->cnt);
-    cudaFree(t->out2); cudaFree(t->s_lr); cudaFree(t->s_hr); cudaFree(t->s_mask);
+    cudaFree(t->out2); cudaFree(t->s_lr); cudaFree(t->s_hr); cudaFree(t->s_mask); cudaFree(t->wg_partials);
     delete t;
 }
 

@@ -1,0 +1,353 @@
+// engine_tc.cu -- forward / backward sequencing of the WDSR graph on the row layouts (rows.h): the tensor-core
+// engine (pv_cfg.precision = 1, tf32 tcgen05 kernels) and its fp32 CUDA-core twin on the same layouts (precision = 3).
+//
+// Same graph as engine.cu (reference models/modelsTF.py:15-43, 55-74, 152-164, 177-189; backward = tape.gradient,
+// models/trainClass.py:131), different data layout:
+//   prep (dense) -> mainConv1 -> A0 [PR] -> 12 x { expConv+ReLU -> E ; decConv -> D ; normConv + A_i -> A_i+1 } [PR]
+//   -> reflect pad -> G0 [G] -> convReducer_1..3 (+ReLU) -> G1..G3 -> upscaleConv1 -> U [G] -> tail (+ 2-D skip path)
+// Backward: every data-gradient kernel masks its output with the ReLU of the layer it flows into, so the stored
+// tensors are dL/d(pre-activation) and the weight-gradient kernels need no mask.
+#include <cmath>
+#include <cstring>
+
+#include "engine.h"
+
+namespace pv {
+namespace {
+
+struct Taps { int n; int off[MAX_TAPS]; int c0[MAX_TAPS]; int chunk[MAX_TAPS]; };
+
+RowGeom pr_geom() {
+    RowGeom g;
+    g.lead = 640; g.pstride = 10 * 529; g.plane = 529; g.pw = 23; g.t0 = 0; g.nt = 9; g.nh = 22; g.nw = 22;
+    g.row0 = 0; g.nrows = 9 * 529;
+    return g;
+}
+// G layout of the tensor after k valid 3x3x3 convolutions of the reflect-padded 24x24x9 block output
+RowGeom g_geom(int k) {
+    RowGeom g;
+    const int T = 9 - 2 * k;
+    g.lead = 1280; g.pstride = (long long)(T + 2) * 576; g.plane = 576; g.pw = 24; g.t0 = 2;
+    g.nt = T; g.nh = 24 - 2 * k; g.nw = 24 - 2 * k; g.row0 = 2 * 576; g.nrows = T * 576;
+    return g;
+}
+size_t rows_per(const RowGeom& g, int C) { return (size_t)g.pstride * C; }
+size_t rows_extra(const RowGeom& g, int C) { return (size_t)(g.lead + ROW_TAIL) * C; }
+
+// taps of a 3x3x3 convolution as row offsets; sign = +1 forward, -1 data gradient (listed in ascending offset order)
+Taps conv3_taps(int plane, int pw, bool centred, int sign) {
+    Taps t; t.n = 27;
+    for (int i = 0; i < 27; ++i) {
+        const int tau = sign > 0 ? i : 26 - i;
+        const int dt = tau / 9 - (centred ? 1 : 0), dh = (tau / 3) % 3 - (centred ? 1 : 0), dw = tau % 3 - (centred ? 1 : 0);
+        t.off[i] = sign * (dt * plane + dh * pw + dw);
+        t.c0[i] = 0;
+        t.chunk[i] = tau;
+    }
+    return t;
+}
+// a pointwise layer whose input rows are `kin` channels wide: K-chunks of 32 as "taps"
+Taps chunk_taps(int kin) {
+    Taps t; t.n = kin / 32;
+    for (int i = 0; i < t.n; ++i) { t.off[i] = 0; t.c0[i] = 32 * i; t.chunk[i] = i; }
+    return t;
+}
+
+// forward convolution of layer L:  y = act(conv(x) + bias) (+ residual), masked to the valid extent of `og`
+int conv_rows(pv_model* m, const Layer& L, const Taps& tp, const float* x, int xc, const RowGeom& ig, float* y, const RowGeom& og,
+              const float* residual, int B, const char* tag, cudaStream_t st, bool round_out = true) {
+    RowConvP p;
+    memset(&p, 0, sizeof p);
+    p.x = x; p.xc = xc; p.y = y; p.n = L.cout_s; p.B = B;
+    p.in_lead = ig.lead; p.in_pstride = ig.pstride; p.og = og;
+    p.ntap = tp.n; p.kc = 32;
+    const int Kflat = L.taps() * L.cin_s;
+    for (int i = 0; i < tp.n; ++i) {
+        p.off[i] = tp.off[i]; p.c0[i] = tp.c0[i];
+        if (m->use_tc) { p.wr0[i] = 0; p.wc0[i] = 32 * tp.chunk[i]; }       // weffT [cout_s][Kflat]
+        else { p.wr0[i] = 32 * tp.chunk[i]; p.wc0[i] = 0; }                  // weff  [Kflat][cout_s]
+    }
+    if (m->use_tc) { p.w = m->weffT + L.weff_off; p.w_rows = L.cout_s; p.w_cols = Kflat; p.w_kmajor = 1; }
+    else { p.w = m->weff + L.weff_off; p.w_rows = Kflat; p.w_cols = L.cout_s; p.w_kmajor = 0; }
+    p.bias = m->bias_s + L.bias_s_off; p.residual = residual; p.relumask = nullptr; p.relu = L.relu;
+    p.round_tf32 = (m->use_tc && round_out) ? 1 : 0;      // outputs that only feed MMAs are stored round-to-nearest tf32
+    p.flops = 2.0 * B * L.Ho * L.Wo * L.To * L.taps() * L.cin * L.cout;
+    p.tag = tag;
+    return m->use_tc ? launch_rowconv_tc(p, st) : launch_rowconv_simt(p, st);
+}
+
+// data gradient of layer L: gx = conv^T(gz) (+ residual), multiplied by (relumask > 0), masked to the valid extent of `xg`
+int dgrad_rows(pv_model* m, const Layer& L, const Taps& tp /* negated offsets */, int nchunk_out /* cout_s / 32 */,
+               const float* gz, const RowGeom& zg, float* gx, const RowGeom& xg, const float* residual, const float* relumask,
+               int B, const char* tag, cudaStream_t st) {
+    RowConvP p;
+    memset(&p, 0, sizeof p);
+    p.x = gz; p.xc = L.cout_s; p.y = gx; p.n = L.cin_s; p.B = B;
+    p.in_lead = zg.lead; p.in_pstride = zg.pstride; p.og = xg;
+    p.kc = 32;
+    const int Kflat = L.taps() * L.cin_s;
+    int n = 0;
+    for (int i = 0; i < tp.n; ++i)
+        for (int j = 0; j < nchunk_out; ++j, ++n) {
+            if (n >= MAX_TAPS) return set_error(PV_ERR_BAD_ARG, "dgrad_rows: too many taps");
+            p.off[n] = tp.off[i]; p.c0[n] = 32 * j;
+            const int tau = tp.chunk[i];
+            if (m->use_tc) { p.wr0[n] = tau * L.cin_s; p.wc0[n] = 32 * j; }      // weff [Kflat][cout_s]: rows ci, K = co contiguous
+            else { p.wr0[n] = 32 * j; p.wc0[n] = tau * L.cin_s; }                 // weffT [cout_s][Kflat]: rows co (K), ci contiguous
+        }
+    p.ntap = n;
+    if (m->use_tc) { p.w = m->weff + L.weff_off; p.w_rows = Kflat; p.w_cols = L.cout_s; p.w_kmajor = 1; }
+    else { p.w = m->weffT + L.weff_off; p.w_rows = L.cout_s; p.w_cols = Kflat; p.w_kmajor = 0; }
+    p.bias = nullptr; p.residual = residual; p.relumask = relumask; p.relu = 0;
+    p.round_tf32 = m->use_tc ? 1 : 0;
+    p.flops = 2.0 * B * L.Ho * L.Wo * L.To * L.taps() * L.cin * L.cout;
+    p.tag = tag;
+    return m->use_tc ? launch_rowconv_tc(p, st) : launch_rowconv_simt(p, st);
+}
+
+// weight gradient of layer L:  dweff[Kflat][cout_s] += x^T gz,  dbias += column sums of gz
+int wgrad_rows(pv_trainer* t, const Layer& L, const Taps& tp /* forward offsets */, const float* x, int xc, const RowGeom& ig,
+               const float* gz, const RowGeom& og, int B, const char* tag, cudaStream_t st) {
+    pv_model* m = t->m;
+    RowWgradP p;
+    memset(&p, 0, sizeof p);
+    p.x = x; p.xc = xc; p.gz = gz; p.n = L.cout_s; p.B = B;
+    p.dw = t->dweff + L.weff_off; p.dw_cols = L.cout_s; p.db = t->dbias_s + L.bias_s_off;
+    p.in_lead = ig.lead; p.in_pstride = ig.pstride; p.og = og;
+    p.ntap = tp.n; p.kc = 32;
+    for (int i = 0; i < tp.n; ++i) { p.off[i] = tp.off[i]; p.c0[i] = tp.c0[i]; p.dwr0[i] = 32 * tp.chunk[i]; p.dwc0[i] = 0; }
+    p.flops = 2.0 * B * L.Ho * L.Wo * L.To * L.taps() * L.cin * L.cout;
+    p.tag = tag;
+    (void)m;
+    return launch_rowwgrad_simt(p, st);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ self-test
+// Runs each tensor-core kernel configuration of the graph against the CUDA-core kernel on the same random row
+// buffers (values on a coarse dyadic grid, so tf32 products are exact and both paths must agree to fp32 rounding).
+static int selftest_one(const char* name, RowConvP p, size_t in_floats, size_t out_floats, size_t w_floats, std::string& rep) {
+    float *x = nullptr, *w = nullptr, *wt = nullptr, *b = nullptr, *res = nullptr, *msk = nullptr, *y0 = nullptr, *y1 = nullptr;
+    PV_CUDA(cudaMalloc(&x, in_floats * 4)); PV_CUDA(cudaMalloc(&w, w_floats * 4)); PV_CUDA(cudaMalloc(&wt, w_floats * 4));
+    PV_CUDA(cudaMalloc(&b, 256 * 4)); PV_CUDA(cudaMalloc(&res, out_floats * 4)); PV_CUDA(cudaMalloc(&msk, out_floats * 4));
+    PV_CUDA(cudaMalloc(&y0, out_floats * 4)); PV_CUDA(cudaMalloc(&y1, out_floats * 4));
+    std::vector<float> h(std::max(std::max(in_floats, out_floats), w_floats));
+    unsigned s = 12345u;
+    auto fill = [&](float* d, size_t n, int range, float scale) {
+        for (size_t i = 0; i < n; ++i) { s = s * 1664525u + 1013904223u; h[i] = (float)((int)((s >> 16) % (2 * range + 1)) - range) * scale; }
+        return cudaMemcpy(d, h.data(), n * 4, cudaMemcpyHostToDevice);
+    };
+    PV_CUDA(fill(x, in_floats, 4, 0.125f)); PV_CUDA(fill(b, 256, 4, 0.25f));
+    PV_CUDA(fill(res, out_floats, 4, 0.25f)); PV_CUDA(fill(msk, out_floats, 1, 1.0f));
+    // weights: [rows = p.w_rows][cols = p.w_cols] K-major for the tensor cores, transposed copy for the CUDA cores
+    PV_CUDA(fill(wt, w_floats, 3, 0.125f));
+    std::vector<float> hw(w_floats);
+    for (int r = 0; r < p.w_rows; ++r) for (int cc = 0; cc < p.w_cols; ++cc) hw[(size_t)cc * p.w_rows + r] = h[(size_t)r * p.w_cols + cc];
+    PV_CUDA(cudaMemcpy(w, hw.data(), w_floats * 4, cudaMemcpyHostToDevice));
+    PV_CUDA(cudaMemset(y0, 0, out_floats * 4)); PV_CUDA(cudaMemset(y1, 0, out_floats * 4));
+    const bool use_res = p.residual != nullptr, use_msk = p.relumask != nullptr, use_bias = p.bias != nullptr;
+    p.x = x; p.bias = use_bias ? b : nullptr; p.residual = use_res ? res : nullptr; p.relumask = use_msk ? msk : nullptr;
+    RowConvP q = p;                       // CUDA-core twin: transposed weight matrix, swapped box coordinates
+    q.w = w; q.w_kmajor = 0; q.w_rows = p.w_cols; q.w_cols = p.w_rows;
+    for (int i = 0; i < p.ntap; ++i) { q.wr0[i] = p.wc0[i]; q.wc0[i] = p.wr0[i]; }
+    q.y = y0; p.w = wt; p.y = y1;
+    int rc = launch_rowconv_simt(q, 0);
+    if (!rc) rc = launch_rowconv_tc(p, 0);
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest %s: %s", name, cudaGetErrorString(cudaGetLastError()));
+    double worst = 0; size_t bad = 0;
+    if (!rc) {
+        std::vector<float> a(out_floats), c2(out_floats);
+        cudaMemcpy(a.data(), y0, out_floats * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(c2.data(), y1, out_floats * 4, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < out_floats; ++i) { const double d = std::fabs((double)a[i] - c2[i]); if (!(d <= 1e-3)) ++bad; if (d > worst || d != d) worst = d; }
+    }
+    char line[256];
+    snprintf(line, sizeof line, "%-34s %s max|tc - simt| = %.3g, mismatches %zu of %zu%s%s\n", name, (!rc && bad == 0) ? "PASS" : "FAIL",
+             worst, bad, out_floats, rc ? " : " : "", rc ? last_error().c_str() : "");
+    rep += line;
+    cudaFree(x); cudaFree(w); cudaFree(wt); cudaFree(b); cudaFree(res); cudaFree(msk); cudaFree(y0); cudaFree(y1);
+    return (!rc && bad == 0) ? 0 : 1;
+}
+
+int tc_selftest(std::string& rep) {
+    const int B = 3;
+    int fails = 0;
+    auto base = [&](const RowGeom& ig, const RowGeom& og, int xc, int n, const Taps& tp, int nchunk) {
+        RowConvP p;
+        memset(&p, 0, sizeof p);
+        p.xc = xc; p.n = n; p.B = B; p.in_lead = ig.lead; p.in_pstride = ig.pstride; p.og = og; p.kc = 32; p.w_kmajor = 1;
+        int k = 0;
+        for (int i = 0; i < tp.n; ++i) for (int j = 0; j < nchunk; ++j, ++k) { p.off[k] = tp.off[i]; p.c0[k] = tp.c0[i] + 32 * j; p.wr0[k] = 0; p.wc0[k] = 32 * k; }
+        p.ntap = k; p.w_rows = n; p.w_cols = 32 * k;
+        return p;
+    };
+    auto floats = [&](const RowGeom& g, int C) { return (size_t)(g.lead + (long long)B * g.pstride + ROW_TAIL) * C; };
+    const RowGeom pr = pr_geom();
+    float* dummy = reinterpret_cast<float*>(1);
+    {   // normConv forward: 27 centred taps, bias + residual
+        RowConvP p = base(pr, pr, 32, 32, conv3_taps(529, 23, true, +1), 1);
+        p.bias = dummy; p.residual = dummy;
+        fails += selftest_one("conv3 same fwd (+bias +residual)", p, floats(pr, 32), floats(pr, 32), (size_t)p.w_rows * p.w_cols, rep);
+    }
+    {   // normConv data gradient: negated taps, ReLU mask, tf32-rounded output
+        RowConvP p = base(pr, pr, 32, 32, conv3_taps(529, 23, true, -1), 1);
+        p.relumask = dummy; p.round_tf32 = 1;
+        fails += selftest_one("conv3 same dgrad (+relu mask)", p, floats(pr, 32), floats(pr, 32), (size_t)p.w_rows * p.w_cols, rep);
+    }
+    {   // reducer forward (valid taps, G1 -> G2) with ReLU
+        RowConvP p = base(g_geom(1), g_geom(2), 32, 32, conv3_taps(576, 24, false, +1), 1);
+        p.bias = dummy; p.relu = 1;
+        fails += selftest_one("conv3 valid fwd G1->G2 (+relu)", p, floats(g_geom(1), 32), floats(g_geom(2), 32), (size_t)p.w_rows * p.w_cols, rep);
+    }
+    {   // reducer data gradient (G2 -> G1)
+        RowConvP p = base(g_geom(2), g_geom(1), 32, 32, conv3_taps(576, 24, false, -1), 1);
+        p.relumask = dummy;
+        fails += selftest_one("conv3 valid dgrad G2->G1", p, floats(g_geom(2), 32), floats(g_geom(1), 32), (size_t)p.w_rows * p.w_cols, rep);
+    }
+    {   // expConv forward: 1 tap, N = 256, ReLU
+        RowConvP p = base(pr, pr, 32, 256, chunk_taps(32), 1);
+        p.bias = dummy; p.relu = 1;
+        fails += selftest_one("pointwise 32 -> 256 (+relu)", p, floats(pr, 32), floats(pr, 256), (size_t)p.w_rows * p.w_cols, rep);
+    }
+    {   // decConv forward: K = 256 as 8 chunks, N = 32
+        RowConvP p = base(pr, pr, 256, 32, chunk_taps(256), 1);
+        p.bias = dummy;
+        fails += selftest_one("pointwise 256 -> 32", p, floats(pr, 256), floats(pr, 32), (size_t)p.w_rows * p.w_cols, rep);
+    }
+    return fails;
+}
+
+// ------------------------------------------------------------------------------------------ plan
+int tc_build_plan(pv_model* m) {
+    const pv_cfg& c = m->cfg;
+    const RowGeom pr = pr_geom();
+    const int F = m->F, EX = F * c.exp_rate;
+    for (int tr = 0; tr < 2; ++tr) {
+        Pool& P = tr ? m->pool_train : m->pool_infer;
+        P.add("xn", (size_t)m->S * m->S * m->T);
+        P.add("mn", (size_t)m->S * m->S);
+        for (int i = 0; i <= m->R; ++i) P.add(m->A(i, tr), rows_per(pr, F), rows_extra(pr, F));
+        for (int i = 0; i < m->R; ++i) {
+            P.add(m->E(i, tr), rows_per(pr, EX), rows_extra(pr, EX));
+            P.add(m->D(i, tr), rows_per(pr, F), rows_extra(pr, F));
+        }
+        for (int k = 0; k <= 4; ++k) P.add("G" + std::to_string(k), rows_per(g_geom(k), F), rows_extra(g_geom(k), F));
+        for (int i = 0; i < c.scale; ++i) {
+            const Layer& L = m->layers[m->li("residConv" + std::to_string(i + 1))];
+            P.add("q" + std::to_string(i + 1), (size_t)L.Ho * L.Wo * L.cout_s);
+        }
+        if (tr) {
+            P.add("g_a0", rows_per(pr, F), rows_extra(pr, F));
+            P.add("g_a1", rows_per(pr, F), rows_extra(pr, F));
+            P.add("g_D", rows_per(pr, F), rows_extra(pr, F));
+            P.add("g_E", rows_per(pr, EX), rows_extra(pr, EX));
+            for (int k = 0; k <= 4; ++k) P.add("g_G" + std::to_string(k), rows_per(g_geom(k), F), rows_extra(g_geom(k), F));
+            P.add("g_tail", (size_t)m->P * m->P * c.scale * c.scale);
+            for (int i = 0; i + 1 < c.scale; ++i) {
+                const Layer& L = m->layers[m->li("residConv" + std::to_string(i + 1))];
+                P.add("g_q" + std::to_string(i + 1), (size_t)L.Ho * L.Wo * L.cout_s);
+            }
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip_round, cudaStream_t st) {
+    Pool& P = tr ? m->pool_train : m->pool_infer;
+    PV_TRY(P.ensure(B));
+    PV_TRY(refresh_weights(m, st));
+    const pv_cfg& c = m->cfg;
+    const RowGeom pr = pr_geom();
+    const int F = m->F, EX = F * c.exp_rate;
+    const Taps same = conv3_taps(pr.plane, pr.pw, true, +1);
+    const Taps one = chunk_taps(32), wide = chunk_taps(EX);
+
+    PV_TRY(launch_prep(lr, B, m->S * m->S, m->T, c.mean, c.std, P["xn"], P["mn"], st));
+    const Layer& L0 = m->layers[m->li("mainConv1")];
+    PV_TRY(launch_first_conv_pr(P["xn"], m->weff + L0.weff_off, m->bias_s + L0.bias_s_off, B, m->S, m->T, P[m->A(0, tr)], pr, st));
+    for (int i = 0; i < m->R; ++i) {                                   // ResConv3D, modelsTF.py:177-189
+        const int e = m->li("expConv_" + std::to_string(i));
+        PV_TRY(conv_rows(m, m->layers[e], one, P[m->A(i, tr)], F, pr, P[m->E(i, tr)], pr, nullptr, B, "exp_fwd", st));
+        PV_TRY(conv_rows(m, m->layers[e + 1], wide, P[m->E(i, tr)], EX, pr, P[m->D(i, tr)], pr, nullptr, B, "dec_fwd", st));
+        PV_TRY(conv_rows(m, m->layers[e + 2], same, P[m->D(i, tr)], F, pr, P[m->A(i + 1, tr)], pr, P[m->A(i, tr)], B, "norm_fwd", st));
+    }
+    // ConvReduceAndUpscale (T = 9), modelsTF.py:152-164: reflect pad H,W by 1, three valid 3x3x3 + ReLU, upscale conv
+    PV_TRY(launch_pr_to_g_reflect(P[m->A(m->R, tr)], pr, P["G0"], g_geom(0), B, F, st));
+    const Taps valid = conv3_taps(576, 24, false, +1);
+    for (int k = 1; k <= 3; ++k) {
+        const Layer& L = m->layers[m->li("convReducer_" + std::to_string(k))];
+        PV_TRY(conv_rows(m, L, valid, P["G" + std::to_string(k - 1)], F, g_geom(k - 1), P["G" + std::to_string(k)], g_geom(k), nullptr, B, "reducer_fwd", st));
+    }
+    PV_TRY(conv_rows(m, m->layers[m->li("upscaleConv1")], valid, P["G3"], F, g_geom(3), P["G4"], g_geom(4), nullptr, B, "upscale_fwd", st, false));
+    const float* q = P["mn"];
+    for (int i = 0; i < c.scale; ++i) {                                // WDSRNetLRResidualPath, modelsTF.py:45-53
+        float* out = P["q" + std::to_string(i + 1)];
+        PV_TRY(conv_fwd(m, m->li("residConv" + std::to_string(i + 1)), q, out, nullptr, B, st));
+        q = out;
+    }
+    PV_TRY(launch_tail_rows(P["G4"], g_geom(4), F, q, B, m->P, c.scale, c.mean, c.std, clip_round, sr, st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ backward
+int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
+    pv_model* m = t->m;
+    Pool& P = m->pool_train;
+    const pv_cfg& c = m->cfg;
+    const RowGeom pr = pr_geom();
+    const int F = m->F, EX = F * c.exp_rate, R = m->R;
+    const Taps same = conv3_taps(pr.plane, pr.pw, true, +1), same_T = conv3_taps(pr.plane, pr.pw, true, -1);
+    const Taps valid = conv3_taps(576, 24, false, +1), valid_T = conv3_taps(576, 24, false, -1);
+    const Taps one = chunk_taps(32), wide = chunk_taps(EX);
+
+    PV_CUDA(cudaMemsetAsync(t->dweff, 0, m->nweff * sizeof(float), st));
+    PV_CUDA(cudaMemsetAsync(t->dbias_s, 0, m->nbias_s * sizeof(float), st));
+    PV_TRY(launch_tail_bwd_rows(g_sr, B, m->P, c.scale, c.std, P["g_G4"], g_geom(4), F, P["g_tail"], st));
+    {   // ---- 2-D skip path (dense kernels)
+        const float* gout = P["g_tail"];
+        for (int i = c.scale; i >= 1; --i) {
+            const int id = m->li("residConv" + std::to_string(i));
+            const float* in = (i == 1) ? P["mn"] : P["q" + std::to_string(i - 1)];
+            const float* ref = m->layers[id].relu ? P["q" + std::to_string(i)] : nullptr;
+            PV_TRY(conv_wgrad(t, id, in, gout, ref, B, st));
+            if (i > 1) {
+                float* gin = P["g_q" + std::to_string(i - 1)];
+                PV_TRY(conv_dgrad(m, id, gout, ref, gin, nullptr, B, st));
+                gout = gin;
+            }
+        }
+    }
+    {   // ---- upscale conv, then the reducers (G layouts); each dgrad applies the ReLU mask of the layer below
+        const Layer& U = m->layers[m->li("upscaleConv1")];
+        PV_TRY(wgrad_rows(t, U, valid, P["G3"], F, g_geom(3), P["g_G4"], g_geom(4), B, "upscale_wgrad", st));
+        PV_TRY(dgrad_rows(m, U, valid_T, 1, P["g_G4"], g_geom(4), P["g_G3"], g_geom(3), nullptr, P["G3"], B, "upscale_dgrad", st));
+        for (int k = 3; k >= 1; --k) {
+            const Layer& L = m->layers[m->li("convReducer_" + std::to_string(k))];
+            const std::string in = "G" + std::to_string(k - 1), gz = "g_G" + std::to_string(k), gin = "g_G" + std::to_string(k - 1);
+            PV_TRY(wgrad_rows(t, L, valid, P[in], F, g_geom(k - 1), P[gz], g_geom(k), B, "reducer_wgrad", st));
+            PV_TRY(dgrad_rows(m, L, valid_T, 1, P[gz], g_geom(k), P[gin], g_geom(k - 1), nullptr, k > 1 ? P[in] : nullptr, B, "reducer_dgrad", st));
+        }
+        PV_TRY(launch_pr_to_g_reflect_bwd(P["g_G0"], g_geom(0), P["g_a" + std::to_string(R & 1)], pr, B, F, st));
+    }
+    for (int i = R - 1; i >= 0; --i) {          // ---- residual blocks, last to first
+        const int e = m->li("expConv_" + std::to_string(i));
+        const Layer &Le = m->layers[e], &Ld = m->layers[e + 1], &Ln = m->layers[e + 2];
+        const float* G = P["g_a" + std::to_string((i + 1) & 1)];
+        float* gin = P["g_a" + std::to_string(i & 1)];
+        PV_TRY(wgrad_rows(t, Ln, same, P[m->D(i, true)], F, pr, G, pr, B, "norm_wgrad", st));
+        PV_TRY(dgrad_rows(m, Ln, same_T, 1, G, pr, P["g_D"], pr, nullptr, nullptr, B, "norm_dgrad", st));
+        PV_TRY(wgrad_rows(t, Ld, wide, P[m->E(i, true)], EX, pr, P["g_D"], pr, B, "dec_wgrad", st));
+        PV_TRY(dgrad_rows(m, Ld, one, 1, P["g_D"], pr, P["g_E"], pr, nullptr, P[m->E(i, true)], B, "dec_dgrad", st));
+        PV_TRY(wgrad_rows(t, Le, one, P[m->A(i, true)], F, pr, P["g_E"], pr, B, "exp_wgrad", st));
+        // expConv data gradient + the skip connection; block 0 flows into mainConv1's ReLU
+        PV_TRY(dgrad_rows(m, Le, one, EX / 32, P["g_E"], pr, gin, pr, G, i == 0 ? P[m->A(0, true)] : nullptr, B, "exp_dgrad", st));
+    }
+    const Layer& L0 = m->layers[m->li("mainConv1")];
+    PV_TRY(launch_first_conv_pr_wgrad(P["xn"], P["g_a0"], B, m->S, m->T, pr, t->dweff + L0.weff_off, t->dbias_s + L0.bias_s_off, st));
+    PV_TRY(launch_wn_bwd(m->wn_tab, (int)m->layers.size(), m->wn_blocks, m->params, m->scale, t->dweff, t->dbias_s, t->grads, st));
+    return 0;
+}
+
+}  // namespace pv

@@ -111,6 +111,18 @@ __device__ __forceinline__ const WnLayer& find_layer(const WnLayer* tab, int nla
     return tab[lo];
 }
 
+// row engine: TF stores taps as (dh, dw, dt) (Keras kernel [kh,kw,kt,...] on (H,W,T)); the row layouts order them (dt, dh, dw)
+__device__ __forceinline__ int row_tap(const WnLayer& L, int tap) {
+    if (L.mode == 0 || L.taps != 27) return tap;
+    const int dh = tap / 9, dw = (tap / 3) % 3, dt = tap % 3;
+    return (dt * 3 + dh) * 3 + dw;
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
 __device__ __forceinline__ float block_sum_128(float v, float* red) {
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -144,9 +156,12 @@ __global__ void __launch_bounds__(128) wn_prep_kernel(const WnLayer* __restrict_
     }
     for (int k = threadIdx.x; k < K; k += 128) {
         const int tap = k / L.cin, ci = k % L.cin;
-        const float w = v[(long long)k * L.cout + co] * sc;
-        weff[L.weff_off + ((long long)tap * L.cin_s + ci) * L.cout_s + co] = w;
-        weffT[L.weffT_off + ((long long)(L.taps - 1 - tap) * L.cout_s + co) * L.cin_s + ci] = w;
+        float w = v[(long long)k * L.cout + co] * sc;
+        if (L.round_tf32) w = to_tf32(w);
+        const int rt = row_tap(L, tap);
+        weff[L.weff_off + ((long long)rt * L.cin_s + ci) * L.cout_s + co] = w;
+        if (L.mode == 0) weffT[L.weffT_off + ((long long)(L.taps - 1 - tap) * L.cout_s + co) * L.cin_s + ci] = w;
+        else weffT[L.weffT_off + (long long)co * (L.taps * L.cin_s) + (long long)rt * L.cin_s + ci] = w;
     }
 }
 
@@ -163,7 +178,7 @@ __global__ void __launch_bounds__(128) wn_bwd_kernel(const WnLayer* __restrict__
     const float* dw = dweff + L.weff_off;
     float dot = 0.f;
     for (int k = threadIdx.x; k < K; k += 128) {
-        const int tap = k / L.cin, ci = k % L.cin;
+        const int tap = row_tap(L, k / L.cin), ci = k % L.cin;
         dot = fmaf(dw[((long long)tap * L.cin_s + ci) * L.cout_s + co], v[(long long)k * L.cout + co], dot);
     }
     dot = block_sum_128(dot, red);
@@ -174,7 +189,7 @@ __global__ void __launch_bounds__(128) wn_bwd_kernel(const WnLayer* __restrict__
     }
     const float proj = dot * rn * rn;
     for (int k = threadIdx.x; k < K; k += 128) {
-        const int tap = k / L.cin, ci = k % L.cin;
+        const int tap = row_tap(L, k / L.cin), ci = k % L.cin;
         const float d = dw[((long long)tap * L.cin_s + ci) * L.cout_s + co];
         grads[L.v_off + (long long)k * L.cout + co] = sc * (d - v[(long long)k * L.cout + co] * proj);
     }

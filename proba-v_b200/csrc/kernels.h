@@ -56,6 +56,9 @@ struct WnLayer {
     long long weff_off, weffT_off, bias_s_off, scale_off;   // offsets into the derived arenas
     int taps, cin, cout, cin_s, cout_s;
     int first_block;                          // prefix sum of cout over layers
+    int mode;                                 // 0: dense engine (TF tap order, weffT = flipped taps, [tap][co][ci])
+                                              // 1: row engine (taps in (dt,dh,dw) order, weffT = plain transpose [co][Kflat])
+    int round_tf32;                           // round the effective weights to tf32 (they only feed tensor-core MMAs)
 };
 int launch_wn_prep(const WnLayer* table_dev, int nlayers, int nblocks, const float* params, float* weff, float* weffT,
                    float* bias_s, float* scale, cudaStream_t st);

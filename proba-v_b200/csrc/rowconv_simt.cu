@@ -1,0 +1,412 @@
+// rowconv_simt.cu -- fp32 CUDA-core kernels on the row layouts of rows.h.
+//
+// These are (a) the exact-fp32 implementation of every convolution of the tensor-core engine's graph, used for the
+// layers that are not tensor-core shaped (mainConv1, Cin = 1) and as the on-device cross-check of each tcgen05
+// kernel (pv_selftest), and (b) the layout glue between the PR trunk and the valid-conv tail.
+// Reference semantics: Keras Conv3D inside TFA WeightNormalization (modelsTF.py:191-197), tf.pad REFLECT (:157-158).
+#include "rows.h"
+
+namespace pv {
+namespace {
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// ------------------------------------------------------------------------------------------ forward / data gradient
+template <int BN>
+__global__ void __launch_bounds__(256) rowconv_vec_kernel(RowConvP p) {
+    constexpr int BM = 128, BK = 16, TXN = BN / 4, TYN = 256 / TXN, TM = BM / TYN;
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN];
+    const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
+    const long long M = (long long)p.B * p.og.nrows;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int kq = tid & 3;
+    long long ibase[2];
+    bool rvalid[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const long long m = m0 + (tid >> 2) + 64 * e;
+        rvalid[e] = m < M;
+        const long long b = rvalid[e] ? m / p.og.nrows : 0;
+        const int r = p.og.row0 + (rvalid[e] ? (int)(m % p.og.nrows) : 0);
+        ibase[e] = (p.in_lead + b * p.in_pstride + r) * p.xc + kq * 4;
+    }
+    float acc[TM][4];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int tap = 0; tap < p.ntap; ++tap) {
+        const long long toff = (long long)p.off[tap] * p.xc + p.c0[tap];
+        for (int c0 = 0; c0 < p.kc; c0 += BK) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rvalid[e]) v = ldg4(p.x + ibase[e] + toff + c0);
+                const int row = (tid >> 2) + 64 * e;
+                As[kq * 4 + 0][row] = v.x; As[kq * 4 + 1][row] = v.y;
+                As[kq * 4 + 2][row] = v.z; As[kq * 4 + 3][row] = v.w;
+            }
+            if (tid < BK * BN / 4) {
+                const int kk = tid / (BN / 4), nn = (tid % (BN / 4)) * 4;
+                float4 wv;
+                if (p.w_kmajor) {
+                    const float* wp = p.w + (long long)(p.wr0[tap] + n0 + nn) * p.w_cols + p.wc0[tap] + c0 + kk;
+                    wv = make_float4(__ldg(wp), __ldg(wp + p.w_cols), __ldg(wp + 2 * p.w_cols), __ldg(wp + 3 * p.w_cols));
+                } else {
+                    wv = ldg4(p.w + (long long)(p.wr0[tap] + c0 + kk) * p.w_cols + p.wc0[tap] + n0 + nn);
+                }
+                *reinterpret_cast<float4*>(&Bs[kk][nn]) = wv;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                float a[TM];
+#pragma unroll
+                for (int i = 0; i < TM; i += 4) {
+                    const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * TM + i]);
+                    a[i] = av.x; a[i + 1] = av.y; a[i + 2] = av.z; a[i + 3] = av.w;
+                }
+                const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    acc[i][0] = fmaf(a[i], bv.x, acc[i][0]); acc[i][1] = fmaf(a[i], bv.y, acc[i][1]);
+                    acc[i][2] = fmaf(a[i], bv.z, acc[i][2]); acc[i][3] = fmaf(a[i], bv.w, acc[i][3]);
+                }
+            }
+            __syncthreads();
+        }
+    }
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias) bv = ldg4(p.bias + n0 + tx * 4);
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const long long m = m0 + ty * TM + i;
+        if (m >= M) continue;
+        const long long b = m / p.og.nrows;
+        const int r = p.og.row0 + (int)(m % p.og.nrows);
+        const long long yo = (p.og.lead + b * p.og.pstride + r) * p.n + n0 + tx * 4;
+        float4 o = make_float4(acc[i][0] + bv.x, acc[i][1] + bv.y, acc[i][2] + bv.z, acc[i][3] + bv.w);
+        if (p.residual) { const float4 q = ldg4(p.residual + yo); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (p.relumask) {
+            const float4 q = ldg4(p.relumask + yo);
+            o.x = q.x > 0.f ? o.x : 0.f; o.y = q.y > 0.f ? o.y : 0.f; o.z = q.z > 0.f ? o.z : 0.f; o.w = q.w > 0.f ? o.w : 0.f;
+        }
+        if (!row_valid(p.og, r)) o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        *reinterpret_cast<float4*>(p.y + yo) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ weight gradient
+template <int BN>
+__global__ void __launch_bounds__(256) rowwgrad_vec_kernel(RowWgradP p, int m_per_cta) {
+    constexpr int BKO = 64, BMC = 32, TXN = BN / 4, TYN = 256 / TXN, TK = BKO / TYN;
+    __shared__ __align__(16) float At[BMC][BKO + 4];
+    __shared__ __align__(16) float Ys[BMC][BN];
+    const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
+    const long long M = (long long)p.B * p.og.nrows;
+    const int k0 = blockIdx.x * BKO, n0 = blockIdx.y * BN;
+    const int Ktot = p.ntap * p.kc;
+    const long long mlo = (long long)blockIdx.z * m_per_cta;
+    long long mhi = mlo + m_per_cta; if (mhi > M) mhi = M;
+    const int kq = tid & 15;
+    const int kg = k0 + kq * 4;
+    const bool kvalid = kg < Ktot;
+    const int tap = kvalid ? kg / p.kc : 0, ci = kvalid ? kg % p.kc : 0;
+    const long long toff = (long long)p.off[tap] * p.xc + p.c0[tap] + ci;
+
+    float acc[TK][4];
+#pragma unroll
+    for (int i = 0; i < TK; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool do_bias = (blockIdx.x == 0) && (ty == 0) && p.db != nullptr;
+
+    for (long long mc = mlo; mc < mhi; mc += BMC) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int row = (tid >> 4) + 16 * e;
+            const long long m = mc + row;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < mhi && kvalid) {
+                const long long b = m / p.og.nrows;
+                const int r = p.og.row0 + (int)(m % p.og.nrows);
+                v = ldg4(p.x + (p.in_lead + b * p.in_pstride + r) * p.xc + toff);
+            }
+            *reinterpret_cast<float4*>(&At[row][kq * 4]) = v;
+        }
+        for (int f = tid; f < BMC * BN / 4; f += 256) {
+            const int row = f / (BN / 4), nn = (f % (BN / 4)) * 4;
+            const long long m = mc + row;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < mhi) {
+                const long long b = m / p.og.nrows;
+                const int r = p.og.row0 + (int)(m % p.og.nrows);
+                v = ldg4(p.gz + (p.og.lead + b * p.og.pstride + r) * p.n + n0 + nn);
+            }
+            *reinterpret_cast<float4*>(&Ys[row][nn]) = v;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int mm = 0; mm < BMC; ++mm) {
+            float a[TK];
+#pragma unroll
+            for (int i = 0; i < TK; ++i) a[i] = At[mm][ty * TK + i];
+            const float4 yv = *reinterpret_cast<const float4*>(&Ys[mm][tx * 4]);
+#pragma unroll
+            for (int i = 0; i < TK; ++i) {
+                acc[i][0] = fmaf(a[i], yv.x, acc[i][0]); acc[i][1] = fmaf(a[i], yv.y, acc[i][1]);
+                acc[i][2] = fmaf(a[i], yv.z, acc[i][2]); acc[i][3] = fmaf(a[i], yv.w, acc[i][3]);
+            }
+            if (do_bias) { bsum[0] += yv.x; bsum[1] += yv.y; bsum[2] += yv.z; bsum[3] += yv.w; }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TK; ++i) {
+        const int k = k0 + ty * TK + i;
+        if (k >= Ktot) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            atomicAdd(p.dw + (long long)(p.dwr0[k / p.kc] + k % p.kc) * p.dw_cols + p.dwc0[k / p.kc] + n0 + tx * 4 + j, acc[i][j]);
+    }
+    if (do_bias)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(p.db + n0 + tx * 4 + j, bsum[j]);
+}
+
+// ------------------------------------------------------------------------------------------ mainConv1 into PR
+// one thread per (voxel, 8 output channels); taps in (dt,dh,dw) order, zero 'same' padding by predication
+__global__ void __launch_bounds__(256) first_conv_pr_kernel(const float* __restrict__ xn, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, int B, int S, int T,
+                                                            float* __restrict__ y, RowGeom g) {
+    __shared__ float ws[27 * 32 + 32];
+    for (int i = threadIdx.x; i < 27 * 32 + 32; i += 256) ws[i] = i < 27 * 32 ? w[i] : bias[i - 27 * 32];
+    __syncthreads();
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long nvox = (long long)B * T * S * S;
+    if (idx >= nvox * 4) return;
+    const int cg = (int)(idx & 3);
+    long long v = idx >> 2;
+    const int ww = (int)(v % S); v /= S;
+    const int hh = (int)(v % S); v /= S;
+    const int tt = (int)(v % T); const long long b = v / T;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = ws[27 * 32 + cg * 8 + j];
+    for (int dt = -1; dt <= 1; ++dt) {
+        const int t2 = tt + dt; if (t2 < 0 || t2 >= T) continue;
+        for (int dh = -1; dh <= 1; ++dh) {
+            const int h2 = hh + dh; if (h2 < 0 || h2 >= S) continue;
+            for (int dw = -1; dw <= 1; ++dw) {
+                const int w2 = ww + dw; if (w2 < 0 || w2 >= S) continue;
+                const float x = __ldg(xn + ((b * S + h2) * S + w2) * T + t2);
+                const float* wr = ws + (((dt + 1) * 3 + (dh + 1)) * 3 + (dw + 1)) * 32 + cg * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(x, wr[j], acc[j]);
+            }
+        }
+    }
+    float* o = y + (g.lead + b * g.pstride + (long long)(g.t0 + tt) * g.plane + hh * g.pw + ww) * 32 + cg * 8;
+    *reinterpret_cast<float4*>(o) = make_float4(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+    *reinterpret_cast<float4*>(o + 4) = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+}
+
+// dw[tap][n] += sum_vox xn[vox + tap] * gz[row(vox)][n]; db[n] += sum gz.  lane = n, one warp walks voxels.
+__global__ void __launch_bounds__(256) first_conv_pr_wgrad_kernel(const float* __restrict__ xn, const float* __restrict__ gz,
+                                                                  int B, int S, int T, RowGeom g, float* __restrict__ dw,
+                                                                  float* __restrict__ db) {
+    __shared__ float red[8][28][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long nvox = (long long)B * T * S * S;
+    float acc[28];
+#pragma unroll
+    for (int j = 0; j < 28; ++j) acc[j] = 0.f;
+    for (long long v0 = (long long)blockIdx.x * 8 + warp; v0 < nvox; v0 += (long long)gridDim.x * 8) {
+        long long v = v0;
+        const int ww = (int)(v % S); v /= S;
+        const int hh = (int)(v % S); v /= S;
+        const int tt = (int)(v % T); const long long b = v / T;
+        const float gv = __ldg(gz + (g.lead + b * g.pstride + (long long)(g.t0 + tt) * g.plane + hh * g.pw + ww) * 32 + lane);
+        acc[27] += gv;
+#pragma unroll
+        for (int tap = 0; tap < 27; ++tap) {
+            const int t2 = tt + tap / 9 - 1, h2 = hh + (tap / 3) % 3 - 1, w2 = ww + tap % 3 - 1;
+            float x = 0.f;
+            if (t2 >= 0 && t2 < T && h2 >= 0 && h2 < S && w2 >= 0 && w2 < S) x = __ldg(xn + ((b * S + h2) * S + w2) * T + t2);
+            acc[tap] = fmaf(x, gv, acc[tap]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 28; ++j) red[warp][j][lane] = acc[j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 28 * 32; i += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) s += red[wv][i / 32][i % 32];
+        if (i < 27 * 32) atomicAdd(dw + i, s); else atomicAdd(db + (i - 27 * 32), s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ PR <-> G (reflect pad)
+__device__ __forceinline__ int refl(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+__global__ void pr_to_g_reflect_kernel(const float* __restrict__ a, RowGeom pr, float* __restrict__ g0, RowGeom gg,
+                                       long long n, int C4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = (int)(i % C4); long long r = i / C4;
+    const int w = (int)(r % gg.nw); r /= gg.nw;
+    const int h = (int)(r % gg.nh); r /= gg.nh;
+    const int t = (int)(r % gg.nt); const long long b = r / gg.nt;
+    const long long src = pr.lead + b * pr.pstride + (long long)(pr.t0 + t) * pr.plane + refl(h - 1, pr.nh) * pr.pw + refl(w - 1, pr.nw);
+    const long long dst = gg.lead + b * gg.pstride + (long long)(gg.t0 + t) * gg.plane + h * gg.pw + w;
+    reinterpret_cast<float4*>(g0)[dst * C4 + c] = __ldg(reinterpret_cast<const float4*>(a) + src * C4 + c);
+}
+
+__device__ __forceinline__ int preimages(int i, int n, int p, int (&o)[3]) {
+    int c = 0;
+    o[c++] = i + p;
+    if (i >= 1 && i <= p) o[c++] = p - i;
+    if (i <= n - 2 && i >= n - 1 - p) o[c++] = p + 2 * (n - 1) - i;
+    return c;
+}
+
+__global__ void pr_to_g_reflect_bwd_kernel(const float* __restrict__ gg0, RowGeom gg, float* __restrict__ ga, RowGeom pr,
+                                           long long n, int C4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = (int)(i % C4); long long r = i / C4;
+    const int w = (int)(r % pr.nw); r /= pr.nw;
+    const int h = (int)(r % pr.nh); r /= pr.nh;
+    const int t = (int)(r % pr.nt); const long long b = r / pr.nt;
+    int hs[3], ws[3];
+    const int nh = preimages(h, pr.nh, 1, hs), nw = preimages(w, pr.nw, 1, ws);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int x = 0; x < nh; ++x)
+        for (int y = 0; y < nw; ++y) {
+            const long long src = gg.lead + b * gg.pstride + (long long)(gg.t0 + t) * gg.plane + hs[x] * gg.pw + ws[y];
+            const float4 q = __ldg(reinterpret_cast<const float4*>(gg0) + src * C4 + c);
+            s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+        }
+    const long long dst = pr.lead + b * pr.pstride + (long long)(pr.t0 + t) * pr.plane + h * pr.pw + w;
+    reinterpret_cast<float4*>(ga)[dst * C4 + c] = s;
+}
+
+// sr[b, s*h+i, s*w+j] = (U[row(b,0,h,w)][i*s+j] + resid[b,h,w,i*s+j]) * std + mean
+__global__ void tail_rows_kernel(const float* __restrict__ u, RowGeom g, int uc, const float* __restrict__ resid, long long n,
+                                 int P, int s, float mean, float stdv, int clip_round, float* __restrict__ sr) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int PS = P * s;
+    const int X = (int)(i % PS); long long r = i / PS;
+    const int Y = (int)(r % PS); const long long b = r / PS;
+    const int c = (Y % s) * s + (X % s);
+    const long long urow = g.lead + b * g.pstride + (long long)g.t0 * g.plane + (Y / s) * g.pw + X / s;
+    float v = (__ldg(u + urow * uc + c) + __ldg(resid + ((b * P + Y / s) * P + X / s) * (s * s) + c)) * stdv + mean;
+    if (clip_round) v = rintf(fminf(fmaxf(v, 0.f), 65536.f));
+    sr[i] = v;
+}
+
+__global__ void tail_bwd_rows_kernel(const float* __restrict__ dsr, long long n, int P, int s, float stdv,
+                                     float* __restrict__ gu, RowGeom g, int uc, float* __restrict__ dtail) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // index into [B,P,P,s*s]
+    if (i >= n) return;
+    const int c = (int)(i % (s * s)); long long r = i / (s * s);
+    const int w = (int)(r % P); r /= P;
+    const int h = (int)(r % P); const long long b = r / P;
+    const int PS = P * s;
+    const float v = __ldg(dsr + (b * PS + h * s + c / s) * PS + w * s + c % s) * stdv;
+    dtail[i] = v;
+    gu[(g.lead + b * g.pstride + (long long)g.t0 * g.plane + h * g.pw + w) * uc + c] = v;
+}
+
+}  // namespace
+
+int launch_tail_rows(const float* u, RowGeom g, int uc, const float* resid, int B, int P, int scale, float mean, float stdv,
+                     int clip_round, float* sr, cudaStream_t st) {
+    const long long n = (long long)B * P * scale * P * scale;
+    PV_TIMED("tail", st, 0.0, (double)n * 12.0);
+    tail_rows_kernel<<<cdiv(n, 256), 256, 0, st>>>(u, g, uc, resid, n, P, scale, mean, stdv, clip_round, sr);
+    PV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_tail_bwd_rows(const float* dsr, int B, int P, int scale, float stdv, float* gu, RowGeom g, int uc, float* dtail, cudaStream_t st) {
+    const long long n = (long long)B * P * P * scale * scale;
+    PV_TIMED("tail_bwd", st, 0.0, (double)n * 12.0);
+    tail_bwd_rows_kernel<<<cdiv(n, 256), 256, 0, st>>>(dsr, n, P, scale, stdv, gu, g, uc, dtail);
+    PV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_rowconv_simt(const RowConvP& p, cudaStream_t st) {
+    const long long M = (long long)p.B * p.og.nrows;
+    if (M <= 0 || p.kc % 16 || p.n % 32 || p.xc % 4) return set_error(PV_ERR_BAD_ARG, "rowconv_simt: bad shape");
+    PV_TIMED(p.tag ? p.tag : "rowconv_simt", st, p.flops, 0.0);
+    if (p.n % 64 == 0) { dim3 grid(cdiv(M, 128), p.n / 64); rowconv_vec_kernel<64><<<grid, 256, 0, st>>>(p); }
+    else { dim3 grid(cdiv(M, 128), p.n / 32); rowconv_vec_kernel<32><<<grid, 256, 0, st>>>(p); }
+    PV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_rowwgrad_simt(const RowWgradP& p, cudaStream_t st) {
+    const long long M = (long long)p.B * p.og.nrows;
+    const int Ktot = p.ntap * p.kc;
+    if (M <= 0 || p.kc % 16 || p.n % 32 || p.xc % 4) return set_error(PV_ERR_BAD_ARG, "rowwgrad_simt: bad shape");
+    PV_TIMED(p.tag ? p.tag : "rowwgrad_simt", st, p.flops, 0.0);
+    const int BN = (p.n % 64 == 0) ? 64 : 32;
+    const int kt = cdiv(Ktot, 64), nt = p.n / BN;
+    int msplit = 148 * 4 / (kt * nt); if (msplit < 1) msplit = 1;
+    long long per = (M + msplit - 1) / msplit;
+    per = ((per + 31) / 32) * 32;
+    msplit = cdiv(M, per);
+    dim3 grid(kt, nt, msplit);
+    if (BN == 64) rowwgrad_vec_kernel<64><<<grid, 256, 0, st>>>(p, (int)per);
+    else rowwgrad_vec_kernel<32><<<grid, 256, 0, st>>>(p, (int)per);
+    PV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_first_conv_pr(const float* xn, const float* w, const float* bias, int B, int S, int T, float* y, RowGeom g, cudaStream_t st) {
+    const long long n = (long long)B * T * S * S * 4;
+    PV_TIMED("first_conv_pr", st, 2.0 * B * T * S * S * 27 * 32, 0.0);
+    first_conv_pr_kernel<<<cdiv(n, 256), 256, 0, st>>>(xn, w, bias, B, S, T, y, g);
+    PV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, int T, RowGeom g, float* dw, float* db, cudaStream_t st) {
+    PV_TIMED("first_conv_pr_wgrad", st, 2.0 * B * T * S * S * 27 * 32, 0.0);
+    first_conv_pr_wgrad_kernel<<<148 * 4, 256, 0, st>>>(xn, gz, B, S, T, g, dw, db);
+    PV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st) {
+    const long long n = (long long)B * gg.nt * gg.nh * gg.nw * (C / 4);
+    PV_TIMED("pr_to_g_reflect", st);
+    pr_to_g_reflect_kernel<<<cdiv(n, 256), 256, 0, st>>>(a, pr, g0, gg, n, C / 4);
+    PV_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st) {
+    const long long n = (long long)B * pr.nt * pr.nh * pr.nw * (C / 4);
+    PV_TIMED("pr_to_g_reflect_bwd", st);
+    pr_to_g_reflect_bwd_kernel<<<cdiv(n, 256), 256, 0, st>>>(gg0, gg, ga, pr, n, C / 4);
+    PV_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace pv

@@ -1,0 +1,107 @@
+// rows.h -- the "row" activation layouts of the tensor-core engine (pv_cfg.precision = 1) and the descriptors of
+// the convolutions expressed on them.
+//
+// An activation is a 2-D array [rows][C] fp32 (C = 32 or 256 channels, 128 B or 1 KB per row).  A row is one voxel.
+// Rows are ordered so that every tap of a 3x3x3 convolution is a CONSTANT row offset, which lets the tensor-core
+// kernels present each tap's A operand as a row-shifted view of one shared-memory tile (implicit GEMM without
+// im2col), and lets zero padding be real zero rows in memory:
+//
+//   PR layout  ('same' trunk: mainConv1 output, the 12 residual blocks; reference modelsTF.py:58-60,177-189)
+//       row(b,t,h,w) = lead + b*pstride + t*529 + h*23 + w        t in 0..8, h,w in 0..21
+//       column w = 22 and row h = 22 of every plane are zero, plane t = 9 of every patch is zero (pstride = 10*529):
+//       one shared zero row/column/plane serves as BOTH the left and right 'same' padding of its neighbours.
+//       tap (dt,dh,dw) in {-1,0,1}^3  ->  offset dt*529 + dh*23 + dw.
+//   G layout   (valid-conv tail: reducers + upscale conv on the reflect-padded block output; modelsTF.py:152-164)
+//       row(b,t,h,w) = lead + b*pstride + (2+t)*576 + h*24 + w    planes of 24x24, two leading zero planes per patch
+//       tap (dt,dh,dw) in {0,1,2}^3 -> offset dt*576 + dh*24 + dw (data gradient: the negated offsets, which is why
+//       the leading planes and everything outside the valid extent are kept zero).
+//
+// Invariant: rows outside the valid extent (RowGeom) are zero in every buffer a convolution reads.
+#pragma once
+#include "common.cuh"
+
+namespace pv {
+
+struct RowGeom {
+    long long lead;      // rows before patch 0
+    long long pstride;   // rows per patch
+    int plane, pw;       // rows per plane, rows per image line
+    int t0;              // first data plane inside a patch
+    int nt, nh, nw;      // valid extent
+    int row0;            // first row (inside a patch) worth computing; multiple of 128
+    int nrows;           // rows to compute per patch starting at row0 (tensor-core kernels round up to 128)
+};
+
+__host__ __device__ inline bool row_valid(const RowGeom& g, int r /* row inside the patch */) {
+    const int t = r / g.plane - g.t0;
+    const int q = r % g.plane;
+    const int h = q / g.pw, w = q % g.pw;
+    return t >= 0 && t < g.nt && h < g.nh && w < g.nw;
+}
+
+constexpr int ROW_TAIL = 2048;   // rows allocated (and zero) after the last patch of every row buffer
+constexpr int MAX_TAPS = 27;
+constexpr int MAX_SLABS = 8;
+
+// out[orow][n] = mask( act( sum_tap sum_k x[irow + off[tap]][c0[tap] + k] * w[tap][k][n] + bias[n] ) (+ res) ) (* relumask>0)
+//   orow = og.lead + b*og.pstride + r,  irow = in_lead + b*in_pstride + r,   r in [og.row0, og.row0 + og.nrows)
+struct RowConvP {
+    const float* x; int xc;            // input rows, channels per input row (row stride)
+    // weights: one 2-D fp32 matrix [w_rows][w_cols]; tap `t` uses the 32 x n block whose element (k, n) sits at
+    //   w[(wr0[t] + (w_kmajor ? n : k)) * w_cols + wc0[t] + (w_kmajor ? k : n)]
+    // w_kmajor = 1: rows are output channels, K contiguous (the tcgen05 B operand, loaded by TMA as a {32, n} box);
+    // w_kmajor = 0: rows are K, output channels contiguous (what the CUDA-core kernel prefers).
+    const float* w; int w_rows, w_cols, w_kmajor;
+    int wr0[MAX_TAPS], wc0[MAX_TAPS];
+    const float* bias;                 // [n] or nullptr
+    const float* residual;             // [rows][n] same rows as y, or nullptr
+    const float* relumask;             // [rows][n]: output multiplied by (relumask > 0), or nullptr
+    float* y; int n;                   // output rows, channels per output row
+    int B;
+    long long in_lead, in_pstride;
+    RowGeom og;
+    int ntap; int kc;                  // taps, input channels consumed per tap (32)
+    int off[MAX_TAPS];                 // row offset of each tap
+    int c0[MAX_TAPS];                  // first input channel of each tap (K-chunks of a wide row; 0 for real taps)
+    int relu;
+    int round_tf32;                    // round the stored output to tf32 (round-to-nearest) -- it only feeds MMAs
+    double flops;                      // algorithmic flops (timing report)
+    const char* tag;
+};
+
+// dw[tap][k][n] += sum_rows x[irow + off[tap]][c0[tap] + k] * gz[orow][n];   db[n] += sum_rows gz[orow][n]
+struct RowWgradP {
+    const float* x; int xc;
+    const float* gz; int n;
+    float* dw; int dw_cols;            // element (tap, k, n) at dw[(dwr0[tap] + k) * dw_cols + dwc0[tap] + n]
+    int dwr0[MAX_TAPS], dwc0[MAX_TAPS];
+    float* db;                         // [n] or nullptr
+    int B;
+    long long in_lead, in_pstride;
+    RowGeom og;
+    int ntap; int kc;
+    int off[MAX_TAPS];
+    int c0[MAX_TAPS];
+    double flops;
+    const char* tag;
+};
+
+int launch_rowconv_simt(const RowConvP& p, cudaStream_t st);
+int launch_rowwgrad_simt(const RowWgradP& p, cudaStream_t st);
+int launch_rowconv_tc(const RowConvP& p, cudaStream_t st);          // tcgen05 + TMA implicit GEMM (conv_tc.cu)
+int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, size_t partial_floats);
+
+// mainConv1 (Cin = 1, 27 taps, ReLU) from the normalised dense LR [B,S,S,T] (h,w,t order) into the PR layout
+int launch_first_conv_pr(const float* xn, const float* w /*[27][32] taps in (dt,dh,dw) order*/, const float* bias, int B, int S, int T,
+                         float* y, RowGeom g, cudaStream_t st);
+int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, int T, RowGeom g, float* dw, float* db, cudaStream_t st);
+// PR block output -> G layout with the reducer's reflect padding (tf.pad REFLECT by 1 on H and W), and its adjoint
+int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st);
+int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st);
+
+// tail on the row layouts: sr = (depth_to_space(U[:, :, :9]) + depth_to_space(resid)) * std + mean [clip, round]; and its adjoint
+int launch_tail_rows(const float* u, RowGeom g, int uc, const float* resid, int B, int P, int scale, float mean, float stdv,
+                     int clip_round, float* sr, cudaStream_t st);
+int launch_tail_bwd_rows(const float* dsr, int B, int P, int scale, float stdv, float* gu, RowGeom g, int uc, float* dtail, cudaStream_t st);
+
+}  // namespace pv

@@ -1,0 +1,106 @@
+"""GPU parity of the row-layout engines: precision "fp32_rows" (CUDA-core kernels on the tensor-core engine's layouts,
+same strict bars as the dense fp32 engine) and precision "tf32" (tcgen05 tensor-core kernels; the north_star's
+"fp32/TF32" bar of 1e-3 max relative error on SR, loss within 1e-3, cPSNR within 0.01 dB; gradient tolerance stated below).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.losses import OracleLosses
+from oracle.step import loss_and_grads
+from tests.helpers import cuda_model, oracle_and_params, rel_err
+
+pytestmark = pytest.mark.gpu
+
+SR_TOL = 1e-3
+TF32_GRAD_TOL = 2e-2      # per-tensor max error / max |grad|: tf32 operands (10-bit mantissa) through 40 layers, both directions
+
+
+def test_tensor_core_kernels_agree_with_cuda_core_kernels():
+    from probav_b200._lib import selftest
+    fails, report = selftest()
+    print(report)
+    assert fails == 0, report
+
+
+@pytest.mark.parametrize("precision", ["fp32_rows", "tf32"])
+def test_forward_small_graph(small_cfg, precision):
+    from probav_b200 import synth
+    om, p = oracle_and_params(small_cfg, seed=1)
+    m = cuda_model(small_cfg, p, precision=precision)
+    lr, _, _ = synth.make_batch(5, seed=2)
+    ref = om.forward(p, torch.from_numpy(lr).double()).numpy()
+    got = m(lr)
+    e = rel_err(got, ref)
+    print(f"{precision}: SR max rel err {e:.3e}, in sigma units {np.abs(got - ref).max() / 3160.7272:.3e}")
+    assert e < SR_TOL
+    if precision == "fp32_rows":
+        assert np.abs(got - ref).max() / 3160.7272 < 1e-3
+    got_dev = m(torch.from_numpy(lr).cuda()).cpu().numpy()
+    assert np.array_equal(got_dev, got)
+
+
+@pytest.mark.parametrize("precision", ["fp32_rows", "tf32"])
+def test_forward_full_graph(full_cfg, precision):
+    from probav_b200 import synth
+    om, p = oracle_and_params(full_cfg, seed=4)
+    m = cuda_model(full_cfg, p, precision=precision)
+    lr, _, _ = synth.make_batch(3, seed=6)
+    ref = om.forward(p, torch.from_numpy(lr).double()).numpy()
+    got = m(lr)
+    e = rel_err(got, ref)
+    print(f"{precision}: SR max rel err {e:.3e}, in sigma units {np.abs(got - ref).max() / 3160.7272:.3e}")
+    assert e < SR_TOL
+
+
+def _trainer(pb, m):
+    import tempfile
+    L = pb.Losses((48, 48, 1))
+    d = tempfile.mkdtemp(prefix="pv_")
+    return pb.ModelTrainer(m, L.shiftCompensatedL1Loss, L.shiftCompensatedcPSNR, pb.Nadam(5e-4), d + "/ckpt", d + "/log")
+
+
+@pytest.mark.parametrize("precision,cfgname,B", [("fp32_rows", "small", 4), ("fp32_rows", "full", 2), ("tf32", "small", 4), ("tf32", "full", 2)])
+def test_gradients(small_cfg, full_cfg, precision, cfgname, B):
+    import probav_b200 as pb
+    from probav_b200 import synth
+    cfg = small_cfg if cfgname == "small" else full_cfg
+    om, p = oracle_and_params(cfg, seed=10)
+    m = cuda_model(cfg, p, precision=precision)
+    lr, hr, mask = synth.make_batch(B, seed=11, hr_zero_under_mask=True)
+    ol = OracleLosses((48, 48, 1))
+    loss, g, sr, cps = loss_and_grads(om, ol, p, torch.from_numpy(lr).double(), torch.from_numpy(hr).double(), torch.from_numpy(mask))
+    t = _trainer(pb, m)
+    lossv, psnrv = t.forward_backward(lr, hr, mask)
+    assert abs(lossv - float(loss)) < 1e-3 * abs(float(loss))
+    assert abs(psnrv - float(cps.mean())) < 0.01
+    got = t.get_grads()
+    tol = 1e-3 if precision == "fp32_rows" else TF32_GRAD_TOL
+    worst, worst_k = 0.0, None
+    for k, ref in g.items():
+        if np.abs(ref.numpy()).max() == 0:
+            continue
+        e = rel_err(got[k], ref.numpy())
+        if e > worst:
+            worst, worst_k = e, k
+    print(f"{precision}/{cfgname}: worst gradient rel err {worst:.3e} at {worst_k}")
+    assert worst < tol, (worst, worst_k)
+
+
+def test_train_step_tf32_tracks_oracle(small_cfg):
+    import probav_b200 as pb
+    from oracle.optim import OracleNadam
+    from oracle.step import train_step
+    from probav_b200 import synth
+    om, p = oracle_and_params(small_cfg, seed=20)
+    m = cuda_model(small_cfg, p, precision="tf32")
+    t = _trainer(pb, m)
+    oopt = OracleNadam(5e-4)
+    ol = OracleLosses((48, 48, 1))
+    params = p
+    for step in range(3):
+        lr, hr, mask = synth.make_batch(4, seed=30 + step, hr_zero_under_mask=True)
+        params, loss, cps, _ = train_step(om, ol, oopt, params, torch.from_numpy(lr).double(), torch.from_numpy(hr).double(), torch.from_numpy(mask))
+        lossv, psnrv = t.trainStep(lr, hr, mask)
+        assert abs(lossv - float(loss)) < 2e-3 * abs(float(loss)), step
+        assert abs(psnrv - float(cps.mean())) < 0.02, step
