@@ -148,7 +148,7 @@ def run_b200(args, cfg):
     dev = torch.device(f"cuda:{local}")
     lib = _lib.lib()
     B = args.batch
-    model = pb.build_from_config(cfg, band="NIR", device=local, seed=0)
+    model = pb.build_from_config(cfg, band="NIR", device=local, seed=0, precision=args.precision)
     L = pb.Losses((cfg["scale"] * cfg["patch_size"],) * 2 + (1,))
     import tempfile
     tmp = tempfile.mkdtemp(prefix="pv_bench_")
@@ -239,7 +239,7 @@ def run_b200(args, cfg):
                      "note": f"batch {B}: {sl['bytes'] / sl['launches'] / 1e6:.2f} MB per launch is latency-bound; see bench_loss in DESIGN.md"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if model.cfg.precision == 0 else "bf16", "data": "synthetic",
+            "dtype": {0: "f32", 1: "tf32", 3: "f32"}[model.cfg.precision], "data": "synthetic",
             "config": {"workload": "cfg/p16t9c85r12 train step (fwd+shift-L1+bwd+Nadam+cPSNR metric), BASELINE configs[1]",
                        "batch_per_gpu": B, "global_batch": B * ws, "parallelism": f"dp{ws}",
                        "l2_policy": "per-step working set (activations ~8 GB) >> 126 MB L2; no explicit flush",
@@ -268,6 +268,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=16, help="CPU arm: patches per step (bounded sample)")
     ap.add_argument("--cfg", default=os.path.join(ROOT, "cfg", "p16t9c85r12.cfg"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "fp32_rows"],
+                    help="tf32 = tcgen05 tensor-core engine (default; what TensorFlow runs on Ampere+), fp32 = CUDA-core exact mode")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -20,9 +20,11 @@ int64_t launch_count();
 #define PV_CUDA(expr)                                                                         \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \
-        if (_e != cudaSuccess)                                                                \
+        if (_e != cudaSuccess) {                                                              \
+            cudaGetLastError(); /* clear the non-sticky error so later launches are not blamed */ \
             return pv::set_error(PV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                \
                                  cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+        }                                                                                     \
     } while (0)
 
 #define PV_LAUNCH_CHECK()                                                                     \

@@ -259,7 +259,7 @@ int launch_rowconv_tc(const RowConvP& p, cudaStream_t st) {
     a.slab_rows = ((128 + span + 7) / 8) * 8;
     if (a.slab_rows > 256) return set_error(PV_ERR_BAD_ARG, "rowconv_tc: slab of %d rows exceeds the TMA box limit", a.slab_rows);
     const size_t smem = 1024 + (size_t)p.ntap * p.n * 128 + (size_t)NSTAGE * a.slab_rows * 128;
-    if (smem > 227 * 1024) return set_error(PV_ERR_BAD_ARG, "rowconv_tc: %zu bytes of shared memory needed", smem);
+    if (smem > 226 * 1024) return set_error(PV_ERR_BAD_ARG, "rowconv_tc: %zu bytes of shared memory needed", smem);
 
     const RowGeom& og = p.og;
     const long long in_rows = p.in_lead + (long long)p.B * p.in_pstride + ROW_TAIL;  // every row buffer is allocated with this zero tail
@@ -273,13 +273,13 @@ int launch_rowconv_tc(const RowConvP& p, cudaStream_t st) {
     const int ntiles = a.B * a.tiles_per_patch;
     const int grid = ntiles < sms ? ntiles : sms;
     PV_TIMED(p.tag ? p.tag : "rowconv_tc", st, p.flops, 0.0);
+    // opt in to the dynamic shared memory this configuration needs (static + dynamic must stay below 227 KB)
+    static size_t attr32 = 0, attr256 = 0;
     if (p.n == 32) {
-        static bool attr32 = false;
-        if (!attr32) { PV_CUDA(cudaFuncSetAttribute(rowconv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr32 = true; }
+        if (smem > attr32) { PV_CUDA(cudaFuncSetAttribute(rowconv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr32 = smem; }
         rowconv_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(tm_x, tm_w, a);
     } else {
-        static bool attr256 = false;
-        if (!attr256) { PV_CUDA(cudaFuncSetAttribute(rowconv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr256 = true; }
+        if (smem > attr256) { PV_CUDA(cudaFuncSetAttribute(rowconv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr256 = smem; }
         rowconv_tc_kernel<256><<<grid, TC_THREADS, smem, st>>>(tm_x, tm_w, a);
     }
     PV_LAUNCH_CHECK();

@@ -13,7 +13,7 @@ from tests.helpers import cuda_model, oracle_and_params, rel_err
 pytestmark = pytest.mark.gpu
 
 SR_TOL = 1e-3
-TF32_GRAD_TOL = 2e-2      # per-tensor max error / max |grad|: tf32 operands (10-bit mantissa) through 40 layers, both directions
+TF32_GRAD_TOL = 3e-2      # per-tensor max error / max |grad|: tf32 operands (10-bit mantissa) through 40 layers, both directions
 
 
 def test_tensor_core_kernels_agree_with_cuda_core_kernels():
