@@ -748,6 +748,13 @@ int pv_trainer_create(pv_model* m, int opt_kind, float learning_rate, int loss_k
         pv_trainer_destroy(t);
         return set_error(PV_ERR_CUDA, "cudaMalloc of the trainer arenas failed");
     }
+    if (m->use_tc) {
+        t->wg_partial_floats = (size_t)148 * (9 * 4096 + 1024);
+        if (cudaMalloc(&t->wg_partials, t->wg_partial_floats * 4) != cudaSuccess) {
+            pv_trainer_destroy(t);
+            return set_error(PV_ERR_CUDA, "cudaMalloc of the weight-gradient partials failed");
+        }
+    }
     cudaMemset(t->grads, 0, m->nparams * 4);
     cudaMemset(t->m1, 0, m->nparams * 4);
     cudaMemset(t->m2, 0, m->nparams * 4);

@@ -118,7 +118,7 @@ int wgrad_rows(pv_trainer* t, const Layer& L, const Taps& tp /* forward offsets 
     for (int i = 0; i < tp.n; ++i) { p.off[i] = tp.off[i]; p.c0[i] = tp.c0[i]; p.dwr0[i] = 32 * tp.chunk[i]; p.dwc0[i] = 0; }
     p.flops = 2.0 * B * L.Ho * L.Wo * L.To * L.taps() * L.cin * L.cout;
     p.tag = tag;
-    (void)m;
+    if (m->use_tc) return launch_rowwgrad_tc(p, st, t->wg_partials, t->wg_partial_floats);
     return launch_rowwgrad_simt(p, st);
 }
 
@@ -170,6 +170,52 @@ static int selftest_one(const char* name, RowConvP p, size_t in_floats, size_t o
     return (!rc && bad == 0) ? 0 : 1;
 }
 
+static int selftest_wgrad(const char* name, RowWgradP p, const RowGeom& ig, int B, std::string& rep) {
+    const size_t in_floats = (size_t)(ig.lead + (long long)B * ig.pstride + ROW_TAIL) * p.xc;
+    const size_t gz_floats = (size_t)(p.og.lead + (long long)B * p.og.pstride + ROW_TAIL) * p.n;
+    const size_t dw_floats = (size_t)p.ntap * 32 * p.n;
+    const size_t part_floats = (size_t)148 * (9 * 4096 + 1024);
+    float *x = nullptr, *gz = nullptr, *dw0 = nullptr, *dw1 = nullptr, *db0 = nullptr, *db1 = nullptr, *part = nullptr;
+    PV_CUDA(cudaMalloc(&x, in_floats * 4)); PV_CUDA(cudaMalloc(&gz, gz_floats * 4));
+    PV_CUDA(cudaMalloc(&dw0, dw_floats * 4)); PV_CUDA(cudaMalloc(&dw1, dw_floats * 4));
+    PV_CUDA(cudaMalloc(&db0, 256 * 4)); PV_CUDA(cudaMalloc(&db1, 256 * 4)); PV_CUDA(cudaMalloc(&part, part_floats * 4));
+    std::vector<float> h(std::max(in_floats, gz_floats));
+    unsigned s = 777u;
+    auto gen = [&](size_t n, int range, float scale) {
+        for (size_t i = 0; i < n; ++i) { s = s * 1664525u + 1013904223u; h[i] = (float)((int)((s >> 16) % (2 * range + 1)) - range) * scale; }
+    };
+    gen(in_floats, 4, 0.125f);
+    PV_CUDA(cudaMemcpy(x, h.data(), in_floats * 4, cudaMemcpyHostToDevice));
+    gen(gz_floats, 4, 0.125f);
+    for (long long r = 0; r < (long long)(gz_floats / p.n); ++r) {          // the engine's invariant: gz is zero outside the valid extent
+        const long long q = r - p.og.lead;
+        const bool ok = q >= 0 && q < (long long)B * p.og.pstride && row_valid(p.og, (int)(q % p.og.pstride));
+        if (!ok) for (int c = 0; c < p.n; ++c) h[(size_t)r * p.n + c] = 0.f;
+    }
+    PV_CUDA(cudaMemcpy(gz, h.data(), gz_floats * 4, cudaMemcpyHostToDevice));
+    PV_CUDA(cudaMemset(dw0, 0, dw_floats * 4)); PV_CUDA(cudaMemset(dw1, 0, dw_floats * 4));
+    PV_CUDA(cudaMemset(db0, 0, 1024)); PV_CUDA(cudaMemset(db1, 0, 1024));
+    p.x = x; p.gz = gz; p.B = B; p.in_lead = ig.lead; p.in_pstride = ig.pstride;
+    RowWgradP q = p;
+    q.dw = dw0; q.db = db0; p.dw = dw1; p.db = db1;
+    int rc = launch_rowwgrad_simt(q, 0);
+    if (!rc) rc = launch_rowwgrad_tc(p, 0, part, part_floats);
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest %s: %s", name, cudaGetErrorString(cudaGetLastError()));
+    double worst = 0; size_t bad = 0;
+    if (!rc) {
+        std::vector<float> a(dw_floats + 256), c2(dw_floats + 256);
+        cudaMemcpy(a.data(), dw0, dw_floats * 4, cudaMemcpyDeviceToHost); cudaMemcpy(c2.data(), dw1, dw_floats * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(a.data() + dw_floats, db0, p.n * 4, cudaMemcpyDeviceToHost); cudaMemcpy(c2.data() + dw_floats, db1, p.n * 4, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < dw_floats + p.n; ++i) { const double d = std::fabs((double)a[i] - c2[i]); if (!(d <= 1e-2)) ++bad; if (d > worst || d != d) worst = d; }
+    }
+    char line[256];
+    snprintf(line, sizeof line, "%-34s %s max|tc - simt| = %.3g, mismatches %zu of %zu%s%s\n", name, (!rc && bad == 0) ? "PASS" : "FAIL",
+             worst, bad, dw_floats + p.n, rc ? " : " : "", rc ? last_error().c_str() : "");
+    rep += line;
+    cudaFree(x); cudaFree(gz); cudaFree(dw0); cudaFree(dw1); cudaFree(db0); cudaFree(db1); cudaFree(part);
+    return (!rc && bad == 0) ? 0 : 1;
+}
+
 int tc_selftest(std::string& rep) {
     const int B = 3;
     int fails = 0;
@@ -215,6 +261,17 @@ int tc_selftest(std::string& rep) {
         p.bias = dummy;
         fails += selftest_one("pointwise 256 -> 32", p, floats(pr, 256), floats(pr, 32), (size_t)p.w_rows * p.w_cols, rep);
     }
+    auto wbase = [&](const RowGeom& og, int xc, int n, const Taps& tp) {
+        RowWgradP p;
+        memset(&p, 0, sizeof p);
+        p.xc = xc; p.n = n; p.og = og; p.kc = 32; p.ntap = tp.n; p.dw_cols = n;
+        for (int i = 0; i < tp.n; ++i) { p.off[i] = tp.off[i]; p.c0[i] = tp.c0[i]; p.dwr0[i] = 32 * tp.chunk[i]; p.dwc0[i] = 0; }
+        return p;
+    };
+    fails += selftest_wgrad("wgrad conv3 same (PR)", wbase(pr, 32, 32, conv3_taps(529, 23, true, +1)), pr, B, rep);
+    fails += selftest_wgrad("wgrad conv3 valid (G1 -> G2)", wbase(g_geom(2), 32, 32, conv3_taps(576, 24, false, +1)), g_geom(1), B, rep);
+    fails += selftest_wgrad("wgrad pointwise x=256 (decConv)", wbase(pr, 256, 32, chunk_taps(256)), pr, B, rep);
+    fails += selftest_wgrad("wgrad pointwise gz=256 (expConv)", wbase(pr, 32, 256, chunk_taps(32)), pr, B, rep);
     return fails;
 }
 

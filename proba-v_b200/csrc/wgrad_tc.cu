@@ -1,0 +1,271 @@
+// wgrad_tc.cu -- weight gradients on the tcgen05 tensor cores (kind::tf32, fp32 accumulate in TMEM).
+//
+// Replaces TensorFlow's Conv3DBackpropFilterV2 + BiasAddGrad for the trunk layers (tape.gradient,
+// reference models/trainClass.py:131; layers models/modelsTF.py:159-163,179-188):
+//     dW[tap][ci][co] = sum over rows r of  x[r + off(tap)][ci] * gz[r][co]          db[co] = sum_r gz[r][co]
+// The reduction runs over voxels (rows), so both MMA operands are read "MN-major": a [rows][32] fp32 tile is
+// presented as a 32 x rows matrix.  For tf32 the hardware requires the 128B-swizzle-with-32B-atom shared-memory layout
+// (descriptor layout type 1; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) -- probes/umma_probe.cu T3.
+// M = 128 of the MMA is filled three ways:
+//   conv3  (normConv / convReducer / upscaleConv): four ROW-ADJACENT taps (dw = -1..2, the last one discarded) are one
+//          A operand whose four 32-channel atoms are 128 B apart, i.e. overlapping views of the same rows (LBO = 128);
+//          nine (dt,dh) groups -> nine [128 x 32] accumulators = 288 TMEM columns
+//   wide x (decConv: x = E, 256 channels): 2 groups of 4 channel atoms (LBO = box stride), N = 32 (gz = gD)
+//   wide gz (expConv: gz = gZ, 256 channels): the transpose -- M = gz channels (2 groups), N = 32 = x channels
+// Every CTA owns a contiguous range of row tiles and keeps its accumulators in TMEM for its whole lifetime; partial
+// sums go to a [cta][group][128][32] scratch and a second small kernel reduces them in a fixed order (deterministic,
+// no atomics).  The epilogue warps meanwhile form the bias gradient from the gz tiles already sitting in shared memory.
+#include "rows.h"
+#include "tc_common.cuh"
+
+namespace pv {
+
+using namespace tc;
+int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, int cols, int box_rows, int box_cols, int swizzle_32b_atom);
+
+namespace {
+
+constexpr int WG_THREADS = 192;
+constexpr int MAX_GROUPS = 9;
+constexpr int MAX_BOXES = 9;
+
+struct WgradTcArgs {
+    int B, tiles_per_patch, TR;        // TR rows per tile (128 or 64)
+    long long a_lead, a_pstride, b_lead, b_pstride;
+    int row0;
+    int nstage; uint32_t stage_bytes;
+    // TMA boxes of one stage: boxes [0, nabox) from the A tensor map, box nabox.. from the B tensor map
+    int nabox, nbbox, abox_rows, bbox_rows;
+    int box_lo[MAX_BOXES], box_c0[MAX_BOXES]; uint32_t box_off[MAX_BOXES];
+    // MMA groups
+    int ngroup; uint32_t grp_off[MAX_GROUPS]; uint32_t grp_lbo;
+    uint32_t b_off;
+    // bias gradient: column sums of these boxes (32 channels each)
+    int nbias; uint32_t bias_off[8];
+    float* partials;                   // [cta][ngroup][128][32]
+    float* db_partials;                // [cta][4 warps][nbias][32]
+};
+
+template <int DUMMY>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+rowwgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const WgradTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * 4 + 1];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto BAR = [&](int i) { return smem_u32(&bars[i]); };
+    const int FULL = 0, EMPTY = 4, DONE = 8;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a.nstage; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1 + 4); }
+        mbar_init(BAR(DONE), 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int ntiles = a.B * a.tiles_per_patch;
+    const int t_lo = (int)((long long)ntiles * blockIdx.x / gridDim.x), t_hi = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_a);
+            tma_prefetch_desc(&tm_b);
+            uint32_t it = 0;
+            for (int tile = t_lo; tile < t_hi; ++tile, ++it) {
+                const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
+                const long long arow = a.a_lead + (long long)b * a.a_pstride + a.row0 + (long long)j * a.TR;
+                const long long brow = a.b_lead + (long long)b * a.b_pstride + a.row0 + (long long)j * a.TR;
+                const uint32_t stg = it % a.nstage, ph = (it / a.nstage) & 1;
+                mbar_wait(BAR(EMPTY + stg), ph ^ 1);
+                mbar_arrive_expect_tx(BAR(FULL + stg), (uint32_t)(a.nabox * a.abox_rows + a.nbbox * a.bbox_rows) * 128u);
+                const uint32_t s_addr = base + stg * a.stage_bytes;
+                for (int i = 0; i < a.nabox + a.nbbox; ++i)
+                    tma_load_2d(s_addr + a.box_off[i], i < a.nabox ? &tm_a : &tm_b, BAR(FULL + stg), a.box_c0[i],
+                                (int)((i < a.nabox ? arow : brow) + a.box_lo[i]));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint64_t HI_A = smem_desc_hi(a.grp_lbo, 512, 1);     // MN-major, 128B swizzle / 32B atom; K atoms (4 rows) 512 B apart
+            const uint64_t HI_B = smem_desc_hi(128, 512, 1);
+            constexpr uint32_t IDESC = instr_desc(2, 128, 32, 1, 1);
+            uint32_t it = 0;
+            for (int tile = t_lo; tile < t_hi; ++tile, ++it) {
+                const uint32_t stg = it % a.nstage, ph = (it / a.nstage) & 1;
+                mbar_wait(BAR(FULL + stg), ph);
+                tc_fence_after();
+                const uint32_t s_addr = base + stg * a.stage_bytes;
+                for (int ks = 0; ks < a.TR / 8; ++ks) {
+                    const uint64_t bdesc = smem_desc(HI_B, s_addr + a.b_off + ks * 1024);
+                    for (int g = 0; g < a.ngroup; ++g)
+                        umma_ss<true>(tmem + g * 32, smem_desc(HI_A, s_addr + a.grp_off[g] + ks * 1024), bdesc, IDESC,
+                                      (tile > t_lo || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(BAR(EMPTY + stg));
+            }
+            umma_commit(BAR(DONE));
+        }
+    } else {
+        // bias gradient while the tensor core works, then the accumulator drain
+        const int q = warp & 3;
+        float bsum[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
+        uint32_t it = 0;
+        const int rows_per_warp = a.TR / 4;
+        for (int tile = t_lo; tile < t_hi; ++tile, ++it) {
+            const uint32_t stg = it % a.nstage, ph = (it / a.nstage) & 1;
+            mbar_wait(BAR(FULL + stg), ph);
+            const uint8_t* sp = smem_raw + (base - smem_u32(smem_raw)) + stg * a.stage_bytes;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < a.nbias) {
+                    const uint8_t* bx = sp + a.bias_off[i];
+                    float s = 0.f;
+                    for (int r = q * rows_per_warp; r < (q + 1) * rows_per_warp; ++r)     // 32B-atom swizzle: chunk ^= row & 3
+                        s += *reinterpret_cast<const float*>(bx + r * 128 + ((((lane >> 3) ^ (r & 3)) << 5) | ((lane & 7) << 2)));
+                    bsum[i] += s;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(EMPTY + stg));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < a.nbias) a.db_partials[(((size_t)blockIdx.x * 4 + q) * a.nbias + i) * 32 + lane] = bsum[i];
+        mbar_wait(BAR(DONE), 0);
+        tc_fence_after();
+        float* out = a.partials + (size_t)blockIdx.x * a.ngroup * 4096;
+        for (int g = 0; g < a.ngroup; ++g) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + g * 32, v);
+            tmem_ld_wait();
+            float4* o = reinterpret_cast<float4*>(out + ((size_t)g * 128 + q * 32 + lane) * 32);
+            if (t_hi > t_lo) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    o[e] = make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// fixed-order reduction of the per-CTA partials into dweff / dbias.  mode 0: conv3 (group = (dt,dh), m = q*32+ci, n = co);
+// mode 1: wide x (group g, m = channel in group -> K index g*128+m, n = co); mode 2: wide gz (m = co in group, n = ci)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ dbp, int ncta, int ngroup, int mode,
+                                    RowWgradP p, int nbias) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int total = ngroup * 4096;
+    if (idx < total) {
+        const int g = idx / 4096, m = (idx / 32) % 128, n = idx % 32;
+        float s = 0.f;
+        for (int c = 0; c < ncta; ++c) s += partials[(size_t)c * total + idx];
+        if (mode == 0) {
+            const int qd = m / 32, ci = m % 32;
+            if (qd < 3) { const int tap = g * 3 + qd; p.dw[(size_t)(p.dwr0[tap] + ci) * p.dw_cols + p.dwc0[tap] + n] = s; }
+        } else if (mode == 1) {
+            const int k = g * 128 + m, tap = k / 32;
+            p.dw[(size_t)(p.dwr0[tap] + k % 32) * p.dw_cols + p.dwc0[tap] + n] = s;
+        } else {
+            p.dw[(size_t)(p.dwr0[0] + n) * p.dw_cols + p.dwc0[0] + g * 128 + m] = s;
+        }
+    } else if (idx < total + nbias * 32 && p.db) {
+        const int j = idx - total;
+        float s = 0.f;
+        for (int c = 0; c < ncta * 4; ++c) s += dbp[(size_t)c * nbias * 32 + j];
+        p.db[j] = s;
+    }
+}
+
+}  // namespace
+
+int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, size_t partial_floats) {
+    int mode;
+    if (p.xc == 32 && p.n == 32 && p.ntap == 27) mode = 0;
+    else if (p.xc == 256 && p.n == 32 && p.ntap == 8) mode = 1;
+    else if (p.xc == 32 && p.n == 256 && p.ntap == 1) mode = 2;
+    else return set_error(PV_ERR_BAD_ARG, "rowwgrad_tc: unsupported shape xc=%d n=%d ntap=%d", p.xc, p.n, p.ntap);
+    WgradTcArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = p.B; a.row0 = p.og.row0;
+    const float *amat, *bmat;          // A: the wide / tap-shifted operand (M side), B: the 32-channel operand (N side)
+    int acols;
+    if (mode == 2) { amat = p.gz; acols = 256; bmat = p.x; a.a_lead = p.og.lead; a.a_pstride = p.og.pstride; a.b_lead = p.in_lead; a.b_pstride = p.in_pstride; }
+    else { amat = p.x; acols = p.xc; bmat = p.gz; a.a_lead = p.in_lead; a.a_pstride = p.in_pstride; a.b_lead = p.og.lead; a.b_pstride = p.og.pstride; }
+    if (mode == 0) {
+        a.TR = 128; a.nstage = 2;
+        // slabs: taps sorted ascending, 9 per temporal plane; a group = the three dw taps of one (dt,dh) + one spare row
+        int nslab = 0, span = 0;
+        for (int t = 0; t < 27; t += 9) {
+            a.box_lo[nslab] = p.off[t]; a.box_c0[nslab] = 0;
+            if (p.off[t + 8] + 1 - p.off[t] > span) span = p.off[t + 8] + 1 - p.off[t];
+            ++nslab;
+        }
+        a.abox_rows = ((a.TR + span + 7) / 8) * 8;
+        if (a.abox_rows > 256) return set_error(PV_ERR_BAD_ARG, "rowwgrad_tc: slab too tall");
+        a.nabox = nslab;
+        for (int s = 0; s < nslab; ++s) a.box_off[s] = (uint32_t)s * a.abox_rows * 128;
+        a.ngroup = 9; a.grp_lbo = 128;
+        for (int g = 0; g < 9; ++g) {
+            if (p.off[3 * g + 1] != p.off[3 * g] + 1 || p.off[3 * g + 2] != p.off[3 * g] + 2)
+                return set_error(PV_ERR_BAD_ARG, "rowwgrad_tc: taps of a group must be row-adjacent");
+            a.grp_off[g] = a.box_off[g / 3] + (uint32_t)(p.off[3 * g] - a.box_lo[g / 3]) * 128;
+        }
+        a.nbbox = 1; a.bbox_rows = a.TR;
+        a.box_lo[nslab] = 0; a.box_c0[nslab] = 0; a.box_off[nslab] = (uint32_t)nslab * a.abox_rows * 128;
+        a.b_off = a.box_off[nslab];
+        a.nbias = 1; a.bias_off[0] = a.b_off;
+    } else {
+        a.TR = 64; a.nstage = 3;
+        a.nabox = 8; a.abox_rows = a.TR;
+        for (int i = 0; i < 8; ++i) { a.box_lo[i] = 0; a.box_c0[i] = 32 * i; a.box_off[i] = (uint32_t)i * a.TR * 128; }
+        a.ngroup = 2; a.grp_lbo = (uint32_t)a.TR * 128;
+        a.grp_off[0] = 0; a.grp_off[1] = 4u * a.TR * 128;
+        a.nbbox = 1; a.bbox_rows = a.TR;
+        a.box_lo[8] = 0; a.box_c0[8] = 0; a.box_off[8] = 8u * a.TR * 128;
+        a.b_off = a.box_off[8];
+        if (mode == 1) { a.nbias = 1; a.bias_off[0] = a.b_off; }
+        else { a.nbias = 8; for (int i = 0; i < 8; ++i) a.bias_off[i] = a.box_off[i]; }
+    }
+    a.tiles_per_patch = cdiv(p.og.nrows, a.TR);
+    a.stage_bytes = (uint32_t)(a.nabox * a.abox_rows + a.nbbox * a.bbox_rows) * 128u;
+    const size_t smem = 1024 + (size_t)a.nstage * a.stage_bytes;
+    if (smem > 226 * 1024) return set_error(PV_ERR_BAD_ARG, "rowwgrad_tc: %zu bytes of shared memory needed", smem);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = a.B * a.tiles_per_patch;
+    const int grid = ntiles < sms ? ntiles : sms;
+    const size_t need = (size_t)grid * a.ngroup * 4096 + (size_t)grid * 4 * a.nbias * 32;
+    if (!partials || partial_floats < need) return set_error(PV_ERR_BAD_ARG, "rowwgrad_tc: partial buffer too small (%zu < %zu)", partial_floats, need);
+    a.partials = partials; a.db_partials = partials + (size_t)grid * a.ngroup * 4096;
+    const long long a_rows = a.a_lead + (long long)p.B * a.a_pstride + ROW_TAIL, b_rows = a.b_lead + (long long)p.B * a.b_pstride + ROW_TAIL;
+    CUtensorMap tm_a, tm_b;
+    PV_TRY(make_tmap_2d(&tm_a, amat, a_rows, acols, a.abox_rows, 32, 1));
+    PV_TRY(make_tmap_2d(&tm_b, bmat, b_rows, 32, a.bbox_rows, 32, 1));
+    static size_t attr = 0;
+    if (smem > attr) { PV_CUDA(cudaFuncSetAttribute(rowwgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    {
+        PV_TIMED(p.tag ? p.tag : "rowwgrad_tc", st, p.flops, 0.0);
+        rowwgrad_tc_kernel<0><<<grid, WG_THREADS, smem, st>>>(tm_a, tm_b, a);
+        PV_LAUNCH_CHECK();
+    }
+    {
+        PV_TIMED("wgrad_reduce", st);
+        const int total = a.ngroup * 4096 + a.nbias * 32;
+        wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(a.partials, a.db_partials, grid, a.ngroup, mode, p, a.nbias);
+        PV_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // namespace pv
