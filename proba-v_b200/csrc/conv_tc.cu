@@ -114,7 +114,7 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 
     if (warp == 0) {
         // ================================================================== TMA producer
-        if (lane == 0) {
+        if (elect_one_sync()) {
             tma_prefetch_desc(&tm_x);
             tma_prefetch_desc(&tm_w);
             mbar_arrive_expect_tx(BAR(WBAR), (uint32_t)a.ntap * W_TAP_BYTES);
@@ -133,7 +133,7 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         }
     } else if (warp == 1) {
         // ================================================================== MMA issuer (one thread)
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint64_t HI = smem_desc_hi(16, 1024, 2);          // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
             constexpr uint32_t IDESC = instr_desc(2, 128, NOUT, 0, 0);  // tf32 x tf32 -> f32, M = 128, N = NOUT
             mbar_wait(BAR(WBAR), 0);
@@ -151,11 +151,12 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                     tc_fence_after();
                     const uint32_t s_addr = st_smem + stg * stage_bytes;
                     for (int t = a.slab_tap0[s]; t < a.slab_tap0[s + 1]; ++t) {
-                        const uint32_t a_addr = s_addr + (uint32_t)a.tap_row[t] * 128u;
-                        const uint32_t b_addr = w_smem + (uint32_t)t * W_TAP_BYTES;
+                        // descriptors differ only in their 14-bit start-address field: +2 (= 32 B >> 4) per K8 step
+                        const uint64_t adesc = smem_desc(HI, s_addr + (uint32_t)a.tap_row[t] * 128u);
+                        const uint64_t bdesc = smem_desc(HI, w_smem + (uint32_t)t * W_TAP_BYTES);
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {                 // 32 channels = 4 x K8
-                            umma_ss<true>(d_tmem, smem_desc(HI, a_addr + ks * 32), smem_desc(HI, b_addr + ks * 32), IDESC, accumulate);
+                            umma_ss<true>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, IDESC, accumulate);
                             accumulate = 1;
                         }
                     }
@@ -175,6 +176,16 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const bool in_patch = r < a.og.row0 + a.og.nrows && r < a.og.pstride;
             const bool valid = in_patch && row_valid(a.og, r);
             const long long orow = a.og.lead + (long long)b * a.og.pstride + r;
+            // N = 32: fetch this row's residual / ReLU-mask operands BEFORE waiting for the accumulator, so their
+            // global-memory latency overlaps the MMAs of this tile instead of serialising behind them
+            float4 pre_r[8], pre_m[8];
+            if (NOUT == 32) {
+#pragma unroll
+                for (int g4 = 0; g4 < 8; ++g4) {
+                    pre_r[g4] = (a.residual && in_patch) ? __ldg(reinterpret_cast<const float4*>(a.residual + orow * NOUT) + g4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    pre_m[g4] = (a.relumask && in_patch) ? __ldg(reinterpret_cast<const float4*>(a.relumask + orow * NOUT) + g4) : make_float4(1.f, 1.f, 1.f, 1.f);
+                }
+            }
             mbar_wait(BAR(TFULL + acc), aph);
             tc_fence_after();
 #pragma unroll 1
@@ -201,7 +212,7 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         o[0] += bq.x; o[1] += bq.y; o[2] += bq.z; o[3] += bq.w;
                     }
                     if (rp) {
-                        const float4 rq = __ldg(reinterpret_cast<const float4*>(rp) + g4);
+                        const float4 rq = NOUT == 32 ? pre_r[g4] : __ldg(reinterpret_cast<const float4*>(rp) + g4);
                         o[0] += rq.x; o[1] += rq.y; o[2] += rq.z; o[3] += rq.w;
                     }
                     if (a.relu) {
@@ -209,7 +220,7 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                         for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
                     }
                     if (mp) {
-                        const float4 mq = __ldg(reinterpret_cast<const float4*>(mp) + g4);
+                        const float4 mq = NOUT == 32 ? pre_m[g4] : __ldg(reinterpret_cast<const float4*>(mp) + g4);
                         o[0] = mq.x > 0.f ? o[0] : 0.f; o[1] = mq.y > 0.f ? o[1] : 0.f;
                         o[2] = mq.z > 0.f ? o[2] : 0.f; o[3] = mq.w > 0.f ? o[3] : 0.f;
                     }

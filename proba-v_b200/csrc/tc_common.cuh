@@ -13,6 +13,21 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp.  Code guarded by this predicate is known by ptxas to run on a single thread, so the
+// uniform-register operands of tcgen05.mma / TMA are fed by plain R2UR moves instead of per-operand ELECT/BRA.U.ANY
+// uniformisation loops (which cost ~90 cycles per MMA when the guard is `lane == 0`; profiles/r01_conv_tc_v1_stalls.md).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "@px mov.s32 %0, 1;\n"
+        "}\n" : "+r"(pred));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -70,7 +70,7 @@ rowwgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     const int t_lo = (int)((long long)ntiles * blockIdx.x / gridDim.x), t_hi = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             tma_prefetch_desc(&tm_a);
             tma_prefetch_desc(&tm_b);
             uint32_t it = 0;
@@ -88,7 +88,7 @@ rowwgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one_sync()) {
             const uint64_t HI_A = smem_desc_hi(a.grp_lbo, 512, 1);     // MN-major, 128B swizzle / 32B atom; K atoms (4 rows) 512 B apart
             const uint64_t HI_B = smem_desc_hi(128, 512, 1);
             constexpr uint32_t IDESC = instr_desc(2, 128, 32, 1, 1);
