@@ -170,6 +170,147 @@ static int selftest_one(const char* name, RowConvP p, size_t in_floats, size_t o
     return (!rc && bad == 0) ? 0 : 1;
 }
 
+// fused expand -> ReLU -> decay against the two CUDA-core kernels run back to back
+static int selftest_resfront(std::string& rep) {
+    const int B = 3;
+    const RowGeom pr = pr_geom();
+    const size_t rows = (size_t)(pr.lead + (long long)B * pr.pstride + ROW_TAIL);
+    float *x, *we, *weT, *wd, *wdT, *be, *bd, *E, *d0, *d1;
+    PV_CUDA(cudaMalloc(&x, rows * 32 * 4)); PV_CUDA(cudaMalloc(&we, 8192 * 4)); PV_CUDA(cudaMalloc(&weT, 8192 * 4));
+    PV_CUDA(cudaMalloc(&wd, 8192 * 4)); PV_CUDA(cudaMalloc(&wdT, 8192 * 4)); PV_CUDA(cudaMalloc(&be, 1024)); PV_CUDA(cudaMalloc(&bd, 128));
+    PV_CUDA(cudaMalloc(&E, rows * 256 * 4)); PV_CUDA(cudaMalloc(&d0, rows * 32 * 4)); PV_CUDA(cudaMalloc(&d1, rows * 32 * 4));
+    std::vector<float> h(rows * 32), t(8192);
+    unsigned s = 4242u;
+    auto gen = [&](std::vector<float>& v, size_t n, int range, float scale) {
+        for (size_t i = 0; i < n; ++i) { s = s * 1664525u + 1013904223u; v[i] = (float)((int)((s >> 16) % (2 * range + 1)) - range) * scale; }
+    };
+    gen(h, rows * 32, 4, 0.125f); PV_CUDA(cudaMemcpy(x, h.data(), rows * 32 * 4, cudaMemcpyHostToDevice));
+    gen(h, 8192, 3, 0.125f);                                       // We [32][256] (k rows, n cols)
+    for (int k = 0; k < 32; ++k) for (int n = 0; n < 256; ++n) t[(size_t)n * 32 + k] = h[(size_t)k * 256 + n];
+    PV_CUDA(cudaMemcpy(we, h.data(), 8192 * 4, cudaMemcpyHostToDevice)); PV_CUDA(cudaMemcpy(weT, t.data(), 8192 * 4, cudaMemcpyHostToDevice));
+    gen(h, 8192, 3, 0.125f);                                       // Wd [256][32]
+    for (int k = 0; k < 256; ++k) for (int n = 0; n < 32; ++n) t[(size_t)n * 256 + k] = h[(size_t)k * 32 + n];
+    PV_CUDA(cudaMemcpy(wd, h.data(), 8192 * 4, cudaMemcpyHostToDevice)); PV_CUDA(cudaMemcpy(wdT, t.data(), 8192 * 4, cudaMemcpyHostToDevice));
+    gen(h, 256, 4, 0.25f); PV_CUDA(cudaMemcpy(be, h.data(), 1024, cudaMemcpyHostToDevice));
+    gen(h, 32, 4, 0.25f); PV_CUDA(cudaMemcpy(bd, h.data(), 128, cudaMemcpyHostToDevice));
+    PV_CUDA(cudaMemset(d0, 0, rows * 32 * 4)); PV_CUDA(cudaMemset(d1, 0, rows * 32 * 4)); PV_CUDA(cudaMemset(E, 0, rows * 256 * 4));
+    RowConvP p;
+    memset(&p, 0, sizeof p);
+    p.x = x; p.xc = 32; p.w = we; p.w_rows = 32; p.w_cols = 256; p.w_kmajor = 0; p.bias = be; p.y = E; p.n = 256; p.B = B;
+    p.in_lead = pr.lead; p.in_pstride = pr.pstride; p.og = pr; p.ntap = 1; p.kc = 32; p.relu = 1;
+    int rc = launch_rowconv_simt(p, 0);
+    RowConvP q;
+    memset(&q, 0, sizeof q);
+    q.x = E; q.xc = 256; q.w = wd; q.w_rows = 256; q.w_cols = 32; q.w_kmajor = 0; q.bias = bd; q.y = d0; q.n = 32; q.B = B;
+    q.in_lead = pr.lead; q.in_pstride = pr.pstride; q.og = pr; q.ntap = 8; q.kc = 32;
+    for (int j = 0; j < 8; ++j) { q.c0[j] = 32 * j; q.wr0[j] = 32 * j; }
+    if (!rc) rc = launch_rowconv_simt(q, 0);
+    if (!rc) rc = launch_resfront_fwd_tc(x, weT, wdT, be, bd, d1, pr, B, 0, 0.0, 0);
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest resfront: %s", cudaGetErrorString(cudaGetLastError()));
+    double worst = 0; size_t bad = 0;
+    if (!rc) {
+        std::vector<float> a(rows * 32), c2(rows * 32);
+        cudaMemcpy(a.data(), d0, rows * 32 * 4, cudaMemcpyDeviceToHost); cudaMemcpy(c2.data(), d1, rows * 32 * 4, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < rows * 32; ++i) { const double dd = std::fabs((double)a[i] - c2[i]); if (!(dd <= 1e-3)) ++bad; if (dd > worst || dd != dd) worst = dd; }
+    }
+    char line[256];
+    snprintf(line, sizeof line, "%-34s %s max|tc - simt| = %.3g, mismatches %zu of %zu%s%s\n", "fused exp->relu->dec fwd", (!rc && bad == 0) ? "PASS" : "FAIL",
+             worst, bad, rows * 32, rc ? " : " : "", rc ? last_error().c_str() : "");
+    rep += line;
+    cudaFree(x); cudaFree(we); cudaFree(weT); cudaFree(wd); cudaFree(wdT); cudaFree(be); cudaFree(bd); cudaFree(E); cudaFree(d0); cudaFree(d1);
+    return (!rc && bad == 0) ? 0 : 1;
+}
+
+// fused backward of the expand/decay chain (data + weight kernels) against the CUDA-core kernels chained through HBM
+static int selftest_resback(std::string& rep) {
+    const int B = 3;
+    const RowGeom pr = pr_geom();
+    const size_t rows = (size_t)(pr.lead + (long long)B * pr.pstride + ROW_TAIL);
+    const size_t part_floats = (size_t)148 * (9 * 4096 + 1024);
+    float *x, *gd, *G, *M, *we, *weT, *wd, *wdT, *be, *E, *gZ, *ga0, *ga1, *dwd0, *dwd1, *dwe0, *dwe1, *db0, *db1, *part;
+    PV_CUDA(cudaMalloc(&x, rows * 128)); PV_CUDA(cudaMalloc(&gd, rows * 128)); PV_CUDA(cudaMalloc(&G, rows * 128)); PV_CUDA(cudaMalloc(&M, rows * 128));
+    PV_CUDA(cudaMalloc(&we, 32768)); PV_CUDA(cudaMalloc(&weT, 32768)); PV_CUDA(cudaMalloc(&wd, 32768)); PV_CUDA(cudaMalloc(&wdT, 32768));
+    PV_CUDA(cudaMalloc(&be, 1024)); PV_CUDA(cudaMalloc(&E, rows * 1024)); PV_CUDA(cudaMalloc(&gZ, rows * 1024));
+    PV_CUDA(cudaMalloc(&ga0, rows * 128)); PV_CUDA(cudaMalloc(&ga1, rows * 128));
+    PV_CUDA(cudaMalloc(&dwd0, 32768)); PV_CUDA(cudaMalloc(&dwd1, 32768)); PV_CUDA(cudaMalloc(&dwe0, 32768)); PV_CUDA(cudaMalloc(&dwe1, 32768));
+    PV_CUDA(cudaMalloc(&db0, 2048)); PV_CUDA(cudaMalloc(&db1, 2048)); PV_CUDA(cudaMalloc(&part, part_floats * 4));
+    std::vector<float> h(rows * 32), t(8192);
+    unsigned s = 99u;
+    auto gen = [&](std::vector<float>& v, size_t n, int range, float scale) {
+        for (size_t i = 0; i < n; ++i) { s = s * 1664525u + 1013904223u; v[i] = (float)((int)((s >> 16) % (2 * range + 1)) - range) * scale; }
+    };
+    auto mask_rows = [&](std::vector<float>& v) {
+        for (size_t r = 0; r < rows; ++r) {
+            const long long q = (long long)r - pr.lead;
+            const bool ok = q >= 0 && q < (long long)B * pr.pstride && row_valid(pr, (int)(q % pr.pstride));
+            if (!ok) for (int c = 0; c < 32; ++c) v[r * 32 + c] = 0.f;
+        }
+    };
+    gen(h, rows * 32, 4, 0.125f); mask_rows(h); PV_CUDA(cudaMemcpy(x, h.data(), rows * 128, cudaMemcpyHostToDevice));
+    gen(h, rows * 32, 4, 0.125f); mask_rows(h); PV_CUDA(cudaMemcpy(gd, h.data(), rows * 128, cudaMemcpyHostToDevice));
+    gen(h, rows * 32, 4, 0.25f); PV_CUDA(cudaMemcpy(G, h.data(), rows * 128, cudaMemcpyHostToDevice));
+    gen(h, rows * 32, 1, 1.0f); PV_CUDA(cudaMemcpy(M, h.data(), rows * 128, cudaMemcpyHostToDevice));
+    gen(h, 8192, 3, 0.125f);                                       // We [32 ci][256 ch]
+    for (int k = 0; k < 32; ++k) for (int n = 0; n < 256; ++n) t[(size_t)n * 32 + k] = h[(size_t)k * 256 + n];
+    PV_CUDA(cudaMemcpy(we, h.data(), 32768, cudaMemcpyHostToDevice)); PV_CUDA(cudaMemcpy(weT, t.data(), 32768, cudaMemcpyHostToDevice));
+    gen(h, 8192, 3, 0.125f);                                       // Wd [256 ch][32 co]
+    for (int k = 0; k < 256; ++k) for (int n = 0; n < 32; ++n) t[(size_t)n * 256 + k] = h[(size_t)k * 32 + n];
+    PV_CUDA(cudaMemcpy(wd, h.data(), 32768, cudaMemcpyHostToDevice)); PV_CUDA(cudaMemcpy(wdT, t.data(), 32768, cudaMemcpyHostToDevice));
+    gen(h, 256, 4, 0.25f); PV_CUDA(cudaMemcpy(be, h.data(), 1024, cudaMemcpyHostToDevice));
+    for (float* p : {E, gZ}) PV_CUDA(cudaMemset(p, 0, rows * 1024));
+    for (float* p : {ga0, ga1}) PV_CUDA(cudaMemset(p, 0, rows * 128));
+    for (float* p : {dwd0, dwd1, dwe0, dwe1}) PV_CUDA(cudaMemset(p, 0, 32768));
+    PV_CUDA(cudaMemset(db0, 0, 2048)); PV_CUDA(cudaMemset(db1, 0, 2048));
+    auto conv = [&](const float* in, int xc, const float* w, int wr, int wc, float* out, int n) {
+        RowConvP p;
+        memset(&p, 0, sizeof p);
+        p.x = in; p.xc = xc; p.w = w; p.w_rows = wr; p.w_cols = wc; p.w_kmajor = 0; p.y = out; p.n = n; p.B = B;
+        p.in_lead = pr.lead; p.in_pstride = pr.pstride; p.og = pr; p.ntap = xc / 32; p.kc = 32;
+        for (int j = 0; j < p.ntap; ++j) { p.c0[j] = 32 * j; p.wr0[j] = 32 * j; }
+        return p;
+    };
+    RowConvP pe = conv(x, 32, we, 32, 256, E, 256); pe.bias = be; pe.relu = 1;
+    int rc = launch_rowconv_simt(pe, 0);
+    RowConvP pz = conv(gd, 32, wdT, 32, 256, gZ, 256); pz.relumask = E;              // gZ = (gD Wd^T) .* (E > 0)
+    if (!rc) rc = launch_rowconv_simt(pz, 0);
+    RowConvP pa = conv(gZ, 256, weT, 256, 32, ga0, 32); pa.residual = G; pa.relumask = M;
+    if (!rc) rc = launch_rowconv_simt(pa, 0);
+    auto wg = [&](const float* in, int xc, const float* gz, int n, float* dw, float* db) {
+        RowWgradP p;
+        memset(&p, 0, sizeof p);
+        p.x = in; p.xc = xc; p.gz = gz; p.n = n; p.dw = dw; p.dw_cols = n; p.db = db; p.B = B;
+        p.in_lead = pr.lead; p.in_pstride = pr.pstride; p.og = pr; p.ntap = xc / 32; p.kc = 32;
+        for (int j = 0; j < p.ntap; ++j) { p.c0[j] = 32 * j; p.dwr0[j] = 32 * j; }
+        return p;
+    };
+    if (!rc) rc = launch_rowwgrad_simt(wg(E, 256, gd, 32, dwd0, db0 + 256), 0);
+    if (!rc) rc = launch_rowwgrad_simt(wg(x, 32, gZ, 256, dwe0, db0), 0);
+    if (!rc) rc = launch_resfront_bwd_data_tc(x, gd, weT, wd, we, be, G, M, ga1, pr, B, 0, 0.0, 0);
+    if (!rc) rc = launch_resfront_bwd_weight_tc(x, gd, weT, wd, be, dwd1, dwe1, db1, db1 + 256, pr, B, part, part_floats, 0.0, 0);
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest resback: %s", cudaGetErrorString(cudaGetLastError()));
+    auto cmp = [&](const char* name, const float* d0, const float* d1, size_t n) {
+        std::vector<float> a(n), c2(n);
+        cudaMemcpy(a.data(), d0, n * 4, cudaMemcpyDeviceToHost); cudaMemcpy(c2.data(), d1, n * 4, cudaMemcpyDeviceToHost);
+        double worst = 0, ref = 0; size_t bad = 0;
+        for (size_t i = 0; i < n; ++i) ref = std::max(ref, (double)std::fabs(a[i]));
+        for (size_t i = 0; i < n; ++i) { const double dd = std::fabs((double)a[i] - c2[i]); if (!(dd <= 1e-5 * ref + 1e-6)) ++bad; if (dd > worst || dd != dd) worst = dd; }
+        char line[256];
+        snprintf(line, sizeof line, "%-34s %s max|tc - simt| = %.3g (max |ref| %.3g), mismatches %zu of %zu\n", name, bad == 0 ? "PASS" : "FAIL", worst, ref, bad, n);
+        rep += line;
+        return bad == 0 ? 0 : 1;
+    };
+    int fails = 0;
+    if (rc) { rep += std::string("fused exp/dec backward              FAIL : ") + last_error() + "\n"; fails = 1; }
+    else {
+        fails += cmp("fused bwd: gA (+skip, relu mask)", ga0, ga1, rows * 32);
+        fails += cmp("fused bwd: dW decConv", dwd0, dwd1, 8192);
+        fails += cmp("fused bwd: dW expConv", dwe0, dwe1, 8192);
+        fails += cmp("fused bwd: db expConv | db decConv", db0, db1, 288);
+    }
+    for (float* p : {x, gd, G, M, we, weT, wd, wdT, be, E, gZ, ga0, ga1, dwd0, dwd1, dwe0, dwe1, db0, db1, part}) cudaFree(p);
+    return fails;
+}
+
 static int selftest_wgrad(const char* name, RowWgradP p, const RowGeom& ig, int B, std::string& rep) {
     const size_t in_floats = (size_t)(ig.lead + (long long)B * ig.pstride + ROW_TAIL) * p.xc;
     const size_t gz_floats = (size_t)(p.og.lead + (long long)B * p.og.pstride + ROW_TAIL) * p.n;
@@ -261,6 +402,8 @@ int tc_selftest(std::string& rep) {
         p.bias = dummy;
         fails += selftest_one("pointwise 256 -> 32", p, floats(pr, 256), floats(pr, 32), (size_t)p.w_rows * p.w_cols, rep);
     }
+    fails += selftest_resfront(rep);
+    fails += selftest_resback(rep);
     auto wbase = [&](const RowGeom& og, int xc, int n, const Taps& tp) {
         RowWgradP p;
         memset(&p, 0, sizeof p);
@@ -286,7 +429,7 @@ int tc_build_plan(pv_model* m) {
         P.add("mn", (size_t)m->S * m->S);
         for (int i = 0; i <= m->R; ++i) P.add(m->A(i, tr), rows_per(pr, F), rows_extra(pr, F));
         for (int i = 0; i < m->R; ++i) {
-            P.add(m->E(i, tr), rows_per(pr, EX), rows_extra(pr, EX));
+            if (!m->use_tc) P.add(m->E(i, tr), rows_per(pr, EX), rows_extra(pr, EX));   // tensor-core engine keeps E in TMEM
             P.add(m->D(i, tr), rows_per(pr, F), rows_extra(pr, F));
         }
         for (int k = 0; k <= 4; ++k) P.add("G" + std::to_string(k), rows_per(g_geom(k), F), rows_extra(g_geom(k), F));
@@ -298,7 +441,7 @@ int tc_build_plan(pv_model* m) {
             P.add("g_a0", rows_per(pr, F), rows_extra(pr, F));
             P.add("g_a1", rows_per(pr, F), rows_extra(pr, F));
             P.add("g_D", rows_per(pr, F), rows_extra(pr, F));
-            P.add("g_E", rows_per(pr, EX), rows_extra(pr, EX));
+            if (!m->use_tc) P.add("g_E", rows_per(pr, EX), rows_extra(pr, EX));
             for (int k = 0; k <= 4; ++k) P.add("g_G" + std::to_string(k), rows_per(g_geom(k), F), rows_extra(g_geom(k), F));
             P.add("g_tail", (size_t)m->P * m->P * c.scale * c.scale);
             for (int i = 0; i + 1 < c.scale; ++i) {
@@ -326,8 +469,15 @@ int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip
     PV_TRY(launch_first_conv_pr(P["xn"], m->weff + L0.weff_off, m->bias_s + L0.bias_s_off, B, m->S, m->T, P[m->A(0, tr)], pr, st));
     for (int i = 0; i < m->R; ++i) {                                   // ResConv3D, modelsTF.py:177-189
         const int e = m->li("expConv_" + std::to_string(i));
-        PV_TRY(conv_rows(m, m->layers[e], one, P[m->A(i, tr)], F, pr, P[m->E(i, tr)], pr, nullptr, B, "exp_fwd", st));
-        PV_TRY(conv_rows(m, m->layers[e + 1], wide, P[m->E(i, tr)], EX, pr, P[m->D(i, tr)], pr, nullptr, B, "dec_fwd", st));
+        const Layer &Le = m->layers[e], &Ld = m->layers[e + 1];
+        if (m->use_tc) {                // expand -> ReLU -> decay in one kernel; E never leaves TMEM
+            const double fl = 2.0 * B * Le.Ho * Le.Wo * Le.To * ((double)Le.cin * Le.cout + (double)Ld.cin * Ld.cout);
+            PV_TRY(launch_resfront_fwd_tc(P[m->A(i, tr)], m->weffT + Le.weff_off, m->weffT + Ld.weff_off, m->bias_s + Le.bias_s_off,
+                                          m->bias_s + Ld.bias_s_off, P[m->D(i, tr)], pr, B, 1, fl, st));
+        } else {
+            PV_TRY(conv_rows(m, Le, one, P[m->A(i, tr)], F, pr, P[m->E(i, tr)], pr, nullptr, B, "exp_fwd", st));
+            PV_TRY(conv_rows(m, Ld, wide, P[m->E(i, tr)], EX, pr, P[m->D(i, tr)], pr, nullptr, B, "dec_fwd", st));
+        }
         PV_TRY(conv_rows(m, m->layers[e + 2], same, P[m->D(i, tr)], F, pr, P[m->A(i + 1, tr)], pr, P[m->A(i, tr)], B, "norm_fwd", st));
     }
     // ConvReduceAndUpscale (T = 9), modelsTF.py:152-164: reflect pad H,W by 1, three valid 3x3x3 + ReLU, upscale conv
@@ -395,6 +545,17 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
         float* gin = P["g_a" + std::to_string(i & 1)];
         PV_TRY(wgrad_rows(t, Ln, same, P[m->D(i, true)], F, pr, G, pr, B, "norm_wgrad", st));
         PV_TRY(dgrad_rows(m, Ln, same_T, 1, G, pr, P["g_D"], pr, nullptr, nullptr, B, "norm_dgrad", st));
+        if (m->use_tc) {                // expand/decay backward on chip: E and gZ are recomputed in TMEM, never stored
+            const double fl = 2.0 * B * Le.Ho * Le.Wo * Le.To * ((double)Le.cin * Le.cout + (double)Ld.cin * Ld.cout);
+            PV_TRY(launch_resfront_bwd_weight_tc(P[m->A(i, true)], P["g_D"], m->weffT + Le.weff_off, m->weff + Ld.weff_off,
+                                                 m->bias_s + Le.bias_s_off, t->dweff + Ld.weff_off, t->dweff + Le.weff_off,
+                                                 t->dbias_s + Le.bias_s_off, t->dbias_s + Ld.bias_s_off, pr, B, t->wg_partials,
+                                                 t->wg_partial_floats, 2.0 * fl, st));
+            PV_TRY(launch_resfront_bwd_data_tc(P[m->A(i, true)], P["g_D"], m->weffT + Le.weff_off, m->weff + Ld.weff_off,
+                                               m->weff + Le.weff_off, m->bias_s + Le.bias_s_off, G, i == 0 ? P[m->A(0, true)] : nullptr,
+                                               gin, pr, B, 1, 2.0 * fl, st));
+            continue;
+        }
         PV_TRY(wgrad_rows(t, Ld, wide, P[m->E(i, true)], EX, pr, P["g_D"], pr, B, "dec_wgrad", st));
         PV_TRY(dgrad_rows(m, Ld, one, 1, P["g_D"], pr, P["g_E"], pr, nullptr, P[m->E(i, true)], B, "dec_dgrad", st));
         PV_TRY(wgrad_rows(t, Le, one, P[m->A(i, true)], F, pr, P["g_E"], pr, B, "exp_wgrad", st));

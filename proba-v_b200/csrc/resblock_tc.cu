@@ -1,0 +1,637 @@
+// resblock_tc.cu -- the 1x1x1 expand (x8) -> ReLU -> decay chain of a WDSR residual block as ONE tcgen05 kernel per
+// direction; the 256-channel expanded tensor lives only in TMEM (reference models/modelsTF.py:179-183 ResConv3D:
+// expConv_i + ReLU, decConv_i; the reference materialises a 571 MB tensor per block here).
+//
+//   forward   D = (relu(X We^T + be)) Wd^T + bd                                    resfront_fwd_kernel
+//       per 128-row tile and per half h of the 256 expanded channels:
+//         MMA1 (SS)  E_h[128 x 128] = X[128 x 32] . We_h^T          operands from shared memory (TMA), result in TMEM
+//         epilogue   E_h <- tf32(relu(E_h + be_h))  IN PLACE in TMEM (tcgen05.ld -> registers -> tcgen05.st)
+//         MMA2 (TS)  D[128 x 32] += E_h . Wd_h^T                     A operand read straight from TMEM
+//       tcgen05 instructions execute in issue order, so MMA1 of the next half simply queues behind MMA2 of this one.
+//       Two CTAs per SM (256 TMEM columns, ~98 KB shared memory each) overlap one CTA's epilogue with the other's MMAs.
+//
+// Layouts as in rows.h (PR rows, 32 channels, 128 B per row); weights are the effective (weight-normalised, tf32)
+// matrices prepared by wn_prep: weT_exp [256][32], weT_dec [32][256] (both K contiguous).
+#include "rows.h"
+#include "tc_common.cuh"
+
+namespace pv {
+
+using namespace tc;
+int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, int cols, int box_rows, int box_cols, int swizzle_32b_atom);
+
+namespace {
+
+constexpr int RF_THREADS = 192;
+
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+struct ResFwdArgs {
+    int B, tiles_per_patch;
+    RowGeom g;                         // geometry shared by X and D (PR layout)
+    const float* bias_e;               // [256]
+    const float* bias_d;               // [32]
+    float* d;                          // output rows [.. x 32]
+    int round_tf32;
+};
+
+__global__ void __launch_bounds__(RF_THREADS, 2)
+resfront_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_we,
+                    const __grid_constant__ CUtensorMap tm_wd, const ResFwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[9];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_be[256], s_bd[32];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t we_smem = base;                  // [256 rows x 128 B]
+    const uint32_t wd_smem = base + 32768;          // 8 K-chunks x [32 rows x 128 B]
+    const uint32_t x_smem = base + 65536;           // 2 stages x [128 rows x 128 B]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto BAR = [&](int i) { return smem_u32(&bars[i]); };
+    const int FULL = 0, EMPTY = 2, WBAR = 4, D1 = 5, EB = 6, D2 = 7, D2FREE = 8;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
+        mbar_init(BAR(WBAR), 1); mbar_init(BAR(D1), 1); mbar_init(BAR(EB), 4); mbar_init(BAR(D2), 1); mbar_init(BAR(D2FREE), 4);
+        fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i < 256; i += RF_THREADS) s_be[i] = a.bias_e[i];
+    if (threadIdx.x < 32) s_bd[threadIdx.x] = a.bias_d[threadIdx.x];
+    if (warp == 1) tmem_alloc<256>(smem_u32(&tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;                // columns [0,128): E half, [128,160): D accumulator
+    const int ntiles = a.B * a.tiles_per_patch;
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_we); tma_prefetch_desc(&tm_wd);
+            mbar_arrive_expect_tx(BAR(WBAR), 65536);
+            tma_load_2d(we_smem, &tm_we, BAR(WBAR), 0, 0);
+            for (int j = 0; j < 8; ++j) tma_load_2d(wd_smem + j * 4096, &tm_wd, BAR(WBAR), 32 * j, 0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
+                const long long row0 = a.g.lead + (long long)b * a.g.pstride + a.g.row0 + j * 128;
+                const uint32_t stg = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(BAR(EMPTY + stg), ph ^ 1);
+                mbar_arrive_expect_tx(BAR(FULL + stg), 16384);
+                tma_load_2d(x_smem + stg * 16384, &tm_x, BAR(FULL + stg), 0, (int)row0);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one_sync()) {
+            constexpr uint64_t HI = smem_desc_hi(16, 1024, 2);
+            constexpr uint32_t IDESC1 = instr_desc(2, 128, 128, 0, 0);   // E half: N = 128
+            constexpr uint32_t IDESC2 = instr_desc(2, 128, 32, 0, 0);    // D: N = 32
+            mbar_wait(BAR(WBAR), 0);
+            tc_fence_after();
+            uint32_t it = 0, n_e = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const uint32_t stg = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(BAR(FULL + stg), ph);
+                tc_fence_after();
+                const uint64_t xdesc = smem_desc(HI, x_smem + stg * 16384);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint64_t wdesc = smem_desc(HI, we_smem + h * 16384);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_ss<true>(tmem, xdesc + 2 * ks, wdesc + 2 * ks, IDESC1, ks > 0);
+                    if (h == 1) umma_commit(BAR(EMPTY + stg));          // X tile consumed
+                    umma_commit(BAR(D1));
+                    mbar_wait(BAR(EB), n_e & 1); ++n_e;                  // relu(E_h) is back in TMEM
+                    tc_fence_after();
+                    if (h == 0) { mbar_wait(BAR(D2FREE), (it & 1) ^ 1); tc_fence_after(); }   // previous tile's D has been read
+#pragma unroll
+                    for (int ks = 0; ks < 16; ++ks) {
+                        const uint64_t bdesc = smem_desc(HI, wd_smem + (4 * h + (ks >> 2)) * 4096) + 2 * (ks & 3);
+                        umma_ts<true>(tmem + 128, tmem + ks * 8, bdesc, IDESC2, (h > 0 || ks > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(BAR(D2));
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t it = 0, n_d1 = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
+            const int r = a.g.row0 + j * 128 + q * 32 + lane;
+            const bool in_patch = r < a.g.row0 + a.g.nrows && r < a.g.pstride;
+            const bool valid = in_patch && row_valid(a.g, r);
+            const long long orow = a.g.lead + (long long)b * a.g.pstride + r;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                mbar_wait(BAR(D1), n_d1 & 1); ++n_d1;
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_base + c * 32, v);
+                    tmem_ld_wait();
+                    const float* be = s_be + h * 128 + c * 32;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(rna_tf32(fmaxf(__uint_as_float(v[e]) + be[e], 0.f)));
+                    tmem_st32(lane_base + c * 32, v);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(EB));
+            }
+            mbar_wait(BAR(D2), it & 1);
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld32(lane_base + 128, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(D2FREE));
+            if (in_patch) {
+                float4* yp = reinterpret_cast<float4*>(a.d + orow * 32);
+#pragma unroll
+                for (int g4 = 0; g4 < 8; ++g4) {
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        o[e] = valid ? __uint_as_float(v[g4 * 4 + e]) + s_bd[g4 * 4 + e] : 0.f;
+                        if (a.round_tf32) o[e] = rna_tf32(o[e]);
+                    }
+                    yp[g4] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<256>(tmem);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+//   backward, data path     gA = ((gD Wd^T) .* [X We^T + be > 0]) We + G   (.* relumask)        resfront_bwd_data_kernel
+//       rows on TMEM lanes, per half h of the expanded channels:
+//         MMA (SS)  E_h  = X  . We_h^T        (recomputed, never stored)          TMEM cols [0,128)
+//         MMA (SS)  gE_h = gD . Wd_h          (decConv data gradient)             TMEM cols [128,256)
+//         epilogue  gZ_h = tf32(gE_h where E_h + be_h > 0 else 0)  in place over gE_h
+//         MMA (TS)  gA  += gZ_h . We_h        (expConv data gradient)             TMEM cols [256,288)
+//       final epilogue: + G (skip connection), optional ReLU mask of the layer below, zero-padding mask, store.
+struct ResBwdDataArgs {
+    int B, tiles_per_patch;
+    RowGeom g;
+    const float* bias_e;               // [256]
+    const float* residual;             // G rows [.. x 32]
+    const float* relumask;             // rows [.. x 32] or nullptr
+    float* ga;                         // output rows [.. x 32]
+    int round_tf32;
+};
+
+__global__ void __launch_bounds__(RF_THREADS, 1)
+resfront_bwd_data_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_gd,
+                         const __grid_constant__ CUtensorMap tm_weT, const __grid_constant__ CUtensorMap tm_wd,
+                         const __grid_constant__ CUtensorMap tm_we, const ResBwdDataArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[9];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_be[256];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t weT_smem = base;                 // We^T [256 rows(ch) x 32 ci]       B operand of E = X We^T
+    const uint32_t wd_smem = base + 32768;          // Wd   [256 rows(ch) x 32 co]       B operand of gE = gD Wd
+    const uint32_t we_smem = base + 65536;          // We   8 chunks x [32 rows(ci) x 32 ch]   B operand of gA = gZ We
+    const uint32_t st_smem = base + 98304;          // 2 stages x { X [128 x 32], gD [128 x 32] }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto BAR = [&](int i) { return smem_u32(&bars[i]); };
+    const int FULL = 0, EMPTY = 2, WBAR = 4, D1 = 5, EB = 6, D2 = 7, D2FREE = 8;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
+        mbar_init(BAR(WBAR), 1); mbar_init(BAR(D1), 1); mbar_init(BAR(EB), 4); mbar_init(BAR(D2), 1); mbar_init(BAR(D2FREE), 4);
+        fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i < 256; i += RF_THREADS) s_be[i] = a.bias_e[i];
+    if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int ntiles = a.B * a.tiles_per_patch;
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_gd);
+            mbar_arrive_expect_tx(BAR(WBAR), 98304);
+            tma_load_2d(weT_smem, &tm_weT, BAR(WBAR), 0, 0);
+            tma_load_2d(wd_smem, &tm_wd, BAR(WBAR), 0, 0);
+            for (int j = 0; j < 8; ++j) tma_load_2d(we_smem + j * 4096, &tm_we, BAR(WBAR), 32 * j, 0);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
+                const long long row0 = a.g.lead + (long long)b * a.g.pstride + a.g.row0 + j * 128;
+                const uint32_t stg = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(BAR(EMPTY + stg), ph ^ 1);
+                mbar_arrive_expect_tx(BAR(FULL + stg), 32768);
+                tma_load_2d(st_smem + stg * 32768, &tm_x, BAR(FULL + stg), 0, (int)row0);
+                tma_load_2d(st_smem + stg * 32768 + 16384, &tm_gd, BAR(FULL + stg), 0, (int)row0);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one_sync()) {
+            constexpr uint64_t HI = smem_desc_hi(16, 1024, 2);
+            constexpr uint32_t IDESC1 = instr_desc(2, 128, 128, 0, 0);
+            constexpr uint32_t IDESC2 = instr_desc(2, 128, 32, 0, 0);
+            mbar_wait(BAR(WBAR), 0);
+            tc_fence_after();
+            uint32_t it = 0, n_e = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const uint32_t stg = it & 1, ph = (it >> 1) & 1;
+                mbar_wait(BAR(FULL + stg), ph);
+                tc_fence_after();
+                const uint64_t xdesc = smem_desc(HI, st_smem + stg * 32768), gdesc = smem_desc(HI, st_smem + stg * 32768 + 16384);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint64_t w1 = smem_desc(HI, weT_smem + h * 16384), w2 = smem_desc(HI, wd_smem + h * 16384);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_ss<true>(tmem, xdesc + 2 * ks, w1 + 2 * ks, IDESC1, ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_ss<true>(tmem + 128, gdesc + 2 * ks, w2 + 2 * ks, IDESC1, ks > 0);
+                    if (h == 1) umma_commit(BAR(EMPTY + stg));
+                    umma_commit(BAR(D1));
+                    mbar_wait(BAR(EB), n_e & 1); ++n_e;
+                    tc_fence_after();
+                    if (h == 0) { mbar_wait(BAR(D2FREE), (it & 1) ^ 1); tc_fence_after(); }
+#pragma unroll
+                    for (int ks = 0; ks < 16; ++ks) {
+                        const uint64_t bdesc = smem_desc(HI, we_smem + (4 * h + (ks >> 2)) * 4096) + 2 * (ks & 3);
+                        umma_ts<true>(tmem + 256, tmem + 128 + ks * 8, bdesc, IDESC2, (h > 0 || ks > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(BAR(D2));
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t it = 0, n_d1 = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
+            const int r = a.g.row0 + j * 128 + q * 32 + lane;
+            const bool in_patch = r < a.g.row0 + a.g.nrows && r < a.g.pstride;
+            const bool valid = in_patch && row_valid(a.g, r);
+            const long long orow = a.g.lead + (long long)b * a.g.pstride + r;
+            float4 pre_r[8], pre_m[8];
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4) {
+                pre_r[g4] = (a.residual && in_patch) ? __ldg(reinterpret_cast<const float4*>(a.residual + orow * 32) + g4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                pre_m[g4] = (a.relumask && in_patch) ? __ldg(reinterpret_cast<const float4*>(a.relumask + orow * 32) + g4) : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                mbar_wait(BAR(D1), n_d1 & 1); ++n_d1;
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t e[32], v[32];
+                    tmem_ld32(lane_base + c * 32, e);
+                    tmem_ld32(lane_base + 128 + c * 32, v);
+                    tmem_ld_wait();
+                    const float* be = s_be + h * 128 + c * 32;
+#pragma unroll
+                    for (int k = 0; k < 32; ++k)
+                        v[k] = (__uint_as_float(e[k]) + be[k] > 0.f) ? __float_as_uint(rna_tf32(__uint_as_float(v[k]))) : 0u;
+                    tmem_st32(lane_base + 128 + c * 32, v);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(EB));
+            }
+            mbar_wait(BAR(D2), it & 1);
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld32(lane_base + 256, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(D2FREE));
+            if (in_patch) {
+                float4* yp = reinterpret_cast<float4*>(a.ga + orow * 32);
+#pragma unroll
+                for (int g4 = 0; g4 < 8; ++g4) {
+                    float o[4] = {__uint_as_float(v[g4 * 4]) + pre_r[g4].x, __uint_as_float(v[g4 * 4 + 1]) + pre_r[g4].y,
+                                  __uint_as_float(v[g4 * 4 + 2]) + pre_r[g4].z, __uint_as_float(v[g4 * 4 + 3]) + pre_r[g4].w};
+                    const float mk[4] = {pre_m[g4].x, pre_m[g4].y, pre_m[g4].z, pre_m[g4].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (!(mk[e] > 0.f) || !valid) o[e] = 0.f;
+                        if (a.round_tf32) o[e] = rna_tf32(o[e]);
+                    }
+                    yp[g4] = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+//   backward, weight path   dWd = E^T gD,  dWe = X^T gZ,  dbe = sum_rows gZ,  dbd = sum_rows gD     resfront_bwd_weight_kernel
+//       The reductions run over rows, so the expanded tensors are produced TRANSPOSED -- channels on the 128 TMEM lanes,
+//       rows along the columns -- which makes them legal TS-mode A operands ([M = channel lanes] x [K = rows]):
+//         MMA (SS)  E_h^T  = We_h . X^T     (A = We^T rows of this half, B = X tile, both K-major)      cols [0,128)
+//         MMA (SS)  gE_h^T = Wd_h . gD^T    (A = Wd rows of this half,  B = gD tile)                    cols [128,256)
+//         epilogue  E_h^T <- tf32(relu(. + be)),  gZ_h^T <- tf32(gE_h^T where E > 0)  in place;  dbe += row sums of gZ^T
+//         MMA (TS)  dWd_h[ch x co] += E_h^T  . gD   (B = gD tile read MN-major: 32B-atom swizzled copy)  cols [256+32h, +32)
+//         MMA (TS)  dWe_h[ch x ci] += gZ_h^T . X    (B = X tile read MN-major)                            cols [320+32h, +32)
+//       The four [128 x 32] accumulators stay in TMEM for the CTA's lifetime; per-CTA partials are reduced afterwards.
+struct ResBwdWeightArgs {
+    int B, tiles_per_patch;
+    RowGeom g;
+    const float* bias_e;
+    float* partials;                   // [cta][4][128][32]: dWd half 0, half 1, dWe^T half 0, half 1
+    float* db_partials;                // [cta][256 (dbe) + 4 x 32 (dbd per epilogue warp)]
+};
+
+__global__ void __launch_bounds__(RF_THREADS, 1)
+resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_gd,
+                           const __grid_constant__ CUtensorMap tm_x32, const __grid_constant__ CUtensorMap tm_gd32,
+                           const __grid_constant__ CUtensorMap tm_weT, const __grid_constant__ CUtensorMap tm_wd,
+                           const ResBwdWeightArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[8];
+    __shared__ uint32_t tmem_slot;
+    __shared__ float s_be[256];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t weT_smem = base;                 // We^T [256 rows(ch) x 32 ci]   A operand of E^T
+    const uint32_t wd_smem = base + 32768;          // Wd   [256 rows(ch) x 32 co]   A operand of gE^T
+    const uint32_t st_smem = base + 65536;          // 2 stages x { X (K-major), gD (K-major), X (MN), gD (MN) } x 16 KB
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto BAR = [&](int i) { return smem_u32(&bars[i]); };
+    const int FULL = 0, EMPTY = 2, WBAR = 4, D1 = 5, EB = 6, DONE = 7;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1 + 4); }
+        mbar_init(BAR(WBAR), 1); mbar_init(BAR(D1), 1); mbar_init(BAR(EB), 4); mbar_init(BAR(DONE), 1);
+        fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i < 256; i += RF_THREADS) s_be[i] = a.bias_e[i];
+    if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const int ntiles = a.B * a.tiles_per_patch;
+    const int t_lo = (int)((long long)ntiles * blockIdx.x / gridDim.x), t_hi = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            mbar_arrive_expect_tx(BAR(WBAR), 65536);
+            tma_load_2d(weT_smem, &tm_weT, BAR(WBAR), 0, 0);
+            tma_load_2d(wd_smem, &tm_wd, BAR(WBAR), 0, 0);
+            uint32_t it = 0;
+            for (int tile = t_lo; tile < t_hi; ++tile, ++it) {
+                const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
+                const int row0 = (int)(a.g.lead + (long long)b * a.g.pstride + a.g.row0 + j * 128);
+                const uint32_t stg = it & 1, ph = (it >> 1) & 1, sa = st_smem + stg * 65536;
+                mbar_wait(BAR(EMPTY + stg), ph ^ 1);
+                mbar_arrive_expect_tx(BAR(FULL + stg), 65536);
+                tma_load_2d(sa, &tm_x, BAR(FULL + stg), 0, row0);
+                tma_load_2d(sa + 16384, &tm_gd, BAR(FULL + stg), 0, row0);
+                tma_load_2d(sa + 32768, &tm_x32, BAR(FULL + stg), 0, row0);
+                tma_load_2d(sa + 49152, &tm_gd32, BAR(FULL + stg), 0, row0);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one_sync()) {
+            constexpr uint64_t HI = smem_desc_hi(16, 1024, 2);            // K-major SW128
+            constexpr uint64_t HI_MN = smem_desc_hi(128, 512, 1);         // MN-major, 128B swizzle / 32B atom
+            constexpr uint32_t IDESC1 = instr_desc(2, 128, 128, 0, 0);    // [128 ch] x [N = 128 rows]
+            constexpr uint32_t IDESC2 = instr_desc(2, 128, 32, 0, 1);     // TS: A from TMEM, B MN-major, N = 32
+            mbar_wait(BAR(WBAR), 0);
+            tc_fence_after();
+            uint32_t it = 0, n_e = 0;
+            for (int tile = t_lo; tile < t_hi; ++tile, ++it) {
+                const uint32_t stg = it & 1, ph = (it >> 1) & 1, sa = st_smem + stg * 65536;
+                mbar_wait(BAR(FULL + stg), ph);
+                tc_fence_after();
+                const uint64_t xdesc = smem_desc(HI, sa), gdesc = smem_desc(HI, sa + 16384);
+                const uint64_t x32 = smem_desc(HI_MN, sa + 32768), g32 = smem_desc(HI_MN, sa + 49152);
+                const uint32_t first = tile == t_lo ? 0u : 1u;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint64_t w1 = smem_desc(HI, weT_smem + h * 16384), w2 = smem_desc(HI, wd_smem + h * 16384);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_ss<true>(tmem, w1 + 2 * ks, xdesc + 2 * ks, IDESC1, ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_ss<true>(tmem + 128, w2 + 2 * ks, gdesc + 2 * ks, IDESC1, ks > 0);
+                    umma_commit(BAR(D1));
+                    mbar_wait(BAR(EB), n_e & 1); ++n_e;
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 16; ++ks)       // K = 8 rows per step: 1024 B further into the MN-major tiles
+                        umma_ts<true>(tmem + 256 + 32 * h, tmem + ks * 8, g32 + 64 * ks, IDESC2, (first | (ks > 0)) ? 1u : 0u);
+#pragma unroll
+                    for (int ks = 0; ks < 16; ++ks)
+                        umma_ts<true>(tmem + 320 + 32 * h, tmem + 128 + ks * 8, x32 + 64 * ks, IDESC2, (first | (ks > 0)) ? 1u : 0u);
+                }
+                umma_commit(BAR(EMPTY + stg));
+            }
+            umma_commit(BAR(DONE));
+        }
+    } else {
+        const int q = warp & 3;
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        float dbe[2] = {0.f, 0.f}, dbd = 0.f;
+        uint32_t it = 0, n_d1 = 0;
+        for (int tile = t_lo; tile < t_hi; ++tile, ++it) {
+            const uint32_t stg = it & 1, ph = (it >> 1) & 1;
+            mbar_wait(BAR(FULL + stg), ph);
+            {   // dbd: column sums of the gD tile (K-major SW128 copy: 16-byte chunk ^= row & 7); warp q takes rows [32q, 32q+32)
+                const uint8_t* gp = smem_raw + (st_smem - smem_u32(smem_raw)) + stg * 65536 + 16384;
+                float sacc = 0.f;
+                for (int r = q * 32; r < q * 32 + 32; ++r)
+                    sacc += *reinterpret_cast<const float*>(gp + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                dbd += sacc;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(EMPTY + stg));
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                mbar_wait(BAR(D1), n_d1 & 1); ++n_d1;
+                tc_fence_after();
+                const float be = s_be[h * 128 + q * 32 + lane];       // this thread's channel
+                float zsum = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t e[32], v[32];
+                    tmem_ld32(lane_base + c * 32, e);
+                    tmem_ld32(lane_base + 128 + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) {
+                        const float ev = fmaxf(__uint_as_float(e[k]) + be, 0.f);
+                        const float zv = ev > 0.f ? rna_tf32(__uint_as_float(v[k])) : 0.f;
+                        zsum += zv;
+                        e[k] = __float_as_uint(rna_tf32(ev));
+                        v[k] = __float_as_uint(zv);
+                    }
+                    tmem_st32(lane_base + c * 32, e);
+                    tmem_st32(lane_base + 128 + c * 32, v);
+                }
+                dbe[h] += zsum;
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(EB));
+            }
+        }
+        float* dbp = a.db_partials + (size_t)blockIdx.x * 384;
+        dbp[q * 32 + lane] = dbe[0];
+        dbp[128 + q * 32 + lane] = dbe[1];
+        dbp[256 + q * 32 + lane] = dbd;
+        mbar_wait(BAR(DONE), 0);
+        tc_fence_after();
+        float* out = a.partials + (size_t)blockIdx.x * 4 * 4096;
+        for (int g = 0; g < 4; ++g) {
+            uint32_t v[32];
+            tmem_ld32(lane_base + 256 + g * 32, v);
+            tmem_ld_wait();
+            float4* o = reinterpret_cast<float4*>(out + ((size_t)g * 128 + q * 32 + lane) * 32);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                o[e] = t_hi > t_lo ? make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+// dWd [256][32] (= dweff of decConv), dWe [32][256] (= dweff of expConv), dbe [256], dbd [32] from the per-CTA partials
+__global__ void resfront_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ dbp, int ncta,
+                                       float* __restrict__ dwd, float* __restrict__ dwe, float* __restrict__ dbe, float* __restrict__ dbd) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx < 4 * 4096) {
+        float s = 0.f;
+        for (int c = 0; c < ncta; ++c) s += partials[(size_t)c * 16384 + idx];
+        const int g = idx / 4096, m = (idx / 32) % 128, n = idx % 32;
+        if (g < 2) dwd[(size_t)(g * 128 + m) * 32 + n] = s;                 // [ch][co]
+        else dwe[(size_t)n * 256 + (g - 2) * 128 + m] = s;                  // [ci][ch]
+    } else if (idx < 4 * 4096 + 256) {
+        const int j = idx - 4 * 4096;
+        float s = 0.f;
+        for (int c = 0; c < ncta; ++c) s += dbp[(size_t)c * 384 + j];
+        dbe[j] = s;
+    } else if (idx < 4 * 4096 + 256 + 32) {
+        const int j = idx - 4 * 4096 - 256;
+        float s = 0.f;
+        for (int c = 0; c < ncta; ++c) for (int w = 0; w < 4; ++w) s += dbp[(size_t)c * 384 + 256 + w * 32 + j];
+        dbd[j] = s;
+    }
+}
+
+}  // namespace
+
+// D = decConv(relu(expConv(X))) on PR rows.  weT_exp [256][32], weT_dec [32][256], biases padded to 256 / 32.
+int launch_resfront_fwd_tc(const float* x, const float* weT_exp, const float* weT_dec, const float* bias_e, const float* bias_d,
+                           float* d, const RowGeom& g, int B, int round_tf32, double flops, cudaStream_t st) {
+    ResFwdArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.tiles_per_patch = cdiv(g.nrows, 128); a.g = g; a.bias_e = bias_e; a.bias_d = bias_d; a.d = d; a.round_tf32 = round_tf32;
+    const long long rows = g.lead + (long long)B * g.pstride + ROW_TAIL;
+    CUtensorMap tm_x, tm_we, tm_wd;
+    PV_TRY(make_tmap_2d(&tm_x, x, rows, 32, 128, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_we, weT_exp, 256, 32, 256, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_wd, weT_dec, 32, 256, 32, 32, 0));
+    const size_t smem = 1024 + 65536 + 2 * 16384;
+    static bool attr = false;
+    if (!attr) { PV_CUDA(cudaFuncSetAttribute(resfront_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = a.B * a.tiles_per_patch;
+    const int grid = ntiles < 2 * sms ? ntiles : 2 * sms;
+    PV_TIMED("resfront_fwd", st, flops, 0.0);
+    resfront_fwd_kernel<<<grid, RF_THREADS, smem, st>>>(tm_x, tm_we, tm_wd, a);
+    PV_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace pv
+
+namespace pv {
+// gA = dgrad_exp(dgrad_dec(gD) .* relu'(E)) + G, E recomputed from X.  weT_exp [256][32], w_dec [256][32] (= weff of decConv),
+// w_exp [32][256] (= weff of expConv)
+int launch_resfront_bwd_data_tc(const float* x, const float* gd, const float* weT_exp, const float* w_dec, const float* w_exp,
+                                const float* bias_e, const float* residual, const float* relumask, float* ga, const RowGeom& g,
+                                int B, int round_tf32, double flops, cudaStream_t st) {
+    ResBwdDataArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.tiles_per_patch = cdiv(g.nrows, 128); a.g = g; a.bias_e = bias_e; a.residual = residual; a.relumask = relumask;
+    a.ga = ga; a.round_tf32 = round_tf32;
+    const long long rows = g.lead + (long long)B * g.pstride + ROW_TAIL;
+    CUtensorMap tm_x, tm_gd, tm_weT, tm_wd, tm_we;
+    PV_TRY(make_tmap_2d(&tm_x, x, rows, 32, 128, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_gd, gd, rows, 32, 128, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_weT, weT_exp, 256, 32, 256, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_wd, w_dec, 256, 32, 256, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_we, w_exp, 32, 256, 32, 32, 0));
+    const size_t smem = 1024 + 98304 + 2 * 32768;
+    static bool attr = false;
+    if (!attr) { PV_CUDA(cudaFuncSetAttribute(resfront_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = a.B * a.tiles_per_patch;
+    const int grid = ntiles < sms ? ntiles : sms;
+    PV_TIMED("resfront_bwd_data", st, flops, 0.0);
+    resfront_bwd_data_kernel<<<grid, RF_THREADS, smem, st>>>(tm_x, tm_gd, tm_weT, tm_wd, tm_we, a);
+    PV_LAUNCH_CHECK();
+    return 0;
+}
+}  // namespace pv
+
+namespace pv {
+// weight / bias gradients of expConv and decConv of one block, E and gZ recomputed on chip
+int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* weT_exp, const float* w_dec, const float* bias_e,
+                                  float* dw_dec, float* dw_exp, float* db_exp, float* db_dec, const RowGeom& g, int B,
+                                  float* partials, size_t partial_floats, double flops, cudaStream_t st) {
+    ResBwdWeightArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.tiles_per_patch = cdiv(g.nrows, 128); a.g = g; a.bias_e = bias_e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = a.B * a.tiles_per_patch;
+    const int grid = ntiles < sms ? ntiles : sms;
+    const size_t need = (size_t)grid * (4 * 4096 + 384);
+    if (!partials || partial_floats < need) return set_error(PV_ERR_BAD_ARG, "resfront_bwd_weight: partial buffer too small");
+    a.partials = partials; a.db_partials = partials + (size_t)grid * 4 * 4096;
+    const long long rows = g.lead + (long long)B * g.pstride + ROW_TAIL;
+    CUtensorMap tm_x, tm_gd, tm_x32, tm_gd32, tm_weT, tm_wd;
+    PV_TRY(make_tmap_2d(&tm_x, x, rows, 32, 128, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_gd, gd, rows, 32, 128, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_x32, x, rows, 32, 128, 32, 1));
+    PV_TRY(make_tmap_2d(&tm_gd32, gd, rows, 32, 128, 32, 1));
+    PV_TRY(make_tmap_2d(&tm_weT, weT_exp, 256, 32, 256, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_wd, w_dec, 256, 32, 256, 32, 0));
+    const size_t smem = 1024 + 65536 + 2 * 65536;
+    static bool attr = false;
+    if (!attr) { PV_CUDA(cudaFuncSetAttribute(resfront_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    {
+        PV_TIMED("resfront_bwd_weight", st, flops, 0.0);
+        resfront_bwd_weight_kernel<<<grid, RF_THREADS, smem, st>>>(tm_x, tm_gd, tm_x32, tm_gd32, tm_weT, tm_wd, a);
+        PV_LAUNCH_CHECK();
+    }
+    {
+        PV_TIMED("wgrad_reduce", st);
+        resfront_reduce_kernel<<<cdiv(4 * 4096 + 288, 256), 256, 0, st>>>(a.partials, a.db_partials, grid, dw_dec, dw_exp, db_exp, db_dec);
+        PV_LAUNCH_CHECK();
+    }
+    return 0;
+}
+}  // namespace pv
