@@ -57,7 +57,7 @@ int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, int cols, in
 namespace {
 
 constexpr int NSTAGE = 4;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-5 and 6-9: two epilogue groups (one per TMEM accumulator)
 
 struct ConvTcArgs {
     // tiles
@@ -136,6 +136,9 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (elect_one_sync()) {
             constexpr uint64_t HI = smem_desc_hi(16, 1024, 2);          // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
             constexpr uint32_t IDESC = instr_desc(2, 128, NOUT, 0, 0);  // tf32 x tf32 -> f32, M = 128, N = NOUT
+            uint32_t tap_inc[27];                     // start-address increments (16-byte units) of the 27 tap views
+#pragma unroll
+            for (int t = 0; t < 27; ++t) tap_inc[t] = (uint32_t)a.tap_row[t] * 8u;
             mbar_wait(BAR(WBAR), 0);
             tc_fence_after();
             uint32_t it = 0, tl = 0;
@@ -145,32 +148,56 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + acc * NOUT;
                 uint32_t accumulate = 0;
-                for (int s = 0; s < a.nslab; ++s, ++it) {
-                    const uint32_t stg = it % NSTAGE, ph = (it / NSTAGE) & 1;
-                    mbar_wait(BAR(FULL + stg), ph);
-                    tc_fence_after();
-                    const uint32_t s_addr = st_smem + stg * stage_bytes;
-                    for (int t = a.slab_tap0[s]; t < a.slab_tap0[s + 1]; ++t) {
-                        // descriptors differ only in their 14-bit start-address field: +2 (= 32 B >> 4) per K8 step
-                        const uint64_t adesc = smem_desc(HI, s_addr + (uint32_t)a.tap_row[t] * 128u);
-                        const uint64_t bdesc = smem_desc(HI, w_smem + (uint32_t)t * W_TAP_BYTES);
+                constexpr uint32_t HI32 = (uint32_t)(HI >> 32), LO32 = (uint32_t)HI;   // LO32: the LBO field (bits 16-29)
+                if (a.nslab == 3 && a.ntap == 27) {
+                    // 3x3x3 fast path: 3 slabs x 9 taps x 4 K-steps fully unrolled; per MMA one 32-bit add per descriptor
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {                 // 32 channels = 4 x K8
-                            umma_ss<true>(d_tmem, adesc + 2 * ks, bdesc + 2 * ks, IDESC, accumulate);
-                            accumulate = 1;
+                    for (int s = 0; s < 3; ++s, ++it) {
+                        const uint32_t stg = it % NSTAGE, ph = (it / NSTAGE) & 1;
+                        mbar_wait(BAR(FULL + stg), ph);
+                        tc_fence_after();
+                        const uint32_t a_lo = ((st_smem + stg * stage_bytes) >> 4) | LO32;
+                        const uint32_t b_lo = ((w_smem >> 4) | LO32) + (uint32_t)(s * 9) * (W_TAP_BYTES >> 4);
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                umma_ss_tf32_lohi(d_tmem, a_lo + tap_inc[s * 9 + t] + 2 * ks, b_lo + t * (W_TAP_BYTES >> 4) + 2 * ks, HI32, IDESC, accumulate);
+                                accumulate = 1;
+                            }
                         }
+                        umma_commit(BAR(EMPTY + stg));
                     }
-                    umma_commit(BAR(EMPTY + stg));      // slab may be overwritten once these MMAs have read it
+                } else {
+                    for (int s = 0; s < a.nslab; ++s, ++it) {
+                        const uint32_t stg = it % NSTAGE, ph = (it / NSTAGE) & 1;
+                        mbar_wait(BAR(FULL + stg), ph);
+                        tc_fence_after();
+                        const uint32_t s_addr = st_smem + stg * stage_bytes;
+                        for (int t = a.slab_tap0[s]; t < a.slab_tap0[s + 1]; ++t) {
+                            const uint32_t a_lo = ((s_addr + (uint32_t)a.tap_row[t] * 128u) >> 4) | LO32, b_lo = ((w_smem + (uint32_t)t * W_TAP_BYTES) >> 4) | LO32;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {             // 32 channels = 4 x K8
+                                umma_ss_tf32_lohi(d_tmem, a_lo + 2 * ks, b_lo + 2 * ks, HI32, IDESC, accumulate);
+                                accumulate = 1;
+                            }
+                        }
+                        umma_commit(BAR(EMPTY + stg));  // slab may be overwritten once these MMAs have read it
+                    }
                 }
                 umma_commit(BAR(TFULL + acc));          // accumulator complete
             }
         }
     } else {
-        // ================================================================== epilogue (4 warps, TMEM lane quarter = warp % 4)
+        // ================================================================== epilogue: two groups of 4 warps (TMEM lane quarter =
+        // warp % 4); group g drains accumulator g, i.e. every other tile, so one group's global-memory latency (residual /
+        // mask prefetch, stores) overlaps the other group's tile
         const int q = warp & 3;
+        const uint32_t grp = (uint32_t)(warp - 2) >> 2;
         uint32_t tl = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
             const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+            if (acc != grp) continue;
             const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
             const int r = a.og.row0 + j * 128 + q * 32 + lane;            // row inside the patch
             const bool in_patch = r < a.og.row0 + a.og.nrows && r < a.og.pstride;

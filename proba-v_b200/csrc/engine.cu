@@ -748,7 +748,7 @@ int pv_trainer_create(pv_model* m, int opt_kind, float learning_rate, int loss_k
         pv_trainer_destroy(t);
         return set_error(PV_ERR_CUDA, "cudaMalloc of the trainer arenas failed");
     }
-    if (m->use_tc) {
+    if (m->rows) {
         t->wg_partial_floats = (size_t)148 * (9 * 4096 + 1024);
         if (cudaMalloc(&t->wg_partials, t->wg_partial_floats * 4) != cudaSuccess) {
             pv_trainer_destroy(t);

@@ -563,7 +563,8 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
         PV_TRY(dgrad_rows(m, Le, one, EX / 32, P["g_E"], pr, gin, pr, G, i == 0 ? P[m->A(0, true)] : nullptr, B, "exp_dgrad", st));
     }
     const Layer& L0 = m->layers[m->li("mainConv1")];
-    PV_TRY(launch_first_conv_pr_wgrad(P["xn"], P["g_a0"], B, m->S, m->T, pr, t->dweff + L0.weff_off, t->dbias_s + L0.bias_s_off, st));
+    PV_TRY(launch_first_conv_pr_wgrad(P["xn"], P["g_a0"], B, m->S, m->T, pr, t->dweff + L0.weff_off, t->dbias_s + L0.bias_s_off,
+                                      t->wg_partials, t->wg_partial_floats, st));
     PV_TRY(launch_wn_bwd(m->wn_tab, (int)m->layers.size(), m->wn_blocks, m->params, m->scale, t->dweff, t->dbias_s, t->grads, st));
     return 0;
 }

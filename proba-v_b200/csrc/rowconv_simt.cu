@@ -224,27 +224,39 @@ __global__ void __launch_bounds__(256) first_conv_pr_kernel(const float* __restr
 
 // dw[tap][n] += sum_vox xn[vox + tap] * gz[row(vox)][n]; db[n] += sum gz.  lane = n, one warp walks voxels.
 __global__ void __launch_bounds__(256) first_conv_pr_wgrad_kernel(const float* __restrict__ xn, const float* __restrict__ gz,
-                                                                  int B, int S, int T, RowGeom g, float* __restrict__ dw,
-                                                                  float* __restrict__ db) {
+                                                                  int B, int S, int T, RowGeom g, float* __restrict__ partials) {
     __shared__ float red[8][28][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long nvox = (long long)B * T * S * S;
     float acc[28];
 #pragma unroll
     for (int j = 0; j < 28; ++j) acc[j] = 0.f;
-    for (long long v0 = (long long)blockIdx.x * 8 + warp; v0 < nvox; v0 += (long long)gridDim.x * 8) {
-        long long v = v0;
-        const int ww = (int)(v % S); v /= S;
-        const int hh = (int)(v % S); v /= S;
-        const int tt = (int)(v % T); const long long b = v / T;
-        const float gv = __ldg(gz + (g.lead + b * g.pstride + (long long)(g.t0 + tt) * g.plane + hh * g.pw + ww) * 32 + lane);
-        acc[27] += gv;
+    // two voxels per iteration: their gz / x loads are independent, which hides most of the global-memory latency
+    const long long stride = (long long)gridDim.x * 8;
+    for (long long v0 = (long long)blockIdx.x * 8 + warp; v0 < nvox; v0 += 2 * stride) {
+        float gv[2];
+        int tt[2], hh[2], ww[2];
+        long long bb[2];
 #pragma unroll
-        for (int tap = 0; tap < 27; ++tap) {
-            const int t2 = tt + tap / 9 - 1, h2 = hh + (tap / 3) % 3 - 1, w2 = ww + tap % 3 - 1;
-            float x = 0.f;
-            if (t2 >= 0 && t2 < T && h2 >= 0 && h2 < S && w2 >= 0 && w2 < S) x = __ldg(xn + ((b * S + h2) * S + w2) * T + t2);
-            acc[tap] = fmaf(x, gv, acc[tap]);
+        for (int u = 0; u < 2; ++u) {
+            long long v = v0 + u * stride;
+            const bool ok = v < nvox;
+            if (!ok) v = 0;
+            ww[u] = (int)(v % S); v /= S;
+            hh[u] = (int)(v % S); v /= S;
+            tt[u] = (int)(v % T); bb[u] = v / T;
+            gv[u] = ok ? __ldg(gz + (g.lead + bb[u] * g.pstride + (long long)(g.t0 + tt[u]) * g.plane + hh[u] * g.pw + ww[u]) * 32 + lane) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            acc[27] += gv[u];
+#pragma unroll
+            for (int tap = 0; tap < 27; ++tap) {
+                const int t2 = tt[u] + tap / 9 - 1, h2 = hh[u] + (tap / 3) % 3 - 1, w2 = ww[u] + tap % 3 - 1;
+                float x = 0.f;
+                if (t2 >= 0 && t2 < T && h2 >= 0 && h2 < S && w2 >= 0 && w2 < S) x = __ldg(xn + ((bb[u] * S + h2) * S + w2) * T + t2);
+                acc[tap] = fmaf(x, gv[u], acc[tap]);
+            }
         }
     }
 #pragma unroll
@@ -254,8 +266,16 @@ __global__ void __launch_bounds__(256) first_conv_pr_wgrad_kernel(const float* _
         float s = 0.f;
 #pragma unroll
         for (int wv = 0; wv < 8; ++wv) s += red[wv][i / 32][i % 32];
-        if (i < 27 * 32) atomicAdd(dw + i, s); else atomicAdd(db + (i - 27 * 32), s);
+        partials[(size_t)blockIdx.x * (28 * 32) + i] = s;       // fixed-order second stage below: deterministic, no atomics
     }
+}
+
+__global__ void first_conv_pr_wgrad_reduce_kernel(const float* __restrict__ partials, int ncta, float* __restrict__ dw, float* __restrict__ db) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= 28 * 32) return;
+    float s = 0.f;
+    for (int c = 0; c < ncta; ++c) s += partials[(size_t)c * (28 * 32) + i];
+    if (i < 27 * 32) dw[i] = s; else db[i - 27 * 32] = s;
 }
 
 // ------------------------------------------------------------------------------------------ PR <-> G (reflect pad)
@@ -386,9 +406,14 @@ int launch_first_conv_pr(const float* xn, const float* w, const float* bias, int
     return 0;
 }
 
-int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, int T, RowGeom g, float* dw, float* db, cudaStream_t st) {
+int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, int T, RowGeom g, float* dw, float* db,
+                               float* partials, size_t partial_floats, cudaStream_t st) {
+    const int grid = 148 * 8;
+    if (!partials || partial_floats < (size_t)grid * 28 * 32) return set_error(PV_ERR_BAD_ARG, "first_conv_pr_wgrad: partial buffer too small");
     PV_TIMED("first_conv_pr_wgrad", st, 2.0 * B * T * S * S * 27 * 32, 0.0);
-    first_conv_pr_wgrad_kernel<<<148 * 4, 256, 0, st>>>(xn, gz, B, S, T, g, dw, db);
+    first_conv_pr_wgrad_kernel<<<grid, 256, 0, st>>>(xn, gz, B, S, T, g, partials);
+    PV_LAUNCH_CHECK();
+    first_conv_pr_wgrad_reduce_kernel<<<7, 128, 0, st>>>(partials, grid, dw, db);
     PV_LAUNCH_CHECK();
     return 0;
 }

@@ -105,7 +105,8 @@ int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* 
 // mainConv1 (Cin = 1, 27 taps, ReLU) from the normalised dense LR [B,S,S,T] (h,w,t order) into the PR layout
 int launch_first_conv_pr(const float* xn, const float* w /*[27][32] taps in (dt,dh,dw) order*/, const float* bias, int B, int S, int T,
                          float* y, RowGeom g, cudaStream_t st);
-int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, int T, RowGeom g, float* dw, float* db, cudaStream_t st);
+int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, int T, RowGeom g, float* dw, float* db,
+                               float* partials, size_t partial_floats, cudaStream_t st);
 // PR block output -> G layout with the reducer's reflect padding (tf.pad REFLECT by 1 on H and W), and its adjoint
 int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st);
 int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st);

@@ -104,6 +104,21 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t adesc, uint64_
         asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
                      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Same, with each descriptor given as (low word, shared high word): the 14-bit start-address field lives in the low word,
+// so the issuing thread advances a descriptor with ONE 32-bit add and ptxas keeps the constant high word in a uniform
+// register (the 64-bit form costs ~9 uniform-datapath instructions per MMA; profiles/r01_tc_v2_ncu_full_summary.md).
+__device__ __forceinline__ void umma_ss_tf32_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // A operand read from TMEM ([128 lanes x K columns]), B from smem
 template <bool TF32>
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

@@ -91,18 +91,29 @@ rowwgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         if (elect_one_sync()) {
             const uint64_t HI_A = smem_desc_hi(a.grp_lbo, 512, 1);     // MN-major, 128B swizzle / 32B atom; K atoms (4 rows) 512 B apart
             const uint64_t HI_B = smem_desc_hi(128, 512, 1);
+            const uint32_t HI32 = (uint32_t)(HI_A >> 32), LO_A = (uint32_t)HI_A, LO_B = (uint32_t)HI_B;
             constexpr uint32_t IDESC = instr_desc(2, 128, 32, 1, 1);
+            uint32_t grp_inc[MAX_GROUPS];
+#pragma unroll
+            for (int g = 0; g < MAX_GROUPS; ++g) grp_inc[g] = a.grp_off[g] >> 4;
             uint32_t it = 0;
             for (int tile = t_lo; tile < t_hi; ++tile, ++it) {
                 const uint32_t stg = it % a.nstage, ph = (it / a.nstage) & 1;
                 mbar_wait(BAR(FULL + stg), ph);
                 tc_fence_after();
-                const uint32_t s_addr = base + stg * a.stage_bytes;
-                for (int ks = 0; ks < a.TR / 8; ++ks) {
-                    const uint64_t bdesc = smem_desc(HI_B, s_addr + a.b_off + ks * 1024);
-                    for (int g = 0; g < a.ngroup; ++g)
-                        umma_ss<true>(tmem + g * 32, smem_desc(HI_A, s_addr + a.grp_off[g] + ks * 1024), bdesc, IDESC,
-                                      (tile > t_lo || ks > 0) ? 1u : 0u);
+                const uint32_t s_lo = (base + stg * a.stage_bytes) >> 4;
+                const uint32_t a_lo = s_lo | LO_A, b_lo = (s_lo + (a.b_off >> 4)) | LO_B;
+                const uint32_t first = tile > t_lo ? 1u : 0u;
+                if (a.ngroup == 9) {
+                    for (int ks = 0; ks < a.TR / 8; ++ks) {
+#pragma unroll
+                        for (int g = 0; g < 9; ++g)
+                            umma_ss_tf32_lohi(tmem + g * 32, a_lo + grp_inc[g] + ks * 64, b_lo + ks * 64, HI32, IDESC, first | (ks > 0 ? 1u : 0u));
+                    }
+                } else {
+                    for (int ks = 0; ks < a.TR / 8; ++ks)
+                        for (int g = 0; g < a.ngroup; ++g)
+                            umma_ss_tf32_lohi(tmem + g * 32, a_lo + (a.grp_off[g] >> 4) + ks * 64, b_lo + ks * 64, HI32, IDESC, first | (ks > 0 ? 1u : 0u));
                 }
                 umma_commit(BAR(EMPTY + stg));
             }
