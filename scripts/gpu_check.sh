@@ -12,6 +12,6 @@ cat gpurun_out/bench_${TAG}.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
 cat gpurun_out/bench_ref_${TAG}.json
 # launch list of one steady-state train step (3 warm-up steps skipped); numbers under ncu are never bench values
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-430} -c ${NCU_COUNT:-150} --csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-330} -c ${NCU_COUNT:-115} --csv \
     --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_${TAG}.log 2>&1
 echo "ncu rc=$?"
