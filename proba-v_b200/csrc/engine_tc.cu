@@ -205,7 +205,7 @@ static int selftest_resfront(std::string& rep) {
     q.in_lead = pr.lead; q.in_pstride = pr.pstride; q.og = pr; q.ntap = 8; q.kc = 32;
     for (int j = 0; j < 8; ++j) { q.c0[j] = 32 * j; q.wr0[j] = 32 * j; }
     if (!rc) rc = launch_rowconv_simt(q, 0);
-    if (!rc) rc = launch_resfront_fwd_tc(x, weT, wdT, be, bd, d1, pr, B, 0, 0.0, 0);
+    if (!rc) rc = launch_resfront_fwd_tc(x, weT, wdT, be, bd, d1, nullptr, pr, B, 0, 0.0, 0);
     if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest resfront: %s", cudaGetErrorString(cudaGetLastError()));
     double worst = 0; size_t bad = 0;
     if (!rc) {
@@ -285,7 +285,12 @@ static int selftest_resback(std::string& rep) {
     };
     if (!rc) rc = launch_rowwgrad_simt(wg(E, 256, gd, 32, dwd0, db0 + 256), 0);
     if (!rc) rc = launch_rowwgrad_simt(wg(x, 32, gZ, 256, dwe0, db0), 0);
-    if (!rc) rc = launch_resfront_bwd_data_tc(x, gd, weT, wd, we, be, G, M, ga1, pr, B, 0, 0.0, 0);
+    // the backward-data kernel consumes the ReLU bits the fused forward emits
+    float *dtmp = nullptr, *bd0 = nullptr; uint32_t* bits = nullptr;
+    PV_CUDA(cudaMalloc(&dtmp, rows * 128)); PV_CUDA(cudaMalloc(&bd0, 128)); PV_CUDA(cudaMalloc(&bits, rows * 32));
+    PV_CUDA(cudaMemset(bd0, 0, 128)); PV_CUDA(cudaMemset(bits, 0, rows * 32));
+    if (!rc) rc = launch_resfront_fwd_tc(x, weT, wdT, be, bd0, dtmp, bits, pr, B, 0, 0.0, 0);
+    if (!rc) rc = launch_resfront_bwd_data_tc(gd, wd, we, bits, G, M, ga1, pr, B, 0, 0.0, 0);
     if (!rc) rc = launch_resfront_bwd_weight_tc(x, gd, weT, wd, be, dwd1, dwe1, db1, db1 + 256, pr, B, part, part_floats, 0.0, 0);
     if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest resback: %s", cudaGetErrorString(cudaGetLastError()));
     auto cmp = [&](const char* name, const float* d0, const float* d1, size_t n) {
@@ -307,7 +312,8 @@ static int selftest_resback(std::string& rep) {
         fails += cmp("fused bwd: dW expConv", dwe0, dwe1, 8192);
         fails += cmp("fused bwd: db expConv | db decConv", db0, db1, 288);
     }
-    for (float* p : {x, gd, G, M, we, weT, wd, wdT, be, E, gZ, ga0, ga1, dwd0, dwd1, dwe0, dwe1, db0, db1, part}) cudaFree(p);
+    for (float* p : {x, gd, G, M, we, weT, wd, wdT, be, E, gZ, ga0, ga1, dwd0, dwd1, dwe0, dwe1, db0, db1, part, dtmp, bd0}) cudaFree(p);
+    cudaFree(bits);
     return fails;
 }
 
@@ -430,6 +436,7 @@ int tc_build_plan(pv_model* m) {
         for (int i = 0; i <= m->R; ++i) P.add(m->A(i, tr), rows_per(pr, F), rows_extra(pr, F));
         for (int i = 0; i < m->R; ++i) {
             if (!m->use_tc) P.add(m->E(i, tr), rows_per(pr, EX), rows_extra(pr, EX));   // tensor-core engine keeps E in TMEM
+            else if (tr) P.add("M" + std::to_string(i), rows_per(pr, 8), rows_extra(pr, 8));    // ... and only its ReLU bits (32 B / row)
             P.add(m->D(i, tr), rows_per(pr, F), rows_extra(pr, F));
         }
         for (int k = 0; k <= 4; ++k) P.add("G" + std::to_string(k), rows_per(g_geom(k), F), rows_extra(g_geom(k), F));
@@ -473,7 +480,8 @@ int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip
         if (m->use_tc) {                // expand -> ReLU -> decay in one kernel; E never leaves TMEM
             const double fl = 2.0 * B * Le.Ho * Le.Wo * Le.To * ((double)Le.cin * Le.cout + (double)Ld.cin * Ld.cout);
             PV_TRY(launch_resfront_fwd_tc(P[m->A(i, tr)], m->weffT + Le.weff_off, m->weffT + Ld.weff_off, m->bias_s + Le.bias_s_off,
-                                          m->bias_s + Ld.bias_s_off, P[m->D(i, tr)], pr, B, 1, fl, st));
+                                          m->bias_s + Ld.bias_s_off, P[m->D(i, tr)],
+                                          tr ? reinterpret_cast<uint32_t*>(P["M" + std::to_string(i)]) : nullptr, pr, B, 1, fl, st));
         } else {
             PV_TRY(conv_rows(m, Le, one, P[m->A(i, tr)], F, pr, P[m->E(i, tr)], pr, nullptr, B, "exp_fwd", st));
             PV_TRY(conv_rows(m, Ld, wide, P[m->E(i, tr)], EX, pr, P[m->D(i, tr)], pr, nullptr, B, "dec_fwd", st));
@@ -551,9 +559,9 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
                                                  m->bias_s + Le.bias_s_off, t->dweff + Ld.weff_off, t->dweff + Le.weff_off,
                                                  t->dbias_s + Le.bias_s_off, t->dbias_s + Ld.bias_s_off, pr, B, t->wg_partials,
                                                  t->wg_partial_floats, 2.0 * fl, st));
-            PV_TRY(launch_resfront_bwd_data_tc(P[m->A(i, true)], P["g_D"], m->weffT + Le.weff_off, m->weff + Ld.weff_off,
-                                               m->weff + Le.weff_off, m->bias_s + Le.bias_s_off, G, i == 0 ? P[m->A(0, true)] : nullptr,
-                                               gin, pr, B, 1, 2.0 * fl, st));
+            PV_TRY(launch_resfront_bwd_data_tc(P["g_D"], m->weff + Ld.weff_off, m->weff + Le.weff_off,
+                                               reinterpret_cast<const uint32_t*>(P["M" + std::to_string(i)]), G,
+                                               i == 0 ? P[m->A(0, true)] : nullptr, gin, pr, B, 1, fl, st));
             continue;
         }
         PV_TRY(wgrad_rows(t, Ld, wide, P[m->E(i, true)], EX, pr, P["g_D"], pr, B, "dec_wgrad", st));

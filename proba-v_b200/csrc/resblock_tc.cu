@@ -30,302 +30,224 @@ __device__ __forceinline__ float rna_tf32(float x) {
     return __uint_as_float(u);
 }
 
-struct ResFwdArgs {
-    int B, tiles_per_patch;
-    RowGeom g;                         // geometry shared by X and D (PR layout)
-    const float* bias_e;               // [256]
-    const float* bias_d;               // [32]
-    float* d;                          // output rows [.. x 32]
-    int round_tf32;
-};
-
-__global__ void __launch_bounds__(RF_THREADS, 2)
-resfront_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_we,
-                    const __grid_constant__ CUtensorMap tm_wd, const ResFwdArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[9];
-    __shared__ uint32_t tmem_slot;
-    __shared__ float s_be[256], s_bd[32];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t we_smem = base;                  // [256 rows x 128 B]
-    const uint32_t wd_smem = base + 32768;          // 8 K-chunks x [32 rows x 128 B]
-    const uint32_t x_smem = base + 65536;           // 2 stages x [128 rows x 128 B]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    auto BAR = [&](int i) { return smem_u32(&bars[i]); };
-    const int FULL = 0, EMPTY = 2, WBAR = 4, D1 = 5, EB = 6, D2 = 7, D2FREE = 8;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
-        mbar_init(BAR(WBAR), 1); mbar_init(BAR(D1), 1); mbar_init(BAR(EB), 4); mbar_init(BAR(D2), 1); mbar_init(BAR(D2FREE), 4);
-        fence_mbar_init();
-    }
-    for (int i = threadIdx.x; i < 256; i += RF_THREADS) s_be[i] = a.bias_e[i];
-    if (threadIdx.x < 32) s_bd[threadIdx.x] = a.bias_d[threadIdx.x];
-    if (warp == 1) tmem_alloc<256>(smem_u32(&tmem_slot));
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = tmem_slot;                // columns [0,128): E half, [128,160): D accumulator
-    const int ntiles = a.B * a.tiles_per_patch;
-
-    if (warp == 0) {
-        if (elect_one_sync()) {
-            tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_we); tma_prefetch_desc(&tm_wd);
-            mbar_arrive_expect_tx(BAR(WBAR), 65536);
-            tma_load_2d(we_smem, &tm_we, BAR(WBAR), 0, 0);
-            for (int j = 0; j < 8; ++j) tma_load_2d(wd_smem + j * 4096, &tm_wd, BAR(WBAR), 32 * j, 0);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
-                const long long row0 = a.g.lead + (long long)b * a.g.pstride + a.g.row0 + j * 128;
-                const uint32_t stg = it & 1, ph = (it >> 1) & 1;
-                mbar_wait(BAR(EMPTY + stg), ph ^ 1);
-                mbar_arrive_expect_tx(BAR(FULL + stg), 16384);
-                tma_load_2d(x_smem + stg * 16384, &tm_x, BAR(FULL + stg), 0, (int)row0);
-            }
-        }
-    } else if (warp == 1) {
-        if (elect_one_sync()) {
-            constexpr uint64_t HI = smem_desc_hi(16, 1024, 2);
-            constexpr uint32_t IDESC1 = instr_desc(2, 128, 128, 0, 0);   // E half: N = 128
-            constexpr uint32_t IDESC2 = instr_desc(2, 128, 32, 0, 0);    // D: N = 32
-            mbar_wait(BAR(WBAR), 0);
-            tc_fence_after();
-            uint32_t it = 0, n_e = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const uint32_t stg = it & 1, ph = (it >> 1) & 1;
-                mbar_wait(BAR(FULL + stg), ph);
-                tc_fence_after();
-                const uint64_t xdesc = smem_desc(HI, x_smem + stg * 16384);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint64_t wdesc = smem_desc(HI, we_smem + h * 16384);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_ss<true>(tmem, xdesc + 2 * ks, wdesc + 2 * ks, IDESC1, ks > 0);
-                    if (h == 1) umma_commit(BAR(EMPTY + stg));          // X tile consumed
-                    umma_commit(BAR(D1));
-                    mbar_wait(BAR(EB), n_e & 1); ++n_e;                  // relu(E_h) is back in TMEM
-                    tc_fence_after();
-                    if (h == 0) { mbar_wait(BAR(D2FREE), (it & 1) ^ 1); tc_fence_after(); }   // previous tile's D has been read
-#pragma unroll
-                    for (int ks = 0; ks < 16; ++ks) {
-                        const uint64_t bdesc = smem_desc(HI, wd_smem + (4 * h + (ks >> 2)) * 4096) + 2 * (ks & 3);
-                        umma_ts<true>(tmem + 128, tmem + ks * 8, bdesc, IDESC2, (h > 0 || ks > 0) ? 1u : 0u);
-                    }
-                }
-                umma_commit(BAR(D2));
-            }
-        }
-    } else {
-        const int q = warp & 3;
-        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-        uint32_t it = 0, n_d1 = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
-            const int r = a.g.row0 + j * 128 + q * 32 + lane;
-            const bool in_patch = r < a.g.row0 + a.g.nrows && r < a.g.pstride;
-            const bool valid = in_patch && row_valid(a.g, r);
-            const long long orow = a.g.lead + (long long)b * a.g.pstride + r;
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                mbar_wait(BAR(D1), n_d1 & 1); ++n_d1;
-                tc_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(lane_base + c * 32, v);
-                    tmem_ld_wait();
-                    const float* be = s_be + h * 128 + c * 32;
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(rna_tf32(fmaxf(__uint_as_float(v[e]) + be[e], 0.f)));
-                    tmem_st32(lane_base + c * 32, v);
-                }
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(EB));
-            }
-            mbar_wait(BAR(D2), it & 1);
-            tc_fence_after();
-            uint32_t v[32];
-            tmem_ld32(lane_base + 128, v);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(D2FREE));
-            if (in_patch) {
-                float4* yp = reinterpret_cast<float4*>(a.d + orow * 32);
-#pragma unroll
-                for (int g4 = 0; g4 < 8; ++g4) {
-                    float o[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        o[e] = valid ? __uint_as_float(v[g4 * 4 + e]) + s_bd[g4 * 4 + e] : 0.f;
-                        if (a.round_tf32) o[e] = rna_tf32(o[e]);
-                    }
-                    yp[g4] = make_float4(o[0], o[1], o[2], o[3]);
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc<256>(tmem);
-}
-
 // ----------------------------------------------------------------------------------------------------------------
-//   backward, data path     gA = ((gD Wd^T) .* [X We^T + be > 0]) We + G   (.* relumask)        resfront_bwd_data_kernel
-//       rows on TMEM lanes, per half h of the expanded channels:
-//         MMA (SS)  E_h  = X  . We_h^T        (recomputed, never stored)          TMEM cols [0,128)
-//         MMA (SS)  gE_h = gD . Wd_h          (decConv data gradient)             TMEM cols [128,256)
-//         epilogue  gZ_h = tf32(gE_h where E_h + be_h > 0 else 0)  in place over gE_h
-//         MMA (TS)  gA  += gZ_h . We_h        (expConv data gradient)             TMEM cols [256,288)
-//       final epilogue: + G (skip connection), optional ReLU mask of the layer below, zero-padding mask, store.
-struct ResBwdDataArgs {
+// Forward and backward-data share one kernel (MODE 0 / 1): both are
+//     MMA1 (SS)  H_h[128 x 128] = T[128 x 32] . W1_h^T      T = X (fwd) | gD (bwd);  W1 = We^T (fwd) | Wd (bwd)
+//     epilogue   H_h <- f(H_h) in place in TMEM               fwd: tf32(relu(. + be)), emits the ReLU bit mask (32 B / row)
+//                                                             bwd: tf32(.) where the forward's mask bit is set, else 0
+//     MMA2 (TS)  O[128 x 32] += H_h . W2_h^T                 W2 = Wd^T (fwd) | We (bwd)
+//     final      fwd: O + bd;  bwd: O + G (skip connection), ReLU mask of the layer below;  zero-padding mask, store
+// The unit of pipelining is a half tile (128 rows x 128 expanded channels).  TMEM holds three H buffers (384 columns) and
+// two O accumulators (64 columns): the MMA thread issues MMA1 of unit u+1 BEFORE MMA2 of unit u, so the tensor pipe works
+// on the next unit while the epilogue warps stream unit u through tcgen05.ld/st (TMEM reads run at ~64-100 B/cycle/SM,
+// profiles/r01_tmem_rate_probe.log, and are this kernel's floor).  tcgen05 instructions execute in issue order, which
+// is what makes re-using an H buffer three units later safe without another barrier.  Two epilogue groups of four
+// warps take alternate tiles.
+constexpr int RP_THREADS = 320;
+
+struct ResPipeArgs {
     int B, tiles_per_patch;
     RowGeom g;
-    const float* bias_e;               // [256]
-    const float* residual;             // G rows [.. x 32]
-    const float* relumask;             // rows [.. x 32] or nullptr
-    float* ga;                         // output rows [.. x 32]
+    const float* bias1;                // fwd: be [256]
+    const float* bias2;                // fwd: bd [32]
+    uint32_t* mask;                    // [rows][8] ReLU bit mask: written by fwd (nullable), read by bwd
+    const float* residual;             // bwd: G rows
+    const float* relumask;             // bwd: rows or nullptr
+    float* out;                        // rows [.. x 32]
     int round_tf32;
 };
 
-__global__ void __launch_bounds__(RF_THREADS, 1)
-resfront_bwd_data_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_gd,
-                         const __grid_constant__ CUtensorMap tm_weT, const __grid_constant__ CUtensorMap tm_wd,
-                         const __grid_constant__ CUtensorMap tm_we, const ResBwdDataArgs a) {
+template <int MODE>
+__global__ void __launch_bounds__(RP_THREADS, 1)
+resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant__ CUtensorMap tm_w1,
+                     const __grid_constant__ CUtensorMap tm_w2, const ResPipeArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[9];
+    __shared__ __align__(8) uint64_t bars[17];
     __shared__ uint32_t tmem_slot;
-    __shared__ float s_be[256];
+    __shared__ __align__(16) float s_b1[256];
+    __shared__ __align__(16) float s_b2[32];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t weT_smem = base;                 // We^T [256 rows(ch) x 32 ci]       B operand of E = X We^T
-    const uint32_t wd_smem = base + 32768;          // Wd   [256 rows(ch) x 32 co]       B operand of gE = gD Wd
-    const uint32_t we_smem = base + 65536;          // We   8 chunks x [32 rows(ci) x 32 ch]   B operand of gA = gZ We
-    const uint32_t st_smem = base + 98304;          // 2 stages x { X [128 x 32], gD [128 x 32] }
+    const uint32_t w1_smem = base;                  // [256 rows x 128 B]: two halves of 128 rows
+    const uint32_t w2_smem = base + 32768;          // 8 K-chunks x [32 rows x 128 B]
+    const uint32_t t_smem = base + 65536;           // 3 stages x [128 rows x 128 B]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto BAR = [&](int i) { return smem_u32(&bars[i]); };
-    const int FULL = 0, EMPTY = 2, WBAR = 4, D1 = 5, EB = 6, D2 = 7, D2FREE = 8;
+    const int FULL = 0, EMPTY = 3, WBAR = 6, EFULL = 7, EREADY = 10, DFULL = 13, DFREE = 15;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
-        mbar_init(BAR(WBAR), 1); mbar_init(BAR(D1), 1); mbar_init(BAR(EB), 4); mbar_init(BAR(D2), 1); mbar_init(BAR(D2FREE), 4);
+        for (int i = 0; i < 3; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); mbar_init(BAR(EFULL + i), 1); mbar_init(BAR(EREADY + i), 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(DFULL + i), 1); mbar_init(BAR(DFREE + i), 4); }
+        mbar_init(BAR(WBAR), 1);
         fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < 256; i += RF_THREADS) s_be[i] = a.bias_e[i];
+    if (MODE == 0) {
+        for (int i = threadIdx.x; i < 256; i += RP_THREADS) s_b1[i] = a.bias1[i];
+        if (threadIdx.x < 32) s_b2[threadIdx.x] = a.bias2[threadIdx.x];
+    }
     if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = tmem_slot;
+    const uint32_t tmem = tmem_slot;                // H buffers at columns 0 / 128 / 256, O accumulators at 384 / 416
     const int ntiles = a.B * a.tiles_per_patch;
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     if (warp == 0) {
         if (elect_one_sync()) {
-            tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_gd);
-            mbar_arrive_expect_tx(BAR(WBAR), 98304);
-            tma_load_2d(weT_smem, &tm_weT, BAR(WBAR), 0, 0);
-            tma_load_2d(wd_smem, &tm_wd, BAR(WBAR), 0, 0);
-            for (int j = 0; j < 8; ++j) tma_load_2d(we_smem + j * 4096, &tm_we, BAR(WBAR), 32 * j, 0);
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            tma_prefetch_desc(&tm_t);
+            mbar_arrive_expect_tx(BAR(WBAR), 65536);
+            tma_load_2d(w1_smem, &tm_w1, BAR(WBAR), 0, 0);
+            for (int j = 0; j < 8; ++j) tma_load_2d(w2_smem + j * 4096, &tm_w2, BAR(WBAR), 32 * j, 0);
+            for (int tl = 0; tl < my_tiles; ++tl) {
+                const int tile = blockIdx.x + tl * gridDim.x;
                 const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
                 const long long row0 = a.g.lead + (long long)b * a.g.pstride + a.g.row0 + j * 128;
-                const uint32_t stg = it & 1, ph = (it >> 1) & 1;
+                const uint32_t stg = tl % 3, ph = (tl / 3) & 1;
                 mbar_wait(BAR(EMPTY + stg), ph ^ 1);
-                mbar_arrive_expect_tx(BAR(FULL + stg), 32768);
-                tma_load_2d(st_smem + stg * 32768, &tm_x, BAR(FULL + stg), 0, (int)row0);
-                tma_load_2d(st_smem + stg * 32768 + 16384, &tm_gd, BAR(FULL + stg), 0, (int)row0);
+                mbar_arrive_expect_tx(BAR(FULL + stg), 16384);
+                tma_load_2d(t_smem + stg * 16384, &tm_t, BAR(FULL + stg), 0, (int)row0);
             }
         }
     } else if (warp == 1) {
         if (elect_one_sync()) {
             constexpr uint64_t HI = smem_desc_hi(16, 1024, 2);
+            constexpr uint32_t HI32 = (uint32_t)(HI >> 32), LO32 = (uint32_t)HI;
             constexpr uint32_t IDESC1 = instr_desc(2, 128, 128, 0, 0);
             constexpr uint32_t IDESC2 = instr_desc(2, 128, 32, 0, 0);
             mbar_wait(BAR(WBAR), 0);
             tc_fence_after();
-            uint32_t it = 0, n_e = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const uint32_t stg = it & 1, ph = (it >> 1) & 1;
-                mbar_wait(BAR(FULL + stg), ph);
-                tc_fence_after();
-                const uint64_t xdesc = smem_desc(HI, st_smem + stg * 32768), gdesc = smem_desc(HI, st_smem + stg * 32768 + 16384);
+            const int U = 2 * my_tiles;
+            for (int u = 0; u <= U; ++u) {
+                if (u < U) {                        // MMA1 of unit u
+                    const int tl = u >> 1, h = u & 1;
+                    const uint32_t stg = tl % 3, ph = (tl / 3) & 1, eb = u % 3;
+                    if (h == 0) { mbar_wait(BAR(FULL + stg), ph); tc_fence_after(); }
+                    const uint32_t t_lo = ((t_smem + stg * 16384) >> 4) | LO32, w_lo = ((w1_smem + h * 16384) >> 4) | LO32;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint64_t w1 = smem_desc(HI, weT_smem + h * 16384), w2 = smem_desc(HI, wd_smem + h * 16384);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_ss<true>(tmem, xdesc + 2 * ks, w1 + 2 * ks, IDESC1, ks > 0);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_ss<true>(tmem + 128, gdesc + 2 * ks, w2 + 2 * ks, IDESC1, ks > 0);
+                    for (int ks = 0; ks < 4; ++ks) umma_ss_tf32_lohi(tmem + eb * 128, t_lo + 2 * ks, w_lo + 2 * ks, HI32, IDESC1, ks > 0);
                     if (h == 1) umma_commit(BAR(EMPTY + stg));
-                    umma_commit(BAR(D1));
-                    mbar_wait(BAR(EB), n_e & 1); ++n_e;
+                    umma_commit(BAR(EFULL + eb));
+                }
+                if (u >= 1) {                       // MMA2 of unit u - 1
+                    const int v = u - 1, tl = v >> 1, h = v & 1;
+                    const uint32_t eb = v % 3, db = tl & 1;
+                    mbar_wait(BAR(EREADY + eb), (v / 3) & 1);
                     tc_fence_after();
-                    if (h == 0) { mbar_wait(BAR(D2FREE), (it & 1) ^ 1); tc_fence_after(); }
+                    if (h == 0) { mbar_wait(BAR(DFREE + db), ((tl >> 1) & 1) ^ 1); tc_fence_after(); }
 #pragma unroll
                     for (int ks = 0; ks < 16; ++ks) {
-                        const uint64_t bdesc = smem_desc(HI, we_smem + (4 * h + (ks >> 2)) * 4096) + 2 * (ks & 3);
-                        umma_ts<true>(tmem + 256, tmem + 128 + ks * 8, bdesc, IDESC2, (h > 0 || ks > 0) ? 1u : 0u);
+                        const uint64_t bdesc = smem_desc(HI, w2_smem + (4 * h + (ks >> 2)) * 4096) + 2 * (ks & 3);
+                        umma_ts<true>(tmem + 384 + 32 * db, tmem + eb * 128 + ks * 8, bdesc, IDESC2, (h > 0 || ks > 0) ? 1u : 0u);
                     }
+                    if (h == 1) umma_commit(BAR(DFULL + db));
                 }
-                umma_commit(BAR(D2));
             }
         }
     } else {
         const int q = warp & 3;
+        const int grp = (warp - 2) >> 2;
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-        uint32_t it = 0, n_d1 = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        for (int tl = grp; tl < my_tiles; tl += 2) {
+            const int tile = blockIdx.x + tl * gridDim.x;
             const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
             const int r = a.g.row0 + j * 128 + q * 32 + lane;
             const bool in_patch = r < a.g.row0 + a.g.nrows && r < a.g.pstride;
             const bool valid = in_patch && row_valid(a.g, r);
             const long long orow = a.g.lead + (long long)b * a.g.pstride + r;
-            float4 pre_r[8], pre_m[8];
+            // ReLU bits of this row: word (h, c) covers expanded channels h*128 + c*32 .. +31, element e at bit 31 - e,
+            // 1 = activation positive.  fwd builds them with one funnel shift per element, bwd tests them.
+            uint4 mlo = make_uint4(0u, 0u, 0u, 0u), mhi = mlo;
+            float4 pre_r[8];
+            if (MODE == 1) {
+                mlo = __ldg(reinterpret_cast<const uint4*>(a.mask + orow * 8));
+                mhi = __ldg(reinterpret_cast<const uint4*>(a.mask + orow * 8) + 1);
 #pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) {
-                pre_r[g4] = (a.residual && in_patch) ? __ldg(reinterpret_cast<const float4*>(a.residual + orow * 32) + g4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                pre_m[g4] = (a.relumask && in_patch) ? __ldg(reinterpret_cast<const float4*>(a.relumask + orow * 32) + g4) : make_float4(1.f, 1.f, 1.f, 1.f);
+                for (int g4 = 0; g4 < 8; ++g4)
+                    pre_r[g4] = (a.residual && in_patch) ? __ldg(reinterpret_cast<const float4*>(a.residual + orow * 32) + g4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                mbar_wait(BAR(D1), n_d1 & 1); ++n_d1;
+            for (int h = 0; h < 2; ++h) {                     // rolled on purpose: the unrolled body thrashes the instruction cache
+                const int u = 2 * tl + h;
+                const uint32_t eb = u % 3, hb = lane_base + eb * 128;
+                uint4 w4 = h ? mhi : mlo;
+                uint32_t wd[4] = {w4.x, w4.y, w4.z, w4.w};
+                mbar_wait(BAR(EFULL + eb), (u / 3) & 1);
                 tc_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t e[32], v[32];
-                    tmem_ld32(lane_base + c * 32, e);
-                    tmem_ld32(lane_base + 128 + c * 32, v);
-                    tmem_ld_wait();
-                    const float* be = s_be + h * 128 + c * 32;
+                uint32_t va[32], vb[32];
+                tmem_ld32(hb, va);
 #pragma unroll
-                    for (int k = 0; k < 32; ++k)
-                        v[k] = (__uint_as_float(e[k]) + be[k] > 0.f) ? __float_as_uint(rna_tf32(__uint_as_float(v[k]))) : 0u;
-                    tmem_st32(lane_base + 128 + c * 32, v);
+                for (int c = 0; c < 4; ++c) {                 // chunk c lives in va (c even) or vb (c odd); the next chunk's load is
+                    tmem_ld_wait();                           // issued before this one is processed
+                    uint32_t (&cur)[32] = (c & 1) ? vb : va;
+                    uint32_t (&nxt)[32] = (c & 1) ? va : vb;
+                    if (c < 3) tmem_ld32(hb + (c + 1) * 32, nxt);
+                    if (MODE == 0) {
+                        uint32_t sgn = 0;
+                        const float4* be4 = reinterpret_cast<const float4*>(s_b1 + h * 128 + c * 32);
+#pragma unroll
+                        for (int e4 = 0; e4 < 8; ++e4) {
+                            const float4 bq = be4[e4];
+                            const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                // x = relu(y) >= +0; (bits(x) - 1) has its sign bit set exactly when x == 0, i.e. when y <= 0,
+                                // which is tf.nn.relu's gradient convention (0 at y == 0)
+                                const uint32_t x = __float_as_uint(rna_tf32(fmaxf(__uint_as_float(cur[e4 * 4 + e]) + bb[e], 0.f)));
+                                sgn = __funnelshift_l(x - 1u, sgn, 1);
+                                cur[e4 * 4 + e] = x;
+                            }
+                        }
+                        wd[c] = ~sgn;
+                    } else {
+                        const uint32_t bits = wd[c];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            cur[e] = __float_as_uint(rna_tf32(__uint_as_float(cur[e]))) & (uint32_t)((int32_t)(bits << e) >> 31);
+                    }
+                    tmem_st32(hb + c * 32, cur);
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(EB));
+                if (lane == 0) mbar_arrive(BAR(EREADY + eb));
+                if (MODE == 0) { w4 = make_uint4(wd[0], wd[1], wd[2], wd[3]); if (h) mhi = w4; else mlo = w4; }
             }
-            mbar_wait(BAR(D2), it & 1);
+            if (MODE == 0 && a.mask && in_patch) {
+                uint4* mp = reinterpret_cast<uint4*>(a.mask + orow * 8);
+                mp[0] = mlo;
+                mp[1] = mhi;
+            }
+            const uint32_t db = tl & 1;
+            mbar_wait(BAR(DFULL + db), (tl >> 1) & 1);
             tc_fence_after();
             uint32_t v[32];
-            tmem_ld32(lane_base + 256, v);
+            tmem_ld32(lane_base + 384 + 32 * db, v);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(D2FREE));
+            if (lane == 0) mbar_arrive(BAR(DFREE + db));
             if (in_patch) {
-                float4* yp = reinterpret_cast<float4*>(a.ga + orow * 32);
+                float4* yp = reinterpret_cast<float4*>(a.out + orow * 32);
 #pragma unroll
                 for (int g4 = 0; g4 < 8; ++g4) {
-                    float o[4] = {__uint_as_float(v[g4 * 4]) + pre_r[g4].x, __uint_as_float(v[g4 * 4 + 1]) + pre_r[g4].y,
-                                  __uint_as_float(v[g4 * 4 + 2]) + pre_r[g4].z, __uint_as_float(v[g4 * 4 + 3]) + pre_r[g4].w};
-                    const float mk[4] = {pre_m[g4].x, pre_m[g4].y, pre_m[g4].z, pre_m[g4].w};
+                    float o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[e] = __uint_as_float(v[g4 * 4 + e]);
+                    if (MODE == 0) {
+                        const float4 bq = reinterpret_cast<const float4*>(s_b2)[g4];
+                        o[0] += bq.x; o[1] += bq.y; o[2] += bq.z; o[3] += bq.w;
+                    } else {
+                        o[0] += pre_r[g4].x; o[1] += pre_r[g4].y; o[2] += pre_r[g4].z; o[3] += pre_r[g4].w;
+                        if (a.relumask) {           // only the first block flows into a ReLU (mainConv1): not worth prefetch registers
+                            const float4 mq = __ldg(reinterpret_cast<const float4*>(a.relumask + orow * 32) + g4);
+                            if (!(mq.x > 0.f)) o[0] = 0.f;
+                            if (!(mq.y > 0.f)) o[1] = 0.f;
+                            if (!(mq.z > 0.f)) o[2] = 0.f;
+                            if (!(mq.w > 0.f)) o[3] = 0.f;
+                        }
+                    }
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        if (!(mk[e] > 0.f) || !valid) o[e] = 0.f;
+                        if (!valid) o[e] = 0.f;
                         if (a.round_tf32) o[e] = rna_tf32(o[e]);
                     }
                     yp[g4] = make_float4(o[0], o[1], o[2], o[3]);
@@ -534,65 +456,51 @@ __global__ void resfront_reduce_kernel(const float* __restrict__ partials, const
     }
 }
 
-}  // namespace
-
-// D = decConv(relu(expConv(X))) on PR rows.  weT_exp [256][32], weT_dec [32][256], biases padded to 256 / 32.
-int launch_resfront_fwd_tc(const float* x, const float* weT_exp, const float* weT_dec, const float* bias_e, const float* bias_d,
-                           float* d, const RowGeom& g, int B, int round_tf32, double flops, cudaStream_t st) {
-    ResFwdArgs a;
-    memset(&a, 0, sizeof a);
-    a.B = B; a.tiles_per_patch = cdiv(g.nrows, 128); a.g = g; a.bias_e = bias_e; a.bias_d = bias_d; a.d = d; a.round_tf32 = round_tf32;
-    const long long rows = g.lead + (long long)B * g.pstride + ROW_TAIL;
-    CUtensorMap tm_x, tm_we, tm_wd;
-    PV_TRY(make_tmap_2d(&tm_x, x, rows, 32, 128, 32, 0));
-    PV_TRY(make_tmap_2d(&tm_we, weT_exp, 256, 32, 256, 32, 0));
-    PV_TRY(make_tmap_2d(&tm_wd, weT_dec, 32, 256, 32, 32, 0));
-    const size_t smem = 1024 + 65536 + 2 * 16384;
+template <int MODE>
+static int launch_respipe(const float* t, const float* w1, const float* w2, const ResPipeArgs& a0, const char* tag, double flops, cudaStream_t st) {
+    ResPipeArgs a = a0;
+    a.tiles_per_patch = cdiv(a.g.nrows, 128);
+    const long long rows = a.g.lead + (long long)a.B * a.g.pstride + ROW_TAIL;
+    CUtensorMap tm_t, tm_w1, tm_w2;
+    PV_TRY(make_tmap_2d(&tm_t, t, rows, 32, 128, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_w1, w1, 256, 32, 256, 32, 0));      // [256 rows][32]: We^T (fwd) | Wd (bwd)
+    PV_TRY(make_tmap_2d(&tm_w2, w2, 32, 256, 32, 32, 0));       // [32 rows][256]: Wd^T (fwd) | We (bwd)
+    const size_t smem = 1024 + 65536 + 3 * 16384;
     static bool attr = false;
-    if (!attr) { PV_CUDA(cudaFuncSetAttribute(resfront_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int ntiles = a.B * a.tiles_per_patch;
-    const int grid = ntiles < 2 * sms ? ntiles : 2 * sms;
-    PV_TIMED("resfront_fwd", st, flops, 0.0);
-    resfront_fwd_kernel<<<grid, RF_THREADS, smem, st>>>(tm_x, tm_we, tm_wd, a);
-    PV_LAUNCH_CHECK();
-    return 0;
-}
-
-}  // namespace pv
-
-namespace pv {
-// gA = dgrad_exp(dgrad_dec(gD) .* relu'(E)) + G, E recomputed from X.  weT_exp [256][32], w_dec [256][32] (= weff of decConv),
-// w_exp [32][256] (= weff of expConv)
-int launch_resfront_bwd_data_tc(const float* x, const float* gd, const float* weT_exp, const float* w_dec, const float* w_exp,
-                                const float* bias_e, const float* residual, const float* relumask, float* ga, const RowGeom& g,
-                                int B, int round_tf32, double flops, cudaStream_t st) {
-    ResBwdDataArgs a;
-    memset(&a, 0, sizeof a);
-    a.B = B; a.tiles_per_patch = cdiv(g.nrows, 128); a.g = g; a.bias_e = bias_e; a.residual = residual; a.relumask = relumask;
-    a.ga = ga; a.round_tf32 = round_tf32;
-    const long long rows = g.lead + (long long)B * g.pstride + ROW_TAIL;
-    CUtensorMap tm_x, tm_gd, tm_weT, tm_wd, tm_we;
-    PV_TRY(make_tmap_2d(&tm_x, x, rows, 32, 128, 32, 0));
-    PV_TRY(make_tmap_2d(&tm_gd, gd, rows, 32, 128, 32, 0));
-    PV_TRY(make_tmap_2d(&tm_weT, weT_exp, 256, 32, 256, 32, 0));
-    PV_TRY(make_tmap_2d(&tm_wd, w_dec, 256, 32, 256, 32, 0));
-    PV_TRY(make_tmap_2d(&tm_we, w_exp, 32, 256, 32, 32, 0));
-    const size_t smem = 1024 + 98304 + 2 * 32768;
-    static bool attr = false;
-    if (!attr) { PV_CUDA(cudaFuncSetAttribute(resfront_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    if (!attr) { PV_CUDA(cudaFuncSetAttribute(resfront_pipe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = a.B * a.tiles_per_patch;
     const int grid = ntiles < sms ? ntiles : sms;
-    PV_TIMED("resfront_bwd_data", st, flops, 0.0);
-    resfront_bwd_data_kernel<<<grid, RF_THREADS, smem, st>>>(tm_x, tm_gd, tm_weT, tm_wd, tm_we, a);
+    PV_TIMED(tag, st, flops, 0.0);
+    resfront_pipe_kernel<MODE><<<grid, RP_THREADS, smem, st>>>(tm_t, tm_w1, tm_w2, a);
     PV_LAUNCH_CHECK();
     return 0;
 }
+
+}  // namespace
+
+// D = decConv(relu(expConv(X))) on PR rows.  weT_exp [256][32], weT_dec [32][256], biases padded to 256 / 32.
+// relu_bits (nullable): [rows][8] uint32, bit (c % 32) of word c / 32 = (E[row][c] > 0), consumed by the backward-data kernel.
+int launch_resfront_fwd_tc(const float* x, const float* weT_exp, const float* weT_dec, const float* bias_e, const float* bias_d,
+                           float* d, uint32_t* relu_bits, const RowGeom& g, int B, int round_tf32, double flops, cudaStream_t st) {
+    ResPipeArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.g = g; a.bias1 = bias_e; a.bias2 = bias_d; a.mask = relu_bits; a.out = d; a.round_tf32 = round_tf32;
+    return launch_respipe<0>(x, weT_exp, weT_dec, a, "resfront_fwd", flops, st);
+}
+
+// gA = ((gD Wd^T) .* relu_bits) We + G  (.* relumask).  w_dec [256][32] (= weff of decConv), w_exp [32][256] (= weff of expConv)
+int launch_resfront_bwd_data_tc(const float* gd, const float* w_dec, const float* w_exp, const uint32_t* relu_bits,
+                                const float* residual, const float* relumask, float* ga, const RowGeom& g,
+                                int B, int round_tf32, double flops, cudaStream_t st) {
+    ResPipeArgs a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.g = g; a.mask = const_cast<uint32_t*>(relu_bits); a.residual = residual; a.relumask = relumask; a.out = ga; a.round_tf32 = round_tf32;
+    return launch_respipe<1>(gd, w_dec, w_exp, a, "resfront_bwd_data", flops, st);
+}
+
 }  // namespace pv
 
 namespace pv {

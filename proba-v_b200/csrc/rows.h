@@ -91,12 +91,12 @@ int launch_rowwgrad_simt(const RowWgradP& p, cudaStream_t st);
 int launch_rowconv_tc(const RowConvP& p, cudaStream_t st);          // tcgen05 + TMA implicit GEMM (conv_tc.cu)
 int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, size_t partial_floats);
 
-// fused expConv + ReLU + decConv of one residual block (resblock_tc.cu); the expanded tensor stays in TMEM
+// fused expConv + ReLU + decConv of one residual block (resblock_tc.cu); the expanded tensor stays in TMEM.
+// relu_bits: [rows][8] uint32 ReLU bit mask written by the forward (nullable) and consumed by the backward-data kernel.
 int launch_resfront_fwd_tc(const float* x, const float* weT_exp, const float* weT_dec, const float* bias_e, const float* bias_d,
-                           float* d, const RowGeom& g, int B, int round_tf32, double flops, cudaStream_t st);
-
-int launch_resfront_bwd_data_tc(const float* x, const float* gd, const float* weT_exp, const float* w_dec, const float* w_exp,
-                                const float* bias_e, const float* residual, const float* relumask, float* ga, const RowGeom& g,
+                           float* d, uint32_t* relu_bits, const RowGeom& g, int B, int round_tf32, double flops, cudaStream_t st);
+int launch_resfront_bwd_data_tc(const float* gd, const float* w_dec, const float* w_exp, const uint32_t* relu_bits,
+                                const float* residual, const float* relumask, float* ga, const RowGeom& g,
                                 int B, int round_tf32, double flops, cudaStream_t st);
 int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* weT_exp, const float* w_dec, const float* bias_e,
                                   float* dw_dec, float* dw_exp, float* db_exp, float* db_dec, const RowGeom& g, int B,
