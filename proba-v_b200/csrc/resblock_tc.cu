@@ -270,21 +270,25 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
 //         MMA (TS)  dWd_h[ch x co] += E_h^T  . gD   (B = gD tile read MN-major: 32B-atom swizzled copy)  cols [256+32h, +32)
 //         MMA (TS)  dWe_h[ch x ci] += gZ_h^T . X    (B = X tile read MN-major)                            cols [320+32h, +32)
 //       The four [128 x 32] accumulators stay in TMEM for the CTA's lifetime; per-CTA partials are reduced afterwards.
+//       Pipelining unit = (half h of the channels, 64-row sub-tile s): E^T and gE^T of a unit take 64 + 64 TMEM columns;
+//       three unit buffers (384 columns) + the four accumulators (128 columns) fill TMEM exactly.  As in the forward
+//       kernel the MMA thread issues the two SS MMAs of unit u+1 before the two TS MMAs of unit u, and two epilogue
+//       groups of four warps take alternate units.
 struct ResBwdWeightArgs {
     int B, tiles_per_patch;
     RowGeom g;
     const float* bias_e;
     float* partials;                   // [cta][4][128][32]: dWd half 0, half 1, dWe^T half 0, half 1
-    float* db_partials;                // [cta][256 (dbe) + 4 x 32 (dbd per epilogue warp)]
+    float* db_partials;                // [cta][2 groups][256 (dbe)] then [cta][8 warps][32 (dbd)]
 };
 
-__global__ void __launch_bounds__(RF_THREADS, 1)
+__global__ void __launch_bounds__(RP_THREADS, 1)
 resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_gd,
                            const __grid_constant__ CUtensorMap tm_x32, const __grid_constant__ CUtensorMap tm_gd32,
                            const __grid_constant__ CUtensorMap tm_weT, const __grid_constant__ CUtensorMap tm_wd,
                            const ResBwdWeightArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[8];
+    __shared__ __align__(8) uint64_t bars[12];
     __shared__ uint32_t tmem_slot;
     __shared__ float s_be[256];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -293,31 +297,33 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
     const uint32_t st_smem = base + 65536;          // 2 stages x { X (K-major), gD (K-major), X (MN), gD (MN) } x 16 KB
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto BAR = [&](int i) { return smem_u32(&bars[i]); };
-    const int FULL = 0, EMPTY = 2, WBAR = 4, D1 = 5, EB = 6, DONE = 7;
+    const int FULL = 0, EMPTY = 2, WBAR = 4, EFULL = 5, EREADY = 8, DONE = 11;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1 + 4); }
-        mbar_init(BAR(WBAR), 1); mbar_init(BAR(D1), 1); mbar_init(BAR(EB), 4); mbar_init(BAR(DONE), 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1 + 8); }
+        for (int i = 0; i < 3; ++i) { mbar_init(BAR(EFULL + i), 1); mbar_init(BAR(EREADY + i), 4); }
+        mbar_init(BAR(WBAR), 1); mbar_init(BAR(DONE), 1);
         fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < 256; i += RF_THREADS) s_be[i] = a.bias_e[i];
+    for (int i = threadIdx.x; i < 256; i += RP_THREADS) s_be[i] = a.bias_e[i];
     if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = tmem_slot;
+    const uint32_t tmem = tmem_slot;                // unit buffers at columns 0 / 128 / 256 (E^T | gE^T), accumulators at 384 + 32 k
     const int ntiles = a.B * a.tiles_per_patch;
     const int t_lo = (int)((long long)ntiles * blockIdx.x / gridDim.x), t_hi = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
+    const int my_tiles = t_hi - t_lo;
 
     if (warp == 0) {
         if (elect_one_sync()) {
             mbar_arrive_expect_tx(BAR(WBAR), 65536);
             tma_load_2d(weT_smem, &tm_weT, BAR(WBAR), 0, 0);
             tma_load_2d(wd_smem, &tm_wd, BAR(WBAR), 0, 0);
-            uint32_t it = 0;
-            for (int tile = t_lo; tile < t_hi; ++tile, ++it) {
+            for (int tl = 0; tl < my_tiles; ++tl) {
+                const int tile = t_lo + tl;
                 const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
                 const int row0 = (int)(a.g.lead + (long long)b * a.g.pstride + a.g.row0 + j * 128);
-                const uint32_t stg = it & 1, ph = (it >> 1) & 1, sa = st_smem + stg * 65536;
+                const uint32_t stg = tl & 1, ph = (tl >> 1) & 1, sa = st_smem + stg * 65536;
                 mbar_wait(BAR(EMPTY + stg), ph ^ 1);
                 mbar_arrive_expect_tx(BAR(FULL + stg), 65536);
                 tma_load_2d(sa, &tm_x, BAR(FULL + stg), 0, row0);
@@ -329,103 +335,109 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
     } else if (warp == 1) {
         if (elect_one_sync()) {
             constexpr uint64_t HI = smem_desc_hi(16, 1024, 2);            // K-major SW128
+            constexpr uint32_t HI32 = (uint32_t)(HI >> 32), LO32 = (uint32_t)HI;
             constexpr uint64_t HI_MN = smem_desc_hi(128, 512, 1);         // MN-major, 128B swizzle / 32B atom
-            constexpr uint32_t IDESC1 = instr_desc(2, 128, 128, 0, 0);    // [128 ch] x [N = 128 rows]
+            constexpr uint32_t IDESC1 = instr_desc(2, 128, 64, 0, 0);     // [128 ch] x [N = 64 rows]
             constexpr uint32_t IDESC2 = instr_desc(2, 128, 32, 0, 1);     // TS: A from TMEM, B MN-major, N = 32
             mbar_wait(BAR(WBAR), 0);
             tc_fence_after();
-            uint32_t it = 0, n_e = 0;
-            for (int tile = t_lo; tile < t_hi; ++tile, ++it) {
-                const uint32_t stg = it & 1, ph = (it >> 1) & 1, sa = st_smem + stg * 65536;
-                mbar_wait(BAR(FULL + stg), ph);
-                tc_fence_after();
-                const uint64_t xdesc = smem_desc(HI, sa), gdesc = smem_desc(HI, sa + 16384);
-                const uint64_t x32 = smem_desc(HI_MN, sa + 32768), g32 = smem_desc(HI_MN, sa + 49152);
-                const uint32_t first = tile == t_lo ? 0u : 1u;
+            const int U = 4 * my_tiles;
+            for (int u = 0; u <= U; ++u) {
+                if (u < U) {                        // the two SS MMAs of unit u = (tile, h, s)
+                    const int tl = u >> 2, h = (u >> 1) & 1, sub = u & 1;
+                    const uint32_t stg = tl & 1, ph = (tl >> 1) & 1, sa = st_smem + stg * 65536, eb = u % 3;
+                    if ((u & 3) == 0) { mbar_wait(BAR(FULL + stg), ph); tc_fence_after(); }
+                    const uint32_t x_lo = ((sa + sub * 8192) >> 4) | LO32, g_lo = ((sa + 16384 + sub * 8192) >> 4) | LO32;
+                    const uint32_t w1 = ((weT_smem + h * 16384) >> 4) | LO32, w2 = ((wd_smem + h * 16384) >> 4) | LO32;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint64_t w1 = smem_desc(HI, weT_smem + h * 16384), w2 = smem_desc(HI, wd_smem + h * 16384);
+                    for (int ks = 0; ks < 4; ++ks) umma_ss_tf32_lohi(tmem + eb * 128, w1 + 2 * ks, x_lo + 2 * ks, HI32, IDESC1, ks > 0);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_ss<true>(tmem, w1 + 2 * ks, xdesc + 2 * ks, IDESC1, ks > 0);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_ss<true>(tmem + 128, w2 + 2 * ks, gdesc + 2 * ks, IDESC1, ks > 0);
-                    umma_commit(BAR(D1));
-                    mbar_wait(BAR(EB), n_e & 1); ++n_e;
-                    tc_fence_after();
-#pragma unroll
-                    for (int ks = 0; ks < 16; ++ks)       // K = 8 rows per step: 1024 B further into the MN-major tiles
-                        umma_ts<true>(tmem + 256 + 32 * h, tmem + ks * 8, g32 + 64 * ks, IDESC2, (first | (ks > 0)) ? 1u : 0u);
-#pragma unroll
-                    for (int ks = 0; ks < 16; ++ks)
-                        umma_ts<true>(tmem + 320 + 32 * h, tmem + 128 + ks * 8, x32 + 64 * ks, IDESC2, (first | (ks > 0)) ? 1u : 0u);
+                    for (int ks = 0; ks < 4; ++ks) umma_ss_tf32_lohi(tmem + eb * 128 + 64, w2 + 2 * ks, g_lo + 2 * ks, HI32, IDESC1, ks > 0);
+                    umma_commit(BAR(EFULL + eb));
                 }
-                umma_commit(BAR(EMPTY + stg));
+                if (u >= 1) {                       // the two TS MMAs of unit u - 1
+                    const int v = u - 1, tl = v >> 2, h = (v >> 1) & 1, sub = v & 1;
+                    const uint32_t stg = tl & 1, sa = st_smem + stg * 65536, eb = v % 3;
+                    mbar_wait(BAR(EREADY + eb), (v / 3) & 1);
+                    tc_fence_after();
+                    const uint64_t x32 = smem_desc(HI_MN, sa + 32768 + sub * 8192), g32 = smem_desc(HI_MN, sa + 49152 + sub * 8192);
+                    const uint32_t first = (tl == 0 && sub == 0) ? 0u : 1u;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)        // K = 8 rows per step: 1024 B further into the MN-major tiles
+                        umma_ts<true>(tmem + 384 + 32 * h, tmem + eb * 128 + ks * 8, g32 + 64 * ks, IDESC2, (first | (ks > 0)) ? 1u : 0u);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_ts<true>(tmem + 448 + 32 * h, tmem + eb * 128 + 64 + ks * 8, x32 + 64 * ks, IDESC2, (first | (ks > 0)) ? 1u : 0u);
+                    if ((v & 3) == 3) umma_commit(BAR(EMPTY + stg));      // last unit of the tile: the stage may be refilled
+                }
             }
             umma_commit(BAR(DONE));
         }
     } else {
         const int q = warp & 3;
+        const int grp = (warp - 2) >> 2;
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-        float dbe[2] = {0.f, 0.f}, dbd = 0.f;
-        uint32_t it = 0, n_d1 = 0;
-        for (int tile = t_lo; tile < t_hi; ++tile, ++it) {
-            const uint32_t stg = it & 1, ph = (it >> 1) & 1;
-            mbar_wait(BAR(FULL + stg), ph);
-            {   // dbd: column sums of the gD tile (K-major SW128 copy: 16-byte chunk ^= row & 7); warp q takes rows [32q, 32q+32)
+        float dbe0 = 0.f, dbe1 = 0.f, dbd = 0.f;
+        const int U = 4 * my_tiles;
+#pragma unroll 1
+        for (int u = grp; u < U; u += 2) {          // sub-tile s == grp for every unit of this group
+            const int tl = u >> 2, h = (u >> 1) & 1;
+            const uint32_t stg = tl & 1, ph = (tl >> 1) & 1, eb = u % 3;
+            if (h == 0) {   // dbd: column sums of this group's 64 rows of the gD tile (K-major SW128 copy: 16-byte chunk ^= row & 7)
+                mbar_wait(BAR(FULL + stg), ph);
                 const uint8_t* gp = smem_raw + (st_smem - smem_u32(smem_raw)) + stg * 65536 + 16384;
                 float sacc = 0.f;
-                for (int r = q * 32; r < q * 32 + 32; ++r)
+                for (int r = grp * 64 + q * 16; r < grp * 64 + q * 16 + 16; ++r)
                     sacc += *reinterpret_cast<const float*>(gp + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
                 dbd += sacc;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(EMPTY + stg));
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                mbar_wait(BAR(D1), n_d1 & 1); ++n_d1;
-                tc_fence_after();
-                const float be = s_be[h * 128 + q * 32 + lane];       // this thread's channel
-                float zsum = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t e[32], v[32];
-                    tmem_ld32(lane_base + c * 32, e);
-                    tmem_ld32(lane_base + 128 + c * 32, v);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) {
-                        const float ev = fmaxf(__uint_as_float(e[k]) + be, 0.f);
-                        const float zv = ev > 0.f ? rna_tf32(__uint_as_float(v[k])) : 0.f;
-                        zsum += zv;
-                        e[k] = __float_as_uint(rna_tf32(ev));
-                        v[k] = __float_as_uint(zv);
-                    }
-                    tmem_st32(lane_base + c * 32, e);
-                    tmem_st32(lane_base + 128 + c * 32, v);
-                }
-                dbe[h] += zsum;
-                tmem_st_wait();
-                tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(EB));
+                if (lane == 0) mbar_arrive(BAR(EMPTY + stg));
             }
+            mbar_wait(BAR(EFULL + eb), (u / 3) & 1);
+            tc_fence_after();
+            const float be = s_be[h * 128 + q * 32 + lane];           // this thread's channel
+            float zsum = 0.f;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t e[32], v[32];
+                tmem_ld32(lane_base + eb * 128 + c * 32, e);
+                tmem_ld32(lane_base + eb * 128 + 64 + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const uint32_t x = __float_as_uint(rna_tf32(fmaxf(__uint_as_float(e[k]) + be, 0.f)));
+                    const uint32_t z = __float_as_uint(rna_tf32(__uint_as_float(v[k]))) & ~(uint32_t)((int32_t)(x - 1u) >> 31);   // 0 where E == 0
+                    zsum += __uint_as_float(z);
+                    e[k] = x;
+                    v[k] = z;
+                }
+                tmem_st32(lane_base + eb * 128 + c * 32, e);
+                tmem_st32(lane_base + eb * 128 + 64 + c * 32, v);
+            }
+            if (h) dbe1 += zsum; else dbe0 += zsum;
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(EREADY + eb));
         }
-        float* dbp = a.db_partials + (size_t)blockIdx.x * 384;
-        dbp[q * 32 + lane] = dbe[0];
-        dbp[128 + q * 32 + lane] = dbe[1];
-        dbp[256 + q * 32 + lane] = dbd;
+        float* dbp = a.db_partials + (size_t)blockIdx.x * (512 + 256);
+        dbp[grp * 256 + q * 32 + lane] = dbe0;
+        dbp[grp * 256 + 128 + q * 32 + lane] = dbe1;
+        dbp[512 + (grp * 4 + q) * 32 + lane] = dbd;
         mbar_wait(BAR(DONE), 0);
         tc_fence_after();
         float* out = a.partials + (size_t)blockIdx.x * 4 * 4096;
-        for (int g = 0; g < 4; ++g) {
+#pragma unroll 1
+        for (int g2 = 0; g2 < 2; ++g2) {            // group 0 drains the dWd accumulators, group 1 the dWe^T ones
+            const int g = grp * 2 + g2;
             uint32_t v[32];
-            tmem_ld32(lane_base + 256 + g * 32, v);
+            tmem_ld32(lane_base + 384 + g * 32, v);
             tmem_ld_wait();
             float4* o = reinterpret_cast<float4*>(out + ((size_t)g * 128 + q * 32 + lane) * 32);
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-                o[e] = t_hi > t_lo ? make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                o[e] = my_tiles > 0 ? make_float4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     tc_fence_before();
@@ -446,12 +458,12 @@ __global__ void resfront_reduce_kernel(const float* __restrict__ partials, const
     } else if (idx < 4 * 4096 + 256) {
         const int j = idx - 4 * 4096;
         float s = 0.f;
-        for (int c = 0; c < ncta; ++c) s += dbp[(size_t)c * 384 + j];
+        for (int c = 0; c < ncta; ++c) s += dbp[(size_t)c * 768 + j] + dbp[(size_t)c * 768 + 256 + j];     // two epilogue groups
         dbe[j] = s;
     } else if (idx < 4 * 4096 + 256 + 32) {
         const int j = idx - 4 * 4096 - 256;
         float s = 0.f;
-        for (int c = 0; c < ncta; ++c) for (int w = 0; w < 4; ++w) s += dbp[(size_t)c * 384 + 256 + w * 32 + j];
+        for (int c = 0; c < ncta; ++c) for (int w = 0; w < 8; ++w) s += dbp[(size_t)c * 768 + 512 + w * 32 + j];
         dbd[j] = s;
     }
 }
@@ -516,7 +528,7 @@ int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = a.B * a.tiles_per_patch;
     const int grid = ntiles < sms ? ntiles : sms;
-    const size_t need = (size_t)grid * (4 * 4096 + 384);
+    const size_t need = (size_t)grid * (4 * 4096 + 768);
     if (!partials || partial_floats < need) return set_error(PV_ERR_BAD_ARG, "resfront_bwd_weight: partial buffer too small");
     a.partials = partials; a.db_partials = partials + (size_t)grid * 4 * 4096;
     const long long rows = g.lead + (long long)B * g.pstride + ROW_TAIL;
@@ -532,7 +544,7 @@ int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* 
     if (!attr) { PV_CUDA(cudaFuncSetAttribute(resfront_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     {
         PV_TIMED("resfront_bwd_weight", st, flops, 0.0);
-        resfront_bwd_weight_kernel<<<grid, RF_THREADS, smem, st>>>(tm_x, tm_gd, tm_x32, tm_gd32, tm_weT, tm_wd, a);
+        resfront_bwd_weight_kernel<<<grid, RP_THREADS, smem, st>>>(tm_x, tm_gd, tm_x32, tm_gd32, tm_weT, tm_wd, a);
         PV_LAUNCH_CHECK();
     }
     {
