@@ -450,8 +450,14 @@ __global__ void resfront_reduce_kernel(const float* __restrict__ partials, const
                                        float* __restrict__ dwd, float* __restrict__ dwe, float* __restrict__ dbe, float* __restrict__ dbd) {
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx < 4 * 4096) {
-        float s = 0.f;
-        for (int c = 0; c < ncta; ++c) s += partials[(size_t)c * 16384 + idx];
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int c = 0;
+        for (; c + 3 < ncta; c += 4) {
+            s0 += partials[(size_t)c * 16384 + idx]; s1 += partials[(size_t)(c + 1) * 16384 + idx];
+            s2 += partials[(size_t)(c + 2) * 16384 + idx]; s3 += partials[(size_t)(c + 3) * 16384 + idx];
+        }
+        for (; c < ncta; ++c) s0 += partials[(size_t)c * 16384 + idx];
+        const float s = (s0 + s1) + (s2 + s3);
         const int g = idx / 4096, m = (idx / 32) % 128, n = idx % 32;
         if (g < 2) dwd[(size_t)(g * 128 + m) * 32 + n] = s;                 // [ch][co]
         else dwe[(size_t)n * 256 + (g - 2) * 128 + m] = s;                  // [ci][ch]

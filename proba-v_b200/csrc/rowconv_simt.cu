@@ -222,52 +222,62 @@ __global__ void __launch_bounds__(256) first_conv_pr_kernel(const float* __restr
     *reinterpret_cast<float4*>(o + 4) = make_float4(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
 }
 
-// dw[tap][n] += sum_vox xn[vox + tap] * gz[row(vox)][n]; db[n] += sum gz.  lane = n, one warp walks voxels.
+// dw[tap][n] = sum_vox xn[vox + tap] * gz[row(vox)][n]; db[n] = sum gz.  A CTA stages 128 voxels at a time in shared
+// memory (their 27 input taps + a constant 1 for the bias, and their 32 gradient channels) and forms the 28 x 32
+// outer-product sums with warp w owning taps {w, w+8, w+16, w+24} and lane = output channel.  Per-CTA partials, reduced below.
 __global__ void __launch_bounds__(256) first_conv_pr_wgrad_kernel(const float* __restrict__ xn, const float* __restrict__ gz,
                                                                   int B, int S, int T, RowGeom g, float* __restrict__ partials) {
-    __shared__ float red[8][28][32];
+    __shared__ float xs[128][29];
+    __shared__ __align__(16) float gs[128][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long nvox = (long long)B * T * S * S;
-    float acc[28];
-#pragma unroll
-    for (int j = 0; j < 28; ++j) acc[j] = 0.f;
-    // two voxels per iteration: their gz / x loads are independent, which hides most of the global-memory latency
-    const long long stride = (long long)gridDim.x * 8;
-    for (long long v0 = (long long)blockIdx.x * 8 + warp; v0 < nvox; v0 += 2 * stride) {
-        float gv[2];
-        int tt[2], hh[2], ww[2];
-        long long bb[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            long long v = v0 + u * stride;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long v0 = (long long)blockIdx.x * 128; v0 < nvox; v0 += (long long)gridDim.x * 128) {
+        if (threadIdx.x < 128) {
+            long long v = v0 + threadIdx.x;
             const bool ok = v < nvox;
             if (!ok) v = 0;
-            ww[u] = (int)(v % S); v /= S;
-            hh[u] = (int)(v % S); v /= S;
-            tt[u] = (int)(v % T); bb[u] = v / T;
-            gv[u] = ok ? __ldg(gz + (g.lead + bb[u] * g.pstride + (long long)(g.t0 + tt[u]) * g.plane + hh[u] * g.pw + ww[u]) * 32 + lane) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            acc[27] += gv[u];
+            const int ww = (int)(v % S); v /= S;
+            const int hh = (int)(v % S); v /= S;
+            const int tt = (int)(v % T); const long long b = v / T;
 #pragma unroll
             for (int tap = 0; tap < 27; ++tap) {
-                const int t2 = tt[u] + tap / 9 - 1, h2 = hh[u] + (tap / 3) % 3 - 1, w2 = ww[u] + tap % 3 - 1;
+                const int t2 = tt + tap / 9 - 1, h2 = hh + (tap / 3) % 3 - 1, w2 = ww + tap % 3 - 1;
                 float x = 0.f;
-                if (t2 >= 0 && t2 < T && h2 >= 0 && h2 < S && w2 >= 0 && w2 < S) x = __ldg(xn + ((bb[u] * S + h2) * S + w2) * T + t2);
-                acc[tap] = fmaf(x, gv[u], acc[tap]);
+                if (ok && t2 >= 0 && t2 < T && h2 >= 0 && h2 < S && w2 >= 0 && w2 < S) x = __ldg(xn + ((b * S + h2) * S + w2) * T + t2);
+                xs[threadIdx.x][tap] = x;
+            }
+            xs[threadIdx.x][27] = ok ? 1.f : 0.f;
+        } else {
+            for (int f = threadIdx.x - 128; f < 128 * 8; f += 128) {
+                const int i = f >> 3, c4 = f & 7;
+                long long v = v0 + i;
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (v < nvox) {
+                    const int ww = (int)(v % S); v /= S;
+                    const int hh = (int)(v % S); v /= S;
+                    const int tt = (int)(v % T); const long long b = v / T;
+                    q = __ldg(reinterpret_cast<const float4*>(gz + (g.lead + b * g.pstride + (long long)(g.t0 + tt) * g.plane + hh * g.pw + ww) * 32) + c4);
+                }
+                *reinterpret_cast<float4*>(&gs[i][c4 * 4]) = q;
             }
         }
+        __syncthreads();
+#pragma unroll 4
+        for (int i = 0; i < 128; ++i) {
+            const float gv = gs[i][lane];
+            acc[0] = fmaf(xs[i][warp], gv, acc[0]);
+            acc[1] = fmaf(xs[i][warp + 8], gv, acc[1]);
+            acc[2] = fmaf(xs[i][warp + 16], gv, acc[2]);
+            if (warp < 4) acc[3] = fmaf(xs[i][warp + 24], gv, acc[3]);
+        }
+        __syncthreads();
     }
-#pragma unroll
-    for (int j = 0; j < 28; ++j) red[warp][j][lane] = acc[j];
-    __syncthreads();
-    for (int i = threadIdx.x; i < 28 * 32; i += 256) {
-        float s = 0.f;
-#pragma unroll
-        for (int wv = 0; wv < 8; ++wv) s += red[wv][i / 32][i % 32];
-        partials[(size_t)blockIdx.x * (28 * 32) + i] = s;       // fixed-order second stage below: deterministic, no atomics
-    }
+    float* out = partials + (size_t)blockIdx.x * (28 * 32);
+    out[warp * 32 + lane] = acc[0];
+    out[(warp + 8) * 32 + lane] = acc[1];
+    out[(warp + 16) * 32 + lane] = acc[2];
+    if (warp < 4) out[(warp + 24) * 32 + lane] = acc[3];
 }
 
 __global__ void first_conv_pr_wgrad_reduce_kernel(const float* __restrict__ partials, int ncta, float* __restrict__ dw, float* __restrict__ db) {
@@ -408,7 +418,7 @@ int launch_first_conv_pr(const float* xn, const float* w, const float* bias, int
 
 int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, int T, RowGeom g, float* dw, float* db,
                                float* partials, size_t partial_floats, cudaStream_t st) {
-    const int grid = 148 * 8;
+    const int grid = 148 * 4;
     if (!partials || partial_floats < (size_t)grid * 28 * 32) return set_error(PV_ERR_BAD_ARG, "first_conv_pr_wgrad: partial buffer too small");
     PV_TIMED("first_conv_pr_wgrad", st, 2.0 * B * T * S * S * 27 * 32, 0.0);
     first_conv_pr_wgrad_kernel<<<grid, 256, 0, st>>>(xn, gz, B, S, T, g, partials);

@@ -178,8 +178,14 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partials, const fl
     const int total = ngroup * 4096;
     if (idx < total) {
         const int g = idx / 4096, m = (idx / 32) % 128, n = idx % 32;
-        float s = 0.f;
-        for (int c = 0; c < ncta; ++c) s += partials[(size_t)c * total + idx];
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;          // four independent chains: more loads in flight, fixed order
+        int c = 0;
+        for (; c + 3 < ncta; c += 4) {
+            s0 += partials[(size_t)c * total + idx]; s1 += partials[(size_t)(c + 1) * total + idx];
+            s2 += partials[(size_t)(c + 2) * total + idx]; s3 += partials[(size_t)(c + 3) * total + idx];
+        }
+        for (; c < ncta; ++c) s0 += partials[(size_t)c * total + idx];
+        const float s = (s0 + s1) + (s2 + s3);
         if (mode == 0) {
             const int qd = m / 32, ci = m % 32;
             if (qd < 3) { const int tap = g * 3 + qd; p.dw[(size_t)(p.dwr0[tap] + ci) * p.dw_cols + p.dwc0[tap] + n] = s; }
