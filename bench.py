@@ -141,6 +141,7 @@ def run_b200(args, cfg):
 
     import probav_b200 as pb
     from probav_b200 import _lib, parallel, synth
+    os.environ["NCCL_DEBUG"] = os.environ.get("PV_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line (NCCL prints its version there)
     rank, ws, local = parallel.init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
@@ -213,6 +214,8 @@ def run_b200(args, cfg):
     rep = _lib.timing_report()
     lib.pv_timing_reset()
     barrier()
+    if ws > 1:
+        dist.destroy_process_group()
     if rank != 0:
         return
     peaks = load_peaks()

@@ -37,7 +37,8 @@ def init_from_env(backend: str = None) -> Tuple[int, int, int]:
             torch.cuda.set_device(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
-        dist.init_process_group(backend=backend, rank=rank, world_size=ws)
+        kw = {"device_id": torch.device(f"cuda:{local}")} if backend == "nccl" else {}
+        dist.init_process_group(backend=backend, rank=rank, world_size=ws, **kw)
     return rank, ws, local
 
 
