@@ -735,8 +735,8 @@ int pv_trainer_create(pv_model* m, int opt_kind, float learning_rate, int loss_k
     if (!m || !out) return set_error(PV_ERR_BAD_ARG, "pv_trainer_create: null argument");
     *out = nullptr;
     if (opt_kind < PV_OPT_SGD || opt_kind > PV_OPT_NADAM) return set_error(PV_ERR_BAD_ARG, "unknown optimizer %d", opt_kind);
-    if (loss_kind != PV_LOSS_L1 && loss_kind != PV_LOSS_L2)
-        return set_error(PV_ERR_BAD_ARG, "loss kind %d is not built yet (l1 and l2 are)", loss_kind);
+    if (loss_kind != PV_LOSS_L1 && loss_kind != PV_LOSS_L2 && loss_kind != PV_LOSS_L1EDGE)
+        return set_error(PV_ERR_BAD_ARG, "unknown loss kind %d", loss_kind);
     if (m->P * m->cfg.scale != 48)
         return set_error(PV_ERR_BAD_CONFIG, "training needs scale*patch_size = 48 (fused loss backward); got %d", m->P * m->cfg.scale);
     PV_CUDA(cudaSetDevice(m->device));

@@ -34,6 +34,7 @@ constexpr int NT = 256;       // threads per CTA, 252 of them own a strip
 constexpr int NW = NT / 32;
 constexpr int RS = 58;        // smem row stride (float2) of the window: conflict-free for the strip pattern
 constexpr int HMW = PX + S - 1;       // 13 window pixels feed one strip over 7 column shifts
+constexpr int RT = CT + 1;            // row stride of the residual tile (43: odd, conflict-light)
 
 struct __align__(16) Smem {
     float2 hm[WT * RS];       // (h', m) of the HR window; reused as the dSR tile in pass 3
@@ -45,6 +46,8 @@ struct __align__(16) Smem {
     float red[NW];
     float center;
     int best;
+    float edge[NS];           // sobel term of the L1Edge loss per shift
+    float rt[2][CT * RT];     // residual tile r = h - (p + b) m of one shift (double buffered); rt[1] doubles as the adjoint tile
 };
 
 // Reduce N (power of two <= 32) per-lane values across the warp with N-1 + log2(32/N) shuffles:
@@ -228,6 +231,50 @@ __device__ __forceinline__ int argmin49(const float* v, int lane) {
     return bi;
 }
 
+// ---------------------------------------------------------------------------------------------- L1Edge (sobel) pass
+// tf.image.sobel_edges: REFLECT pad by 1, Ky = [[-1,-2,-1],[0,0,0],[1,2,1]], Kx = Ky^T.
+// loss.py:219-224 takes sobel(h) - sobel((p+b) m) on the 42x42 crops = sobel(r) (linear), summed |.| over both directions.
+__device__ __forceinline__ int reflect42(int i) { return i < 0 ? -i : (i >= CT ? 2 * CT - 2 - i : i); }
+
+__device__ __forceinline__ void sobel_at(const float* __restrict__ R, int y, int x, float& gy, float& gx) {
+    const int ym = reflect42(y - 1) * RT, y0 = y * RT, yp = reflect42(y + 1) * RT;
+    const int xm = reflect42(x - 1), xp = reflect42(x + 1);
+    const float a = R[ym + xm], b = R[ym + x], c = R[ym + xp];
+    const float d = R[y0 + xm], f = R[y0 + xp];
+    const float g = R[yp + xm], h = R[yp + x], k = R[yp + xp];
+    gy = (g + 2.f * h + k) - (a + 2.f * b + c);
+    gx = (c + 2.f * f + k) - (a + 2.f * d + g);
+}
+
+// per shift: residual tile -> shared memory -> sum |sobel_y| + |sobel_x| ; s.edge[shift] = that sum (un-normalised)
+__device__ __forceinline__ void edge_pass(Smem& s, const float (&p)[PX], bool active, int r, int c0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int sh = 0; sh < NS; ++sh) {
+        const int i = sh / S, j = sh % S;
+        float* R = s.rt[sh & 1];
+        if (active) {
+            const float b = s.bias[sh];
+            const float2* row = &s.hm[(r + i) * RS + c0 + j];
+#pragma unroll
+            for (int x = 0; x < PX; ++x) R[r * RT + c0 + x] = fmaf(-(p[x] + b), row[x].y, row[x].x);
+        }
+        __syncthreads();          // tile complete (the other buffer is still being read by nobody: two shifts apart)
+        float e = 0.f;
+        if (active) {
+#pragma unroll
+            for (int x = 0; x < PX; ++x) {
+                float gy, gx;
+                sobel_at(R, r, c0 + x, gy, gx);
+                e += fabsf(gy) + fabsf(gx);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
+        if (lane == 0) s.part[warp][sh][2] = e;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- fused patch kernel
 // one CTA per 48x48 sample (targetShape (48,48,1), the p16 configs: train.py:86-87)
 __global__ void __launch_bounds__(NT)
@@ -253,14 +300,16 @@ shift_loss_patch_kernel(int kind, const float* __restrict__ hr, const uint8_t* _
     }
     __syncthreads();
     pass2<true>(s, p, vx, active, r, c0);
+    if (kind == PV_LOSS_L1EDGE) edge_pass(s, p, active, r, c0);      // fills part[..][..][2] (pass2 only wrote [0], [1])
     __syncthreads();
     if (t < NS) {
-        float a1 = 0.f, a2 = 0.f;
+        float a1 = 0.f, a2 = 0.f, e = 0.f;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) { a1 += s.part[w][t][0]; a2 += s.part[w][t][1]; }
+        for (int w = 0; w < NW; ++w) { a1 += s.part[w][t][0]; a2 += s.part[w][t][1]; e += s.part[w][t][2]; }
         const float inv = 1.0f / s.cnt[t];
         s.l1[t] = inv * a1;                            // loss.py:227
         s.l2[t] = inv * a2;                            // loss.py:231
+        s.edge[t] = 0.7f * (inv * a1) + (1.0f - 0.7f) * (inv * e);   // loss.py:224, pi = 0.7 (loss.py:21)
         if (stack_out) {
             float* o = stack_out + ((size_t)b * NS + t) * 4;
             o[0] = s.l1[t]; o[1] = s.l2[t]; o[2] = s.cnt[t]; o[3] = s.bias[t];
@@ -268,8 +317,8 @@ shift_loss_patch_kernel(int kind, const float* __restrict__ hr, const uint8_t* _
     }
     __syncthreads();
     if (warp == 0) {
-        const float* sel = (kind == PV_LOSS_L2) ? s.l2 : s.l1;
-        const int bi = argmin49(sel, lane);            // reduce_min over the stack (loss.py:83 / :70)
+        const float* sel = (kind == PV_LOSS_L2) ? s.l2 : (kind == PV_LOSS_L1EDGE ? s.edge : s.l1);
+        const int bi = argmin49(sel, lane);            // reduce_min over the stack (loss.py:83 / :70 / :96)
         const int b2 = argmin49(s.l2, lane);           // max cPSNR <=> min L2 (loss.py:51)
         if (lane == 0) {
             s.best = bi;
@@ -287,14 +336,42 @@ shift_loss_patch_kernel(int kind, const float* __restrict__ hr, const uint8_t* _
     const float bias = s.bias[bi], N = s.cnt[bi];
     float q[PX], mm[PX];
     float sqm = 0.f;
+    if (kind == PV_LOSS_L1EDGE) {
+        // adjoint of the sobel term: Q = Ky^T sign(Ky r) + Kx^T sign(Kx r) with the reflect padding folded in, built by
+        // scattering each pixel's two signs through its 3x3 stencil (all addends are small integers: order-independent)
+        float* R = s.rt[0];
+        float* Q = s.rt[1];
+        for (int k = t; k < CT * RT; k += NT) Q[k] = 0.f;
+        if (active) {
+            const float2* row = &s.hm[(r + i) * RS + c0 + j];
+#pragma unroll
+            for (int x = 0; x < PX; ++x) R[r * RT + c0 + x] = fmaf(-(p[x] + bias), row[x].y, row[x].x);
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll 1
+            for (int x = 0; x < PX; ++x) {
+                float gy, gx;
+                sobel_at(R, r, c0 + x, gy, gx);
+                const float sy = gy > 0.f ? 1.f : (gy < 0.f ? -1.f : 0.f), sx = gx > 0.f ? 1.f : (gx < 0.f ? -1.f : 0.f);
+                const int ym = reflect42(r - 1) * RT, y0 = r * RT, yp = reflect42(r + 1) * RT;
+                const int xc = c0 + x, xm = reflect42(xc - 1), xp = reflect42(xc + 1);
+                atomicAdd(&Q[ym + xm], -sy - sx); atomicAdd(&Q[ym + xc], -2.f * sy); atomicAdd(&Q[ym + xp], -sy + sx);
+                atomicAdd(&Q[y0 + xm], -2.f * sx);                                       atomicAdd(&Q[y0 + xp], 2.f * sx);
+                atomicAdd(&Q[yp + xm], sy - sx);   atomicAdd(&Q[yp + xc], 2.f * sy);  atomicAdd(&Q[yp + xp], sy + sx);
+            }
+        }
+        __syncthreads();
+    }
     if (active) {
         const float2* row = &s.hm[(r + i) * RS + c0 + j];
 #pragma unroll
         for (int x = 0; x < PX; ++x) {
             const float2 w = row[x];
             const float tt = fmaf(-(p[x] + bias), w.y, w.x);
-            // L1: d|r|/dr = sign(r), sign(0) = 0 (tf.abs gradient);  L2: d r^2/dr = 2r
-            q[x] = (kind == PV_LOSS_L2) ? 2.0f * tt : (tt > 0.f ? 1.f : (tt < 0.f ? -1.f : 0.f));
+            // L1: d|r|/dr = sign(r), sign(0) = 0 (tf.abs gradient);  L2: d r^2/dr = 2r;  L1Edge: 0.7 sign(r) + 0.3 sobel adjoint
+            const float sg = tt > 0.f ? 1.f : (tt < 0.f ? -1.f : 0.f);
+            q[x] = (kind == PV_LOSS_L2) ? 2.0f * tt : (kind == PV_LOSS_L1EDGE ? 0.7f * sg + (1.0f - 0.7f) * s.rt[1][r * RT + c0 + x] : sg);
             mm[x] = w.y;
             sqm = fmaf(q[x], w.y, sqm);
         }
@@ -447,8 +524,11 @@ int shift_loss_device(int kind, const float* hr, const uint8_t* mask, const floa
         return set_error(PV_ERR_BAD_ARG, "pv_shift_loss: hr, mask, sr, loss_per_sample, best_shift, clear_count are required");
     if (border != BORDER)
         return set_error(PV_ERR_BAD_ARG, "pv_shift_loss: cropBorder=%d unsupported (reference default 3, loss.py:13)", border);
-    if (kind != PV_LOSS_L1 && kind != PV_LOSS_L2)
-        return set_error(PV_ERR_BAD_ARG, "pv_shift_loss: loss kind %d not implemented by this kernel", kind);
+    if (kind != PV_LOSS_L1 && kind != PV_LOSS_L2 && kind != PV_LOSS_L1EDGE)
+        return set_error(PV_ERR_BAD_ARG, "pv_shift_loss: unknown loss kind %d", kind);
+    if (kind == PV_LOSS_L1EDGE && !(H == WT && W == WT))
+        return set_error(PV_ERR_BAD_ARG, "pv_shift_loss: the sobel/L1 mix is built for 48x48 training targets only (the reference "
+                                         "scores whole scenes with cPSNR, evaluate.py:76-87)");
     if (B <= 0 || H <= 2 * border || W <= 2 * border)
         return set_error(PV_ERR_BAD_ARG, "pv_shift_loss: bad shape B=%d H=%d W=%d", B, H, W);
     // algorithmic bytes per sample: HR f32 + SR f32 + bool mask read, dSR f32 written when fused

@@ -380,3 +380,51 @@ def test_fit_loop_runs_and_loss_decreases(small_cfg):
     l_last, _ = t.testStep(X[:32], y[:32], msk[:32])
     assert t.step == 24 and l_last < l_first
     assert len([f for f in os.listdir(t.ckptDir) if f.startswith("ckpt-")]) >= 1
+
+
+# =============================================================================================== L1Edge (sobel + L1 mix)
+@pytest.mark.parametrize("case", ["all_clear", "masked_zero_hr"])
+def test_l1edge_loss_matches_oracle(case):
+    # loss.py:86-97,126-138,219-224: 0.7 * L1 + 0.3 * sum|sobel(h) - sobel((p+b) m)| / N, min over the 49 shifts
+    pb = _pb()
+    hr, mask, sr = _loss_inputs(12, seed=31, all_clear=(case == "all_clear"), zero_under_mask=True)
+    L = OracleLosses((48, 48, 1))
+    best, idx, cnt, stack = L.details("l1edge", hr, mask, sr)
+    out = pb.Losses((48, 48, 1)).evaluate("sobel_l1_mix", _np(hr), _np(mask, np.uint8), _np(sr), want_grad=True)
+    assert np.array_equal(out["best_shift"], _np(idx, np.int32))
+    assert np.array_equal(out["clear_count"], _np(cnt, np.int32))
+    assert rel_err(out["loss_per_sample"], _np(best, np.float64)) < LOSS_TOL
+    srg = sr.clone().requires_grad_(True)
+    L.shiftCompensatedL1EdgeLoss(hr, mask, srg).backward()
+    # d|sobel|/dr = sign(sobel): a pixel whose sobel response is below the fp32 resolution of r (|g| < ~5e-3 on values of
+    # ~1e4) can take the other sign than in the fp64 oracle; each such tie touches the 6 pixels of one stencil.  Everything
+    # else must agree to GRAD_TOL.
+    ref = _np(srg.grad, np.float64)
+    err = np.abs(out["dsr"] - ref) / np.abs(ref).max()
+    assert (err > GRAD_TOL).sum() <= 12 and err.max() < 1.0, ((err > GRAD_TOL).sum(), err.max())
+    assert abs(float(pb.Losses((48, 48, 1)).shiftCompensatedL1EdgeLoss(_np(hr), _np(mask, np.uint8), _np(sr))) - float(best.mean())) < LOSS_TOL * float(best.mean())
+
+
+def test_l1edge_golden_fixture_and_train_step(small_cfg):
+    pb = _pb()
+    z = np.load(os.path.join(GOLDEN, "shift_loss_golden.npz"))
+    out = pb.Losses((48, 48, 1)).evaluate("sobel_l1_mix", z["hr"], z["mask"], z["sr"])
+    assert np.array_equal(out["best_shift"], z["best_shift_l1edge"])
+    assert rel_err(out["loss_per_sample"], z["loss_l1edge"]) < LOSS_TOL
+    # cfg [Train] loss = sobel_l1_mix (train.py:95-96; BASELINE config 5): gradients through the whole graph
+    om, p = oracle_and_params(small_cfg, seed=44)
+    m = cuda_model(small_cfg, p)
+    from probav_b200 import synth
+    lr, hr, mask = synth.make_batch(3, seed=45, hr_zero_under_mask=True)
+    ol = OracleLosses((48, 48, 1))
+    loss, g, sr, cps = loss_and_grads(om, ol, p, torch.from_numpy(lr).double(), torch.from_numpy(hr).double(), torch.from_numpy(mask), "sobel_l1_mix")
+    import tempfile
+    Lc = pb.Losses((48, 48, 1))
+    d = tempfile.mkdtemp(prefix="pv_")
+    t = pb.ModelTrainer(m, pb.loss_from_config(Lc, "sobel_l1_mix"), Lc.shiftCompensatedcPSNR, pb.Nadam(5e-4), d + "/c", d + "/l")
+    lossv, psnrv = t.forward_backward(lr, hr, mask)
+    assert abs(lossv - float(loss)) < LOSS_TOL * abs(float(loss))
+    got = t.get_grads()
+    for k, ref in g.items():
+        if np.abs(ref.numpy()).max() > 0:
+            assert rel_err(got[k], ref.numpy()) < GRAD_TOL, k
