@@ -228,10 +228,12 @@ def run_b200(args, cfg):
     traffic = None
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tf):
-        traffic = json.load(open(tf)).get(top[0])
+        traffic = json.load(open(tf)).get(top[0])          # bytes per launch from the committed ncu capture
     ach = top[1]["flops"] / (top[1]["ms"] * 1e-3) / 1e12
     roofline = {"kernel": top[0], "bound": "tensor", "achieved": ach, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tensor_sustained"], "traffic": traffic, "peak_source": peaks["source"] + ", bf16 sustained",
+                "note": "kind::tf32 MMAs run at half the bf16 rate; with N = 32 each M128xN32xK8 MMA costs 54 cycles (4 KB A-operand "
+                        "read from shared memory is not overlapped), i.e. 603 of 2048 MAC/cycle/SM -- profiles/r01_umma_rate_probe.log",
                 "avg_launch_ms": top[1]["ms"] / top[1]["launches"], "share_of_step": top[1]["ms"] / tot_ms}
     sl = rep.get("shift_loss_patch")
     roof_loss = None
