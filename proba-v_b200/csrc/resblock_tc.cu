@@ -12,6 +12,7 @@
 //
 // Layouts as in rows.h (PR rows, 32 channels, 128 B per row); weights are the effective (weight-normalised, tf32)
 // matrices prepared by wn_prep: weT_exp [256][32], weT_dec [32][256] (both K contiguous).
+#include "reduce.cuh"
 #include "rows.h"
 #include "tc_common.cuh"
 
@@ -445,32 +446,32 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
     if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
-// dWd [256][32] (= dweff of decConv), dWe [32][256] (= dweff of expConv), dbe [256], dbd [32] from the per-CTA partials
-__global__ void resfront_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ dbp, int ncta,
-                                       float* __restrict__ dwd, float* __restrict__ dwe, float* __restrict__ dbe, float* __restrict__ dbd) {
-    const int idx = blockIdx.x * 256 + threadIdx.x;
-    if (idx < 4 * 4096) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int c = 0;
-        for (; c + 3 < ncta; c += 4) {
-            s0 += partials[(size_t)c * 16384 + idx]; s1 += partials[(size_t)(c + 1) * 16384 + idx];
-            s2 += partials[(size_t)(c + 2) * 16384 + idx]; s3 += partials[(size_t)(c + 3) * 16384 + idx];
+// dWd [256][32] (= dweff of decConv), dWe [32][256] (= dweff of expConv), dbe [256], dbd [32] from the per-CTA partials;
+// fixed-order block reduction (reduce.cuh).  Blocks [0,128): weight gradients; 128,129: dbe; 130: dbd.
+__global__ void __launch_bounds__(256)
+resfront_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ dbp, int ncta,
+                       float* __restrict__ dwd, float* __restrict__ dwe, float* __restrict__ dbe, float* __restrict__ dbd) {
+    __shared__ float4 sm[256];
+    const int b = blockIdx.x, x = threadIdx.x & 31;
+    if (b < 128) {
+        const float4 s = block_rowsum4(partials, ncta, [](int r) { return (size_t)r * 16384; }, b * 32, true, sm);
+        if (threadIdx.x >= 32) return;
+        const float v[4] = {s.x, s.y, s.z, s.w};
+        const int idx0 = (b * 32 + x) * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int idx = idx0 + e;
+            const int g = idx / 4096, m = (idx / 32) % 128, n = idx % 32;
+            if (g < 2) dwd[(size_t)(g * 128 + m) * 32 + n] = v[e];                 // [ch][co]
+            else dwe[(size_t)n * 256 + (g - 2) * 128 + m] = v[e];                  // [ci][ch]
         }
-        for (; c < ncta; ++c) s0 += partials[(size_t)c * 16384 + idx];
-        const float s = (s0 + s1) + (s2 + s3);
-        const int g = idx / 4096, m = (idx / 32) % 128, n = idx % 32;
-        if (g < 2) dwd[(size_t)(g * 128 + m) * 32 + n] = s;                 // [ch][co]
-        else dwe[(size_t)n * 256 + (g - 2) * 128 + m] = s;                  // [ci][ch]
-    } else if (idx < 4 * 4096 + 256) {
-        const int j = idx - 4 * 4096;
-        float s = 0.f;
-        for (int c = 0; c < ncta; ++c) s += dbp[(size_t)c * 768 + j] + dbp[(size_t)c * 768 + 256 + j];     // two epilogue groups
-        dbe[j] = s;
-    } else if (idx < 4 * 4096 + 256 + 32) {
-        const int j = idx - 4 * 4096 - 256;
-        float s = 0.f;
-        for (int c = 0; c < ncta; ++c) for (int w = 0; w < 8; ++w) s += dbp[(size_t)c * 768 + 512 + w * 32 + j];
-        dbd[j] = s;
+    } else if (b < 130) {       // dbe: both epilogue groups of every CTA
+        const float4 s = block_rowsum4(dbp, 2 * ncta, [](int r) { return (size_t)(r >> 1) * 768 + (r & 1) * 256; }, (b - 128) * 32, true, sm);
+        if (threadIdx.x < 32) { float* o = dbe + ((b - 128) * 32 + x) * 4; o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w; }
+    } else {                    // dbd: eight epilogue warps of every CTA
+        const bool ok = x < 8;
+        const float4 s = block_rowsum4(dbp, 8 * ncta, [](int r) { return (size_t)(r >> 3) * 768 + 512 + (r & 7) * 32; }, 0, ok, sm);
+        if (threadIdx.x < 32 && ok) { float* o = dbd + x * 4; o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w; }
     }
 }
 
@@ -555,7 +556,7 @@ int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* 
     }
     {
         PV_TIMED("wgrad_reduce", st);
-        resfront_reduce_kernel<<<cdiv(4 * 4096 + 288, 256), 256, 0, st>>>(a.partials, a.db_partials, grid, dw_dec, dw_exp, db_exp, db_dec);
+        resfront_reduce_kernel<<<131, 256, 0, st>>>(a.partials, a.db_partials, grid, dw_dec, dw_exp, db_exp, db_dec);
         PV_LAUNCH_CHECK();
     }
     return 0;

@@ -4,6 +4,7 @@
 // layers that are not tensor-core shaped (mainConv1, Cin = 1) and as the on-device cross-check of each tcgen05
 // kernel (pv_selftest), and (b) the layout glue between the PR trunk and the valid-conv tail.
 // Reference semantics: Keras Conv3D inside TFA WeightNormalization (modelsTF.py:191-197), tf.pad REFLECT (:157-158).
+#include "reduce.cuh"
 #include "rows.h"
 
 namespace pv {
@@ -280,12 +281,14 @@ __global__ void __launch_bounds__(256) first_conv_pr_wgrad_kernel(const float* _
     if (warp < 4) out[(warp + 24) * 32 + lane] = acc[3];
 }
 
-__global__ void first_conv_pr_wgrad_reduce_kernel(const float* __restrict__ partials, int ncta, float* __restrict__ dw, float* __restrict__ db) {
-    const int i = blockIdx.x * 128 + threadIdx.x;
-    if (i >= 28 * 32) return;
-    float s = 0.f;
-    for (int c = 0; c < ncta; ++c) s += partials[(size_t)c * (28 * 32) + i];
-    if (i < 27 * 32) dw[i] = s; else db[i - 27 * 32] = s;
+__global__ void __launch_bounds__(256)
+first_conv_pr_wgrad_reduce_kernel(const float* __restrict__ partials, int ncta, float* __restrict__ dw, float* __restrict__ db) {
+    __shared__ float4 sm[256];      // 7 blocks x 32 float4 columns = the 28 x 32 outputs (27 taps + bias); fixed order (reduce.cuh)
+    const float4 s = block_rowsum4(partials, ncta, [](int r) { return (size_t)r * (28 * 32); }, blockIdx.x * 32, true, sm);
+    if (threadIdx.x >= 32) return;
+    const int i = (blockIdx.x * 32 + threadIdx.x) * 4;
+    float* o = i < 27 * 32 ? dw + i : db + (i - 27 * 32);
+    o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w;
 }
 
 // ------------------------------------------------------------------------------------------ PR <-> G (reflect pad)
@@ -423,7 +426,7 @@ int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, i
     PV_TIMED("first_conv_pr_wgrad", st, 2.0 * B * T * S * S * 27 * 32, 0.0);
     first_conv_pr_wgrad_kernel<<<grid, 256, 0, st>>>(xn, gz, B, S, T, g, partials);
     PV_LAUNCH_CHECK();
-    first_conv_pr_wgrad_reduce_kernel<<<7, 128, 0, st>>>(partials, grid, dw, db);
+    first_conv_pr_wgrad_reduce_kernel<<<7, 256, 0, st>>>(partials, grid, dw, db);
     PV_LAUNCH_CHECK();
     return 0;
 }

@@ -8,13 +8,19 @@
 // (descriptor layout type 1; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) -- probes/umma_probe.cu T3.
 // M = 128 of the MMA is filled three ways:
 //   conv3  (normConv / convReducer / upscaleConv): four ROW-ADJACENT taps (dw = -1..2, the last one discarded) are one
-//          A operand whose four 32-channel atoms are 128 B apart, i.e. overlapping views of the same rows (LBO = 128);
-//          nine (dt,dh) groups -> nine [128 x 32] accumulators = 288 TMEM columns
+//          A operand whose four 32-channel atoms are 128 B apart, i.e. overlapping views of the same rows (LBO = 128).
+//          The three dh taps ride on the OTHER operand: dW[dt,dh,dw] = sum_r' x[r' + off(dt,0,dw)] * gz[r' - dh*pw], so
+//          B is three 32-channel atoms of the gz tile one image line (pw rows) apart (LBO = pw * 128 B) and N = 96.
+//          An M128 x N32 x K8 tf32 MMA costs 32 + N/2 cycles (probes/umma_rate.cu: the 4 KB A fetch is not overlapped),
+//          so one N = 96 MMA (80 cycles) replaces three N = 32 MMAs (163 cycles).  Three dt groups -> three [128 x 96]
+//          accumulators = 288 TMEM columns.  Tiles run 2*pw rows past the patch's row range so that every gz row meets
+//          every dh (gz is zero outside its valid extent, rows.h invariant).
 //   wide x (decConv: x = E, 256 channels): 2 groups of 4 channel atoms (LBO = box stride), N = 32 (gz = gD)
 //   wide gz (expConv: gz = gZ, 256 channels): the transpose -- M = gz channels (2 groups), N = 32 = x channels
 // Every CTA owns a contiguous range of row tiles and keeps its accumulators in TMEM for its whole lifetime; partial
 // sums go to a [cta][group][128][32] scratch and a second small kernel reduces them in a fixed order (deterministic,
 // no atomics).  The epilogue warps meanwhile form the bias gradient from the gz tiles already sitting in shared memory.
+#include "reduce.cuh"
 #include "rows.h"
 #include "tc_common.cuh"
 
@@ -39,7 +45,9 @@ struct WgradTcArgs {
     int box_lo[MAX_BOXES], box_c0[MAX_BOXES]; uint32_t box_off[MAX_BOXES];
     // MMA groups
     int ngroup; uint32_t grp_off[MAX_GROUPS]; uint32_t grp_lbo;
-    uint32_t b_off;
+    int nn;                            // N of one MMA: 32, or 96 (conv3: three dh atoms of the gz tile, b_lbo bytes apart)
+    uint32_t b_off, b_lbo;
+    uint32_t bias_row0;                // first row of the gz box that belongs to this tile (conv3: 2*pw)
     // bias gradient: column sums of these boxes (32 channels each)
     int nbias; uint32_t bias_off[8];
     float* partials;                   // [cta][ngroup][128][32]
@@ -90,9 +98,9 @@ rowwgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     } else if (warp == 1) {
         if (elect_one_sync()) {
             const uint64_t HI_A = smem_desc_hi(a.grp_lbo, 512, 1);     // MN-major, 128B swizzle / 32B atom; K atoms (4 rows) 512 B apart
-            const uint64_t HI_B = smem_desc_hi(128, 512, 1);
+            const uint64_t HI_B = smem_desc_hi(a.b_lbo, 512, 1);
             const uint32_t HI32 = (uint32_t)(HI_A >> 32), LO_A = (uint32_t)HI_A, LO_B = (uint32_t)HI_B;
-            constexpr uint32_t IDESC = instr_desc(2, 128, 32, 1, 1);
+            const uint32_t IDESC = instr_desc(2, 128, a.nn, 1, 1);
             uint32_t grp_inc[MAX_GROUPS];
 #pragma unroll
             for (int g = 0; g < MAX_GROUPS; ++g) grp_inc[g] = a.grp_off[g] >> 4;
@@ -104,11 +112,11 @@ rowwgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 const uint32_t s_lo = (base + stg * a.stage_bytes) >> 4;
                 const uint32_t a_lo = s_lo | LO_A, b_lo = (s_lo + (a.b_off >> 4)) | LO_B;
                 const uint32_t first = tile > t_lo ? 1u : 0u;
-                if (a.ngroup == 9) {
+                if (a.nn == 96) {
                     for (int ks = 0; ks < a.TR / 8; ++ks) {
 #pragma unroll
-                        for (int g = 0; g < 9; ++g)
-                            umma_ss_tf32_lohi(tmem + g * 32, a_lo + grp_inc[g] + ks * 64, b_lo + ks * 64, HI32, IDESC, first | (ks > 0 ? 1u : 0u));
+                        for (int g = 0; g < 3; ++g)
+                            umma_ss_tf32_lohi(tmem + g * 96, a_lo + grp_inc[g] + ks * 64, b_lo + ks * 64, HI32, IDESC, first | (ks > 0 ? 1u : 0u));
                     }
                 } else {
                     for (int ks = 0; ks < a.TR / 8; ++ks)
@@ -136,7 +144,7 @@ rowwgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 if (i < a.nbias) {
                     const uint8_t* bx = sp + a.bias_off[i];
                     float s = 0.f;
-                    for (int r = q * rows_per_warp; r < (q + 1) * rows_per_warp; ++r)     // 32B-atom swizzle: chunk ^= row & 3
+                    for (int r = a.bias_row0 + q * rows_per_warp; r < (int)a.bias_row0 + (q + 1) * rows_per_warp; ++r)     // 32B-atom swizzle: chunk ^= row & 3
                         s += *reinterpret_cast<const float*>(bx + r * 128 + ((((lane >> 3) ^ (r & 3)) << 5) | ((lane & 7) << 2)));
                     bsum[i] += s;
                 }
@@ -154,7 +162,9 @@ rowwgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             uint32_t v[32];
             tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + g * 32, v);
             tmem_ld_wait();
-            float4* o = reinterpret_cast<float4*>(out + ((size_t)g * 128 + q * 32 + lane) * 32);
+            // conv3: columns g*32.. of the TMEM block are (dt = g/3, atom j = g%3) with dh index 2 - j; stored as group dt*3 + dh
+            const int gs = a.nn == 96 ? (g / 3) * 3 + (2 - g % 3) : g;
+            float4* o = reinterpret_cast<float4*>(out + ((size_t)gs * 128 + q * 32 + lane) * 32);
             if (t_hi > t_lo) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
@@ -170,36 +180,42 @@ rowwgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
-// fixed-order reduction of the per-CTA partials into dweff / dbias.  mode 0: conv3 (group = (dt,dh), m = q*32+ci, n = co);
-// mode 1: wide x (group g, m = channel in group -> K index g*128+m, n = co); mode 2: wide gz (m = co in group, n = ci)
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ dbp, int ncta, int ngroup, int mode,
-                                    RowWgradP p, int nbias) {
-    const int idx = blockIdx.x * 256 + threadIdx.x;
+// fixed-order reduction of the per-CTA partials into dweff / dbias (reduce.cuh).  mode 0: conv3 (group = (dt,dh),
+// m = q*32+ci, n = co); mode 1: wide x (group g, m = channel in group -> K index g*128+m, n = co); mode 2: wide gz
+// (m = co in group, n = ci).  Blocks [0, total/128) own 128 weight-gradient outputs each, the remaining blocks the bias sums.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ dbp, int ncta, int ngroup, int mode,
+                    RowWgradP p, int nbias) {
+    __shared__ float4 sm[256];
     const int total = ngroup * 4096;
-    if (idx < total) {
-        const int g = idx / 4096, m = (idx / 32) % 128, n = idx % 32;
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;          // four independent chains: more loads in flight, fixed order
-        int c = 0;
-        for (; c + 3 < ncta; c += 4) {
-            s0 += partials[(size_t)c * total + idx]; s1 += partials[(size_t)(c + 1) * total + idx];
-            s2 += partials[(size_t)(c + 2) * total + idx]; s3 += partials[(size_t)(c + 3) * total + idx];
+    const int nmain = total / 128;
+    if ((int)blockIdx.x < nmain) {
+        const float4 s = block_rowsum4(partials, ncta, [total](int r) { return (size_t)r * total; }, blockIdx.x * 32, true, sm);
+        if (threadIdx.x >= 32) return;
+        const float v[4] = {s.x, s.y, s.z, s.w};
+        const int idx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int idx = idx0 + e;
+            const int g = idx / 4096, m = (idx / 32) % 128, n = idx % 32;
+            if (mode == 0) {
+                const int qd = m / 32, ci = m % 32;
+                if (qd < 3) { const int tap = g * 3 + qd; p.dw[(size_t)(p.dwr0[tap] + ci) * p.dw_cols + p.dwc0[tap] + n] = v[e]; }
+            } else if (mode == 1) {
+                const int k = g * 128 + m, tap = k / 32;
+                p.dw[(size_t)(p.dwr0[tap] + k % 32) * p.dw_cols + p.dwc0[tap] + n] = v[e];
+            } else {
+                p.dw[(size_t)(p.dwr0[0] + n) * p.dw_cols + p.dwc0[0] + g * 128 + m] = v[e];
+            }
         }
-        for (; c < ncta; ++c) s0 += partials[(size_t)c * total + idx];
-        const float s = (s0 + s1) + (s2 + s3);
-        if (mode == 0) {
-            const int qd = m / 32, ci = m % 32;
-            if (qd < 3) { const int tap = g * 3 + qd; p.dw[(size_t)(p.dwr0[tap] + ci) * p.dw_cols + p.dwc0[tap] + n] = s; }
-        } else if (mode == 1) {
-            const int k = g * 128 + m, tap = k / 32;
-            p.dw[(size_t)(p.dwr0[tap] + k % 32) * p.dw_cols + p.dwc0[tap] + n] = s;
-        } else {
-            p.dw[(size_t)(p.dwr0[0] + n) * p.dw_cols + p.dwc0[0] + g * 128 + m] = s;
+    } else {
+        const int bb = blockIdx.x - nmain, w = nbias * 32;
+        const bool ok = (bb * 32 + (int)(threadIdx.x & 31)) * 4 < w;
+        const float4 s = block_rowsum4(dbp, ncta * 4, [w](int r) { return (size_t)r * w; }, bb * 32, ok, sm);
+        if (threadIdx.x < 32 && ok && p.db) {
+            float* o = p.db + (bb * 32 + threadIdx.x) * 4;
+            o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w;
         }
-    } else if (idx < total + nbias * 32 && p.db) {
-        const int j = idx - total;
-        float s = 0.f;
-        for (int c = 0; c < ncta * 4; ++c) s += dbp[(size_t)c * nbias * 32 + j];
-        p.db[j] = s;
     }
 }
 
@@ -218,29 +234,28 @@ int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, siz
     int acols;
     if (mode == 2) { amat = p.gz; acols = 256; bmat = p.x; a.a_lead = p.og.lead; a.a_pstride = p.og.pstride; a.b_lead = p.in_lead; a.b_pstride = p.in_pstride; }
     else { amat = p.x; acols = p.xc; bmat = p.gz; a.a_lead = p.in_lead; a.a_pstride = p.in_pstride; a.b_lead = p.og.lead; a.b_pstride = p.og.pstride; }
+    a.nn = 32; a.b_lbo = 128; a.bias_row0 = 0;
+    int extra_rows = 0;
     if (mode == 0) {
-        a.TR = 128; a.nstage = 2;
-        // slabs: taps sorted ascending, 9 per temporal plane; a group = the three dw taps of one (dt,dh) + one spare row
-        int nslab = 0, span = 0;
-        for (int t = 0; t < 27; t += 9) {
-            a.box_lo[nslab] = p.off[t]; a.box_c0[nslab] = 0;
-            if (p.off[t + 8] + 1 - p.off[t] > span) span = p.off[t + 8] + 1 - p.off[t];
-            ++nslab;
-        }
-        a.abox_rows = ((a.TR + span + 7) / 8) * 8;
-        if (a.abox_rows > 256) return set_error(PV_ERR_BAD_ARG, "rowwgrad_tc: slab too tall");
-        a.nabox = nslab;
-        for (int s = 0; s < nslab; ++s) a.box_off[s] = (uint32_t)s * a.abox_rows * 128;
-        a.ngroup = 9; a.grp_lbo = 128;
+        a.TR = 128; a.nstage = 3;
+        // taps sorted ascending: index 9*dt + 3*dh + dw.  A: one slab per dt holding rows [off(dt,0,0), +TR+3] (four dw views);
+        // B: the gz tile plus the 2*pw rows before it, whose three line-shifted views are the dh atoms (atom j <-> dh = 2 - j)
+        const int pw = p.off[3] - p.off[0];
         for (int g = 0; g < 9; ++g) {
-            if (p.off[3 * g + 1] != p.off[3 * g] + 1 || p.off[3 * g + 2] != p.off[3 * g] + 2)
-                return set_error(PV_ERR_BAD_ARG, "rowwgrad_tc: taps of a group must be row-adjacent");
-            a.grp_off[g] = a.box_off[g / 3] + (uint32_t)(p.off[3 * g] - a.box_lo[g / 3]) * 128;
+            if (p.off[3 * g + 1] != p.off[3 * g] + 1 || p.off[3 * g + 2] != p.off[3 * g] + 2 || p.off[3 * g] != p.off[9 * (g / 3)] + (g % 3) * pw)
+                return set_error(PV_ERR_BAD_ARG, "rowwgrad_tc: taps must form a (dt, dh, dw) lattice with unit dw stride");
         }
-        a.nbbox = 1; a.bbox_rows = a.TR;
-        a.box_lo[nslab] = 0; a.box_c0[nslab] = 0; a.box_off[nslab] = (uint32_t)nslab * a.abox_rows * 128;
-        a.b_off = a.box_off[nslab];
+        if (pw < 4 || pw > 60) return set_error(PV_ERR_BAD_ARG, "rowwgrad_tc: unsupported line stride %d", pw);
+        a.abox_rows = a.TR + 8;
+        a.nabox = 3;
+        for (int s = 0; s < 3; ++s) { a.box_lo[s] = p.off[9 * s]; a.box_c0[s] = 0; a.box_off[s] = (uint32_t)s * a.abox_rows * 128; a.grp_off[s] = a.box_off[s]; }
+        a.ngroup = 9; a.grp_lbo = 128;             // ngroup counts the [128 x 32] partial blocks (dt, dh); the MMAs run as 3 x N96
+        a.nn = 96; a.b_lbo = (uint32_t)pw * 128; a.bias_row0 = 2 * pw;
+        a.nbbox = 1; a.bbox_rows = ((a.TR + 2 * pw + 7) / 8) * 8;
+        a.box_lo[3] = -2 * pw; a.box_c0[3] = 0; a.box_off[3] = 3u * a.abox_rows * 128;
+        a.b_off = a.box_off[3];
         a.nbias = 1; a.bias_off[0] = a.b_off;
+        extra_rows = 2 * pw;
     } else {
         a.TR = 64; a.nstage = 3;
         a.nabox = 8; a.abox_rows = a.TR;
@@ -253,7 +268,7 @@ int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, siz
         if (mode == 1) { a.nbias = 1; a.bias_off[0] = a.b_off; }
         else { a.nbias = 8; for (int i = 0; i < 8; ++i) a.bias_off[i] = a.box_off[i]; }
     }
-    a.tiles_per_patch = cdiv(p.og.nrows, a.TR);
+    a.tiles_per_patch = cdiv(p.og.nrows + extra_rows, a.TR);
     a.stage_bytes = (uint32_t)(a.nabox * a.abox_rows + a.nbbox * a.bbox_rows) * 128u;
     const size_t smem = 1024 + (size_t)a.nstage * a.stage_bytes;
     if (smem > 226 * 1024) return set_error(PV_ERR_BAD_ARG, "rowwgrad_tc: %zu bytes of shared memory needed", smem);
@@ -278,8 +293,7 @@ int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, siz
     }
     {
         PV_TIMED("wgrad_reduce", st);
-        const int total = a.ngroup * 4096 + a.nbias * 32;
-        wgrad_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(a.partials, a.db_partials, grid, a.ngroup, mode, p, a.nbias);
+        wgrad_reduce_kernel<<<a.ngroup * 32 + cdiv(a.nbias * 8, 32), 256, 0, st>>>(a.partials, a.db_partials, grid, a.ngroup, mode, p, a.nbias);
         PV_LAUNCH_CHECK();
     }
     return 0;
