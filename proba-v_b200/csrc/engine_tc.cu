@@ -127,7 +127,10 @@ int wgrad_rows(pv_trainer* t, const Layer& L, const Taps& tp /* forward offsets 
 // ------------------------------------------------------------------------------------------ self-test
 // Runs each tensor-core kernel configuration of the graph against the CUDA-core kernel on the same random row
 // buffers (values on a coarse dyadic grid, so tf32 products are exact and both paths must agree to fp32 rounding).
-static int selftest_one(const char* name, RowConvP p, size_t in_floats, size_t out_floats, size_t w_floats, std::string& rep) {
+// `ig` (nullable): geometry of the input rows; rows outside its valid extent are zeroed, which is the engine's layout
+// invariant (rows.h) and what the N = 96 kernel's halo-free first lane relies on.
+static int selftest_one(const char* name, RowConvP p, size_t in_floats, size_t out_floats, size_t w_floats, std::string& rep,
+                        const RowGeom* ig = nullptr) {
     float *x = nullptr, *w = nullptr, *wt = nullptr, *b = nullptr, *res = nullptr, *msk = nullptr, *y0 = nullptr, *y1 = nullptr;
     PV_CUDA(cudaMalloc(&x, in_floats * 4)); PV_CUDA(cudaMalloc(&w, w_floats * 4)); PV_CUDA(cudaMalloc(&wt, w_floats * 4));
     PV_CUDA(cudaMalloc(&b, 256 * 4)); PV_CUDA(cudaMalloc(&res, out_floats * 4)); PV_CUDA(cudaMalloc(&msk, out_floats * 4));
@@ -138,7 +141,18 @@ static int selftest_one(const char* name, RowConvP p, size_t in_floats, size_t o
         for (size_t i = 0; i < n; ++i) { s = s * 1664525u + 1013904223u; h[i] = (float)((int)((s >> 16) % (2 * range + 1)) - range) * scale; }
         return cudaMemcpy(d, h.data(), n * 4, cudaMemcpyHostToDevice);
     };
-    PV_CUDA(fill(x, in_floats, 4, 0.125f)); PV_CUDA(fill(b, 256, 4, 0.25f));
+    if (ig) {
+        for (size_t i = 0; i < in_floats; ++i) { s = s * 1664525u + 1013904223u; h[i] = (float)((int)((s >> 16) % 9) - 4) * 0.125f; }
+        for (long long r = 0; r < (long long)(in_floats / p.xc); ++r) {
+            const long long q = r - ig->lead;
+            const bool ok = q >= 0 && q < (long long)p.B * ig->pstride && row_valid(*ig, (int)(q % ig->pstride));
+            if (!ok) for (int c = 0; c < p.xc; ++c) h[(size_t)r * p.xc + c] = 0.f;
+        }
+        PV_CUDA(cudaMemcpy(x, h.data(), in_floats * 4, cudaMemcpyHostToDevice));
+    } else {
+        PV_CUDA(fill(x, in_floats, 4, 0.125f));
+    }
+    PV_CUDA(fill(b, 256, 4, 0.25f));
     PV_CUDA(fill(res, out_floats, 4, 0.25f)); PV_CUDA(fill(msk, out_floats, 1, 1.0f));
     // weights: [rows = p.w_rows][cols = p.w_cols] K-major for the tensor cores, transposed copy for the CUDA cores
     PV_CUDA(fill(wt, w_floats, 3, 0.125f));
@@ -381,12 +395,12 @@ int tc_selftest(std::string& rep) {
     {   // normConv forward: 27 centred taps, bias + residual
         RowConvP p = base(pr, pr, 32, 32, conv3_taps(529, 23, true, +1), 1);
         p.bias = dummy; p.residual = dummy;
-        fails += selftest_one("conv3 same fwd (+bias +residual)", p, floats(pr, 32), floats(pr, 32), (size_t)p.w_rows * p.w_cols, rep);
+        fails += selftest_one("conv3 same fwd (+bias +residual)", p, floats(pr, 32), floats(pr, 32), (size_t)p.w_rows * p.w_cols, rep, &pr);
     }
     {   // normConv data gradient: negated taps, ReLU mask, tf32-rounded output
         RowConvP p = base(pr, pr, 32, 32, conv3_taps(529, 23, true, -1), 1);
         p.relumask = dummy; p.round_tf32 = 1;
-        fails += selftest_one("conv3 same dgrad (+relu mask)", p, floats(pr, 32), floats(pr, 32), (size_t)p.w_rows * p.w_cols, rep);
+        fails += selftest_one("conv3 same dgrad (+relu mask)", p, floats(pr, 32), floats(pr, 32), (size_t)p.w_rows * p.w_cols, rep, &pr);
     }
     {   // reducer forward (valid taps, G1 -> G2) with ReLU
         RowConvP p = base(g_geom(1), g_geom(2), 32, 32, conv3_taps(576, 24, false, +1), 1);

@@ -90,6 +90,10 @@ int launch_rowconv_simt(const RowConvP& p, cudaStream_t st);
 int launch_rowwgrad_simt(const RowWgradP& p, cudaStream_t st);
 int launch_rowconv_tc(const RowConvP& p, cudaStream_t st);          // tcgen05 + TMA implicit GEMM (conv_tc.cu)
 int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, size_t partial_floats);
+// 3x3x3 lattice convolutions on 32-channel rows with the dw taps folded into N = 96 (conv3_tc.cu); launch_rowconv_tc
+// dispatches to it unless the environment variable PV_CONV3_N32 is set (A/B timing against the N = 32 formulation)
+bool rowconv3_tc_supported(const RowConvP& p);
+int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st);
 
 // fused expConv + ReLU + decConv of one residual block (resblock_tc.cu); the expanded tensor stays in TMEM.
 // relu_bits: [rows][8] uint32 ReLU bit mask written by the forward (nullable) and consumed by the backward-data kernel.
