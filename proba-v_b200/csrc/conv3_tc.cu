@@ -14,10 +14,12 @@
 // Tiling.  PR layout (rows.h; 'same' convolutions): a plane is 22 lines of 23 rows (column 22 = zero padding).  Tiles
 // start at plane rows 0, 126, 252, 378: lane 0 of the first tile needs no left halo because row -1 is a padding
 // column (Q_0 there is a sum over zero rows), lane 127 of the last tile is row 505, a padding column itself -> exactly
-// four tiles per plane, 36 per patch (the N = 32 kernel needed 38).  Tiles are ordered (patch, chunk, t) and every CTA
+// four tiles per plane, 36 per patch (the N = 32 kernel needed 38).  Tiles are ordered (chunk, patch, t) and every CTA
 // owns a contiguous range, so going from plane t to t + 1 re-uses two of the three temporal slabs already in shared
-// memory: ~1.3 TMA slab loads per tile instead of 3.  Other layouts (G: valid convolutions of the reducers) use flat
-// tiles of 126 output rows with a halo lane on both sides and three fresh slabs per tile.
+// memory, and going from the last plane of a patch to the first plane of the next re-uses one (the shared zero plane):
+// ~1.2 TMA slab loads per tile instead of 3, and the five-stage slab ring never drains inside a CTA's range.  Other
+// layouts (G: valid convolutions of the reducers) use flat tiles of 126 output rows with a halo lane on both sides and
+// three fresh slabs per tile.
 //
 // Warp roles as in conv_tc.cu: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer (one elected thread), warps 2-5 and
 // 6-9 two epilogue groups draining alternate tiles (TMEM accumulator double buffer, 2 x 96 columns).
@@ -32,7 +34,7 @@ int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, int cols, in
 namespace {
 
 constexpr int C3_THREADS = 320;
-constexpr int C3_STAGES = 4;
+constexpr int C3_STAGES = 5;
 constexpr int C3_TILE = 126;           // output rows per tile (128 TMEM lanes minus the two halo lanes)
 
 struct Conv3Args {
@@ -41,6 +43,7 @@ struct Conv3Args {
     int chunks, nt;                    // plane mode: tiles per plane, planes per patch; flat: tiles per patch, 1
     int plane_rows;                    // plane mode: rows per plane (input and output geometry agree)
     int plane_out_rows;                // plane mode: rows of a plane that may be written (nh * pw)
+    int chain_patches;                 // plane mode: pstride == (nt + 1) * plane, so patch b+1 continues patch b's slab chain
     long long in_lead, in_pstride;
     RowGeom og;
     int slab_rows;                     // 128 + 2 * pw rounded up to 8
@@ -57,22 +60,22 @@ __device__ __forceinline__ float rna_tf32(float x) {
     return __uint_as_float(u);
 }
 
-struct TileInfo { int b, c, t; int r0; bool fresh; bool lane0_out; };
+struct TileInfo { int b, c, t; int r0; int nnew; bool lane0_out; };      // nnew: temporal slabs this tile has to load (the others are its predecessor's)
 
 __device__ __forceinline__ TileInfo tile_info(const Conv3Args& a, int tile, int t_lo) {
     TileInfo ti;
-    if (a.plane_mode) {
-        const int per_patch = a.chunks * a.nt;
-        ti.b = tile / per_patch;
-        const int rem = tile - ti.b * per_patch;
-        ti.c = rem / a.nt; ti.t = rem - ti.c * a.nt;
+    if (a.plane_mode) {                                      // tile = (c * B + b) * nt + t
+        const int per_chunk = a.B * a.nt;
+        ti.c = tile / per_chunk;
+        const int rem = tile - ti.c * per_chunk;
+        ti.b = rem / a.nt; ti.t = rem - ti.b * a.nt;
         ti.r0 = a.og.row0 + ti.t * a.plane_rows + ti.c * C3_TILE;
-        ti.fresh = ti.t == 0 || tile == t_lo;
+        ti.nnew = (tile == t_lo || rem == 0) ? 3 : (ti.t == 0 ? (a.chain_patches ? 2 : 3) : 1);
         ti.lane0_out = ti.c == 0;
     } else {
         ti.b = tile / a.chunks; ti.c = tile - ti.b * a.chunks; ti.t = 0;
         ti.r0 = a.og.row0 - 1 + ti.c * C3_TILE;
-        ti.fresh = true;
+        ti.nnew = 3;
         ti.lane0_out = false;
     }
     return ti;
@@ -83,6 +86,7 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * C3_STAGES + 5];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_bias[32];
     __shared__ __align__(16) float xch[2][2][4][2][32];       // [epilogue group][tile parity][warp][0: last lane's Q_0, 1: first lane's Q_2][channel]
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t w_smem = base;                              // 27 taps x [32 co rows x 128 B], sorted-tap order
@@ -98,6 +102,7 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         mbar_init(BAR(WBAR), 1);
         fence_mbar_init();
     }
+    if (threadIdx.x < 32) s_bias[threadIdx.x] = a.bias ? a.bias[threadIdx.x] : 0.f;
     if (warp == 1) tmem_alloc<256>(smem_u32(&tmem_slot));
     tc_fence_before();
     __syncthreads();
@@ -117,7 +122,7 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             for (int tile = t_lo; tile < t_hi; ++tile) {
                 const TileInfo ti = tile_info(a, tile, t_lo);
                 const long long irow0 = a.in_lead + (long long)ti.b * a.in_pstride + ti.r0;
-                for (int s = ti.fresh ? 0 : 2; s < 3; ++s, ++n) {
+                for (int s = 3 - ti.nnew; s < 3; ++s, ++n) {
                     const uint32_t stg = n % C3_STAGES, ph = (n / C3_STAGES) & 1;
                     mbar_wait(BAR(EMPTY + stg), ph ^ 1);
                     mbar_arrive_expect_tx(BAR(FULL + stg), stage_bytes);
@@ -134,19 +139,31 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             const uint32_t dh_inc = (uint32_t)a.pw * 8u;                // one image line further into the slab (16-byte units)
             mbar_wait(BAR(WBAR), 0);
             tc_fence_after();
-            uint32_t n = 0, tl = 0;
+            // The issuing thread must stay ahead of the tensor pipe (an N = 96 MMA retires every ~80 cycles), so the per-tile
+            // bookkeeping is incremental: (c, b, t) counters instead of divisions, ring stages and barrier parities in registers.
+            TileInfo ti = tile_info(a, t_lo, t_lo);
+            int tb = ti.b, tt = ti.t;
+            uint32_t nnew = 3;
+            uint32_t s0 = 0, s1 = 0, s2 = 0, nxt = 0;        // stages of the slabs dtI = 0,1,2 in use; next stage the producer fills
+            uint32_t fullph = 0;                             // bit s: parity FULL[s] completes with next
+            uint32_t tl = 0;
             for (int tile = t_lo; tile < t_hi; ++tile, ++tl) {
-                const TileInfo ti = tile_info(a, tile, t_lo);
                 const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
-                const uint32_t nnew = ti.fresh ? 3u : 1u;
-                n += nnew;                                               // this tile uses slabs n-3, n-2, n-1
+                for (uint32_t i = 0; i < nnew; ++i) { s0 = s1; s1 = s2; s2 = nxt; nxt = nxt == C3_STAGES - 1 ? 0 : nxt + 1; }
+                // what the next tile inherits decides which slabs are released after this one
+                uint32_t nnext = 3;
+                if (a.plane_mode) {
+                    if (++tt == a.nt) { tt = 0; if (++tb == a.B) tb = 0; }
+                    nnext = tt != 0 ? 1u : ((tb != 0 && a.chain_patches) ? 2u : 3u);
+                }
+                if (tile + 1 == t_hi) nnext = 3;
                 mbar_wait(BAR(TEMPTY + acc), aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem + acc * 96;
 #pragma unroll
                 for (int s = 0; s < 3; ++s) {
-                    const uint32_t k = n - 3 + s, stg = k % C3_STAGES;
-                    if (s >= 3 - (int)nnew) { mbar_wait(BAR(FULL + stg), (k / C3_STAGES) & 1); tc_fence_after(); }
+                    const uint32_t stg = s == 0 ? s0 : (s == 1 ? s1 : s2);
+                    if (s >= 3 - (int)nnew) { mbar_wait(BAR(FULL + stg), (fullph >> stg) & 1); fullph ^= 1u << stg; tc_fence_after(); }
                     const uint32_t a_lo = ((st_smem + stg * stage_bytes) >> 4) | LO32;
                     const uint32_t b_lo = ((w_smem >> 4) | LO32) + (uint32_t)(s * 9) * 256u;
 #pragma unroll
@@ -155,13 +172,11 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                         for (int ks = 0; ks < 4; ++ks)
                             umma_ss_tf32_lohi(d_tmem, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
                     }
+                    // release the slabs the next tile does not inherit: as many (oldest first) as it loads itself
+                    if (s < (int)nnext) umma_commit(BAR(EMPTY + stg));
                 }
-                // release the slabs no later tile of this run needs: the oldest one, or all three at the end of a run
-                bool last_of_run = tile + 1 == t_hi;
-                if (!last_of_run) last_of_run = tile_info(a, tile + 1, t_lo).fresh;
-                if (last_of_run) { for (uint32_t k = n - 3; k < n; ++k) umma_commit(BAR(EMPTY + k % C3_STAGES)); }
-                else umma_commit(BAR(EMPTY + (n - 3) % C3_STAGES));
                 umma_commit(BAR(TFULL + acc));
+                nnew = nnext;
             }
         }
     } else {
@@ -235,10 +250,8 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #pragma unroll
             for (int g4 = 0; g4 < 8; ++g4) {
                 float e[4] = {o[4 * g4], o[4 * g4 + 1], o[4 * g4 + 2], o[4 * g4 + 3]};
-                if (a.bias) {
-                    const float4 bq = __ldg(reinterpret_cast<const float4*>(a.bias) + g4);
-                    e[0] += bq.x; e[1] += bq.y; e[2] += bq.z; e[3] += bq.w;
-                }
+                const float4 bq = reinterpret_cast<const float4*>(s_bias)[g4];
+                e[0] += bq.x; e[1] += bq.y; e[2] += bq.z; e[3] += bq.w;
                 if (a.residual) { e[0] += pre[g4].x; e[1] += pre[g4].y; e[2] += pre[g4].z; e[3] += pre[g4].w; }
                 if (a.relu) {
 #pragma unroll
@@ -295,11 +308,12 @@ int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st) {
     if (plane_mode) {
         a.plane_mode = 1; a.nt = og.nt; a.plane_rows = og.plane; a.plane_out_rows = og.nh * og.pw;
         a.chunks = cdiv(og.nh * og.pw - 2, C3_TILE);      // first tile yields 127 rows, the others 126; the last row is a padding column
+        a.chain_patches = og.pstride == (long long)(og.nt + 1) * og.plane ? 1 : 0;
     } else {
         a.plane_mode = 0; a.nt = 1; a.chunks = cdiv(og.nrows, C3_TILE);
     }
     const size_t smem = 1024 + 27 * 4096 + (size_t)C3_STAGES * a.slab_rows * 128;
-    if (smem > 220 * 1024) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: %zu bytes of shared memory needed", smem);
+    if (smem > 222 * 1024) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: %zu bytes of shared memory needed", smem);
     const long long in_rows = p.in_lead + (long long)p.B * p.in_pstride + ROW_TAIL;
     CUtensorMap tm_x, tm_w;
     PV_TRY(make_tmap_2d(&tm_x, p.x, in_rows, 32, a.slab_rows, 32, 0));
