@@ -17,12 +17,13 @@
 // four tiles per plane, 36 per patch (the N = 32 kernel needed 38).  Tiles are ordered (chunk, patch, t) and every CTA
 // owns a contiguous range, so going from plane t to t + 1 re-uses two of the three temporal slabs already in shared
 // memory, and going from the last plane of a patch to the first plane of the next re-uses one (the shared zero plane):
-// ~1.2 TMA slab loads per tile instead of 3, and the five-stage slab ring never drains inside a CTA's range.  Other
+// ~1.2 TMA slab loads per tile instead of 3, and the four-stage slab ring never drains inside a CTA's range.  Other
 // layouts (G: valid convolutions of the reducers) use flat tiles of 126 output rows with a halo lane on both sides and
 // three fresh slabs per tile.
 //
 // Warp roles as in conv_tc.cu: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer (one elected thread), warps 2-5 and
 // 6-9 two epilogue groups draining alternate tiles (TMEM accumulator double buffer, 2 x 96 columns).
+#include "rowio.cuh"
 #include "rows.h"
 #include "tc_common.cuh"
 
@@ -34,7 +35,7 @@ int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, int cols, in
 namespace {
 
 constexpr int C3_THREADS = 320;
-constexpr int C3_STAGES = 5;
+constexpr int C3_STAGES = 4;
 constexpr int C3_TILE = 126;           // output rows per tile (128 TMEM lanes minus the two halo lanes)
 
 struct Conv3Args {
@@ -92,6 +93,7 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     const uint32_t w_smem = base;                              // 27 taps x [32 co rows x 128 B], sorted-tap order
     const uint32_t stage_bytes = (uint32_t)a.slab_rows * 128u;
     const uint32_t st_smem = base + 27u * 4096u;
+    uint8_t* const io_scratch = smem_raw + (base - smem_u32(smem_raw)) + 27u * 4096u + C3_STAGES * stage_bytes;   // 8 epilogue warps x 2 KB (rowio.cuh)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto BAR = [&](int i) { return smem_u32(&bars[i]); };
     const int FULL = 0, EMPTY = C3_STAGES, TFULL = 2 * C3_STAGES, TEMPTY = 2 * C3_STAGES + 2, WBAR = 2 * C3_STAGES + 4;
@@ -194,12 +196,14 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             if (a.plane_mode) in_patch = in_patch && (ti.c * C3_TILE + L) < a.plane_out_rows;
             const bool valid = in_patch && row_valid(a.og, r);
             const long long orow = a.og.lead + (long long)ti.b * a.og.pstride + r;
-            // this row's residual (forward) or ReLU-mask (data gradient) operand, fetched before waiting for the accumulator
+            // this warp's 32 rows are contiguous in global memory: all traffic goes through the coalescing helpers of rowio.cuh
+            const uint32_t rowmask = __ballot_sync(0xffffffffu, in_patch);
+            const long long orow_w = orow - lane;                         // row of this warp's lane 0
+            uint8_t* const sc = io_scratch + (warp - 2) * ROWIO_SCRATCH_BYTES;
+            // the rows' residual (forward) or ReLU-mask (data gradient) operand, requested before waiting for the accumulator
             const float* pre_src = a.residual ? a.residual : a.relumask;
             float4 pre[8];
-#pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4)
-                pre[g4] = (pre_src && in_patch) ? __ldg(reinterpret_cast<const float4*>(pre_src + orow * 32) + g4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pre_src) rowio_ldg_chunks(pre_src + orow_w * 32, rowmask, pre);
             mbar_wait(BAR(TFULL + acc), aph);
             tc_fence_after();
             uint32_t v0[32], v1[32], v2[32];
@@ -245,11 +249,13 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     o[4 * g4] += h.x; o[4 * g4 + 1] += h.y; o[4 * g4 + 2] += h.z; o[4 * g4 + 3] += h.w;
                 }
             }
-            if (!in_patch) continue;
-            float4* yp = reinterpret_cast<float4*>(a.y + orow * 32);
+            if (pre_src) { float4 t[8]; 
+#pragma unroll
+                for (int g4 = 0; g4 < 8; ++g4) t[g4] = pre[g4];
+                rowio_rows_from_chunks(t, pre, sc); }
 #pragma unroll
             for (int g4 = 0; g4 < 8; ++g4) {
-                float e[4] = {o[4 * g4], o[4 * g4 + 1], o[4 * g4 + 2], o[4 * g4 + 3]};
+                float* e = o + 4 * g4;
                 const float4 bq = reinterpret_cast<const float4*>(s_bias)[g4];
                 e[0] += bq.x; e[1] += bq.y; e[2] += bq.z; e[3] += bq.w;
                 if (a.residual) { e[0] += pre[g4].x; e[1] += pre[g4].y; e[2] += pre[g4].z; e[3] += pre[g4].w; }
@@ -258,7 +264,7 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     for (int k = 0; k < 4; ++k) e[k] = fmaxf(e[k], 0.f);
                 }
                 if (a.relumask) {
-                    const float4 mq = a.residual ? __ldg(reinterpret_cast<const float4*>(a.relumask + orow * 32) + g4) : pre[g4];
+                    const float4 mq = (a.residual && in_patch) ? __ldg(reinterpret_cast<const float4*>(a.relumask + orow * 32) + g4) : pre[g4];
                     e[0] = mq.x > 0.f ? e[0] : 0.f; e[1] = mq.y > 0.f ? e[1] : 0.f;
                     e[2] = mq.z > 0.f ? e[2] : 0.f; e[3] = mq.w > 0.f ? e[3] : 0.f;
                 }
@@ -267,8 +273,8 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < 4; ++k) e[k] = rna_tf32(e[k]);
                 }
-                yp[g4] = make_float4(e[0], e[1], e[2], e[3]);
             }
+            rowio_store_rows(a.y + orow_w * 32, o, rowmask, sc);
         }
     }
     tc_fence_before();
@@ -312,7 +318,7 @@ int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st) {
     } else {
         a.plane_mode = 0; a.nt = 1; a.chunks = cdiv(og.nrows, C3_TILE);
     }
-    const size_t smem = 1024 + 27 * 4096 + (size_t)C3_STAGES * a.slab_rows * 128;
+    const size_t smem = 1024 + 27 * 4096 + (size_t)C3_STAGES * a.slab_rows * 128 + 8 * ROWIO_SCRATCH_BYTES;
     if (smem > 222 * 1024) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: %zu bytes of shared memory needed", smem);
     const long long in_rows = p.in_lead + (long long)p.B * p.in_pstride + ROW_TAIL;
     CUtensorMap tm_x, tm_w;
