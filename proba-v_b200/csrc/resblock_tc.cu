@@ -13,6 +13,7 @@
 // Layouts as in rows.h (PR rows, 32 channels, 128 B per row); weights are the effective (weight-normalised, tf32)
 // matrices prepared by wn_prep: weT_exp [256][32], weT_dec [32][256] (both K contiguous).
 #include "reduce.cuh"
+#include "rowio.cuh"
 #include "rows.h"
 #include "tc_common.cuh"
 
@@ -71,6 +72,7 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
     const uint32_t w1_smem = base;                  // [256 rows x 128 B]: two halves of 128 rows
     const uint32_t w2_smem = base + 32768;          // 8 K-chunks x [32 rows x 128 B]
     const uint32_t t_smem = base + 65536;           // 3 stages x [128 rows x 128 B]
+    uint8_t* const io_scratch = smem_raw + (base - smem_u32(smem_raw)) + 65536 + 3 * 16384;   // 8 epilogue warps x 2 KB (rowio.cuh)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto BAR = [&](int i) { return smem_u32(&bars[i]); };
     const int FULL = 0, EMPTY = 3, WBAR = 6, EFULL = 7, EREADY = 10, DFULL = 13, DFREE = 15;
@@ -158,12 +160,18 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
             // 1 = activation positive.  fwd builds them with one funnel shift per element, bwd tests them.
             uint4 mlo = make_uint4(0u, 0u, 0u, 0u), mhi = mlo;
             float4 pre_r[8];
+            // the warp's 32 rows are contiguous in global memory: row-wide traffic goes through the coalescing helpers (rowio.cuh)
+            const uint32_t rowmask = __ballot_sync(0xffffffffu, in_patch);
+            const long long orow_w = orow - lane;
+            uint8_t* const sc = io_scratch + (warp - 2) * ROWIO_SCRATCH_BYTES;
             if (MODE == 1) {
                 mlo = __ldg(reinterpret_cast<const uint4*>(a.mask + orow * 8));
                 mhi = __ldg(reinterpret_cast<const uint4*>(a.mask + orow * 8) + 1);
+                if (a.residual) rowio_ldg_chunks(a.residual + orow_w * 32, rowmask, pre_r);
+                else {
 #pragma unroll
-                for (int g4 = 0; g4 < 8; ++g4)
-                    pre_r[g4] = (a.residual && in_patch) ? __ldg(reinterpret_cast<const float4*>(a.residual + orow * 32) + g4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int g4 = 0; g4 < 8; ++g4) pre_r[g4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {                     // rolled on purpose: the unrolled body thrashes the instruction cache
@@ -226,11 +234,17 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(DFREE + db));
-            if (in_patch) {
-                float4* yp = reinterpret_cast<float4*>(a.out + orow * 32);
+            if (MODE == 1 && a.residual) {
+                float4 t[8];
+#pragma unroll
+                for (int g4 = 0; g4 < 8; ++g4) t[g4] = pre_r[g4];
+                rowio_rows_from_chunks(t, pre_r, sc);
+            }
+            {
+                float out_row[32];
 #pragma unroll
                 for (int g4 = 0; g4 < 8; ++g4) {
-                    float o[4];
+                    float* o = out_row + 4 * g4;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) o[e] = __uint_as_float(v[g4 * 4 + e]);
                     if (MODE == 0) {
@@ -238,7 +252,7 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                         o[0] += bq.x; o[1] += bq.y; o[2] += bq.z; o[3] += bq.w;
                     } else {
                         o[0] += pre_r[g4].x; o[1] += pre_r[g4].y; o[2] += pre_r[g4].z; o[3] += pre_r[g4].w;
-                        if (a.relumask) {           // only the first block flows into a ReLU (mainConv1): not worth prefetch registers
+                        if (a.relumask && in_patch) {           // only the first block flows into a ReLU (mainConv1): not worth prefetch registers
                             const float4 mq = __ldg(reinterpret_cast<const float4*>(a.relumask + orow * 32) + g4);
                             if (!(mq.x > 0.f)) o[0] = 0.f;
                             if (!(mq.y > 0.f)) o[1] = 0.f;
@@ -251,8 +265,8 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                         if (!valid) o[e] = 0.f;
                         if (a.round_tf32) o[e] = rna_tf32(o[e]);
                     }
-                    yp[g4] = make_float4(o[0], o[1], o[2], o[3]);
                 }
+                rowio_store_rows(a.out + orow_w * 32, out_row, rowmask, sc);
             }
         }
     }
@@ -484,7 +498,7 @@ static int launch_respipe(const float* t, const float* w1, const float* w2, cons
     PV_TRY(make_tmap_2d(&tm_t, t, rows, 32, 128, 32, 0));
     PV_TRY(make_tmap_2d(&tm_w1, w1, 256, 32, 256, 32, 0));      // [256 rows][32]: We^T (fwd) | Wd (bwd)
     PV_TRY(make_tmap_2d(&tm_w2, w2, 32, 256, 32, 32, 0));       // [32 rows][256]: Wd^T (fwd) | We (bwd)
-    const size_t smem = 1024 + 65536 + 3 * 16384;
+    const size_t smem = 1024 + 65536 + 3 * 16384 + 8 * ROWIO_SCRATCH_BYTES;
     static bool attr = false;
     if (!attr) { PV_CUDA(cudaFuncSetAttribute(resfront_pipe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     int dev = 0, sms = 148;
