@@ -511,10 +511,17 @@ int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip
     }
     PV_TRY(conv_rows(m, m->layers[m->li("upscaleConv1")], valid, P["G3"], F, g_geom(3), P["G4"], g_geom(4), nullptr, B, "upscale_fwd", st, false));
     const float* q = P["mn"];
-    for (int i = 0; i < c.scale; ++i) {                                // WDSRNetLRResidualPath, modelsTF.py:45-53
-        float* out = P["q" + std::to_string(i + 1)];
-        PV_TRY(conv_fwd(m, m->li("residConv" + std::to_string(i + 1)), q, out, nullptr, B, st));
-        q = out;
+    if (c.scale == 3 && skip2d_supported(m->S, c.scale * c.scale)) {   // WDSRNetLRResidualPath, modelsTF.py:45-53: one fused kernel
+        const Layer &R1 = m->layers[m->li("residConv1")], &R2 = m->layers[m->li("residConv2")], &R3 = m->layers[m->li("residConv3")];
+        PV_TRY(launch_skip2d_fwd(P["mn"], m->weff + R1.weff_off, m->bias_s + R1.bias_s_off, m->weff + R2.weff_off, m->bias_s + R2.bias_s_off,
+                                 m->weff + R3.weff_off, m->bias_s + R3.bias_s_off, B, m->S, c.scale * c.scale, P["q1"], P["q2"], P["q3"], st));
+        q = P["q3"];
+    } else {
+        for (int i = 0; i < c.scale; ++i) {
+            float* out = P["q" + std::to_string(i + 1)];
+            PV_TRY(conv_fwd(m, m->li("residConv" + std::to_string(i + 1)), q, out, nullptr, B, st));
+            q = out;
+        }
     }
     PV_TRY(launch_tail_rows(P["G4"], g_geom(4), F, q, B, m->P, c.scale, c.mean, c.std, clip_round, sr, st));
     return 0;
@@ -534,7 +541,13 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
     PV_CUDA(cudaMemsetAsync(t->dweff, 0, m->nweff * sizeof(float), st));
     PV_CUDA(cudaMemsetAsync(t->dbias_s, 0, m->nbias_s * sizeof(float), st));
     PV_TRY(launch_tail_bwd_rows(g_sr, B, m->P, c.scale, c.std, P["g_G4"], g_geom(4), F, P["g_tail"], st));
-    {   // ---- 2-D skip path (dense kernels)
+    if (c.scale == 3 && skip2d_supported(m->S, c.scale * c.scale) &&
+        skip2d_partial_floats(B, m->S, c.scale * c.scale) <= t->wg_partial_floats) {   // ---- 2-D skip path: one fused kernel + a fixed-order reduction
+        const Layer &R1 = m->layers[m->li("residConv1")], &R2 = m->layers[m->li("residConv2")], &R3 = m->layers[m->li("residConv3")];
+        PV_TRY(launch_skip2d_bwd(P["mn"], P["q1"], P["q2"], P["g_tail"], m->weff + R2.weff_off, m->weff + R3.weff_off, B, m->S,
+                                 c.scale * c.scale, t->wg_partials, t->wg_partial_floats, t->dweff + R1.weff_off, t->dweff + R2.weff_off,
+                                 t->dweff + R3.weff_off, t->dbias_s + R1.bias_s_off, t->dbias_s + R2.bias_s_off, t->dbias_s + R3.bias_s_off, st));
+    } else {   // ---- 2-D skip path (dense kernels)
         const float* gout = P["g_tail"];
         for (int i = c.scale; i >= 1; --i) {
             const int id = m->li("residConv" + std::to_string(i));
