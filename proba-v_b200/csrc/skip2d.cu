@@ -26,18 +26,27 @@ struct Skip2dShape {
 };
 
 // out[p][co] = act(b[co] + sum_{tap,ci} in[p + tap][ci] * w[tap][ci][co]) over a So x So output from an (So+2)^2 input
-__device__ __forceinline__ void conv3x3_valid(const float* __restrict__ in, int Si, int cin, const float* __restrict__ w,
-                                              const float* __restrict__ b, int C, bool relu, float* __restrict__ out) {
+template <int CT, int CINT>
+__device__ __forceinline__ void conv3x3_valid(const float* __restrict__ in, int Si, int cin_rt, const float* __restrict__ w,
+                                              const float* __restrict__ b, int C_rt, bool relu, float* __restrict__ out) {
+    const int C = CT ? CT : C_rt, cin = CINT ? CINT : cin_rt;      // compile-time counts let the ci loop unroll: independent LDS, no latency chain
     const int So = Si - 2;
     for (int idx = threadIdx.x; idx < So * So * C; idx += SK_THREADS) {
         const int co = idx % C, p = idx / C, h = p / So, x = p % So;
         float acc = b[co];
-        for (int a = 0; a < 3; ++a)
-            for (int bb = 0; bb < 3; ++bb) {
-                const float* ip = in + ((h + a) * Si + x + bb) * cin;
-                const float* wp = w + (a * 3 + bb) * cin * C + co;
-                for (int ci = 0; ci < cin; ++ci) acc = fmaf(ip[ci], wp[ci * C], acc);
+        float acc1 = 0.f, acc2 = 0.f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float* ip = in + ((h + a) * Si + x) * cin;
+            const float* wp = w + (a * 3) * cin * C + co;
+#pragma unroll
+            for (int ci = 0; ci < cin; ++ci) {
+                acc = fmaf(ip[ci], wp[ci * C], acc);
+                acc1 = fmaf(ip[cin + ci], wp[(cin + ci) * C], acc1);
+                acc2 = fmaf(ip[2 * cin + ci], wp[(2 * cin + ci) * C], acc2);
             }
+        }
+        acc += acc1 + acc2;
         out[idx] = relu ? fmaxf(acc, 0.f) : acc;
     }
 }
@@ -56,11 +65,19 @@ skip2d_fwd_kernel(const float* __restrict__ mn, const float* __restrict__ w1, co
     for (int i = threadIdx.x; i < sh.nw2(); i += SK_THREADS) { sw2[i] = w2[i]; sw3[i] = w3[i]; }
     if (threadIdx.x < C) { sb[threadIdx.x] = b1[threadIdx.x]; sb[C + threadIdx.x] = b2[threadIdx.x]; sb[2 * C + threadIdx.x] = b3[threadIdx.x]; }
     __syncthreads();
-    conv3x3_valid(x, S, 1, sw1, sb, C, true, a1);
-    __syncthreads();
-    conv3x3_valid(a1, sh.s1(), C, sw2, sb + C, C, false, a2);
-    __syncthreads();
-    conv3x3_valid(a2, sh.s2(), C, sw3, sb + 2 * C, C, false, a3);
+    if (C == 9) {
+        conv3x3_valid<9, 1>(x, S, 1, sw1, sb, C, true, a1);
+        __syncthreads();
+        conv3x3_valid<9, 9>(a1, sh.s1(), C, sw2, sb + C, C, false, a2);
+        __syncthreads();
+        conv3x3_valid<9, 9>(a2, sh.s2(), C, sw3, sb + 2 * C, C, false, a3);
+    } else {
+        conv3x3_valid<0, 0>(x, S, 1, sw1, sb, C, true, a1);
+        __syncthreads();
+        conv3x3_valid<0, 0>(a1, sh.s1(), C, sw2, sb + C, C, false, a2);
+        __syncthreads();
+        conv3x3_valid<0, 0>(a2, sh.s2(), C, sw3, sb + 2 * C, C, false, a3);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < n1; i += SK_THREADS) q1[(size_t)b * n1 + i] = a1[i];
     for (int i = threadIdx.x; i < n2; i += SK_THREADS) q2[(size_t)b * n2 + i] = a2[i];
@@ -68,39 +85,58 @@ skip2d_fwd_kernel(const float* __restrict__ mn, const float* __restrict__ w1, co
 }
 
 // gin[p][ci] = sum_{tap,co} g[p - tap][co] * w[tap][ci][co]   (full correlation: So = Sg + 2), optionally * (ref > 0)
-__device__ __forceinline__ void dgrad3x3(const float* __restrict__ g, int Sg, const float* __restrict__ w, int C,
+template <int CT>
+__device__ __forceinline__ void dgrad3x3(const float* __restrict__ g, int Sg, const float* __restrict__ w, int C_rt,
                                          const float* __restrict__ relu_ref, float* __restrict__ gin) {
+    const int C = CT ? CT : C_rt;
     const int So = Sg + 2;
     for (int idx = threadIdx.x; idx < So * So * C; idx += SK_THREADS) {
         const int ci = idx % C, p = idx / C, h = p / So, x = p % So;
-        float acc = 0.f;
+        float acc = 0.f, acc1 = 0.f, acc2 = 0.f;
+#pragma unroll
         for (int a = 0; a < 3; ++a) {
             const int hh = h - a;
             if (hh < 0 || hh >= Sg) continue;
-            for (int bb = 0; bb < 3; ++bb) {
-                const int xx = x - bb;
-                if (xx < 0 || xx >= Sg) continue;
-                const float* gp = g + (hh * Sg + xx) * C;
-                const float* wp = w + ((a * 3 + bb) * C + ci) * C;
-                for (int co = 0; co < C; ++co) acc = fmaf(gp[co], wp[co], acc);
+            const float* gp = g + (hh * Sg + x) * C;
+            const float* wp = w + ((a * 3) * C + ci) * C;
+            const bool ok0 = x < Sg, ok1 = x >= 1 && x - 1 < Sg, ok2 = x >= 2;
+#pragma unroll
+            for (int co = 0; co < C; ++co) {
+                if (ok0) acc = fmaf(gp[co], wp[co], acc);
+                if (ok1) acc1 = fmaf(gp[co - C], wp[C * C + co], acc1);
+                if (ok2) acc2 = fmaf(gp[co - 2 * C], wp[2 * C * C + co], acc2);
             }
         }
+        acc += acc1 + acc2;
         if (relu_ref && !(relu_ref[idx] > 0.f)) acc = 0.f;
         gin[idx] = acc;
     }
 }
 
 // dw[tap][ci][co] = sum_p in[p + tap][ci] * g[p][co],  db[co] = sum_p g[p][co]   (g is Sg x Sg, in is (Sg+2)^2)
-__device__ __forceinline__ void wgrad3x3(const float* __restrict__ in, int cin, const float* __restrict__ g, int Sg, int C,
+template <int CT>
+__device__ __forceinline__ void wgrad3x3(const float* __restrict__ in, int cin, const float* __restrict__ g, int Sg, int C_rt,
                                          float* __restrict__ dw, float* __restrict__ db) {
+    const int C = CT ? CT : C_rt;
     const int Si = Sg + 2, nw = 9 * cin * C;
     for (int idx = threadIdx.x; idx < nw + C; idx += SK_THREADS) {
         float acc = 0.f;
         if (idx < nw) {
             const int co = idx % C, ci = (idx / C) % cin, tap = idx / (C * cin), a = tap / 3, bb = tap % 3;
-            for (int h = 0; h < Sg; ++h)
-                for (int x = 0; x < Sg; ++x) acc = fmaf(in[((h + a) * Si + x + bb) * cin + ci], g[(h * Sg + x) * C + co], acc);
-            dw[idx] = acc;
+            float acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;      // four independent chains over the pixels of a line
+            for (int h = 0; h < Sg; ++h) {
+                const float* ip = in + ((h + a) * Si + bb) * cin + ci;
+                const float* gp = g + (h * Sg) * C + co;
+                int x = 0;
+                for (; x + 3 < Sg; x += 4) {
+                    acc = fmaf(ip[x * cin], gp[x * C], acc);
+                    acc1 = fmaf(ip[(x + 1) * cin], gp[(x + 1) * C], acc1);
+                    acc2 = fmaf(ip[(x + 2) * cin], gp[(x + 2) * C], acc2);
+                    acc3 = fmaf(ip[(x + 3) * cin], gp[(x + 3) * C], acc3);
+                }
+                for (; x < Sg; ++x) acc = fmaf(ip[x * cin], gp[x * C], acc);
+            }
+            dw[idx] = (acc + acc1) + (acc2 + acc3);
         } else {
             const int co = idx - nw;
             for (int p = 0; p < Sg * Sg; ++p) acc += g[p * C + co];
@@ -126,13 +162,23 @@ skip2d_bwd_kernel(const float* __restrict__ mn, const float* __restrict__ q1, co
     __syncthreads();
     float* out = partials + (size_t)b * sh.npart();
     float* dw1 = out; float* dw2 = dw1 + sh.nw1(); float* dw3 = dw2 + sh.nw2(); float* db = dw3 + sh.nw2();
-    dgrad3x3(gg3, sh.s3(), sw3, C, nullptr, gg2);
-    wgrad3x3(a2, C, gg3, sh.s3(), C, dw3, db + 2 * C);
-    __syncthreads();
-    dgrad3x3(gg2, sh.s2(), sw2, C, a1, gg1);              // flows into residConv1's ReLU
-    wgrad3x3(a1, C, gg2, sh.s2(), C, dw2, db + C);
-    __syncthreads();
-    wgrad3x3(x, 1, gg1, sh.s1(), C, dw1, db);
+    if (C == 9) {
+        dgrad3x3<9>(gg3, sh.s3(), sw3, C, nullptr, gg2);
+        wgrad3x3<9>(a2, C, gg3, sh.s3(), C, dw3, db + 2 * C);
+        __syncthreads();
+        dgrad3x3<9>(gg2, sh.s2(), sw2, C, a1, gg1);           // flows into residConv1's ReLU
+        wgrad3x3<9>(a1, C, gg2, sh.s2(), C, dw2, db + C);
+        __syncthreads();
+        wgrad3x3<9>(x, 1, gg1, sh.s1(), C, dw1, db);
+    } else {
+        dgrad3x3<0>(gg3, sh.s3(), sw3, C, nullptr, gg2);
+        wgrad3x3<0>(a2, C, gg3, sh.s3(), C, dw3, db + 2 * C);
+        __syncthreads();
+        dgrad3x3<0>(gg2, sh.s2(), sw2, C, a1, gg1);
+        wgrad3x3<0>(a1, C, gg2, sh.s2(), C, dw2, db + C);
+        __syncthreads();
+        wgrad3x3<0>(x, 1, gg1, sh.s1(), C, dw1, db);
+    }
     for (int i = sh.nw1() + 2 * sh.nw2() + 3 * C + threadIdx.x; i < sh.npart(); i += SK_THREADS) out[i] = 0.f;
 }
 
