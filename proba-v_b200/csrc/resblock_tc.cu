@@ -462,13 +462,13 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
 
 // dWd [256][32] (= dweff of decConv), dWe [32][256] (= dweff of expConv), dbe [256], dbd [32] from the per-CTA partials;
 // fixed-order block reduction (reduce.cuh).  Blocks [0,128): weight gradients; 128,129: dbe; 130: dbd.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 resfront_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ dbp, int ncta,
                        float* __restrict__ dwd, float* __restrict__ dwe, float* __restrict__ dbe, float* __restrict__ dbd) {
-    __shared__ float4 sm[256];
+    __shared__ float4 sm[1024];
     const int b = blockIdx.x, x = threadIdx.x & 31;
     if (b < 128) {
-        const float4 s = block_rowsum4(partials, ncta, [](int r) { return (size_t)r * 16384; }, b * 32, true, sm);
+        const float4 s = block_rowsum4<32>(partials, ncta, [](int r) { return (size_t)r * 16384; }, b * 32, true, sm);
         if (threadIdx.x >= 32) return;
         const float v[4] = {s.x, s.y, s.z, s.w};
         const int idx0 = (b * 32 + x) * 4;
@@ -480,11 +480,11 @@ resfront_reduce_kernel(const float* __restrict__ partials, const float* __restri
             else dwe[(size_t)n * 256 + (g - 2) * 128 + m] = v[e];                  // [ci][ch]
         }
     } else if (b < 130) {       // dbe: both epilogue groups of every CTA
-        const float4 s = block_rowsum4(dbp, 2 * ncta, [](int r) { return (size_t)(r >> 1) * 768 + (r & 1) * 256; }, (b - 128) * 32, true, sm);
+        const float4 s = block_rowsum4<32>(dbp, 2 * ncta, [](int r) { return (size_t)(r >> 1) * 768 + (r & 1) * 256; }, (b - 128) * 32, true, sm);
         if (threadIdx.x < 32) { float* o = dbe + ((b - 128) * 32 + x) * 4; o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w; }
     } else {                    // dbd: eight epilogue warps of every CTA
         const bool ok = x < 8;
-        const float4 s = block_rowsum4(dbp, 8 * ncta, [](int r) { return (size_t)(r >> 3) * 768 + 512 + (r & 7) * 32; }, 0, ok, sm);
+        const float4 s = block_rowsum4<32>(dbp, 8 * ncta, [](int r) { return (size_t)(r >> 3) * 768 + 512 + (r & 7) * 32; }, 0, ok, sm);
         if (threadIdx.x < 32 && ok) { float* o = dbd + x * 4; o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w; }
     }
 }
@@ -570,7 +570,7 @@ int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* 
     }
     {
         PV_TIMED("wgrad_reduce", st);
-        resfront_reduce_kernel<<<131, 256, 0, st>>>(a.partials, a.db_partials, grid, dw_dec, dw_exp, db_exp, db_dec);
+        resfront_reduce_kernel<<<131, 1024, 0, st>>>(a.partials, a.db_partials, grid, dw_dec, dw_exp, db_exp, db_dec);
         PV_LAUNCH_CHECK();
     }
     return 0;

@@ -281,10 +281,10 @@ __global__ void __launch_bounds__(256) first_conv_pr_wgrad_kernel(const float* _
     if (warp < 4) out[(warp + 24) * 32 + lane] = acc[3];
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 first_conv_pr_wgrad_reduce_kernel(const float* __restrict__ partials, int ncta, float* __restrict__ dw, float* __restrict__ db) {
-    __shared__ float4 sm[256];      // 7 blocks x 32 float4 columns = the 28 x 32 outputs (27 taps + bias); fixed order (reduce.cuh)
-    const float4 s = block_rowsum4(partials, ncta, [](int r) { return (size_t)r * (28 * 32); }, blockIdx.x * 32, true, sm);
+    __shared__ float4 sm[1024];     // 7 blocks x 32 float4 columns = the 28 x 32 outputs (27 taps + bias); fixed order (reduce.cuh)
+    const float4 s = block_rowsum4<32>(partials, ncta, [](int r) { return (size_t)r * (28 * 32); }, blockIdx.x * 32, true, sm);
     if (threadIdx.x >= 32) return;
     const int i = (blockIdx.x * 32 + threadIdx.x) * 4;
     float* o = i < 27 * 32 ? dw + i : db + (i - 27 * 32);
@@ -426,7 +426,7 @@ int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, i
     PV_TIMED("first_conv_pr_wgrad", st, 2.0 * B * T * S * S * 27 * 32, 0.0);
     first_conv_pr_wgrad_kernel<<<grid, 256, 0, st>>>(xn, gz, B, S, T, g, partials);
     PV_LAUNCH_CHECK();
-    first_conv_pr_wgrad_reduce_kernel<<<7, 256, 0, st>>>(partials, grid, dw, db);
+    first_conv_pr_wgrad_reduce_kernel<<<7, 1024, 0, st>>>(partials, grid, dw, db);
     PV_LAUNCH_CHECK();
     return 0;
 }

@@ -188,7 +188,7 @@ skip2d_reduce_kernel(const float* __restrict__ partials, int B, Skip2dShape sh, 
     __shared__ float4 smr[256];
     const int np = sh.npart();
     const bool ok = (int)(blockIdx.x * 32 + (threadIdx.x & 31)) * 4 < np;
-    const float4 s = block_rowsum4(partials, B, [np](int r) { return (size_t)r * np; }, blockIdx.x * 32, ok, smr);
+    const float4 s = block_rowsum4<8>(partials, B, [np](int r) { return (size_t)r * np; }, blockIdx.x * 32, ok, smr);
     if (threadIdx.x >= 32 || !ok) return;
     const float v[4] = {s.x, s.y, s.z, s.w};
     const int n1 = sh.nw1(), n2 = sh.nw2(), C = sh.C;

@@ -183,14 +183,14 @@ rowwgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 // fixed-order reduction of the per-CTA partials into dweff / dbias (reduce.cuh).  mode 0: conv3 (group = (dt,dh),
 // m = q*32+ci, n = co); mode 1: wide x (group g, m = channel in group -> K index g*128+m, n = co); mode 2: wide gz
 // (m = co in group, n = ci).  Blocks [0, total/128) own 128 weight-gradient outputs each, the remaining blocks the bias sums.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 wgrad_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ dbp, int ncta, int ngroup, int mode,
                     RowWgradP p, int nbias) {
-    __shared__ float4 sm[256];
+    __shared__ float4 sm[1024];
     const int total = ngroup * 4096;
     const int nmain = total / 128;
     if ((int)blockIdx.x < nmain) {
-        const float4 s = block_rowsum4(partials, ncta, [total](int r) { return (size_t)r * total; }, blockIdx.x * 32, true, sm);
+        const float4 s = block_rowsum4<32>(partials, ncta, [total](int r) { return (size_t)r * total; }, blockIdx.x * 32, true, sm);
         if (threadIdx.x >= 32) return;
         const float v[4] = {s.x, s.y, s.z, s.w};
         const int idx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
@@ -211,7 +211,7 @@ wgrad_reduce_kernel(const float* __restrict__ partials, const float* __restrict_
     } else {
         const int bb = blockIdx.x - nmain, w = nbias * 32;
         const bool ok = (bb * 32 + (int)(threadIdx.x & 31)) * 4 < w;
-        const float4 s = block_rowsum4(dbp, ncta * 4, [w](int r) { return (size_t)r * w; }, bb * 32, ok, sm);
+        const float4 s = block_rowsum4<32>(dbp, ncta * 4, [w](int r) { return (size_t)r * w; }, bb * 32, ok, sm);
         if (threadIdx.x < 32 && ok && p.db) {
             float* o = p.db + (bb * 32 + threadIdx.x) * 4;
             o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w;
@@ -293,7 +293,7 @@ int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, siz
     }
     {
         PV_TIMED("wgrad_reduce", st);
-        wgrad_reduce_kernel<<<a.ngroup * 32 + cdiv(a.nbias * 8, 32), 256, 0, st>>>(a.partials, a.db_partials, grid, a.ngroup, mode, p, a.nbias);
+        wgrad_reduce_kernel<<<a.ngroup * 32 + cdiv(a.nbias * 8, 32), 1024, 0, st>>>(a.partials, a.db_partials, grid, a.ngroup, mode, p, a.nbias);
         PV_LAUNCH_CHECK();
     }
     return 0;
