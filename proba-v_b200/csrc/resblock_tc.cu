@@ -32,6 +32,13 @@ __device__ __forceinline__ float rna_tf32(float x) {
     return __uint_as_float(u);
 }
 
+// Round-to-nearest tf32 for a value that only feeds a kind::tf32 MMA from TMEM: add half a tf32 ulp to the bit pattern
+// (sign-magnitude, so this rounds half away from zero) and leave the low 13 bits alone -- the tensor core ignores them.
+// One integer add instead of the FSETP / IADD / LOP3 sequence cvt.rna.tf32.f32 compiles to; the epilogues below are
+// issue-bound on exactly these per-element instructions (PV_DEBUG timing experiments: the element math was half of the
+// forward kernel's run time).  Non-finite inputs are not preserved (an Inf would become a NaN pattern).
+__device__ __forceinline__ uint32_t tf32_bump(uint32_t bits) { return bits + 0x1000u; }
+
 // ----------------------------------------------------------------------------------------------------------------
 // Forward and backward-data share one kernel (MODE 0 / 1): both are
 //     MMA1 (SS)  H_h[128 x 128] = T[128 x 32] . W1_h^T      T = X (fwd) | gD (bwd);  W1 = We^T (fwd) | Wd (bwd)
@@ -200,9 +207,9 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                             for (int e = 0; e < 4; ++e) {
                                 // x = relu(y) >= +0; (bits(x) - 1) has its sign bit set exactly when x == 0, i.e. when y <= 0,
                                 // which is tf.nn.relu's gradient convention (0 at y == 0)
-                                const uint32_t x = __float_as_uint(rna_tf32(fmaxf(__uint_as_float(cur[e4 * 4 + e]) + bb[e], 0.f)));
+                                const uint32_t x = __float_as_uint(fmaxf(__uint_as_float(cur[e4 * 4 + e]) + bb[e], 0.f));
                                 sgn = __funnelshift_l(x - 1u, sgn, 1);
-                                cur[e4 * 4 + e] = x;
+                                cur[e4 * 4 + e] = tf32_bump(x);
                             }
                         }
                         wd[c] = ~sgn;
@@ -210,7 +217,7 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                         const uint32_t bits = wd[c];
 #pragma unroll
                         for (int e = 0; e < 32; ++e)
-                            cur[e] = __float_as_uint(rna_tf32(__uint_as_float(cur[e]))) & (uint32_t)((int32_t)(bits << e) >> 31);
+                            cur[e] = (bits & (0x80000000u >> e)) ? tf32_bump(cur[e]) : 0u;
                     }
                     tmem_st32(hb + c * 32, cur);
                 }
@@ -420,11 +427,11 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
                 tmem_ld_wait();
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
-                    const uint32_t x = __float_as_uint(rna_tf32(fmaxf(__uint_as_float(e[k]) + be, 0.f)));
-                    const uint32_t z = __float_as_uint(rna_tf32(__uint_as_float(v[k]))) & ~(uint32_t)((int32_t)(x - 1u) >> 31);   // 0 where E == 0
-                    zsum += __uint_as_float(z);
-                    e[k] = x;
-                    v[k] = z;
+                    const float x = fmaxf(__uint_as_float(e[k]) + be, 0.f);
+                    const bool pos = x > 0.f;                              // tf.nn.relu's gradient convention: 0 at E == 0
+                    zsum += pos ? __uint_as_float(v[k]) : 0.f;             // bias gradient from the unrounded value
+                    e[k] = tf32_bump(__float_as_uint(x));
+                    v[k] = pos ? tf32_bump(v[k]) : 0u;
                 }
                 tmem_st32(lane_base + eb * 128 + c * 32, e);
                 tmem_st32(lane_base + eb * 128 + 64 + c * 32, v);
