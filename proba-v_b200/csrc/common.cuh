@@ -42,6 +42,20 @@ int64_t launch_count();
         if (_s != 0) return _s;                                                               \
     } while (0)
 
+// Launch with programmatic stream serialization (see tc_common.cuh pdl_wait / pdl_trigger).  PV_NO_PDL=1 falls back to a
+// plain launch (the griddepcontrol instructions are no-ops then).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // Per-kernel-class device timing behind pv_timing_* (bench.py's roofline): when enabled, a launch is bracketed by

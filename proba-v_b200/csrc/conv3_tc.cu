@@ -120,6 +120,8 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             tma_prefetch_desc(&tm_w);
             mbar_arrive_expect_tx(BAR(WBAR), 27u * 4096u);
             for (int t = 0; t < 27; ++t) tma_load_2d(w_smem + t * 4096, &tm_w, BAR(WBAR), a.tap_wc[t], a.tap_wr[t]);
+            pdl_wait();                                      // activations come from the previous kernel
+            pdl_trigger();
             uint32_t n = 0;                                  // slabs loaded so far: slab k lives in stage k % 4
             for (int tile = t_lo; tile < t_hi; ++tile) {
                 const TileInfo ti = tile_info(a, tile, t_lo);
@@ -186,6 +188,7 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         const int q = warp & 3;
         const uint32_t grp = (uint32_t)(warp - 2) >> 2;
         uint32_t tl = 0;
+        pdl_wait();
         for (int tile = t_lo; tile < t_hi; ++tile, ++tl) {
             const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
             if (acc != grp) continue;
@@ -332,7 +335,7 @@ int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st) {
     PV_TIMED(p.tag ? p.tag : "rowconv3_tc", st, p.flops, 0.0);
     static size_t attr = 0;
     if (smem > attr) { PV_CUDA(cudaFuncSetAttribute(rowconv3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
-    rowconv3_tc_kernel<<<grid, C3_THREADS, smem, st>>>(tm_x, tm_w, a);
+    PV_CUDA(launch_pdl(rowconv3_tc_kernel, grid, C3_THREADS, smem, st, tm_x, tm_w, a));
     PV_LAUNCH_CHECK();
     return 0;
 }

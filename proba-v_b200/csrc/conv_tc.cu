@@ -120,6 +120,8 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             tma_prefetch_desc(&tm_w);
             mbar_arrive_expect_tx(BAR(WBAR), (uint32_t)a.ntap * W_TAP_BYTES);
             for (int t = 0; t < a.ntap; ++t) tma_load_2d(w_smem + t * W_TAP_BYTES, &tm_w, BAR(WBAR), a.tap_wc[t], a.tap_wr[t]);
+            pdl_wait();
+            pdl_trigger();
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
@@ -196,6 +198,7 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const int q = warp & 3;
         const uint32_t grp = (uint32_t)(warp - 2) >> 2;
         uint32_t tl = 0;
+        pdl_wait();
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tl) {
             const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
             if (acc != grp) continue;
@@ -318,10 +321,10 @@ int launch_rowconv_tc(const RowConvP& p, cudaStream_t st) {
     static size_t attr32 = 0, attr256 = 0;
     if (p.n == 32) {
         if (smem > attr32) { PV_CUDA(cudaFuncSetAttribute(rowconv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr32 = smem; }
-        rowconv_tc_kernel<32><<<grid, TC_THREADS, smem, st>>>(tm_x, tm_w, a);
+        PV_CUDA(launch_pdl(rowconv_tc_kernel<32>, grid, TC_THREADS, smem, st, tm_x, tm_w, a));
     } else {
         if (smem > attr256) { PV_CUDA(cudaFuncSetAttribute(rowconv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr256 = smem; }
-        rowconv_tc_kernel<256><<<grid, TC_THREADS, smem, st>>>(tm_x, tm_w, a);
+        PV_CUDA(launch_pdl(rowconv_tc_kernel<256>, grid, TC_THREADS, smem, st, tm_x, tm_w, a));
     }
     PV_LAUNCH_CHECK();
     return 0;

@@ -11,6 +11,7 @@
 //   resolve / resolveByBatch / reconstruct_from_patches   test.py:114-160     -> pv_resolve*, pv_predict_*
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -38,6 +39,7 @@ int set_error(int code, const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches += n; }
 int64_t launch_count() { return g_launches.load(); }
+bool pdl_enabled() { static const bool on = getenv("PV_NO_PDL") == nullptr; return on; }
 
 // ------------------------------------------------------------------------------------------ kernel timing
 namespace {

@@ -107,6 +107,8 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
             mbar_arrive_expect_tx(BAR(WBAR), 65536);
             tma_load_2d(w1_smem, &tm_w1, BAR(WBAR), 0, 0);
             for (int j = 0; j < 8; ++j) tma_load_2d(w2_smem + j * 4096, &tm_w2, BAR(WBAR), 32 * j, 0);
+            pdl_wait();
+            pdl_trigger();
             for (int tl = 0; tl < my_tiles; ++tl) {
                 const int tile = blockIdx.x + tl * gridDim.x;
                 const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
@@ -156,6 +158,7 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
         const int q = warp & 3;
         const int grp = (warp - 2) >> 2;
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        pdl_wait();
         for (int tl = grp; tl < my_tiles; tl += 2) {
             const int tile = blockIdx.x + tl * gridDim.x;
             const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
@@ -341,6 +344,8 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
             mbar_arrive_expect_tx(BAR(WBAR), 65536);
             tma_load_2d(weT_smem, &tm_weT, BAR(WBAR), 0, 0);
             tma_load_2d(wd_smem, &tm_wd, BAR(WBAR), 0, 0);
+            pdl_wait();
+            pdl_trigger();
             for (int tl = 0; tl < my_tiles; ++tl) {
                 const int tile = t_lo + tl;
                 const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
@@ -401,6 +406,7 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         float dbe0 = 0.f, dbe1 = 0.f, dbd = 0.f;
         const int U = 4 * my_tiles;
+        pdl_wait();                                          // the partial buffers may still be read by the previous reduction
 #pragma unroll 1
         for (int u = grp; u < U; u += 2) {          // sub-tile s == grp for every unit of this group
             const int tl = u >> 2, h = (u >> 1) & 1;
@@ -473,6 +479,7 @@ __global__ void __launch_bounds__(1024)
 resfront_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ dbp, int ncta,
                        float* __restrict__ dwd, float* __restrict__ dwe, float* __restrict__ dbe, float* __restrict__ dbd) {
     __shared__ float4 sm[1024];
+    tc::pdl_wait();
     const int b = blockIdx.x, x = threadIdx.x & 31;
     if (b < 128) {
         const float4 s = block_rowsum4<32>(partials, ncta, [](int r) { return (size_t)r * 16384; }, b * 32, true, sm);
@@ -514,7 +521,7 @@ static int launch_respipe(const float* t, const float* w1, const float* w2, cons
     const int ntiles = a.B * a.tiles_per_patch;
     const int grid = ntiles < sms ? ntiles : sms;
     PV_TIMED(tag, st, flops, 0.0);
-    resfront_pipe_kernel<MODE><<<grid, RP_THREADS, smem, st>>>(tm_t, tm_w1, tm_w2, a);
+    PV_CUDA(launch_pdl(resfront_pipe_kernel<MODE>, grid, RP_THREADS, smem, st, tm_t, tm_w1, tm_w2, a));
     PV_LAUNCH_CHECK();
     return 0;
 }
@@ -572,12 +579,12 @@ int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* 
     if (!attr) { PV_CUDA(cudaFuncSetAttribute(resfront_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     {
         PV_TIMED("resfront_bwd_weight", st, flops, 0.0);
-        resfront_bwd_weight_kernel<<<grid, RP_THREADS, smem, st>>>(tm_x, tm_gd, tm_x32, tm_gd32, tm_weT, tm_wd, a);
+        PV_CUDA(launch_pdl(resfront_bwd_weight_kernel, grid, RP_THREADS, smem, st, tm_x, tm_gd, tm_x32, tm_gd32, tm_weT, tm_wd, a));
         PV_LAUNCH_CHECK();
     }
     {
         PV_TIMED("wgrad_reduce", st);
-        resfront_reduce_kernel<<<131, 1024, 0, st>>>(a.partials, a.db_partials, grid, dw_dec, dw_exp, db_exp, db_dec);
+        PV_CUDA(launch_pdl(resfront_reduce_kernel, 131, 1024, 0, st, (const float*)a.partials, (const float*)a.db_partials, grid, dw_dec, dw_exp, db_exp, db_dec));
         PV_LAUNCH_CHECK();
     }
     return 0;

@@ -28,6 +28,16 @@ __device__ __forceinline__ bool elect_one_sync() {
     return pred != 0;
 }
 
+// ------------------------------------------------------------------------------------------ programmatic dependent launch
+// Kernels launched with pv::launch_pdl may start (barrier setup, TMEM allocation, weight loads) while the previous kernel
+// of the stream is still draining.  pdl_wait() blocks until that kernel has completed and its writes are visible: every
+// thread calls it before its first access to activations / gradients / scratch in global memory.  pdl_trigger() lets
+// the NEXT kernel's CTAs be scheduled as SMs free up; it is issued only AFTER this kernel's own pdl_wait(), so a
+// dependent never starts before its grand-parent has completed (weights and biases, which come from wn_prep several
+// kernels earlier with ordinary launches in between, may therefore be read before pdl_wait()).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

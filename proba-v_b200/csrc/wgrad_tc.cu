@@ -81,6 +81,8 @@ rowwgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         if (elect_one_sync()) {
             tma_prefetch_desc(&tm_a);
             tma_prefetch_desc(&tm_b);
+            pdl_wait();
+            pdl_trigger();
             uint32_t it = 0;
             for (int tile = t_lo; tile < t_hi; ++tile, ++it) {
                 const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
@@ -129,6 +131,7 @@ rowwgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         }
     } else {
         // bias gradient while the tensor core works, then the accumulator drain
+        pdl_wait();                                          // the partial buffers may still be read by the previous reduction
         const int q = warp & 3;
         float bsum[8];
 #pragma unroll
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(1024)
 wgrad_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ dbp, int ncta, int ngroup, int mode,
                     RowWgradP p, int nbias) {
     __shared__ float4 sm[1024];
+    tc::pdl_wait();
     const int total = ngroup * 4096;
     const int nmain = total / 128;
     if ((int)blockIdx.x < nmain) {
@@ -288,12 +292,12 @@ int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, siz
     if (smem > attr) { PV_CUDA(cudaFuncSetAttribute(rowwgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
     {
         PV_TIMED(p.tag ? p.tag : "rowwgrad_tc", st, p.flops, 0.0);
-        rowwgrad_tc_kernel<0><<<grid, WG_THREADS, smem, st>>>(tm_a, tm_b, a);
+        PV_CUDA(launch_pdl(rowwgrad_tc_kernel<0>, grid, WG_THREADS, smem, st, tm_a, tm_b, a));
         PV_LAUNCH_CHECK();
     }
     {
         PV_TIMED("wgrad_reduce", st);
-        wgrad_reduce_kernel<<<a.ngroup * 32 + cdiv(a.nbias * 8, 32), 1024, 0, st>>>(a.partials, a.db_partials, grid, a.ngroup, mode, p, a.nbias);
+        PV_CUDA(launch_pdl(wgrad_reduce_kernel, a.ngroup * 32 + cdiv(a.nbias * 8, 32), 1024, 0, st, a.partials, a.db_partials, grid, a.ngroup, mode, p, a.nbias));
         PV_LAUNCH_CHECK();
     }
     return 0;
