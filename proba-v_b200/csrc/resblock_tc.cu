@@ -159,6 +159,15 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
         const int grp = (warp - 2) >> 2;
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         pdl_wait();
+        // bwd: the ReLU bits are needed by the very first chunk of a tile, so they are fetched one tile ahead (the row-wide
+        // residual is only needed at the end of the tile and is requested at its start)
+        auto mask_row = [&](int tl2) -> const uint4* {
+            const int tile2 = blockIdx.x + tl2 * gridDim.x;
+            const int b2 = tile2 / a.tiles_per_patch, j2 = tile2 % a.tiles_per_patch;
+            return reinterpret_cast<const uint4*>(a.mask + (a.g.lead + (long long)b2 * a.g.pstride + a.g.row0 + j2 * 128 + q * 32 + lane) * 8);
+        };
+        uint4 nlo = make_uint4(0u, 0u, 0u, 0u), nhi = nlo;
+        if (MODE == 1 && grp < my_tiles) { const uint4* mp = mask_row(grp); nlo = __ldg(mp); nhi = __ldg(mp + 1); }
         for (int tl = grp; tl < my_tiles; tl += 2) {
             const int tile = blockIdx.x + tl * gridDim.x;
             const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
@@ -175,8 +184,8 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
             const long long orow_w = orow - lane;
             uint8_t* const sc = io_scratch + (warp - 2) * ROWIO_SCRATCH_BYTES;
             if (MODE == 1) {
-                mlo = __ldg(reinterpret_cast<const uint4*>(a.mask + orow * 8));
-                mhi = __ldg(reinterpret_cast<const uint4*>(a.mask + orow * 8) + 1);
+                mlo = nlo; mhi = nhi;
+                if (tl + 2 < my_tiles) { const uint4* mp = mask_row(tl + 2); nlo = __ldg(mp); nhi = __ldg(mp + 1); }
                 if (a.residual) rowio_ldg_chunks(a.residual + orow_w * 32, rowmask, pre_r);
                 else {
 #pragma unroll
