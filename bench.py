@@ -229,10 +229,19 @@ def run_b200(args, cfg):
     if os.path.exists(tf):
         traffic = json.load(open(tf)).get(top[0])          # bytes per launch from the committed ncu capture
     ach = top[1]["flops"] / (top[1]["ms"] * 1e-3) / 1e12
+    notes = {
+        "resfront_bwd_weight": "fused expand/decay weight gradients: E^T and gE^T recomputed transposed in TMEM (not counted as algorithmic "
+                               "flops), TS-mode N=32 MMAs at 39 cycles each; MMA-issue floor 82 us per launch, see DESIGN.md section 4",
+        "norm_wgrad": "conv3 weight gradient as M128xN96xK8 MMAs (80 cycles each, 75 % of the M slots useful): floor 64 us per launch",
+        "norm_fwd": "conv3 forward as 36 M128xN96xK8 MMAs per 126 rows: floor 47 us per launch",
+        "norm_dgrad": "conv3 data gradient as 36 M128xN96xK8 MMAs per 126 rows: floor 47 us per launch",
+    }
     roofline = {"kernel": top[0], "bound": "tensor", "achieved": ach, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tensor_sustained"], "traffic": traffic, "peak_source": peaks["source"] + ", bf16 sustained",
-                "note": "kind::tf32 MMAs run at half the bf16 rate; with N = 32 each M128xN32xK8 MMA costs 54 cycles (4 KB A-operand "
-                        "read from shared memory is not overlapped), i.e. 603 of 2048 MAC/cycle/SM -- profiles/r01_umma_rate_probe.log",
+                "frac_of_tf32_peak": ach / (0.5 * peaks["tensor_sustained"]),
+                "note": "kind::tf32 MMAs run at half the bf16 rate, and an M128xNxK8 tf32 MMA costs 32 + N/2 cycles (the A-operand fetch "
+                        "is not overlapped; profiles/r01_umma_rate_probe.log), so N <= 96 GEMMs cannot exceed 60 % of the tf32 pipe. "
+                        + notes.get(top[0], ""),
                 "avg_launch_ms": top[1]["ms"] / top[1]["launches"], "share_of_step": top[1]["ms"] / tot_ms}
     sl = rep.get("shift_loss_patch")
     roof_loss = None

@@ -209,7 +209,8 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                     uint32_t (&nxt)[32] = (c & 1) ? va : vb;
                     if (c < 3) tmem_ld32(hb + (c + 1) * 32, nxt);
                     if (MODE == 0) {
-                        uint32_t sgn = 0;
+                        // four independent 8-element sign chains (one serial 32-long funnel-shift chain would pace the warp)
+                        uint32_t sg[4] = {0u, 0u, 0u, 0u};
                         const float4* be4 = reinterpret_cast<const float4*>(s_b1 + h * 128 + c * 32);
 #pragma unroll
                         for (int e4 = 0; e4 < 8; ++e4) {
@@ -220,11 +221,11 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                                 // x = relu(y) >= +0; (bits(x) - 1) has its sign bit set exactly when x == 0, i.e. when y <= 0,
                                 // which is tf.nn.relu's gradient convention (0 at y == 0)
                                 const uint32_t x = __float_as_uint(fmaxf(__uint_as_float(cur[e4 * 4 + e]) + bb[e], 0.f));
-                                sgn = __funnelshift_l(x - 1u, sgn, 1);
+                                sg[e4 >> 1] = __funnelshift_l(x - 1u, sg[e4 >> 1], 1);
                                 cur[e4 * 4 + e] = tf32_bump(x);
                             }
                         }
-                        wd[c] = ~sgn;
+                        wd[c] = ~((sg[0] << 24) | ((sg[1] & 0xffu) << 16) | ((sg[2] & 0xffu) << 8) | (sg[3] & 0xffu));
                     } else {
                         const uint32_t bits = wd[c];
 #pragma unroll
@@ -433,7 +434,7 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
             mbar_wait(BAR(EFULL + eb), (u / 3) & 1);
             tc_fence_after();
             const float be = s_be[h * 128 + q * 32 + lane];           // this thread's channel
-            float zsum = 0.f;
+            float zs[4] = {0.f, 0.f, 0.f, 0.f};               // four independent chains for the bias-gradient row sum
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t e[32], v[32];
@@ -444,13 +445,14 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
                 for (int k = 0; k < 32; ++k) {
                     const float x = fmaxf(__uint_as_float(e[k]) + be, 0.f);
                     const bool pos = x > 0.f;                              // tf.nn.relu's gradient convention: 0 at E == 0
-                    zsum += pos ? __uint_as_float(v[k]) : 0.f;             // bias gradient from the unrounded value
+                    zs[k & 3] += pos ? __uint_as_float(v[k]) : 0.f;        // bias gradient from the unrounded value
                     e[k] = tf32_bump(__float_as_uint(x));
                     v[k] = pos ? tf32_bump(v[k]) : 0u;
                 }
                 tmem_st32(lane_base + eb * 128 + c * 32, e);
                 tmem_st32(lane_base + eb * 128 + 64 + c * 32, v);
             }
+            const float zsum = (zs[0] + zs[1]) + (zs[2] + zs[3]);
             if (h) dbe1 += zsum; else dbe0 += zsum;
             tmem_st_wait();
             tc_fence_before();
