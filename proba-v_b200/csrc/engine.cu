@@ -752,11 +752,19 @@ int pv_trainer_create(pv_model* m, int opt_kind, float learning_rate, int loss_k
     }
     if (m->rows) {
         t->wg_partial_floats = (size_t)148 * (9 * 4096 + 1024);
-        if (cudaMalloc(&t->wg_partials, t->wg_partial_floats * 4) != cudaSuccess) {
+        // deferred reductions: one private region per conv3 layer (R norm convs + reducers + upscale), per fused block,
+        // for mainConv1 and for the 2-D skip path (sized for batches up to 4096; larger batches fall back to immediate mode)
+        const size_t conv3_layers = (size_t)m->R + m->nred + 1;
+        const size_t arena = t->wg_partial_floats + conv3_layers * ((size_t)148 * (9 * 4096 + 128) + 64) +
+                             (size_t)m->R * ((size_t)148 * (4 * 4096 + 768) + 64) + (size_t)148 * 4 * 28 * 32 + 64 +
+                             pv::skip2d_partial_floats(4096, m->S, m->cfg.scale * m->cfg.scale) + 64;
+        t->rq.arena_floats = arena;
+        if (cudaMalloc(&t->wg_partials, arena * 4) != cudaSuccess) {
             pv_trainer_destroy(t);
             return set_error(PV_ERR_CUDA, "cudaMalloc of the weight-gradient partials failed");
         }
     }
+    t->rq.arena = t->wg_partials;
     cudaMemset(t->grads, 0, m->nparams * 4);
     cudaMemset(t->m1, 0, m->nparams * 4);
     cudaMemset(t->m2, 0, m->nparams * 4);

@@ -118,7 +118,7 @@ int wgrad_rows(pv_trainer* t, const Layer& L, const Taps& tp /* forward offsets 
     for (int i = 0; i < tp.n; ++i) { p.off[i] = tp.off[i]; p.c0[i] = tp.c0[i]; p.dwr0[i] = 32 * tp.chunk[i]; p.dwc0[i] = 0; }
     p.flops = 2.0 * B * L.Ho * L.Wo * L.To * L.taps() * L.cin * L.cout;
     p.tag = tag;
-    if (m->use_tc) return launch_rowwgrad_tc(p, st, t->wg_partials, t->wg_partial_floats);
+    if (m->use_tc) return launch_rowwgrad_tc(p, st, t->wg_partials, t->wg_partial_floats, &t->rq);
     return launch_rowwgrad_simt(p, st);
 }
 
@@ -538,6 +538,7 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
     const Taps valid = conv3_taps(576, 24, false, +1), valid_T = conv3_taps(576, 24, false, -1);
     const Taps one = chunk_taps(32), wide = chunk_taps(EX);
 
+    t->rq.reset(t->wg_partial_floats);        // deferred partial reductions of this pass: one launch before wn_bwd
     PV_CUDA(cudaMemsetAsync(t->dweff, 0, m->nweff * sizeof(float), st));
     PV_CUDA(cudaMemsetAsync(t->dbias_s, 0, m->nbias_s * sizeof(float), st));
     PV_TRY(launch_tail_bwd_rows(g_sr, B, m->P, c.scale, c.std, P["g_G4"], g_geom(4), F, P["g_tail"], st));
@@ -546,7 +547,7 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
         const Layer &R1 = m->layers[m->li("residConv1")], &R2 = m->layers[m->li("residConv2")], &R3 = m->layers[m->li("residConv3")];
         PV_TRY(launch_skip2d_bwd(P["mn"], P["q1"], P["q2"], P["g_tail"], m->weff + R2.weff_off, m->weff + R3.weff_off, B, m->S,
                                  c.scale * c.scale, t->wg_partials, t->wg_partial_floats, t->dweff + R1.weff_off, t->dweff + R2.weff_off,
-                                 t->dweff + R3.weff_off, t->dbias_s + R1.bias_s_off, t->dbias_s + R2.bias_s_off, t->dbias_s + R3.bias_s_off, st));
+                                 t->dweff + R3.weff_off, t->dbias_s + R1.bias_s_off, t->dbias_s + R2.bias_s_off, t->dbias_s + R3.bias_s_off, st, &t->rq));
     } else {   // ---- 2-D skip path (dense kernels)
         const float* gout = P["g_tail"];
         for (int i = c.scale; i >= 1; --i) {
@@ -585,7 +586,7 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
             PV_TRY(launch_resfront_bwd_weight_tc(P[m->A(i, true)], P["g_D"], m->weffT + Le.weff_off, m->weff + Ld.weff_off,
                                                  m->bias_s + Le.bias_s_off, t->dweff + Ld.weff_off, t->dweff + Le.weff_off,
                                                  t->dbias_s + Le.bias_s_off, t->dbias_s + Ld.bias_s_off, pr, B, t->wg_partials,
-                                                 t->wg_partial_floats, 2.0 * fl, st));
+                                                 t->wg_partial_floats, 2.0 * fl, st, &t->rq));
             PV_TRY(launch_resfront_bwd_data_tc(P["g_D"], m->weff + Ld.weff_off, m->weff + Le.weff_off,
                                                reinterpret_cast<const uint32_t*>(P["M" + std::to_string(i)]), G,
                                                i == 0 ? P[m->A(0, true)] : nullptr, gin, pr, B, 1, fl, st));
@@ -599,7 +600,8 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
     }
     const Layer& L0 = m->layers[m->li("mainConv1")];
     PV_TRY(launch_first_conv_pr_wgrad(P["xn"], P["g_a0"], B, m->S, m->T, pr, t->dweff + L0.weff_off, t->dbias_s + L0.bias_s_off,
-                                      t->wg_partials, t->wg_partial_floats, st));
+                                      t->wg_partials, t->wg_partial_floats, st, &t->rq));
+    PV_TRY(launch_deferred_reduce(t->rq, st));
     PV_TRY(launch_wn_bwd(m->wn_tab, (int)m->layers.size(), m->wn_blocks, m->params, m->scale, t->dweff, t->dbias_s, t->grads, st));
     return 0;
 }

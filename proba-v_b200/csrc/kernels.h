@@ -76,6 +76,7 @@ int launch_sgd(float* p, const float* g, long long n, float lr, cudaStream_t st)
 int launch_scene_to_patches(const float* scenes, int ns, int T, int H, int W, int patch, int max_shift, float* patches, cudaStream_t st);
 int launch_stitch(const float* sr_patches, int ns, int n, int P, float* scenes, cudaStream_t st);
 
+struct ReduceQueue;   // wgrad_reduce.cuh
 // learned low-frequency skip path (modelsTF.py:45-53) fused: three 3x3 valid Conv2D 1 -> C (ReLU) -> C -> C, one CTA per patch (skip2d.cu)
 bool skip2d_supported(int S, int C);
 size_t skip2d_partial_floats(int B, int S, int C);
@@ -83,7 +84,7 @@ int launch_skip2d_fwd(const float* mn, const float* w1, const float* b1, const f
                       const float* b3, int B, int S, int C, float* q1, float* q2, float* q3, cudaStream_t st);
 int launch_skip2d_bwd(const float* mn, const float* q1, const float* q2, const float* g3, const float* w2, const float* w3,
                       int B, int S, int C, float* partials, size_t partial_floats, float* dw1, float* dw2, float* dw3,
-                      float* db1, float* db2, float* db3, cudaStream_t st);
+                      float* db1, float* db2, float* db3, cudaStream_t st, ReduceQueue* rq = nullptr);
 
 int launch_mean(const float* v, int n, float* out, cudaStream_t st);
 int shift_loss_device(int kind, const float* hr, const uint8_t* mask, const float* sr, int B, int H, int W,

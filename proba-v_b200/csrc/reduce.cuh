@@ -12,29 +12,30 @@ __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4
 
 // Sum over r < nrows of the float4 at src[rowoff(r) + col4*4 .. +3].  All NW*32 threads of the block must call; the result
 // is returned to the threads of warp 0 (threadIdx.x < 32, col4 = col4_base + threadIdx.x); `sm` is a [NW][32] float4
-// scratch.  Warp y owns rows y, y+NW, y+2NW, ...; with NW = 32 a 148-row reduction is at most five independent loads per
-// thread, all in flight at once (the 8-warp version spent ~5 dependent L2 round trips per launch, 15-25 us measured).
+// scratch.  Warp y owns rows y, y+NW, y+2NW, ...  and walks them in chunks of up to 20: all loads of a chunk are issued
+// before the first add, so a 148-row reduction by 8 warps is ONE memory round trip with 19 loads in flight per thread
+// (a 4-way unrolled loop spent five dependent round trips, 15-25 us per launch).
 template <int NW, typename RowOff>
 __device__ __forceinline__ float4 block_rowsum4(const float* __restrict__ src, int nrows, RowOff rowoff, int col4_base, bool col_ok, float4* sm) {
+    constexpr int CH = 20;
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (col_ok) {
         const size_t c = (size_t)(col4_base + x) * 4;
-        int r = y;
-        for (; r + 3 * NW < nrows; r += 4 * NW) {
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src + rowoff(r) + c));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(src + rowoff(r + NW) + c));
-            const float4 v2 = __ldg(reinterpret_cast<const float4*>(src + rowoff(r + 2 * NW) + c));
-            const float4 v3 = __ldg(reinterpret_cast<const float4*>(src + rowoff(r + 3 * NW) + c));
-            a0 = f4add(a0, v0); a1 = f4add(a1, v1); a2 = f4add(a2, v2); a3 = f4add(a3, v3);
+        for (int r0 = y; r0 < nrows; r0 += CH * NW) {
+            float4 v[CH];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int r = r0 + i * NW;
+                v[i] = r < nrows ? __ldg(reinterpret_cast<const float4*>(src + rowoff(r) + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float4 a0 = v[0], a1 = v[1], a2 = v[2], a3 = v[3];
+#pragma unroll
+            for (int i = 4; i < CH; i += 4) { a0 = f4add(a0, v[i]); a1 = f4add(a1, v[i + 1]); a2 = f4add(a2, v[i + 2]); a3 = f4add(a3, v[i + 3]); }
+            acc = f4add(acc, f4add(f4add(a0, a1), f4add(a2, a3)));
         }
-        float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0, t2 = t0;       // up to three leftover rows, loaded together
-        if (r < nrows) t0 = __ldg(reinterpret_cast<const float4*>(src + rowoff(r) + c));
-        if (r + NW < nrows) t1 = __ldg(reinterpret_cast<const float4*>(src + rowoff(r + NW) + c));
-        if (r + 2 * NW < nrows) t2 = __ldg(reinterpret_cast<const float4*>(src + rowoff(r + 2 * NW) + c));
-        a0 = f4add(a0, t0); a1 = f4add(a1, t1); a2 = f4add(a2, t2);
     }
-    sm[y * 32 + x] = f4add(f4add(a0, a1), f4add(a2, a3));
+    sm[y * 32 + x] = acc;
     __syncthreads();
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     if (y == 0) {

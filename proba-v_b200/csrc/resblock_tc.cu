@@ -12,10 +12,10 @@
 //
 // Layouts as in rows.h (PR rows, 32 channels, 128 B per row); weights are the effective (weight-normalised, tf32)
 // matrices prepared by wn_prep: weT_exp [256][32], weT_dec [32][256] (both K contiguous).
-#include "reduce.cuh"
 #include "rowio.cuh"
 #include "rows.h"
 #include "tc_common.cuh"
+#include "wgrad_reduce.cuh"
 
 namespace pv {
 
@@ -484,34 +484,13 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
     if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
-// dWd [256][32] (= dweff of decConv), dWe [32][256] (= dweff of expConv), dbe [256], dbd [32] from the per-CTA partials;
-// fixed-order block reduction (reduce.cuh).  Blocks [0,128): weight gradients; 128,129: dbe; 130: dbd.
-__global__ void __launch_bounds__(1024)
+// immediate (non-deferred) reduction of the per-CTA partials (wgrad_reduce.cuh has the body)
+__global__ void __launch_bounds__(256)
 resfront_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ dbp, int ncta,
                        float* __restrict__ dwd, float* __restrict__ dwe, float* __restrict__ dbe, float* __restrict__ dbd) {
-    __shared__ float4 sm[1024];
+    __shared__ float4 sm[256];
     tc::pdl_wait();
-    const int b = blockIdx.x, x = threadIdx.x & 31;
-    if (b < 128) {
-        const float4 s = block_rowsum4<32>(partials, ncta, [](int r) { return (size_t)r * 16384; }, b * 32, true, sm);
-        if (threadIdx.x >= 32) return;
-        const float v[4] = {s.x, s.y, s.z, s.w};
-        const int idx0 = (b * 32 + x) * 4;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int idx = idx0 + e;
-            const int g = idx / 4096, m = (idx / 32) % 128, n = idx % 32;
-            if (g < 2) dwd[(size_t)(g * 128 + m) * 32 + n] = v[e];                 // [ch][co]
-            else dwe[(size_t)n * 256 + (g - 2) * 128 + m] = v[e];                  // [ci][ch]
-        }
-    } else if (b < 130) {       // dbe: both epilogue groups of every CTA
-        const float4 s = block_rowsum4<32>(dbp, 2 * ncta, [](int r) { return (size_t)(r >> 1) * 768 + (r & 1) * 256; }, (b - 128) * 32, true, sm);
-        if (threadIdx.x < 32) { float* o = dbe + ((b - 128) * 32 + x) * 4; o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w; }
-    } else {                    // dbd: eight epilogue warps of every CTA
-        const bool ok = x < 8;
-        const float4 s = block_rowsum4<32>(dbp, 8 * ncta, [](int r) { return (size_t)(r >> 3) * 768 + 512 + (r & 7) * 32; }, 0, ok, sm);
-        if (threadIdx.x < 32 && ok) { float* o = dbd + x * 4; o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w; }
-    }
+    resfront_reduce_body(blockIdx.x, partials, dbp, ncta, dwd, dwe, dbe, dbd, sm);
 }
 
 template <int MODE>
@@ -565,7 +544,7 @@ namespace pv {
 // weight / bias gradients of expConv and decConv of one block, E and gZ recomputed on chip
 int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* weT_exp, const float* w_dec, const float* bias_e,
                                   float* dw_dec, float* dw_exp, float* db_exp, float* db_dec, const RowGeom& g, int B,
-                                  float* partials, size_t partial_floats, double flops, cudaStream_t st) {
+                                  float* partials, size_t partial_floats, double flops, cudaStream_t st, ReduceQueue* rq) {
     ResBwdWeightArgs a;
     memset(&a, 0, sizeof a);
     a.B = B; a.tiles_per_patch = cdiv(g.nrows, 128); a.g = g; a.bias_e = bias_e;
@@ -575,6 +554,8 @@ int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* 
     const int ntiles = a.B * a.tiles_per_patch;
     const int grid = ntiles < sms ? ntiles : sms;
     const size_t need = (size_t)grid * (4 * 4096 + 768);
+    float* deferred = rq ? rq->take(need) : nullptr;
+    if (deferred) { partials = deferred; partial_floats = need; }
     if (!partials || partial_floats < need) return set_error(PV_ERR_BAD_ARG, "resfront_bwd_weight: partial buffer too small");
     a.partials = partials; a.db_partials = partials + (size_t)grid * 4 * 4096;
     const long long rows = g.lead + (long long)B * g.pstride + ROW_TAIL;
@@ -593,9 +574,15 @@ int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* 
         PV_CUDA(launch_pdl(resfront_bwd_weight_kernel, grid, RP_THREADS, smem, st, tm_x, tm_gd, tm_x32, tm_gd32, tm_weT, tm_wd, a));
         PV_LAUNCH_CHECK();
     }
-    {
+    if (deferred) {
+        ReduceJob j;
+        memset(&j, 0, sizeof j);
+        j.kind = 1; j.nblocks = RESFRONT_REDUCE_BLOCKS; j.partials = a.partials; j.dbp = a.db_partials; j.ncta = grid;
+        j.dwd = dw_dec; j.dwe = dw_exp; j.dbe = db_exp; j.dbd = db_dec;
+        rq->push(j);
+    } else {
         PV_TIMED("wgrad_reduce", st);
-        PV_CUDA(launch_pdl(resfront_reduce_kernel, 131, 1024, 0, st, (const float*)a.partials, (const float*)a.db_partials, grid, dw_dec, dw_exp, db_exp, db_dec));
+        PV_CUDA(launch_pdl(resfront_reduce_kernel, RESFRONT_REDUCE_BLOCKS, 256, 0, st, (const float*)a.partials, (const float*)a.db_partials, grid, dw_dec, dw_exp, db_exp, db_dec));
         PV_LAUNCH_CHECK();
     }
     return 0;

@@ -4,7 +4,7 @@
 // layers that are not tensor-core shaped (mainConv1, Cin = 1) and as the on-device cross-check of each tcgen05
 // kernel (pv_selftest), and (b) the layout glue between the PR trunk and the valid-conv tail.
 // Reference semantics: Keras Conv3D inside TFA WeightNormalization (modelsTF.py:191-197), tf.pad REFLECT (:157-158).
-#include "reduce.cuh"
+#include "wgrad_reduce.cuh"
 #include "rows.h"
 
 namespace pv {
@@ -281,14 +281,10 @@ __global__ void __launch_bounds__(256) first_conv_pr_wgrad_kernel(const float* _
     if (warp < 4) out[(warp + 24) * 32 + lane] = acc[3];
 }
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 first_conv_pr_wgrad_reduce_kernel(const float* __restrict__ partials, int ncta, float* __restrict__ dw, float* __restrict__ db) {
-    __shared__ float4 sm[1024];     // 7 blocks x 32 float4 columns = the 28 x 32 outputs (27 taps + bias); fixed order (reduce.cuh)
-    const float4 s = block_rowsum4<32>(partials, ncta, [](int r) { return (size_t)r * (28 * 32); }, blockIdx.x * 32, true, sm);
-    if (threadIdx.x >= 32) return;
-    const int i = (blockIdx.x * 32 + threadIdx.x) * 4;
-    float* o = i < 27 * 32 ? dw + i : db + (i - 27 * 32);
-    o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w;
+    __shared__ float4 sm[256];     // 7 blocks x 32 float4 columns = the 28 x 32 outputs (27 taps + bias); fixed order (wgrad_reduce.cuh)
+    first_conv_reduce_body(blockIdx.x, partials, ncta, dw, db, sm);
 }
 
 // ------------------------------------------------------------------------------------------ PR <-> G (reflect pad)
@@ -420,14 +416,23 @@ int launch_first_conv_pr(const float* xn, const float* w, const float* bias, int
 }
 
 int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, int T, RowGeom g, float* dw, float* db,
-                               float* partials, size_t partial_floats, cudaStream_t st) {
+                               float* partials, size_t partial_floats, cudaStream_t st, ReduceQueue* rq) {
     const int grid = 148 * 4;
+    float* deferred = rq ? rq->take((size_t)grid * 28 * 32) : nullptr;
+    if (deferred) { partials = deferred; partial_floats = (size_t)grid * 28 * 32; }
     if (!partials || partial_floats < (size_t)grid * 28 * 32) return set_error(PV_ERR_BAD_ARG, "first_conv_pr_wgrad: partial buffer too small");
     PV_TIMED("first_conv_pr_wgrad", st, 2.0 * B * T * S * S * 27 * 32, 0.0);
     first_conv_pr_wgrad_kernel<<<grid, 256, 0, st>>>(xn, gz, B, S, T, g, partials);
     PV_LAUNCH_CHECK();
-    first_conv_pr_wgrad_reduce_kernel<<<7, 1024, 0, st>>>(partials, grid, dw, db);
-    PV_LAUNCH_CHECK();
+    if (deferred) {
+        ReduceJob j;
+        memset(&j, 0, sizeof j);
+        j.kind = 2; j.nblocks = FIRST_CONV_REDUCE_BLOCKS; j.partials = partials; j.ncta = grid; j.sc.dw = dw; j.sc.db = db;
+        rq->push(j);
+    } else {
+        first_conv_pr_wgrad_reduce_kernel<<<FIRST_CONV_REDUCE_BLOCKS, 256, 0, st>>>(partials, grid, dw, db);
+        PV_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -89,7 +89,8 @@ struct RowWgradP {
 int launch_rowconv_simt(const RowConvP& p, cudaStream_t st);
 int launch_rowwgrad_simt(const RowWgradP& p, cudaStream_t st);
 int launch_rowconv_tc(const RowConvP& p, cudaStream_t st);          // tcgen05 + TMA implicit GEMM (conv_tc.cu)
-int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, size_t partial_floats);
+struct ReduceQueue;   // wgrad_reduce.cuh: when given, the launcher defers its partial reduction to launch_deferred_reduce()
+int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, size_t partial_floats, ReduceQueue* rq = nullptr);
 // 3x3x3 lattice convolutions on 32-channel rows with the dw taps folded into N = 96 (conv3_tc.cu); launch_rowconv_tc
 // dispatches to it unless the environment variable PV_CONV3_N32 is set (A/B timing against the N = 32 formulation)
 bool rowconv3_tc_supported(const RowConvP& p);
@@ -104,13 +105,13 @@ int launch_resfront_bwd_data_tc(const float* gd, const float* w_dec, const float
                                 int B, int round_tf32, double flops, cudaStream_t st);
 int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* weT_exp, const float* w_dec, const float* bias_e,
                                   float* dw_dec, float* dw_exp, float* db_exp, float* db_dec, const RowGeom& g, int B,
-                                  float* partials, size_t partial_floats, double flops, cudaStream_t st);
+                                  float* partials, size_t partial_floats, double flops, cudaStream_t st, ReduceQueue* rq = nullptr);
 
 // mainConv1 (Cin = 1, 27 taps, ReLU) from the normalised dense LR [B,S,S,T] (h,w,t order) into the PR layout
 int launch_first_conv_pr(const float* xn, const float* w /*[27][32] taps in (dt,dh,dw) order*/, const float* bias, int B, int S, int T,
                          float* y, RowGeom g, cudaStream_t st);
 int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, int T, RowGeom g, float* dw, float* db,
-                               float* partials, size_t partial_floats, cudaStream_t st);
+                               float* partials, size_t partial_floats, cudaStream_t st, ReduceQueue* rq = nullptr);
 // PR block output -> G layout with the reducer's reflect padding (tf.pad REFLECT by 1 on H and W), and its adjoint
 int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st);
 int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st);

@@ -8,7 +8,7 @@
 // Layouts (dense engine conventions, kernels.h): activations [B, H, W, C] fp32; effective weights w[(tap*cin + ci)*C + co]
 // with tap = a*3 + b (TF order); partial vector = { dW1[9*C], dW2[9*C*C], dW3[9*C*C], db1[C], db2[C], db3[C] }.
 #include "kernels.h"
-#include "reduce.cuh"
+#include "wgrad_reduce.cuh"
 
 namespace pv {
 namespace {
@@ -22,7 +22,7 @@ struct Skip2dShape {
     __host__ __device__ int s3() const { return S - 6; }
     __host__ __device__ int nw1() const { return 9 * C; }
     __host__ __device__ int nw2() const { return 9 * C * C; }
-    __host__ __device__ int npart() const { return ((nw1() + 2 * nw2() + 3 * C + 3) / 4) * 4; }
+    __host__ __device__ int npart() const { return skip2d_npart(C); }
 };
 
 // out[p][co] = act(b[co] + sum_{tap,ci} in[p + tap][ci] * w[tap][ci][co]) over a So x So output from an (So+2)^2 input
@@ -183,27 +183,10 @@ skip2d_bwd_kernel(const float* __restrict__ mn, const float* __restrict__ q1, co
 }
 
 __global__ void __launch_bounds__(256)
-skip2d_reduce_kernel(const float* __restrict__ partials, int B, Skip2dShape sh, float* __restrict__ dw1, float* __restrict__ dw2,
+skip2d_reduce_kernel(const float* __restrict__ partials, int B, int C, float* __restrict__ dw1, float* __restrict__ dw2,
                      float* __restrict__ dw3, float* __restrict__ db1, float* __restrict__ db2, float* __restrict__ db3) {
     __shared__ float4 smr[256];
-    const int np = sh.npart();
-    const bool ok = (int)(blockIdx.x * 32 + (threadIdx.x & 31)) * 4 < np;
-    const float4 s = block_rowsum4<8>(partials, B, [np](int r) { return (size_t)r * np; }, blockIdx.x * 32, ok, smr);
-    if (threadIdx.x >= 32 || !ok) return;
-    const float v[4] = {s.x, s.y, s.z, s.w};
-    const int n1 = sh.nw1(), n2 = sh.nw2(), C = sh.C;
-    for (int e = 0; e < 4; ++e) {
-        int i = (blockIdx.x * 32 + threadIdx.x) * 4 + e;
-        if (i < n1) { dw1[i] = v[e]; continue; }
-        i -= n1;
-        if (i < n2) { dw2[i] = v[e]; continue; }
-        i -= n2;
-        if (i < n2) { dw3[i] = v[e]; continue; }
-        i -= n2;
-        if (i < C) db1[i] = v[e];
-        else if (i < 2 * C) db2[i - C] = v[e];
-        else if (i < 3 * C) db3[i - 2 * C] = v[e];
-    }
+    skip2d_reduce_body(blockIdx.x, partials, B, C, dw1, dw2, dw3, db1, db2, db3, smr);
 }
 
 }  // namespace
@@ -227,8 +210,10 @@ size_t skip2d_partial_floats(int B, int S, int C) { return (size_t)B * Skip2dSha
 
 int launch_skip2d_bwd(const float* mn, const float* q1, const float* q2, const float* g3, const float* w2, const float* w3,
                       int B, int S, int C, float* partials, size_t partial_floats, float* dw1, float* dw2, float* dw3,
-                      float* db1, float* db2, float* db3, cudaStream_t st) {
+                      float* db1, float* db2, float* db3, cudaStream_t st, ReduceQueue* rq) {
     Skip2dShape sh{S, C};
+    float* deferred = rq ? rq->take(skip2d_partial_floats(B, S, C)) : nullptr;
+    if (deferred) { partials = deferred; partial_floats = skip2d_partial_floats(B, S, C); }
     if (!partials || partial_floats < skip2d_partial_floats(B, S, C)) return set_error(PV_ERR_BAD_ARG, "skip2d_bwd: partial buffer too small");
     const size_t smem = sizeof(float) * ((size_t)S * S + (size_t)(2 * sh.s1() * sh.s1() + 2 * sh.s2() * sh.s2() + sh.s3() * sh.s3()) * C + 2 * sh.nw2());
     static size_t attr = 0;
@@ -238,9 +223,15 @@ int launch_skip2d_bwd(const float* mn, const float* q1, const float* q2, const f
         skip2d_bwd_kernel<<<B, SK_THREADS, smem, st>>>(mn, q1, q2, g3, w2, w3, sh, partials);
         PV_LAUNCH_CHECK();
     }
-    {
+    if (deferred) {
+        ReduceJob j;
+        memset(&j, 0, sizeof j);
+        j.kind = 3; j.nblocks = skip2d_reduce_blocks(C); j.partials = partials; j.ncta = B; j.C = C; j.S = S;
+        j.o0 = dw1; j.o1 = dw2; j.o2 = dw3; j.o3 = db1; j.o4 = db2; j.o5 = db3;
+        rq->push(j);
+    } else {
         PV_TIMED("wgrad_reduce", st);
-        skip2d_reduce_kernel<<<cdiv(sh.npart(), 128), 256, 0, st>>>(partials, B, sh, dw1, dw2, dw3, db1, db2, db3);
+        skip2d_reduce_kernel<<<skip2d_reduce_blocks(C), 256, 0, st>>>(partials, B, C, dw1, dw2, dw3, db1, db2, db3);
         PV_LAUNCH_CHECK();
     }
     return 0;

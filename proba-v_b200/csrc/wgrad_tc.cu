@@ -20,9 +20,9 @@
 // Every CTA owns a contiguous range of row tiles and keeps its accumulators in TMEM for its whole lifetime; partial
 // sums go to a [cta][group][128][32] scratch and a second small kernel reduces them in a fixed order (deterministic,
 // no atomics).  The epilogue warps meanwhile form the bias gradient from the gz tiles already sitting in shared memory.
-#include "reduce.cuh"
 #include "rows.h"
 #include "tc_common.cuh"
+#include "wgrad_reduce.cuh"
 
 namespace pv {
 
@@ -183,49 +183,18 @@ rowwgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
-// fixed-order reduction of the per-CTA partials into dweff / dbias (reduce.cuh).  mode 0: conv3 (group = (dt,dh),
-// m = q*32+ci, n = co); mode 1: wide x (group g, m = channel in group -> K index g*128+m, n = co); mode 2: wide gz
-// (m = co in group, n = ci).  Blocks [0, total/128) own 128 weight-gradient outputs each, the remaining blocks the bias sums.
-__global__ void __launch_bounds__(1024)
+// immediate (non-deferred) reduction: one launch right after the producer (wgrad_reduce.cuh has the body)
+__global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partials, const float* __restrict__ dbp, int ncta, int ngroup, int mode,
-                    RowWgradP p, int nbias) {
-    __shared__ float4 sm[1024];
+                    const __grid_constant__ WgradScatter sc, int nbias) {
+    __shared__ float4 sm[256];
     tc::pdl_wait();
-    const int total = ngroup * 4096;
-    const int nmain = total / 128;
-    if ((int)blockIdx.x < nmain) {
-        const float4 s = block_rowsum4<32>(partials, ncta, [total](int r) { return (size_t)r * total; }, blockIdx.x * 32, true, sm);
-        if (threadIdx.x >= 32) return;
-        const float v[4] = {s.x, s.y, s.z, s.w};
-        const int idx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int idx = idx0 + e;
-            const int g = idx / 4096, m = (idx / 32) % 128, n = idx % 32;
-            if (mode == 0) {
-                const int qd = m / 32, ci = m % 32;
-                if (qd < 3) { const int tap = g * 3 + qd; p.dw[(size_t)(p.dwr0[tap] + ci) * p.dw_cols + p.dwc0[tap] + n] = v[e]; }
-            } else if (mode == 1) {
-                const int k = g * 128 + m, tap = k / 32;
-                p.dw[(size_t)(p.dwr0[tap] + k % 32) * p.dw_cols + p.dwc0[tap] + n] = v[e];
-            } else {
-                p.dw[(size_t)(p.dwr0[0] + n) * p.dw_cols + p.dwc0[0] + g * 128 + m] = v[e];
-            }
-        }
-    } else {
-        const int bb = blockIdx.x - nmain, w = nbias * 32;
-        const bool ok = (bb * 32 + (int)(threadIdx.x & 31)) * 4 < w;
-        const float4 s = block_rowsum4<32>(dbp, ncta * 4, [w](int r) { return (size_t)r * w; }, bb * 32, ok, sm);
-        if (threadIdx.x < 32 && ok && p.db) {
-            float* o = p.db + (bb * 32 + threadIdx.x) * 4;
-            o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w;
-        }
-    }
+    wgrad_reduce_body(blockIdx.x, partials, dbp, ncta, ngroup, mode, sc, nbias, sm);
 }
 
 }  // namespace
 
-int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, size_t partial_floats) {
+int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, size_t partial_floats, ReduceQueue* rq) {
     int mode;
     if (p.xc == 32 && p.n == 32 && p.ntap == 27) mode = 0;
     else if (p.xc == 256 && p.n == 32 && p.ntap == 8) mode = 1;
@@ -282,6 +251,8 @@ int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, siz
     const int ntiles = a.B * a.tiles_per_patch;
     const int grid = ntiles < sms ? ntiles : sms;
     const size_t need = (size_t)grid * a.ngroup * 4096 + (size_t)grid * 4 * a.nbias * 32;
+    float* deferred = rq ? rq->take(need) : nullptr;       // deferred reduction: a private region of the trainer's arena
+    if (deferred) { partials = deferred; partial_floats = need; }
     if (!partials || partial_floats < need) return set_error(PV_ERR_BAD_ARG, "rowwgrad_tc: partial buffer too small (%zu < %zu)", partial_floats, need);
     a.partials = partials; a.db_partials = partials + (size_t)grid * a.ngroup * 4096;
     const long long a_rows = a.a_lead + (long long)p.B * a.a_pstride + ROW_TAIL, b_rows = a.b_lead + (long long)p.B * a.b_pstride + ROW_TAIL;
@@ -295,9 +266,18 @@ int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, siz
         PV_CUDA(launch_pdl(rowwgrad_tc_kernel<0>, grid, WG_THREADS, smem, st, tm_a, tm_b, a));
         PV_LAUNCH_CHECK();
     }
-    {
+    WgradScatter sc;
+    sc.dw = p.dw; sc.dw_cols = p.dw_cols; sc.db = p.db;
+    for (int i = 0; i < MAX_TAPS; ++i) { sc.dwr0[i] = p.dwr0[i]; sc.dwc0[i] = p.dwc0[i]; }
+    if (deferred) {
+        ReduceJob j;
+        memset(&j, 0, sizeof j);
+        j.kind = 0; j.nblocks = wgrad_reduce_blocks(a.ngroup, a.nbias); j.partials = a.partials; j.dbp = a.db_partials; j.ncta = grid;
+        j.ngroup = a.ngroup; j.mode = mode; j.nbias = a.nbias; j.sc = sc;
+        rq->push(j);
+    } else {
         PV_TIMED("wgrad_reduce", st);
-        PV_CUDA(launch_pdl(wgrad_reduce_kernel, a.ngroup * 32 + cdiv(a.nbias * 8, 32), 1024, 0, st, a.partials, a.db_partials, grid, a.ngroup, mode, p, a.nbias));
+        PV_CUDA(launch_pdl(wgrad_reduce_kernel, wgrad_reduce_blocks(a.ngroup, a.nbias), 256, 0, st, (const float*)a.partials, (const float*)a.db_partials, grid, a.ngroup, mode, sc, a.nbias));
         PV_LAUNCH_CHECK();
     }
     return 0;
