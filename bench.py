@@ -48,6 +48,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None                 # the timed region (host clock); samples are time-stamped as they are read
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def __enter__(self):
         try:
@@ -62,7 +69,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc:
@@ -76,7 +83,8 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.03)]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -174,18 +182,27 @@ def run_b200(args, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
-    # ---- device-resident timing
-    for _ in range(args.warmup):
-        trainer.trainStep(d_lr, d_hr, d_mk, sync=False)
-    barrier()
-    n0 = lib.pv_launch_count()
+    # ---- device-resident timing (the clock sampler is started before the warm-up so that nvidia-smi is already
+    # streaming when the timed region begins; only samples stamped inside the region are reported)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
+        t_up = time.time()
+        for _ in range(args.warmup):
+            trainer.trainStep(d_lr, d_hr, d_mk, sync=False)
+        barrier()
+        while not clk.rows and time.time() - t_up < 3.0:      # first nvidia-smi sample can take a few hundred ms
+            time.sleep(0.01)                                  # (no GPU work here: ranks must stay in lock-step for the all-reduce)
+        for _ in range(2):                                    # back to steady state after the wait
+            trainer.trainStep(d_lr, d_hr, d_mk, sync=False)
+        barrier()
+        n0 = lib.pv_launch_count()
+        clk.mark_start()
         e0.record()
         for _ in range(args.steps):
             trainer.trainStep(d_lr, d_hr, d_mk, sync=False)
         e1.record()
         barrier()
+        clk.mark_end()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = int(lib.pv_launch_count() - n0)
     value = ws * B * args.steps / (ms * 1e-3)
