@@ -150,6 +150,15 @@ int  pv_eval_step_host(pv_trainer* t, const float* lr_host, const float* hr_host
 int  pv_train_forward_backward(pv_trainer* t, const float* lr_dev, const float* hr_dev, const uint8_t* mask_dev,
                                int B, float grad_scale, float* out_dev, void* stream);
 int  pv_trainer_grad_arena(pv_trainer* t, float** dev_ptr, int64_t* n);     /* same layout as the param arena */
+/* The same in two stages, so that the caller can all-reduce the first gradient bucket while the second half of the
+ * backward pass runs (TF's MirroredStrategy overlaps its per-variable all-reduces with backward the same way,
+ * debug/trainMultiGPU.py:65-68).  stage 0: forward, loss, backward of the tail / reducers / last R/2 blocks;
+ * stage 1: the remaining blocks and mainConv1 (lr/hr/mask/out are ignored).  On return [*grad_lo, *grad_hi) is the
+ * contiguous range of the gradient arena that is final (in stream order).  Gradients are bit-identical to the
+ * unstaged call. */
+int  pv_train_forward_backward_staged(pv_trainer* t, const float* lr_dev, const float* hr_dev, const uint8_t* mask_dev,
+                                      int B, float grad_scale, float* out_dev, int stage, int64_t* grad_lo,
+                                      int64_t* grad_hi, void* stream);
 int  pv_apply_gradients(pv_trainer* t, void* stream);
 /* optimizer state for tf.train.Checkpoint parity (trainClass.py:33-39): iter, momentum_cache, m, v */
 int  pv_trainer_get_state(pv_trainer* t, int64_t* iter, double* momentum_cache, float* m_host, float* v_host, int64_t n);

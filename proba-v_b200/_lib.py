@@ -58,6 +58,8 @@ _SIGS = {
     "pv_eval_step": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, _P]),
     "pv_eval_step_host": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
     "pv_train_forward_backward": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_float, _P, _P]),
+    "pv_train_forward_backward_staged": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_float, _P, C.c_int, C.POINTER(C.c_int64),
+                                                   C.POINTER(C.c_int64), _P]),
     "pv_trainer_grad_arena": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "pv_apply_gradients": (C.c_int, [_P, _P]),
     "pv_trainer_get_state": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_double), _P, _P, C.c_int64]),

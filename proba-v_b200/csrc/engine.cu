@@ -305,9 +305,10 @@ static int model_forward(pv_model* m, const float* lr, int B, float* sr, bool tr
 }
 
 // tape.gradient(loss, trainable_variables): trainClass.py:131.  g_sr = dL/dSR [B, sP, sP].
-static int model_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
+static int model_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int stage = -1) {
     pv_model* m = t->m;
-    if (m->rows) return tc_backward(t, g_sr, B, st);
+    if (m->rows) return tc_backward(t, g_sr, B, st, stage);
+    if (stage == 1) return 0;                  // dense engine: one bucket, everything is final after stage 0
     Pool& P = m->pool_train;
     const pv_cfg& c = m->cfg;
     PV_CUDA(cudaMemsetAsync(t->dweff, 0, m->nweff * sizeof(float), st));
@@ -389,7 +390,7 @@ static int trainer_ensure(pv_trainer* t, int B) {
 
 // fwd -> loss (+ cPSNR metric in the same pass) [-> grads]
 static int trainer_fwd_loss(pv_trainer* t, const float* lr, const float* hr, const uint8_t* mask, int B, float grad_scale,
-                            bool backward, float* out_dev, cudaStream_t st) {
+                            bool backward, float* out_dev, cudaStream_t st, int stage = -1) {
     if (!lr || !hr || !mask || !out_dev || B <= 0) return set_error(PV_ERR_BAD_ARG, "step: null buffer or B=%d", B);
     pv_model* m = t->m;
     PV_TRY(trainer_ensure(t, B));
@@ -398,7 +399,7 @@ static int trainer_fwd_loss(pv_trainer* t, const float* lr, const float* hr, con
     PV_TRY(shift_loss_device(t->loss_kind, hr, mask, t->sr, B, HW, HW, 3, grad_scale, t->loss_ps, t->best, t->cnt,
                              t->cpsnr_ps, out_dev, backward ? t->dsr : nullptr, nullptr, st));
     PV_TRY(launch_mean(t->cpsnr_ps, B, out_dev + 1, st));
-    if (backward) PV_TRY(model_backward(t, t->dsr, B, st));
+    if (backward) PV_TRY(model_backward(t, t->dsr, B, st, stage));
     return 0;
 }
 
@@ -529,11 +530,13 @@ int pv_model_create(const pv_cfg* cfg, int device, pv_model** out) {
         w.weff_off = L.weff_off; w.weffT_off = L.weff_off; w.bias_s_off = L.bias_s_off; w.scale_off = L.scale_off;
         w.taps = L.taps(); w.cin = L.cin; w.cout = L.cout; w.cin_s = L.cin_s; w.cout_s = L.cout_s;
         w.first_block = blocks;
+        m->wn_first.push_back(blocks);
         w.mode = L.wn_mode;
         w.round_tf32 = (m->use_tc && L.wn_mode == 1 && L.cin > 1) ? 1 : 0;
         blocks += L.cout;
     }
     m->wn_blocks = blocks;
+    m->wn_first.push_back(blocks);
     if (cudaMalloc(&m->wn_tab, tab.size() * sizeof(WnLayer)) != cudaSuccess ||
         cudaMemcpy(m->wn_tab, tab.data(), tab.size() * sizeof(WnLayer), cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(set_error(PV_ERR_CUDA, "weight-norm table upload failed"));
@@ -785,6 +788,25 @@ int pv_train_forward_backward(pv_trainer* t, const float* lr, const float* hr, c
                               float* out_dev, void* stream) {
     if (!t) return set_error(PV_ERR_BAD_ARG, "null trainer");
     return trainer_fwd_loss(t, lr, hr, mask, B, grad_scale, true, out_dev, S_(stream));
+}
+
+int pv_train_forward_backward_staged(pv_trainer* t, const float* lr, const float* hr, const uint8_t* mask, int B, float grad_scale,
+                                     float* out_dev, int stage, int64_t* grad_lo, int64_t* grad_hi, void* stream) {
+    if (!t || !grad_lo || !grad_hi) return set_error(PV_ERR_BAD_ARG, "pv_train_forward_backward_staged: null argument");
+    if (stage != 0 && stage != 1) return set_error(PV_ERR_BAD_ARG, "pv_train_forward_backward_staged: stage must be 0 or 1, got %d", stage);
+    pv_model* m = t->m;
+    // the parameter arena is laid out in layer order, so each bucket is one contiguous range of the gradient arena
+    const int split = m->rows ? pv::tc_bucket_split_layer(m) : 0;
+    const int64_t cut = split < (int)m->layers.size() ? m->layers[split].v_off : m->nparams;
+    if (stage == 0) {
+        PV_TRY(trainer_fwd_loss(t, lr, hr, mask, B, grad_scale, true, out_dev, S_(stream), 0));
+        *grad_lo = cut; *grad_hi = m->nparams;
+    } else {
+        PV_CUDA(cudaSetDevice(m->device));
+        PV_TRY(model_backward(t, t->dsr, B, S_(stream), 1));
+        *grad_lo = 0; *grad_hi = cut;
+    }
+    return 0;
 }
 
 int pv_apply_gradients(pv_trainer* t, void* stream) {

@@ -77,6 +77,7 @@ struct pv_model {
     float *params = nullptr, *weff = nullptr, *weffT = nullptr, *bias_s = nullptr, *scale = nullptr;
     WnLayer* wn_tab = nullptr;
     int wn_blocks = 0;
+    std::vector<int> wn_first;         // first wn block of layer i (prefix sum of cout), size layers + 1
     bool weff_dirty = true;
     Pool pool_infer, pool_train;
     bool rows = false;                 // row-layout engine (cfg.precision != 0), engine_tc.cu
@@ -118,7 +119,10 @@ namespace pv {
 // row-layout (tensor-core) engine, engine_tc.cu
 int tc_build_plan(pv_model* m);
 int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool train, int clip_round, cudaStream_t st);
-int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st);
+// stage -1: the whole backward pass; 0 / 1: its two gradient buckets (data-parallel overlap, pv_train_forward_backward_staged):
+// stage 0 = tail, skip path, reducers and residual blocks R-1 .. R/2; stage 1 = blocks R/2-1 .. 0 and mainConv1
+int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int stage = -1);
+int tc_bucket_split_layer(const pv_model* m);      // first layer (index) whose gradients are final after stage 0
 int refresh_weights(pv_model* m, cudaStream_t st);
 int tc_selftest(std::string& report);
 // dense-layout conv helpers of engine.cu (the 2-D low-frequency path uses them in both engines)

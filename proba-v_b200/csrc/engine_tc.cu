@@ -528,7 +528,9 @@ int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip
 }
 
 // ------------------------------------------------------------------------------------------ backward
-int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
+int tc_bucket_split_layer(const pv_model* m) { return m->li("expConv_" + std::to_string(m->R / 2)); }
+
+int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int stage) {
     pv_model* m = t->m;
     Pool& P = m->pool_train;
     const pv_cfg& c = m->cfg;
@@ -538,7 +540,16 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
     const Taps valid = conv3_taps(576, 24, false, +1), valid_T = conv3_taps(576, 24, false, -1);
     const Taps one = chunk_taps(32), wide = chunk_taps(EX);
 
-    t->rq.reset(t->wg_partial_floats);        // deferred partial reductions of this pass: one launch before wn_bwd
+    const int isplit = R / 2;                  // blocks R-1 .. isplit belong to bucket 0
+    const int lsplit = tc_bucket_split_layer(m), nlayers = (int)m->layers.size();
+    // finalises the gradients of layers [la, lb): pending partial reductions, then the weight-norm backward of that range
+    auto finish = [&](int la, int lb) -> int {
+        PV_TRY(launch_deferred_reduce(t->rq, st));
+        return launch_wn_bwd(m->wn_tab, nlayers, m->wn_first[lb] - m->wn_first[la], m->params, m->scale, t->dweff, t->dbias_s, t->grads, st,
+                             m->wn_first[la]);
+    };
+    if (stage != 1) {
+    t->rq.reset(t->wg_partial_floats);        // deferred partial reductions of this pass: one launch per bucket, before wn_bwd
     PV_CUDA(cudaMemsetAsync(t->dweff, 0, m->nweff * sizeof(float), st));
     PV_CUDA(cudaMemsetAsync(t->dbias_s, 0, m->nbias_s * sizeof(float), st));
     PV_TRY(launch_tail_bwd_rows(g_sr, B, m->P, c.scale, c.std, P["g_G4"], g_geom(4), F, P["g_tail"], st));
@@ -574,7 +585,9 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
         }
         PV_TRY(launch_pr_to_g_reflect_bwd(P["g_G0"], g_geom(0), P["g_a" + std::to_string(R & 1)], pr, B, F, st));
     }
-    for (int i = R - 1; i >= 0; --i) {          // ---- residual blocks, last to first
+    }   // stage != 1
+    const int i_hi = stage == 1 ? isplit - 1 : R - 1, i_lo = stage == 0 ? isplit : 0;
+    for (int i = i_hi; i >= i_lo; --i) {        // ---- residual blocks, last to first
         const int e = m->li("expConv_" + std::to_string(i));
         const Layer &Le = m->layers[e], &Ld = m->layers[e + 1], &Ln = m->layers[e + 2];
         const float* G = P["g_a" + std::to_string((i + 1) & 1)];
@@ -598,12 +611,11 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st) {
         // expConv data gradient + the skip connection; block 0 flows into mainConv1's ReLU
         PV_TRY(dgrad_rows(m, Le, one, EX / 32, P["g_E"], pr, gin, pr, G, i == 0 ? P[m->A(0, true)] : nullptr, B, "exp_dgrad", st));
     }
+    if (stage == 0) return finish(lsplit, nlayers);
     const Layer& L0 = m->layers[m->li("mainConv1")];
     PV_TRY(launch_first_conv_pr_wgrad(P["xn"], P["g_a0"], B, m->S, m->T, pr, t->dweff + L0.weff_off, t->dbias_s + L0.bias_s_off,
                                       t->wg_partials, t->wg_partial_floats, st, &t->rq));
-    PV_TRY(launch_deferred_reduce(t->rq, st));
-    PV_TRY(launch_wn_bwd(m->wn_tab, (int)m->layers.size(), m->wn_blocks, m->params, m->scale, t->dweff, t->dbias_s, t->grads, st));
-    return 0;
+    return finish(0, stage == 1 ? lsplit : nlayers);
 }
 
 }  // namespace pv

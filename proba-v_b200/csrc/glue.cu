@@ -169,10 +169,10 @@ __global__ void __launch_bounds__(128) wn_prep_kernel(const WnLayer* __restrict_
 __global__ void __launch_bounds__(128) wn_bwd_kernel(const WnLayer* __restrict__ tab, int nlayers,
                                                      const float* __restrict__ params, const float* __restrict__ scale,
                                                      const float* __restrict__ dweff, const float* __restrict__ dbias_s,
-                                                     float* __restrict__ grads) {
+                                                     float* __restrict__ grads, int block0) {
     __shared__ float red[4];
     int co;
-    const WnLayer L = find_layer(tab, nlayers, blockIdx.x, co);
+    const WnLayer L = find_layer(tab, nlayers, blockIdx.x + block0, co);
     const int K = L.taps * L.cin;
     const float* v = params + L.v_off;
     const float* dw = dweff + L.weff_off;
@@ -319,9 +319,10 @@ int launch_wn_prep(const WnLayer* tab, int nlayers, int nblocks, const float* pa
 }
 
 int launch_wn_bwd(const WnLayer* tab, int nlayers, int nblocks, const float* params, const float* scale,
-                  const float* dweff, const float* dbias_s, float* grads, cudaStream_t st) {
+                  const float* dweff, const float* dbias_s, float* grads, cudaStream_t st, int block0) {
+    if (nblocks <= 0) return 0;
     PV_TIMED("wn_bwd", st);
-    wn_bwd_kernel<<<nblocks, 128, 0, st>>>(tab, nlayers, params, scale, dweff, dbias_s, grads);
+    wn_bwd_kernel<<<nblocks, 128, 0, st>>>(tab, nlayers, params, scale, dweff, dbias_s, grads, block0);
     PV_LAUNCH_CHECK();
     return 0;
 }

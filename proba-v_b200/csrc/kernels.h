@@ -63,7 +63,7 @@ struct WnLayer {
 int launch_wn_prep(const WnLayer* table_dev, int nlayers, int nblocks, const float* params, float* weff, float* weffT,
                    float* bias_s, float* scale, cudaStream_t st);
 int launch_wn_bwd(const WnLayer* table_dev, int nlayers, int nblocks, const float* params, const float* scale,
-                  const float* dweff, const float* dbias_s, float* grads, cudaStream_t st);
+                  const float* dweff, const float* dbias_s, float* grads, cudaStream_t st, int block0 = 0);   // blocks [block0, block0 + nblocks): a layer sub-range
 int launch_g_from_v(const WnLayer* table_dev, int nlayers, int nblocks, float* params, cudaStream_t st);
 
 // optimizers over the flat arena (train.py:77-83)

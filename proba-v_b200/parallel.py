@@ -63,6 +63,16 @@ def allreduce_sum_(t):
     return t
 
 
+def allreduce_sum_async_(t):
+    """Asynchronous in-place SUM all-reduce of one gradient bucket; returns the work handle (None for world 1).  With
+    NCCL the collective is enqueued on NCCL's own stream behind the producer kernels of the current stream, so compute
+    launched afterwards overlaps it; wait() makes the current stream wait for it."""
+    _, ws = world()
+    if ws > 1:
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
+    return None
+
+
 def broadcast_(t, src: int = 0):
     _, ws = world()
     if ws > 1:

@@ -173,7 +173,9 @@ class ModelTrainer:
         return lossv, psnrv
 
     def _dp_step(self, patchLR, patchHR, maskHR, global_batch):
-        """fwd/bwd on the local shard -> ONE all-reduce(SUM) of the flat gradient arena -> identical update on every rank."""
+        """fwd/bwd on the local shard in two stages; the all-reduce(SUM) of the first gradient bucket (tail, reducers, last
+        R/2 blocks) runs on NCCL's stream while the second half of the backward pass computes; identical update on every
+        rank.  The two buckets are contiguous ranges of the flat gradient arena (never per-variable messages)."""
         import torch
         dev = patchLR.device if _buf.is_cuda_tensor(patchLR) else torch.device(f"cuda:{self._model.device}")
         B = int(patchLR.shape[0])
@@ -184,8 +186,17 @@ class ModelTrainer:
         m = _buf.dev_tensor(maskHR, torch.uint8, dev)
         out = torch.empty(2, dtype=torch.float32, device=dev)
         st = _buf.current_stream_ptr(dev)
-        check(lib().pv_train_forward_backward(self._h, _buf.ptr(x), _buf.ptr(y), _buf.ptr(m), B, parallel.grad_scale(gb), _buf.ptr(out), st))
-        parallel.allreduce_sum_(self.grad_view())
+        g = self.grad_view()
+        lo, hi = C.c_int64(), C.c_int64()
+        works = []
+        for stage in (0, 1):
+            check(lib().pv_train_forward_backward_staged(self._h, _buf.ptr(x), _buf.ptr(y), _buf.ptr(m), B, parallel.grad_scale(gb),
+                                                         _buf.ptr(out), stage, C.byref(lo), C.byref(hi), st))
+            if hi.value > lo.value:
+                works.append(parallel.allreduce_sum_async_(g[lo.value:hi.value]))
+        for w in works:
+            if w is not None:
+                w.wait()                      # stream-level wait: the optimizer kernel is ordered after both collectives
         check(lib().pv_apply_gradients(self._h, st))
         return out
 

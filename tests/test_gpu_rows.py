@@ -104,3 +104,45 @@ def test_train_step_tf32_tracks_oracle(small_cfg):
         lossv, psnrv = t.trainStep(lr, hr, mask)
         assert abs(lossv - float(loss)) < 2e-3 * abs(float(loss)), step
         assert abs(psnrv - float(cps.mean())) < 0.02, step
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp32_rows", "fp32"])
+def test_staged_backward_buckets_are_bit_identical(small_cfg, precision):
+    """pv_train_forward_backward_staged (two gradient buckets for the overlapped data-parallel all-reduce) must produce
+    exactly the gradients of the one-shot call, and its two ranges must tile the gradient arena."""
+    import ctypes as C
+    import probav_b200 as pb
+    from probav_b200 import _buf, _lib, synth
+    from probav_b200._lib import check
+    om, p = oracle_and_params(small_cfg, seed=40)
+    m = cuda_model(small_cfg, p, precision=precision)
+    t = _trainer(pb, m)
+    lr, hr, mask = synth.make_batch(4, seed=41, hr_zero_under_mask=True)
+    t.forward_backward(lr, hr, mask)
+    ref = t.grad_view().clone()
+    t.grad_view().zero_()
+    dev = torch.device(f"cuda:{m.device}")
+    x, y, k = torch.from_numpy(lr).to(dev), torch.from_numpy(hr).to(dev), torch.from_numpy(mask.astype(np.uint8)).to(dev)
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    lo, hi = C.c_int64(), C.c_int64()
+    ranges = []
+
+    def same(a, b):
+        if precision == "tf32":         # tensor-core engine: fixed-order reductions, bit-reproducible
+            assert torch.equal(a, b)
+        else:                           # CUDA-core twins accumulate weight gradients with atomics
+            assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-12
+
+    for stage in (0, 1):
+        check(_lib.lib().pv_train_forward_backward_staged(t._h, _buf.ptr(x), _buf.ptr(y), _buf.ptr(k), 4, 0.25, _buf.ptr(out), stage,
+                                                          C.byref(lo), C.byref(hi), _buf.current_stream_ptr(dev)))
+        ranges.append((lo.value, hi.value))
+        if stage == 0:      # the first bucket is final before the second stage runs
+            torch.cuda.synchronize()
+            same(t.grad_view()[lo.value:hi.value], ref[lo.value:hi.value])
+    torch.cuda.synchronize()
+    same(t.grad_view(), ref)
+    n = ref.numel()
+    assert ranges[0][1] == n and ranges[1][0] == 0 and ranges[1][1] == ranges[0][0]
+    if precision != "fp32":
+        assert 0 < ranges[0][0] < n       # the row engines really split the arena
