@@ -187,6 +187,11 @@ class ModelTrainer:
         out = torch.empty(2, dtype=torch.float32, device=dev)
         st = _buf.current_stream_ptr(dev)
         g = self.grad_view()
+        if os.environ.get("PV_DP_OVERLAP", "1") == "0":       # one all-reduce of the whole arena after backward (A/B measurements)
+            check(lib().pv_train_forward_backward(self._h, _buf.ptr(x), _buf.ptr(y), _buf.ptr(m), B, parallel.grad_scale(gb), _buf.ptr(out), st))
+            parallel.allreduce_sum_(g)
+            check(lib().pv_apply_gradients(self._h, st))
+            return out
         lo, hi = C.c_int64(), C.c_int64()
         works = []
         for stage in (0, 1):
