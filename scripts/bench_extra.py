@@ -34,7 +34,7 @@ for prec in ("tf32", "fp32"):
     m = pb.build_from_config(cfg, precision=prec)
     ns = 32
     lr, hrs, msk = synth.make_scene(ns, seed=3)
-    m.predict_from_scenes(lr[:4])
+    m.predict_from_scenes(lr)                 # warm-up at the full batch: the activation pools are sized on first use
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     reps = 3
