@@ -45,6 +45,9 @@ int64_t launch_count();
 // Launch with programmatic stream serialization (see tc_common.cuh pdl_wait / pdl_trigger).  PV_NO_PDL=1 falls back to a
 // plain launch (the griddepcontrol instructions are no-ops then).
 bool pdl_enabled();
+bool pdl_simple_enabled();     // PV_PDL_SIMPLE=1 also launches the small elementwise / reduction kernels with PDL.  Off by default:
+                               // measured 6.20 vs 6.12 ms per step (their early-launched blocks wait on SM resources the
+                               // persistent tensor-core kernels' tails could use)
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
@@ -53,6 +56,20 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// device side of launch_pdl for the simple (non tensor-core) kernels: first statement of the kernel.  They never trigger
+// their dependents explicitly (the implicit trigger at block exit comes after this wait, which keeps the chain transitive).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_grid_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_simple(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    if (pdl_simple_enabled()) return launch_pdl(kernel, grid, block, smem, st, static_cast<KArgs>(args)...);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -7,6 +7,7 @@ namespace pv {
 namespace {
 
 __global__ void __launch_bounds__(256) deferred_reduce_kernel(const __grid_constant__ ReduceJobs J) {
+    pdl_grid_wait();
     __shared__ float4 sm[256];
     int j = 0;
     while (j + 1 < J.njobs && (int)blockIdx.x >= J.block_start[j + 1]) ++j;
@@ -24,7 +25,7 @@ int launch_deferred_reduce(ReduceQueue& q, cudaStream_t st) {
     if (q.jobs.njobs == 0) return 0;
     const int blocks = q.jobs.block_start[q.jobs.njobs];
     PV_TIMED("wgrad_reduce", st);
-    deferred_reduce_kernel<<<blocks, 256, 0, st>>>(q.jobs);
+    PV_CUDA(launch_pdl_simple(deferred_reduce_kernel, blocks, 256, 0, st, q.jobs));
     PV_LAUNCH_CHECK();
     q.jobs.njobs = 0;
     return 0;

@@ -39,6 +39,7 @@ int set_error(int code, const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches += n; }
 int64_t launch_count() { return g_launches.load(); }
+bool pdl_simple_enabled() { static const bool on = [] { const char* e = getenv("PV_PDL_SIMPLE"); return e && e[0] == '1'; }(); return on; }
 bool pdl_enabled() { static const bool on = getenv("PV_NO_PDL") == nullptr; return on; }
 
 // ------------------------------------------------------------------------------------------ kernel timing

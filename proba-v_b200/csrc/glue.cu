@@ -13,6 +13,7 @@ namespace {
 // ------------------------------------------------------------------------------------------ prep
 __global__ void prep_kernel(const float* __restrict__ lr, long long nvox, int T, float mean, float inv_std,
                             float* __restrict__ xn, float* __restrict__ mn) {
+    pdl_grid_wait();
     const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, h, w)
     if (v >= nvox) return;
     const float* src = lr + v * T;
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(128) wn_prep_kernel(const WnLayer* __restrict_
                                                       const float* __restrict__ params, float* __restrict__ weff,
                                                       float* __restrict__ weffT, float* __restrict__ bias_s,
                                                       float* __restrict__ scale) {
+    pdl_grid_wait();
     __shared__ float red[4];
     int co;
     const WnLayer L = find_layer(tab, nlayers, blockIdx.x, co);
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(128) wn_bwd_kernel(const WnLayer* __restrict__
                                                      const float* __restrict__ params, const float* __restrict__ scale,
                                                      const float* __restrict__ dweff, const float* __restrict__ dbias_s,
                                                      float* __restrict__ grads, int block0) {
+    pdl_grid_wait();
     __shared__ float red[4];
     int co;
     const WnLayer L = find_layer(tab, nlayers, blockIdx.x + block0, co);
@@ -211,6 +214,7 @@ __global__ void __launch_bounds__(128) g_from_v_kernel(const WnLayer* __restrict
 // ------------------------------------------------------------------------------------------ optimizers
 __global__ void nadam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long long n, NadamScalars s) {
+    pdl_grid_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float gi = g[i];
@@ -270,7 +274,7 @@ __global__ void stitch_kernel(const float* __restrict__ sr, long long ntot, int 
 int launch_prep(const float* lr, int B, int HW, int T, float mean, float stdv, float* xn, float* mn, cudaStream_t st) {
     PV_TIMED("prep", st);
     const long long nvox = (long long)B * HW;
-    prep_kernel<<<cdiv(nvox, 256), 256, 0, st>>>(lr, nvox, T, mean, 1.0f / stdv, xn, mn);
+    PV_CUDA(launch_pdl_simple(prep_kernel, cdiv(nvox, 256), 256, 0, st, lr, nvox, T, mean, 1.0f / stdv, xn, mn));
     PV_LAUNCH_CHECK();
     return 0;
 }
@@ -313,7 +317,7 @@ int launch_tail_bwd(const float* dsr, int B, int P, int scale, float stdv, float
 int launch_wn_prep(const WnLayer* tab, int nlayers, int nblocks, const float* params, float* weff, float* weffT,
                    float* bias_s, float* scale, cudaStream_t st) {
     PV_TIMED("wn_prep", st);
-    wn_prep_kernel<<<nblocks, 128, 0, st>>>(tab, nlayers, params, weff, weffT, bias_s, scale);
+    PV_CUDA(launch_pdl_simple(wn_prep_kernel, nblocks, 128, 0, st, tab, nlayers, params, weff, weffT, bias_s, scale));
     PV_LAUNCH_CHECK();
     return 0;
 }
@@ -322,7 +326,7 @@ int launch_wn_bwd(const WnLayer* tab, int nlayers, int nblocks, const float* par
                   const float* dweff, const float* dbias_s, float* grads, cudaStream_t st, int block0) {
     if (nblocks <= 0) return 0;
     PV_TIMED("wn_bwd", st);
-    wn_bwd_kernel<<<nblocks, 128, 0, st>>>(tab, nlayers, params, scale, dweff, dbias_s, grads, block0);
+    PV_CUDA(launch_pdl_simple(wn_bwd_kernel, nblocks, 128, 0, st, tab, nlayers, params, scale, dweff, dbias_s, grads, block0));
     PV_LAUNCH_CHECK();
     return 0;
 }
@@ -336,7 +340,7 @@ int launch_g_from_v(const WnLayer* tab, int nlayers, int nblocks, float* params,
 
 int launch_nadam(float* p, const float* g, float* m, float* v, long long n, NadamScalars s, cudaStream_t st) {
     PV_TIMED("nadam", st);
-    nadam_kernel<<<cdiv(n, 256), 256, 0, st>>>(p, g, m, v, n, s);
+    PV_CUDA(launch_pdl_simple(nadam_kernel, cdiv(n, 256), 256, 0, st, p, g, m, v, n, s));
     PV_LAUNCH_CHECK();
     return 0;
 }

@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(256) rowwgrad_vec_kernel(RowWgradP p, int m_pe
 __global__ void __launch_bounds__(256) first_conv_pr_kernel(const float* __restrict__ xn, const float* __restrict__ w,
                                                             const float* __restrict__ bias, int B, int S, int T,
                                                             float* __restrict__ y, RowGeom g) {
+    pdl_grid_wait();
     extern __shared__ float fsm[];
     // blockIdx.y selects a chunk of temporal planes [tc0, tc0 + tcn) (one chunk per patch measured fastest at B = 128: 47 us vs 58 us for three)
     const int tchunk = (T + gridDim.y - 1) / gridDim.y, tc0 = blockIdx.y * tchunk, tcn = min(tchunk, T - tc0);
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(256) first_conv_pr_kernel(const float* __restr
 // outer-product sums with warp w owning taps {w, w+8, w+16, w+24} and lane = output channel.  Per-CTA partials, reduced below.
 __global__ void __launch_bounds__(256) first_conv_pr_wgrad_kernel(const float* __restrict__ xn, const float* __restrict__ gz,
                                                                   int B, int S, int T, RowGeom g, float* __restrict__ partials) {
+    pdl_grid_wait();
     __shared__ float xs[128][29];
     __shared__ __align__(16) float gs[128][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -319,6 +321,7 @@ __device__ __forceinline__ int refl(int i, int n) { return i < 0 ? -i : (i >= n 
 
 __global__ void pr_to_g_reflect_kernel(const float* __restrict__ a, RowGeom pr, float* __restrict__ g0, RowGeom gg,
                                        long long n, int C4) {
+    pdl_grid_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int c = (int)(i % C4); long long r = i / C4;
@@ -340,6 +343,7 @@ __device__ __forceinline__ int preimages(int i, int n, int p, int (&o)[3]) {
 
 __global__ void pr_to_g_reflect_bwd_kernel(const float* __restrict__ gg0, RowGeom gg, float* __restrict__ ga, RowGeom pr,
                                            long long n, int C4) {
+    pdl_grid_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int c = (int)(i % C4); long long r = i / C4;
@@ -362,6 +366,7 @@ __global__ void pr_to_g_reflect_bwd_kernel(const float* __restrict__ gg0, RowGeo
 // sr[b, s*h+i, s*w+j] = (U[row(b,0,h,w)][i*s+j] + resid[b,h,w,i*s+j]) * std + mean
 __global__ void tail_rows_kernel(const float* __restrict__ u, RowGeom g, int uc, const float* __restrict__ resid, long long n,
                                  int P, int s, float mean, float stdv, int clip_round, float* __restrict__ sr) {
+    pdl_grid_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int PS = P * s;
@@ -376,6 +381,7 @@ __global__ void tail_rows_kernel(const float* __restrict__ u, RowGeom g, int uc,
 
 __global__ void tail_bwd_rows_kernel(const float* __restrict__ dsr, long long n, int P, int s, float stdv,
                                      float* __restrict__ gu, RowGeom g, int uc, float* __restrict__ dtail) {
+    pdl_grid_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // index into [B,P,P,s*s]
     if (i >= n) return;
     const int c = (int)(i % (s * s)); long long r = i / (s * s);
@@ -393,7 +399,7 @@ int launch_tail_rows(const float* u, RowGeom g, int uc, const float* resid, int 
                      int clip_round, float* sr, cudaStream_t st) {
     const long long n = (long long)B * P * scale * P * scale;
     PV_TIMED("tail", st, 0.0, (double)n * 12.0);
-    tail_rows_kernel<<<cdiv(n, 256), 256, 0, st>>>(u, g, uc, resid, n, P, scale, mean, stdv, clip_round, sr);
+    PV_CUDA(launch_pdl_simple(tail_rows_kernel, cdiv(n, 256), 256, 0, st, u, g, uc, resid, n, P, scale, mean, stdv, clip_round, sr));
     PV_LAUNCH_CHECK();
     return 0;
 }
@@ -401,7 +407,7 @@ int launch_tail_rows(const float* u, RowGeom g, int uc, const float* resid, int 
 int launch_tail_bwd_rows(const float* dsr, int B, int P, int scale, float stdv, float* gu, RowGeom g, int uc, float* dtail, cudaStream_t st) {
     const long long n = (long long)B * P * P * scale * scale;
     PV_TIMED("tail_bwd", st, 0.0, (double)n * 12.0);
-    tail_bwd_rows_kernel<<<cdiv(n, 256), 256, 0, st>>>(dsr, n, P, scale, stdv, gu, g, uc, dtail);
+    PV_CUDA(launch_pdl_simple(tail_bwd_rows_kernel, cdiv(n, 256), 256, 0, st, dsr, n, P, scale, stdv, gu, g, uc, dtail));
     PV_LAUNCH_CHECK();
     return 0;
 }
@@ -440,7 +446,7 @@ int launch_first_conv_pr(const float* xn, const float* w, const float* bias, int
     static size_t attr = 0;
     if (smem > attr) { PV_CUDA(cudaFuncSetAttribute(first_conv_pr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
     PV_TIMED("first_conv_pr", st, 2.0 * B * T * S * S * 27 * 32, 0.0);
-    first_conv_pr_kernel<<<dim3(B, 1), 256, smem, st>>>(xn, w, bias, B, S, T, y, g);
+    PV_CUDA(launch_pdl_simple(first_conv_pr_kernel, dim3(B, 1), 256, smem, st, xn, w, bias, B, S, T, y, g));
     PV_LAUNCH_CHECK();
     return 0;
 }
@@ -452,7 +458,7 @@ int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, i
     if (deferred) { partials = deferred; partial_floats = (size_t)grid * 28 * 32; }
     if (!partials || partial_floats < (size_t)grid * 28 * 32) return set_error(PV_ERR_BAD_ARG, "first_conv_pr_wgrad: partial buffer too small");
     PV_TIMED("first_conv_pr_wgrad", st, 2.0 * B * T * S * S * 27 * 32, 0.0);
-    first_conv_pr_wgrad_kernel<<<grid, 256, 0, st>>>(xn, gz, B, S, T, g, partials);
+    PV_CUDA(launch_pdl_simple(first_conv_pr_wgrad_kernel, grid, 256, 0, st, xn, gz, B, S, T, g, partials));
     PV_LAUNCH_CHECK();
     if (deferred) {
         ReduceJob j;
@@ -469,7 +475,7 @@ int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, i
 int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st) {
     const long long n = (long long)B * gg.nt * gg.nh * gg.nw * (C / 4);
     PV_TIMED("pr_to_g_reflect", st);
-    pr_to_g_reflect_kernel<<<cdiv(n, 256), 256, 0, st>>>(a, pr, g0, gg, n, C / 4);
+    PV_CUDA(launch_pdl_simple(pr_to_g_reflect_kernel, cdiv(n, 256), 256, 0, st, a, pr, g0, gg, n, C / 4));
     PV_LAUNCH_CHECK();
     return 0;
 }
@@ -477,7 +483,7 @@ int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, in
 int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st) {
     const long long n = (long long)B * pr.nt * pr.nh * pr.nw * (C / 4);
     PV_TIMED("pr_to_g_reflect_bwd", st);
-    pr_to_g_reflect_bwd_kernel<<<cdiv(n, 256), 256, 0, st>>>(gg0, gg, ga, pr, n, C / 4);
+    PV_CUDA(launch_pdl_simple(pr_to_g_reflect_bwd_kernel, cdiv(n, 256), 256, 0, st, gg0, gg, ga, pr, n, C / 4));
     PV_LAUNCH_CHECK();
     return 0;
 }

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(SK_THREADS)
 skip2d_fwd_kernel(const float* __restrict__ mn, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                   const float* __restrict__ b2, const float* __restrict__ w3, const float* __restrict__ b3, Skip2dShape sh,
                   float* __restrict__ q1, float* __restrict__ q2, float* __restrict__ q3) {
+    pdl_grid_wait();
     extern __shared__ float sm[];
     const int S = sh.S, C = sh.C, n0 = S * S, n1 = sh.s1() * sh.s1() * C, n2 = sh.s2() * sh.s2() * C, n3 = sh.s3() * sh.s3() * C;
     float* x = sm; float* a1 = x + n0; float* a2 = a1 + n1; float* a3 = a2 + n2;
@@ -148,6 +149,7 @@ __device__ __forceinline__ void wgrad3x3(const float* __restrict__ in, int cin, 
 __global__ void __launch_bounds__(SK_THREADS)
 skip2d_bwd_kernel(const float* __restrict__ mn, const float* __restrict__ q1, const float* __restrict__ q2, const float* __restrict__ g3,
                   const float* __restrict__ w2, const float* __restrict__ w3, Skip2dShape sh, float* __restrict__ partials) {
+    pdl_grid_wait();
     extern __shared__ float sm[];
     const int S = sh.S, C = sh.C, n0 = S * S, n1 = sh.s1() * sh.s1() * C, n2 = sh.s2() * sh.s2() * C, n3 = sh.s3() * sh.s3() * C;
     float* x = sm; float* a1 = x + n0; float* a2 = a1 + n1; float* gg3 = a2 + n2;
@@ -201,7 +203,7 @@ int launch_skip2d_fwd(const float* mn, const float* w1, const float* b1, const f
     static size_t attr = 0;
     if (smem > attr) { PV_CUDA(cudaFuncSetAttribute(skip2d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
     PV_TIMED("skip2d_fwd", st, 2.0 * B * C * (9.0 * sh.s1() * sh.s1() + 9.0 * C * (sh.s2() * sh.s2() + sh.s3() * sh.s3())), 0.0);
-    skip2d_fwd_kernel<<<B, SK_THREADS, smem, st>>>(mn, w1, b1, w2, b2, w3, b3, sh, q1, q2, q3);
+    PV_CUDA(launch_pdl_simple(skip2d_fwd_kernel, B, SK_THREADS, smem, st, mn, w1, b1, w2, b2, w3, b3, sh, q1, q2, q3));
     PV_LAUNCH_CHECK();
     return 0;
 }
@@ -220,7 +222,7 @@ int launch_skip2d_bwd(const float* mn, const float* q1, const float* q2, const f
     if (smem > attr) { PV_CUDA(cudaFuncSetAttribute(skip2d_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
     {
         PV_TIMED("skip2d_bwd", st, 4.0 * B * C * (9.0 * sh.s1() * sh.s1() + 9.0 * C * (sh.s2() * sh.s2() + sh.s3() * sh.s3())), 0.0);
-        skip2d_bwd_kernel<<<B, SK_THREADS, smem, st>>>(mn, q1, q2, g3, w2, w3, sh, partials);
+        PV_CUDA(launch_pdl_simple(skip2d_bwd_kernel, B, SK_THREADS, smem, st, mn, q1, q2, g3, w2, w3, sh, partials));
         PV_LAUNCH_CHECK();
     }
     if (deferred) {
