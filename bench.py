@@ -267,13 +267,19 @@ def run_b200(args, cfg):
         roof_loss = {"kernel": "shift_loss_patch", "bound": "hbm", "achieved": a, "peak": peaks["hbm"], "unit": "GB/s",
                      "frac": a / peaks["hbm"], "traffic": None,
                      "note": f"batch {B}: {sl['bytes'] / sl['launches'] / 1e6:.2f} MB per launch is latency-bound; see bench_loss in DESIGN.md"}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
+    cfg_name = os.path.splitext(os.path.basename(args.cfg))[0]
+    is_headline = cfg_name == "p16t9c85r12"
+    workload = (f"cfg/{cfg_name} train step (fwd+shift-L1+bwd+Nadam+cPSNR metric)" + (", BASELINE configs[1]" if is_headline else
+                f", {cfg['num_low_res_imgs']} LR frames, {cfg['num_res_blocks']} blocks"))
+    # algorithmic flops per patch: SURVEY Appendix A for the headline graph, else the sum the kernels' launchers report
+    gflop_per_patch = TRAIN_GFLOP_PER_PATCH if is_headline else sum(v["flops"] for v in rep.values()) / 2 / B / 1e9
+    line = {"metric": METRIC if is_headline else METRIC.replace("p16t9c85r12", cfg_name), "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {0: "f32", 1: "tf32", 3: "f32"}[model.cfg.precision], "data": "synthetic",
-            "config": {"workload": "cfg/p16t9c85r12 train step (fwd+shift-L1+bwd+Nadam+cPSNR metric), BASELINE configs[1]",
+            "config": {"workload": workload,
                        "batch_per_gpu": B, "global_batch": B * ws, "parallelism": f"dp{ws}",
                        "l2_policy": "per-step working set (activations ~8 GB) >> 126 MB L2; no explicit flush",
-                       "algorithmic_tflops": value * TRAIN_GFLOP_PER_PATCH / 1e3},
+                       "algorithmic_tflops": value * gflop_per_patch / 1e3},
             "clocks": clk.summary(),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

@@ -122,9 +122,9 @@ static int build_plan(pv_model* m) {
         return set_error(PV_ERR_BAD_CONFIG, "precision=%d: 0 = fp32 (CUDA cores), 1 = tf32 (tcgen05 tensor cores), 3 = fp32 on the row layouts", c.precision);
     m->rows = c.precision != 0;
     m->use_tc = c.precision == 1;
-    if (m->rows && (c.num_low_res_imgs != 9 || c.num_filters != 32 || c.num_filters * c.exp_rate != 256 || c.scale != 3 ||
+    if (m->rows && ((c.num_low_res_imgs != 7 && c.num_low_res_imgs != 9 && c.num_low_res_imgs != 13) || c.num_filters != 32 || c.num_filters * c.exp_rate != 256 || c.scale != 3 ||
                     c.patch_size != 16 || c.max_shift != 6 || (int)(c.num_filters * c.decay_rate) > 32))
-        return set_error(PV_ERR_BAD_CONFIG, "the tensor-core engine is built for the p16t9 family (T=9, 32 filters, exp_rate 8, scale 3, "
+        return set_error(PV_ERR_BAD_CONFIG, "the tensor-core engine is built for the p16 family (T in {7, 9, 13}, 32 filters, exp_rate 8, scale 3, "
                                             "patch 16, max_shift 6); use precision fp32 for other graphs");
     m->S = c.patch_size + c.max_shift;            // modelsTF.py:19
     m->T = c.num_low_res_imgs; m->P = c.patch_size; m->F = c.num_filters; m->R = c.num_res_blocks;

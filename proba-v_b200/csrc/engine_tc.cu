@@ -17,19 +17,55 @@ namespace {
 
 struct Taps { int n; int off[MAX_TAPS]; int c0[MAX_TAPS]; int chunk[MAX_TAPS]; };
 
-RowGeom pr_geom() {
+// PR layout of a 22 x 22 x T trunk activation (T = num_low_res_imgs: 7, 9 or 13 on this engine)
+RowGeom pr_geom(int T = 9) {
     RowGeom g;
-    g.lead = 640; g.pstride = 10 * 529; g.plane = 529; g.pw = 23; g.t0 = 0; g.nt = 9; g.nh = 22; g.nw = 22;
-    g.row0 = 0; g.nrows = 9 * 529;
+    g.lead = 640; g.pstride = (long long)(T + 1) * 529; g.plane = 529; g.pw = 23; g.t0 = 0; g.nt = T; g.nh = 22; g.nw = 22;
+    g.row0 = 0; g.nrows = T * 529;
     return g;
 }
-// G layout of the tensor after k valid 3x3x3 convolutions of the reflect-padded 24x24x9 block output
-RowGeom g_geom(int k) {
+// G layout of a tensor whose valid extent is nt planes of nh x nw (inside planes of 24 x 24, two leading zero planes)
+RowGeom g_dims(int nt, int nh, int nw) {
     RowGeom g;
-    const int T = 9 - 2 * k;
-    g.lead = 1280; g.pstride = (long long)(T + 2) * 576; g.plane = 576; g.pw = 24; g.t0 = 2;
-    g.nt = T; g.nh = 24 - 2 * k; g.nw = 24 - 2 * k; g.row0 = 2 * 576; g.nrows = T * 576;
+    g.lead = 1280; g.pstride = (long long)(nt + 2) * 576; g.plane = 576; g.pw = 24; g.t0 = 2;
+    g.nt = nt; g.nh = nh; g.nw = nw; g.row0 = 2 * 576; g.nrows = nt * 576;
     return g;
+}
+// ... after k valid 3x3x3 convolutions of the reflect-padded 24x24x9 block output (the T = 9 tail; used by the self-test)
+RowGeom g_geom(int k) { return g_dims(9 - 2 * k, 24 - 2 * k, 24 - 2 * k); }
+
+// The reducer tail on G buffers (modelsTF.py:62-69: ConvReduceAndUpscale for T = 9, v2 for T = 7, v3 for T = 13): reducer i
+// reads "Gi<i>" -- the reflect-padded (by pad_i on H and W) copy of its predecessor's output, or that output itself when
+// pad_i = 0 -- and writes "Go<i>"; the upscale conv reads the last "Go" and writes "U".
+struct TailStep { std::string in, out; RowGeom ig, og; int pad; bool copy; };
+std::vector<TailStep> tail_plan(const pv_model* m) {
+    std::vector<TailStep> v;
+    int nt = m->T, nh = m->S, nw = m->S;
+    for (int i = 0; i < m->nred; ++i) {
+        TailStep s;
+        s.pad = m->red_pad[3 * i];
+        s.copy = i == 0 || s.pad > 0;                       // the first reducer always needs the PR -> G re-layout
+        nh += 2 * s.pad; nw += 2 * s.pad;
+        s.in = s.copy ? "Gi" + std::to_string(i + 1) : v.back().out;
+        s.ig = g_dims(nt, nh, nw);
+        nt -= 2; nh -= 2; nw -= 2;
+        s.out = "Go" + std::to_string(i + 1);
+        s.og = g_dims(nt, nh, nw);
+        v.push_back(s);
+    }
+    return v;
+}
+bool tail_plan_supported(const pv_model* m) {
+    if (m->nred < 1) return false;
+    int nt = m->T, nh = m->S;
+    for (int i = 0; i < m->nred; ++i) {
+        const int ph = m->red_pad[3 * i], pw = m->red_pad[3 * i + 1], pt = m->red_pad[3 * i + 2];
+        if (ph != pw || ph > 1 || pt != 0) return false;   // T = 19 pads T and uses a 5x5x5 reducer: dense engine only
+        nh += 2 * ph;
+        if (nh > 24) return false;
+        nt -= 2; nh -= 2;
+    }
+    return nt == 3 && nh == m->P + 2;
 }
 size_t rows_per(const RowGeom& g, int C) { return (size_t)g.pstride * C; }
 size_t rows_extra(const RowGeom& g, int C) { return (size_t)(g.lead + ROW_TAIL) * C; }
@@ -441,8 +477,13 @@ int tc_selftest(std::string& rep) {
 // ------------------------------------------------------------------------------------------ plan
 int tc_build_plan(pv_model* m) {
     const pv_cfg& c = m->cfg;
-    const RowGeom pr = pr_geom();
+    const RowGeom pr = pr_geom(m->T);
     const int F = m->F, EX = F * c.exp_rate;
+    if (!tail_plan_supported(m))
+        return set_error(PV_ERR_BAD_CONFIG, "the row engine runs the T = 7, 9 and 13 reducer tails (modelsTF.py:62-67); "
+                                            "num_low_res_imgs=%d needs precision fp32", m->T);
+    const std::vector<TailStep> tail = tail_plan(m);
+    const RowGeom ug = g_dims(1, m->P, m->P);
     for (int tr = 0; tr < 2; ++tr) {
         Pool& P = tr ? m->pool_train : m->pool_infer;
         P.add("xn", (size_t)m->S * m->S * m->T);
@@ -453,7 +494,11 @@ int tc_build_plan(pv_model* m) {
             else if (tr) P.add("M" + std::to_string(i), rows_per(pr, 8), rows_extra(pr, 8));    // ... and only its ReLU bits (32 B / row)
             P.add(m->D(i, tr), rows_per(pr, F), rows_extra(pr, F));
         }
-        for (int k = 0; k <= 4; ++k) P.add("G" + std::to_string(k), rows_per(g_geom(k), F), rows_extra(g_geom(k), F));
+        for (const TailStep& ts : tail) {
+            if (ts.copy) P.add(ts.in, rows_per(ts.ig, F), rows_extra(ts.ig, F));
+            P.add(ts.out, rows_per(ts.og, F), rows_extra(ts.og, F));
+        }
+        P.add("U", rows_per(ug, F), rows_extra(ug, F));
         for (int i = 0; i < c.scale; ++i) {
             const Layer& L = m->layers[m->li("residConv" + std::to_string(i + 1))];
             P.add("q" + std::to_string(i + 1), (size_t)L.Ho * L.Wo * L.cout_s);
@@ -463,7 +508,11 @@ int tc_build_plan(pv_model* m) {
             P.add("g_a1", rows_per(pr, F), rows_extra(pr, F));
             P.add("g_D", rows_per(pr, F), rows_extra(pr, F));
             if (!m->use_tc) P.add("g_E", rows_per(pr, EX), rows_extra(pr, EX));
-            for (int k = 0; k <= 4; ++k) P.add("g_G" + std::to_string(k), rows_per(g_geom(k), F), rows_extra(g_geom(k), F));
+            for (const TailStep& ts : tail) {
+                if (ts.copy) P.add("g_" + ts.in, rows_per(ts.ig, F), rows_extra(ts.ig, F));
+                P.add("g_" + ts.out, rows_per(ts.og, F), rows_extra(ts.og, F));
+            }
+            P.add("g_U", rows_per(ug, F), rows_extra(ug, F));
             P.add("g_tail", (size_t)m->P * m->P * c.scale * c.scale);
             for (int i = 0; i + 1 < c.scale; ++i) {
                 const Layer& L = m->layers[m->li("residConv" + std::to_string(i + 1))];
@@ -480,10 +529,12 @@ int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip
     PV_TRY(P.ensure(B));
     PV_TRY(refresh_weights(m, st));
     const pv_cfg& c = m->cfg;
-    const RowGeom pr = pr_geom();
+    const RowGeom pr = pr_geom(m->T);
     const int F = m->F, EX = F * c.exp_rate;
     const Taps same = conv3_taps(pr.plane, pr.pw, true, +1);
     const Taps one = chunk_taps(32), wide = chunk_taps(EX);
+    const std::vector<TailStep> tail = tail_plan(m);
+    const RowGeom ug = g_dims(1, m->P, m->P);
 
     PV_TRY(launch_prep(lr, B, m->S * m->S, m->T, c.mean, c.std, P["xn"], P["mn"], st));
     const Layer& L0 = m->layers[m->li("mainConv1")];
@@ -502,14 +553,17 @@ int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip
         }
         PV_TRY(conv_rows(m, m->layers[e + 2], same, P[m->D(i, tr)], F, pr, P[m->A(i + 1, tr)], pr, P[m->A(i, tr)], B, "norm_fwd", st));
     }
-    // ConvReduceAndUpscale (T = 9), modelsTF.py:152-164: reflect pad H,W by 1, three valid 3x3x3 + ReLU, upscale conv
-    PV_TRY(launch_pr_to_g_reflect(P[m->A(m->R, tr)], pr, P["G0"], g_geom(0), B, F, st));
+    // ConvReduceAndUpscale (T = 9: modelsTF.py:152-164, reflect pad H,W by 1 before reducer 1), v2 (T = 7: :166-175, no pad),
+    // v3 (T = 13: :123-150, reflect pad before reducers 1-3): valid 3x3x3 + ReLU reducers, then the upscale conv
     const Taps valid = conv3_taps(576, 24, false, +1);
-    for (int k = 1; k <= 3; ++k) {
-        const Layer& L = m->layers[m->li("convReducer_" + std::to_string(k))];
-        PV_TRY(conv_rows(m, L, valid, P["G" + std::to_string(k - 1)], F, g_geom(k - 1), P["G" + std::to_string(k)], g_geom(k), nullptr, B, "reducer_fwd", st));
+    for (size_t k = 0; k < tail.size(); ++k) {
+        const TailStep& ts = tail[k];
+        if (k == 0) PV_TRY(launch_pr_to_g_reflect(P[m->A(m->R, tr)], pr, P[ts.in], ts.ig, B, F, st, ts.pad));
+        else if (ts.copy) PV_TRY(launch_pr_to_g_reflect(P[tail[k - 1].out], tail[k - 1].og, P[ts.in], ts.ig, B, F, st, ts.pad));
+        const Layer& L = m->layers[m->li("convReducer_" + std::to_string(k + 1))];
+        PV_TRY(conv_rows(m, L, valid, P[ts.in], F, ts.ig, P[ts.out], ts.og, nullptr, B, "reducer_fwd", st));
     }
-    PV_TRY(conv_rows(m, m->layers[m->li("upscaleConv1")], valid, P["G3"], F, g_geom(3), P["G4"], g_geom(4), nullptr, B, "upscale_fwd", st, false));
+    PV_TRY(conv_rows(m, m->layers[m->li("upscaleConv1")], valid, P[tail.back().out], F, tail.back().og, P["U"], ug, nullptr, B, "upscale_fwd", st, false));
     const float* q = P["mn"];
     if (c.scale == 3 && skip2d_supported(m->S, c.scale * c.scale)) {   // WDSRNetLRResidualPath, modelsTF.py:45-53: one fused kernel
         const Layer &R1 = m->layers[m->li("residConv1")], &R2 = m->layers[m->li("residConv2")], &R3 = m->layers[m->li("residConv3")];
@@ -523,7 +577,7 @@ int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip
             q = out;
         }
     }
-    PV_TRY(launch_tail_rows(P["G4"], g_geom(4), F, q, B, m->P, c.scale, c.mean, c.std, clip_round, sr, st));
+    PV_TRY(launch_tail_rows(P["U"], ug, F, q, B, m->P, c.scale, c.mean, c.std, clip_round, sr, st));
     return 0;
 }
 
@@ -534,8 +588,10 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int st
     pv_model* m = t->m;
     Pool& P = m->pool_train;
     const pv_cfg& c = m->cfg;
-    const RowGeom pr = pr_geom();
+    const RowGeom pr = pr_geom(m->T);
     const int F = m->F, EX = F * c.exp_rate, R = m->R;
+    const std::vector<TailStep> tail = tail_plan(m);
+    const RowGeom ug = g_dims(1, m->P, m->P);
     const Taps same = conv3_taps(pr.plane, pr.pw, true, +1), same_T = conv3_taps(pr.plane, pr.pw, true, -1);
     const Taps valid = conv3_taps(576, 24, false, +1), valid_T = conv3_taps(576, 24, false, -1);
     const Taps one = chunk_taps(32), wide = chunk_taps(EX);
@@ -552,7 +608,7 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int st
     t->rq.reset(t->wg_partial_floats);        // deferred partial reductions of this pass: one launch per bucket, before wn_bwd
     PV_CUDA(cudaMemsetAsync(t->dweff, 0, m->nweff * sizeof(float), st));
     PV_CUDA(cudaMemsetAsync(t->dbias_s, 0, m->nbias_s * sizeof(float), st));
-    PV_TRY(launch_tail_bwd_rows(g_sr, B, m->P, c.scale, c.std, P["g_G4"], g_geom(4), F, P["g_tail"], st));
+    PV_TRY(launch_tail_bwd_rows(g_sr, B, m->P, c.scale, c.std, P["g_U"], ug, F, P["g_tail"], st));
     if (c.scale == 3 && skip2d_supported(m->S, c.scale * c.scale) &&
         skip2d_partial_floats(B, m->S, c.scale * c.scale) <= t->wg_partial_floats) {   // ---- 2-D skip path: one fused kernel + a fixed-order reduction
         const Layer &R1 = m->layers[m->li("residConv1")], &R2 = m->layers[m->li("residConv2")], &R3 = m->layers[m->li("residConv3")];
@@ -575,15 +631,20 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int st
     }
     {   // ---- upscale conv, then the reducers (G layouts); each dgrad applies the ReLU mask of the layer below
         const Layer& U = m->layers[m->li("upscaleConv1")];
-        PV_TRY(wgrad_rows(t, U, valid, P["G3"], F, g_geom(3), P["g_G4"], g_geom(4), B, "upscale_wgrad", st));
-        PV_TRY(dgrad_rows(m, U, valid_T, 1, P["g_G4"], g_geom(4), P["g_G3"], g_geom(3), nullptr, P["G3"], B, "upscale_dgrad", st));
-        for (int k = 3; k >= 1; --k) {
-            const Layer& L = m->layers[m->li("convReducer_" + std::to_string(k))];
-            const std::string in = "G" + std::to_string(k - 1), gz = "g_G" + std::to_string(k), gin = "g_G" + std::to_string(k - 1);
-            PV_TRY(wgrad_rows(t, L, valid, P[in], F, g_geom(k - 1), P[gz], g_geom(k), B, "reducer_wgrad", st));
-            PV_TRY(dgrad_rows(m, L, valid_T, 1, P[gz], g_geom(k), P[gin], g_geom(k - 1), nullptr, k > 1 ? P[in] : nullptr, B, "reducer_dgrad", st));
+        const TailStep& last = tail.back();
+        PV_TRY(wgrad_rows(t, U, valid, P[last.out], F, last.og, P["g_U"], ug, B, "upscale_wgrad", st));
+        PV_TRY(dgrad_rows(m, U, valid_T, 1, P["g_U"], ug, P["g_" + last.out], last.og, nullptr, P[last.out], B, "upscale_dgrad", st));
+        for (int k = (int)tail.size() - 1; k >= 0; --k) {
+            const TailStep& ts = tail[k];
+            const Layer& L = m->layers[m->li("convReducer_" + std::to_string(k + 1))];
+            PV_TRY(wgrad_rows(t, L, valid, P[ts.in], F, ts.ig, P["g_" + ts.out], ts.og, B, "reducer_wgrad", st));
+            // the input is the previous reducer's ReLU output itself (mask here) or a padded copy of it (mask in the pad adjoint)
+            PV_TRY(dgrad_rows(m, L, valid_T, 1, P["g_" + ts.out], ts.og, P["g_" + ts.in], ts.ig, nullptr, (k > 0 && !ts.copy) ? P[ts.in] : nullptr,
+                              B, "reducer_dgrad", st));
+            if (k > 0 && ts.copy)
+                PV_TRY(launch_pr_to_g_reflect_bwd(P["g_" + ts.in], ts.ig, P["g_" + tail[k - 1].out], tail[k - 1].og, B, F, st, ts.pad, P[tail[k - 1].out]));
         }
-        PV_TRY(launch_pr_to_g_reflect_bwd(P["g_G0"], g_geom(0), P["g_a" + std::to_string(R & 1)], pr, B, F, st));
+        PV_TRY(launch_pr_to_g_reflect_bwd(P["g_" + tail[0].in], tail[0].ig, P["g_a" + std::to_string(R & 1)], pr, B, F, st, tail[0].pad));
     }
     }   // stage != 1
     const int i_hi = stage == 1 ? isplit - 1 : R - 1, i_lo = stage == 0 ? isplit : 0;

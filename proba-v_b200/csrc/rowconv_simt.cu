@@ -319,8 +319,10 @@ first_conv_pr_wgrad_reduce_kernel(const float* __restrict__ partials, int ncta, 
 // ------------------------------------------------------------------------------------------ PR <-> G (reflect pad)
 __device__ __forceinline__ int refl(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
+// `pad` = reflect padding per side on H and W (tf.pad REFLECT, modelsTF.py:125-135,157): 1, or 0 for a plain re-layout
+// (ConvReduceAndUpscalev2 pads nothing, modelsTF.py:166-175).  The source may be a PR or a G buffer.
 __global__ void pr_to_g_reflect_kernel(const float* __restrict__ a, RowGeom pr, float* __restrict__ g0, RowGeom gg,
-                                       long long n, int C4) {
+                                       long long n, int C4, int pad) {
     pdl_grid_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -328,7 +330,7 @@ __global__ void pr_to_g_reflect_kernel(const float* __restrict__ a, RowGeom pr, 
     const int w = (int)(r % gg.nw); r /= gg.nw;
     const int h = (int)(r % gg.nh); r /= gg.nh;
     const int t = (int)(r % gg.nt); const long long b = r / gg.nt;
-    const long long src = pr.lead + b * pr.pstride + (long long)(pr.t0 + t) * pr.plane + refl(h - 1, pr.nh) * pr.pw + refl(w - 1, pr.nw);
+    const long long src = pr.lead + b * pr.pstride + (long long)(pr.t0 + t) * pr.plane + refl(h - pad, pr.nh) * pr.pw + refl(w - pad, pr.nw);
     const long long dst = gg.lead + b * gg.pstride + (long long)(gg.t0 + t) * gg.plane + h * gg.pw + w;
     reinterpret_cast<float4*>(g0)[dst * C4 + c] = __ldg(reinterpret_cast<const float4*>(a) + src * C4 + c);
 }
@@ -341,8 +343,10 @@ __device__ __forceinline__ int preimages(int i, int n, int p, int (&o)[3]) {
     return c;
 }
 
+// adjoint of the kernel above; `relumask` (nullable, same rows as ga): the result is multiplied by (relumask > 0), i.e. the
+// gradient flows into the ReLU output the padded tensor was made from (convReducePad_2/3 of the T = 13 graph)
 __global__ void pr_to_g_reflect_bwd_kernel(const float* __restrict__ gg0, RowGeom gg, float* __restrict__ ga, RowGeom pr,
-                                           long long n, int C4) {
+                                           long long n, int C4, int pad, const float* __restrict__ relumask) {
     pdl_grid_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -351,7 +355,7 @@ __global__ void pr_to_g_reflect_bwd_kernel(const float* __restrict__ gg0, RowGeo
     const int h = (int)(r % pr.nh); r /= pr.nh;
     const int t = (int)(r % pr.nt); const long long b = r / pr.nt;
     int hs[3], ws[3];
-    const int nh = preimages(h, pr.nh, 1, hs), nw = preimages(w, pr.nw, 1, ws);
+    const int nh = preimages(h, pr.nh, pad, hs), nw = preimages(w, pr.nw, pad, ws);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int x = 0; x < nh; ++x)
         for (int y = 0; y < nw; ++y) {
@@ -360,6 +364,10 @@ __global__ void pr_to_g_reflect_bwd_kernel(const float* __restrict__ gg0, RowGeo
             s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
         }
     const long long dst = pr.lead + b * pr.pstride + (long long)(pr.t0 + t) * pr.plane + h * pr.pw + w;
+    if (relumask) {
+        const float4 r4 = __ldg(reinterpret_cast<const float4*>(relumask) + dst * C4 + c);
+        s.x = r4.x > 0.f ? s.x : 0.f; s.y = r4.y > 0.f ? s.y : 0.f; s.z = r4.z > 0.f ? s.z : 0.f; s.w = r4.w > 0.f ? s.w : 0.f;
+    }
     reinterpret_cast<float4*>(ga)[dst * C4 + c] = s;
 }
 
@@ -472,18 +480,23 @@ int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, i
     return 0;
 }
 
-int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st) {
+int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st, int pad) {
+    if (pad < 0 || pad > 1 || gg.nh != pr.nh + 2 * pad || gg.nw != pr.nw + 2 * pad || gg.nt != pr.nt)
+        return set_error(PV_ERR_BAD_ARG, "pr_to_g_reflect: %dx%dx%d + pad %d does not give %dx%dx%d", pr.nh, pr.nw, pr.nt, pad, gg.nh, gg.nw, gg.nt);
     const long long n = (long long)B * gg.nt * gg.nh * gg.nw * (C / 4);
     PV_TIMED("pr_to_g_reflect", st);
-    PV_CUDA(launch_pdl_simple(pr_to_g_reflect_kernel, cdiv(n, 256), 256, 0, st, a, pr, g0, gg, n, C / 4));
+    PV_CUDA(launch_pdl_simple(pr_to_g_reflect_kernel, cdiv(n, 256), 256, 0, st, a, pr, g0, gg, n, C / 4, pad));
     PV_LAUNCH_CHECK();
     return 0;
 }
 
-int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st) {
+int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st, int pad,
+                               const float* relumask) {
+    if (pad < 0 || pad > 1 || gg.nh != pr.nh + 2 * pad || gg.nw != pr.nw + 2 * pad || gg.nt != pr.nt)
+        return set_error(PV_ERR_BAD_ARG, "pr_to_g_reflect_bwd: geometry mismatch");
     const long long n = (long long)B * pr.nt * pr.nh * pr.nw * (C / 4);
     PV_TIMED("pr_to_g_reflect_bwd", st);
-    PV_CUDA(launch_pdl_simple(pr_to_g_reflect_bwd_kernel, cdiv(n, 256), 256, 0, st, gg0, gg, ga, pr, n, C / 4));
+    PV_CUDA(launch_pdl_simple(pr_to_g_reflect_bwd_kernel, cdiv(n, 256), 256, 0, st, gg0, gg, ga, pr, n, C / 4, pad, relumask));
     PV_LAUNCH_CHECK();
     return 0;
 }

@@ -112,9 +112,11 @@ int launch_first_conv_pr(const float* xn, const float* w /*[27][32] taps in (dt,
                          float* y, RowGeom g, cudaStream_t st);
 int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, int T, RowGeom g, float* dw, float* db,
                                float* partials, size_t partial_floats, cudaStream_t st, ReduceQueue* rq = nullptr);
-// PR block output -> G layout with the reducer's reflect padding (tf.pad REFLECT by 1 on H and W), and its adjoint
-int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st);
-int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st);
+// PR (or G) tensor -> G layout with the reducer's reflect padding (tf.pad REFLECT by `pad` = 0 or 1 on H and W), and its
+// adjoint (optionally multiplied by (relumask > 0): the padded tensor was a ReLU output)
+int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st, int pad = 1);
+int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st, int pad = 1,
+                               const float* relumask = nullptr);
 
 // tail on the row layouts: sr = (depth_to_space(U[:, :, :9]) + depth_to_space(resid)) * std + mean [clip, round]; and its adjoint
 int launch_tail_rows(const float* u, RowGeom g, int uc, const float* resid, int B, int P, int scale, float mean, float stdv,

@@ -146,3 +146,57 @@ def test_staged_backward_buckets_are_bit_identical(small_cfg, precision):
     assert ranges[0][1] == n and ranges[1][0] == 0 and ranges[1][1] == ranges[0][0]
     if precision != "fp32":
         assert 0 < ranges[0][0] < n       # the row engines really split the arena
+
+
+# ---- the other reducer tails of the reference graph on the row engines (modelsTF.py:62-67): ConvReduceAndUpscalev2 (T = 7, no
+# ---- reflect pad) and ConvReduceAndUpscalev3 (T = 13, reflect pads before reducers 1-3, five reducers)
+@pytest.mark.parametrize("precision", ["fp32_rows", "tf32"])
+@pytest.mark.parametrize("T", [7, 13])
+def test_forward_other_frame_counts(small_cfg, precision, T):
+    from probav_b200 import synth
+    cfg = dict(small_cfg, numImgLR=T)
+    om, p = oracle_and_params(cfg, seed=50 + T)
+    m = cuda_model(cfg, p, precision=precision)
+    lr, _, _ = synth.make_batch(5, T=T, seed=2)
+    ref = om.forward(p, torch.from_numpy(lr).double()).numpy()
+    got = m(lr)
+    e = rel_err(got, ref)
+    print(f"{precision} T={T}: SR max rel err {e:.3e}")
+    assert e < SR_TOL
+    if precision == "fp32_rows":
+        assert np.abs(got - ref).max() / 3160.7272 < 1e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32_rows", "tf32"])
+@pytest.mark.parametrize("T", [7, 13])
+def test_gradients_other_frame_counts(small_cfg, precision, T):
+    import probav_b200 as pb
+    from probav_b200 import synth
+    cfg = dict(small_cfg, numImgLR=T)
+    om, p = oracle_and_params(cfg, seed=60 + T)
+    m = cuda_model(cfg, p, precision=precision)
+    lr, hr, mask = synth.make_batch(3, T=T, seed=11, hr_zero_under_mask=True)
+    ol = OracleLosses((48, 48, 1))
+    loss, g, sr, cps = loss_and_grads(om, ol, p, torch.from_numpy(lr).double(), torch.from_numpy(hr).double(), torch.from_numpy(mask))
+    t = _trainer(pb, m)
+    lossv, psnrv = t.forward_backward(lr, hr, mask)
+    assert abs(lossv - float(loss)) < 1e-3 * abs(float(loss))
+    assert abs(psnrv - float(cps.mean())) < 0.01
+    got = t.get_grads()
+    tol = 1e-3 if precision == "fp32_rows" else TF32_GRAD_TOL
+    worst, worst_k = 0.0, None
+    for k, ref in g.items():
+        if np.abs(ref.numpy()).max() == 0:
+            continue
+        e = rel_err(got[k], ref.numpy())
+        if e > worst:
+            worst, worst_k = e, k
+    print(f"{precision} T={T}: worst gradient rel err {worst:.3e} at {worst_k}")
+    assert worst < tol, (worst, worst_k)
+
+
+def test_row_engine_rejects_t19(small_cfg):
+    """ConvReduceAndUpscaleEx (T = 19: a 5x5x5 reducer and reflect pads along T) stays on the dense fp32 engine."""
+    import probav_b200 as pb
+    with pytest.raises((ValueError, RuntimeError)):
+        pb.WDSRConv3D("superResolutionNet", "NIR", 8075.2045, 3160.7272, 6).build(**dict(small_cfg, numImgLR=19), precision="tf32")
