@@ -88,6 +88,28 @@ class WDSRModel:
                 flat[v.offset:v.offset + v.numel] = w.reshape(-1)
         self.set_flat(flat)
 
+    def layer_names(self) -> List[str]:
+        seen = []
+        for v in self._vars:
+            layer = v.name.rsplit("/", 1)[0]
+            if layer not in seen:
+                seen.append(layer)
+        return seen
+
+    def restore_checkpoint(self, ckpt_dir_or_prefix: str) -> dict:
+        """tf.train.Checkpoint(model=...).restore(manager.latest_checkpoint) of test.py:58-67: loads the weights of a TensorFlow
+        checkpoint (written by the reference or by ModelTrainer.save) and returns its {"step", "psnr", "save_counter"}."""
+        import os
+        from . import tfckpt
+        prefix = ckpt_dir_or_prefix
+        if os.path.isdir(prefix):
+            prefix = tfckpt.latest_checkpoint(prefix)
+            if prefix is None:
+                raise FileNotFoundError(f"no checkpoint in {ckpt_dir_or_prefix}")
+        z = tfckpt.load_checkpoint(prefix, self.layer_names())
+        self.set_weights(z["weights"])
+        return {k: z[k] for k in ("step", "psnr", "save_counter")}
+
     def init_weights(self, seed: int = 0):
         """Keras defaults under TFA WeightNormalization(data_init=False): v Glorot-uniform, bias 0, g <- ||v||."""
         rng = np.random.default_rng(seed)

@@ -7,7 +7,6 @@ from __future__ import annotations
 
 import ctypes as C
 import glob
-import json
 import logging
 import os
 import time
@@ -15,7 +14,7 @@ from typing import List
 
 import numpy as np
 
-from . import _buf, parallel
+from . import _buf, parallel, tbevents, tfckpt
 from ._lib import PV_LOSS, PV_OPT, check, lib
 from .loss import LOSS_KIND_OF_METHOD
 
@@ -90,12 +89,15 @@ class ModelTrainer:
         self.step = 0               # ckpt.step
         self.psnr = 1.0             # ckpt.psnr
         self.max_to_keep = 5
+        self.save_counter = 0       # ckpt.save_counter
         self._rng = np.random.default_rng(seed)
+        self._val_rng = np.random.default_rng(seed + 1)     # the training index stream is drawn from the prefetch thread
         h = C.c_void_p()
         check(lib().pv_trainer_create(model._h, PV_OPT[optimizer.kind], optimizer.learning_rate, PV_LOSS[kind], C.byref(h)))
         self._h = h
         self._out = np.zeros(2, np.float32)
-        self._scalars = open(os.path.join(logDir, "scalars.jsonl"), "a") if parallel.world()[0] == 0 else None
+        # tf.summary.create_file_writer(logDir) (trainClass.py:41): a TensorBoard event file, rank 0 only
+        self._scalars = tbevents.SummaryWriter(logDir) if parallel.world()[0] == 0 else None
         self._grad_view = None
         self.restore()
 
@@ -103,38 +105,75 @@ class ModelTrainer:
     def model(self):
         return self._model
 
-    # ---- checkpoint (stands in for tf.train.Checkpoint + CheckpointManager(max_to_keep=5), trainClass.py:33-39)
-    def _latest(self):
+    # ---- checkpoint: tf.train.Checkpoint(step, psnr, optimizer, model) + CheckpointManager(max_to_keep=5) (trainClass.py:33-39),
+    # written in TensorFlow's own tensor-bundle format (tfckpt.py): ckpt-N.index, ckpt-N.data-00000-of-00001, `checkpoint`
+    def _layer_names(self):
+        return self._model.layer_names()
+
+    def _legacy_latest(self):
         files = sorted(glob.glob(os.path.join(self.ckptDir, "ckpt-*.npz")), key=lambda f: int(f.split("-")[-1][:-4]))
         return files[-1] if files else None
 
+    def _split(self, flat):
+        return {v.name: flat[v.offset:v.offset + v.numel].reshape(v.shape) for v in self._model.trainable_variables}
+
+    def _join(self, d):
+        flat = np.zeros(self._model.nparams, np.float32)
+        for v in self._model.trainable_variables:
+            if v.name in d:
+                flat[v.offset:v.offset + v.numel] = np.asarray(d[v.name], np.float32).reshape(-1)
+        return flat
+
     def restore(self):
-        f = self._latest()
-        if f:
+        """trainClass.py:52-59: restore the newest checkpoint of ckptDir, if any (TF bundle; .npz of earlier versions too)."""
+        prefix = tfckpt.latest_checkpoint(self.ckptDir)
+        n = self._model.nparams
+        if prefix:
+            z = tfckpt.load_checkpoint(prefix, self._layer_names())
+            self._model.set_weights(z["weights"])
+            o = z["opt"]
+            if o is not None and o.get("m") and o.get("v"):
+                m1, m2 = self._join(o["m"]), self._join(o["v"])
+                check(lib().pv_trainer_set_state(self._h, int(o["iter"]), float(o.get("momentum_cache", 1.0)), _buf.ptr(m1), _buf.ptr(m2), n))
+            self.step = int(z["step"]) if z["step"] is not None else 0
+            self.psnr = float(z["psnr"]) if z["psnr"] is not None else self.psnr
+            self.save_counter = int(z["save_counter"] or 0)
+        else:
+            f = self._legacy_latest()
+            if not f:
+                return
             z = np.load(f)
             self._model.set_flat(z["params"])
-            n = self._model.nparams
             m1 = np.ascontiguousarray(z["opt_m"], np.float32)
             m2 = np.ascontiguousarray(z["opt_v"], np.float32)
             check(lib().pv_trainer_set_state(self._h, int(z["opt_iter"]), float(z["momentum_cache"]), _buf.ptr(m1), _buf.ptr(m2), n))
             self.step, self.psnr = int(z["step"]), float(z["psnr"])
-            print(f"[ INFO ] Model restored from checkpoint at step {self.step}.")
+        print(f"[ INFO ] Model restored from checkpoint at step {self.step}.")
 
     def save(self):
+        """CheckpointManager.save (trainClass.py:118-120): ckpt-<save_counter>, keeps the newest max_to_keep."""
         if parallel.world()[0] != 0:
             return None
         n = self._model.nparams
         it, mc = C.c_int64(), C.c_double()
         m1, m2 = np.empty(n, np.float32), np.empty(n, np.float32)
         check(lib().pv_trainer_get_state(self._h, C.byref(it), C.byref(mc), _buf.ptr(m1), _buf.ptr(m2), n))
-        files = sorted(glob.glob(os.path.join(self.ckptDir, "ckpt-*.npz")), key=lambda f: int(f.split("-")[-1][:-4]))
-        k = int(files[-1].split("-")[-1][:-4]) + 1 if files else 1
-        path = os.path.join(self.ckptDir, f"ckpt-{k}.npz")
-        np.savez(path, params=self._model.get_flat(), opt_m=m1, opt_v=m2, opt_iter=it.value, momentum_cache=mc.value,
-                 step=self.step, psnr=self.psnr, names=np.array([v.name for v in self._model.trainable_variables]))
-        for old in files[:max(0, len(files) + 1 - self.max_to_keep)]:
-            os.remove(old)
-        return path
+        self.save_counter += 1
+        name = f"ckpt-{self.save_counter}"
+        prefix = os.path.join(self.ckptDir, name)
+        o = self.optimizer
+        opt = {"iter": it.value, "learning_rate": o.learning_rate, "beta_1": getattr(o, "beta_1", 0.9), "beta_2": getattr(o, "beta_2", 0.999),
+               "decay": 0.0, "momentum_cache": mc.value, "m": self._split(m1), "v": self._split(m2)}
+        tfckpt.save_checkpoint(prefix, self._layer_names(), self._model.get_weights(), self.step, self.psnr, self.save_counter, opt)
+        st = tfckpt.read_checkpoint_state(self.ckptDir)
+        paths, stamps = st["all_model_checkpoint_paths"] + [name], st["all_model_checkpoint_timestamps"] + [time.time()]
+        while len(paths) > self.max_to_keep:
+            old = os.path.join(self.ckptDir, paths.pop(0))
+            stamps.pop(0)
+            for f in glob.glob(old + ".index") + glob.glob(old + ".data-*"):
+                os.remove(f)
+        tfckpt.write_checkpoint_state(self.ckptDir, paths, stamps, st["last_preserved_timestamp"])
+        return prefix + ".index"
 
     # ---- steps
     def _run(self, fn_host, fn_dev, patchLR, patchHR, maskHR):
@@ -247,12 +286,12 @@ class ModelTrainer:
 
     def _scalar(self, tag, value, step):
         if self._scalars:
-            self._scalars.write(json.dumps({"tag": tag, "value": float(value), "step": int(step), "wall_time": time.time()}) + "\n")
+            self._scalars.scalar(tag, value, step)
 
     # ---- fit loop
     def fitTrainData(self, X, y, globalBatchSize: int, epochs: int, valData: List, bufferSize: int = 256,
                      valSteps: int = 64, saveBestOnly: bool = True, initEpoch: int = 0, maxSteps: int = None,
-                     logEvery: int = 1):
+                     logEvery: int = 1, prefetch: bool = True):
         """trainClass.py:61-122.  X [N,S,S,T,1]; y = [HR [N,..,1], mask]; valData = [X_val, y_val, mask_val].
         Under torch.distributed every rank walks the same index stream and takes its shard of each global batch."""
         rank, ws = parallel.world()
@@ -263,9 +302,21 @@ class ModelTrainer:
         step = globalStep % totalSteps if totalSteps else 0
         epoch = initEpoch
         stream = batched(shuffled_index_stream(n, epochs, bufferSize, self._rng), globalBatchSize)
+        if prefetch:      # .prefetch(AUTOTUNE) of utils/utils.py:32-34: this rank's shard is gathered into pinned memory and copied
+            import torch  # to the GPU on a side stream while the previous step computes (pipeline.py)
+            from .pipeline import PrefetchLoader
+            batches = PrefetchLoader((X, yHR, yMask), stream, device=torch.device(f"cuda:{self._model.device}"), rank=rank,
+                                     world_size=ws, max_batch=globalBatchSize)
+        else:
+            def host_batches():
+                for idx in stream:
+                    lo, hi = parallel.shard_bounds(len(idx), rank, ws)
+                    sel = np.sort(idx[lo:hi]) if hi > lo else idx[:0]
+                    yield len(idx), (X[sel], yHR[sel], yMask[sel])
+            batches = host_batches()
         logger.info("[ INFO ] Begin training...")
         done = 0
-        for idx in stream:
+        for gb, (xb, yb, mb) in batches:
             if totalSteps - step == 0:
                 epoch += 1
                 step = self.step % totalSteps
@@ -274,9 +325,7 @@ class ModelTrainer:
                     mtr.reset_states()
             step += 1
             globalStep += 1
-            lo, hi = parallel.shard_bounds(len(idx), rank, ws)
-            sel = np.sort(idx[lo:hi]) if hi > lo else idx[:0]
-            self.trainStep(X[sel], yHR[sel], yMask[sel], global_batch=len(idx))
+            self.trainStep(xb, yb, mb, global_batch=gb)
             self.step += 1
             if logEvery and (step % logEvery == 0) and rank == 0:
                 logger.info(f"[ EPOCH {epoch}/{epochs} ] - [ STEP {step}/{totalSteps} ] Loss: {self.trainLoss.result():.6f}, "
@@ -287,7 +336,7 @@ class ModelTrainer:
                 self.testLoss.reset_states()
                 self.testPSNR.reset_states()
                 Xv, yv, mv = valData
-                vstream = batched(shuffled_index_stream(len(Xv), 1, bufferSize, self._rng), globalBatchSize)
+                vstream = batched(shuffled_index_stream(len(Xv), 1, bufferSize, self._val_rng), globalBatchSize)
                 for k, vidx in enumerate(vstream):
                     if k >= valSteps:
                         break

@@ -366,6 +366,24 @@ def test_eval_step_and_checkpoint_roundtrip(small_cfg):
     l2b, _ = t.trainStep(lr, hr, mask)
     # the weight-gradient kernels reduce with fp32 atomics (order not fixed), so the step repeats to rounding, not bitwise
     assert l2a == l2b and np.abs(m.get_flat() - w2).max() < 0.02 * 5e-4
+    # the files are TensorFlow tensor bundles with the reference's key layout (trainClass.py:33-39; tests/test_tfckpt.py pins the format)
+    from probav_b200 import tfckpt
+    r = tfckpt.BundleReader(path[:-len(".index")])
+    nl = len(t._layer_names())
+    assert len(r.entries) == nl * 10 + 6 + 3 + 1
+    assert int(r.tensor("step/.ATTRIBUTES/VARIABLE_VALUE")) == 1 and int(r.tensor("save_counter/.ATTRIBUTES/VARIABLE_VALUE")) == 1
+    v0 = m.trainable_variables[0]
+    assert v0.name == "mainConv1/v"
+    assert np.array_equal(r.tensor("model/layer_with_weights-0/v/.ATTRIBUTES/VARIABLE_VALUE").reshape(-1), w1[v0.offset:v0.offset + v0.numel])
+    for _ in range(6):                      # CheckpointManager(max_to_keep=5)
+        t.save()
+    st = tfckpt.read_checkpoint_state(t.ckptDir)
+    assert st["all_model_checkpoint_paths"] == [f"ckpt-{i}" for i in range(3, 8)]
+    assert sorted(f for f in os.listdir(t.ckptDir) if f.endswith(".index")) == [f"ckpt-{i}.index" for i in range(3, 8)]
+    # a fresh model + trainer on the same directory resumes from it (train.py re-run; test.py:58-67 restores the model only)
+    m2 = cuda_model(small_cfg, oracle_and_params(small_cfg, seed=99)[1])
+    m2.restore_checkpoint(t.ckptDir)
+    assert np.array_equal(m2.get_flat(), m.get_flat())
 
 
 def test_fit_loop_runs_and_loss_decreases(small_cfg):

@@ -200,3 +200,25 @@ def test_row_engine_rejects_t19(small_cfg):
     import probav_b200 as pb
     with pytest.raises((ValueError, RuntimeError)):
         pb.WDSRConv3D("superResolutionNet", "NIR", 8075.2045, 3160.7272, 6).build(**dict(small_cfg, numImgLR=19), precision="tf32")
+
+
+def test_fit_loop_prefetch_pipeline_matches_host_batches(small_cfg):
+    """fitTrainData with the pinned-memory prefetch pipeline (pipeline.py) takes exactly the steps of the plain host-gather
+    loop: the tf32 engine is bit-reproducible, so the trained weights must be identical; the log is a TensorBoard event file."""
+    import glob
+    import probav_b200 as pb
+    from probav_b200 import synth, tbevents
+    X, y, msk = synth.make_batch(40, seed=70, hr_zero_under_mask=True)
+    out = []
+    for prefetch in (True, False):
+        m = pb.WDSRConv3D("n", "NIR", 8075.2045, 3160.7272, 6).build(**small_cfg, seed=5, precision="tf32")
+        t = _trainer(pb, m)
+        t.evalStep = 2
+        t.fitTrainData(X, [y, msk], 16, 2, [X[:16], y[:16], msk[:16]], valSteps=1, saveBestOnly=False, logEvery=0, prefetch=prefetch)
+        assert t.step == 5                         # 80 samples / 16
+        out.append(m.get_flat())
+        t.close()
+        ev = tbevents.read_scalars(glob.glob(t.logDir + "/events.out.tfevents.*")[0])
+        assert [e.tag for e in ev[1:5]] == ["Train PSNR", "Train loss", "Train PSNR", "Train loss"]
+        assert {e.tag for e in ev[1:]} == {"Train PSNR", "Train loss", "Test loss", "Test PSNR"}
+    assert np.array_equal(out[0], out[1])

@@ -135,3 +135,44 @@ def test_data_parallel_contract_gloo_world2():
     other = [r for r in res if r[0] == "r1"][0]
     assert main[0] < 1e-10 and main[1] < 1e-9 and main[2] < 1e-9
     assert main[3] == 0.0 and other[1] == 0.0           # broadcast from rank 0
+
+
+def test_prefetch_loader_yields_the_rank_shard_of_every_global_batch():
+    """pipeline.PrefetchLoader on host arrays (device=None): same batches as gathering by hand, for both ranks of a
+    2-rank job, including the partial last batch (utils/utils.py:32-34 has no drop_remainder)."""
+    from probav_b200 import parallel
+    from probav_b200.pipeline import PrefetchLoader
+    from probav_b200.trainClass import batched, shuffled_index_stream
+    N = 50
+    X = np.arange(N * 6, dtype=np.float32).reshape(N, 2, 3)
+    y = np.arange(N, dtype=np.float32).reshape(N, 1)
+    m = (np.arange(N) % 3 == 0).reshape(N, 1)
+    ref = list(batched(shuffled_index_stream(N, 2, 16, np.random.default_rng(0)), 8))
+    assert sum(len(b) for b in ref) == 2 * N and len(ref[-1]) == 4
+    for rank in (0, 1):
+        ld = PrefetchLoader((X, y, m), batched(shuffled_index_stream(N, 2, 16, np.random.default_rng(0)), 8), device=None,
+                            rank=rank, world_size=2, depth=2)
+        seen = 0
+        for (gb, (a, b, c)), idx in zip(ld, ref):
+            lo, hi = parallel.shard_bounds(len(idx), rank, 2)
+            sel = np.sort(idx[lo:hi])
+            assert gb == len(idx)
+            assert np.array_equal(a, X[sel]) and np.array_equal(b, y[sel]) and np.array_equal(c, m[sel].view(np.uint8))
+            seen += 1
+        assert seen == len(ref)
+    # leaving the loop early stops the producer thread
+    ld = PrefetchLoader((X, y, m), batched(shuffled_index_stream(N, 50, 16, np.random.default_rng(1)), 8), device=None)
+    for i, _ in enumerate(ld):
+        if i == 2:
+            break
+    ld.close()
+    assert ld._thread is None
+
+
+def test_prefetch_loader_propagates_producer_errors():
+    from probav_b200.pipeline import PrefetchLoader
+    X = np.zeros((4, 2), np.float32)
+    ld = PrefetchLoader((X,), [np.array([0, 1]), np.array([7, 9])], device=None)
+    with pytest.raises(IndexError):
+        for _ in ld:
+            pass
