@@ -230,6 +230,35 @@ def run_b200(args, cfg):
     rep = _lib.timing_report()
     lib.pv_timing_reset()
     barrier()
+
+    # ---- second half of BASELINE.json's metric: 384x384 scene SR inference (configs[3]; reference test.py:103-160 +
+    # dataGenerator.py:108-121): host LR scenes [T,128,128] in, host SR scenes [384,384] out; reflect-pad + patching, forward,
+    # clip + round-half-even and the 8x8 stitch all run on the device.  Scenes are sharded by rank (replicas only).
+    scene = None
+    if not args.no_scene_infer:
+        ns = args.scenes
+        lr_s, _, _ = synth.make_scene(ns, T=cfg["num_low_res_imgs"], seed=300 + rank)
+        model.predict_from_scenes(lr_s)                       # sizes the inference activation pool
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            model.predict_from_scenes(lr_s)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0) / 3
+        d_s = torch.from_numpy(lr_s).to(dev)                  # device-resident variant (inputs in HBM, outputs left in HBM)
+        model.predict_from_scenes(d_s)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(3):
+            model.predict_from_scenes(d_s)
+        s1.record()
+        barrier()
+        dms = max_over_ranks(s0.elapsed_time(s1)) / 3
+        scene = {"metric": "384x384 scene SR infer/s (9x128x128 LR in, 64 patches per scene, clip+round+stitch on device, host to host)",
+                 "value": ws * ns / dt, "unit": "scenes/s", "scenes_per_call": ns, "ms_per_scene": dt / ns * 1e3,
+                 "device_resident_value": ws * ns / (dms * 1e-3), "algorithmic_tflops": ws * ns / dt * 0.2655,
+                 "h2d_bytes_per_scene": int(lr_s[0].nbytes), "d2h_bytes_per_scene": 384 * 384 * 4}
     if ws > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -284,7 +313,7 @@ def run_b200(args, cfg):
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "roofline": roofline, "roofline_shift_loss": roof_loss, "kernels": kernels,
-            "last_loss": lossv, "last_cpsnr": psnrv}
+            "scene_infer": scene, "last_loss": lossv, "last_cpsnr": psnrv}
     if ws == 1 and not args.no_cpu_baseline:
         v, sec, cores = cpu_reference_steps(cfg, args.ref_batch, 2, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -317,6 +346,8 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=16, help="CPU arm: patches per step (bounded sample)")
     ap.add_argument("--cfg", default=os.path.join(ROOT, "cfg", "p16t9c85r12.cfg"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scene-infer", action="store_true")
+    ap.add_argument("--scenes", type=int, default=32, help="scenes per inference call of the scene_infer leg")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "fp32_rows"],
                     help="tf32 = tcgen05 tensor-core engine (default; what TensorFlow runs on Ampere+), fp32 = CUDA-core exact mode")
     args = ap.parse_args()

@@ -107,6 +107,9 @@ int  pv_predict_scenes_host(pv_model* m, const float* lr_patches_host, int nscen
  * windows (patch+max_shift) stride patch -> model -> resolve -> stitched [nscenes, scale*H, scale*W]. */
 int  pv_predict_from_scenes_host(pv_model* m, const float* lr_scenes_host, int nscenes, int H, int W,
                                  float* sr_scenes_host);
+/* same with device-resident scenes (asynchronous on `stream`) */
+int  pv_predict_from_scenes(pv_model* m, const float* lr_scenes_dev, int nscenes, int H, int W,
+                            float* sr_scenes_dev, void* stream);
 
 /* ---- losses: Losses(targetShape, cropBorder=3, bitDepth=16)  loss.py:13-35 ------------------- */
 /* One pass over (hr, mask, sr) evaluates all (2*border+1)^2 shifts (loss.py:48-50 loop), the per-shift

@@ -47,6 +47,7 @@ _SIGS = {
     "pv_resolve_host": (C.c_int, [_P, _P, C.c_int, _P]),
     "pv_predict_scenes_host": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     "pv_predict_from_scenes_host": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "pv_predict_from_scenes": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "pv_shift_loss": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                 _P, _P, _P, _P, _P, _P, _P, _P]),
     "pv_shift_loss_host": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,

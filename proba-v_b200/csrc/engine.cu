@@ -552,6 +552,7 @@ void pv_model_destroy(pv_model* m) {
     m->pool_train.release();
     cudaFree(m->params); cudaFree(m->weff); cudaFree(m->weffT); cudaFree(m->bias_s); cudaFree(m->scale); cudaFree(m->wn_tab);
     cudaFree(m->stage_lr); cudaFree(m->stage_sr); cudaFree(m->stage_scene);
+    m->scene_pipe.release();
     delete m;
 }
 
@@ -662,31 +663,85 @@ int pv_predict_scenes_host(pv_model* m, const float* lr_patches_host, int nscene
     return 0;
 }
 
-int pv_predict_from_scenes_host(pv_model* m, const float* lr_scenes_host, int nscenes, int H, int W, float* sr_scenes_host) {
-    if (!m || !lr_scenes_host || !sr_scenes_host || nscenes <= 0) return set_error(PV_ERR_BAD_ARG, "predict_from_scenes: bad argument");
-    if (H != W || H % m->P) return set_error(PV_ERR_BAD_ARG, "predict_from_scenes: scene %dx%d must be square and a multiple of patch_size", H, W);
+// device-resident scenes in, device-resident stitched scenes out; chunks of SCENE_CHUNK_PATCHES patches per forward pass
+static const int SCENE_CHUNK_PATCHES = 512;
+
+static int predict_chunk(pv_model* m, const float* scn_dev, int ns, int H, int W, float* out_dev, cudaStream_t st) {
+    const int n = H / m->P;
+    const size_t PP = (size_t)m->P * m->cfg.scale;
+    PV_TRY(launch_scene_to_patches(scn_dev, ns, m->T, H, W, m->P, m->cfg.max_shift, m->stage_lr, st));
+    PV_TRY(model_forward(m, m->stage_lr, ns * n * n, m->stage_sr, false, 1, st));
+    return launch_stitch(m->stage_sr, ns, n, (int)PP, out_dev, st);
+}
+
+static int scene_args_ok(pv_model* m, const void* a, const void* b, int nscenes, int H, int W) {
+    if (!m || !a || !b || nscenes <= 0) return set_error(PV_ERR_BAD_ARG, "predict_from_scenes: bad argument");
+    if (H != W || H <= 0 || H % m->P) return set_error(PV_ERR_BAD_ARG, "predict_from_scenes: scene %dx%d must be square and a multiple of patch_size", H, W);
+    return 0;
+}
+
+int pv_predict_from_scenes(pv_model* m, const float* lr_scenes_dev, int nscenes, int H, int W, float* sr_scenes_dev, void* stream) {
+    PV_TRY(scene_args_ok(m, lr_scenes_dev, sr_scenes_dev, nscenes, H, W));
     PV_CUDA(cudaSetDevice(m->device));
     const int n = H / m->P, pps = n * n;
     const size_t nin = (size_t)m->S * m->S * m->T, PP = (size_t)m->P * m->cfg.scale, nout = PP * PP, nsc = (size_t)m->T * H * W;
-    const int chunk = std::max(1, 256 / pps);
-    float* scn = nullptr;
-    PV_CUDA(cudaMalloc(&scn, nsc * chunk * sizeof(float)));
+    const int chunk = std::max(1, SCENE_CHUNK_PATCHES / pps);
+    PV_TRY(stage_ensure(&m->stage_lr, &m->stage_lr_n, nin * pps * chunk));
+    PV_TRY(stage_ensure(&m->stage_sr, &m->stage_sr_n, nout * pps * chunk));
+    for (int s = 0; s < nscenes; s += chunk)
+        PV_TRY(predict_chunk(m, lr_scenes_dev + nsc * s, std::min(chunk, nscenes - s), H, W, sr_scenes_dev + nout * pps * s, S_(stream)));
+    return 0;
+}
+
+// Host scenes in, host scenes out.  Two slots of pinned staging + device buffers: while chunk c computes, chunk c+1 is copied
+// into pinned memory and up to the device on a copy-in stream, and chunk c-1 comes back on a copy-out stream and is copied to
+// the caller's (pageable) array -- the PCIe transfers and both host memcpys overlap the forward pass.
+int pv_predict_from_scenes_host(pv_model* m, const float* lr_scenes_host, int nscenes, int H, int W, float* sr_scenes_host) {
+    PV_TRY(scene_args_ok(m, lr_scenes_host, sr_scenes_host, nscenes, H, W));
+    PV_CUDA(cudaSetDevice(m->device));
+    PV_CUDA(cudaDeviceSynchronize());     // the private non-blocking streams below do not order against work already in flight
+    const int n = H / m->P, pps = n * n;
+    const size_t nin = (size_t)m->S * m->S * m->T, PP = (size_t)m->P * m->cfg.scale, nout = PP * PP, nsc = (size_t)m->T * H * W;
+    const int chunk = std::max(1, SCENE_CHUNK_PATCHES / pps);
+    pv::ScenePipe& sp = m->scene_pipe;
+    PV_TRY(sp.ensure(nsc * chunk, nout * pps * chunk));
+    PV_TRY(stage_ensure(&m->stage_lr, &m->stage_lr_n, nin * pps * chunk));
+    PV_TRY(stage_ensure(&m->stage_sr, &m->stage_sr_n, nout * pps * chunk));
+    const int nchunks = (nscenes + chunk - 1) / chunk;
     int rc = 0;
-    do {
-        if ((rc = stage_ensure(&m->stage_lr, &m->stage_lr_n, nin * pps * chunk))) break;
-        if ((rc = stage_ensure(&m->stage_sr, &m->stage_sr_n, nout * pps * chunk))) break;
-        if ((rc = stage_ensure(&m->stage_scene, &m->stage_scene_n, nout * pps * chunk))) break;
-        for (int s = 0; s < nscenes && !rc; s += chunk) {
-            const int ns = std::min(chunk, nscenes - s);
-            if (cudaMemcpyAsync(scn, lr_scenes_host + nsc * s, nsc * ns * sizeof(float), cudaMemcpyHostToDevice, 0) != cudaSuccess) { rc = set_error(PV_ERR_CUDA, "H2D failed"); break; }
-            if ((rc = launch_scene_to_patches(scn, ns, m->T, H, W, m->P, m->cfg.max_shift, m->stage_lr, 0))) break;
-            if ((rc = model_forward(m, m->stage_lr, ns * pps, m->stage_sr, false, 1, 0))) break;
-            if ((rc = launch_stitch(m->stage_sr, ns, n, (int)PP, m->stage_scene, 0))) break;
-            if (cudaMemcpyAsync(sr_scenes_host + nout * pps * s, m->stage_scene, nout * pps * ns * sizeof(float), cudaMemcpyDeviceToHost, 0) != cudaSuccess) { rc = set_error(PV_ERR_CUDA, "D2H failed"); break; }
+    auto drain = [&](int c) {            // chunk c's result: wait for its D2H, then copy pinned -> caller
+        const int slot = c & 1, s0 = c * chunk, ns = std::min(chunk, nscenes - s0);
+        if (cudaEventSynchronize(sp.ev_out[slot]) != cudaSuccess) return set_error(PV_ERR_CUDA, "predict_from_scenes: D2H failed");
+        std::memcpy(sr_scenes_host + nout * pps * s0, sp.pin_out[slot], nout * pps * ns * sizeof(float));
+        return 0;
+    };
+    for (int c = 0; c < nchunks && !rc; ++c) {
+        const int slot = c & 1, s0 = c * chunk, ns = std::min(chunk, nscenes - s0);
+        if (c >= 2 && cudaEventSynchronize(sp.ev_in[slot]) != cudaSuccess) { rc = set_error(PV_ERR_CUDA, "predict_from_scenes: H2D failed"); break; }
+        std::memcpy(sp.pin_in[slot], lr_scenes_host + nsc * s0, nsc * ns * sizeof(float));
+        if (c >= 2) cudaStreamWaitEvent(sp.st_in, sp.ev_patched[slot], 0);       // scn[slot] was consumed by chunk c-2's patching
+        if (cudaMemcpyAsync(sp.scn[slot], sp.pin_in[slot], nsc * ns * sizeof(float), cudaMemcpyHostToDevice, sp.st_in) != cudaSuccess) {
+            rc = set_error(PV_ERR_CUDA, "predict_from_scenes: H2D failed"); break;
         }
-    } while (0);
-    cudaStreamSynchronize(0);
-    cudaFree(scn);
+        cudaEventRecord(sp.ev_in[slot], sp.st_in);
+        cudaStreamWaitEvent(sp.st_c, sp.ev_in[slot], 0);
+        if (c >= 2) cudaStreamWaitEvent(sp.st_c, sp.ev_out[slot], 0);            // out[slot] has left the device (chunk c-2)
+        if ((rc = launch_scene_to_patches(sp.scn[slot], ns, m->T, H, W, m->P, m->cfg.max_shift, m->stage_lr, sp.st_c))) break;
+        cudaEventRecord(sp.ev_patched[slot], sp.st_c);
+        if ((rc = model_forward(m, m->stage_lr, ns * pps, m->stage_sr, false, 1, sp.st_c))) break;
+        if ((rc = launch_stitch(m->stage_sr, ns, n, (int)PP, sp.out[slot], sp.st_c))) break;
+        cudaEventRecord(sp.ev_done[slot], sp.st_c);
+        if (c >= 1) rc = drain(c - 1);                                           // overlaps chunk c's forward pass
+        if (rc) break;
+        cudaStreamWaitEvent(sp.st_out, sp.ev_done[slot], 0);
+        if (cudaMemcpyAsync(sp.pin_out[slot], sp.out[slot], nout * pps * ns * sizeof(float), cudaMemcpyDeviceToHost, sp.st_out) != cudaSuccess) {
+            rc = set_error(PV_ERR_CUDA, "predict_from_scenes: D2H failed"); break;
+        }
+        cudaEventRecord(sp.ev_out[slot], sp.st_out);
+    }
+    if (!rc) rc = drain(nchunks - 1);
+    if (cudaStreamSynchronize(sp.st_c) != cudaSuccess && !rc) rc = set_error(PV_ERR_CUDA, "predict_from_scenes: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaStreamSynchronize(sp.st_in); cudaStreamSynchronize(sp.st_out);
     return rc;
 }
 

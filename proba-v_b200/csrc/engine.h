@@ -59,6 +59,55 @@ struct Pool {
     }
 };
 
+// double-buffered staging of the host-to-host scene prediction path (pv_predict_from_scenes_host)
+struct ScenePipe {
+    float *pin_in[2] = {nullptr, nullptr}, *pin_out[2] = {nullptr, nullptr};   // pinned host
+    float *scn[2] = {nullptr, nullptr}, *out[2] = {nullptr, nullptr};           // device
+    size_t cap_in = 0, cap_out = 0;
+    cudaStream_t st_in = nullptr, st_c = nullptr, st_out = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_patched[2] = {}, ev_done[2] = {}, ev_out[2] = {};
+    bool made = false;
+    int ensure(size_t n_in, size_t n_out) {
+        if (!made) {
+            PV_CUDA(cudaStreamCreateWithFlags(&st_in, cudaStreamNonBlocking));
+            PV_CUDA(cudaStreamCreateWithFlags(&st_c, cudaStreamNonBlocking));
+            PV_CUDA(cudaStreamCreateWithFlags(&st_out, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                PV_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+                PV_CUDA(cudaEventCreateWithFlags(&ev_patched[i], cudaEventDisableTiming));
+                PV_CUDA(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+                PV_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+            }
+            made = true;
+        }
+        if (n_in > cap_in) {
+            for (int i = 0; i < 2; ++i) {
+                cudaFreeHost(pin_in[i]); cudaFree(scn[i]); pin_in[i] = scn[i] = nullptr;
+                PV_CUDA(cudaHostAlloc(&pin_in[i], n_in * sizeof(float), cudaHostAllocDefault));
+                PV_CUDA(cudaMalloc(&scn[i], n_in * sizeof(float)));
+            }
+            cap_in = n_in;
+        }
+        if (n_out > cap_out) {
+            for (int i = 0; i < 2; ++i) {
+                cudaFreeHost(pin_out[i]); cudaFree(out[i]); pin_out[i] = out[i] = nullptr;
+                PV_CUDA(cudaHostAlloc(&pin_out[i], n_out * sizeof(float), cudaHostAllocDefault));
+                PV_CUDA(cudaMalloc(&out[i], n_out * sizeof(float)));
+            }
+            cap_out = n_out;
+        }
+        return 0;
+    }
+    void release() {
+        for (int i = 0; i < 2; ++i) { cudaFreeHost(pin_in[i]); cudaFreeHost(pin_out[i]); cudaFree(scn[i]); cudaFree(out[i]); }
+        if (made) {
+            cudaStreamDestroy(st_in); cudaStreamDestroy(st_c); cudaStreamDestroy(st_out);
+            for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_patched[i]); cudaEventDestroy(ev_done[i]); cudaEventDestroy(ev_out[i]); }
+        }
+        made = false; cap_in = cap_out = 0;
+    }
+};
+
 }  // namespace pv
 
 using pv::Layer;
@@ -84,6 +133,7 @@ struct pv_model {
     bool use_tc = false;               // tcgen05 kernels (precision 1) vs the CUDA-core row kernels (precision 3)
     float *stage_lr = nullptr, *stage_sr = nullptr, *stage_scene = nullptr;   // host-API staging
     size_t stage_lr_n = 0, stage_sr_n = 0, stage_scene_n = 0;
+    pv::ScenePipe scene_pipe;
 
     int li(const std::string& n) const {
         for (size_t i = 0; i < layers.size(); ++i) if (layers[i].name == n) return (int)i;

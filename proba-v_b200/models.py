@@ -157,7 +157,18 @@ class WDSRModel:
         return out
 
     def predict_from_scenes(self, scenesLR) -> np.ndarray:
-        """[nscenes, T, H, W] host LR scenes -> [nscenes, s*H, s*W, 1]; patching + stitching on device."""
+        """[nscenes, T, H, W] LR scenes -> [nscenes, s*H, s*W, 1]; patching + stitching on device.  numpy in -> numpy out
+        (pinned double-buffered transfers overlapped with the forward pass); torch CUDA in -> torch CUDA out (asynchronous)."""
+        if _buf.is_cuda_tensor(scenesLR):
+            import torch
+            x = _buf.dev_tensor(scenesLR, torch.float32, scenesLR.device)
+            ns, T, H, W = x.shape
+            if T != self.T:
+                raise ValueError(f"expected {self.T} LR frames, got {T}")
+            s = self.cfg.scale
+            y = torch.empty((ns, s * H, s * W, 1), dtype=torch.float32, device=x.device)
+            check(lib().pv_predict_from_scenes(self._h, _buf.ptr(x), ns, H, W, _buf.ptr(y), _buf.current_stream_ptr(x.device)))
+            return y
         x = _buf.host_array(scenesLR, np.float32)
         ns, T, H, W = x.shape
         if T != self.T:

@@ -2,6 +2,8 @@
 same strict bars as the dense fp32 engine) and precision "tf32" (tcgen05 tensor-core kernels; the north_star's
 "fp32/TF32" bar of 1e-3 max relative error on SR, loss within 1e-3, cPSNR within 0.01 dB; gradient tolerance stated below).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -222,3 +224,43 @@ def test_fit_loop_prefetch_pipeline_matches_host_batches(small_cfg):
         assert [e.tag for e in ev[1:5]] == ["Train PSNR", "Train loss", "Train PSNR", "Train loss"]
         assert {e.tag for e in ev[1:]} == {"Train PSNR", "Train loss", "Test loss", "Test PSNR"}
     assert np.array_equal(out[0], out[1])
+
+
+def test_train_and_test_entry_points(tmp_path):
+    """train.py -> TF checkpoint + TensorBoard log; test.py restores it and writes stitched 384x384 16-bit PNGs numbered like
+    the reference (test.py:80-99)."""
+    import glob
+    from probav_b200 import cli, tfckpt
+    cfg = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cfg", "p16t9c85r12.cfg")).read().replace("modelInfo", str(tmp_path / "modelInfo")).replace("testout", str(tmp_path / "testout"))
+    cfg = cfg.replace("num_res_blocks=12", "num_res_blocks=2").replace("batch_size=128", "batch_size=16")
+    path = tmp_path / "tiny.cfg"
+    path.write_text(cfg)
+    ckptDir, logDir = cli.train_main(["--cfg", str(path), "--band", "NIR", "--synthetic", "48", "--max-steps", "3"])
+    assert ckptDir == str(tmp_path / "modelInfo" / "ckpt_tiny" / "NIR")
+    prefix = tfckpt.latest_checkpoint(ckptDir)
+    assert prefix and int(tfckpt.BundleReader(prefix).tensor("step/.ATTRIBUTES/VARIABLE_VALUE")) == 3
+    assert glob.glob(logDir + "/events.out.tfevents.*")
+    outDir = cli.test_main(["--cfg", str(path), "--band", "NIR", "--totest", "TEST", "--synthetic", "2"])
+    files = sorted(os.listdir(outDir))
+    assert files == ["imgset1306.png", "imgset1307.png"]
+    img = cli.read_png16(os.path.join(outDir, files[0]))
+    assert img.shape == (384, 384) and 1000 < img.mean() < 20000
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+def test_pipelined_scene_prediction_matches_patch_path(small_cfg, precision):
+    """pv_predict_from_scenes_host (pinned double-buffered chunks on private streams) and pv_predict_from_scenes (device
+    tensors) give the bits of the patch-level path for a scene count that is not a multiple of the chunk (8 scenes)."""
+    import probav_b200 as pb
+    from probav_b200 import synth
+    from oracle.step import scene_to_patches
+    m = pb.WDSRConv3D("n", "NIR", 8075.2045, 3160.7272, 6).build(**small_cfg, seed=7, precision=precision)
+    lr_sc, _, _ = synth.make_scene(19, seed=4)
+    patches = np.stack([scene_to_patches(s) for s in lr_sc])
+    ref = m.predict_scenes(patches)
+    got = m.predict_from_scenes(lr_sc)
+    assert got.shape == (19, 384, 384, 1) and np.array_equal(got, ref)
+    again = m.predict_from_scenes(lr_sc[:3])                       # staging slots are reused across calls
+    assert np.array_equal(again, ref[:3])
+    dev = m.predict_from_scenes(torch.from_numpy(lr_sc).cuda())
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), ref)

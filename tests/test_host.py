@@ -176,3 +176,21 @@ def test_prefetch_loader_propagates_producer_errors():
     with pytest.raises(IndexError):
         for _ in ld:
             pass
+
+
+def test_cli_flags_and_png_writer(tmp_path):
+    """train.py / test.py keep the reference's flags and defaults (train.py:26-32, test.py:25-31); predictions are saved as
+    16-bit grayscale PNGs (test.py:99)."""
+    from probav_b200 import cli
+    a = cli.train_parser().parse_args([])
+    assert (a.cfg, a.band, a.modelType) == ("cfg/yourcfg.cfg", "NIR", "patchNet")
+    b = cli.test_parser().parse_args(["--totest", "TRAIN"])
+    assert (b.cfg, b.band, b.totest) == ("cfg/FINAL.cfg", "RED", "TRAIN")
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 65536, size=(37, 53)).astype(np.float64)
+    p = str(tmp_path / "imgset0001.png")
+    cli.write_png16(p, img)
+    back = cli.read_png16(p)
+    assert back.dtype == np.uint16 and np.array_equal(back, img.astype(np.uint16))
+    with pytest.raises(ValueError):
+        cli.write_png16(p, np.zeros((2, 2, 3)))
