@@ -298,7 +298,8 @@ def run_b200(args, cfg):
                      "note": f"batch {B}: {sl['bytes'] / sl['launches'] / 1e6:.2f} MB per launch is latency-bound; see bench_loss in DESIGN.md"}
     cfg_name = os.path.splitext(os.path.basename(args.cfg))[0]
     is_headline = cfg_name == "p16t9c85r12"
-    workload = (f"cfg/{cfg_name} train step (fwd+shift-L1+bwd+Nadam+cPSNR metric)" + (", BASELINE configs[1]" if is_headline else
+    loss_name = {"l1": "L1", "l2": "L2", "sobel_l1_mix": "L1Edge"}.get(cfg["loss"], cfg["loss"])
+    workload = (f"cfg/{cfg_name} train step (fwd+shift-{loss_name}+bwd+Nadam+cPSNR metric)" + (", BASELINE configs[1]" if is_headline else
                 f", {cfg['num_low_res_imgs']} LR frames, {cfg['num_res_blocks']} blocks"))
     # algorithmic flops per patch: SURVEY Appendix A for the headline graph, else the sum the kernels' launchers report
     gflop_per_patch = TRAIN_GFLOP_PER_PATCH if is_headline else sum(v["flops"] for v in rep.values()) / 2 / B / 1e9

@@ -264,3 +264,61 @@ def test_pipelined_scene_prediction_matches_patch_path(small_cfg, precision):
     assert np.array_equal(again, ref[:3])
     dev = m.predict_from_scenes(torch.from_numpy(lr_sc).cuda())
     assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), ref)
+
+
+def test_full_size_batch_properties_tf32(full_cfg):
+    """BASELINE.json's batch (128 patches, cfg/p16t9c85r12) is too large for the CPU oracle to back-propagate in seconds, so the
+    full-size step is checked through size-independent properties: patches are independent (splitting the batch does not change
+    a single SR bit), the batch gradient is the mean of the half-batch gradients, per-sample losses average to the batch loss,
+    and the whole step is bit-reproducible (fixed-order reductions)."""
+    import probav_b200 as pb
+    from probav_b200 import synth
+    om, p = oracle_and_params(full_cfg, seed=80)
+    m = cuda_model(full_cfg, p, precision="tf32")
+    B = 128
+    lr, hr, mask = synth.make_batch(B, seed=81, hr_zero_under_mask=True)
+    sr = m(lr)
+    assert np.array_equal(sr[:64], m(lr[:64])) and np.array_equal(sr[64:], m(lr[64:]))
+    assert np.array_equal(sr[5:6], m(lr[5:6]))                      # a one-patch batch
+    # the oracle on a 3-patch sample of the same batch
+    ref = om.forward(p, torch.from_numpy(lr[[0, 63, 127]]).double()).numpy()
+    assert rel_err(sr[[0, 63, 127]], ref) < SR_TOL
+    t = _trainer(pb, m)
+    l_all, c_all = t.forward_backward(lr, hr, mask)
+    g_all = t.grad_view().clone()
+    l_again, _ = t.forward_backward(lr, hr, mask)
+    assert l_again == l_all and torch.equal(t.grad_view(), g_all)   # bit-reproducible
+    l_a, c_a = t.forward_backward(lr[:64], hr[:64], mask[:64])
+    g_a = t.grad_view().clone()
+    l_b, c_b = t.forward_backward(lr[64:], hr[64:], mask[64:])
+    g_b = t.grad_view().clone()
+    assert abs(l_all - 0.5 * (l_a + l_b)) < 1e-5 * abs(l_all) and abs(c_all - 0.5 * (c_a + c_b)) < 1e-4
+    g_half = 0.5 * (g_a + g_b)
+    assert float((g_all - g_half).abs().max()) < 2e-4 * float(g_all.abs().max())
+    # per-sample losses of the loss kernel average to the step's loss
+    L = pb.Losses((48, 48, 1))
+    per = L.evaluate("l1", hr, mask, sr)
+    assert abs(float(np.mean(per["loss_per_sample"])) - l_all) < 1e-5 * abs(l_all)
+
+
+@pytest.mark.parametrize("B", [1, 3, 129])
+def test_odd_batch_sizes_after_a_larger_batch(small_cfg, B):
+    """Row buffers are sized for the largest batch seen; a smaller or ragged batch afterwards must not see stale rows."""
+    from probav_b200 import synth
+    import probav_b200 as pb
+    om, p = oracle_and_params(small_cfg, seed=90)
+    m = cuda_model(small_cfg, p, precision="tf32")
+    big, _, _ = synth.make_batch(160, seed=91)
+    m(big)
+    lr, hr, mask = synth.make_batch(B, seed=92 + B, hr_zero_under_mask=True)
+    sel = [0, B // 2, B - 1]
+    ref = om.forward(p, torch.from_numpy(lr[sel]).double()).numpy()
+    assert rel_err(m(lr)[sel], ref) < SR_TOL
+    t = _trainer(pb, m)
+    t.forward_backward(big[:140], np.repeat(hr[:1], 140, 0), np.repeat(mask[:1], 140, 0))
+    l1, _ = t.forward_backward(lr, hr, mask)
+    g1 = t.grad_view().clone()
+    m2 = cuda_model(small_cfg, p, precision="tf32")          # a fresh model that never saw the larger batch
+    t2 = _trainer(pb, m2)
+    l2, _ = t2.forward_backward(lr, hr, mask)
+    assert l1 == l2 and torch.equal(g1, t2.grad_view())
