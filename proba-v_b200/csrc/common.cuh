@@ -85,4 +85,20 @@ struct KernelTimer {
 };
 #define PV_TIMED(name, st, ...) pv::KernelTimer _pv_kt(name, st, ##__VA_ARGS__)
 
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: cache the value set per device ordinal so that
+// a process driving several GPUs (tests on a multi-GPU box) raises the limit on each of them.
+template <typename F>
+inline cudaError_t ensure_dyn_smem(F* func, size_t smem, size_t (&cache)[16]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 15;
+    if (smem > cache[dev]) {
+        const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cache[dev] = smem;
+    }
+    return cudaSuccess;
+}
+
 }  // namespace pv

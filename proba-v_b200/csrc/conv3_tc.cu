@@ -333,8 +333,8 @@ int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st) {
     const int ntiles = a.B * a.chunks * a.nt;
     const int grid = ntiles < sms ? ntiles : sms;
     PV_TIMED(p.tag ? p.tag : "rowconv3_tc", st, p.flops, 0.0);
-    static size_t attr = 0;
-    if (smem > attr) { PV_CUDA(cudaFuncSetAttribute(rowconv3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    static size_t attr[16] = {};
+    PV_CUDA(ensure_dyn_smem(rowconv3_tc_kernel, smem, attr));
     PV_CUDA(launch_pdl(rowconv3_tc_kernel, grid, C3_THREADS, smem, st, tm_x, tm_w, a));
     PV_LAUNCH_CHECK();
     return 0;

@@ -318,12 +318,12 @@ int launch_rowconv_tc(const RowConvP& p, cudaStream_t st) {
     const int grid = ntiles < sms ? ntiles : sms;
     PV_TIMED(p.tag ? p.tag : "rowconv_tc", st, p.flops, 0.0);
     // opt in to the dynamic shared memory this configuration needs (static + dynamic must stay below 227 KB)
-    static size_t attr32 = 0, attr256 = 0;
+    static size_t attr32[16] = {}, attr256[16] = {};
     if (p.n == 32) {
-        if (smem > attr32) { PV_CUDA(cudaFuncSetAttribute(rowconv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr32 = smem; }
+        PV_CUDA(ensure_dyn_smem(rowconv_tc_kernel<32>, smem, attr32));
         PV_CUDA(launch_pdl(rowconv_tc_kernel<32>, grid, TC_THREADS, smem, st, tm_x, tm_w, a));
     } else {
-        if (smem > attr256) { PV_CUDA(cudaFuncSetAttribute(rowconv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr256 = smem; }
+        PV_CUDA(ensure_dyn_smem(rowconv_tc_kernel<256>, smem, attr256));
         PV_CUDA(launch_pdl(rowconv_tc_kernel<256>, grid, TC_THREADS, smem, st, tm_x, tm_w, a));
     }
     PV_LAUNCH_CHECK();

@@ -503,8 +503,8 @@ static int launch_respipe(const float* t, const float* w1, const float* w2, cons
     PV_TRY(make_tmap_2d(&tm_w1, w1, 256, 32, 256, 32, 0));      // [256 rows][32]: We^T (fwd) | Wd (bwd)
     PV_TRY(make_tmap_2d(&tm_w2, w2, 32, 256, 32, 32, 0));       // [32 rows][256]: Wd^T (fwd) | We (bwd)
     const size_t smem = 1024 + 65536 + 3 * 16384 + 8 * ROWIO_SCRATCH_BYTES;
-    static bool attr = false;
-    if (!attr) { PV_CUDA(cudaFuncSetAttribute(resfront_pipe_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    static size_t attr[16] = {};
+    PV_CUDA(ensure_dyn_smem(resfront_pipe_kernel<MODE>, smem, attr));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -567,8 +567,8 @@ int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* 
     PV_TRY(make_tmap_2d(&tm_weT, weT_exp, 256, 32, 256, 32, 0));
     PV_TRY(make_tmap_2d(&tm_wd, w_dec, 256, 32, 256, 32, 0));
     const size_t smem = 1024 + 65536 + 2 * 65536;
-    static bool attr = false;
-    if (!attr) { PV_CUDA(cudaFuncSetAttribute(resfront_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    static size_t attr[16] = {};
+    PV_CUDA(ensure_dyn_smem(resfront_bwd_weight_kernel, smem, attr));
     {
         PV_TIMED("resfront_bwd_weight", st, flops, 0.0);
         PV_CUDA(launch_pdl(resfront_bwd_weight_kernel, grid, RP_THREADS, smem, st, tm_x, tm_gd, tm_x32, tm_gd32, tm_weT, tm_wd, a));

@@ -4,6 +4,7 @@
 // layers that are not tensor-core shaped (mainConv1, Cin = 1) and as the on-device cross-check of each tcgen05
 // kernel (pv_selftest), and (b) the layout glue between the PR trunk and the valid-conv tail.
 // Reference semantics: Keras Conv3D inside TFA WeightNormalization (modelsTF.py:191-197), tf.pad REFLECT (:157-158).
+#include <cstdlib>
 #include "wgrad_reduce.cuh"
 #include "rows.h"
 
@@ -310,6 +311,84 @@ __global__ void __launch_bounds__(256) first_conv_pr_wgrad_kernel(const float* _
     if (warp < 4) out[(warp + 24) * 32 + lane] = acc[3];
 }
 
+// Second formulation (the one launched for S = 22 when the partial budget allows it): a work item is (patch, chunk of temporal
+// planes).  The item's normalised LR window is staged zero-padded in shared memory exactly as in the forward kernel; lane =
+// output channel, a warp owns whole image lines (t, h): it first issues the line's S coalesced 128-byte gradient-row loads
+// (S independent loads in flight per lane), then for each (dt, dh) reads the S + 2 inputs of that line once (broadcast LDS)
+// and forms 3 S FMAs per lane -- 0.4 loads per FMA instead of 1.25, no scattered global gathers, no integer divisions in the
+// inner loop.  Each warp keeps all 28 x 32 sums (27 taps + bias) in registers over every item of its CTA; the 8 warps are
+// summed in a fixed order at the end and the CTA writes ONE partial [28][32] (layout of the kernel above, same reduction).
+template <int S>
+__global__ void __launch_bounds__(256) first_conv_pr_wgrad_items_kernel(const float* __restrict__ xn, const float* __restrict__ gz,
+                                                                        int B, int T, int tchunks, RowGeom g,
+                                                                        float* __restrict__ partials) {
+    pdl_grid_wait();
+    extern __shared__ float fsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tchunk = (T + tchunks - 1) / tchunks;
+    constexpr int Sp = S + 2, wp = Sp + 1;
+    float acc[28];
+#pragma unroll
+    for (int k = 0; k < 28; ++k) acc[k] = 0.f;
+    for (int item = blockIdx.x; item < B * tchunks; item += gridDim.x) {
+        const int b = item / tchunks, tc0 = (item % tchunks) * tchunk, tcn = min(tchunk, T - tc0);
+        if (tcn <= 0) continue;
+        const int Tp = tcn + 2;
+        __syncthreads();                                            // the previous item's window is no longer read
+        for (int i = threadIdx.x; i < Tp * Sp * wp; i += 256) fsm[i] = 0.f;
+        __syncthreads();
+        for (int i = threadIdx.x; i < S * S * T; i += 256) {        // xn is [h][w][t]
+            const int t = i % T, ww = (i / T) % S, hh = i / (T * S);
+            const int tl = t - tc0 + 1;
+            if (tl >= 0 && tl < Tp) fsm[(tl * Sp + hh + 1) * wp + ww + 1] = __ldg(xn + (size_t)b * S * S * T + i);
+        }
+        __syncthreads();
+        const float* gzb = gz + (g.lead + (long long)b * g.pstride + (long long)(g.t0 + tc0) * g.plane) * 32 + lane;
+#pragma unroll 1
+        for (int line = warp; line < tcn * S; line += 8) {
+            const int tt = line / S, hh = line % S;
+            const float* gp = gzb + ((long long)tt * g.plane + hh * g.pw) * 32;
+            float gv[S];
+#pragma unroll
+            for (int w = 0; w < S; ++w) gv[w] = __ldg(gp + w * 32);
+            float bs = 0.f;
+#pragma unroll
+            for (int w = 0; w < S; ++w) bs += gv[w];
+            acc[27] += bs;
+#pragma unroll
+            for (int dt = 0; dt < 3; ++dt)
+#pragma unroll
+                for (int dh = 0; dh < 3; ++dh) {
+                    const float* xp = fsm + ((tt + dt) * Sp + hh + dh) * wp;           // padded line: tap dw of voxel w is xp[w + dw]
+                    float xv[S + 2];
+#pragma unroll
+                    for (int w = 0; w < S + 2; ++w) xv[w] = xp[w];
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < S; ++w) {
+                        a0 = fmaf(xv[w], gv[w], a0);
+                        a1 = fmaf(xv[w + 1], gv[w], a1);
+                        a2 = fmaf(xv[w + 2], gv[w], a2);
+                    }
+                    float* a3 = acc + (dt * 3 + dh) * 3;
+                    a3[0] += a0; a3[1] += a1; a3[2] += a2;
+                }
+        }
+    }
+    __syncthreads();
+    float* red = fsm;                                               // [8 warps][28][32]
+#pragma unroll
+    for (int k = 0; k < 28; ++k) red[(warp * 28 + k) * 32 + lane] = acc[k];
+    __syncthreads();
+    float* out = partials + (size_t)blockIdx.x * (28 * 32);
+    for (int i = threadIdx.x; i < 28 * 32; i += 256) {
+        float s0 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s0 += red[w * 28 * 32 + i];
+        out[i] = s0;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 first_conv_pr_wgrad_reduce_kernel(const float* __restrict__ partials, int ncta, float* __restrict__ dw, float* __restrict__ db) {
     __shared__ float4 sm[256];     // 7 blocks x 32 float4 columns = the 28 x 32 outputs (27 taps + bias); fixed order (wgrad_reduce.cuh)
@@ -451,8 +530,8 @@ int launch_rowwgrad_simt(const RowWgradP& p, cudaStream_t st) {
 int launch_first_conv_pr(const float* xn, const float* w, const float* bias, int B, int S, int T, float* y, RowGeom g, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)(T + 2) * (S + 2) * (S + 3) + 27 * 32 + 32);
     if (smem > 200 * 1024) return set_error(PV_ERR_BAD_ARG, "first_conv_pr: patch of %dx%dx%d does not fit in shared memory", S, S, T);
-    static size_t attr = 0;
-    if (smem > attr) { PV_CUDA(cudaFuncSetAttribute(first_conv_pr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    static size_t attr[16] = {};
+    PV_CUDA(ensure_dyn_smem(first_conv_pr_kernel, smem, attr));
     PV_TIMED("first_conv_pr", st, 2.0 * B * T * S * S * 27 * 32, 0.0);
     PV_CUDA(launch_pdl_simple(first_conv_pr_kernel, dim3(B, 1), 256, smem, st, xn, w, bias, B, S, T, y, g));
     PV_LAUNCH_CHECK();
@@ -461,12 +540,28 @@ int launch_first_conv_pr(const float* xn, const float* w, const float* bias, int
 
 int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, int T, RowGeom g, float* dw, float* db,
                                float* partials, size_t partial_floats, cudaStream_t st, ReduceQueue* rq) {
-    const int grid = 148 * 4;
+    const int max_grid = 148 * 4;                                   // partial budget of the trainer's arena (engine.cu)
+    // items = (patch, chunk of planes): three chunks per patch while that fits the partial budget (B <= 197), else fewer
+    int tchunks = 3;
+    while (tchunks > 1 && (long long)B * tchunks > max_grid) --tchunks;
+    if (tchunks > T) tchunks = T;
+    const int tchunk = (T + tchunks - 1) / tchunks;
+    const size_t smem_win = sizeof(float) * (size_t)(tchunk + 2) * (S + 2) * (S + 3), smem_red = sizeof(float) * 8 * 28 * 32;
+    const size_t smem = smem_win > smem_red ? smem_win : smem_red;
+    const bool items = S == 22 && getenv("PV_FIRST_WGRAD_V1") == nullptr && smem <= 200 * 1024;
+    const long long nitems = (long long)B * tchunks;
+    const int grid = items ? (int)(nitems < max_grid ? nitems : max_grid) : max_grid;
     float* deferred = rq ? rq->take((size_t)grid * 28 * 32) : nullptr;
     if (deferred) { partials = deferred; partial_floats = (size_t)grid * 28 * 32; }
     if (!partials || partial_floats < (size_t)grid * 28 * 32) return set_error(PV_ERR_BAD_ARG, "first_conv_pr_wgrad: partial buffer too small");
     PV_TIMED("first_conv_pr_wgrad", st, 2.0 * B * T * S * S * 27 * 32, 0.0);
-    PV_CUDA(launch_pdl_simple(first_conv_pr_wgrad_kernel, grid, 256, 0, st, xn, gz, B, S, T, g, partials));
+    if (items) {
+        static size_t attr[16] = {};
+        PV_CUDA(ensure_dyn_smem(first_conv_pr_wgrad_items_kernel<22>, smem, attr));
+        PV_CUDA(launch_pdl_simple(first_conv_pr_wgrad_items_kernel<22>, grid, 256, smem, st, xn, gz, B, T, tchunks, g, partials));
+    } else {
+        PV_CUDA(launch_pdl_simple(first_conv_pr_wgrad_kernel, grid, 256, 0, st, xn, gz, B, S, T, g, partials));
+    }
     PV_LAUNCH_CHECK();
     if (deferred) {
         ReduceJob j;

@@ -200,8 +200,8 @@ int launch_skip2d_fwd(const float* mn, const float* w1, const float* b1, const f
     Skip2dShape sh{S, C};
     const size_t smem = sizeof(float) * ((size_t)S * S + (size_t)(sh.s1() * sh.s1() + sh.s2() * sh.s2() + sh.s3() * sh.s3()) * C +
                                          sh.nw1() + 2 * sh.nw2() + 3 * C);
-    static size_t attr = 0;
-    if (smem > attr) { PV_CUDA(cudaFuncSetAttribute(skip2d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    static size_t attr[16] = {};
+    PV_CUDA(ensure_dyn_smem(skip2d_fwd_kernel, smem, attr));
     PV_TIMED("skip2d_fwd", st, 2.0 * B * C * (9.0 * sh.s1() * sh.s1() + 9.0 * C * (sh.s2() * sh.s2() + sh.s3() * sh.s3())), 0.0);
     PV_CUDA(launch_pdl_simple(skip2d_fwd_kernel, B, SK_THREADS, smem, st, mn, w1, b1, w2, b2, w3, b3, sh, q1, q2, q3));
     PV_LAUNCH_CHECK();
@@ -218,8 +218,8 @@ int launch_skip2d_bwd(const float* mn, const float* q1, const float* q2, const f
     if (deferred) { partials = deferred; partial_floats = skip2d_partial_floats(B, S, C); }
     if (!partials || partial_floats < skip2d_partial_floats(B, S, C)) return set_error(PV_ERR_BAD_ARG, "skip2d_bwd: partial buffer too small");
     const size_t smem = sizeof(float) * ((size_t)S * S + (size_t)(2 * sh.s1() * sh.s1() + 2 * sh.s2() * sh.s2() + sh.s3() * sh.s3()) * C + 2 * sh.nw2());
-    static size_t attr = 0;
-    if (smem > attr) { PV_CUDA(cudaFuncSetAttribute(skip2d_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    static size_t attr[16] = {};
+    PV_CUDA(ensure_dyn_smem(skip2d_bwd_kernel, smem, attr));
     {
         PV_TIMED("skip2d_bwd", st, 4.0 * B * C * (9.0 * sh.s1() * sh.s1() + 9.0 * C * (sh.s2() * sh.s2() + sh.s3() * sh.s3())), 0.0);
         PV_CUDA(launch_pdl_simple(skip2d_bwd_kernel, B, SK_THREADS, smem, st, mn, q1, q2, g3, w2, w3, sh, partials));

@@ -259,8 +259,8 @@ int launch_rowwgrad_tc(const RowWgradP& p, cudaStream_t st, float* partials, siz
     CUtensorMap tm_a, tm_b;
     PV_TRY(make_tmap_2d(&tm_a, amat, a_rows, acols, a.abox_rows, 32, 1));
     PV_TRY(make_tmap_2d(&tm_b, bmat, b_rows, 32, a.bbox_rows, 32, 1));
-    static size_t attr = 0;
-    if (smem > attr) { PV_CUDA(cudaFuncSetAttribute(rowwgrad_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    static size_t attr[16] = {};
+    PV_CUDA(ensure_dyn_smem(rowwgrad_tc_kernel<0>, smem, attr));
     {
         PV_TIMED(p.tag ? p.tag : "rowwgrad_tc", st, p.flops, 0.0);
         PV_CUDA(launch_pdl(rowwgrad_tc_kernel<0>, grid, WG_THREADS, smem, st, tm_a, tm_b, a));
