@@ -133,7 +133,9 @@ def run_reference(args, cfg):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg/p16t9c85r12 train step (fwd+shift-L1+bwd+Nadam+cPSNR metric)", "batch_per_step": b,
+            "config": {"workload": "cfg/p16t9c85r12 train step (fwd+shift-L1+bwd+Nadam+cPSNR metric), BASELINE configs[1]",
+                       "batch_per_gpu": cfg["batch_size"], "global_batch": cfg["batch_size"], "parallelism": "host cores",
+                       "sample_batch_per_step": b,
                        "note": "TensorFlow/TFA are not installable here (no wheels, no network): the reference arm is the "
                                "oracle, a PyTorch-CPU restatement of models/modelsTF.py + loss.py + trainClass.py"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
