@@ -40,7 +40,8 @@ __device__ __forceinline__ float rna_tf32(float x) {
 __device__ __forceinline__ uint32_t tf32_bump(uint32_t bits) { return bits + 0x1000u; }
 
 // ----------------------------------------------------------------------------------------------------------------
-// Forward and backward-data share one kernel (MODE 0 / 1): both are
+// Forward and backward-data share one kernel (MODE 0 = training forward, 1 = backward-data, 2 = inference forward: the same
+// as 0 without the ReLU bit mask, i.e. 3 instead of 5 instructions per expanded element in the epilogue): both are
 //     MMA1 (SS)  H_h[128 x 128] = T[128 x 32] . W1_h^T      T = X (fwd) | gD (bwd);  W1 = We^T (fwd) | Wd (bwd)
 //     epilogue   H_h <- f(H_h) in place in TMEM               fwd: tf32(relu(. + be)), emits the ReLU bit mask (32 B / row)
 //                                                             bwd: tf32(.) where the forward's mask bit is set, else 0
@@ -89,7 +90,7 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
         mbar_init(BAR(WBAR), 1);
         fence_mbar_init();
     }
-    if (MODE == 0) {
+    if (MODE != 1) {
         for (int i = threadIdx.x; i < 256; i += RP_THREADS) s_b1[i] = a.bias1[i];
         if (threadIdx.x < 32) s_b2[threadIdx.x] = a.bias2[threadIdx.x];
     }
@@ -226,6 +227,16 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                             }
                         }
                         wd[c] = ~((sg[0] << 24) | ((sg[1] & 0xffu) << 16) | ((sg[2] & 0xffu) << 8) | (sg[3] & 0xffu));
+                    } else if (MODE == 2) {
+                        const float4* be4 = reinterpret_cast<const float4*>(s_b1 + h * 128 + c * 32);
+#pragma unroll
+                        for (int e4 = 0; e4 < 8; ++e4) {
+                            const float4 bq = be4[e4];
+                            const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                cur[e4 * 4 + e] = tf32_bump(__float_as_uint(fmaxf(__uint_as_float(cur[e4 * 4 + e]) + bb[e], 0.f)));
+                        }
                     } else {
                         const uint32_t bits = wd[c];
 #pragma unroll
@@ -267,7 +278,7 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                     float* o = out_row + 4 * g4;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) o[e] = __uint_as_float(v[g4 * 4 + e]);
-                    if (MODE == 0) {
+                    if (MODE != 1) {
                         const float4 bq = reinterpret_cast<const float4*>(s_b2)[g4];
                         o[0] += bq.x; o[1] += bq.y; o[2] += bq.z; o[3] += bq.w;
                     } else {
@@ -525,6 +536,7 @@ int launch_resfront_fwd_tc(const float* x, const float* weT_exp, const float* we
     ResPipeArgs a;
     memset(&a, 0, sizeof a);
     a.B = B; a.g = g; a.bias1 = bias_e; a.bias2 = bias_d; a.mask = relu_bits; a.out = d; a.round_tf32 = round_tf32;
+    if (!relu_bits) return launch_respipe<2>(x, weT_exp, weT_dec, a, "resfront_fwd_infer", flops, st);
     return launch_respipe<0>(x, weT_exp, weT_dec, a, "resfront_fwd", flops, st);
 }
 
