@@ -48,3 +48,16 @@ class Enhancer:
 
     def reconstruct(self, patches):
         return reconstruct_from_patches(np.asarray(patches))
+
+
+def calcRelativePSNR(patchPredOne, patchPredTwo, patchHR):
+    """evaluate.py:76-87: shift-compensated cPSNR of two candidate reconstructions against the same (masked-array) HR scenes,
+    [N, P, P, 1] each -> two [N] arrays.  The mask convention is the reference's: clear = ~patchHR.mask."""
+    from .loss import Losses
+    P = np.asarray(patchPredOne).shape[2]
+    loss = Losses(targetShape=(P, P, 1))
+    clear = ~np.ma.getmaskarray(patchHR)
+    hr = np.asarray(np.ma.getdata(patchHR), np.float32)
+    one = loss.shiftCompensatedcPSNR(hr, clear, np.asarray(patchPredOne, np.float32))
+    two = loss.shiftCompensatedcPSNR(hr, clear, np.asarray(patchPredTwo, np.float32))
+    return np.asarray(one), np.asarray(two)
