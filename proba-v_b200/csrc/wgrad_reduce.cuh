@@ -38,6 +38,9 @@ __device__ __forceinline__ void wgrad_reduce_body(int blk, const float* __restri
     const int total = ngroup * 4096;
     const int nmain = total / 128;
     if (blk < nmain) {
+        // conv3 partials are [group][128 = 4 x 32][32] with only three of the four 32-row quarters holding dw taps: the blocks
+        // of the fourth quarter have nothing to sum (and the producer does not store it)
+        if (mode == 0 && (blk & 31) >= 24) return;
         const float4 s = block_rowsum4<8>(partials, ncta, [total](int r) { return (size_t)r * total; }, blk * 32, true, sm);
         if (threadIdx.x >= 32) return;
         const float v[4] = {s.x, s.y, s.z, s.w};

@@ -162,6 +162,7 @@ rowwgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         tc_fence_after();
         float* out = a.partials + (size_t)blockIdx.x * a.ngroup * 4096;
         for (int g = 0; g < a.ngroup; ++g) {
+            if (a.nn == 96 && q == 3) break;                  // conv3: lanes 96..127 are the unused fourth dw slot (never reduced)
             uint32_t v[32];
             tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + g * 32, v);
             tmem_ld_wait();
