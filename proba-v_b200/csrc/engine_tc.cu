@@ -255,18 +255,28 @@ static int selftest_resfront(std::string& rep) {
     q.in_lead = pr.lead; q.in_pstride = pr.pstride; q.og = pr; q.ntap = 8; q.kc = 32;
     for (int j = 0; j < 8; ++j) { q.c0[j] = 32 * j; q.wr0[j] = 32 * j; }
     if (!rc) rc = launch_rowconv_simt(q, 0);
-    if (!rc) rc = launch_resfront_fwd_tc(x, weT, wdT, be, bd, d1, nullptr, pr, B, 0, 0.0, 0);
-    if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest resfront: %s", cudaGetErrorString(cudaGetLastError()));
-    double worst = 0; size_t bad = 0;
-    if (!rc) {
-        std::vector<float> a(rows * 32), c2(rows * 32);
-        cudaMemcpy(a.data(), d0, rows * 32 * 4, cudaMemcpyDeviceToHost); cudaMemcpy(c2.data(), d1, rows * 32 * 4, cudaMemcpyDeviceToHost);
-        for (size_t i = 0; i < rows * 32; ++i) { const double dd = std::fabs((double)a[i] - c2[i]); if (!(dd <= 1e-3)) ++bad; if (dd > worst || dd != dd) worst = dd; }
+    // both forward variants: inference (no ReLU bit mask) and training (bit mask written)
+    uint32_t* bits = nullptr;
+    PV_CUDA(cudaMalloc(&bits, rows * 32));
+    size_t bad = 0;
+    for (int variant = 0; variant < 2; ++variant) {
+        PV_CUDA(cudaMemset(d1, 0, rows * 32 * 4));
+        if (!rc) rc = launch_resfront_fwd_tc(x, weT, wdT, be, bd, d1, variant ? bits : nullptr, pr, B, 0, 0.0, 0);
+        if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest resfront: %s", cudaGetErrorString(cudaGetLastError()));
+        double worst = 0; size_t badv = 0;
+        if (!rc) {
+            std::vector<float> a(rows * 32), c2(rows * 32);
+            cudaMemcpy(a.data(), d0, rows * 32 * 4, cudaMemcpyDeviceToHost); cudaMemcpy(c2.data(), d1, rows * 32 * 4, cudaMemcpyDeviceToHost);
+            for (size_t i = 0; i < rows * 32; ++i) { const double dd = std::fabs((double)a[i] - c2[i]); if (!(dd <= 1e-3)) ++badv; if (dd > worst || dd != dd) worst = dd; }
+        }
+        char line[256];
+        snprintf(line, sizeof line, "%-34s %s max|tc - simt| = %.3g, mismatches %zu of %zu%s%s\n",
+                 variant ? "fused exp->relu->dec fwd (train)" : "fused exp->relu->dec fwd (infer)", (!rc && badv == 0) ? "PASS" : "FAIL",
+                 worst, badv, rows * 32, rc ? " : " : "", rc ? last_error().c_str() : "");
+        rep += line;
+        bad += badv;
     }
-    char line[256];
-    snprintf(line, sizeof line, "%-34s %s max|tc - simt| = %.3g, mismatches %zu of %zu%s%s\n", "fused exp->relu->dec fwd", (!rc && bad == 0) ? "PASS" : "FAIL",
-             worst, bad, rows * 32, rc ? " : " : "", rc ? last_error().c_str() : "");
-    rep += line;
+    cudaFree(bits);
     cudaFree(x); cudaFree(we); cudaFree(weT); cudaFree(wd); cudaFree(wdT); cudaFree(be); cudaFree(bd); cudaFree(E); cudaFree(d0); cudaFree(d1);
     return (!rc && bad == 0) ? 0 : 1;
 }
