@@ -205,6 +205,11 @@ class ModelTrainer:
         if not sync and _buf.is_cuda_tensor(out):
             return out
         lossv, psnrv = float(out[0]), float(out[1])
+        if not sync:            # host arrays in: the C-ABI host entry already synchronised; the fit loop folds the values itself
+            if ws > 1:
+                lossv, psnrv = parallel.reduce_metrics(lossv, psnrv, int(patchLR.shape[0]), device=getattr(out, "device", None))
+            self._last_host = (lossv, psnrv)
+            return None
         if ws > 1:
             lossv, psnrv = parallel.reduce_metrics(lossv, psnrv, int(patchLR.shape[0]), device=out.device)
         self.trainLoss(lossv)
@@ -316,8 +321,31 @@ class ModelTrainer:
             batches = host_batches()
         logger.info("[ INFO ] Begin training...")
         done = 0
+        # The reference reads the running means back on every step (logger + tf.summary, trainClass.py:96-102), which would drain
+        # the GPU once per step.  Here the step's [loss, cPSNR] (summed over ranks on the device) is copied to pinned memory
+        # asynchronously and folded into the means -- and logged, with the same values and step numbers -- one iteration later,
+        # after the NEXT step has been queued; evaluation, epoch boundaries and the end of the loop flush it first.
+        pending = None
+
+        def finish(p):
+            if p is None:
+                return None
+            ev, host, n_glob, p_step, p_gstep, p_epoch = p
+            if ev is not None:
+                ev.synchronize()
+            lossv, psnrv = float(host[0]) / n_glob, float(host[1]) / n_glob
+            self.trainLoss(lossv)
+            self.trainPSNR(psnrv)
+            if logEvery and (p_step % logEvery == 0) and rank == 0:
+                logger.info(f"[ EPOCH {p_epoch}/{epochs} ] - [ STEP {p_step}/{totalSteps} ] Loss: {self.trainLoss.result():.6f}, "
+                            f"cPSNR: {self.trainPSNR.result():.3f}")
+            self._scalar("Train PSNR", self.trainPSNR.result(), p_gstep)
+            self._scalar("Train loss", self.trainLoss.result(), p_gstep)
+            return None
+
         for gb, (xb, yb, mb) in batches:
             if totalSteps - step == 0:
+                pending = finish(pending)
                 epoch += 1
                 step = self.step % totalSteps
                 logger.info(f"[ ***************  NEW EPOCH  *************** ] Epoch number {epoch}")
@@ -325,14 +353,17 @@ class ModelTrainer:
                     mtr.reset_states()
             step += 1
             globalStep += 1
-            self.trainStep(xb, yb, mb, global_batch=gb)
+            out = self.trainStep(xb, yb, mb, global_batch=gb, sync=False)
             self.step += 1
-            if logEvery and (step % logEvery == 0) and rank == 0:
-                logger.info(f"[ EPOCH {epoch}/{epochs} ] - [ STEP {step}/{totalSteps} ] Loss: {self.trainLoss.result():.6f}, "
-                            f"cPSNR: {self.trainPSNR.result():.3f}")
-            self._scalar("Train PSNR", self.trainPSNR.result(), globalStep)
-            self._scalar("Train loss", self.trainLoss.result(), globalStep)
+            if _buf.is_cuda_tensor(out):
+                cur = (*self._metrics_async(out, int(xb.shape[0]), gb), step, globalStep, epoch)
+                finish(pending)                    # the previous step's numbers, while this step runs
+                pending = cur
+            else:                                  # host path (prefetch=False with numpy batches): trainStep already synchronised
+                pending = finish(pending)
+                finish((None, [self._last_host[0], self._last_host[1]], 1, step, globalStep, epoch))
             if step != 0 and (step % self.evalStep) == 0:
+                pending = finish(pending)
                 self.testLoss.reset_states()
                 self.testPSNR.reset_states()
                 Xv, yv, mv = valData
@@ -356,8 +387,26 @@ class ModelTrainer:
             done += 1
             if maxSteps and done >= maxSteps:
                 break
+        pending = finish(pending)
         if self._scalars:
             self._scalars.flush()
+
+    def _metrics_async(self, out_dev, n_local: int, n_global: int):
+        """[loss, cPSNR] of this rank's shard (device) -> pinned host [sum loss, sum cPSNR] over the GLOBAL batch, asynchronously:
+        returns (event, pinned tensor, n_global).  Two pinned slots alternate, so a slot is read before it is reused."""
+        import torch
+        if not hasattr(self, "_mslots"):
+            self._mslots = [torch.empty(2, dtype=torch.float64).pin_memory() for _ in range(2)]
+            self._mslot = 0
+        v = out_dev.double() * float(n_local)
+        if parallel.world()[1] > 1:
+            parallel.allreduce_sum_(v)
+        host = self._mslots[self._mslot]
+        self._mslot ^= 1
+        host.copy_(v, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(out_dev.device))
+        return ev, host, n_global
 
     def close(self):
         if getattr(self, "_h", None):
