@@ -81,9 +81,12 @@ def read_records(path: str, verify: bool = True) -> Iterator[bytes]:
     pos = 0
     while pos + 12 <= len(b):
         (ln,) = struct.unpack("<Q", b[pos:pos + 8])
-        if pos + 16 + ln > len(b):
+        if ln and pos + 16 + ln > len(b):
             break                                      # truncated tail (a writer that was killed): what TF's reader tolerates too
         payload = b[pos + 12:pos + 12 + ln]
+        if ln == 0 and not any(b[pos:]):
+            break                                      # zero-filled tail: blocks the file system pre-allocated for a writer that
+                                                       # died (one of the reference's own logs ends like this)
         if verify:
             if unmask_crc(struct.unpack("<I", b[pos + 8:pos + 12])[0]) != crc32c(b[pos:pos + 8]):
                 raise ValueError(f"{path}: length crc mismatch at {pos}")
