@@ -34,7 +34,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("PV_NVCC_FLAGS", "").split(), "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()
