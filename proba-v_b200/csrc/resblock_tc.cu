@@ -54,6 +54,14 @@ __device__ __forceinline__ uint32_t tf32_bump(uint32_t bits) { return bits + 0x1
 // is what makes re-using an H buffer three units later safe without another barrier.  Two epilogue groups of four
 // warps take alternate tiles.
 constexpr int RP_THREADS = 320;
+// Epilogue groups (of four warps) of the forward / backward-data kernel: template parameter G.  The backward-data kernel runs
+// three groups taking every third tile (448 threads, 128 registers; measured 0.917 -> 0.857 ms per step), the forward kernels two
+// (three were 2 % slower there).  With three groups a group returns to the same H buffer two barrier phases later, which a
+// parity wait cannot tell from "already complete", so the "H ready" barriers are then indexed by u mod 6: every barrier has
+// ONE waiting group and consecutive phases.  (The accumulator barriers are safe: tcgen05 commits arrive in issue order.)
+constexpr int respipe_groups(int mode) { return mode == 1 ? 3 : 2; }
+constexpr int respipe_threads(int g) { return 64 + 128 * g; }
+constexpr int respipe_nef(int g) { return g == 2 ? 3 : 2 * g; }       // number of "H ready" (EFULL) barriers
 
 struct ResPipeArgs {
     int B, tiles_per_patch;
@@ -68,11 +76,12 @@ struct ResPipeArgs {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(RP_THREADS, 1)
+__global__ void __launch_bounds__(respipe_threads(respipe_groups(MODE)), 1)
 resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant__ CUtensorMap tm_w1,
                      const __grid_constant__ CUtensorMap tm_w2, const ResPipeArgs a) {
+    constexpr int RPG = respipe_groups(MODE), RPP_THREADS = respipe_threads(RPG), NEF = respipe_nef(RPG);
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[17];
+    __shared__ __align__(8) uint64_t bars[14 + NEF];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_b1[256];
     __shared__ __align__(16) float s_b2[32];
@@ -83,15 +92,16 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
     uint8_t* const io_scratch = smem_raw + (base - smem_u32(smem_raw)) + 65536 + 3 * 16384;   // 8 epilogue warps x 2 KB (rowio.cuh)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto BAR = [&](int i) { return smem_u32(&bars[i]); };
-    const int FULL = 0, EMPTY = 3, WBAR = 6, EFULL = 7, EREADY = 10, DFULL = 13, DFREE = 15;
+    const int FULL = 0, EMPTY = 3, WBAR = 6, EFULL = 7, EREADY = 7 + NEF, DFULL = 10 + NEF, DFREE = 12 + NEF;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); mbar_init(BAR(EFULL + i), 1); mbar_init(BAR(EREADY + i), 4); }
+        for (int i = 0; i < 3; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); mbar_init(BAR(EREADY + i), 4); }
+        for (int i = 0; i < NEF; ++i) mbar_init(BAR(EFULL + i), 1);
         for (int i = 0; i < 2; ++i) { mbar_init(BAR(DFULL + i), 1); mbar_init(BAR(DFREE + i), 4); }
         mbar_init(BAR(WBAR), 1);
         fence_mbar_init();
     }
     if (MODE != 1) {
-        for (int i = threadIdx.x; i < 256; i += RP_THREADS) s_b1[i] = a.bias1[i];
+        for (int i = threadIdx.x; i < 256; i += RPP_THREADS) s_b1[i] = a.bias1[i];
         if (threadIdx.x < 32) s_b2[threadIdx.x] = a.bias2[threadIdx.x];
     }
     if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
@@ -138,7 +148,7 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) umma_ss_tf32_lohi(tmem + eb * 128, t_lo + 2 * ks, w_lo + 2 * ks, HI32, IDESC1, ks > 0);
                     if (h == 1) umma_commit(BAR(EMPTY + stg));
-                    umma_commit(BAR(EFULL + eb));
+                    umma_commit(BAR(EFULL + u % NEF));
                 }
                 if (u >= 1) {                       // MMA2 of unit u - 1
                     const int v = u - 1, tl = v >> 1, h = v & 1;
@@ -169,7 +179,7 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
         };
         uint4 nlo = make_uint4(0u, 0u, 0u, 0u), nhi = nlo;
         if (MODE == 1 && grp < my_tiles) { const uint4* mp = mask_row(grp); nlo = __ldg(mp); nhi = __ldg(mp + 1); }
-        for (int tl = grp; tl < my_tiles; tl += 2) {
+        for (int tl = grp; tl < my_tiles; tl += RPG) {
             const int tile = blockIdx.x + tl * gridDim.x;
             const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
             const int r = a.g.row0 + j * 128 + q * 32 + lane;
@@ -186,7 +196,7 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
             uint8_t* const sc = io_scratch + (warp - 2) * ROWIO_SCRATCH_BYTES;
             if (MODE == 1) {
                 mlo = nlo; mhi = nhi;
-                if (tl + 2 < my_tiles) { const uint4* mp = mask_row(tl + 2); nlo = __ldg(mp); nhi = __ldg(mp + 1); }
+                if (tl + RPG < my_tiles) { const uint4* mp = mask_row(tl + RPG); nlo = __ldg(mp); nhi = __ldg(mp + 1); }
                 if (a.residual) rowio_ldg_chunks(a.residual + orow_w * 32, rowmask, pre_r);
                 else {
 #pragma unroll
@@ -199,7 +209,7 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                 const uint32_t eb = u % 3, hb = lane_base + eb * 128;
                 uint4 w4 = h ? mhi : mlo;
                 uint32_t wd[4] = {w4.x, w4.y, w4.z, w4.w};
-                mbar_wait(BAR(EFULL + eb), (u / 3) & 1);
+                mbar_wait(BAR(EFULL + u % NEF), (u / NEF) & 1);
                 tc_fence_after();
                 uint32_t va[32], vb[32];
                 tmem_ld32(hb, va);
@@ -513,7 +523,7 @@ static int launch_respipe(const float* t, const float* w1, const float* w2, cons
     PV_TRY(make_tmap_2d(&tm_t, t, rows, 32, 128, 32, 0));
     PV_TRY(make_tmap_2d(&tm_w1, w1, 256, 32, 256, 32, 0));      // [256 rows][32]: We^T (fwd) | Wd (bwd)
     PV_TRY(make_tmap_2d(&tm_w2, w2, 32, 256, 32, 32, 0));       // [32 rows][256]: Wd^T (fwd) | We (bwd)
-    const size_t smem = 1024 + 65536 + 3 * 16384 + 8 * ROWIO_SCRATCH_BYTES;
+    const size_t smem = 1024 + 65536 + 3 * 16384 + 4 * respipe_groups(MODE) * ROWIO_SCRATCH_BYTES;
     static size_t attr[16] = {};
     PV_CUDA(ensure_dyn_smem(resfront_pipe_kernel<MODE>, smem, attr));
     int dev = 0, sms = 148;
@@ -522,7 +532,7 @@ static int launch_respipe(const float* t, const float* w1, const float* w2, cons
     const int ntiles = a.B * a.tiles_per_patch;
     const int grid = ntiles < sms ? ntiles : sms;
     PV_TIMED(tag, st, flops, 0.0);
-    PV_CUDA(launch_pdl(resfront_pipe_kernel<MODE>, grid, RP_THREADS, smem, st, tm_t, tm_w1, tm_w2, a));
+    PV_CUDA(launch_pdl(resfront_pipe_kernel<MODE>, grid, respipe_threads(respipe_groups(MODE)), smem, st, tm_t, tm_w1, tm_w2, a));
     PV_LAUNCH_CHECK();
     return 0;
 }
