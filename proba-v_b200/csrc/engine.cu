@@ -815,7 +815,7 @@ int pv_trainer_create(pv_model* m, int opt_kind, float learning_rate, int loss_k
         // for mainConv1 and for the 2-D skip path (sized for batches up to 4096; larger batches fall back to immediate mode)
         const size_t conv3_layers = (size_t)m->R + m->nred + 1;
         const size_t arena = t->wg_partial_floats + conv3_layers * ((size_t)148 * (9 * 4096 + 128) + 64) +
-                             (size_t)m->R * ((size_t)148 * (4 * 4096 + 768) + 64) + (size_t)148 * 4 * 28 * 32 + 64 +
+                             (size_t)m->R * ((size_t)148 * (4 * 4096 + pv::RESBW_DBP) + 64) + (size_t)148 * 4 * 28 * 32 + 64 +
                              pv::skip2d_partial_floats(4096, m->S, m->cfg.scale * m->cfg.scale) + 64;
         t->rq.arena_floats = arena;
         if (cudaMalloc(&t->wg_partials, arena * 4) != cudaSuccess) {

@@ -330,15 +330,16 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
 //       three unit buffers (384 columns) + the four accumulators (128 columns) fill TMEM exactly.  As in the forward
 //       kernel the MMA thread issues the two SS MMAs of unit u+1 before the two TS MMAs of unit u, and two epilogue
 //       groups of four warps take alternate units.
+constexpr int RBW_THREADS = 64 + 128 * RESBW_GROUPS;
 struct ResBwdWeightArgs {
     int B, tiles_per_patch;
     RowGeom g;
     const float* bias_e;
     float* partials;                   // [cta][4][128][32]: dWd half 0, half 1, dWe^T half 0, half 1
-    float* db_partials;                // [cta][2 groups][256 (dbe)] then [cta][8 warps][32 (dbd)]
+    float* db_partials;                // [cta][groups][256 (dbe)] then [cta][groups x 4 warps][32 (dbd)]
 };
 
-__global__ void __launch_bounds__(RP_THREADS, 1)
+__global__ void __launch_bounds__(RBW_THREADS, 1)
 resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_gd,
                            const __grid_constant__ CUtensorMap tm_x32, const __grid_constant__ CUtensorMap tm_gd32,
                            const __grid_constant__ CUtensorMap tm_weT, const __grid_constant__ CUtensorMap tm_wd,
@@ -360,7 +361,7 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
         mbar_init(BAR(WBAR), 1); mbar_init(BAR(DONE), 1);
         fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < 256; i += RP_THREADS) s_be[i] = a.bias_e[i];
+    for (int i = threadIdx.x; i < 256; i += RBW_THREADS) s_be[i] = a.bias_e[i];
     if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
     tc_fence_before();
     __syncthreads();
@@ -439,14 +440,14 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
         const int U = 4 * my_tiles;
         pdl_wait();                                          // the partial buffers may still be read by the previous reduction
 #pragma unroll 1
-        for (int u = grp; u < U; u += 2) {          // sub-tile s == grp for every unit of this group
-            const int tl = u >> 2, h = (u >> 1) & 1;
+        for (int u = grp; u < U; u += RESBW_GROUPS) {      // with three groups unit u always lives in H buffer u % 3 == grp
+            const int tl = u >> 2, h = (u >> 1) & 1, sub = u & 1;
             const uint32_t stg = tl & 1, ph = (tl >> 1) & 1, eb = u % 3;
             if (h == 0) {   // dbd: column sums of this group's 64 rows of the gD tile (K-major SW128 copy: 16-byte chunk ^= row & 7)
                 mbar_wait(BAR(FULL + stg), ph);
                 const uint8_t* gp = smem_raw + (st_smem - smem_u32(smem_raw)) + stg * 65536 + 16384;
                 float sacc = 0.f;
-                for (int r = grp * 64 + q * 16; r < grp * 64 + q * 16 + 16; ++r)
+                for (int r = sub * 64 + q * 16; r < sub * 64 + q * 16 + 16; ++r)
                     sacc += *reinterpret_cast<const float*>(gp + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
                 dbd += sacc;
                 __syncwarp();
@@ -480,15 +481,15 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(EREADY + eb));
         }
-        float* dbp = a.db_partials + (size_t)blockIdx.x * (512 + 256);
+        float* dbp = a.db_partials + (size_t)blockIdx.x * RESBW_DBP;
         dbp[grp * 256 + q * 32 + lane] = dbe0;
         dbp[grp * 256 + 128 + q * 32 + lane] = dbe1;
-        dbp[512 + (grp * 4 + q) * 32 + lane] = dbd;
+        dbp[RESBW_GROUPS * 256 + (grp * 4 + q) * 32 + lane] = dbd;
         mbar_wait(BAR(DONE), 0);
         tc_fence_after();
         float* out = a.partials + (size_t)blockIdx.x * 4 * 4096;
 #pragma unroll 1
-        for (int g2 = 0; g2 < 2; ++g2) {            // group 0 drains the dWd accumulators, group 1 the dWe^T ones
+        for (int g2 = 0; g2 < 2 && grp < 2; ++g2) { // group 0 drains the dWd accumulators, group 1 the dWe^T ones
             const int g = grp * 2 + g2;
             uint32_t v[32];
             tmem_ld32(lane_base + 384 + g * 32, v);
@@ -575,7 +576,7 @@ int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = a.B * a.tiles_per_patch;
     const int grid = ntiles < sms ? ntiles : sms;
-    const size_t need = (size_t)grid * (4 * 4096 + 768);
+    const size_t need = (size_t)grid * (4 * 4096 + RESBW_DBP);
     float* deferred = rq ? rq->take(need) : nullptr;
     if (deferred) { partials = deferred; partial_floats = need; }
     if (!partials || partial_floats < need) return set_error(PV_ERR_BAD_ARG, "resfront_bwd_weight: partial buffer too small");
@@ -593,7 +594,7 @@ int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* 
     PV_CUDA(ensure_dyn_smem(resfront_bwd_weight_kernel, smem, attr));
     {
         PV_TIMED("resfront_bwd_weight", st, flops, 0.0);
-        PV_CUDA(launch_pdl(resfront_bwd_weight_kernel, grid, RP_THREADS, smem, st, tm_x, tm_gd, tm_x32, tm_gd32, tm_weT, tm_wd, a));
+        PV_CUDA(launch_pdl(resfront_bwd_weight_kernel, grid, RBW_THREADS, smem, st, tm_x, tm_gd, tm_x32, tm_gd32, tm_weT, tm_wd, a));
         PV_LAUNCH_CHECK();
     }
     if (deferred) {

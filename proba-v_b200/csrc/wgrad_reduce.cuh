@@ -70,9 +70,16 @@ __device__ __forceinline__ void wgrad_reduce_body(int blk, const float* __restri
     }
 }
 
+// epilogue groups (of four warps) of resfront_bwd_weight_kernel and the per-CTA bias-gradient partial they write:
+// [group][256 (dbe)] then [group x 4 warps][32 (dbd)]
+#ifndef PV_RESBW_GROUPS
+#define PV_RESBW_GROUPS 2
+#endif
+constexpr int RESBW_GROUPS = PV_RESBW_GROUPS;
+constexpr int RESBW_DBP = RESBW_GROUPS * 256 + RESBW_GROUPS * 4 * 32;
 constexpr int RESFRONT_REDUCE_BLOCKS = 131;
 // dWd [256][32] (= dweff of decConv), dWe [32][256] (= dweff of expConv), dbe [256], dbd [32] from the per-CTA partials
-// [cta][4][128][32] and [cta][768].  Blocks [0,128): weight gradients; 128,129: dbe; 130: dbd.
+// [cta][4][128][32] and [cta][RESBW_DBP].  Blocks [0,128): weight gradients; 128,129: dbe; 130: dbd.
 __device__ __forceinline__ void resfront_reduce_body(int b, const float* __restrict__ partials, const float* __restrict__ dbp, int ncta,
                                                      float* __restrict__ dwd, float* __restrict__ dwe, float* __restrict__ dbe,
                                                      float* __restrict__ dbd, float4* sm) {
@@ -90,11 +97,12 @@ __device__ __forceinline__ void resfront_reduce_body(int b, const float* __restr
             else dwe[(size_t)n * 256 + (g - 2) * 128 + m] = v[e];                  // [ci][ch]
         }
     } else if (b < 130) {       // dbe: both epilogue groups of every CTA
-        const float4 s = block_rowsum4<8>(dbp, 2 * ncta, [](int r) { return (size_t)(r >> 1) * 768 + (r & 1) * 256; }, (b - 128) * 32, true, sm);
+        const float4 s = block_rowsum4<8>(dbp, RESBW_GROUPS * ncta, [](int r) { return (size_t)(r / RESBW_GROUPS) * RESBW_DBP + (r % RESBW_GROUPS) * 256; }, (b - 128) * 32, true, sm);
         if (threadIdx.x < 32) { float* o = dbe + ((b - 128) * 32 + x) * 4; o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w; }
     } else {                    // dbd: eight epilogue warps of every CTA
         const bool ok = x < 8;
-        const float4 s = block_rowsum4<8>(dbp, 8 * ncta, [](int r) { return (size_t)(r >> 3) * 768 + 512 + (r & 7) * 32; }, 0, ok, sm);
+        constexpr int NWD = RESBW_GROUPS * 4;      // epilogue warps per CTA
+        const float4 s = block_rowsum4<8>(dbp, NWD * ncta, [](int r) { return (size_t)(r / NWD) * RESBW_DBP + RESBW_GROUPS * 256 + (r % NWD) * 32; }, 0, ok, sm);
         if (threadIdx.x < 32 && ok) { float* o = dbd + x * 4; o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = s.w; }
     }
 }
