@@ -7,7 +7,8 @@ from .parseConfig import parseConfig                      # noqa: F401
 from .models import WDSRConv3D, WDSRModel, build_from_config   # noqa: F401
 from .loss import Losses, loss_from_config                # noqa: F401
 from .trainClass import ModelTrainer                      # noqa: F401
-from .testClass import Enhancer, calcRelativePSNR, evaluate, resolve, resolveByBatch, reconstruct_from_patches   # noqa: F401
+from .testClass import (Enhancer, calcRelativePSNR, evaluate, resolve, resolveByBatch, resolveBySampleAveraging,  # noqa: F401
+                        reconstruct_from_patches)
 from .optimizers import Adam, Nadam, SGD                  # noqa: F401
 from . import optimizers, parallel, synth                 # noqa: F401
 

@@ -61,3 +61,16 @@ def calcRelativePSNR(patchPredOne, patchPredTwo, patchHR):
     one = loss.shiftCompensatedcPSNR(hr, clear, np.asarray(patchPredOne, np.float32))
     two = loss.shiftCompensatedcPSNR(hr, clear, np.asarray(patchPredTwo, np.float32))
     return np.asarray(one), np.asarray(two)
+
+
+def resolveBySampleAveraging(model, lr_batch, repeats: int = 20):
+    """test.py:137-146: test-time augmentation over the frame order -- `repeats` cumulative random permutations of the T axis
+    (np.random.permutation, the reference's global RNG), each resolved (clip + round), then averaged.  [B,S,S,T,1] -> [B,sP,sP,1]."""
+    lr_batch = np.asarray(lr_batch, np.float32)
+    acc = None
+    for _ in range(repeats):
+        newIdx = np.random.permutation(lr_batch.shape[3])
+        lr_batch = lr_batch[:, :, :, newIdx, :]
+        res = np.asarray(resolve(model, np.ascontiguousarray(lr_batch)), np.float64)
+        acc = res if acc is None else acc + res
+    return (acc / repeats).astype(np.float32)

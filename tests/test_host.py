@@ -194,3 +194,30 @@ def test_cli_flags_and_png_writer(tmp_path):
     assert back.dtype == np.uint16 and np.array_equal(back, img.astype(np.uint16))
     with pytest.raises(ValueError):
         cli.write_png16(p, np.zeros((2, 2, 3)))
+
+
+def test_predict_helpers_with_a_stub_model():
+    """Host-side logic of the predict path (test.py:125-160) against a stub model: batch splitting with a remainder, the
+    n x n row-major stitch, and the frame-order test-time augmentation (a frame-order-invariant model must be unchanged)."""
+    import probav_b200 as pb
+
+    class Stub:
+        calls = []
+
+        def __call__(self, lr, training=False, resolve=False):
+            Stub.calls.append(lr.shape[0])
+            s = np.asarray(lr, np.float32).sum(axis=3)[:, :16, :16, :]                     # permutation-invariant over T
+            return np.round(np.clip(np.repeat(np.repeat(s, 3, 1), 3, 2), 0, 65536))
+
+    rng = np.random.default_rng(0)
+    lr = rng.uniform(0, 900, size=(37, 22, 22, 9, 1)).astype(np.float32)
+    whole = Stub()(lr)
+    Stub.calls.clear()
+    by = pb.resolveByBatch(Stub(), lr, batch_size=16)
+    assert Stub.calls == [16, 16, 5] and np.array_equal(by, whole)                      # test.py:126-134
+    np.random.seed(0)
+    avg = pb.resolveBySampleAveraging(Stub(), lr[:4], repeats=5)
+    assert np.allclose(avg, whole[:4], atol=0.51)      # the float32 sum over T depends on the frame order only in its last bit, before rounding
+    imgs = np.arange(64 * 4).reshape(64, 2, 2, 1).astype(np.float64)
+    rec = pb.reconstruct_from_patches(imgs)
+    assert rec.shape == (16, 16, 1) and np.array_equal(rec[2:4, 4:6], imgs[1 * 8 + 2])   # row-major: block (i=1, j=2)
