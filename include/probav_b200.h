@@ -2,7 +2,7 @@
  *
  * The reference (mmbajo/PROBA-V) is pure Python on TensorFlow: it has no FFI of its own, its
  * boundary is Python call signatures.  Each entry point below names the reference interface it
- * replaces (file:line relative to the reference tree); proba-v_b200/*.py re-creates those Python
+ * replaces (file:line relative to the reference tree); the Python modules under proba-v_b200/ re-create those Python
  * signatures on top of this ABI (see INTEGRATION.md for the binding stub).
  *
  * Conventions

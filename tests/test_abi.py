@@ -62,3 +62,26 @@ def test_bad_cfg_is_rejected_like_the_reference_graph_would():
         pb.WDSRConv3D("n", "NIR", 8075.2, 3160.7, 6).build(3, 32, (3, 3, 3), 2, 8, 0.8, 12, 16, True)
     with pytest.raises(ValueError):
         pb.WDSRConv3D("n", "NIR", 8075.2, 3160.7, 4).build(3, 32, (3, 3, 3), 2, 8, 0.8, 9, 16, True)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++-isms, no torch types) and a C program must link against
+    the library and call into it (pv_abi_version / pv_device_count / pv_last_error need no GPU)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    subprocess.check_call([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", "-pedantic", HEADER])
+    if not os.path.exists(LIB):
+        import __graft_entry__
+        __graft_entry__.build()
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "probav_b200.h"\n'
+                   'int main(void) { pv_model* m = 0; pv_cfg c = {0}; int rc = pv_model_create(&c, 0, &m);\n'
+                   '  printf("%d %d %d\\n", pv_abi_version(), rc != 0, pv_last_error()[0] != 0); return 0; }\n')
+    exe = tmp_path / "t"
+    subprocess.check_call([gcc, "-std=c99", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe),
+                           "-L", os.path.dirname(LIB), "-lprobav_b200", "-Wl,-rpath," + os.path.dirname(LIB)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120).stdout.split()
+    assert out == ["1", "1", "1"]          # ABI version 1; an all-zero cfg is rejected with a message, no crash
