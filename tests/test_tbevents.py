@@ -76,3 +76,24 @@ def test_truncated_tail_is_tolerated_and_corruption_is_caught(tb, tmp_path):
     p.write_bytes(bad)
     with pytest.raises(ValueError, match="crc"):
         list(tb.read_records(str(p)))
+
+
+def test_event_codec_agrees_with_tensorflows_generated_proto(tb):
+    """encode_event against TensorFlow's generated Event / Summary classes (shipped inside `tensorboard`): parse, compare
+    fields, and re-serialize byte for byte."""
+    pb2 = pytest.importorskip("tensorboard.compat.proto.event_pb2")
+    for ev in (tb.ScalarEvent(1583836565.721661, 163018, "Train PSNR", 47.63618087768555),
+               tb.ScalarEvent(12.5, 0, "Test loss", float("inf")),
+               tb.ScalarEvent(1583765479.0, 0, None, None, "brain.Event:2")):
+        blob = tb.encode_event(ev)
+        msg = pb2.Event.FromString(blob)
+        assert msg.SerializeToString() == blob
+        assert msg.wall_time == ev.wall_time and msg.step == ev.step
+        if ev.tag is None:
+            assert msg.file_version == "brain.Event:2"
+        else:
+            v = msg.summary.value[0]
+            assert v.tag == ev.tag and v.metadata.plugin_data.plugin_name == "scalars"
+            assert v.tensor.dtype == 1 and len(v.tensor.tensor_shape.dim) == 0            # DT_FLOAT scalar
+            import struct
+            assert struct.unpack("<f", v.tensor.tensor_content)[0] == pytest.approx(ev.value, rel=1e-7) or math.isinf(ev.value)
