@@ -33,6 +33,12 @@ def test_crc32c_known_answers(tfckpt):
     assert tfckpt.crc32c(b"6789", tfckpt.crc32c(b"12345")) == 0xE3069283
     for c in (0, 1, 0xDEADBEEF, 0xFFFFFFFF):
         assert tfckpt.unmask_crc(tfckpt.mask_crc(c)) == c
+    # ... and against the TFRecord checksum implementation that ships with the `tensorboard` package
+    pw = pytest.importorskip("tensorboard.compat.tensorflow_stub.pywrap_tensorflow")
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 8, 9, 63, 64, 1000, 4097):
+        b = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert pw.masked_crc32c(b) == tfckpt.mask_crc(tfckpt.crc32c(b)), n
 
 
 def test_reference_index_parses_and_every_checksum_holds(tfckpt, specs):
