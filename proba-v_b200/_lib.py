@@ -102,14 +102,15 @@ def check(status: int):
 
 
 def timing_report() -> dict:
-    """{kernel class: dict(launches, ms, flops, bytes)} accumulated since pv_timing_reset (device-synchronising)."""
+    """{kernel class: dict(launches, ms, flops, bytes, exec_flops)} accumulated since pv_timing_reset (device-synchronising).
+    flops / bytes are ALGORITHMIC (unpadded shapes, no recomputation); exec_flops is what the kernels execute."""
     n = lib().pv_timing_report(None, 0)
     buf = C.create_string_buffer(max(n, 1))
     lib().pv_timing_report(buf, n)
     out = {}
     for line in buf.value.decode().splitlines():
-        name, cnt, ms, fl, by = line.split()
-        out[name] = dict(launches=int(cnt), ms=float(ms), flops=float(fl), bytes=float(by))
+        name, cnt, ms, fl, by, ex = line.split()
+        out[name] = dict(launches=int(cnt), ms=float(ms), flops=float(fl), bytes=float(by), exec_flops=float(ex))
     return out
 
 

@@ -76,9 +76,10 @@ static inline cudaError_t launch_pdl_simple(void (*kernel)(KArgs...), dim3 grid,
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // Per-kernel-class device timing behind pv_timing_* (bench.py's roofline): when enabled, a launch is bracketed by
-// CUDA events on its own stream and tagged with its ALGORITHMIC flops / bytes (unpadded shapes).
+// CUDA events on its own stream and tagged with its ALGORITHMIC flops / bytes (unpadded shapes: the roofline numerator) and,
+// where they differ, the flops the kernel EXECUTES (recomputation, channel padding, extra compensation passes).
 struct KernelTimer {
-    KernelTimer(const char* name, cudaStream_t st, double flops = 0.0, double bytes = 0.0);
+    KernelTimer(const char* name, cudaStream_t st, double flops = 0.0, double bytes = 0.0, double exec_flops = 0.0);
     ~KernelTimer();
     int slot;
     cudaStream_t st;

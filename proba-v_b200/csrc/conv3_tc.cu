@@ -332,7 +332,7 @@ int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = a.B * a.chunks * a.nt;
     const int grid = ntiles < sms ? ntiles : sms;
-    PV_TIMED(p.tag ? p.tag : "rowconv3_tc", st, p.flops, 0.0);
+    PV_TIMED(p.tag ? p.tag : "rowconv3_tc", st, p.flops, 0.0, 2.0 * (double)ntiles * 128.0 * 96.0 * 288.0);
     static size_t attr[16] = {};
     PV_CUDA(ensure_dyn_smem(rowconv3_tc_kernel, smem, attr));
     PV_CUDA(launch_pdl(rowconv3_tc_kernel, grid, C3_THREADS, smem, st, tm_x, tm_w, a));

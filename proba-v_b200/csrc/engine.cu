@@ -44,14 +44,14 @@ bool pdl_enabled() { static const bool on = getenv("PV_NO_PDL") == nullptr; retu
 
 // ------------------------------------------------------------------------------------------ kernel timing
 namespace {
-struct TimedLaunch { const char* name; cudaEvent_t a, b; double flops, bytes; };
+struct TimedLaunch { const char* name; cudaEvent_t a, b; double flops, bytes, exec_flops; };
 std::vector<TimedLaunch> g_timed;
 bool g_timing = false;
 }  // namespace
 
-KernelTimer::KernelTimer(const char* name, cudaStream_t s, double flops, double bytes) : slot(-1), st(s) {
+KernelTimer::KernelTimer(const char* name, cudaStream_t s, double flops, double bytes, double exec_flops) : slot(-1), st(s) {
     if (!g_timing) return;
-    TimedLaunch t{name, nullptr, nullptr, flops, bytes};
+    TimedLaunch t{name, nullptr, nullptr, flops, bytes, exec_flops > 0.0 ? exec_flops : flops};
     if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return;
     cudaEventRecord(t.a, st);
     slot = (int)g_timed.size();
@@ -269,7 +269,7 @@ static int model_forward(pv_model* m, const float* lr, int B, float* sr, bool tr
     PV_CUDA(cudaSetDevice(m->device));
     if (m->rows) return tc_forward(m, lr, B, sr, tr, clip_round, st);
     Pool& P = tr ? m->pool_train : m->pool_infer;
-    PV_TRY(P.ensure(B));
+    PV_TRY(P.ensure(B, st));
     PV_TRY(refresh_weights(m, st));
     const pv_cfg& c = m->cfg;
     PV_TRY(launch_prep(lr, B, m->S * m->S, m->T, c.mean, c.std, P["xn"], P["mn"], st));
@@ -462,18 +462,18 @@ int pv_timing_reset(void) {
 
 int pv_timing_report(char* buf, int cap) {
     if (cudaDeviceSynchronize() != cudaSuccess) return set_error(PV_ERR_CUDA, "timing_report: device sync failed");
-    struct Acc { long long n = 0; double ms = 0, flops = 0, bytes = 0; };
+    struct Acc { long long n = 0; double ms = 0, flops = 0, bytes = 0, exec_flops = 0; };
     std::map<std::string, Acc> acc;
     for (auto& t : pv::g_timed) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, t.a, t.b) != cudaSuccess) { cudaGetLastError(); continue; }
         Acc& a = acc[t.name];
-        a.n++; a.ms += ms; a.flops += t.flops; a.bytes += t.bytes;
+        a.n++; a.ms += ms; a.flops += t.flops; a.bytes += t.bytes; a.exec_flops += t.exec_flops;
     }
     std::string out;
     char line[256];
     for (auto& kv : acc) {
-        snprintf(line, sizeof line, "%s %lld %.6f %.6e %.6e\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops, kv.second.bytes);
+        snprintf(line, sizeof line, "%s %lld %.6f %.6e %.6e %.6e\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops, kv.second.bytes, kv.second.exec_flops);
         out += line;
     }
     if (buf && cap > 0) { std::strncpy(buf, out.c_str(), cap - 1); buf[cap - 1] = 0; }
@@ -827,6 +827,11 @@ int pv_trainer_create(pv_model* m, int opt_kind, float learning_rate, int loss_k
     cudaMemset(t->grads, 0, m->nparams * 4);
     cudaMemset(t->m1, 0, m->nparams * 4);
     cudaMemset(t->m2, 0, m->nparams * 4);
+    // legacy-stream memsets are not ordered against non-blocking streams: make them complete before the handle is used
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        pv_trainer_destroy(t);
+        return set_error(PV_ERR_CUDA, "pv_trainer_create: device synchronisation failed");
+    }
     *out = t;
     return 0;
 }
@@ -843,6 +848,12 @@ void pv_trainer_destroy(pv_trainer* t) {
 int pv_train_forward_backward(pv_trainer* t, const float* lr, const float* hr, const uint8_t* mask, int B, float grad_scale,
                               float* out_dev, void* stream) {
     if (!t) return set_error(PV_ERR_BAD_ARG, "null trainer");
+    if (B == 0) {       // empty data-parallel shard: zero gradients (see pv_train_forward_backward_staged)
+        PV_CUDA(cudaSetDevice(t->m->device));
+        PV_CUDA(cudaMemsetAsync(t->grads, 0, (size_t)t->m->nparams * sizeof(float), S_(stream)));
+        if (out_dev) PV_CUDA(cudaMemsetAsync(out_dev, 0, 2 * sizeof(float), S_(stream)));
+        return 0;
+    }
     return trainer_fwd_loss(t, lr, hr, mask, B, grad_scale, true, out_dev, S_(stream));
 }
 
@@ -854,6 +865,16 @@ int pv_train_forward_backward_staged(pv_trainer* t, const float* lr, const float
     // the parameter arena is laid out in layer order, so each bucket is one contiguous range of the gradient arena
     const int split = m->rows ? pv::tc_bucket_split_layer(m) : 0;
     const int64_t cut = split < (int)m->layers.size() ? m->layers[split].v_off : m->nparams;
+    if (B == 0) {
+        // A rank whose shard of the last partial global batch is empty (fewer samples than ranks) contributes zero gradients
+        // and still joins both all-reduces (trainClass._dp_step): the reference's single process keeps the partial batch
+        // (trainClass.py:84-93), so the data-parallel job must not dead-lock on it.
+        PV_CUDA(cudaSetDevice(m->device));
+        *grad_lo = stage == 0 ? cut : 0; *grad_hi = stage == 0 ? m->nparams : cut;
+        PV_CUDA(cudaMemsetAsync(t->grads + *grad_lo, 0, (size_t)(*grad_hi - *grad_lo) * sizeof(float), S_(stream)));
+        if (stage == 0 && out_dev) PV_CUDA(cudaMemsetAsync(out_dev, 0, 2 * sizeof(float), S_(stream)));
+        return 0;
+    }
     if (stage == 0) {
         PV_TRY(trainer_fwd_loss(t, lr, hr, mask, B, grad_scale, true, out_dev, S_(stream), 0));
         *grad_lo = cut; *grad_hi = m->nparams;

@@ -35,14 +35,17 @@ struct Pool {
         for (auto& s : spec) if (s.name == n) { s.per = std::max(s.per, per); s.extra = std::max(s.extra, extra); return; }
         spec.push_back({n, per, extra});
     }
-    int ensure(int B) {
+    // `st`: the stream the buffers' first kernels will be launched on.  The zero-fill must be ordered before them, and a
+    // cudaMemset on the legacy stream is NOT ordered against cudaStreamNonBlocking streams (scene pipeline, torch side
+    // streams), so it is issued on `st` itself.
+    int ensure(int B, cudaStream_t st) {
         if (B <= cap) return 0;
         release();
         for (auto& s : spec) {
             float* d = nullptr;
             const size_t bytes = (s.per * (size_t)B + s.extra) * sizeof(float);
             PV_CUDA(cudaMalloc(&d, bytes));
-            PV_CUDA(cudaMemset(d, 0, bytes));           // row layouts rely on never-written padding rows being zero
+            PV_CUDA(cudaMemsetAsync(d, 0, bytes, st));  // row layouts rely on never-written padding rows being zero
             ptr[s.name] = d;
         }
         cap = B;

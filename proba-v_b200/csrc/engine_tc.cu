@@ -536,7 +536,7 @@ int tc_build_plan(pv_model* m) {
 // ------------------------------------------------------------------------------------------ forward
 int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip_round, cudaStream_t st) {
     Pool& P = tr ? m->pool_train : m->pool_infer;
-    PV_TRY(P.ensure(B));
+    PV_TRY(P.ensure(B, st));
     PV_TRY(refresh_weights(m, st));
     const pv_cfg& c = m->cfg;
     const RowGeom pr = pr_geom(m->T);
@@ -670,7 +670,7 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int st
             PV_TRY(launch_resfront_bwd_weight_tc(P[m->A(i, true)], P["g_D"], m->weffT + Le.weff_off, m->weff + Ld.weff_off,
                                                  m->bias_s + Le.bias_s_off, t->dweff + Ld.weff_off, t->dweff + Le.weff_off,
                                                  t->dbias_s + Le.bias_s_off, t->dbias_s + Ld.bias_s_off, pr, B, t->wg_partials,
-                                                 t->wg_partial_floats, 2.0 * fl, st, &t->rq));
+                                                 t->wg_partial_floats, fl, st, &t->rq));
             PV_TRY(launch_resfront_bwd_data_tc(P["g_D"], m->weff + Ld.weff_off, m->weff + Le.weff_off,
                                                reinterpret_cast<const uint32_t*>(P["M" + std::to_string(i)]), G,
                                                i == 0 ? P[m->A(0, true)] : nullptr, gin, pr, B, 1, fl, st));

@@ -532,7 +532,7 @@ static int launch_respipe(const float* t, const float* w1, const float* w2, cons
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = a.B * a.tiles_per_patch;
     const int grid = ntiles < sms ? ntiles : sms;
-    PV_TIMED(tag, st, flops, 0.0);
+    PV_TIMED(tag, st, flops, 0.0, 2.0 * 2.0 * (double)ntiles * 128.0 * 32.0 * 256.0);
     PV_CUDA(launch_pdl(resfront_pipe_kernel<MODE>, grid, respipe_threads(respipe_groups(MODE)), smem, st, tm_t, tm_w1, tm_w2, a));
     PV_LAUNCH_CHECK();
     return 0;
@@ -593,7 +593,9 @@ int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* 
     static size_t attr[16] = {};
     PV_CUDA(ensure_dyn_smem(resfront_bwd_weight_kernel, smem, attr));
     {
-        PV_TIMED("resfront_bwd_weight", st, flops, 0.0);
+        // algorithmic: dWe + dWd.  Executed: E^T and gE^T are recomputed on chip, and every GEMM runs on the padded 32 x 256 shapes
+        // over whole 128-row tiles: 4 GEMMs of 2 * rows * 32 * 256 flops.
+        PV_TIMED("resfront_bwd_weight", st, flops, 0.0, 4.0 * 2.0 * (double)ntiles * 128.0 * 32.0 * 256.0);
         PV_CUDA(launch_pdl(resfront_bwd_weight_kernel, grid, RBW_THREADS, smem, st, tm_x, tm_gd, tm_x32, tm_gd32, tm_weT, tm_wd, a));
         PV_LAUNCH_CHECK();
     }

@@ -87,7 +87,7 @@ def _free_port():
     return p
 
 
-def _dp_worker(rank, ws, port, q):
+def _dp_worker(rank, ws, port, q, nsamp=5):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws), LOCAL_RANK=str(rank))
     torch.set_num_threads(1)
     r, w, _ = parallel.init_from_env(backend="gloo")
@@ -99,13 +99,19 @@ def _dp_worker(rank, ws, port, q):
     from probav_b200 import synth
     om = OracleWDSR(8075.2045, 3160.7272, 6, 3, 8, (3, 3, 3), 1, 2, 0.8, 9, 16)
     p = init_params(om.specs, seed=0)
-    lr, hr, mask = synth.make_batch(5, seed=3, hr_zero_under_mask=True)      # 5 samples -> unequal shards 3 + 2
+    lr, hr, mask = synth.make_batch(nsamp, seed=3, hr_zero_under_mask=True)      # 5 samples -> unequal shards 3 + 2
     ol = OracleLosses((48, 48, 1))
-    lo, hi = parallel.shard_bounds(5, rank, ws)
+    lo, hi = parallel.shard_bounds(nsamp, rank, ws)
     t = lambda a: torch.from_numpy(a[lo:hi])
-    loss, g, _, cps = loss_and_grads(om, ol, p, t(lr).double(), t(hr).double(), t(mask))
     n_local = hi - lo
-    flat = torch.cat([v.reshape(-1) for v in g.values()]) * (n_local * parallel.grad_scale(5))   # mean over shard -> sum/global
+    if n_local == 0:
+        # a partial last global batch with fewer samples than ranks: the empty rank contributes zero gradients and zero-weight
+        # metrics but joins every collective (trainClass._dp_step with B = 0; pv_train_forward_backward_staged zero-fills)
+        flat = torch.zeros(sum(v.numel() for v in p.values()), dtype=torch.float64)
+        loss, cps = torch.zeros(()), torch.zeros(1)
+    else:
+        loss, g, _, cps = loss_and_grads(om, ol, p, t(lr).double(), t(hr).double(), t(mask))
+        flat = torch.cat([v.reshape(-1) for v in g.values()]) * (n_local * parallel.grad_scale(nsamp))   # mean over shard -> sum/global
     parallel.allreduce_sum_(flat)
     gl, gc = parallel.reduce_metrics(float(loss), float(cps.mean()), n_local)
     w0 = torch.zeros(4) + rank
@@ -120,11 +126,12 @@ def _dp_worker(rank, ws, port, q):
     dist.destroy_process_group()
 
 
-def test_data_parallel_contract_gloo_world2():
+@pytest.mark.parametrize("nsamp", [5, 1])       # 1 sample on 2 ranks: rank 1's shard is empty (last partial batch < world size)
+def test_data_parallel_contract_gloo_world2(nsamp):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q, nsamp)) for r in range(2)]
     for p_ in procs:
         p_.start()
     res = [q.get(timeout=240) for _ in range(2)]
