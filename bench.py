@@ -310,7 +310,7 @@ def run_b200(args, cfg):
     gflop_per_patch = TRAIN_GFLOP_PER_PATCH if is_headline else sum(v["flops"] for v in rep.values()) / 2 / B / 1e9
     line = {"metric": METRIC if is_headline else METRIC.replace("p16t9c85r12", cfg_name), "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {0: "f32", 1: "tf32", 3: "f32"}[model.cfg.precision], "data": "synthetic",
+            "dtype": {0: "f32", 1: "tf32", 3: "f32", 4: "tf32x3"}[model.cfg.precision], "data": "synthetic",
             "config": {"workload": workload,
                        "batch_per_gpu": B, "global_batch": B * ws, "parallelism": f"dp{ws}",
                        "l2_policy": "per-step working set (activations ~8 GB) >> 126 MB L2; no explicit flush",
@@ -354,7 +354,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scene-infer", action="store_true")
     ap.add_argument("--scenes", type=int, default=32, help="scenes per inference call of the scene_infer leg")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "fp32_rows"],
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3", "fp32", "fp32_rows"],
                     help="tf32 = tcgen05 tensor-core engine (default; what TensorFlow runs on Ampere+), fp32 = CUDA-core exact mode")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -57,7 +57,10 @@ typedef struct pv_cfg {
     float   std;                /* datasetAllStd  (train.py:49,52)                             */
     int32_t precision;          /* 0 = fp32 on CUDA cores (exact mode); 1 = tf32 on the tcgen05 tensor cores, fp32 accumulate
                                  * (what TensorFlow itself runs on Ampere-or-newer GPUs by default); 3 = fp32 CUDA-core
-                                 * kernels on the tensor-core engine's row layouts (debug / cross-check) */
+                                 * kernels on the tensor-core engine's row layouts (debug / cross-check);
+                                 * 4 = error-compensated tf32 on the tensor cores ("tf32x3"): every forward product is computed as
+                                 * x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (hi = tf32(v), lo = v - hi) and the data gradients use
+                                 * w_hi + w_lo, which brings SR to ~1e-6 and the gradients inside the 1e-3 bar */
 } pv_cfg;
 
 typedef enum pv_loss_kind {     /* cfg [Train] loss (train.py:93-100)                          */

@@ -112,6 +112,43 @@ class _QStraight(torch.autograd.Function):
         return g, None
 
 
+class _FusedExpDec(torch.autograd.Function):
+    """expConv (1x1x1) -> ReLU -> decConv (1x1x1) of one block as the engine's three fused kernels compute it.
+
+    forward        E = relu(q_a(x) q_w(We) + be),  D = q_a(E) q_w(Wd) + bd                       (resfront forward)
+    data gradient  gZ = (q_g(gD) q_wb(Wd)^T) . mask,  gx = q_g(gZ) q_wb(We)^T                     (resfront_bwd_data)
+    weight kernel  RECOMPUTES  E_w = relu(q_xw(x) q_ww(We) + be)  and  gZ_w = (q_g(gD) q_ww(Wd)^T) . mask  on chip, then
+                   dWd = q_rn(E_w)^T q_g(gD),  dWe = q_xw(x)^T q_rn(gZ_w)                         (resfront_bwd_weight)
+    `ww` / `xw` are the quantisers of that recomputation (the kernel has single-pass tf32 operands: "rn")."""
+    @staticmethod
+    def forward(ctx, x, We, be, Wd, bd, m):
+        xs = x.shape
+        X = x.reshape(-1, xs[-1])
+        we, wd = We.reshape(We.shape[-2], We.shape[-1]), Wd.reshape(Wd.shape[-2], Wd.shape[-1])
+        E = torch.relu(Q[m["act"]](X) @ Q[m["wt"]](we) + be)
+        D = Q[m["act"]](E) @ Q[m["wt"]](wd) + bd
+        ctx.save_for_backward(X, we, be, wd, E)
+        ctx.m, ctx.xs, ctx.ws = m, xs, (We.shape, Wd.shape)
+        return D.reshape(*xs[:-1], wd.shape[-1])
+
+    @staticmethod
+    def backward(ctx, gD):
+        X, we, be, wd, E = ctx.saved_tensors
+        m = ctx.m
+        G = Q[m["grad"]](gD.reshape(-1, gD.shape[-1]))
+        mask = (E > 0).to(G.dtype)
+        wtb = m.get("wt_b") or m["wt"]
+        gZ = (G @ Q[wtb](wd).t()) * mask
+        gx = Q[m["grad"]](gZ) @ Q[wtb](we).t()
+        ww, xw = m.get("ww", "rn"), m.get("xw", "rn")
+        Xw = Q[xw](X)
+        Ew = torch.relu(Xw @ Q[ww](we) + be)
+        gZw = (G @ Q[ww](wd).t()) * mask
+        dWd = q_rn(Ew).t() @ G
+        dWe = Xw.t() @ q_rn(gZw)
+        return gx.reshape(ctx.xs), dWe.reshape(ctx.ws[0]), gZw.sum(0), dWd.reshape(ctx.ws[1]), gD.reshape(-1, gD.shape[-1]).sum(0), None
+
+
 DEFAULT = dict(act="rn", wt="rn", grad="rn", stream="rn", gstream="rn")      # the round-1 tf32 engine
 
 
@@ -137,8 +174,12 @@ class TensorCoreModel(OracleWDSR):
         h = self._wn(p, "mainConv1", xn, "same", True)        # Cin = 1: CUDA cores, fp32
         h = _QStraight.apply(_QGrad.apply(h, m["gstream"]), m["stream"])
         for i in range(self.numResBlocks):
-            e = self._tc(p, f"expConv_{i}", h, "same", True)
-            d = self._tc(p, f"decConv_{i}", e, "same", False)
+            if m.get("fused"):
+                d = _FusedExpDec.apply(h, wn_kernel(p[f"expConv_{i}/v"], p[f"expConv_{i}/g"]), p[f"expConv_{i}/bias"],
+                                       wn_kernel(p[f"decConv_{i}/v"], p[f"decConv_{i}/g"]), p[f"decConv_{i}/bias"], m)
+            else:
+                e = self._tc(p, f"expConv_{i}", h, "same", True)
+                d = self._tc(p, f"decConv_{i}", e, "same", False)
             n = self._tc(p, f"normConv_{i}", d, "same", False)
             h = n + h
             h = _QStraight.apply(_QGrad.apply(h, m["gstream"]), m["stream"])

@@ -76,7 +76,7 @@ def train_parser() -> argparse.ArgumentParser:
     ap.add_argument("--synthetic", type=int, default=0, help="train on N seeded synthetic patches instead of the .npy files")
     ap.add_argument("--max-steps", type=int, default=None)
     ap.add_argument("--eval-step", type=int, default=1000)
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "fp32_rows"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3", "fp32", "fp32_rows"])
     return ap
 
 
@@ -126,7 +126,7 @@ def test_parser() -> argparse.ArgumentParser:
     ap.add_argument("--band", type=str, default="RED")
     ap.add_argument("--totest", type=str, default="TEST")
     ap.add_argument("--synthetic", type=int, default=0, help="predict N seeded synthetic 128x128 scenes instead of the .npy file")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "fp32_rows"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3", "fp32", "fp32_rows"])
     return ap
 
 

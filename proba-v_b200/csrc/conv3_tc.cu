@@ -51,7 +51,7 @@ struct Conv3Args {
     int slab_lo[3];                    // first row of temporal slab dtI relative to the tile's lane-0 row
     int pw;                            // rows per image line: dh view stride inside a slab
     int tap_wr[MAX_TAPS], tap_wc[MAX_TAPS];
-    const float* bias; const float* residual; const float* relumask; float* y;
+    const float* bias; const float* residual; const float* residual2; const float* residual3; const float* relumask; float* y; float* y_lo;
     int relu, round_tf32;
 };
 
@@ -207,6 +207,18 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             const float* pre_src = a.residual ? a.residual : a.relumask;
             float4 pre[8];
             if (pre_src) rowio_ldg_chunks(pre_src + orow_w * 32, rowmask, pre);
+            if (a.residual2) {                                            // further addends (compensated forward): summed chunk-wise,
+                float4 t2[8];                                             // hi + lo of the skip connection first, then the partial pass
+                rowio_ldg_chunks(a.residual2 + orow_w * 32, rowmask, t2);
+                if (a.residual3) {
+                    float4 t3[8];
+                    rowio_ldg_chunks(a.residual3 + orow_w * 32, rowmask, t3);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { t2[i].x += t3[i].x; t2[i].y += t3[i].y; t2[i].z += t3[i].z; t2[i].w += t3[i].w; }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { pre[i].x += t2[i].x; pre[i].y += t2[i].y; pre[i].z += t2[i].z; pre[i].w += t2[i].w; }
+            }
             mbar_wait(BAR(TFULL + acc), aph);
             tc_fence_after();
             uint32_t v0[32], v1[32], v2[32];
@@ -277,7 +289,15 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     for (int k = 0; k < 4; ++k) e[k] = rna_tf32(e[k]);
                 }
             }
-            rowio_store_rows(a.y + orow_w * 32, o, rowmask, sc);
+            if (a.y_lo) {                                                 // hi / lo split of the fp32 result (hi is tf32-exact)
+                float lo[32];
+#pragma unroll
+                for (int c = 0; c < 32; ++c) { const float hi = rna_tf32(o[c]); lo[c] = o[c] - hi; o[c] = hi; }
+                rowio_store_rows(a.y + orow_w * 32, o, rowmask, sc);
+                rowio_store_rows(a.y_lo + orow_w * 32, lo, rowmask, sc);
+            } else {
+                rowio_store_rows(a.y + orow_w * 32, o, rowmask, sc);
+            }
         }
     }
     tc_fence_before();
@@ -305,6 +325,9 @@ int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st) {
     const int pw = p.off[3] - p.off[0];
     a.B = p.B; a.in_lead = p.in_lead; a.in_pstride = p.in_pstride; a.og = og; a.pw = pw;
     a.bias = p.bias; a.residual = p.residual; a.relumask = p.relumask; a.y = p.y; a.relu = p.relu; a.round_tf32 = p.round_tf32;
+    a.residual2 = p.residual2; a.residual3 = p.residual3; a.y_lo = p.y_lo;
+    if ((p.residual2 || p.residual3) && !p.residual) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: residual2/3 need residual");
+    if (p.residual3 && !p.residual2) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: residual3 needs residual2");
     a.slab_rows = ((128 + 2 * pw + 7) / 8) * 8;
     // lane l of a tile accumulates Q[rho = r0 + l]; its A rows for group g are rho + base_g + 1 with base_g = off[3g]
     for (int s = 0; s < 3; ++s) a.slab_lo[s] = p.off[9 * s] + 1;

@@ -118,10 +118,12 @@ static int build_plan(pv_model* m) {
     if (!c.is_grayscale)
         return set_error(PV_ERR_BAD_CONFIG, "is_grayscale=0 (3-channel input) is not built; PROBA-V bands are single-channel");
     const int ks = c.kernel_size;
-    if (c.precision != 0 && c.precision != 1 && c.precision != 3)
-        return set_error(PV_ERR_BAD_CONFIG, "precision=%d: 0 = fp32 (CUDA cores), 1 = tf32 (tcgen05 tensor cores), 3 = fp32 on the row layouts", c.precision);
+    if (c.precision != 0 && c.precision != 1 && c.precision != 3 && c.precision != 4)
+        return set_error(PV_ERR_BAD_CONFIG, "precision=%d: 0 = fp32 (CUDA cores), 1 = tf32 (tcgen05 tensor cores), 3 = fp32 on the row layouts, "
+                                            "4 = error-compensated tf32 (3 x tf32 forward, split-weight data gradients)", c.precision);
     m->rows = c.precision != 0;
-    m->use_tc = c.precision == 1;
+    m->use_tc = c.precision == 1 || c.precision == 4;
+    m->x3 = c.precision == 4;
     if (m->rows && ((c.num_low_res_imgs != 7 && c.num_low_res_imgs != 9 && c.num_low_res_imgs != 13) || c.num_filters != 32 || c.num_filters * c.exp_rate != 256 || c.scale != 3 ||
                     c.patch_size != 16 || c.max_shift != 6 || (int)(c.num_filters * c.decay_rate) > 32))
         return set_error(PV_ERR_BAD_CONFIG, "the tensor-core engine is built for the p16 family (T in {7, 9, 13}, 32 filters, exp_rate 8, scale 3, "
@@ -258,7 +260,8 @@ int conv_wgrad(pv_trainer* t, int li, const float* in, const float* gout, const 
 
 int refresh_weights(pv_model* m, cudaStream_t st) {
     if (!m->weff_dirty) return 0;
-    PV_TRY(launch_wn_prep(m->wn_tab, (int)m->layers.size(), m->wn_blocks, m->params, m->weff, m->weffT, m->bias_s, m->scale, st));
+    PV_TRY(launch_wn_prep(m->wn_tab, (int)m->layers.size(), m->wn_blocks, m->params, m->weff, m->weffT, m->bias_s, m->scale, st,
+                          m->weff_lo, m->weffT_lo));
     m->weff_dirty = false;
     return 0;
 }
@@ -522,6 +525,12 @@ int pv_model_create(const pv_cfg* cfg, int device, pv_model** out) {
     cudaMemset(m->weff, 0, m->nweff * sizeof(float));
     cudaMemset(m->weffT, 0, m->nweff * sizeof(float));
     cudaMemset(m->bias_s, 0, m->nbias_s * sizeof(float));
+    if (m->x3) {
+        if (cudaMalloc(&m->weff_lo, m->nweff * sizeof(float)) != cudaSuccess || cudaMalloc(&m->weffT_lo, m->nweff * sizeof(float)) != cudaSuccess)
+            return fail(set_error(PV_ERR_CUDA, "cudaMalloc of the weight remainder arenas failed"));
+        cudaMemset(m->weff_lo, 0, m->nweff * sizeof(float));
+        cudaMemset(m->weffT_lo, 0, m->nweff * sizeof(float));
+    }
     std::vector<WnLayer> tab(m->layers.size());
     int blocks = 0;
     for (size_t i = 0; i < m->layers.size(); ++i) {
@@ -551,6 +560,7 @@ void pv_model_destroy(pv_model* m) {
     m->pool_infer.release();
     m->pool_train.release();
     cudaFree(m->params); cudaFree(m->weff); cudaFree(m->weffT); cudaFree(m->bias_s); cudaFree(m->scale); cudaFree(m->wn_tab);
+    cudaFree(m->weff_lo); cudaFree(m->weffT_lo);
     cudaFree(m->stage_lr); cudaFree(m->stage_sr); cudaFree(m->stage_scene);
     m->scene_pipe.release();
     delete m;

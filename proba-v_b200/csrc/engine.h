@@ -133,7 +133,10 @@ struct pv_model {
     bool weff_dirty = true;
     Pool pool_infer, pool_train;
     bool rows = false;                 // row-layout engine (cfg.precision != 0), engine_tc.cu
-    bool use_tc = false;               // tcgen05 kernels (precision 1) vs the CUDA-core row kernels (precision 3)
+    bool use_tc = false;               // tcgen05 kernels (precision 1, 4) vs the CUDA-core row kernels (precision 3)
+    bool x3 = false;                   // precision 4: error-compensated tensor-core engine.  Every forward product is
+                                       // x_hi w_hi + x_lo w_hi + x_hi w_lo (hi = tf32(v), lo = v - hi), data gradients use w_hi + w_lo
+    float *weff_lo = nullptr, *weffT_lo = nullptr;   // w - tf32(w) in the layouts of weff / weffT
     float *stage_lr = nullptr, *stage_sr = nullptr, *stage_scene = nullptr;   // host-API staging
     size_t stage_lr_n = 0, stage_sr_n = 0, stage_scene_n = 0;
     pv::ScenePipe scene_pipe;

@@ -138,7 +138,47 @@ int dgrad_rows(pv_model* m, const Layer& L, const Taps& tp /* negated offsets */
     p.round_tf32 = m->use_tc ? 1 : 0;
     p.flops = 2.0 * B * L.Ho * L.Wo * L.To * L.taps() * L.cin * L.cout;
     p.tag = tag;
+    if (m->x3) {
+        // precision 4: gx = gz * (w_hi + w_lo).  The weight rounding is the one systematic error of the data-gradient chain
+        // (profiles/r02_tf32_numerics_study.md); the lo pass goes first into the fp32 partial buffer, then rides as the residual.
+        if (residual) return set_error(PV_ERR_BAD_ARG, "dgrad_rows: the split-weight data gradient has no residual slot left");
+        float* yp = m->pool_train["Yp"];
+        RowConvP q = p;
+        q.w = m->weff_lo + L.weff_off; q.relumask = nullptr; q.round_tf32 = 0; q.y = yp; q.flops = 0.0;
+        PV_TRY(launch_rowconv_tc(q, st));
+        p.residual = yp;
+        return launch_rowconv_tc(p, st);
+    }
     return m->use_tc ? launch_rowconv_tc(p, st) : launch_rowconv_simt(p, st);
+}
+
+// Error-compensated forward convolution (precision 4): operands as (hi, lo) row arrays, three passes of the conv3 kernel chained
+// through the fp32 partial buffer `yp` (same geometry as the output):
+//     yp  = x_lo * w_hi;   yp += x_hi * w_lo;   v = x_hi * w_hi + yp + bias (+ res_hi + res_lo), act  ->  (y_hi, y_lo) = split(v)
+// y_lo == nullptr stores v itself (un-rounded fp32: the upscale conv, whose output feeds the CUDA-core tail).
+int conv_rows_x3(pv_model* m, const Layer& L, const Taps& tp, const float* x_hi, const float* x_lo, const RowGeom& ig, float* y_hi, float* y_lo,
+                 const RowGeom& og, const float* res_hi, const float* res_lo, float* yp, int B, const char* tag, cudaStream_t st) {
+    RowConvP p;
+    memset(&p, 0, sizeof p);
+    p.xc = 32; p.n = L.cout_s; p.B = B;
+    p.in_lead = ig.lead; p.in_pstride = ig.pstride; p.og = og;
+    p.ntap = tp.n; p.kc = 32;
+    const int Kflat = L.taps() * L.cin_s;
+    for (int i = 0; i < tp.n; ++i) { p.off[i] = tp.off[i]; p.c0[i] = tp.c0[i]; p.wr0[i] = 0; p.wc0[i] = 32 * tp.chunk[i]; }
+    p.w_rows = L.cout_s; p.w_cols = Kflat; p.w_kmajor = 1;
+    p.flops = 0.0;                       // the algorithmic flops are booked once, on the last pass
+    p.tag = tag;
+    // pass 1: x_lo * w_hi
+    p.x = x_lo; p.w = m->weffT + L.weff_off; p.y = yp;
+    PV_TRY(launch_rowconv_tc(p, st));
+    // pass 2: + x_hi * w_lo (in place: a warp reads exactly the rows it then writes)
+    p.x = x_hi; p.w = m->weffT_lo + L.weff_off; p.residual = yp;
+    PV_TRY(launch_rowconv_tc(p, st));
+    // pass 3: + x_hi * w_hi + bias (+ skip connection), activation, split
+    p.w = m->weffT + L.weff_off; p.bias = m->bias_s + L.bias_s_off; p.relu = L.relu;
+    p.residual2 = res_hi; p.residual3 = res_lo; p.y = y_hi; p.y_lo = y_lo;
+    p.flops = 2.0 * B * L.Ho * L.Wo * L.To * L.taps() * L.cin * L.cout;
+    return launch_rowconv_tc(p, st);
 }
 
 // weight gradient of layer L:  dweff[Kflat][cout_s] += x^T gz,  dbias += column sums of gz
@@ -372,8 +412,188 @@ static int selftest_resback(std::string& rep) {
         fails += cmp("fused bwd: dW expConv", dwe0, dwe1, 8192);
         fails += cmp("fused bwd: db expConv | db decConv", db0, db1, 288);
     }
+    if (!rc) {
+        // split-weight variant of the backward-data kernel (precision 4): with W_lo := W_hi both products double, so the result
+        // must be exactly four times the single-weight one (all values dyadic; the tf32 rounding of H commutes with x2)
+        PV_CUDA(cudaMemset(ga0, 0, rows * 128)); PV_CUDA(cudaMemset(ga1, 0, rows * 128));
+        rc = launch_resfront_bwd_data_tc(gd, wd, we, bits, nullptr, nullptr, ga0, pr, B, 0, 0.0, 0);
+        if (!rc) rc = launch_resfront_bwd_data_tc(gd, wd, we, bits, nullptr, nullptr, ga1, pr, B, 0, 0.0, 0, wd, we);
+        if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest resback split: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rc) { rep += std::string("fused bwd: split weights            FAIL : ") + last_error() + "\n"; fails += 1; }
+        else {
+            std::vector<float> a(rows * 32), c2(rows * 32);
+            cudaMemcpy(a.data(), ga0, rows * 128, cudaMemcpyDeviceToHost); cudaMemcpy(c2.data(), ga1, rows * 128, cudaMemcpyDeviceToHost);
+            size_t bad = 0; double ref = 0;
+            for (size_t i = 0; i < rows * 32; ++i) { ref = std::max(ref, (double)std::fabs(a[i])); if (4.0f * a[i] != c2[i]) ++bad; }
+            char line[256];
+            snprintf(line, sizeof line, "%-34s %s gA(W, W) == 4 gA(W) (max |ref| %.3g), mismatches %zu of %zu\n", "fused bwd: split weights (W+W)",
+                     (bad == 0 && ref > 0) ? "PASS" : "FAIL", ref, bad, rows * 32);
+            rep += line;
+            fails += (bad == 0 && ref > 0) ? 0 : 1;
+        }
+    }
     for (float* p : {x, gd, G, M, we, weT, wd, wdT, be, E, gZ, ga0, ga1, dwd0, dwd1, dwe0, dwe1, db0, db1, part, dtmp, bd0}) cudaFree(p);
     cudaFree(bits);
+    return fails;
+}
+
+// ---- error-compensated kernels (precision 4) against the fp32 CUDA-core kernels on NON-dyadic random data: the three-MMA
+// products must agree with fp32 arithmetic to ~1e-6 (a missing lo term would show up at ~1e-3)
+static float host_tf32(float v) {
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    u = (u + 0x1000u) & 0xffffe000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+struct SplitBuf {
+    float *full = nullptr, *hi = nullptr, *lo = nullptr;
+    int upload(const std::vector<float>& h) {
+        const size_t n = h.size();
+        std::vector<float> a(n), b(n);
+        for (size_t i = 0; i < n; ++i) { a[i] = host_tf32(h[i]); b[i] = h[i] - a[i]; }
+        PV_CUDA(cudaMalloc(&full, n * 4)); PV_CUDA(cudaMalloc(&hi, n * 4)); PV_CUDA(cudaMalloc(&lo, n * 4));
+        PV_CUDA(cudaMemcpy(full, h.data(), n * 4, cudaMemcpyHostToDevice));
+        PV_CUDA(cudaMemcpy(hi, a.data(), n * 4, cudaMemcpyHostToDevice));
+        PV_CUDA(cudaMemcpy(lo, b.data(), n * 4, cudaMemcpyHostToDevice));
+        return 0;
+    }
+    void release() { cudaFree(full); cudaFree(hi); cudaFree(lo); }
+};
+
+static int selftest_x3(std::string& rep) {
+    const int B = 3;
+    const RowGeom pr = pr_geom();
+    const size_t rows = (size_t)(pr.lead + (long long)B * pr.pstride + ROW_TAIL);
+    unsigned s = 20261017u;
+    auto rnd = [&](float scale) { s = s * 1664525u + 1013904223u; return ((float)(s >> 8) / 16777216.0f - 0.5f) * 2.0f * scale; };
+    auto rows_rand = [&](std::vector<float>& v, float scale) {
+        v.resize(rows * 32);
+        for (size_t r = 0; r < rows; ++r) {
+            const long long q = (long long)r - pr.lead;
+            const bool ok = q >= 0 && q < (long long)B * pr.pstride && row_valid(pr, (int)(q % pr.pstride));
+            for (int c = 0; c < 32; ++c) v[r * 32 + c] = ok ? rnd(scale) : 0.f;
+        }
+    };
+    auto compare = [&](const char* name, const float* ref_d, const float* hi_d, const float* lo_d, size_t n, double tol) {
+        std::vector<float> a(n), h(n), l(n);
+        cudaMemcpy(a.data(), ref_d, n * 4, cudaMemcpyDeviceToHost); cudaMemcpy(h.data(), hi_d, n * 4, cudaMemcpyDeviceToHost);
+        if (lo_d) cudaMemcpy(l.data(), lo_d, n * 4, cudaMemcpyDeviceToHost); else std::fill(l.begin(), l.end(), 0.f);
+        double ref = 0, worst = 0; size_t bad = 0, nontf32 = 0;
+        for (size_t i = 0; i < n; ++i) ref = std::max(ref, (double)std::fabs(a[i]));
+        for (size_t i = 0; i < n; ++i) {
+            const double d = std::fabs((double)h[i] + (double)l[i] - (double)a[i]);
+            if (!(d <= tol * ref)) ++bad;
+            if (d > worst || d != d) worst = d;
+            if (lo_d && host_tf32(h[i]) != h[i]) ++nontf32;          // the hi half must be tf32-exact
+        }
+        char line[256];
+        snprintf(line, sizeof line, "%-34s %s max|x3 - fp32| = %.3g (%.2g of max |ref| %.3g), over tolerance %zu, hi not tf32 %zu of %zu\n", name,
+                 (bad == 0 && nontf32 == 0 && ref > 0) ? "PASS" : "FAIL", worst, ref > 0 ? worst / ref : 0.0, ref, bad, nontf32, n);
+        rep += line;
+        return (bad == 0 && nontf32 == 0 && ref > 0) ? 0 : 1;
+    };
+    int fails = 0, rc = 0;
+    std::vector<float> h;
+    SplitBuf X, RES, W3, WE, WD;
+    rows_rand(h, 1.0f); PV_TRY(X.upload(h));
+    rows_rand(h, 1.0f); PV_TRY(RES.upload(h));
+    // ---------------- conv3 'same' forward, bias + skip connection: weights [co = 32][K = 27 * 32] K-major for the tensor cores
+    {
+        std::vector<float> wk(32 * 864), wt(864 * 32), bb(32);
+        for (auto& v : wk) v = rnd(0.08f);
+        for (int co = 0; co < 32; ++co) for (int k = 0; k < 864; ++k) wt[(size_t)k * 32 + co] = wk[(size_t)co * 864 + k];
+        for (auto& v : bb) v = rnd(0.5f);
+        PV_TRY(W3.upload(wk));
+        float *wt_d, *b_d, *y0, *yh, *yl, *yp;
+        PV_CUDA(cudaMalloc(&wt_d, wt.size() * 4)); PV_CUDA(cudaMalloc(&b_d, 128));
+        PV_CUDA(cudaMemcpy(wt_d, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice)); PV_CUDA(cudaMemcpy(b_d, bb.data(), 128, cudaMemcpyHostToDevice));
+        for (float** p : {&y0, &yh, &yl, &yp}) { PV_CUDA(cudaMalloc(p, rows * 128)); PV_CUDA(cudaMemset(*p, 0, rows * 128)); }
+        const Taps tp = conv3_taps(pr.plane, pr.pw, true, +1);
+        RowConvP q;
+        memset(&q, 0, sizeof q);
+        q.x = X.full; q.xc = 32; q.w = wt_d; q.w_rows = 864; q.w_cols = 32; q.w_kmajor = 0; q.bias = b_d; q.residual = RES.full; q.y = y0; q.n = 32; q.B = B;
+        q.in_lead = pr.lead; q.in_pstride = pr.pstride; q.og = pr; q.ntap = 27; q.kc = 32;
+        for (int i = 0; i < 27; ++i) { q.off[i] = tp.off[i]; q.wr0[i] = 32 * i; q.wc0[i] = 0; }
+        rc = launch_rowconv_simt(q, 0);
+        pv_model fm;                                   // just enough of a model for conv_rows_x3
+        fm.weffT = W3.hi; fm.weffT_lo = W3.lo; fm.bias_s = b_d; fm.use_tc = true; fm.x3 = true;
+        Layer L;
+        L.k[0] = L.k[1] = L.k[2] = 3; L.cin = L.cout = L.cin_s = L.cout_s = 32; L.relu = 0; L.weff_off = 0; L.bias_s_off = 0;
+        L.Ho = L.Wo = 22; L.To = 9;
+        if (!rc) rc = conv_rows_x3(&fm, L, tp, X.hi, X.lo, pr, yh, yl, pr, RES.hi, RES.lo, yp, B, "selftest_x3", 0);
+        if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest x3 conv: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rc) { rep += std::string("x3 conv3 same fwd                  FAIL : ") + last_error() + "\n"; ++fails; }
+        else fails += compare("x3 conv3 same fwd (+bias +skip)", y0, yh, yl, rows * 32, 2e-5);
+        for (float* p : {wt_d, b_d, y0, yh, yl, yp}) cudaFree(p);
+    }
+    // ---------------- fused expand -> ReLU -> decay forward
+    {
+        std::vector<float> weT(256 * 32), we(32 * 256), wdT(32 * 256), wd(256 * 32), be(256), bd(32);
+        for (int n = 0; n < 256; ++n) for (int k = 0; k < 32; ++k) { const float v = rnd(0.3f); weT[(size_t)n * 32 + k] = v; we[(size_t)k * 256 + n] = v; }
+        for (int n = 0; n < 32; ++n) for (int k = 0; k < 256; ++k) { const float v = rnd(0.1f); wdT[(size_t)n * 256 + k] = v; wd[(size_t)k * 32 + n] = v; }
+        for (auto& v : be) v = rnd(0.5f);
+        for (auto& v : bd) v = rnd(0.5f);
+        PV_TRY(WE.upload(weT)); PV_TRY(WD.upload(wdT));
+        float *we_d, *wd_d, *be_d, *bd_d, *Ebuf, *d0, *dh, *dl; uint32_t* bits;
+        PV_CUDA(cudaMalloc(&we_d, 32768)); PV_CUDA(cudaMalloc(&wd_d, 32768)); PV_CUDA(cudaMalloc(&be_d, 1024)); PV_CUDA(cudaMalloc(&bd_d, 128));
+        PV_CUDA(cudaMemcpy(we_d, we.data(), 32768, cudaMemcpyHostToDevice)); PV_CUDA(cudaMemcpy(wd_d, wd.data(), 32768, cudaMemcpyHostToDevice));
+        PV_CUDA(cudaMemcpy(be_d, be.data(), 1024, cudaMemcpyHostToDevice)); PV_CUDA(cudaMemcpy(bd_d, bd.data(), 128, cudaMemcpyHostToDevice));
+        PV_CUDA(cudaMalloc(&Ebuf, rows * 1024)); PV_CUDA(cudaMemset(Ebuf, 0, rows * 1024));
+        for (float** p : {&d0, &dh, &dl}) { PV_CUDA(cudaMalloc(p, rows * 128)); PV_CUDA(cudaMemset(*p, 0, rows * 128)); }
+        PV_CUDA(cudaMalloc(&bits, rows * 32)); PV_CUDA(cudaMemset(bits, 0, rows * 32));
+        const int tpp = cdiv(pr.nrows, 128);
+        uint32_t* bits_t;
+        PV_CUDA(cudaMalloc(&bits_t, (size_t)B * tpp * 4096)); PV_CUDA(cudaMemset(bits_t, 0, (size_t)B * tpp * 4096));
+        RowConvP pe;
+        memset(&pe, 0, sizeof pe);
+        pe.x = X.full; pe.xc = 32; pe.w = we_d; pe.w_rows = 32; pe.w_cols = 256; pe.w_kmajor = 0; pe.bias = be_d; pe.y = Ebuf; pe.n = 256; pe.B = B;
+        pe.in_lead = pr.lead; pe.in_pstride = pr.pstride; pe.og = pr; pe.ntap = 1; pe.kc = 32; pe.relu = 1;
+        rc = launch_rowconv_simt(pe, 0);
+        RowConvP pd;
+        memset(&pd, 0, sizeof pd);
+        pd.x = Ebuf; pd.xc = 256; pd.w = wd_d; pd.w_rows = 256; pd.w_cols = 32; pd.w_kmajor = 0; pd.bias = bd_d; pd.y = d0; pd.n = 32; pd.B = B;
+        pd.in_lead = pr.lead; pd.in_pstride = pr.pstride; pd.og = pr; pd.ntap = 8; pd.kc = 32;
+        for (int j = 0; j < 8; ++j) { pd.c0[j] = 32 * j; pd.wr0[j] = 32 * j; }
+        if (!rc) rc = launch_rowconv_simt(pd, 0);
+        for (int variant = 0; variant < 2 && !rc; ++variant) {
+            PV_CUDA(cudaMemset(dh, 0, rows * 128)); PV_CUDA(cudaMemset(dl, 0, rows * 128));
+            rc = launch_resfront_fwd_x3_tc(X.hi, X.lo, WE.hi, WE.lo, WD.hi, WD.lo, be_d, bd_d, dh, dl, variant ? bits : nullptr, variant ? bits_t : nullptr, pr, B, 0.0, 0);
+            if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest x3 resfront: %s", cudaGetErrorString(cudaGetLastError()));
+            if (!rc) fails += compare(variant ? "x3 fused exp->relu->dec (train)" : "x3 fused exp->relu->dec (infer)", d0, dh, dl, rows * 32, 2e-5);
+        }
+        if (!rc) {      // the ReLU bit mask against the fp32 expanded tensor (bit 31 - e of word c / 32 <=> E[row][c] > 0)
+            std::vector<float> Eh(rows * 256);
+            std::vector<uint32_t> bh(rows * 8), bt((size_t)B * tpp * 1024);
+            cudaMemcpy(Eh.data(), Ebuf, rows * 1024, cudaMemcpyDeviceToHost); cudaMemcpy(bh.data(), bits, rows * 32, cudaMemcpyDeviceToHost);
+            cudaMemcpy(bt.data(), bits_t, bt.size() * 4, cudaMemcpyDeviceToHost);
+            size_t bad = 0, set = 0, nvalid = 0, bad_t = 0;
+            for (size_t r = 0; r < rows; ++r) {
+                const long long q = (long long)r - pr.lead;
+                if (!(q >= 0 && q < (long long)B * pr.pstride && row_valid(pr, (int)(q % pr.pstride)))) continue;
+                ++nvalid;
+                for (int c2 = 0; c2 < 256; ++c2) {
+                    const bool bit = (bh[r * 8 + c2 / 32] >> (31 - (c2 & 31))) & 1u, pos = Eh[r * 256 + c2] > 0.f;
+                    if (bit) ++set;
+                    if (bit != pos && std::fabs(Eh[r * 256 + c2]) > 1e-5f) ++bad;
+                    // the transposed copy must hold the same bit: tile = (patch, row / 128), block = (row % 128) / 32, bit = row % 32
+                    const int b2 = (int)(q / pr.pstride), rr = (int)(q % pr.pstride) - pr.row0;
+                    const size_t w = ((size_t)(b2 * tpp + rr / 128) * 4 + (rr % 128) / 32) * 256 + c2;
+                    if ((((bt[w] >> (rr % 32)) & 1u) != 0u) != bit) ++bad_t;
+                }
+            }
+            bad += bad_t;
+            char line[256];
+            snprintf(line, sizeof line, "%-34s %s %zu mismatching bits of %zu (%zu set)\n", "x3 fused fwd: ReLU bit mask", (bad == 0 && set > 0) ? "PASS" : "FAIL", bad, nvalid * 256, set);
+            rep += line;
+            fails += (bad == 0 && set > 0) ? 0 : 1;
+        }
+        if (rc) { rep += std::string("x3 fused exp->relu->dec            FAIL : ") + last_error() + "\n"; ++fails; }
+        for (float* p : {we_d, wd_d, be_d, bd_d, Ebuf, d0, dh, dl}) cudaFree(p);
+        cudaFree(bits); cudaFree(bits_t);
+    }
+    X.release(); RES.release(); W3.release(); WE.release(); WD.release();
     return fails;
 }
 
@@ -470,6 +690,7 @@ int tc_selftest(std::string& rep) {
     }
     fails += selftest_resfront(rep);
     fails += selftest_resback(rep);
+    fails += selftest_x3(rep);
     auto wbase = [&](const RowGeom& og, int xc, int n, const Taps& tp) {
         RowWgradP p;
         memset(&p, 0, sizeof p);
@@ -501,7 +722,10 @@ int tc_build_plan(pv_model* m) {
         for (int i = 0; i <= m->R; ++i) P.add(m->A(i, tr), rows_per(pr, F), rows_extra(pr, F));
         for (int i = 0; i < m->R; ++i) {
             if (!m->use_tc) P.add(m->E(i, tr), rows_per(pr, EX), rows_extra(pr, EX));   // tensor-core engine keeps E in TMEM
-            else if (tr) P.add("M" + std::to_string(i), rows_per(pr, 8), rows_extra(pr, 8));    // ... and only its ReLU bits (32 B / row)
+            else if (tr) {
+                P.add("M" + std::to_string(i), rows_per(pr, 8), rows_extra(pr, 8));    // ... and only its ReLU bits (32 B / row)
+                if (m->x3) P.add("MT" + std::to_string(i), (size_t)cdiv(pr.nrows, 128) * 1024);   // transposed copy for the weight-gradient kernel
+            }
             P.add(m->D(i, tr), rows_per(pr, F), rows_extra(pr, F));
         }
         for (const TailStep& ts : tail) {
@@ -509,6 +733,19 @@ int tc_build_plan(pv_model* m) {
             P.add(ts.out, rows_per(ts.og, F), rows_extra(ts.og, F));
         }
         P.add("U", rows_per(ug, F), rows_extra(ug, F));
+        if (m->x3) {                    // remainders (v - tf32(v)) of the tensors a compensated forward product reads, + the partial-pass buffer
+            size_t yp_per = rows_per(pr, F), yp_extra = rows_extra(pr, F);
+            P.add("a_lo0", rows_per(pr, F), rows_extra(pr, F));
+            P.add("a_lo1", rows_per(pr, F), rows_extra(pr, F));
+            P.add("D_lo", rows_per(pr, F), rows_extra(pr, F));
+            for (const TailStep& ts : tail) {
+                if (ts.copy) P.add(ts.in + "_lo", rows_per(ts.ig, F), rows_extra(ts.ig, F));
+                P.add(ts.out + "_lo", rows_per(ts.og, F), rows_extra(ts.og, F));
+                yp_per = std::max(yp_per, std::max(rows_per(ts.ig, F), rows_per(ts.og, F)));
+                yp_extra = std::max(yp_extra, std::max(rows_extra(ts.ig, F), rows_extra(ts.og, F)));
+            }
+            P.add("Yp", yp_per, yp_extra);
+        }
         for (int i = 0; i < c.scale; ++i) {
             const Layer& L = m->layers[m->li("residConv" + std::to_string(i + 1))];
             P.add("q" + std::to_string(i + 1), (size_t)L.Ho * L.Wo * L.cout_s);
@@ -534,6 +771,73 @@ int tc_build_plan(pv_model* m) {
 }
 
 // ------------------------------------------------------------------------------------------ forward
+// low-frequency skip path + depth_to_space + add + denormalise (modelsTF.py:38-53,73), shared by both forward variants
+static int tc_forward_tail(pv_model* m, int B, float* sr, bool tr, int clip_round, cudaStream_t st) {
+    Pool& P = tr ? m->pool_train : m->pool_infer;
+    const pv_cfg& c = m->cfg;
+    const RowGeom ug = g_dims(1, m->P, m->P);
+    const float* q = P["mn"];
+    if (c.scale == 3 && skip2d_supported(m->S, c.scale * c.scale)) {   // WDSRNetLRResidualPath, modelsTF.py:45-53: one fused kernel
+        const Layer &R1 = m->layers[m->li("residConv1")], &R2 = m->layers[m->li("residConv2")], &R3 = m->layers[m->li("residConv3")];
+        PV_TRY(launch_skip2d_fwd(P["mn"], m->weff + R1.weff_off, m->bias_s + R1.bias_s_off, m->weff + R2.weff_off, m->bias_s + R2.bias_s_off,
+                                 m->weff + R3.weff_off, m->bias_s + R3.bias_s_off, B, m->S, c.scale * c.scale, P["q1"], P["q2"], P["q3"], st));
+        q = P["q3"];
+    } else {
+        for (int i = 0; i < c.scale; ++i) {
+            float* out = P["q" + std::to_string(i + 1)];
+            PV_TRY(conv_fwd(m, m->li("residConv" + std::to_string(i + 1)), q, out, nullptr, B, st));
+            q = out;
+        }
+    }
+    return launch_tail_rows(P["U"], ug, m->F, q, B, m->P, c.scale, c.mean, c.std, clip_round, sr, st);
+}
+
+// precision 4 ("tf32x3"): the same graph with every tensor-core product compensated (resblock_x3_tc.cu, conv_rows_x3).  The hi
+// arrays (tf32(v)) are the ones the backward pass reads, exactly as in the single-pass engine; the lo arrays live only here.
+static int tc_forward_x3(pv_model* m, int B, float* sr, bool tr, int clip_round, cudaStream_t st) {
+    Pool& P = tr ? m->pool_train : m->pool_infer;
+    const RowGeom pr = pr_geom(m->T);
+    const int F = m->F;
+    const Taps same = conv3_taps(pr.plane, pr.pw, true, +1);
+    const std::vector<TailStep> tail = tail_plan(m);
+    const RowGeom ug = g_dims(1, m->P, m->P);
+    float* const yp = P["Yp"];
+    auto alo = [&](int i) { return P[(i & 1) ? "a_lo1" : "a_lo0"]; };
+    const Layer& L0 = m->layers[m->li("mainConv1")];
+    PV_TRY(launch_first_conv_pr(P["xn"], m->weff + L0.weff_off, m->bias_s + L0.bias_s_off, B, m->S, m->T, P[m->A(0, tr)], pr, st, alo(0)));
+    for (int i = 0; i < m->R; ++i) {                                   // ResConv3D, modelsTF.py:177-189
+        const int e = m->li("expConv_" + std::to_string(i));
+        const Layer &Le = m->layers[e], &Ld = m->layers[e + 1];
+        const double fl = 2.0 * B * Le.Ho * Le.Wo * Le.To * ((double)Le.cin * Le.cout + (double)Ld.cin * Ld.cout);
+        PV_TRY(launch_resfront_fwd_x3_tc(P[m->A(i, tr)], alo(i), m->weffT + Le.weff_off, m->weffT_lo + Le.weff_off, m->weffT + Ld.weff_off,
+                                         m->weffT_lo + Ld.weff_off, m->bias_s + Le.bias_s_off, m->bias_s + Ld.bias_s_off, P[m->D(i, tr)], P["D_lo"],
+                                         tr ? reinterpret_cast<uint32_t*>(P["M" + std::to_string(i)]) : nullptr,
+                                         tr ? reinterpret_cast<uint32_t*>(P["MT" + std::to_string(i)]) : nullptr, pr, B, fl, st));
+        PV_TRY(conv_rows_x3(m, m->layers[e + 2], same, P[m->D(i, tr)], P["D_lo"], pr, P[m->A(i + 1, tr)], alo(i + 1), pr, P[m->A(i, tr)], alo(i),
+                            yp, B, "norm_fwd_x3", st));
+    }
+    const Taps valid = conv3_taps(576, 24, false, +1);
+    for (size_t k = 0; k < tail.size(); ++k) {
+        const TailStep& ts = tail[k];
+        const float *in_hi, *in_lo;
+        if (k == 0 || ts.copy) {
+            const float* src_hi = k == 0 ? P[m->A(m->R, tr)] : P[tail[k - 1].out];
+            const float* src_lo = k == 0 ? alo(m->R) : P[tail[k - 1].out + "_lo"];
+            const RowGeom sg = k == 0 ? pr : tail[k - 1].og;
+            PV_TRY(launch_pr_to_g_reflect(src_hi, sg, P[ts.in], ts.ig, B, F, st, ts.pad));
+            PV_TRY(launch_pr_to_g_reflect(src_lo, sg, P[ts.in + "_lo"], ts.ig, B, F, st, ts.pad));
+            in_hi = P[ts.in]; in_lo = P[ts.in + "_lo"];
+        } else {
+            in_hi = P[tail[k - 1].out]; in_lo = P[tail[k - 1].out + "_lo"];
+        }
+        const Layer& L = m->layers[m->li("convReducer_" + std::to_string(k + 1))];
+        PV_TRY(conv_rows_x3(m, L, valid, in_hi, in_lo, ts.ig, P[ts.out], P[ts.out + "_lo"], ts.og, nullptr, nullptr, yp, B, "reducer_fwd_x3", st));
+    }
+    PV_TRY(conv_rows_x3(m, m->layers[m->li("upscaleConv1")], valid, P[tail.back().out], P[tail.back().out + "_lo"], tail.back().og, P["U"], nullptr, ug,
+                        nullptr, nullptr, yp, B, "upscale_fwd_x3", st));
+    return tc_forward_tail(m, B, sr, tr, clip_round, st);
+}
+
 int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip_round, cudaStream_t st) {
     Pool& P = tr ? m->pool_train : m->pool_infer;
     PV_TRY(P.ensure(B, st));
@@ -548,7 +852,9 @@ int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip
 
     PV_TRY(launch_prep(lr, B, m->S * m->S, m->T, c.mean, c.std, P["xn"], P["mn"], st));
     const Layer& L0 = m->layers[m->li("mainConv1")];
-    PV_TRY(launch_first_conv_pr(P["xn"], m->weff + L0.weff_off, m->bias_s + L0.bias_s_off, B, m->S, m->T, P[m->A(0, tr)], pr, st));
+    if (m->x3) return tc_forward_x3(m, B, sr, tr, clip_round, st);
+    PV_TRY(launch_first_conv_pr(P["xn"], m->weff + L0.weff_off, m->bias_s + L0.bias_s_off, B, m->S, m->T, P[m->A(0, tr)], pr, st, nullptr,
+                                m->use_tc ? 1 : 0));
     for (int i = 0; i < m->R; ++i) {                                   // ResConv3D, modelsTF.py:177-189
         const int e = m->li("expConv_" + std::to_string(i));
         const Layer &Le = m->layers[e], &Ld = m->layers[e + 1];
@@ -574,21 +880,7 @@ int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip
         PV_TRY(conv_rows(m, L, valid, P[ts.in], F, ts.ig, P[ts.out], ts.og, nullptr, B, "reducer_fwd", st));
     }
     PV_TRY(conv_rows(m, m->layers[m->li("upscaleConv1")], valid, P[tail.back().out], F, tail.back().og, P["U"], ug, nullptr, B, "upscale_fwd", st, false));
-    const float* q = P["mn"];
-    if (c.scale == 3 && skip2d_supported(m->S, c.scale * c.scale)) {   // WDSRNetLRResidualPath, modelsTF.py:45-53: one fused kernel
-        const Layer &R1 = m->layers[m->li("residConv1")], &R2 = m->layers[m->li("residConv2")], &R3 = m->layers[m->li("residConv3")];
-        PV_TRY(launch_skip2d_fwd(P["mn"], m->weff + R1.weff_off, m->bias_s + R1.bias_s_off, m->weff + R2.weff_off, m->bias_s + R2.bias_s_off,
-                                 m->weff + R3.weff_off, m->bias_s + R3.bias_s_off, B, m->S, c.scale * c.scale, P["q1"], P["q2"], P["q3"], st));
-        q = P["q3"];
-    } else {
-        for (int i = 0; i < c.scale; ++i) {
-            float* out = P["q" + std::to_string(i + 1)];
-            PV_TRY(conv_fwd(m, m->li("residConv" + std::to_string(i + 1)), q, out, nullptr, B, st));
-            q = out;
-        }
-    }
-    PV_TRY(launch_tail_rows(P["U"], ug, F, q, B, m->P, c.scale, c.mean, c.std, clip_round, sr, st));
-    return 0;
+    return tc_forward_tail(m, B, sr, tr, clip_round, st);
 }
 
 // ------------------------------------------------------------------------------------------ backward
@@ -618,7 +910,7 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int st
     t->rq.reset(t->wg_partial_floats);        // deferred partial reductions of this pass: one launch per bucket, before wn_bwd
     PV_CUDA(cudaMemsetAsync(t->dweff, 0, m->nweff * sizeof(float), st));
     PV_CUDA(cudaMemsetAsync(t->dbias_s, 0, m->nbias_s * sizeof(float), st));
-    PV_TRY(launch_tail_bwd_rows(g_sr, B, m->P, c.scale, c.std, P["g_U"], ug, F, P["g_tail"], st));
+    PV_TRY(launch_tail_bwd_rows(g_sr, B, m->P, c.scale, c.std, P["g_U"], ug, F, P["g_tail"], st, m->use_tc ? 1 : 0));
     if (c.scale == 3 && skip2d_supported(m->S, c.scale * c.scale) &&
         skip2d_partial_floats(B, m->S, c.scale * c.scale) <= t->wg_partial_floats) {   // ---- 2-D skip path: one fused kernel + a fixed-order reduction
         const Layer &R1 = m->layers[m->li("residConv1")], &R2 = m->layers[m->li("residConv2")], &R3 = m->layers[m->li("residConv3")];
@@ -652,9 +944,11 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int st
             PV_TRY(dgrad_rows(m, L, valid_T, 1, P["g_" + ts.out], ts.og, P["g_" + ts.in], ts.ig, nullptr, (k > 0 && !ts.copy) ? P[ts.in] : nullptr,
                               B, "reducer_dgrad", st));
             if (k > 0 && ts.copy)
-                PV_TRY(launch_pr_to_g_reflect_bwd(P["g_" + ts.in], ts.ig, P["g_" + tail[k - 1].out], tail[k - 1].og, B, F, st, ts.pad, P[tail[k - 1].out]));
+                PV_TRY(launch_pr_to_g_reflect_bwd(P["g_" + ts.in], ts.ig, P["g_" + tail[k - 1].out], tail[k - 1].og, B, F, st, ts.pad, P[tail[k - 1].out],
+                                                  m->use_tc ? 1 : 0));
         }
-        PV_TRY(launch_pr_to_g_reflect_bwd(P["g_" + tail[0].in], tail[0].ig, P["g_a" + std::to_string(R & 1)], pr, B, F, st, tail[0].pad));
+        PV_TRY(launch_pr_to_g_reflect_bwd(P["g_" + tail[0].in], tail[0].ig, P["g_a" + std::to_string(R & 1)], pr, B, F, st, tail[0].pad, nullptr,
+                                          m->use_tc ? 1 : 0));
     }
     }   // stage != 1
     const int i_hi = stage == 1 ? isplit - 1 : R - 1, i_lo = stage == 0 ? isplit : 0;
@@ -670,10 +964,12 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int st
             PV_TRY(launch_resfront_bwd_weight_tc(P[m->A(i, true)], P["g_D"], m->weffT + Le.weff_off, m->weff + Ld.weff_off,
                                                  m->bias_s + Le.bias_s_off, t->dweff + Ld.weff_off, t->dweff + Le.weff_off,
                                                  t->dbias_s + Le.bias_s_off, t->dbias_s + Ld.bias_s_off, pr, B, t->wg_partials,
-                                                 t->wg_partial_floats, fl, st, &t->rq));
+                                                 t->wg_partial_floats, fl, st, &t->rq,
+                                                 m->x3 ? reinterpret_cast<const uint32_t*>(P["MT" + std::to_string(i)]) : nullptr));
             PV_TRY(launch_resfront_bwd_data_tc(P["g_D"], m->weff + Ld.weff_off, m->weff + Le.weff_off,
                                                reinterpret_cast<const uint32_t*>(P["M" + std::to_string(i)]), G,
-                                               i == 0 ? P[m->A(0, true)] : nullptr, gin, pr, B, 1, fl, st));
+                                               i == 0 ? P[m->A(0, true)] : nullptr, gin, pr, B, 1, fl, st,
+                                               m->x3 ? m->weff_lo + Ld.weff_off : nullptr, m->x3 ? m->weff_lo + Le.weff_off : nullptr));
             continue;
         }
         PV_TRY(wgrad_rows(t, Ld, wide, P[m->E(i, true)], EX, pr, P["g_D"], pr, B, "dec_wgrad", st));

@@ -139,7 +139,8 @@ __device__ __forceinline__ float block_sum_128(float v, float* red) {
 __global__ void __launch_bounds__(128) wn_prep_kernel(const WnLayer* __restrict__ tab, int nlayers,
                                                       const float* __restrict__ params, float* __restrict__ weff,
                                                       float* __restrict__ weffT, float* __restrict__ bias_s,
-                                                      float* __restrict__ scale) {
+                                                      float* __restrict__ scale, float* __restrict__ weff_lo,
+                                                      float* __restrict__ weffT_lo) {
     pdl_grid_wait();
     __shared__ float red[4];
     int co;
@@ -158,12 +159,17 @@ __global__ void __launch_bounds__(128) wn_prep_kernel(const WnLayer* __restrict_
     }
     for (int k = threadIdx.x; k < K; k += 128) {
         const int tap = k / L.cin, ci = k % L.cin;
-        float w = v[(long long)k * L.cout + co] * sc;
+        const float wf = v[(long long)k * L.cout + co] * sc;
+        float w = wf;
         if (L.round_tf32) w = to_tf32(w);
         const int rt = row_tap(L, tap);
         weff[L.weff_off + ((long long)rt * L.cin_s + ci) * L.cout_s + co] = w;
         if (L.mode == 0) weffT[L.weffT_off + ((long long)(L.taps - 1 - tap) * L.cout_s + co) * L.cin_s + ci] = w;
         else weffT[L.weffT_off + (long long)co * (L.taps * L.cin_s) + (long long)rt * L.cin_s + ci] = w;
+        if (weff_lo && L.mode == 1) {       // error-compensated engine: the remainder of the tf32 rounding, same two layouts
+            weff_lo[L.weff_off + ((long long)rt * L.cin_s + ci) * L.cout_s + co] = wf - w;
+            weffT_lo[L.weffT_off + (long long)co * (L.taps * L.cin_s) + (long long)rt * L.cin_s + ci] = wf - w;
+        }
     }
 }
 
@@ -315,9 +321,9 @@ int launch_tail_bwd(const float* dsr, int B, int P, int scale, float stdv, float
 }
 
 int launch_wn_prep(const WnLayer* tab, int nlayers, int nblocks, const float* params, float* weff, float* weffT,
-                   float* bias_s, float* scale, cudaStream_t st) {
+                   float* bias_s, float* scale, cudaStream_t st, float* weff_lo, float* weffT_lo) {
     PV_TIMED("wn_prep", st);
-    PV_CUDA(launch_pdl_simple(wn_prep_kernel, nblocks, 128, 0, st, tab, nlayers, params, weff, weffT, bias_s, scale));
+    PV_CUDA(launch_pdl_simple(wn_prep_kernel, nblocks, 128, 0, st, tab, nlayers, params, weff, weffT, bias_s, scale, weff_lo, weffT_lo));
     PV_LAUNCH_CHECK();
     return 0;
 }

@@ -75,10 +75,14 @@ struct ResPipeArgs {
     int round_tf32;
 };
 
-template <int MODE>
+// WSPLIT (backward-data of the error-compensated engine, precision 4): both weight matrices come as hi + lo (hi = tf32(w),
+// lo = w - hi) and every product is issued twice, T.W_hi + T.W_lo -- the rounding of the weights is a SYSTEMATIC perturbation
+// of the data-gradient chain (the same for every row, accumulating over the 36 layers), unlike the rounding of the gradients.
+template <int MODE, bool WSPLIT>
 __global__ void __launch_bounds__(respipe_threads(respipe_groups(MODE)), 1)
 resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant__ CUtensorMap tm_w1,
-                     const __grid_constant__ CUtensorMap tm_w2, const ResPipeArgs a) {
+                     const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w1l,
+                     const __grid_constant__ CUtensorMap tm_w2l, const ResPipeArgs a) {
     constexpr int RPG = respipe_groups(MODE), RPP_THREADS = respipe_threads(RPG), NEF = respipe_nef(RPG);
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[14 + NEF];
@@ -86,10 +90,12 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
     __shared__ __align__(16) float s_b1[256];
     __shared__ __align__(16) float s_b2[32];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    constexpr uint32_t WBYTES = WSPLIT ? 131072u : 65536u;
     const uint32_t w1_smem = base;                  // [256 rows x 128 B]: two halves of 128 rows
     const uint32_t w2_smem = base + 32768;          // 8 K-chunks x [32 rows x 128 B]
-    const uint32_t t_smem = base + 65536;           // 3 stages x [128 rows x 128 B]
-    uint8_t* const io_scratch = smem_raw + (base - smem_u32(smem_raw)) + 65536 + 3 * 16384;   // 8 epilogue warps x 2 KB (rowio.cuh)
+    const uint32_t w1l_smem = base + 65536, w2l_smem = base + 98304;     // WSPLIT: the lo halves, same layouts
+    const uint32_t t_smem = base + WBYTES;          // 3 stages x [128 rows x 128 B]
+    uint8_t* const io_scratch = smem_raw + (base - smem_u32(smem_raw)) + WBYTES + 3 * 16384;   // 8 epilogue warps x 2 KB (rowio.cuh)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto BAR = [&](int i) { return smem_u32(&bars[i]); };
     const int FULL = 0, EMPTY = 3, WBAR = 6, EFULL = 7, EREADY = 7 + NEF, DFULL = 10 + NEF, DFREE = 12 + NEF;
@@ -115,9 +121,13 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
     if (warp == 0) {
         if (elect_one_sync()) {
             tma_prefetch_desc(&tm_t);
-            mbar_arrive_expect_tx(BAR(WBAR), 65536);
+            mbar_arrive_expect_tx(BAR(WBAR), WBYTES);
             tma_load_2d(w1_smem, &tm_w1, BAR(WBAR), 0, 0);
             for (int j = 0; j < 8; ++j) tma_load_2d(w2_smem + j * 4096, &tm_w2, BAR(WBAR), 32 * j, 0);
+            if (WSPLIT) {
+                tma_load_2d(w1l_smem, &tm_w1l, BAR(WBAR), 0, 0);
+                for (int j = 0; j < 8; ++j) tma_load_2d(w2l_smem + j * 4096, &tm_w2l, BAR(WBAR), 32 * j, 0);
+            }
             pdl_wait();
             pdl_trigger();
             for (int tl = 0; tl < my_tiles; ++tl) {
@@ -147,6 +157,11 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                     const uint32_t t_lo = ((t_smem + stg * 16384) >> 4) | LO32, w_lo = ((w1_smem + h * 16384) >> 4) | LO32;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) umma_ss_tf32_lohi(tmem + eb * 128, t_lo + 2 * ks, w_lo + 2 * ks, HI32, IDESC1, ks > 0);
+                    if (WSPLIT) {
+                        const uint32_t wl_lo = ((w1l_smem + h * 16384) >> 4) | LO32;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) umma_ss_tf32_lohi(tmem + eb * 128, t_lo + 2 * ks, wl_lo + 2 * ks, HI32, IDESC1, 1u);
+                    }
                     if (h == 1) umma_commit(BAR(EMPTY + stg));
                     umma_commit(BAR(EFULL + u % NEF));
                 }
@@ -160,6 +175,10 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                     for (int ks = 0; ks < 16; ++ks) {
                         const uint64_t bdesc = smem_desc(HI, w2_smem + (4 * h + (ks >> 2)) * 4096) + 2 * (ks & 3);
                         umma_ts<true>(tmem + 384 + 32 * db, tmem + eb * 128 + ks * 8, bdesc, IDESC2, (h > 0 || ks > 0) ? 1u : 0u);
+                        if (WSPLIT) {
+                            const uint64_t bl = smem_desc(HI, w2l_smem + (4 * h + (ks >> 2)) * 4096) + 2 * (ks & 3);
+                            umma_ts<true>(tmem + 384 + 32 * db, tmem + eb * 128 + ks * 8, bl, IDESC2, 1u);
+                        }
                     }
                     if (h == 1) umma_commit(BAR(DFULL + db));
                 }
@@ -335,6 +354,7 @@ struct ResBwdWeightArgs {
     int B, tiles_per_patch;
     RowGeom g;
     const float* bias_e;
+    const uint32_t* mask_t;            // nullable: [tile][4][256] transposed ReLU bits of the forward pass (precision 4)
     float* partials;                   // [cta][4][128][32]: dWd half 0, half 1, dWe^T half 0, half 1
     float* db_partials;                // [cta][groups][256 (dbe)] then [cta][groups x 4 warps][32 (dbd)]
 };
@@ -457,6 +477,11 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
             tc_fence_after();
             const float be = s_be[h * 128 + q * 32 + lane];           // this thread's channel
             float zs[4] = {0.f, 0.f, 0.f, 0.f};               // four independent chains for the bias-gradient row sum
+            uint32_t mt[2] = {0u, 0u};
+            if (a.mask_t) {
+                const uint32_t* mp = a.mask_t + ((size_t)(t_lo + tl) * 4 + sub * 2) * 256 + h * 128 + q * 32 + lane;
+                mt[0] = __ldg(mp); mt[1] = __ldg(mp + 256);
+            }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t e[32], v[32];
@@ -466,7 +491,9 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
 #pragma unroll
                 for (int k = 0; k < 32; ++k) {
                     const float x = fmaxf(__uint_as_float(e[k]) + be, 0.f);
-                    const bool pos = x > 0.f;                              // tf.nn.relu's gradient convention: 0 at E == 0
+                    // tf.nn.relu's gradient convention: 0 at E == 0.  With the forward's mask the value and the mask may disagree
+                    // on elements within rounding distance of zero; the mask is what the data path used, so it decides gZ.
+                    const bool pos = a.mask_t ? ((mt[c] >> k) & 1u) != 0u : x > 0.f;
                     zs[k & 3] += pos ? __uint_as_float(v[k]) : 0.f;        // bias gradient from the unrounded value
                     e[k] = tf32_bump(__float_as_uint(x));
                     v[k] = pos ? tf32_bump(v[k]) : 0u;
@@ -515,8 +542,9 @@ resfront_reduce_kernel(const float* __restrict__ partials, const float* __restri
     resfront_reduce_body(blockIdx.x, partials, dbp, ncta, dwd, dwe, dbe, dbd, sm);
 }
 
-template <int MODE>
-static int launch_respipe(const float* t, const float* w1, const float* w2, const ResPipeArgs& a0, const char* tag, double flops, cudaStream_t st) {
+template <int MODE, bool WSPLIT = false>
+static int launch_respipe(const float* t, const float* w1, const float* w2, const ResPipeArgs& a0, const char* tag, double flops, cudaStream_t st,
+                          const float* w1_lo = nullptr, const float* w2_lo = nullptr) {
     ResPipeArgs a = a0;
     a.tiles_per_patch = cdiv(a.g.nrows, 128);
     const long long rows = a.g.lead + (long long)a.B * a.g.pstride + ROW_TAIL;
@@ -524,16 +552,22 @@ static int launch_respipe(const float* t, const float* w1, const float* w2, cons
     PV_TRY(make_tmap_2d(&tm_t, t, rows, 32, 128, 32, 0));
     PV_TRY(make_tmap_2d(&tm_w1, w1, 256, 32, 256, 32, 0));      // [256 rows][32]: We^T (fwd) | Wd (bwd)
     PV_TRY(make_tmap_2d(&tm_w2, w2, 32, 256, 32, 32, 0));       // [32 rows][256]: Wd^T (fwd) | We (bwd)
-    const size_t smem = 1024 + 65536 + 3 * 16384 + 4 * respipe_groups(MODE) * ROWIO_SCRATCH_BYTES;
+    CUtensorMap tm_w1l = tm_w1, tm_w2l = tm_w2;
+    if (WSPLIT) {
+        if (!w1_lo || !w2_lo) return set_error(PV_ERR_BAD_ARG, "resfront: split weights requested without the lo matrices");
+        PV_TRY(make_tmap_2d(&tm_w1l, w1_lo, 256, 32, 256, 32, 0));
+        PV_TRY(make_tmap_2d(&tm_w2l, w2_lo, 32, 256, 32, 32, 0));
+    }
+    const size_t smem = 1024 + (WSPLIT ? 131072 : 65536) + 3 * 16384 + 4 * respipe_groups(MODE) * ROWIO_SCRATCH_BYTES;
     static size_t attr[16] = {};
-    PV_CUDA(ensure_dyn_smem(resfront_pipe_kernel<MODE>, smem, attr));
+    PV_CUDA(ensure_dyn_smem(resfront_pipe_kernel<MODE, WSPLIT>, smem, attr));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = a.B * a.tiles_per_patch;
     const int grid = ntiles < sms ? ntiles : sms;
-    PV_TIMED(tag, st, flops, 0.0, 2.0 * 2.0 * (double)ntiles * 128.0 * 32.0 * 256.0);
-    PV_CUDA(launch_pdl(resfront_pipe_kernel<MODE>, grid, respipe_threads(respipe_groups(MODE)), smem, st, tm_t, tm_w1, tm_w2, a));
+    PV_TIMED(tag, st, flops, 0.0, (WSPLIT ? 2.0 : 1.0) * 2.0 * 2.0 * (double)ntiles * 128.0 * 32.0 * 256.0);
+    PV_CUDA(launch_pdl(resfront_pipe_kernel<MODE, WSPLIT>, grid, respipe_threads(respipe_groups(MODE)), smem, st, tm_t, tm_w1, tm_w2, tm_w1l, tm_w2l, a));
     PV_LAUNCH_CHECK();
     return 0;
 }
@@ -554,10 +588,11 @@ int launch_resfront_fwd_tc(const float* x, const float* weT_exp, const float* we
 // gA = ((gD Wd^T) .* relu_bits) We + G  (.* relumask).  w_dec [256][32] (= weff of decConv), w_exp [32][256] (= weff of expConv)
 int launch_resfront_bwd_data_tc(const float* gd, const float* w_dec, const float* w_exp, const uint32_t* relu_bits,
                                 const float* residual, const float* relumask, float* ga, const RowGeom& g,
-                                int B, int round_tf32, double flops, cudaStream_t st) {
+                                int B, int round_tf32, double flops, cudaStream_t st, const float* w_dec_lo, const float* w_exp_lo) {
     ResPipeArgs a;
     memset(&a, 0, sizeof a);
     a.B = B; a.g = g; a.mask = const_cast<uint32_t*>(relu_bits); a.residual = residual; a.relumask = relumask; a.out = ga; a.round_tf32 = round_tf32;
+    if (w_dec_lo || w_exp_lo) return launch_respipe<1, true>(gd, w_dec, w_exp, a, "resfront_bwd_data_w2", flops, st, w_dec_lo, w_exp_lo);
     return launch_respipe<1>(gd, w_dec, w_exp, a, "resfront_bwd_data", flops, st);
 }
 
@@ -567,10 +602,11 @@ namespace pv {
 // weight / bias gradients of expConv and decConv of one block, E and gZ recomputed on chip
 int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* weT_exp, const float* w_dec, const float* bias_e,
                                   float* dw_dec, float* dw_exp, float* db_exp, float* db_dec, const RowGeom& g, int B,
-                                  float* partials, size_t partial_floats, double flops, cudaStream_t st, ReduceQueue* rq) {
+                                  float* partials, size_t partial_floats, double flops, cudaStream_t st, ReduceQueue* rq,
+                                  const uint32_t* relu_bits_t) {
     ResBwdWeightArgs a;
     memset(&a, 0, sizeof a);
-    a.B = B; a.tiles_per_patch = cdiv(g.nrows, 128); a.g = g; a.bias_e = bias_e;
+    a.B = B; a.tiles_per_patch = cdiv(g.nrows, 128); a.g = g; a.bias_e = bias_e; a.mask_t = relu_bits_t;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -1,0 +1,301 @@
+// resblock_x3_tc.cu -- the fused expand (x8) -> ReLU -> decay forward of a WDSR residual block (reference models/modelsTF.py:
+// 179-183) with ERROR-COMPENSATED tf32 products (pv_cfg.precision = 4, "tf32x3").
+//
+// Why (profiles/r02_tf32_numerics_study.md): the L1 shift loss differentiates to sign(residual), so a forward SR error of 3e-4
+// (single-pass tf32, 10-bit operands through 40 layers) flips the sign of ~0.1 % of the pixels and puts a ~1e-2 error on every
+// gradient tensor, whatever the precision of the backward pass.  The north_star's 1e-3 gradient bar therefore needs an
+// fp32-grade FORWARD.  Every operand is carried as hi + lo with hi = tf32(v) (exact in the MMA) and lo = v - hi (|lo| <= 2^-11 |v|,
+// truncated to tf32 by the tensor core: 2^-21 overall), and every product is
+//        x w  ~=  x_hi w_hi + x_lo w_hi + x_hi w_lo                     (three kind::tf32 MMAs into one fp32 accumulator).
+//
+// Per 128-row tile and per QUARTER q of the 256 expanded channels (64 channels; the E_hi | E_lo pair of a quarter takes
+// 128 TMEM columns, so three unit buffers + two output accumulators fit the 512 columns):
+//     MMA1 (SS, N = 64)  E_q = X_hi We_hi,q^T + X_lo We_hi,q^T + X_hi We_lo,q^T            12 MMAs
+//     epilogue           v = relu(E_q + be);  ReLU bit mask;  E_hi <- tf32(v) in place,  E_lo <- v - tf32(v) next to it
+//     MMA2 (TS, N = 32)  D += E_hi Wd_hi,q^T + E_lo Wd_hi,q^T + E_hi Wd_lo,q^T             24 MMAs
+//     final              D + bd -> (hi, lo) -> two row arrays
+// Pipelining as in resblock_tc.cu: the MMA thread issues MMA1 of unit u+1 before MMA2 of unit u; tcgen05 operations execute in
+// issue order, which is what makes re-using a unit buffer three units later safe.  Two epilogue groups of four warps take
+// alternate tiles.  mbarrier rule (profiles/r01_next_round_notes.md): a parity wait is only correct if the waiter sees EVERY
+// phase of its barrier, so the "E ready" barriers are indexed by (group, quarter): one waiting group, consecutive phases.
+#include "rowio.cuh"
+#include "rows.h"
+#include "tc_common.cuh"
+
+namespace pv {
+
+using namespace tc;
+int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, int cols, int box_rows, int box_cols, int swizzle_32b_atom);
+
+namespace {
+
+constexpr int RX_THREADS = 320;
+
+struct ResX3Args {
+    int B, tiles_per_patch;
+    RowGeom g;
+    const float* bias1;                // be [256]
+    const float* bias2;                // bd [32]
+    uint32_t* mask;                    // [rows][8] ReLU bit mask (training) or nullptr
+    uint32_t* mask_t;                  // [tile][4 row blocks][256 channels]: bit k = row k of the 32-row block (for the weight-gradient kernel)
+    float* out_hi;                     // D rows: tf32(D)
+    float* out_lo;                     //         D - tf32(D)
+};
+
+__device__ __forceinline__ uint32_t tf32_rn_bits(uint32_t bits) { return (bits + 0x1000u) & 0xffffe000u; }
+
+template <int TRAIN>
+__global__ void __launch_bounds__(RX_THREADS, 1)
+resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
+                       const __grid_constant__ CUtensorMap tm_w1h, const __grid_constant__ CUtensorMap tm_w1l,
+                       const __grid_constant__ CUtensorMap tm_w2h, const __grid_constant__ CUtensorMap tm_w2l, const ResX3Args a) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[20];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float s_b1[256];
+    __shared__ __align__(16) float s_b2[32];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w1h_smem = base, w1l_smem = base + 32768;            // [256 rows x 128 B] each
+    const uint32_t w2h_smem = base + 65536, w2l_smem = base + 98304;    // 8 K-chunks x [32 rows x 128 B] each
+    const uint32_t x_smem = base + 131072;                              // 2 stages x { X_hi, X_lo } x [128 rows x 128 B]
+    uint8_t* const io_scratch = smem_raw + (base - smem_u32(smem_raw)) + 131072 + 2 * 32768;   // 8 epilogue warps x 2 KB (rowio.cuh)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto BAR = [&](int i) { return smem_u32(&bars[i]); };
+    const int FULL = 0, EMPTY = 2, WBAR = 4, EFULL = 5, EREADY = 13, DFULL = 16, DFREE = 18;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); mbar_init(BAR(DFULL + i), 1); mbar_init(BAR(DFREE + i), 4); }
+        for (int i = 0; i < 8; ++i) mbar_init(BAR(EFULL + i), 1);
+        for (int i = 0; i < 3; ++i) mbar_init(BAR(EREADY + i), 4);
+        mbar_init(BAR(WBAR), 1);
+        fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i < 256; i += RX_THREADS) s_b1[i] = a.bias1[i];
+    if (threadIdx.x < 32) s_b2[threadIdx.x] = a.bias2[threadIdx.x];
+    if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;                // unit buffers (E_hi 64 | E_lo 64) at columns 0 / 128 / 256, D accumulators at 384 / 416
+    const int ntiles = a.B * a.tiles_per_patch;
+    const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            tma_prefetch_desc(&tm_xh);
+            tma_prefetch_desc(&tm_xl);
+            mbar_arrive_expect_tx(BAR(WBAR), 131072);
+            tma_load_2d(w1h_smem, &tm_w1h, BAR(WBAR), 0, 0);
+            tma_load_2d(w1l_smem, &tm_w1l, BAR(WBAR), 0, 0);
+            for (int j = 0; j < 8; ++j) {
+                tma_load_2d(w2h_smem + j * 4096, &tm_w2h, BAR(WBAR), 32 * j, 0);
+                tma_load_2d(w2l_smem + j * 4096, &tm_w2l, BAR(WBAR), 32 * j, 0);
+            }
+            pdl_wait();
+            pdl_trigger();
+            for (int tl = 0; tl < my_tiles; ++tl) {
+                const int tile = blockIdx.x + tl * gridDim.x;
+                const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
+                const long long row0 = a.g.lead + (long long)b * a.g.pstride + a.g.row0 + j * 128;
+                const uint32_t stg = tl & 1, ph = (tl >> 1) & 1;
+                mbar_wait(BAR(EMPTY + stg), ph ^ 1);
+                mbar_arrive_expect_tx(BAR(FULL + stg), 32768);
+                tma_load_2d(x_smem + stg * 32768, &tm_xh, BAR(FULL + stg), 0, (int)row0);
+                tma_load_2d(x_smem + stg * 32768 + 16384, &tm_xl, BAR(FULL + stg), 0, (int)row0);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one_sync()) {
+            constexpr uint64_t HI = smem_desc_hi(16, 1024, 2);
+            constexpr uint32_t HI32 = (uint32_t)(HI >> 32), LO32 = (uint32_t)HI;
+            constexpr uint32_t IDESC1 = instr_desc(2, 128, 64, 0, 0);
+            constexpr uint32_t IDESC2 = instr_desc(2, 128, 32, 0, 0);
+            mbar_wait(BAR(WBAR), 0);
+            tc_fence_after();
+            const int U = 4 * my_tiles;
+            for (int u = 0; u <= U; ++u) {
+                if (u < U) {                        // MMA1 of unit u
+                    const int tl = u >> 2, q = u & 3;
+                    const uint32_t stg = tl & 1, ph = (tl >> 1) & 1, eb = u % 3;
+                    if (q == 0) { mbar_wait(BAR(FULL + stg), ph); tc_fence_after(); }
+                    const uint32_t xh = ((x_smem + stg * 32768) >> 4) | LO32, xl = ((x_smem + stg * 32768 + 16384) >> 4) | LO32;
+                    const uint32_t wh = ((w1h_smem + q * 8192) >> 4) | LO32, wl = ((w1l_smem + q * 8192) >> 4) | LO32;
+                    const uint32_t d = tmem + eb * 128;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_ss_tf32_lohi(d, xh + 2 * ks, wh + 2 * ks, HI32, IDESC1, ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_ss_tf32_lohi(d, xl + 2 * ks, wh + 2 * ks, HI32, IDESC1, 1u);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) umma_ss_tf32_lohi(d, xh + 2 * ks, wl + 2 * ks, HI32, IDESC1, 1u);
+                    if (q == 3) umma_commit(BAR(EMPTY + stg));
+                    umma_commit(BAR(EFULL + (tl & 1) * 4 + q));
+                }
+                if (u >= 1) {                       // MMA2 of unit u - 1
+                    const int v = u - 1, tl = v >> 2, q = v & 3;
+                    const uint32_t eb = v % 3, db = tl & 1;
+                    mbar_wait(BAR(EREADY + eb), (v / 3) & 1);
+                    tc_fence_after();
+                    if (q == 0) { mbar_wait(BAR(DFREE + db), ((tl >> 1) & 1) ^ 1); tc_fence_after(); }
+                    const uint32_t d = tmem + 384 + 32 * db, eh = tmem + eb * 128, el = eh + 64;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t off = (uint32_t)(2 * q + (ks >> 2)) * 4096;
+                        const uint64_t bh = smem_desc(HI, w2h_smem + off) + 2 * (ks & 3), bl = smem_desc(HI, w2l_smem + off) + 2 * (ks & 3);
+                        umma_ts<true>(d, eh + ks * 8, bh, IDESC2, (q > 0 || ks > 0) ? 1u : 0u);
+                        umma_ts<true>(d, el + ks * 8, bh, IDESC2, 1u);
+                        umma_ts<true>(d, eh + ks * 8, bl, IDESC2, 1u);
+                    }
+                    if (q == 3) umma_commit(BAR(DFULL + db));
+                }
+            }
+        }
+    } else {
+        const int q4 = warp & 3;
+        const int grp = (warp - 2) >> 2;
+        const uint32_t lane_base = tmem + ((uint32_t)(q4 * 32) << 16);
+        pdl_wait();
+        for (int tl = grp; tl < my_tiles; tl += 2) {
+            const int tile = blockIdx.x + tl * gridDim.x;
+            const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
+            const int r = a.g.row0 + j * 128 + q4 * 32 + lane;
+            const bool in_patch = r < a.g.row0 + a.g.nrows && r < a.g.pstride;
+            const bool valid = in_patch && row_valid(a.g, r);
+            const long long orow = a.g.lead + (long long)b * a.g.pstride + r;
+            const uint32_t rowmask = __ballot_sync(0xffffffffu, in_patch);
+            const long long orow_w = orow - lane;
+            uint8_t* const sc = io_scratch + (warp - 2) * ROWIO_SCRATCH_BYTES;
+            const uint32_t tph = (tl >> 1) & 1;               // this group's (tl >> 1)-th tile: every barrier below sees consecutive phases
+            uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {                     // rolled: the unrolled body thrashes the instruction cache
+                const int u = 4 * tl + q;
+                const uint32_t eb = u % 3, hb = lane_base + eb * 128;
+                mbar_wait(BAR(EFULL + grp * 4 + q), tph);
+                tc_fence_after();
+                uint32_t va[32], vb[32];
+                tmem_ld32(hb, va);
+                tmem_ld32(hb + 32, vb);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (c == 0) tmem_ld_wait();               // both loads are complete after the first wait
+                    uint32_t (&cur)[32] = c ? vb : va;
+                    uint32_t lo[32];
+                    uint32_t sg[4] = {0u, 0u, 0u, 0u};
+                    uint32_t colbits = 0u;                    // TRAIN: lane e keeps the row bit-vector of channel e of this chunk
+                    const float4* be4 = reinterpret_cast<const float4*>(s_b1 + q * 64 + c * 32);
+#pragma unroll
+                    for (int e4 = 0; e4 < 8; ++e4) {
+                        const float4 bq = be4[e4];
+                        const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float v = fmaxf(__uint_as_float(cur[e4 * 4 + e]) + bb[e], 0.f);
+                            const uint32_t x = __float_as_uint(v);
+                            // (bits(v) - 1) has its sign bit set exactly when v == 0, i.e. when the pre-activation is <= 0
+                            // (tf.nn.relu's gradient convention)
+                            if (TRAIN) {
+                                sg[e4 >> 1] = __funnelshift_l(x - 1u, sg[e4 >> 1], 1);
+                                const uint32_t vote = __ballot_sync(0xffffffffu, v > 0.f);
+                                if (lane == e4 * 4 + e) colbits = vote;
+                            }
+                            const uint32_t h = tf32_rn_bits(x);
+                            cur[e4 * 4 + e] = h;
+                            lo[e4 * 4 + e] = __float_as_uint(v - __uint_as_float(h));
+                        }
+                    }
+                    tmem_st32(hb + c * 32, cur);
+                    tmem_st32(hb + 64 + c * 32, lo);
+                    if (TRAIN) {                              // word q * 2 + c of the row's mask (static register indexing under the rolled loop)
+                        const uint32_t word = ~((sg[0] << 24) | ((sg[1] & 0xffu) << 16) | ((sg[2] & 0xffu) << 8) | (sg[3] & 0xffu));
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) if (k == q * 2 + c) mw[k] = word;
+                        // transposed copy: one coalesced 128-byte store per (32 rows x 32 channels)
+                        if (a.mask_t) a.mask_t[((size_t)tile * 4 + q4) * 256 + q * 64 + c * 32 + lane] = colbits;
+                    }
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(EREADY + eb));
+            }
+            if (TRAIN && a.mask && in_patch) {
+                uint4* mp = reinterpret_cast<uint4*>(a.mask + orow * 8);
+                mp[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+                mp[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+            }
+            const uint32_t db = tl & 1;                       // == grp
+            mbar_wait(BAR(DFULL + db), tph);
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld32(lane_base + 384 + 32 * db, v);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(DFREE + db));
+            float hi[32], lo[32];
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4) {
+                const float4 bq = reinterpret_cast<const float4*>(s_b2)[g4];
+                const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float d = valid ? __uint_as_float(v[g4 * 4 + e]) + bb[e] : 0.f;
+                    const float h = __uint_as_float(tf32_rn_bits(__float_as_uint(d)));
+                    hi[g4 * 4 + e] = h;
+                    lo[g4 * 4 + e] = d - h;
+                }
+            }
+            rowio_store_rows(a.out_hi + orow_w * 32, hi, rowmask, sc);
+            rowio_store_rows(a.out_lo + orow_w * 32, lo, rowmask, sc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace
+
+// (D_hi, D_lo) = split(decConv(relu(expConv(X_hi + X_lo)))) on PR rows with compensated products.
+//   weT_exp_* [256][32], weT_dec_* [32][256] (K contiguous; hi = tf32(w), lo = w - hi), biases padded to 256 / 32.
+//   relu_bits (nullable): [rows][8] uint32 in resblock_tc.cu's format (consumed by the backward-data kernel).
+//   relu_bits_t (nullable): the same bits transposed, [tile][4][256] uint32 with bit k = row 32 * block + k of the tile, for the
+//   weight-gradient kernel (whose threads own channels): it must use the FORWARD's mask -- its own single-pass recomputation of E
+//   disagrees with the compensated forward on ~1e-4 of the elements, which alone is a ~1e-2 error on dWe (sqrt law).
+int launch_resfront_fwd_x3_tc(const float* x_hi, const float* x_lo, const float* weT_exp_hi, const float* weT_exp_lo,
+                              const float* weT_dec_hi, const float* weT_dec_lo, const float* bias_e, const float* bias_d,
+                              float* d_hi, float* d_lo, uint32_t* relu_bits, uint32_t* relu_bits_t, const RowGeom& g, int B, double flops,
+                              cudaStream_t st) {
+    ResX3Args a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.g = g; a.bias1 = bias_e; a.bias2 = bias_d; a.mask = relu_bits; a.mask_t = relu_bits_t; a.out_hi = d_hi; a.out_lo = d_lo;
+    a.tiles_per_patch = cdiv(g.nrows, 128);
+    const long long rows = g.lead + (long long)B * g.pstride + ROW_TAIL;
+    CUtensorMap tm_xh, tm_xl, tm_w1h, tm_w1l, tm_w2h, tm_w2l;
+    PV_TRY(make_tmap_2d(&tm_xh, x_hi, rows, 32, 128, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_xl, x_lo, rows, 32, 128, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_w1h, weT_exp_hi, 256, 32, 256, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_w1l, weT_exp_lo, 256, 32, 256, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_w2h, weT_dec_hi, 32, 256, 32, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_w2l, weT_dec_lo, 32, 256, 32, 32, 0));
+    const size_t smem = 1024 + 131072 + 2 * 32768 + 8 * ROWIO_SCRATCH_BYTES;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int ntiles = a.B * a.tiles_per_patch;
+    const int grid = ntiles < sms ? ntiles : sms;
+    // executed: three MMAs per product on the padded 32 x 256 shapes, both GEMMs
+    PV_TIMED(relu_bits ? "resfront_fwd_x3" : "resfront_fwd_x3_infer", st, flops, 0.0, 3.0 * 2.0 * 2.0 * (double)ntiles * 128.0 * 32.0 * 256.0);
+    if (relu_bits) {
+        static size_t attr[16] = {};
+        PV_CUDA(ensure_dyn_smem(resfront_fwd_x3_kernel<1>, smem, attr));
+        PV_CUDA(launch_pdl(resfront_fwd_x3_kernel<1>, grid, RX_THREADS, smem, st, tm_xh, tm_xl, tm_w1h, tm_w1l, tm_w2h, tm_w2l, a));
+    } else {
+        static size_t attr[16] = {};
+        PV_CUDA(ensure_dyn_smem(resfront_fwd_x3_kernel<0>, smem, attr));
+        PV_CUDA(launch_pdl(resfront_fwd_x3_kernel<0>, grid, RX_THREADS, smem, st, tm_xh, tm_xl, tm_w1h, tm_w1l, tm_w2h, tm_w2l, a));
+    }
+    PV_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace pv

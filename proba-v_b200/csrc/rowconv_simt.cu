@@ -11,6 +11,13 @@
 namespace pv {
 namespace {
 
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float round_tf32(float x) {
     uint32_t u;
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(256) rowwgrad_vec_kernel(RowWgradP p, int m_pe
 // is FMA-bound instead of load-bound, and a warp stores 8 consecutive rows x 64 B per instruction.
 __global__ void __launch_bounds__(256) first_conv_pr_kernel(const float* __restrict__ xn, const float* __restrict__ w,
                                                             const float* __restrict__ bias, int B, int S, int T,
-                                                            float* __restrict__ y, RowGeom g) {
+                                                            float* __restrict__ y, RowGeom g, float* __restrict__ y_lo, int round_tf32) {
     pdl_grid_wait();
     extern __shared__ float fsm[];
     // blockIdx.y selects a chunk of temporal planes [tc0, tc0 + tcn) (one chunk per patch measured fastest at B = 128: 47 us vs 58 us for three)
@@ -242,7 +249,32 @@ __global__ void __launch_bounds__(256) first_conv_pr_kernel(const float* __restr
                     a1[4] = fmaf(xb, wb.x, a1[4]); a1[5] = fmaf(xb, wb.y, a1[5]); a1[6] = fmaf(xb, wb.z, a1[6]); a1[7] = fmaf(xb, wb.w, a1[7]);
                 }
             }
-        float* o = y + (g.lead + (long long)b * g.pstride + (long long)(g.t0 + tc0 + tt) * g.plane + hh * g.pw + w0) * 32 + cg * 8;
+        const long long oidx = (g.lead + (long long)b * g.pstride + (long long)(g.t0 + tc0 + tt) * g.plane + hh * g.pw + w0) * 32 + cg * 8;
+        float* o = y + oidx;
+        if (y_lo) {     // error-compensated engine: y = tf32(v), y_lo = v - tf32(v)
+            float* ol = y_lo + oidx;
+            float h0[8], l0[8], h1[8], l1[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float v0 = fmaxf(a0[j], 0.f), v1 = fmaxf(a1[j], 0.f);
+                h0[j] = to_tf32(v0); l0[j] = v0 - h0[j]; h1[j] = to_tf32(v1); l1[j] = v1 - h1[j];
+            }
+            *reinterpret_cast<float4*>(o) = make_float4(h0[0], h0[1], h0[2], h0[3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(h0[4], h0[5], h0[6], h0[7]);
+            *reinterpret_cast<float4*>(ol) = make_float4(l0[0], l0[1], l0[2], l0[3]);
+            *reinterpret_cast<float4*>(ol + 4) = make_float4(l0[4], l0[5], l0[6], l0[7]);
+            if (w0 + 1 < S) {
+                *reinterpret_cast<float4*>(o + 32) = make_float4(h1[0], h1[1], h1[2], h1[3]);
+                *reinterpret_cast<float4*>(o + 36) = make_float4(h1[4], h1[5], h1[6], h1[7]);
+                *reinterpret_cast<float4*>(ol + 32) = make_float4(l1[0], l1[1], l1[2], l1[3]);
+                *reinterpret_cast<float4*>(ol + 36) = make_float4(l1[4], l1[5], l1[6], l1[7]);
+            }
+            continue;
+        }
+        if (round_tf32) {       // the output only feeds kind::tf32 MMAs, which truncate a raw fp32 operand: round to nearest here
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a0[j] = to_tf32(fmaxf(a0[j], 0.f)); a1[j] = to_tf32(fmaxf(a1[j], 0.f)); }
+        }
         *reinterpret_cast<float4*>(o) = make_float4(fmaxf(a0[0], 0.f), fmaxf(a0[1], 0.f), fmaxf(a0[2], 0.f), fmaxf(a0[3], 0.f));
         *reinterpret_cast<float4*>(o + 4) = make_float4(fmaxf(a0[4], 0.f), fmaxf(a0[5], 0.f), fmaxf(a0[6], 0.f), fmaxf(a0[7], 0.f));
         if (w0 + 1 < S) {
@@ -425,7 +457,7 @@ __device__ __forceinline__ int preimages(int i, int n, int p, int (&o)[3]) {
 // adjoint of the kernel above; `relumask` (nullable, same rows as ga): the result is multiplied by (relumask > 0), i.e. the
 // gradient flows into the ReLU output the padded tensor was made from (convReducePad_2/3 of the T = 13 graph)
 __global__ void pr_to_g_reflect_bwd_kernel(const float* __restrict__ gg0, RowGeom gg, float* __restrict__ ga, RowGeom pr,
-                                           long long n, int C4, int pad, const float* __restrict__ relumask) {
+                                           long long n, int C4, int pad, const float* __restrict__ relumask, int round_tf32) {
     pdl_grid_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -447,6 +479,9 @@ __global__ void pr_to_g_reflect_bwd_kernel(const float* __restrict__ gg0, RowGeo
         const float4 r4 = __ldg(reinterpret_cast<const float4*>(relumask) + dst * C4 + c);
         s.x = r4.x > 0.f ? s.x : 0.f; s.y = r4.y > 0.f ? s.y : 0.f; s.z = r4.z > 0.f ? s.z : 0.f; s.w = r4.w > 0.f ? s.w : 0.f;
     }
+    // the result only feeds kind::tf32 MMAs, which TRUNCATE a raw fp32 operand (a -2.4e-4 relative bias on the whole upstream
+    // gradient chain, profiles/r02_tf32_numerics_study.md): store it rounded to nearest instead
+    if (round_tf32) { s.x = to_tf32(s.x); s.y = to_tf32(s.y); s.z = to_tf32(s.z); s.w = to_tf32(s.w); }
     reinterpret_cast<float4*>(ga)[dst * C4 + c] = s;
 }
 
@@ -467,7 +502,7 @@ __global__ void tail_rows_kernel(const float* __restrict__ u, RowGeom g, int uc,
 }
 
 __global__ void tail_bwd_rows_kernel(const float* __restrict__ dsr, long long n, int P, int s, float stdv,
-                                     float* __restrict__ gu, RowGeom g, int uc, float* __restrict__ dtail) {
+                                     float* __restrict__ gu, RowGeom g, int uc, float* __restrict__ dtail, int round_tf32) {
     pdl_grid_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // index into [B,P,P,s*s]
     if (i >= n) return;
@@ -477,7 +512,7 @@ __global__ void tail_bwd_rows_kernel(const float* __restrict__ dsr, long long n,
     const int PS = P * s;
     const float v = __ldg(dsr + (b * PS + h * s + c / s) * PS + w * s + c % s) * stdv;
     dtail[i] = v;
-    gu[(g.lead + b * g.pstride + (long long)g.t0 * g.plane + h * g.pw + w) * uc + c] = v;
+    gu[(g.lead + b * g.pstride + (long long)g.t0 * g.plane + h * g.pw + w) * uc + c] = round_tf32 ? to_tf32(v) : v;   // MMA operand: see pr_to_g_reflect_bwd_kernel
 }
 
 }  // namespace
@@ -491,10 +526,10 @@ int launch_tail_rows(const float* u, RowGeom g, int uc, const float* resid, int 
     return 0;
 }
 
-int launch_tail_bwd_rows(const float* dsr, int B, int P, int scale, float stdv, float* gu, RowGeom g, int uc, float* dtail, cudaStream_t st) {
+int launch_tail_bwd_rows(const float* dsr, int B, int P, int scale, float stdv, float* gu, RowGeom g, int uc, float* dtail, cudaStream_t st, int round_tf32) {
     const long long n = (long long)B * P * P * scale * scale;
     PV_TIMED("tail_bwd", st, 0.0, (double)n * 12.0);
-    PV_CUDA(launch_pdl_simple(tail_bwd_rows_kernel, cdiv(n, 256), 256, 0, st, dsr, n, P, scale, stdv, gu, g, uc, dtail));
+    PV_CUDA(launch_pdl_simple(tail_bwd_rows_kernel, cdiv(n, 256), 256, 0, st, dsr, n, P, scale, stdv, gu, g, uc, dtail, round_tf32));
     PV_LAUNCH_CHECK();
     return 0;
 }
@@ -527,13 +562,13 @@ int launch_rowwgrad_simt(const RowWgradP& p, cudaStream_t st) {
     return 0;
 }
 
-int launch_first_conv_pr(const float* xn, const float* w, const float* bias, int B, int S, int T, float* y, RowGeom g, cudaStream_t st) {
+int launch_first_conv_pr(const float* xn, const float* w, const float* bias, int B, int S, int T, float* y, RowGeom g, cudaStream_t st, float* y_lo, int round_tf32) {
     const size_t smem = sizeof(float) * ((size_t)(T + 2) * (S + 2) * (S + 3) + 27 * 32 + 32);
     if (smem > 200 * 1024) return set_error(PV_ERR_BAD_ARG, "first_conv_pr: patch of %dx%dx%d does not fit in shared memory", S, S, T);
     static size_t attr[16] = {};
     PV_CUDA(ensure_dyn_smem(first_conv_pr_kernel, smem, attr));
     PV_TIMED("first_conv_pr", st, 2.0 * B * T * S * S * 27 * 32, 0.0);
-    PV_CUDA(launch_pdl_simple(first_conv_pr_kernel, dim3(B, 1), 256, smem, st, xn, w, bias, B, S, T, y, g));
+    PV_CUDA(launch_pdl_simple(first_conv_pr_kernel, dim3(B, 1), 256, smem, st, xn, w, bias, B, S, T, y, g, y_lo, round_tf32));
     PV_LAUNCH_CHECK();
     return 0;
 }
@@ -586,12 +621,12 @@ int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, in
 }
 
 int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st, int pad,
-                               const float* relumask) {
+                               const float* relumask, int round_tf32) {
     if (pad < 0 || pad > 1 || gg.nh != pr.nh + 2 * pad || gg.nw != pr.nw + 2 * pad || gg.nt != pr.nt)
         return set_error(PV_ERR_BAD_ARG, "pr_to_g_reflect_bwd: geometry mismatch");
     const long long n = (long long)B * pr.nt * pr.nh * pr.nw * (C / 4);
     PV_TIMED("pr_to_g_reflect_bwd", st);
-    PV_CUDA(launch_pdl_simple(pr_to_g_reflect_bwd_kernel, cdiv(n, 256), 256, 0, st, gg0, gg, ga, pr, n, C / 4, pad, relumask));
+    PV_CUDA(launch_pdl_simple(pr_to_g_reflect_bwd_kernel, cdiv(n, 256), 256, 0, st, gg0, gg, ga, pr, n, C / 4, pad, relumask, round_tf32));
     PV_LAUNCH_CHECK();
     return 0;
 }

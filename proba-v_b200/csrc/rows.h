@@ -55,6 +55,9 @@ struct RowConvP {
     int wr0[MAX_TAPS], wc0[MAX_TAPS];
     const float* bias;                 // [n] or nullptr
     const float* residual;             // [rows][n] same rows as y, or nullptr
+    const float* residual2;            // two more addends of the same shape (conv3_tc only): the error-compensated forward chains
+    const float* residual3;            //   its partial passes and the hi / lo halves of the skip connection through them
+    float* y_lo;                       // conv3_tc only: when set, y receives hi = tf32(v) and y_lo the remainder v - hi
     const float* relumask;             // [rows][n]: output multiplied by (relumask > 0), or nullptr
     float* y; int n;                   // output rows, channels per output row
     int B;
@@ -102,25 +105,35 @@ int launch_resfront_fwd_tc(const float* x, const float* weT_exp, const float* we
                            float* d, uint32_t* relu_bits, const RowGeom& g, int B, int round_tf32, double flops, cudaStream_t st);
 int launch_resfront_bwd_data_tc(const float* gd, const float* w_dec, const float* w_exp, const uint32_t* relu_bits,
                                 const float* residual, const float* relumask, float* ga, const RowGeom& g,
-                                int B, int round_tf32, double flops, cudaStream_t st);
+                                int B, int round_tf32, double flops, cudaStream_t st,
+                                const float* w_dec_lo = nullptr, const float* w_exp_lo = nullptr);   // lo halves: two MMAs per product
+// error-compensated forward (resblock_x3_tc.cu): operands and result as (hi, lo) row arrays, three MMAs per product
+int launch_resfront_fwd_x3_tc(const float* x_hi, const float* x_lo, const float* weT_exp_hi, const float* weT_exp_lo,
+                              const float* weT_dec_hi, const float* weT_dec_lo, const float* bias_e, const float* bias_d,
+                              float* d_hi, float* d_lo, uint32_t* relu_bits, uint32_t* relu_bits_t, const RowGeom& g, int B, double flops,
+                              cudaStream_t st);
 int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* weT_exp, const float* w_dec, const float* bias_e,
                                   float* dw_dec, float* dw_exp, float* db_exp, float* db_dec, const RowGeom& g, int B,
-                                  float* partials, size_t partial_floats, double flops, cudaStream_t st, ReduceQueue* rq = nullptr);
+                                  float* partials, size_t partial_floats, double flops, cudaStream_t st, ReduceQueue* rq = nullptr,
+                                  const uint32_t* relu_bits_t = nullptr);   // forward's transposed ReLU mask (resblock_x3_tc.cu) instead of sign(E)
 
 // mainConv1 (Cin = 1, 27 taps, ReLU) from the normalised dense LR [B,S,S,T] (h,w,t order) into the PR layout
+// y_lo (nullable): y receives tf32(v) and y_lo the remainder v - tf32(v) (error-compensated engine)
 int launch_first_conv_pr(const float* xn, const float* w /*[27][32] taps in (dt,dh,dw) order*/, const float* bias, int B, int S, int T,
-                         float* y, RowGeom g, cudaStream_t st);
+                         float* y, RowGeom g, cudaStream_t st, float* y_lo = nullptr, int round_tf32 = 0);
 int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, int T, RowGeom g, float* dw, float* db,
                                float* partials, size_t partial_floats, cudaStream_t st, ReduceQueue* rq = nullptr);
 // PR (or G) tensor -> G layout with the reducer's reflect padding (tf.pad REFLECT by `pad` = 0 or 1 on H and W), and its
 // adjoint (optionally multiplied by (relumask > 0): the padded tensor was a ReLU output)
 int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st, int pad = 1);
+// round_tf32: store the result rounded to nearest tf32 (it only feeds tensor-core MMAs, which would truncate it)
 int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st, int pad = 1,
-                               const float* relumask = nullptr);
+                               const float* relumask = nullptr, int round_tf32 = 0);
 
 // tail on the row layouts: sr = (depth_to_space(U[:, :, :9]) + depth_to_space(resid)) * std + mean [clip, round]; and its adjoint
 int launch_tail_rows(const float* u, RowGeom g, int uc, const float* resid, int B, int P, int scale, float mean, float stdv,
                      int clip_round, float* sr, cudaStream_t st);
-int launch_tail_bwd_rows(const float* dsr, int B, int P, int scale, float stdv, float* gu, RowGeom g, int uc, float* dtail, cudaStream_t st);
+int launch_tail_bwd_rows(const float* dsr, int B, int P, int scale, float stdv, float* gu, RowGeom g, int uc, float* dtail, cudaStream_t st,
+                         int round_tf32 = 0);
 
 }  // namespace pv

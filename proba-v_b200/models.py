@@ -13,7 +13,7 @@ import numpy as np
 from . import _buf
 from ._lib import check, lib, pv_cfg
 
-PRECISION = {"fp32": 0, "tf32": 1, "fp32_rows": 3}
+PRECISION = {"fp32": 0, "tf32": 1, "fp32_rows": 3, "tf32x3": 4}
 
 
 class Variable:

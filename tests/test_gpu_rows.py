@@ -25,7 +25,7 @@ def test_tensor_core_kernels_agree_with_cuda_core_kernels():
     assert fails == 0, report
 
 
-@pytest.mark.parametrize("precision", ["fp32_rows", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32_rows", "tf32", "tf32x3"])
 def test_forward_small_graph(small_cfg, precision):
     from probav_b200 import synth
     om, p = oracle_and_params(small_cfg, seed=1)
@@ -36,13 +36,15 @@ def test_forward_small_graph(small_cfg, precision):
     e = rel_err(got, ref)
     print(f"{precision}: SR max rel err {e:.3e}, in sigma units {np.abs(got - ref).max() / 3160.7272:.3e}")
     assert e < SR_TOL
-    if precision == "fp32_rows":
+    if precision in ("fp32_rows", "tf32x3"):
         assert np.abs(got - ref).max() / 3160.7272 < 1e-3
+    if precision == "tf32x3":
+        assert e < 2e-6        # error-compensated products: fp32-grade forward
     got_dev = m(torch.from_numpy(lr).cuda()).cpu().numpy()
     assert np.array_equal(got_dev, got)
 
 
-@pytest.mark.parametrize("precision", ["fp32_rows", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32_rows", "tf32", "tf32x3"])
 def test_forward_full_graph(full_cfg, precision):
     from probav_b200 import synth
     om, p = oracle_and_params(full_cfg, seed=4)
@@ -62,7 +64,8 @@ def _trainer(pb, m):
     return pb.ModelTrainer(m, L.shiftCompensatedL1Loss, L.shiftCompensatedcPSNR, pb.Nadam(5e-4), d + "/ckpt", d + "/log")
 
 
-@pytest.mark.parametrize("precision,cfgname,B", [("fp32_rows", "small", 4), ("fp32_rows", "full", 2), ("tf32", "small", 4), ("tf32", "full", 2)])
+@pytest.mark.parametrize("precision,cfgname,B", [("fp32_rows", "small", 4), ("fp32_rows", "full", 2), ("tf32", "small", 4), ("tf32", "full", 2),
+                                                 ("tf32x3", "small", 4), ("tf32x3", "full", 2)])
 def test_gradients(small_cfg, full_cfg, precision, cfgname, B):
     import probav_b200 as pb
     from probav_b200 import synth
@@ -77,7 +80,9 @@ def test_gradients(small_cfg, full_cfg, precision, cfgname, B):
     assert abs(lossv - float(loss)) < 1e-3 * abs(float(loss))
     assert abs(psnrv - float(cps.mean())) < 0.01
     got = t.get_grads()
-    tol = 1e-3 if precision == "fp32_rows" else TF32_GRAD_TOL
+    # tiny batches are ill-conditioned for this metric (the exact fp32 engines sit at 6e-4 on B = 2; the full-size check is
+    # test_full_batch_gradients_match_golden): tf32x3 keeps single-pass tf32 in the backward products, bounded here at 4e-3
+    tol = {"fp32_rows": 1e-3, "tf32x3": 4e-3}.get(precision, TF32_GRAD_TOL)
     worst, worst_k = 0.0, None
     for k, ref in g.items():
         if np.abs(ref.numpy()).max() == 0:
@@ -108,7 +113,7 @@ def test_train_step_tf32_tracks_oracle(small_cfg):
         assert abs(psnrv - float(cps.mean())) < 0.02, step
 
 
-@pytest.mark.parametrize("precision", ["tf32", "fp32_rows", "fp32"])
+@pytest.mark.parametrize("precision", ["tf32", "tf32x3", "fp32_rows", "fp32"])
 def test_staged_backward_buckets_are_bit_identical(small_cfg, precision):
     """pv_train_forward_backward_staged (two gradient buckets for the overlapped data-parallel all-reduce) must produce
     exactly the gradients of the one-shot call, and its two ranges must tile the gradient arena."""
@@ -130,7 +135,7 @@ def test_staged_backward_buckets_are_bit_identical(small_cfg, precision):
     ranges = []
 
     def same(a, b):
-        if precision == "tf32":         # tensor-core engine: fixed-order reductions, bit-reproducible
+        if precision in ("tf32", "tf32x3"):         # tensor-core engines: fixed-order reductions, bit-reproducible
             assert torch.equal(a, b)
         else:                           # CUDA-core twins accumulate weight gradients with atomics
             assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-12
@@ -379,6 +384,9 @@ def test_full_batch_gradients_match_golden(full_cfg, precision):
         errs.append((rel_err(got[k[5:]], ref), k[5:]))
     errs.sort(reverse=True)
     med = float(np.median([e for e, _ in errs]))
+    if os.path.isdir("gpurun_out"):          # per-tensor record for profiles/ (scratch directory of a GPU visit)
+        import json
+        json.dump({"precision": precision, "loss": lossv, "sr_err": sr_err, "errs": errs}, open(f"gpurun_out/grad_b128_{precision}.json", "w"))
     print(f"B=128 {precision}: loss {lossv:.4f} (golden {float(z['loss']):.4f}), SR max rel err {sr_err:.2e}, best shift equal on {same_shift}/128, "
           f"gradients: worst {errs[0][0]:.2e} at {errs[0][1]}, median {med:.2e}, over 1e-3: {sum(e > 1e-3 for e, _ in errs)}/{len(errs)}")
     assert sr_err < SR_TOL
