@@ -32,6 +32,39 @@ UNIT = "patches/s"
 TRAIN_GFLOP_PER_PATCH = 12.443      # 3 x 2 073 878 964 MAC x 2
 
 
+def measure_tf32_peak(dev, seconds=0.6):
+    """Measured dense tf32 tensor peak: torch.matmul (cuBLAS) 8192^3 with TF32 allowed, best of 5 (burst) and back to back for
+    `seconds` (sustained, under the power cap) -- the denominator for a kernel whose MMAs are kind::tf32.  Peak measurement
+    only: cuBLAS is not on the product path."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev, dtype=torch.float32)
+        b = torch.randn(n, n, device=dev, dtype=torch.float32)
+        for _ in range(2):
+            a @ b
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        reps = max(3, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            a @ b
+        e1.record(); torch.cuda.synchronize()
+        sus = e0.elapsed_time(e1) / reps
+        fl = 2.0 * n ** 3
+        del a, b
+        return {"tf32_tflops_burst": fl / best / 1e9, "tf32_tflops_sustained": fl / sus / 1e9, "how": "torch.matmul fp32 8192^3, allow_tf32 (cuBLAS), CUDA events"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -135,11 +168,11 @@ def run_reference(args, cfg):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "cfg/p16t9c85r12 train step (fwd+shift-L1+bwd+Nadam+cPSNR metric), BASELINE configs[1]",
                        "batch_per_gpu": cfg["batch_size"], "global_batch": cfg["batch_size"], "parallelism": "host cores",
-                       "sample_batch_per_step": b,
+                       "sample_batch_per_step": b, "same_config": b == cfg["batch_size"],
                        "note": "TensorFlow/TFA are not installable here (no wheels, no network): the reference arm is the "
                                "oracle, a PyTorch-CPU restatement of models/modelsTF.py + loss.py + trainClass.py"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps of batch {b} (of the 128-patch step), torch CPU fp32"},
+                             "sample": f"{args.steps} full steps of batch {b} after {args.warmup} warm-up, torch CPU fp32, all host threads"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -222,6 +255,30 @@ def run_b200(args, cfg):
     h2d = ws * (h_lr.numel() * 4 + h_hr.numel() * 4 + h_mk.numel())
     d2h = ws * 8
 
+    # ---- the single-pass tf32 engine on the same batch, reported BESIDE the headline (it is faster, and its SR / loss / cPSNR
+    # meet the bars, but its gradients sit at ~9e-3 against the 1e-3 bar: tests/test_gpu_rows.py::test_full_batch_gradients_match_golden)
+    side = None
+    model_tf32 = model
+    if args.precision != "tf32" and not args.no_side_tf32:
+        model_tf32 = pb.build_from_config(cfg, band="NIR", device=local, seed=0, precision="tf32")
+        tr2 = pb.ModelTrainer(model_tf32, pb.loss_from_config(L, cfg["loss"]), L.shiftCompensatedcPSNR,
+                              pb.optimizers.from_config(cfg["optimizer"], cfg["learning_rate"]), tmp + "/ckpt2", tmp + "/log2")
+        if ws > 1:
+            parallel.broadcast_(model_tf32.param_arena(), 0)
+        for _ in range(args.warmup):
+            tr2.trainStep(d_lr, d_hr, d_mk, sync=False)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            tr2.trainStep(d_lr, d_hr, d_mk, sync=False)
+        s1.record()
+        barrier()
+        ms2 = max_over_ranks(s0.elapsed_time(s1))
+        side = {"dtype": "tf32", "value": ws * B * args.steps / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / args.steps,
+                "note": "single-pass tf32 tensor-core engine, device-resident batch: SR 2.6e-4, loss and cPSNR inside the bars, gradients "
+                        "9e-3 at batch 128 (bar 1e-3), so it is not the headline"}
+
     # ---- per-kernel-class timing (CUDA events on the launch stream) for the roofline
     lib.pv_timing_reset()
     lib.pv_timing_enable(1)
@@ -238,37 +295,59 @@ def run_b200(args, cfg):
     # clip + round-half-even and the 8x8 stitch all run on the device.  Scenes are sharded by rank (replicas only).
     scene = None
     if not args.no_scene_infer:
+        # Runs on the single-pass tf32 engine: its SR agrees with the oracle to 2.6e-4 (bar 1e-3) and inference has no gradients.
+        # Per call: H2D of the LR scenes, HR scenes and masks (pinned), device patching + forward + clip/round + stitch, shift-cPSNR
+        # scoring of every 384x384 scene at targetShape (384,384,1) (reference evaluate.py:76-87), D2H of the SR scenes and scores.
         ns = args.scenes
-        lr_s, _, _ = synth.make_scene(ns, T=cfg["num_low_res_imgs"], seed=300 + rank)
-        model.predict_from_scenes(lr_s)                       # sizes the inference activation pool
+        lr_s, hr_s, mk_s = synth.make_scene(ns, T=cfg["num_low_res_imgs"], seed=300 + rank)
+        p_lr, p_hr = torch.from_numpy(lr_s).pin_memory(), torch.from_numpy(hr_s).pin_memory()
+        p_mk = torch.from_numpy(mk_s.astype(np.uint8)).pin_memory()
+        LS = pb.Losses(tuple(hr_s.shape[1:]))
+        o_sr = torch.empty(tuple(hr_s.shape), dtype=torch.float32).pin_memory()
+        o_ps = torch.empty(ns, dtype=torch.float32).pin_memory()
+
+        def scene_call():
+            x = p_lr.to(dev, non_blocking=True)
+            y, k = p_hr.to(dev, non_blocking=True), p_mk.to(dev, non_blocking=True)
+            sr = model_tf32.predict_from_scenes(x)                                  # device tensor [ns, 384, 384, 1]
+            ps = LS.shiftCompensatedcPSNR(y, k, sr)
+            o_sr.copy_(sr, non_blocking=True)
+            o_ps.copy_(ps, non_blocking=True)
+            torch.cuda.synchronize()
+
+        scene_call()                                          # sizes the inference activation pool
         barrier()
         t0 = time.perf_counter()
         for _ in range(3):
-            model.predict_from_scenes(lr_s)
+            scene_call()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0) / 3
-        d_s = torch.from_numpy(lr_s).to(dev)                  # device-resident variant (inputs in HBM, outputs left in HBM)
-        model.predict_from_scenes(d_s)
+        d_s = torch.from_numpy(lr_s).to(dev)                  # device-resident, unscored variant (inputs in HBM, outputs left in HBM)
+        model_tf32.predict_from_scenes(d_s)
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
         for _ in range(3):
-            model.predict_from_scenes(d_s)
+            model_tf32.predict_from_scenes(d_s)
         s1.record()
         barrier()
         dms = max_over_ranks(s0.elapsed_time(s1)) / 3
-        scene = {"metric": "384x384 scene SR infer/s (9x128x128 LR in, 64 patches per scene, clip+round+stitch on device, host to host)",
-                 "value": ws * ns / dt, "unit": "scenes/s", "scenes_per_call": ns, "ms_per_scene": dt / ns * 1e3,
-                 "device_resident_value": ws * ns / (dms * 1e-3), "algorithmic_tflops": ws * ns / dt * 0.2655,
-                 "h2d_bytes_per_scene": int(lr_s[0].nbytes), "d2h_bytes_per_scene": 384 * 384 * 4}
+        scene = {"metric": "384x384 scene SR infer/s with shift-cPSNR scoring (9x128x128 LR in, 64 patches per scene, clip+round+stitch and "
+                           "cPSNR on device, host to host), BASELINE configs[3]",
+                 "dtype": "tf32", "value": ws * ns / dt, "unit": "scenes/s", "scenes_per_call": ns, "ms_per_scene": dt / ns * 1e3,
+                 "device_resident_unscored_value": ws * ns / (dms * 1e-3), "algorithmic_tflops": ws * ns / dt * 0.2655,
+                 "mean_cpsnr_random_weights_db": float(o_ps.mean()),
+                 "h2d_bytes_per_scene": int(lr_s[0].nbytes + hr_s[0].nbytes + mk_s[0].size), "d2h_bytes_per_scene": 384 * 384 * 4 + 4}
     if ws > 1:
         dist.destroy_process_group()
     if rank != 0:
         return
     peaks = load_peaks()
+    tf32_peak = measure_tf32_peak(dev)
     tot_ms = sum(v["ms"] for v in rep.values()) or 1.0
     kernels = {k: {"launches_per_step": v["launches"] // 2, "ms_per_step": v["ms"] / 2, "share": v["ms"] / tot_ms,
                    "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None,
+                   "executed_tflops": (v["exec_flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["exec_flops"] > 0 else None,
                    "gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] > 0 else None}
                for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
     top = max(rep.items(), key=lambda kv: kv[1]["ms"])
@@ -277,16 +356,27 @@ def run_b200(args, cfg):
     if os.path.exists(tf):
         traffic = json.load(open(tf)).get(top[0])          # bytes per launch from the committed ncu capture
     ach = top[1]["flops"] / (top[1]["ms"] * 1e-3) / 1e12
+    gflop_per_patch0 = TRAIN_GFLOP_PER_PATCH if os.path.splitext(os.path.basename(args.cfg))[0] == "p16t9c85r12" else sum(v["flops"] for v in rep.values()) / 2 / B / 1e9
     notes = {
         "resfront_bwd_weight": "fused expand/decay weight gradients: E^T and gE^T recomputed transposed in TMEM (not counted as algorithmic "
                                "flops), TS-mode N=32 MMAs at 39 cycles each; MMA-issue floor 82 us per launch, see DESIGN.md section 4",
+        "norm_fwd_x3": "error-compensated conv3 forward: three passes (x_lo w_hi, x_hi w_lo, x_hi w_hi) of 36 M128xN96xK8 MMAs per 126 rows, "
+                       "i.e. 3x the algorithmic MMAs by construction (the price of the 1e-3 gradient bar)",
+        "resfront_fwd_x3": "error-compensated fused expand/ReLU/decay forward: three MMAs per product, expanded tensor as hi | lo in TMEM",
         "norm_wgrad": "conv3 weight gradient as M128xN96xK8 MMAs (80 cycles each, 75 % of the M slots useful): floor 64 us per launch",
         "norm_fwd": "conv3 forward as 36 M128xN96xK8 MMAs per 126 rows: floor 47 us per launch",
         "norm_dgrad": "conv3 data gradient as 36 M128xN96xK8 MMAs per 126 rows: floor 47 us per launch",
     }
     roofline = {"kernel": top[0], "bound": "tensor", "achieved": ach, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tensor_sustained"], "traffic": traffic, "peak_source": peaks["source"] + ", bf16 sustained",
-                "frac_of_tf32_peak": ach / (0.5 * peaks["tensor_sustained"]),
+                "algorithmic_flops_per_launch": top[1]["flops"] / top[1]["launches"],
+                "executed_tflops": top[1]["exec_flops"] / (top[1]["ms"] * 1e-3) / 1e12,
+                "executed_over_algorithmic": top[1]["exec_flops"] / top[1]["flops"] if top[1]["flops"] else None,
+                "tf32_peak_measured": tf32_peak,
+                "frac_of_measured_tf32_peak": ach / tf32_peak["tf32_tflops_sustained"],
+                "executed_frac_of_measured_tf32_peak": top[1]["exec_flops"] / (top[1]["ms"] * 1e-3) / 1e12 / tf32_peak["tf32_tflops_sustained"],
+                "whole_step": {"algorithmic_tflops": value * gflop_per_patch0 / 1e3 / ws, "frac_of_bf16_sustained": value * gflop_per_patch0 / 1e3 / ws / peaks["tensor_sustained"],
+                               "frac_of_measured_tf32_peak": value * gflop_per_patch0 / 1e3 / ws / tf32_peak["tf32_tflops_sustained"]},
                 "note": "kind::tf32 MMAs run at half the bf16 rate, and an M128xNxK8 tf32 MMA costs 32 + N/2 cycles (the A-operand fetch "
                         "is not overlapped; profiles/r01_umma_rate_probe.log), so N <= 96 GEMMs cannot exceed 60 % of the tf32 pipe. "
                         + notes.get(top[0], ""),
@@ -318,12 +408,12 @@ def run_b200(args, cfg):
             "clocks": clk.summary(),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "roofline": roofline, "roofline_shift_loss": roof_loss, "kernels": kernels,
+            "roofline": roofline, "roofline_shift_loss": roof_loss, "single_pass_tf32": side, "kernels": kernels,
             "scene_infer": scene, "last_loss": lossv, "last_cpsnr": psnrv}
     if ws == 1 and not args.no_cpu_baseline:
         v, sec, cores = cpu_reference_steps(cfg, args.ref_batch, 2, 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"2 steps of batch {args.ref_batch} (of the 128-patch step) after 1 warm-up, torch CPU fp32 oracle"}
+                                "sample": f"2 full steps of batch {args.ref_batch} after 1 warm-up, torch CPU fp32 oracle, all host threads"}
     else:
         line["cpu_baseline"] = None
     emit(line)
@@ -349,13 +439,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: cfg batch_size = 128)")
-    ap.add_argument("--ref-batch", type=int, default=16, help="CPU arm: patches per step (bounded sample)")
+    ap.add_argument("--ref-batch", type=int, default=None, help="CPU arm: patches per step (default: the cfg batch, i.e. the same 128-patch step)")
     ap.add_argument("--cfg", default=os.path.join(ROOT, "cfg", "p16t9c85r12.cfg"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scene-infer", action="store_true")
+    ap.add_argument("--no-side-tf32", action="store_true", help="skip the single-pass tf32 measurement reported beside the headline")
     ap.add_argument("--scenes", type=int, default=32, help="scenes per inference call of the scene_infer leg")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3", "fp32", "fp32_rows"],
-                    help="tf32 = tcgen05 tensor-core engine (default; what TensorFlow runs on Ampere+), fp32 = CUDA-core exact mode")
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32", "tf32x3", "fp32", "fp32_rows"],
+                    help="tf32x3 = error-compensated tcgen05 engine (default: the mode that meets the north_star's 1e-3 gradient bar at "
+                         "batch 128), tf32 = single-pass tcgen05 engine (reported beside it), fp32 = CUDA-core exact mode")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -363,6 +455,8 @@ def main():
     cfg = parseConfig(args.cfg)
     if args.batch is None:
         args.batch = cfg["batch_size"]
+    if args.ref_batch is None:
+        args.ref_batch = args.batch
     if args.impl == "reference":
         run_reference(args, cfg)
     else:

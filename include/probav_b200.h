@@ -174,11 +174,16 @@ int  pv_trainer_set_lr(pv_trainer* t, float learning_rate);
 int64_t pv_launch_count(void);
 /* Per-kernel-class device timing (bench.py's roofline; no reference counterpart).  While enabled every kernel
  * launch is bracketed by CUDA events on its stream.  pv_timing_report synchronises the device and writes one line
- * per kernel class: "name launches total_ms algorithmic_flops algorithmic_bytes\n"; returns the number of bytes
+ * per kernel class: "name launches total_ms algorithmic_flops algorithmic_bytes executed_flops\n"; returns the number of bytes
  * written (or needed, if larger than cap). */
 /* Device self-test: every tensor-core kernel configuration against the CUDA-core kernel on the same random buffers.
  * Returns the number of failing configurations (0 = all agree); the per-configuration report goes to buf. */
 int  pv_selftest(char* buf, int cap);
+/* Debug / numerics studies (no reference counterpart): copies the internal activation or gradient buffer `name` of the model's
+ * training (train = 1) or inference pool to the host (device-synchronising).  Row-engine buffer names: a0..aR, D0.., g_a0, g_a1,
+ * g_D, Gi1, Go1.., g_Go1.., U, g_U (csrc/engine_tc.cu).  Returns the buffer's length in floats (copying at most n), or a
+ * negative pv_status when the buffer does not exist. */
+int64_t pv_debug_read_buffer(pv_model* m, const char* name, int train, float* host, int64_t n);
 int  pv_timing_enable(int on);
 int  pv_timing_reset(void);
 int  pv_timing_report(char* buf, int cap);

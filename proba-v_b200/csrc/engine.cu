@@ -455,6 +455,19 @@ int pv_selftest(char* buf, int cap) {
     return fails;
 }
 
+int64_t pv_debug_read_buffer(pv_model* m, const char* name, int train, float* host, int64_t n) {
+    if (!m || !name) return set_error(PV_ERR_BAD_ARG, "pv_debug_read_buffer: null argument");
+    Pool& P = train ? m->pool_train : m->pool_infer;
+    float* d = P[name];
+    if (!d) return set_error(PV_ERR_BAD_ARG, "pv_debug_read_buffer: no buffer '%s' in the %s pool", name, train ? "training" : "inference");
+    int64_t len = 0;
+    for (auto& s : P.spec) if (s.name == name) len = (int64_t)(s.per * (size_t)P.cap + s.extra);
+    PV_CUDA(cudaSetDevice(m->device));
+    PV_CUDA(cudaDeviceSynchronize());
+    if (host && n > 0) PV_CUDA(cudaMemcpy(host, d, (size_t)std::min(n, len) * sizeof(float), cudaMemcpyDeviceToHost));
+    return len;
+}
+
 int pv_timing_enable(int on) { pv::g_timing = on != 0; return 0; }
 
 int pv_timing_reset(void) {

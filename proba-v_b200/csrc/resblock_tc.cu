@@ -359,6 +359,7 @@ struct ResBwdWeightArgs {
     float* db_partials;                // [cta][groups][256 (dbe)] then [cta][groups x 4 warps][32 (dbd)]
 };
 
+template <bool FWD_MASK>     // FWD_MASK: ReLU decisions come from the forward pass's transposed bit mask (a.mask_t) instead of sign(E)
 __global__ void __launch_bounds__(RBW_THREADS, 1)
 resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_gd,
                            const __grid_constant__ CUtensorMap tm_x32, const __grid_constant__ CUtensorMap tm_gd32,
@@ -459,6 +460,15 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
         float dbe0 = 0.f, dbe1 = 0.f, dbd = 0.f;
         const int U = 4 * my_tiles;
         pdl_wait();                                          // the partial buffers may still be read by the previous reduction
+        // FWD_MASK: the unit's two mask words (32 rows each) for this thread's channel, fetched one unit ahead (the load's L2 / HBM
+        // latency is of the order of a unit's whole processing time)
+        auto mask_words = [&](int u2, uint32_t (&w)[2]) {
+            const int tl2 = u2 >> 2, h2 = (u2 >> 1) & 1, sub2 = u2 & 1;
+            const uint32_t* mp = a.mask_t + ((size_t)(t_lo + tl2) * 4 + sub2 * 2) * 256 + h2 * 128 + q * 32 + lane;
+            w[0] = __ldg(mp); w[1] = __ldg(mp + 256);
+        };
+        uint32_t nmt[2] = {0u, 0u};
+        if (FWD_MASK && grp < U) mask_words(grp, nmt);
 #pragma unroll 1
         for (int u = grp; u < U; u += RESBW_GROUPS) {      // with three groups unit u always lives in H buffer u % 3 == grp
             const int tl = u >> 2, h = (u >> 1) & 1, sub = u & 1;
@@ -477,11 +487,8 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
             tc_fence_after();
             const float be = s_be[h * 128 + q * 32 + lane];           // this thread's channel
             float zs[4] = {0.f, 0.f, 0.f, 0.f};               // four independent chains for the bias-gradient row sum
-            uint32_t mt[2] = {0u, 0u};
-            if (a.mask_t) {
-                const uint32_t* mp = a.mask_t + ((size_t)(t_lo + tl) * 4 + sub * 2) * 256 + h * 128 + q * 32 + lane;
-                mt[0] = __ldg(mp); mt[1] = __ldg(mp + 256);
-            }
+            uint32_t mt[2] = {nmt[0], nmt[1]};
+            if (FWD_MASK && u + RESBW_GROUPS < U) mask_words(u + RESBW_GROUPS, nmt);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t e[32], v[32];
@@ -493,7 +500,7 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
                     const float x = fmaxf(__uint_as_float(e[k]) + be, 0.f);
                     // tf.nn.relu's gradient convention: 0 at E == 0.  With the forward's mask the value and the mask may disagree
                     // on elements within rounding distance of zero; the mask is what the data path used, so it decides gZ.
-                    const bool pos = a.mask_t ? ((mt[c] >> k) & 1u) != 0u : x > 0.f;
+                    const bool pos = FWD_MASK ? ((mt[c] >> k) & 1u) != 0u : x > 0.f;
                     zs[k & 3] += pos ? __uint_as_float(v[k]) : 0.f;        // bias gradient from the unrounded value
                     e[k] = tf32_bump(__float_as_uint(x));
                     v[k] = pos ? tf32_bump(v[k]) : 0u;
@@ -626,13 +633,15 @@ int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* 
     PV_TRY(make_tmap_2d(&tm_weT, weT_exp, 256, 32, 256, 32, 0));
     PV_TRY(make_tmap_2d(&tm_wd, w_dec, 256, 32, 256, 32, 0));
     const size_t smem = 1024 + 65536 + 2 * 65536;
-    static size_t attr[16] = {};
-    PV_CUDA(ensure_dyn_smem(resfront_bwd_weight_kernel, smem, attr));
+    static size_t attr[16] = {}, attr_m[16] = {};
+    if (relu_bits_t) PV_CUDA(ensure_dyn_smem(resfront_bwd_weight_kernel<true>, smem, attr_m));
+    else PV_CUDA(ensure_dyn_smem(resfront_bwd_weight_kernel<false>, smem, attr));
     {
         // algorithmic: dWe + dWd.  Executed: E^T and gE^T are recomputed on chip, and every GEMM runs on the padded 32 x 256 shapes
         // over whole 128-row tiles: 4 GEMMs of 2 * rows * 32 * 256 flops.
         PV_TIMED("resfront_bwd_weight", st, flops, 0.0, 4.0 * 2.0 * (double)ntiles * 128.0 * 32.0 * 256.0);
-        PV_CUDA(launch_pdl(resfront_bwd_weight_kernel, grid, RBW_THREADS, smem, st, tm_x, tm_gd, tm_x32, tm_gd32, tm_weT, tm_wd, a));
+        if (relu_bits_t) PV_CUDA(launch_pdl(resfront_bwd_weight_kernel<true>, grid, RBW_THREADS, smem, st, tm_x, tm_gd, tm_x32, tm_gd32, tm_weT, tm_wd, a));
+        else PV_CUDA(launch_pdl(resfront_bwd_weight_kernel<false>, grid, RBW_THREADS, smem, st, tm_x, tm_gd, tm_x32, tm_gd32, tm_weT, tm_wd, a));
         PV_LAUNCH_CHECK();
     }
     if (deferred) {

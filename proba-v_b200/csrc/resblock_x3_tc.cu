@@ -192,11 +192,7 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                             const uint32_t x = __float_as_uint(v);
                             // (bits(v) - 1) has its sign bit set exactly when v == 0, i.e. when the pre-activation is <= 0
                             // (tf.nn.relu's gradient convention)
-                            if (TRAIN) {
-                                sg[e4 >> 1] = __funnelshift_l(x - 1u, sg[e4 >> 1], 1);
-                                const uint32_t vote = __ballot_sync(0xffffffffu, v > 0.f);
-                                if (lane == e4 * 4 + e) colbits = vote;
-                            }
+                            if (TRAIN) sg[e4 >> 1] = __funnelshift_l(x - 1u, sg[e4 >> 1], 1);
                             const uint32_t h = tf32_rn_bits(x);
                             cur[e4 * 4 + e] = h;
                             lo[e4 * 4 + e] = __float_as_uint(v - __uint_as_float(h));
@@ -206,6 +202,16 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                     tmem_st32(hb + 64 + c * 32, lo);
                     if (TRAIN) {                              // word q * 2 + c of the row's mask (static register indexing under the rolled loop)
                         const uint32_t word = ~((sg[0] << 24) | ((sg[1] & 0xffu) << 16) | ((sg[2] & 0xffu) << 8) | (sg[3] & 0xffu));
+                        // 32 x 32 bit-matrix transpose across the warp (lane = row, bit 31 - e = channel e  ->  lane = channel, bit k = row k):
+                        // reverse the bits so that bit e = channel e, then five butterfly stages
+                        colbits = __brev(word);
+#pragma unroll
+                        for (int j = 16; j >= 1; j >>= 1) {
+                            const uint32_t msk = j == 16 ? 0x0000ffffu : (j == 8 ? 0x00ff00ffu : (j == 4 ? 0x0f0f0f0fu : (j == 2 ? 0x33333333u : 0x55555555u)));
+                            const uint32_t other = __shfl_xor_sync(0xffffffffu, colbits, j);
+                            // lanes with bit j clear keep their low halves and take the partner's low halves shifted up; the others mirror it
+                            colbits = (lane & j) ? ((colbits & ~msk) | ((other >> j) & msk)) : ((colbits & msk) | ((other << j) & ~msk));
+                        }
 #pragma unroll
                         for (int k = 0; k < 8; ++k) if (k == q * 2 + c) mw[k] = word;
                         // transposed copy: one coalesced 128-byte store per (32 rows x 32 channels)
