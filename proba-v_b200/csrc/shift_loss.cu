@@ -34,7 +34,9 @@ constexpr int NT = 256;       // threads per CTA, 252 of them own a strip
 constexpr int NW = NT / 32;
 constexpr int RS = 58;        // smem row stride (float2) of the window: conflict-free for the strip pattern
 constexpr int HMW = PX + S - 1;       // 13 window pixels feed one strip over 7 column shifts
-constexpr int RT = CT + 1;            // row stride of the residual tile (43: odd, conflict-light)
+constexpr int RT = CT;                // row stride of the residual tile: 42 = 10 (mod 32) makes the strip pattern (thread = row t / 6,
+                                      // columns 7 (t % 6) + k) hit 32 different banks per warp instruction (43 gave 2-way conflicts: 36 % of the
+                                      // L1Edge kernel's shared-memory wavefronts, profiles/r02_ncu_shift_loss_l1edge_b65536.md)
 
 struct __align__(16) Smem {
     float2 hm[WT * RS];       // (h', m) of the HR window; reused as the dSR tile in pass 3
@@ -208,6 +210,65 @@ __device__ __forceinline__ void pass2(Smem& s, const float (&p)[PX], const float
     }
 }
 
+__device__ __forceinline__ int reflect42(int i) { return i < 0 ? -i : (i >= CT ? 2 * CT - 2 - i : i); }
+
+// ---------------------------------------------------------------------------------------------- pass 2 + sobel (L1Edge)
+// Same sums as pass2<true> plus, per shift, sum |sobel_y(r)| + |sobel_x(r)| of the residual tile r = h' - (p' + b) m
+// (tf.image.sobel_edges pads with REFLECT; loss.py:219-224 is linear in r).  The residual strip is already in registers for
+// the L1 / L2 sums, so the only extra shared-memory traffic per shift is 7 stores + the 3 x 9 neighbourhood loads (round 1
+// re-read the (h', m) window for a separate 49-shift sweep: 2.6x the wavefronts).  Results: s.part[warp][shift][0..2].
+__device__ __forceinline__ void pass2_edge(Smem& s, const float (&p)[PX], bool active, int r, int c0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ym = reflect42(r - 1) * RT, y0 = r * RT, yp = reflect42(r + 1) * RT;
+    const int xl = reflect42(c0 - 1), xr = reflect42(c0 + PX);
+#pragma unroll 1
+    for (int i = 0; i < S; ++i) {
+        float a1[8], a2[8], ed[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a1[j] = a2[j] = ed[j] = 0.f;
+        float2 w[HMW];
+        if (active) {
+            const float2* row = &s.hm[(r + i) * RS + c0];
+#pragma unroll
+            for (int k = 0; k < HMW; ++k) w[k] = row[k];
+        }
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            float* R = s.rt[(i * S + j) & 1];       // strict alternation over the 49 shifts (S is odd)
+            if (active) {
+                const float b = s.bias[i * S + j];
+#pragma unroll
+                for (int x = 0; x < PX; ++x) {
+                    const float t = fmaf(-(p[x] + b), w[x + j].y, w[x + j].x);
+                    a1[j] += fabsf(t);
+                    a2[j] = fmaf(t, t, a2[j]);
+                    R[y0 + c0 + x] = t;
+                }
+            }
+            __syncthreads();      // tile (i, j) complete; the other buffer was last read one shift ago, before this barrier's predecessor
+            if (active) {
+                float v[PX + 2], d[PX + 2];
+#pragma unroll
+                for (int k = 0; k < PX + 2; ++k) {
+                    const int xc = k == 0 ? xl : (k == PX + 1 ? xr : c0 + k - 1);
+                    const float a = R[ym + xc], b2 = R[y0 + xc], c2 = R[yp + xc];
+                    v[k] = a + 2.f * b2 + c2;
+                    d[k] = c2 - a;
+                }
+#pragma unroll
+                for (int x = 0; x < PX; ++x) ed[j] += fabsf(d[x] + 2.f * d[x + 1] + d[x + 2]) + fabsf(v[x + 2] - v[x]);
+            }
+        }
+        warp_reduce_multi<8>(a1, lane);
+        warp_reduce_multi<8>(a2, lane);
+        warp_reduce_multi<8>(ed, lane);
+        if ((lane & 3) == 0 && (lane >> 2) < S) {
+            float* dst = s.part[warp][i * S + (lane >> 2)];
+            dst[0] = a1[0]; dst[1] = a2[0]; dst[2] = ed[0];
+        }
+    }
+}
+
 __device__ __forceinline__ float cpsnr_from_l2(float l2) {
     // loss.py:234-238: 10*log(65535^2/L2)/log(10)
     return 10.0f * (logf(65535.0f * 65535.0f / l2) / logf(10.0f));
@@ -234,7 +295,6 @@ __device__ __forceinline__ int argmin49(const float* v, int lane) {
 // ---------------------------------------------------------------------------------------------- L1Edge (sobel) pass
 // tf.image.sobel_edges: REFLECT pad by 1, Ky = [[-1,-2,-1],[0,0,0],[1,2,1]], Kx = Ky^T.
 // loss.py:219-224 takes sobel(h) - sobel((p+b) m) on the 42x42 crops = sobel(r) (linear), summed |.| over both directions.
-__device__ __forceinline__ int reflect42(int i) { return i < 0 ? -i : (i >= CT ? 2 * CT - 2 - i : i); }
 
 __device__ __forceinline__ void sobel_at(const float* __restrict__ R, int y, int x, float& gy, float& gx) {
     const int ym = reflect42(y - 1) * RT, y0 = y * RT, yp = reflect42(y + 1) * RT;
@@ -246,39 +306,13 @@ __device__ __forceinline__ void sobel_at(const float* __restrict__ R, int y, int
     gx = (c + 2.f * f + k) - (a + 2.f * d + g);
 }
 
-// per shift: residual tile -> shared memory -> sum |sobel_y| + |sobel_x| ; s.edge[shift] = that sum (un-normalised)
-__device__ __forceinline__ void edge_pass(Smem& s, const float (&p)[PX], bool active, int r, int c0) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll 1
-    for (int sh = 0; sh < NS; ++sh) {
-        const int i = sh / S, j = sh % S;
-        float* R = s.rt[sh & 1];
-        if (active) {
-            const float b = s.bias[sh];
-            const float2* row = &s.hm[(r + i) * RS + c0 + j];
-#pragma unroll
-            for (int x = 0; x < PX; ++x) R[r * RT + c0 + x] = fmaf(-(p[x] + b), row[x].y, row[x].x);
-        }
-        __syncthreads();          // tile complete (the other buffer is still being read by nobody: two shifts apart)
-        float e = 0.f;
-        if (active) {
-#pragma unroll
-            for (int x = 0; x < PX; ++x) {
-                float gy, gx;
-                sobel_at(R, r, c0 + x, gy, gx);
-                e += fabsf(gy) + fabsf(gx);
-            }
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) e += __shfl_xor_sync(0xffffffffu, e, off);
-        if (lane == 0) s.part[warp][sh][2] = e;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------- fused patch kernel
 // one CTA per 48x48 sample (targetShape (48,48,1), the p16 configs: train.py:86-87)
-__global__ void __launch_bounds__(NT)
-shift_loss_patch_kernel(int kind, const float* __restrict__ hr, const uint8_t* __restrict__ mask,
+// The loss kind is a template parameter: the sobel sweep of the L1Edge loss needs more registers, which must not cost the L1 / L2
+// kernels their occupancy (with a run-time `kind` the L1 kernel went from 2.36 to 3.02 ms at 65 536 samples).
+template <int kind>
+__global__ void __launch_bounds__(NT, kind == PV_LOSS_L1EDGE ? 3 : 5)      // 42 KB of shared memory per CTA allow five per SM
+shift_loss_patch_kernel(const float* __restrict__ hr, const uint8_t* __restrict__ mask,
                         const float* __restrict__ sr, float grad_scale, float* __restrict__ loss_ps,
                         int32_t* __restrict__ best_shift, int32_t* __restrict__ clear_count,
                         float* __restrict__ cpsnr_ps, float* __restrict__ dsr, float* __restrict__ stack_out) {
@@ -299,8 +333,8 @@ shift_loss_patch_kernel(int kind, const float* __restrict__ hr, const uint8_t* _
         s.bias[t] = (1.0f / N) * (sh - spm);          // loss.py:184 (centred form, identical value)
     }
     __syncthreads();
-    pass2<true>(s, p, vx, active, r, c0);
-    if (kind == PV_LOSS_L1EDGE) edge_pass(s, p, active, r, c0);      // fills part[..][..][2] (pass2 only wrote [0], [1])
+    if (kind == PV_LOSS_L1EDGE) pass2_edge(s, p, active, r, c0);       // L1, L2 and the sobel term of every shift in one sweep
+    else pass2<true>(s, p, vx, active, r, c0);
     __syncthreads();
     if (t < NS) {
         float a1 = 0.f, a2 = 0.f, e = 0.f;
@@ -334,14 +368,22 @@ shift_loss_patch_kernel(int kind, const float* __restrict__ hr, const uint8_t* _
     // ---- pass 3: closed-form gradient at the winning shift
     const int bi = s.best, i = bi / S, j = bi % S;
     const float bias = s.bias[bi], N = s.cnt[bi];
-    float q[PX], mm[PX];
+    float q[PX], mm[PX], qe[PX];
     float sqm = 0.f;
+#pragma unroll
+    for (int x = 0; x < PX; ++x) qe[x] = 0.f;
     if (kind == PV_LOSS_L1EDGE) {
-        // adjoint of the sobel term: Q = Ky^T sign(Ky r) + Kx^T sign(Kx r) with the reflect padding folded in, built by
-        // scattering each pixel's two signs through its 3x3 stencil (all addends are small integers: order-independent)
+        // Adjoint of the sobel term, Q = Ky^T sign(Ky r) + Kx^T sign(Kx r) with the REFLECT padding folded in, as a GATHER
+        // (round 1 scattered 8 shared-memory atomics per pixel: 6 of the kernel's 11 ms at 65 536 samples).  The two sign
+        // tiles are stored as bytes on a domain padded by 2 (zeros); on the un-reflected domain Y, X in [-1, 42]
+        //     Qp[Y][X] = (sy[Y-1][X-1] + 2 sy[Y-1][X] + sy[Y-1][X+1]) - (sy[Y+1][X-1] + 2 sy[Y+1][X] + sy[Y+1][X+1])
+        //              + (sx[Y-1][X-1] + 2 sx[Y][X-1] + sx[Y+1][X-1]) - (sx[Y-1][X+1] + 2 sx[Y][X+1] + sx[Y+1][X+1])
+        // and the reflection maps the virtual lines -1 -> 1 and 42 -> 40:  Q[u][v] = sum over the pre-images of (u, v).
         float* R = s.rt[0];
-        float* Q = s.rt[1];
-        for (int k = t; k < CT * RT; k += NT) Q[k] = 0.f;
+        constexpr int SGW = 48;                                  // row stride (bytes) of a sign tile, 46 rows
+        signed char* SY = reinterpret_cast<signed char*>(s.rt[1]);
+        signed char* SX = SY + 46 * SGW;
+        for (int k = t; k < 2 * 46 * SGW / 4; k += NT) reinterpret_cast<int*>(s.rt[1])[k] = 0;
         if (active) {
             const float2* row = &s.hm[(r + i) * RS + c0 + j];
 #pragma unroll
@@ -353,15 +395,34 @@ shift_loss_patch_kernel(int kind, const float* __restrict__ hr, const uint8_t* _
             for (int x = 0; x < PX; ++x) {
                 float gy, gx;
                 sobel_at(R, r, c0 + x, gy, gx);
-                const float sy = gy > 0.f ? 1.f : (gy < 0.f ? -1.f : 0.f), sx = gx > 0.f ? 1.f : (gx < 0.f ? -1.f : 0.f);
-                const int ym = reflect42(r - 1) * RT, y0 = r * RT, yp = reflect42(r + 1) * RT;
-                const int xc = c0 + x, xm = reflect42(xc - 1), xp = reflect42(xc + 1);
-                atomicAdd(&Q[ym + xm], -sy - sx); atomicAdd(&Q[ym + xc], -2.f * sy); atomicAdd(&Q[ym + xp], -sy + sx);
-                atomicAdd(&Q[y0 + xm], -2.f * sx);                                       atomicAdd(&Q[y0 + xp], 2.f * sx);
-                atomicAdd(&Q[yp + xm], sy - sx);   atomicAdd(&Q[yp + xc], 2.f * sy);  atomicAdd(&Q[yp + xp], sy + sx);
+                SY[(r + 2) * SGW + c0 + x + 2] = gy > 0.f ? 1 : (gy < 0.f ? -1 : 0);
+                SX[(r + 2) * SGW + c0 + x + 2] = gx > 0.f ? 1 : (gx < 0.f ? -1 : 0);
             }
         }
         __syncthreads();
+        if (active) {
+            auto qp = [&](int Y, int X) -> float {
+                const signed char* a = SY + (Y + 1) * SGW + X + 1;    // element (Y - 1, X - 1) of the padded tile
+                const signed char* c = SX + (Y + 1) * SGW + X + 1;
+                const int vy = (a[0] + 2 * a[1] + a[2]) - (a[2 * SGW] + 2 * a[2 * SGW + 1] + a[2 * SGW + 2]);
+                const int vxx = (c[0] + 2 * c[SGW] + c[2 * SGW]) - (c[2] + 2 * c[SGW + 2] + c[2 * SGW + 2]);
+                return (float)(vy + vxx);
+            };
+#pragma unroll 1
+            for (int x = 0; x < PX; ++x) {
+                const int v = c0 + x;
+                float acc = qp(r, v);
+                if (r == 1) acc += qp(-1, v);
+                if (r == CT - 2) acc += qp(CT, v);
+                if (v == 1 || v == CT - 2) {
+                    const int X2 = v == 1 ? -1 : CT;
+                    acc += qp(r, X2);
+                    if (r == 1) acc += qp(-1, X2);
+                    if (r == CT - 2) acc += qp(CT, X2);
+                }
+                qe[x] = acc;
+            }
+        }
     }
     if (active) {
         const float2* row = &s.hm[(r + i) * RS + c0 + j];
@@ -371,7 +432,7 @@ shift_loss_patch_kernel(int kind, const float* __restrict__ hr, const uint8_t* _
             const float tt = fmaf(-(p[x] + bias), w.y, w.x);
             // L1: d|r|/dr = sign(r), sign(0) = 0 (tf.abs gradient);  L2: d r^2/dr = 2r;  L1Edge: 0.7 sign(r) + 0.3 sobel adjoint
             const float sg = tt > 0.f ? 1.f : (tt < 0.f ? -1.f : 0.f);
-            q[x] = (kind == PV_LOSS_L2) ? 2.0f * tt : (kind == PV_LOSS_L1EDGE ? 0.7f * sg + (1.0f - 0.7f) * s.rt[1][r * RT + c0 + x] : sg);
+            q[x] = (kind == PV_LOSS_L2) ? 2.0f * tt : (kind == PV_LOSS_L1EDGE ? 0.7f * sg + (1.0f - 0.7f) * qe[x] : sg);
             mm[x] = w.y;
             sqm = fmaf(q[x], w.y, sqm);
         }
@@ -539,8 +600,9 @@ int shift_loss_device(int kind, const float* hr, const uint8_t* mask, const floa
          reinterpret_cast<uintptr_t>(mask) & 3))
         return set_error(PV_ERR_BAD_ARG, "pv_shift_loss: hr/sr/dsr must be 16-byte aligned and mask 4-byte aligned");
     if (H == WT && W == WT) {
-        shift_loss_patch_kernel<<<B, NT, 0, st>>>(kind, hr, mask, sr, grad_scale, loss_ps, best_shift, clear_count,
-                                                  cpsnr_ps, dsr, stack_out);
+        if (kind == PV_LOSS_L1) shift_loss_patch_kernel<PV_LOSS_L1><<<B, NT, 0, st>>>(hr, mask, sr, grad_scale, loss_ps, best_shift, clear_count, cpsnr_ps, dsr, stack_out);
+        else if (kind == PV_LOSS_L2) shift_loss_patch_kernel<PV_LOSS_L2><<<B, NT, 0, st>>>(hr, mask, sr, grad_scale, loss_ps, best_shift, clear_count, cpsnr_ps, dsr, stack_out);
+        else shift_loss_patch_kernel<PV_LOSS_L1EDGE><<<B, NT, 0, st>>>(hr, mask, sr, grad_scale, loss_ps, best_shift, clear_count, cpsnr_ps, dsr, stack_out);
         PV_LAUNCH_CHECK();
     } else {
         if (dsr) return set_error(PV_ERR_BAD_ARG, "pv_shift_loss: fused backward is only built for 48x48 targets");

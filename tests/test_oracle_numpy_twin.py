@@ -86,3 +86,61 @@ def test_numpy_twin_depth_to_space_and_reflect_known_answers():
                 for j in range(3):
                     assert y[0, 3 * h + i, 3 * w + j, 0] == x[0, h, w, 3 * i + j]
     assert np.pad(np.array([1, 2, 3, 4]), 1, mode="reflect").tolist() == [2, 1, 2, 3, 4, 3]   # tf.pad REFLECT: no edge repeat
+
+
+# ------------------------------------------------------------------------------------------------- losses + one backward
+# Independent NumPy restatement of the shift-compensated L1 loss / cPSNR metric (reference models/loss.py:37-53,73-84,140-152,
+# 168-187,226-238; utils/utils.py:42-44) with explicit Python loops over samples and shifts, and of its gradient by CENTRAL
+# FINITE DIFFERENCES (no autograd, no closed form) -- cross-checks oracle/losses.py's values and its backward.
+def np_shift_scores(hr, mask, sr, border=3):
+    B, H, W, _ = hr.shape
+    ch, cw = H - 2 * border, W - 2 * border
+    S = 2 * border + 1
+    l1 = np.zeros((S * S, B))
+    cps = np.zeros((S * S, B))
+    for b in range(B):
+        pred = sr[b, border:border + ch, border:border + cw, 0].astype(np.float64)           # cropPrediction, loss.py:75-76
+        for i in range(S):
+            for j in range(S):
+                h = hr[b, i:i + ch, j:j + cw, 0].astype(np.float64)                         # loss.py:141
+                m = mask[b, i:i + ch, j:j + cw, 0].astype(np.float64)                       # loss.py:142
+                n = m.sum()                                                                  # loss.py:144
+                bias = (h - pred * m).sum() / n                                              # loss.py:182-187 (HR un-masked)
+                corr = (pred + bias) * m                                                     # loss.py:148-149
+                l1[i * S + j, b] = np.abs(h - corr).sum() / n                                # loss.py:226-228
+                l2 = ((h - corr) ** 2).sum() / n
+                cps[i * S + j, b] = 10.0 * np.log10(65535.0 ** 2 / l2)                       # loss.py:234-238
+    return l1, cps
+
+
+def np_shift_l1_loss(hr, mask, sr):
+    return np_shift_scores(hr, mask, sr)[0].min(axis=0).mean()                              # loss.py:83-84
+
+
+def test_numpy_loss_twin_agrees_with_the_torch_oracle_values_and_backward():
+    from oracle.losses import OracleLosses
+    rng = np.random.default_rng(5)
+    B = 3
+    hr = np.round(rng.random((B, 48, 48, 1)) * 4000 + 6000)
+    sr = np.roll(hr, (2, -1), (1, 2)) + rng.standard_normal((B, 48, 48, 1)) * 45
+    mask = rng.random((B, 48, 48, 1)) > 0.12                                               # raw HR stays under unclear pixels
+    L = OracleLosses((48, 48, 1))
+    t = lambda a: torch.from_numpy(np.asarray(a, np.float64))                               # noqa: E731
+    l1, cps = np_shift_scores(hr, mask, sr)
+    stack = L.stack("l1", t(hr), torch.from_numpy(mask), t(sr))[0].numpy()
+    assert np.abs(stack - l1).max() < 1e-9 * np.abs(l1).max()
+    assert np.array_equal(stack.argmin(axis=0), l1.argmin(axis=0))
+    assert np.abs(L.shiftCompensatedcPSNR(t(hr), torch.from_numpy(mask), t(sr)).numpy() - cps.max(axis=0)).max() < 1e-9
+    assert abs(float(L.shiftCompensatedL1Loss(t(hr), torch.from_numpy(mask), t(sr))) - np_shift_l1_loss(hr, mask, sr)) < 1e-9
+    # backward: autograd of the oracle vs central differences of the NumPy twin on 40 random SR pixels (inside the crop and outside)
+    srg = t(sr).clone().requires_grad_(True)
+    L.shiftCompensatedL1Loss(t(hr), torch.from_numpy(mask), srg).backward()
+    g = srg.grad.numpy()
+    eps = 1e-3                                            # far below the distance of any residual to its kink on this data
+    for _ in range(40):
+        b, y, x = int(rng.integers(B)), int(rng.integers(48)), int(rng.integers(48))
+        d = np.zeros_like(sr)
+        d[b, y, x, 0] = eps
+        fd = (np_shift_l1_loss(hr, mask, sr + d) - np_shift_l1_loss(hr, mask, sr - d)) / (2 * eps)
+        assert abs(fd - g[b, y, x, 0]) < 1e-6 + 1e-4 * abs(g[b, y, x, 0]), (b, y, x, fd, g[b, y, x, 0])
+    assert np.abs(g[:, :3]).max() == 0 and np.abs(g[:, :, 45:]).max() == 0                  # the 3-pixel border never sees a gradient
