@@ -163,7 +163,10 @@ class TensorCoreModel(OracleWDSR):
     def _tc(self, p, name, x, padding, relu, store=True):
         m = self.mode
         w = wn_kernel(p[name + "/v"], p[name + "/g"])
-        y = _QConv.apply(x, w, p[name + "/bias"], padding, m["act"], m["wt"], m["grad"], m.get("act_b") or m["act"], m.get("wt_b") or m["wt"])
+        wtb = m.get("wt_b") or m["wt"]
+        if w.dim() == 5 and w.shape[0] == 3 and m.get("wt_b3"):     # 3x3x3 layers may use a different backward weight quantiser
+            wtb = m["wt_b3"]
+        y = _QConv.apply(x, w, p[name + "/bias"], padding, m["act"], m["wt"], m["grad"], m.get("act_b") or m["act"], wtb)
         return torch.relu(y) if relu else y
 
     def forward(self, p: Dict[str, torch.Tensor], x: torch.Tensor, return_taps: bool = False):
