@@ -154,7 +154,9 @@ int dgrad_rows(pv_model* m, const Layer& L, const Taps& tp /* negated offsets */
 
 // Error-compensated forward convolution (precision 4): operands as (hi, lo) row arrays, three passes of the conv3 kernel chained
 // through the fp32 partial buffer `yp` (same geometry as the output):
-//     yp  = x_lo * w_hi;   yp += x_hi * w_lo;   v = x_hi * w_hi + yp + bias (+ res_hi + res_lo), act  ->  (y_hi, y_lo) = split(v)
+//     yp  = x_lo * w_hi + bias (+ res_hi + res_lo);   yp += x_hi * w_lo;   v = act(x_hi * w_hi + yp)  ->  (y_hi, y_lo) = split(v)
+// The skip connection and the bias ride on the FIRST pass so that every pass's epilogue reads at most two extra row arrays (with all
+// three on the last pass it ran at 104 us against 59 us for the others: ncu long-scoreboard stalls, profiles/r02_ncu_tf32x3_hot_kernels.md).
 // y_lo == nullptr stores v itself (un-rounded fp32: the upscale conv, whose output feeds the CUDA-core tail).
 int conv_rows_x3(pv_model* m, const Layer& L, const Taps& tp, const float* x_hi, const float* x_lo, const RowGeom& ig, float* y_hi, float* y_lo,
                  const RowGeom& og, const float* res_hi, const float* res_lo, float* yp, int B, const char* tag, cudaStream_t st) {
@@ -168,15 +170,15 @@ int conv_rows_x3(pv_model* m, const Layer& L, const Taps& tp, const float* x_hi,
     p.w_rows = L.cout_s; p.w_cols = Kflat; p.w_kmajor = 1;
     p.flops = 0.0;                       // the algorithmic flops are booked once, on the last pass
     p.tag = tag;
-    // pass 1: x_lo * w_hi
-    p.x = x_lo; p.w = m->weffT + L.weff_off; p.y = yp;
+    // pass 1: x_lo * w_hi + bias (+ skip connection)
+    p.x = x_lo; p.w = m->weffT + L.weff_off; p.y = yp; p.bias = m->bias_s + L.bias_s_off;
+    p.residual = res_hi; p.residual2 = res_hi ? res_lo : nullptr;
     PV_TRY(launch_rowconv_tc(p, st));
     // pass 2: + x_hi * w_lo (in place: a warp reads exactly the rows it then writes)
-    p.x = x_hi; p.w = m->weffT_lo + L.weff_off; p.residual = yp;
+    p.x = x_hi; p.w = m->weffT_lo + L.weff_off; p.bias = nullptr; p.residual = yp; p.residual2 = nullptr;
     PV_TRY(launch_rowconv_tc(p, st));
-    // pass 3: + x_hi * w_hi + bias (+ skip connection), activation, split
-    p.w = m->weffT + L.weff_off; p.bias = m->bias_s + L.bias_s_off; p.relu = L.relu;
-    p.residual2 = res_hi; p.residual3 = res_lo; p.y = y_hi; p.y_lo = y_lo;
+    // pass 3: + x_hi * w_hi, activation, split
+    p.w = m->weffT + L.weff_off; p.relu = L.relu; p.y = y_hi; p.y_lo = y_lo;
     p.flops = 2.0 * B * L.Ho * L.Wo * L.To * L.taps() * L.cin * L.cout;
     return launch_rowconv_tc(p, st);
 }
@@ -779,9 +781,10 @@ static int tc_forward_tail(pv_model* m, int B, float* sr, bool tr, int clip_roun
     const float* q = P["mn"];
     if (c.scale == 3 && skip2d_supported(m->S, c.scale * c.scale)) {   // WDSRNetLRResidualPath, modelsTF.py:45-53: one fused kernel
         const Layer &R1 = m->layers[m->li("residConv1")], &R2 = m->layers[m->li("residConv2")], &R3 = m->layers[m->li("residConv3")];
-        PV_TRY(launch_skip2d_fwd(P["mn"], m->weff + R1.weff_off, m->bias_s + R1.bias_s_off, m->weff + R2.weff_off, m->bias_s + R2.bias_s_off,
-                                 m->weff + R3.weff_off, m->bias_s + R3.bias_s_off, B, m->S, c.scale * c.scale, P["q1"], P["q2"], P["q3"], st));
-        q = P["q3"];
+        // ... with depth_to_space + add + de-normalise fused in: ONE kernel after the upscale conv (north_star bullet 2)
+        return launch_skip2d_fwd_tail(P["mn"], m->weff + R1.weff_off, m->bias_s + R1.bias_s_off, m->weff + R2.weff_off, m->bias_s + R2.bias_s_off,
+                                      m->weff + R3.weff_off, m->bias_s + R3.bias_s_off, B, m->S, c.scale * c.scale, P["q1"], P["q2"], P["q3"],
+                                      P["U"], ug, m->F, c.scale, c.mean, c.std, clip_round, sr, st);
     } else {
         for (int i = 0; i < c.scale; ++i) {
             float* out = P["q" + std::to_string(i + 1)];

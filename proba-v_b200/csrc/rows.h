@@ -130,6 +130,10 @@ int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, in
 int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st, int pad = 1,
                                const float* relumask = nullptr, int round_tf32 = 0);
 
+// low-frequency skip path (three 3x3 Conv2D) with the graph's tail fused in (skip2d.cu); u / ug / uc describe the upscale conv's rows
+int launch_skip2d_fwd_tail(const float* mn, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                           const float* b3, int B, int S, int C, float* q1, float* q2, float* q3, const float* u, RowGeom ug, int uc,
+                           int scale, float mean, float stdv, int clip_round, float* sr, cudaStream_t st);
 // tail on the row layouts: sr = (depth_to_space(U[:, :, :9]) + depth_to_space(resid)) * std + mean [clip, round]; and its adjoint
 int launch_tail_rows(const float* u, RowGeom g, int uc, const float* resid, int B, int P, int scale, float mean, float stdv,
                      int clip_round, float* sr, cudaStream_t st);

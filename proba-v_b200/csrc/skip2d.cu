@@ -8,12 +8,20 @@
 // Layouts (dense engine conventions, kernels.h): activations [B, H, W, C] fp32; effective weights w[(tap*cin + ci)*C + co]
 // with tap = a*3 + b (TF order); partial vector = { dW1[9*C], dW2[9*C*C], dW3[9*C*C], db1[C], db2[C], db3[C] }.
 #include "kernels.h"
+#include "rows.h"
 #include "wgrad_reduce.cuh"
 
 namespace pv {
 namespace {
 
 constexpr int SK_THREADS = 256;
+
+// optional fused tail of the forward kernel (sr == nullptr: skip path only)
+struct SkipTail {
+    const float* u; RowGeom g; int uc;       // upscale conv output rows (G layout, one plane per patch), channels per row
+    int scale; float mean, stdv; int clip_round;
+    float* sr;                               // [B, scale*P, scale*P]
+};
 
 struct Skip2dShape {
     int S, C;                        // input side, channels (scale^2)
@@ -54,7 +62,7 @@ __device__ __forceinline__ void conv3x3_valid(const float* __restrict__ in, int 
 __global__ void __launch_bounds__(SK_THREADS)
 skip2d_fwd_kernel(const float* __restrict__ mn, const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                   const float* __restrict__ b2, const float* __restrict__ w3, const float* __restrict__ b3, Skip2dShape sh,
-                  float* __restrict__ q1, float* __restrict__ q2, float* __restrict__ q3) {
+                  float* __restrict__ q1, float* __restrict__ q2, float* __restrict__ q3, SkipTail tl) {
     pdl_grid_wait();
     extern __shared__ float sm[];
     const int S = sh.S, C = sh.C, n0 = S * S, n1 = sh.s1() * sh.s1() * C, n2 = sh.s2() * sh.s2() * C, n3 = sh.s3() * sh.s3() * C;
@@ -83,6 +91,19 @@ skip2d_fwd_kernel(const float* __restrict__ mn, const float* __restrict__ w1, co
     for (int i = threadIdx.x; i < n1; i += SK_THREADS) q1[(size_t)b * n1 + i] = a1[i];
     for (int i = threadIdx.x; i < n2; i += SK_THREADS) q2[(size_t)b * n2 + i] = a2[i];
     for (int i = threadIdx.x; i < n3; i += SK_THREADS) q3[(size_t)b * n3 + i] = a3[i];
+    if (tl.sr) {
+        // Fused tail (modelsTF.py:38-41,52,73; test.py:118-119): depth_to_space of the upscale conv's output U and of this path's a3,
+        // add, de-normalise [clip, round half-even] -- the skip path's result never leaves shared memory.  Threads sweep the
+        // (scale * P)^2 output row-major, so the SR stores are coalesced; the 9 of 32 channels of a U row are read once each.
+        const int P = sh.s3(), s = tl.scale, PS = P * s;
+        for (int i = threadIdx.x; i < PS * PS; i += SK_THREADS) {
+            const int X = i % PS, Y = i / PS, c = (Y % s) * s + (X % s);
+            const long long urow = tl.g.lead + (long long)b * tl.g.pstride + (long long)tl.g.t0 * tl.g.plane + (Y / s) * tl.g.pw + X / s;
+            float v = (__ldg(tl.u + urow * tl.uc + c) + a3[((Y / s) * P + X / s) * C + c]) * tl.stdv + tl.mean;
+            if (tl.clip_round) v = rintf(fminf(fmaxf(v, 0.f), 65536.f));
+            tl.sr[(size_t)b * PS * PS + i] = v;
+        }
+    }
 }
 
 // gin[p][ci] = sum_{tap,co} g[p - tap][co] * w[tap][ci][co]   (full correlation: So = Sg + 2), optionally * (ref > 0)
@@ -197,13 +218,27 @@ bool skip2d_supported(int S, int C) { return S >= 8 && S <= 40 && C >= 1 && C <=
 
 int launch_skip2d_fwd(const float* mn, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
                       const float* b3, int B, int S, int C, float* q1, float* q2, float* q3, cudaStream_t st) {
+    SkipTail tl;
+    memset(&tl, 0, sizeof tl);
+    return launch_skip2d_fwd_tail(mn, w1, b1, w2, b2, w3, b3, B, S, C, q1, q2, q3, nullptr, tl.g, 0, 0, 0.f, 1.f, 0, nullptr, st);
+}
+
+// the same with the graph's tail fused in: sr = (depth_to_space(U[:, :9]) + depth_to_space(skip path)) * std + mean [clip, round]
+int launch_skip2d_fwd_tail(const float* mn, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                           const float* b3, int B, int S, int C, float* q1, float* q2, float* q3, const float* u, RowGeom ug, int uc,
+                           int scale, float mean, float stdv, int clip_round, float* sr, cudaStream_t st) {
     Skip2dShape sh{S, C};
+    if (sr && (scale * scale != C || !u)) return set_error(PV_ERR_BAD_ARG, "skip2d_fwd_tail: scale^2 must equal the path's channel count");
+    SkipTail tl;
+    memset(&tl, 0, sizeof tl);
+    tl.u = u; tl.g = ug; tl.uc = uc; tl.scale = scale; tl.mean = mean; tl.stdv = stdv; tl.clip_round = clip_round; tl.sr = sr;
     const size_t smem = sizeof(float) * ((size_t)S * S + (size_t)(sh.s1() * sh.s1() + sh.s2() * sh.s2() + sh.s3() * sh.s3()) * C +
                                          sh.nw1() + 2 * sh.nw2() + 3 * C);
     static size_t attr[16] = {};
     PV_CUDA(ensure_dyn_smem(skip2d_fwd_kernel, smem, attr));
-    PV_TIMED("skip2d_fwd", st, 2.0 * B * C * (9.0 * sh.s1() * sh.s1() + 9.0 * C * (sh.s2() * sh.s2() + sh.s3() * sh.s3())), 0.0);
-    PV_CUDA(launch_pdl_simple(skip2d_fwd_kernel, B, SK_THREADS, smem, st, mn, w1, b1, w2, b2, w3, b3, sh, q1, q2, q3));
+    PV_TIMED(sr ? "skip2d_fwd_tail" : "skip2d_fwd", st, 2.0 * B * C * (9.0 * sh.s1() * sh.s1() + 9.0 * C * (sh.s2() * sh.s2() + sh.s3() * sh.s3())),
+             sr ? (double)B * sh.s3() * sh.s3() * C * 12.0 : 0.0);
+    PV_CUDA(launch_pdl_simple(skip2d_fwd_kernel, B, SK_THREADS, smem, st, mn, w1, b1, w2, b2, w3, b3, sh, q1, q2, q3, tl));
     PV_LAUNCH_CHECK();
     return 0;
 }
