@@ -166,6 +166,11 @@ int  pv_train_forward_backward_staged(pv_trainer* t, const float* lr_dev, const 
                                       int B, float grad_scale, float* out_dev, int stage, int64_t* grad_lo,
                                       int64_t* grad_hi, void* stream);
 int  pv_apply_gradients(pv_trainer* t, void* stream);
+/* The two halves of tf.GradientTape for callers that bring their own loss (the PyTorch twin, models/modelsPyTorch.py):
+ * pv_trainer_forward = model(lr, training=True) keeping the activations (trainClass.py:127); pv_trainer_backward =
+ * tape.gradient(., model.trainable_variables) for a given dL/dSR [B,Hh,Wh,1] (trainClass.py:131): fills the gradient arena. */
+int  pv_trainer_forward(pv_trainer* t, const float* lr_dev, int B, float* sr_dev, void* stream);
+int  pv_trainer_backward(pv_trainer* t, const float* dsr_dev, int B, void* stream);
 /* optimizer state for tf.train.Checkpoint parity (trainClass.py:33-39): iter, momentum_cache, m, v */
 int  pv_trainer_get_state(pv_trainer* t, int64_t* iter, double* momentum_cache, float* m_host, float* v_host, int64_t n);
 int  pv_trainer_set_state(pv_trainer* t, int64_t iter, double momentum_cache, const float* m_host, const float* v_host, int64_t n);

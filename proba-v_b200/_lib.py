@@ -67,6 +67,8 @@ _SIGS = {
     "pv_trainer_set_state": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P, C.c_int64]),
     "pv_trainer_set_lr": (C.c_int, [_P, C.c_float]),
     "pv_selftest": (C.c_int, [C.c_char_p, C.c_int]),
+    "pv_trainer_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "pv_trainer_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "pv_debug_read_buffer": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_int64]),
     "pv_timing_enable": (C.c_int, [C.c_int]),
     "pv_timing_reset": (C.c_int, []),

@@ -909,6 +909,21 @@ int pv_train_forward_backward_staged(pv_trainer* t, const float* lr, const float
     return 0;
 }
 
+int pv_trainer_forward(pv_trainer* t, const float* lr, int B, float* sr, void* stream) {
+    if (!t) return set_error(PV_ERR_BAD_ARG, "null trainer");
+    t->fwd_B = 0;
+    PV_TRY(model_forward(t->m, lr, B, sr, true, 0, S_(stream)));
+    t->fwd_B = B;
+    return 0;
+}
+
+int pv_trainer_backward(pv_trainer* t, const float* dsr, int B, void* stream) {
+    if (!t || !dsr) return set_error(PV_ERR_BAD_ARG, "pv_trainer_backward: null argument");
+    if (B <= 0 || B != t->fwd_B) return set_error(PV_ERR_STATE, "pv_trainer_backward: no training-mode forward of batch %d to differentiate (last: %d)", B, t->fwd_B);
+    PV_CUDA(cudaSetDevice(t->m->device));
+    return model_backward(t, dsr, B, S_(stream));
+}
+
 int pv_apply_gradients(pv_trainer* t, void* stream) {
     if (!t) return set_error(PV_ERR_BAD_ARG, "null trainer");
     PV_CUDA(cudaSetDevice(t->m->device));

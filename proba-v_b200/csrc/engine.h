@@ -155,6 +155,7 @@ struct pv_trainer {
     int opt = PV_OPT_NADAM, loss_kind = PV_LOSS_L1;
     float lr = 1e-3f;
     long long iter = 0;
+    int fwd_B = 0;                     // batch of the last pv_trainer_forward (what pv_trainer_backward may differentiate)
     double momentum_cache = 1.0;
     float *grads = nullptr, *dweff = nullptr, *dbias_s = nullptr, *m1 = nullptr, *m2 = nullptr;
     // per-batch loss workspace

@@ -261,3 +261,72 @@ def test_empty_shard_contributes_zero_gradients(small_cfg, precision):
     check(_lib.lib().pv_train_forward_backward(t._h, None, None, None, 0, 1.0, _buf.ptr(out), _buf.current_stream_ptr(dev)))
     torch.cuda.synchronize()
     assert float(t.grad_view().abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------- PyTorch twin
+def test_pytorch_twin_matches_the_trainer_and_steps_with_torch_optim(small_cfg):
+    """proba-v_b200/modelsPyTorch.py (the working counterpart of the reference's draft models/modelsPyTorch.py:10-151): the nn.Module
+    runs the same kernels, its autograd gradients equal ModelTrainer's tape.gradient, and a torch optimizer steps the engine's
+    weight arena in place."""
+    import tempfile
+    import probav_b200 as pb
+    from probav_b200 import synth
+    from probav_b200.modelsPyTorch import Conv3DResNet, ShiftL1Loss
+    om, p = oracle_and_params(small_cfg, seed=90)
+    lr, hr, mask = synth.make_batch(4, seed=91, hr_zero_under_mask=False)
+    net = Conv3DResNet((1, 9, 22, 22), 3, small_cfg["numResBlocks"], (3, 3, 3), 32, 8, 0.8, precision="tf32x3")
+    net.model.set_weights({k: v.numpy().astype(np.float32) for k, v in p.items()})
+    x = torch.from_numpy(lr).cuda().permute(0, 4, 3, 1, 2).contiguous()                 # [B, 1, T, H, W]
+    y = torch.from_numpy(hr).cuda().permute(0, 3, 1, 2)
+    k = torch.from_numpy(mask).cuda().permute(0, 3, 1, 2)
+    crit = ShiftL1Loss("l1")
+    sr = net(x)
+    assert tuple(sr.shape) == (4, 1, 48, 48)
+    ref_sr = om.forward(p, torch.from_numpy(lr).double()).numpy()
+    assert rel_err(sr.detach().permute(0, 2, 3, 1).cpu().numpy(), ref_sr) < 1e-5
+    loss = crit(sr, y, k)
+    loss.backward()
+    # the same weights through the reference-shaped trainer
+    m2 = cuda_model(small_cfg, p, precision="tf32x3")
+    L = pb.Losses((48, 48, 1))
+    d = tempfile.mkdtemp(prefix="pv_")
+    t = pb.ModelTrainer(m2, L.shiftCompensatedL1Loss, L.shiftCompensatedcPSNR, pb.Nadam(5e-4), d + "/ckpt", d + "/log")
+    lossv, _ = t.forward_backward(lr, hr, mask)
+    assert abs(float(loss) - lossv) <= 1e-6 * abs(lossv)
+    assert torch.equal(net.theta.grad, t.grad_view())                                  # same kernels, fixed-order reductions: bit-identical
+    # a torch optimizer updates the engine's arena in place, and the next forward sees it
+    opt = torch.optim.SGD(net.parameters(), lr=1e-4)
+    before = net.theta.detach().clone()
+    opt.step()
+    assert not torch.equal(before, net.theta.detach())
+    assert torch.equal(net.theta.detach(), net.model.param_arena())
+    sr2 = net(x)
+    assert float((sr2 - sr).abs().max()) > 0
+    names = [n for n, _ in net.named_variables()]
+    assert names[0] == "mainConv1/v" and len(names) == 3 * (1 + 3 * small_cfg["numResBlocks"] + 3 + 1 + 3)
+
+
+# ------------------------------------------------------------------------------------------------- 64 filters (BASELINE configs[4])
+def test_64_filter_graph_with_sobel_l1_loss(small_cfg):
+    """The scaled-up family of BASELINE configs[4] (num_filters = 64: expand to 512, decay to int(64 * 0.8) = 51 channels,
+    modelsTF.py:177-189) with the Sobel + L1 loss (loss.py:86-97,219-224) on the dense fp32 engine: forward and every gradient."""
+    import probav_b200 as pb
+    import tempfile
+    from probav_b200 import synth
+    cfg = dict(small_cfg, numFilters=64, numResBlocks=2)
+    om, p = oracle_and_params(cfg, seed=95)
+    assert p["decConv_0/v"].shape[-1] == 51 and p["expConv_0/v"].shape[-1] == 512
+    m = cuda_model(cfg, p, precision="fp32")
+    lr, hr, mask = synth.make_batch(3, seed=96, hr_zero_under_mask=False)
+    ol = OracleLosses((48, 48, 1))
+    loss, g, sr, cps = loss_and_grads(om, ol, p, torch.from_numpy(lr).double(), torch.from_numpy(hr).double(), torch.from_numpy(mask), "sobel_l1_mix")
+    assert rel_err(m(lr), sr.numpy()) < 1e-3
+    L = pb.Losses((48, 48, 1))
+    d = tempfile.mkdtemp(prefix="pv_")
+    t = pb.ModelTrainer(m, L.shiftCompensatedL1EdgeLoss, L.shiftCompensatedcPSNR, pb.Nadam(5e-4), d + "/ckpt", d + "/log")
+    lossv, psnrv = t.forward_backward(lr, hr, mask)
+    assert abs(lossv - float(loss)) < 1e-3 * float(loss) and abs(psnrv - float(cps.mean())) < 0.01
+    grads = t.get_grads()
+    worst = max(rel_err(grads[k], v.numpy()) for k, v in g.items() if np.abs(v.numpy()).max() > 0)
+    print(f"F=64, sobel_l1_mix: worst gradient rel err {worst:.2e}")
+    assert worst < 4e-3          # 3-patch batch with a sign-based loss: see test_forward_backward_with_raw_hr
