@@ -9,7 +9,8 @@ One "step" = ModelTrainer.trainStep (reference models/trainClass.py:124-135) on 
 with pinned HOST buffers (H2D of the batch + D2H of loss/cPSNR inside the timed region).  `roofline` describes the
 dominant kernel class, timed live with CUDA events through pv_timing_*; `cpu_baseline` is the oracle (a PyTorch-CPU
 restatement of the TF reference, which cannot be installed here) timed on this box's host cores.
-Weak scaling for N > 1: per-rank batch fixed, ONE NCCL all-reduce of the flat gradient arena per step.
+Weak scaling for N > 1 (default): per-rank batch fixed, the flat gradient arena all-reduced over NCCL in two buckets overlapped with
+the backward pass; `--scaling strong` keeps the GLOBAL batch at the cfg's batch_size instead.
 """
 import argparse
 import json
@@ -399,7 +400,7 @@ def run_b200(args, cfg):
     # algorithmic flops per patch: SURVEY Appendix A for the headline graph, else the sum the kernels' launchers report
     gflop_per_patch = TRAIN_GFLOP_PER_PATCH if is_headline else sum(v["flops"] for v in rep.values()) / 2 / B / 1e9
     line = {"metric": METRIC if is_headline else METRIC.replace("p16t9c85r12", cfg_name), "value": value, "unit": UNIT, "n_gpus": ws, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": {0: "f32", 1: "tf32", 3: "f32", 4: "tf32x3"}[model.cfg.precision], "data": "synthetic",
             "config": {"workload": workload,
                        "batch_per_gpu": B, "global_batch": B * ws, "parallelism": f"dp{ws}",
@@ -441,6 +442,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: cfg batch_size = 128)")
     ap.add_argument("--ref-batch", type=int, default=None, help="CPU arm: patches per step (default: the cfg batch, i.e. the same 128-patch step)")
     ap.add_argument("--cfg", default=os.path.join(ROOT, "cfg", "p16t9c85r12.cfg"))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: per-GPU batch = cfg batch_size (default); strong: GLOBAL batch = cfg batch_size, split over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scene-infer", action="store_true")
     ap.add_argument("--no-side-tf32", action="store_true", help="skip the single-pass tf32 measurement reported beside the headline")
@@ -457,6 +460,11 @@ def main():
         args.batch = cfg["batch_size"]
     if args.ref_batch is None:
         args.ref_batch = args.batch
+    if args.scaling == "strong" and args.impl == "b200":
+        ws = int(os.environ.get("WORLD_SIZE", "1"))
+        if args.batch % ws:
+            raise SystemExit(f"--scaling strong: the global batch {args.batch} does not split over {ws} ranks")
+        args.batch //= ws
     if args.impl == "reference":
         run_reference(args, cfg)
     else:

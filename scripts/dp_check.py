@@ -23,7 +23,7 @@ d = tempfile.mkdtemp(prefix=f"pv_dp_{rank}_") if rank else os.environ.get("PV_DP
 
 
 def run(world_mode: bool):
-    m = pb.WDSRConv3D("n", "NIR", 8075.2045, 3160.7272, 6).build(**cfg, seed=3, precision="tf32", device=local)
+    m = pb.WDSRConv3D("n", "NIR", 8075.2045, 3160.7272, 6).build(**cfg, seed=3, precision=os.environ.get("PV_DP_PRECISION", "tf32x3"), device=local)
     L = pb.Losses((48, 48, 1))
     sub = "dp" if world_mode else "single"
     t = pb.ModelTrainer(m, L.shiftCompensatedL1Loss, L.shiftCompensatedcPSNR, pb.Nadam(5e-4), f"{d}/{sub}/ckpt", f"{d}/{sub}/log", evalStep=2)
