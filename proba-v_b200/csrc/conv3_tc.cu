@@ -23,6 +23,8 @@
 //
 // Warp roles as in conv_tc.cu: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer (one elected thread), warps 2-5 and
 // 6-9 two epilogue groups draining alternate tiles (TMEM accumulator double buffer, 2 x 96 columns).
+#include <cuda_fp16.h>
+
 #include "rowio.cuh"
 #include "rows.h"
 #include "tc_common.cuh"
@@ -52,6 +54,7 @@ struct Conv3Args {
     int pw;                            // rows per image line: dh view stride inside a slab
     int tap_wr[MAX_TAPS], tap_wc[MAX_TAPS];
     const float* bias; const float* residual; const float* residual2; const float* residual3; const float* relumask; float* y; float* y_lo;
+    float* y_pack;                     // packed fp16 pair rows of (hi, lo) (rows.h PACK_SCALE), nullable
     int relu, round_tf32;
 };
 
@@ -82,6 +85,9 @@ __device__ __forceinline__ TileInfo tile_info(const Conv3Args& a, int tile, int 
     return ti;
 }
 
+// F16: the operands are packed fp16 pair rows (rows.h): kind::f16 MMAs, K = 16 per step over the same 128-byte rows, and the
+// accumulator is PACK_SCALE times the two correction products of a compensated convolution (scaled back in the epilogue).
+template <bool F16>
 __global__ void __launch_bounds__(C3_THREADS, 1)
 rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const Conv3Args a) {
     extern __shared__ uint8_t smem_raw[];
@@ -139,7 +145,7 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         if (elect_one_sync()) {
             constexpr uint64_t HI = smem_desc_hi(16, 1024, 2);          // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
             constexpr uint32_t HI32 = (uint32_t)(HI >> 32), LO32 = (uint32_t)HI;
-            constexpr uint32_t IDESC = instr_desc(2, 128, 96, 0, 0);    // tf32 x tf32 -> f32, M = 128, N = 96 (three dw taps)
+            constexpr uint32_t IDESC = instr_desc(F16 ? 0 : 2, 128, 96, 0, 0);    // tf32 (or fp16) operands -> f32, M = 128, N = 96 (three dw taps)
             const uint32_t dh_inc = (uint32_t)a.pw * 8u;                // one image line further into the slab (16-byte units)
             mbar_wait(BAR(WBAR), 0);
             tc_fence_after();
@@ -174,7 +180,8 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     for (int dh = 0; dh < 3; ++dh) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
-                            umma_ss_tf32_lohi(d_tmem, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
+                            if (F16) umma_ss_f16_lohi(d_tmem, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
+                            else umma_ss_tf32_lohi(d_tmem, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
                     }
                     // release the slabs the next tile does not inherit: as many (oldest first) as it loads itself
                     if (s < (int)nnext) umma_commit(BAR(EMPTY + stg));
@@ -250,6 +257,7 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c]), 1);
                 o[c] = __uint_as_float(v1[c]) + (lane > 0 ? left : 0.f) + (lane < 31 ? right : 0.f);
             }
+            constexpr float ACC_SCALE = F16 ? 1.0f / PACK_SCALE : 1.0f;
             if (lane == 0 && q > 0) {
 #pragma unroll
                 for (int g4 = 0; g4 < 8; ++g4) {
@@ -272,7 +280,8 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             for (int g4 = 0; g4 < 8; ++g4) {
                 float* e = o + 4 * g4;
                 const float4 bq = reinterpret_cast<const float4*>(s_bias)[g4];
-                e[0] += bq.x; e[1] += bq.y; e[2] += bq.z; e[3] += bq.w;
+                if (F16) { e[0] = fmaf(e[0], ACC_SCALE, bq.x); e[1] = fmaf(e[1], ACC_SCALE, bq.y); e[2] = fmaf(e[2], ACC_SCALE, bq.z); e[3] = fmaf(e[3], ACC_SCALE, bq.w); }
+                else { e[0] += bq.x; e[1] += bq.y; e[2] += bq.z; e[3] += bq.w; }
                 if (a.residual) { e[0] += pre[g4].x; e[1] += pre[g4].y; e[2] += pre[g4].z; e[3] += pre[g4].w; }
                 if (a.relu) {
 #pragma unroll
@@ -289,12 +298,23 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     for (int k = 0; k < 4; ++k) e[k] = rna_tf32(e[k]);
                 }
             }
-            if (a.y_lo) {                                                 // hi / lo split of the fp32 result (hi is tf32-exact)
+            if (a.y_lo || a.y_pack) {                                     // hi / lo split of the fp32 result (hi is tf32-exact)
                 float lo[32];
 #pragma unroll
                 for (int c = 0; c < 32; ++c) { const float hi = rna_tf32(o[c]); lo[c] = o[c] - hi; o[c] = hi; }
                 rowio_store_rows(a.y + orow_w * 32, o, rowmask, sc);
-                rowio_store_rows(a.y_lo + orow_w * 32, lo, rowmask, sc);
+                if (a.y_lo) rowio_store_rows(a.y_lo + orow_w * 32, lo, rowmask, sc);
+                if (a.y_pack) {                                           // [ fp16(hi) x 32 | fp16(PACK_SCALE * lo) x 32 ] as 32 words
+                    float pk[32];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const __half2 h = __floats2half2_rn(o[2 * c], o[2 * c + 1]);
+                        const __half2 l = __floats2half2_rn(lo[2 * c] * PACK_SCALE, lo[2 * c + 1] * PACK_SCALE);
+                        pk[c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+                        pk[16 + c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l));
+                    }
+                    rowio_store_rows(a.y_pack + orow_w * 32, pk, rowmask, sc);
+                }
             } else {
                 rowio_store_rows(a.y + orow_w * 32, o, rowmask, sc);
             }
@@ -325,7 +345,7 @@ int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st) {
     const int pw = p.off[3] - p.off[0];
     a.B = p.B; a.in_lead = p.in_lead; a.in_pstride = p.in_pstride; a.og = og; a.pw = pw;
     a.bias = p.bias; a.residual = p.residual; a.relumask = p.relumask; a.y = p.y; a.relu = p.relu; a.round_tf32 = p.round_tf32;
-    a.residual2 = p.residual2; a.residual3 = p.residual3; a.y_lo = p.y_lo;
+    a.residual2 = p.residual2; a.residual3 = p.residual3; a.y_lo = p.y_lo; a.y_pack = p.y_pack;
     if ((p.residual2 || p.residual3) && !p.residual) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: residual2/3 need residual");
     if (p.residual3 && !p.residual2) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: residual3 needs residual2");
     a.slab_rows = ((128 + 2 * pw + 7) / 8) * 8;
@@ -355,10 +375,16 @@ int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = a.B * a.chunks * a.nt;
     const int grid = ntiles < sms ? ntiles : sms;
-    PV_TIMED(p.tag ? p.tag : "rowconv3_tc", st, p.flops, 0.0, 2.0 * (double)ntiles * 128.0 * 96.0 * 288.0);
-    static size_t attr[16] = {};
-    PV_CUDA(ensure_dyn_smem(rowconv3_tc_kernel, smem, attr));
-    PV_CUDA(launch_pdl(rowconv3_tc_kernel, grid, C3_THREADS, smem, st, tm_x, tm_w, a));
+    // executed flops: a packed fp16 pass runs K = 64 per tap (both correction products) in the same number of MMAs
+    PV_TIMED(p.tag ? p.tag : "rowconv3_tc", st, p.flops, 0.0, (p.f16_pack ? 2.0 : 1.0) * 2.0 * (double)ntiles * 128.0 * 96.0 * 288.0);
+    static size_t attr[16] = {}, attr_h[16] = {};
+    if (p.f16_pack) {
+        PV_CUDA(ensure_dyn_smem(rowconv3_tc_kernel<true>, smem, attr_h));
+        PV_CUDA(launch_pdl(rowconv3_tc_kernel<true>, grid, C3_THREADS, smem, st, tm_x, tm_w, a));
+    } else {
+        PV_CUDA(ensure_dyn_smem(rowconv3_tc_kernel<false>, smem, attr));
+        PV_CUDA(launch_pdl(rowconv3_tc_kernel<false>, grid, C3_THREADS, smem, st, tm_x, tm_w, a));
+    }
     PV_LAUNCH_CHECK();
     return 0;
 }

@@ -7,6 +7,7 @@
 //   -> reflect pad -> G0 [G] -> convReducer_1..3 (+ReLU) -> G1..G3 -> upscaleConv1 -> U [G] -> tail (+ 2-D skip path)
 // Backward: every data-gradient kernel masks its output with the ReLU of the layer it flows into, so the stored
 // tensors are dL/d(pre-activation) and the weight-gradient kernels need no mask.
+#include <cuda_fp16.h>
 #include <cmath>
 #include <cstring>
 
@@ -152,14 +153,15 @@ int dgrad_rows(pv_model* m, const Layer& L, const Taps& tp /* negated offsets */
     return m->use_tc ? launch_rowconv_tc(p, st) : launch_rowconv_simt(p, st);
 }
 
-// Error-compensated forward convolution (precision 4): operands as (hi, lo) row arrays, three passes of the conv3 kernel chained
+// Error-compensated forward convolution (precision 4), x w ~= x_hi w_hi + (x_lo w_hi + x_hi w_lo), in TWO passes of the conv3 kernel chained
 // through the fp32 partial buffer `yp` (same geometry as the output):
-//     yp  = x_lo * w_hi + bias (+ res_hi + res_lo);   yp += x_hi * w_lo;   v = act(x_hi * w_hi + yp)  ->  (y_hi, y_lo) = split(v)
-// The skip connection and the bias ride on the FIRST pass so that every pass's epilogue reads at most two extra row arrays (with all
-// three on the last pass it ran at 104 us against 59 us for the others: ncu long-scoreboard stalls, profiles/r02_ncu_tf32x3_hot_kernels.md).
-// y_lo == nullptr stores v itself (un-rounded fp32: the upscale conv, whose output feeds the CUDA-core tail).
-int conv_rows_x3(pv_model* m, const Layer& L, const Taps& tp, const float* x_hi, const float* x_lo, const RowGeom& ig, float* y_hi, float* y_lo,
-                 const RowGeom& og, const float* res_hi, const float* res_lo, float* yp, int B, const char* tag, cudaStream_t st) {
+//   pass C (kind::f16, K = 64 per tap over packed fp16 pair rows, rows.h):  yp = x_lo w_hi + x_hi w_lo + bias (+ res_hi + res_lo)
+//   pass M (kind::tf32):                                                   v  = act(x_hi w_hi + yp)  ->  y_hi = tf32(v), y_lo = v - y_hi, y_pack
+// Both correction products ride in ONE launch because a packed row holds [hi | scaled lo] for the activations and [scaled lo | hi] for the
+// weights (round 2's first version ran them as two tf32 passes: two 108 KB weight sets do not fit in shared memory at once).
+// y_lo / y_pack nullable; y_lo == y_pack == nullptr stores v itself (un-rounded fp32: the upscale conv, whose output feeds the CUDA-core tail).
+int conv_rows_x3(pv_model* m, const Layer& L, const Taps& tp, const float* x_hi, const float* x_pack, const RowGeom& ig, float* y_hi, float* y_lo,
+                 float* y_pack, const RowGeom& og, const float* res_hi, const float* res_lo, float* yp, int B, const char* tag, cudaStream_t st) {
     RowConvP p;
     memset(&p, 0, sizeof p);
     p.xc = 32; p.n = L.cout_s; p.B = B;
@@ -168,17 +170,15 @@ int conv_rows_x3(pv_model* m, const Layer& L, const Taps& tp, const float* x_hi,
     const int Kflat = L.taps() * L.cin_s;
     for (int i = 0; i < tp.n; ++i) { p.off[i] = tp.off[i]; p.c0[i] = tp.c0[i]; p.wr0[i] = 0; p.wc0[i] = 32 * tp.chunk[i]; }
     p.w_rows = L.cout_s; p.w_cols = Kflat; p.w_kmajor = 1;
-    p.flops = 0.0;                       // the algorithmic flops are booked once, on the last pass
+    p.flops = 0.0;                       // the algorithmic flops are booked once, on the main pass
     p.tag = tag;
-    // pass 1: x_lo * w_hi + bias (+ skip connection)
-    p.x = x_lo; p.w = m->weffT + L.weff_off; p.y = yp; p.bias = m->bias_s + L.bias_s_off;
+    // pass C: both correction products + bias (+ skip connection)
+    p.x = x_pack; p.w = m->weffT_pack + L.weff_off; p.f16_pack = 1; p.y = yp; p.bias = m->bias_s + L.bias_s_off;
     p.residual = res_hi; p.residual2 = res_hi ? res_lo : nullptr;
     PV_TRY(launch_rowconv_tc(p, st));
-    // pass 2: + x_hi * w_lo (in place: a warp reads exactly the rows it then writes)
-    p.x = x_hi; p.w = m->weffT_lo + L.weff_off; p.bias = nullptr; p.residual = yp; p.residual2 = nullptr;
-    PV_TRY(launch_rowconv_tc(p, st));
-    // pass 3: + x_hi * w_hi, activation, split
-    p.w = m->weffT + L.weff_off; p.relu = L.relu; p.y = y_hi; p.y_lo = y_lo;
+    // pass M: + x_hi * w_hi, activation, split
+    p.x = x_hi; p.w = m->weffT + L.weff_off; p.f16_pack = 0; p.bias = nullptr; p.residual = yp; p.residual2 = nullptr;
+    p.relu = L.relu; p.y = y_hi; p.y_lo = y_lo; p.y_pack = y_pack;
     p.flops = 2.0 * B * L.Ho * L.Wo * L.To * L.taps() * L.cin * L.cout;
     return launch_rowconv_tc(p, st);
 }
@@ -450,18 +450,30 @@ static float host_tf32(float v) {
     return r;
 }
 struct SplitBuf {
-    float *full = nullptr, *hi = nullptr, *lo = nullptr;
-    int upload(const std::vector<float>& h) {
+    float *full = nullptr, *hi = nullptr, *lo = nullptr, *pack = nullptr;
+    // pack_mode 1: activation rows [fp16(hi) | fp16(PACK_SCALE lo)], 2: weight rows [fp16(PACK_SCALE lo) | fp16(hi)] per 32 values (rows.h)
+    int upload(const std::vector<float>& h, int pack_mode = 0) {
         const size_t n = h.size();
         std::vector<float> a(n), b(n);
         for (size_t i = 0; i < n; ++i) { a[i] = host_tf32(h[i]); b[i] = h[i] - a[i]; }
+        if (pack_mode) {
+            std::vector<__half> pk(2 * n);
+            for (size_t r = 0; r < n / 32; ++r)
+                for (int c = 0; c < 32; ++c) {
+                    const __half hh = __float2half_rn(a[r * 32 + c]), ll = __float2half_rn(b[r * 32 + c] * PACK_SCALE);
+                    pk[r * 64 + (pack_mode == 1 ? c : 32 + c)] = hh;
+                    pk[r * 64 + (pack_mode == 1 ? 32 + c : c)] = ll;
+                }
+            PV_CUDA(cudaMalloc(&pack, n * 4));
+            PV_CUDA(cudaMemcpy(pack, pk.data(), n * 4, cudaMemcpyHostToDevice));
+        }
         PV_CUDA(cudaMalloc(&full, n * 4)); PV_CUDA(cudaMalloc(&hi, n * 4)); PV_CUDA(cudaMalloc(&lo, n * 4));
         PV_CUDA(cudaMemcpy(full, h.data(), n * 4, cudaMemcpyHostToDevice));
         PV_CUDA(cudaMemcpy(hi, a.data(), n * 4, cudaMemcpyHostToDevice));
         PV_CUDA(cudaMemcpy(lo, b.data(), n * 4, cudaMemcpyHostToDevice));
         return 0;
     }
-    void release() { cudaFree(full); cudaFree(hi); cudaFree(lo); }
+    void release() { cudaFree(full); cudaFree(hi); cudaFree(lo); cudaFree(pack); }
 };
 
 static int selftest_x3(std::string& rep) {
@@ -499,7 +511,7 @@ static int selftest_x3(std::string& rep) {
     int fails = 0, rc = 0;
     std::vector<float> h;
     SplitBuf X, RES, W3, WE, WD;
-    rows_rand(h, 1.0f); PV_TRY(X.upload(h));
+    rows_rand(h, 1.0f); PV_TRY(X.upload(h, 1));
     rows_rand(h, 1.0f); PV_TRY(RES.upload(h));
     // ---------------- conv3 'same' forward, bias + skip connection: weights [co = 32][K = 27 * 32] K-major for the tensor cores
     {
@@ -507,7 +519,7 @@ static int selftest_x3(std::string& rep) {
         for (auto& v : wk) v = rnd(0.08f);
         for (int co = 0; co < 32; ++co) for (int k = 0; k < 864; ++k) wt[(size_t)k * 32 + co] = wk[(size_t)co * 864 + k];
         for (auto& v : bb) v = rnd(0.5f);
-        PV_TRY(W3.upload(wk));
+        PV_TRY(W3.upload(wk, 2));
         float *wt_d, *b_d, *y0, *yh, *yl, *yp;
         PV_CUDA(cudaMalloc(&wt_d, wt.size() * 4)); PV_CUDA(cudaMalloc(&b_d, 128));
         PV_CUDA(cudaMemcpy(wt_d, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice)); PV_CUDA(cudaMemcpy(b_d, bb.data(), 128, cudaMemcpyHostToDevice));
@@ -520,15 +532,35 @@ static int selftest_x3(std::string& rep) {
         for (int i = 0; i < 27; ++i) { q.off[i] = tp.off[i]; q.wr0[i] = 32 * i; q.wc0[i] = 0; }
         rc = launch_rowconv_simt(q, 0);
         pv_model fm;                                   // just enough of a model for conv_rows_x3
-        fm.weffT = W3.hi; fm.weffT_lo = W3.lo; fm.bias_s = b_d; fm.use_tc = true; fm.x3 = true;
+        fm.weffT = W3.hi; fm.weffT_lo = W3.lo; fm.weffT_pack = W3.pack; fm.bias_s = b_d; fm.use_tc = true; fm.x3 = true;
         Layer L;
         L.k[0] = L.k[1] = L.k[2] = 3; L.cin = L.cout = L.cin_s = L.cout_s = 32; L.relu = 0; L.weff_off = 0; L.bias_s_off = 0;
         L.Ho = L.Wo = 22; L.To = 9;
-        if (!rc) rc = conv_rows_x3(&fm, L, tp, X.hi, X.lo, pr, yh, yl, pr, RES.hi, RES.lo, yp, B, "selftest_x3", 0);
+        float* ypk;
+        PV_CUDA(cudaMalloc(&ypk, rows * 128)); PV_CUDA(cudaMemset(ypk, 0, rows * 128));
+        if (!rc) rc = conv_rows_x3(&fm, L, tp, X.hi, X.pack, pr, yh, yl, ypk, pr, RES.hi, RES.lo, yp, B, "selftest_x3", 0);
         if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest x3 conv: %s", cudaGetErrorString(cudaGetLastError()));
         if (rc) { rep += std::string("x3 conv3 same fwd                  FAIL : ") + last_error() + "\n"; ++fails; }
-        else fails += compare("x3 conv3 same fwd (+bias +skip)", y0, yh, yl, rows * 32, 2e-5);
-        for (float* p : {wt_d, b_d, y0, yh, yl, yp}) cudaFree(p);
+        else {
+            fails += compare("x3 conv3 same fwd (+bias +skip)", y0, yh, yl, rows * 32, 2e-5);
+            // the packed output row must decode to the same (hi, lo) pair, to fp16's 11 bits of the lo half
+            std::vector<float> hh(rows * 32), ll(rows * 32);
+            std::vector<__half> pk(rows * 64);
+            cudaMemcpy(hh.data(), yh, rows * 128, cudaMemcpyDeviceToHost); cudaMemcpy(ll.data(), yl, rows * 128, cudaMemcpyDeviceToHost);
+            cudaMemcpy(pk.data(), ypk, rows * 128, cudaMemcpyDeviceToHost);
+            size_t bad = 0;
+            for (size_t r = 0; r < rows; ++r)
+                for (int c = 0; c < 32; ++c) {
+                    const float dh = __half2float(pk[r * 64 + c]), dl = __half2float(pk[r * 64 + 32 + c]) / PACK_SCALE;
+                    // (values below fp16's normal range, 6e-5, keep fewer bits: absolute floors)
+                    if (std::fabs(dh - hh[r * 32 + c]) > 6e-8f || std::fabs(dl - ll[r * 32 + c]) > 1e-3f * std::fabs(ll[r * 32 + c]) + 2e-11f) ++bad;
+                }
+            char line[256];
+            snprintf(line, sizeof line, "%-34s %s %zu mismatching elements of %zu\n", "x3 conv3: packed fp16 pair output", bad == 0 ? "PASS" : "FAIL", bad, rows * 32);
+            rep += line;
+            fails += bad == 0 ? 0 : 1;
+        }
+        for (float* p : {wt_d, b_d, y0, yh, yl, yp, ypk}) cudaFree(p);
     }
     // ---------------- fused expand -> ReLU -> decay forward
     {
@@ -561,7 +593,15 @@ static int selftest_x3(std::string& rep) {
         if (!rc) rc = launch_rowconv_simt(pd, 0);
         for (int variant = 0; variant < 2 && !rc; ++variant) {
             PV_CUDA(cudaMemset(dh, 0, rows * 128)); PV_CUDA(cudaMemset(dl, 0, rows * 128));
-            rc = launch_resfront_fwd_x3_tc(X.hi, X.lo, WE.hi, WE.lo, WD.hi, WD.lo, be_d, bd_d, dh, dl, variant ? bits : nullptr, variant ? bits_t : nullptr, pr, B, 0.0, 0);
+            rc = launch_resfront_fwd_x3_tc(X.hi, X.lo, WE.hi, WE.lo, WD.hi, WD.lo, be_d, bd_d, dh, dl, variant ? bits : nullptr, variant ? bits_t : nullptr, pr, B, 0.0, 0, variant);
+            if (!rc && variant) {       // the training variant writes packed fp16 pair rows: decode the lo half back to fp32 for the comparison
+                if (cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest x3 resfront: %s", cudaGetErrorString(cudaGetLastError()));
+                std::vector<__half> pk(rows * 64);
+                std::vector<float> ll(rows * 32);
+                cudaMemcpy(pk.data(), dl, rows * 128, cudaMemcpyDeviceToHost);
+                for (size_t r = 0; r < rows; ++r) for (int c = 0; c < 32; ++c) ll[r * 32 + c] = __half2float(pk[r * 64 + 32 + c]) / PACK_SCALE;
+                cudaMemcpy(dl, ll.data(), rows * 128, cudaMemcpyHostToDevice);
+            }
             if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest x3 resfront: %s", cudaGetErrorString(cudaGetLastError()));
             if (!rc) fails += compare(variant ? "x3 fused exp->relu->dec (train)" : "x3 fused exp->relu->dec (infer)", d0, dh, dl, rows * 32, 2e-5);
         }
@@ -739,10 +779,14 @@ int tc_build_plan(pv_model* m) {
             size_t yp_per = rows_per(pr, F), yp_extra = rows_extra(pr, F);
             P.add("a_lo0", rows_per(pr, F), rows_extra(pr, F));
             P.add("a_lo1", rows_per(pr, F), rows_extra(pr, F));
-            P.add("D_lo", rows_per(pr, F), rows_extra(pr, F));
+            P.add("D_pack", rows_per(pr, F), rows_extra(pr, F));         // packed fp16 pair rows (rows.h): what a compensated conv3 reads
             for (const TailStep& ts : tail) {
-                if (ts.copy) P.add(ts.in + "_lo", rows_per(ts.ig, F), rows_extra(ts.ig, F));
+                if (ts.copy) {
+                    P.add(ts.in + "_lo", rows_per(ts.ig, F), rows_extra(ts.ig, F));
+                    P.add(ts.in + "_pack", rows_per(ts.ig, F), rows_extra(ts.ig, F));
+                }
                 P.add(ts.out + "_lo", rows_per(ts.og, F), rows_extra(ts.og, F));
+                P.add(ts.out + "_pack", rows_per(ts.og, F), rows_extra(ts.og, F));
                 yp_per = std::max(yp_per, std::max(rows_per(ts.ig, F), rows_per(ts.og, F)));
                 yp_extra = std::max(yp_extra, std::max(rows_extra(ts.ig, F), rows_extra(ts.og, F)));
             }
@@ -813,31 +857,35 @@ static int tc_forward_x3(pv_model* m, int B, float* sr, bool tr, int clip_round,
         const Layer &Le = m->layers[e], &Ld = m->layers[e + 1];
         const double fl = 2.0 * B * Le.Ho * Le.Wo * Le.To * ((double)Le.cin * Le.cout + (double)Ld.cin * Ld.cout);
         PV_TRY(launch_resfront_fwd_x3_tc(P[m->A(i, tr)], alo(i), m->weffT + Le.weff_off, m->weffT_lo + Le.weff_off, m->weffT + Ld.weff_off,
-                                         m->weffT_lo + Ld.weff_off, m->bias_s + Le.bias_s_off, m->bias_s + Ld.bias_s_off, P[m->D(i, tr)], P["D_lo"],
+                                         m->weffT_lo + Ld.weff_off, m->bias_s + Le.bias_s_off, m->bias_s + Ld.bias_s_off, P[m->D(i, tr)], P["D_pack"],
                                          tr ? reinterpret_cast<uint32_t*>(P["M" + std::to_string(i)]) : nullptr,
-                                         tr ? reinterpret_cast<uint32_t*>(P["MT" + std::to_string(i)]) : nullptr, pr, B, fl, st));
-        PV_TRY(conv_rows_x3(m, m->layers[e + 2], same, P[m->D(i, tr)], P["D_lo"], pr, P[m->A(i + 1, tr)], alo(i + 1), pr, P[m->A(i, tr)], alo(i),
+                                         tr ? reinterpret_cast<uint32_t*>(P["MT" + std::to_string(i)]) : nullptr, pr, B, fl, st, 1));
+        PV_TRY(conv_rows_x3(m, m->layers[e + 2], same, P[m->D(i, tr)], P["D_pack"], pr, P[m->A(i + 1, tr)], alo(i + 1), nullptr, pr, P[m->A(i, tr)], alo(i),
                             yp, B, "norm_fwd_x3", st));
     }
     const Taps valid = conv3_taps(576, 24, false, +1);
     for (size_t k = 0; k < tail.size(); ++k) {
         const TailStep& ts = tail[k];
-        const float *in_hi, *in_lo;
+        const float *in_hi, *in_pack;
         if (k == 0 || ts.copy) {
+            // re-layout (+ reflect pad) of the hi and lo halves, then the packed pair rows of the padded tensor (padding rows pack to zero)
             const float* src_hi = k == 0 ? P[m->A(m->R, tr)] : P[tail[k - 1].out];
             const float* src_lo = k == 0 ? alo(m->R) : P[tail[k - 1].out + "_lo"];
             const RowGeom sg = k == 0 ? pr : tail[k - 1].og;
             PV_TRY(launch_pr_to_g_reflect(src_hi, sg, P[ts.in], ts.ig, B, F, st, ts.pad));
             PV_TRY(launch_pr_to_g_reflect(src_lo, sg, P[ts.in + "_lo"], ts.ig, B, F, st, ts.pad));
-            in_hi = P[ts.in]; in_lo = P[ts.in + "_lo"];
+            PV_TRY(launch_pack_rows(P[ts.in], P[ts.in + "_lo"], P[ts.in + "_pack"], ts.ig.lead + (long long)B * ts.ig.pstride + ROW_TAIL, st));
+            in_hi = P[ts.in]; in_pack = P[ts.in + "_pack"];
         } else {
-            in_hi = P[tail[k - 1].out]; in_lo = P[tail[k - 1].out + "_lo"];
+            in_hi = P[tail[k - 1].out]; in_pack = P[tail[k - 1].out + "_pack"];
         }
         const Layer& L = m->layers[m->li("convReducer_" + std::to_string(k + 1))];
-        PV_TRY(conv_rows_x3(m, L, valid, in_hi, in_lo, ts.ig, P[ts.out], P[ts.out + "_lo"], ts.og, nullptr, nullptr, yp, B, "reducer_fwd_x3", st));
+        // a reducer's output feeds the next conv directly (packed rows) or through a reflect-pad copy (hi + lo): write both
+        PV_TRY(conv_rows_x3(m, L, valid, in_hi, in_pack, ts.ig, P[ts.out], P[ts.out + "_lo"], P[ts.out + "_pack"], ts.og, nullptr, nullptr, yp, B,
+                            "reducer_fwd_x3", st));
     }
-    PV_TRY(conv_rows_x3(m, m->layers[m->li("upscaleConv1")], valid, P[tail.back().out], P[tail.back().out + "_lo"], tail.back().og, P["U"], nullptr, ug,
-                        nullptr, nullptr, yp, B, "upscale_fwd_x3", st));
+    PV_TRY(conv_rows_x3(m, m->layers[m->li("upscaleConv1")], valid, P[tail.back().out], P[tail.back().out + "_pack"], tail.back().og, P["U"], nullptr, nullptr,
+                        ug, nullptr, nullptr, yp, B, "upscale_fwd_x3", st));
     return tc_forward_tail(m, B, sr, tr, clip_round, st);
 }
 

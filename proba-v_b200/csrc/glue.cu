@@ -5,7 +5,10 @@
 //   weight norm     : TFA WeightNormalization kernel = g * v/||v||, all layers in one launch, + backward
 //   optimizers      : Keras Nadam / Adam / SGD over the flat parameter arena (train.py:77-83)
 //   scene geometry  : reflect-pad-3 + unfold(22, stride 16) and the n x n stitch (dataGenerator.py:108-121; test.py:149-160)
+#include <cuda_fp16.h>
+
 #include "kernels.h"
+#include "rows.h"
 
 namespace pv {
 namespace {
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(128) wn_prep_kernel(const WnLayer* __restrict_
                                                       const float* __restrict__ params, float* __restrict__ weff,
                                                       float* __restrict__ weffT, float* __restrict__ bias_s,
                                                       float* __restrict__ scale, float* __restrict__ weff_lo,
-                                                      float* __restrict__ weffT_lo) {
+                                                      float* __restrict__ weffT_lo, float* __restrict__ weffT_pack) {
     pdl_grid_wait();
     __shared__ float red[4];
     int co;
@@ -169,6 +172,13 @@ __global__ void __launch_bounds__(128) wn_prep_kernel(const WnLayer* __restrict_
         if (weff_lo && L.mode == 1) {       // error-compensated engine: the remainder of the tf32 rounding, same two layouts
             weff_lo[L.weff_off + ((long long)rt * L.cin_s + ci) * L.cout_s + co] = wf - w;
             weffT_lo[L.weffT_off + (long long)co * (L.taps * L.cin_s) + (long long)rt * L.cin_s + ci] = wf - w;
+            if (weffT_pack && L.taps == 27 && L.cin_s == 32) {
+                // packed fp16 pair row of (co, tap): [ fp16(PACK_SCALE * w_lo) x 32 | fp16(w_hi) x 32 ] (rows.h) in the 128 bytes
+                // the 32 fp32 K-values of weffT occupy
+                __half* row = reinterpret_cast<__half*>(weffT_pack + L.weffT_off + (long long)co * (L.taps * L.cin_s) + (long long)rt * L.cin_s);
+                row[ci] = __float2half_rn((wf - w) * PACK_SCALE);
+                row[32 + ci] = __float2half_rn(w);
+            }
         }
     }
 }
@@ -321,9 +331,9 @@ int launch_tail_bwd(const float* dsr, int B, int P, int scale, float stdv, float
 }
 
 int launch_wn_prep(const WnLayer* tab, int nlayers, int nblocks, const float* params, float* weff, float* weffT,
-                   float* bias_s, float* scale, cudaStream_t st, float* weff_lo, float* weffT_lo) {
+                   float* bias_s, float* scale, cudaStream_t st, float* weff_lo, float* weffT_lo, float* weffT_pack) {
     PV_TIMED("wn_prep", st);
-    PV_CUDA(launch_pdl_simple(wn_prep_kernel, nblocks, 128, 0, st, tab, nlayers, params, weff, weffT, bias_s, scale, weff_lo, weffT_lo));
+    PV_CUDA(launch_pdl_simple(wn_prep_kernel, nblocks, 128, 0, st, tab, nlayers, params, weff, weffT, bias_s, scale, weff_lo, weffT_lo, weffT_pack));
     PV_LAUNCH_CHECK();
     return 0;
 }

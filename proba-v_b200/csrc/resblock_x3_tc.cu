@@ -18,6 +18,8 @@
 // issue order, which is what makes re-using a unit buffer three units later safe.  Two epilogue groups of four warps take
 // alternate tiles.  mbarrier rule (profiles/r01_next_round_notes.md): a parity wait is only correct if the waiter sees EVERY
 // phase of its barrier, so the "E ready" barriers are indexed by (group, quarter): one waiting group, consecutive phases.
+#include <cuda_fp16.h>
+
 #include "rowio.cuh"
 #include "rows.h"
 #include "tc_common.cuh"
@@ -39,7 +41,8 @@ struct ResX3Args {
     uint32_t* mask;                    // [rows][8] ReLU bit mask (training) or nullptr
     uint32_t* mask_t;                  // [tile][4 row blocks][256 channels]: bit k = row k of the 32-row block (for the weight-gradient kernel)
     float* out_hi;                     // D rows: tf32(D)
-    float* out_lo;                     //         D - tf32(D)
+    float* out_lo;                     //         D - tf32(D), or (pack_out) the packed fp16 pair rows of (hi, lo): what the
+    int pack_out;                      //         compensated 3x3x3 convolution's correction pass reads (rows.h PACK_SCALE)
 };
 
 __device__ __forceinline__ uint32_t tf32_rn_bits(uint32_t bits) { return (bits + 0x1000u) & 0xffffe000u; }
@@ -75,7 +78,7 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = tmem_slot;                // unit buffers (E_hi 64 | E_lo 64) at columns 0 / 128 / 256, D accumulators at 384 / 416
+    const uint32_t tmem = tmem_slot;                // unit buffers (E_hi 64 | E_lo 64) at columns 0 / 128 / 256, D accumulators at 384 / 416 (main), 448 / 480 (corrections)
     const int ntiles = a.B * a.tiles_per_patch;
     const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
@@ -135,14 +138,18 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                     mbar_wait(BAR(EREADY + eb), (v / 3) & 1);
                     tc_fence_after();
                     if (q == 0) { mbar_wait(BAR(DFREE + db), ((tl >> 1) & 1) ^ 1); tc_fence_after(); }
-                    const uint32_t d = tmem + 384 + 32 * db, eh = tmem + eb * 128, el = eh + 64;
+                    // Two accumulators per tile: the 32-step main chain E_hi Wd_hi and the 64-step correction chain.  tcgen05 truncates the
+                    // fp32 accumulator at every accumulation step (one ulp of the ACCUMULATOR, whatever the addend's size), so chaining the tiny
+                    // corrections behind the main sum cost 64 extra truncations of the full-size value (D carried a -4.4e-6 scale error,
+                    // profiles/r02_tf32_numerics_study.md); the correction accumulator is 2^-11 of the size and its truncations are harmless.
+                    const uint32_t d = tmem + 384 + 32 * db, dc = tmem + 448 + 32 * db, eh = tmem + eb * 128, el = eh + 64;
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint32_t off = (uint32_t)(2 * q + (ks >> 2)) * 4096;
                         const uint64_t bh = smem_desc(HI, w2h_smem + off) + 2 * (ks & 3), bl = smem_desc(HI, w2l_smem + off) + 2 * (ks & 3);
                         umma_ts<true>(d, eh + ks * 8, bh, IDESC2, (q > 0 || ks > 0) ? 1u : 0u);
-                        umma_ts<true>(d, el + ks * 8, bh, IDESC2, 1u);
-                        umma_ts<true>(d, eh + ks * 8, bl, IDESC2, 1u);
+                        umma_ts<true>(dc, el + ks * 8, bh, IDESC2, (q > 0 || ks > 0) ? 1u : 0u);
+                        umma_ts<true>(dc, eh + ks * 8, bl, IDESC2, 1u);
                     }
                     if (q == 3) umma_commit(BAR(DFULL + db));
                 }
@@ -231,12 +238,15 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
             const uint32_t db = tl & 1;                       // == grp
             mbar_wait(BAR(DFULL + db), tph);
             tc_fence_after();
-            uint32_t v[32];
+            uint32_t v[32], vc[32];
             tmem_ld32(lane_base + 384 + 32 * db, v);
+            tmem_ld32(lane_base + 448 + 32 * db, vc);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(DFREE + db));
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(vc[c]));   // main + corrections, rounded to nearest
             float hi[32], lo[32];
 #pragma unroll
             for (int g4 = 0; g4 < 8; ++g4) {
@@ -251,7 +261,19 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                 }
             }
             rowio_store_rows(a.out_hi + orow_w * 32, hi, rowmask, sc);
-            rowio_store_rows(a.out_lo + orow_w * 32, lo, rowmask, sc);
+            if (a.pack_out) {
+                float pk[32];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const __half2 h2 = __floats2half2_rn(hi[2 * c], hi[2 * c + 1]);
+                    const __half2 l2 = __floats2half2_rn(lo[2 * c] * PACK_SCALE, lo[2 * c + 1] * PACK_SCALE);
+                    pk[c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h2));
+                    pk[16 + c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l2));
+                }
+                rowio_store_rows(a.out_lo + orow_w * 32, pk, rowmask, sc);
+            } else {
+                rowio_store_rows(a.out_lo + orow_w * 32, lo, rowmask, sc);
+            }
         }
     }
     tc_fence_before();
@@ -270,10 +292,10 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
 int launch_resfront_fwd_x3_tc(const float* x_hi, const float* x_lo, const float* weT_exp_hi, const float* weT_exp_lo,
                               const float* weT_dec_hi, const float* weT_dec_lo, const float* bias_e, const float* bias_d,
                               float* d_hi, float* d_lo, uint32_t* relu_bits, uint32_t* relu_bits_t, const RowGeom& g, int B, double flops,
-                              cudaStream_t st) {
+                              cudaStream_t st, int pack_out) {
     ResX3Args a;
     memset(&a, 0, sizeof a);
-    a.B = B; a.g = g; a.bias1 = bias_e; a.bias2 = bias_d; a.mask = relu_bits; a.mask_t = relu_bits_t; a.out_hi = d_hi; a.out_lo = d_lo;
+    a.B = B; a.g = g; a.bias1 = bias_e; a.bias2 = bias_d; a.mask = relu_bits; a.mask_t = relu_bits_t; a.out_hi = d_hi; a.out_lo = d_lo; a.pack_out = pack_out;
     a.tiles_per_patch = cdiv(g.nrows, 128);
     const long long rows = g.lead + (long long)B * g.pstride + ROW_TAIL;
     CUtensorMap tm_xh, tm_xl, tm_w1h, tm_w1l, tm_w2h, tm_w2l;

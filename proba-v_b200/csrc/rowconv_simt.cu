@@ -4,6 +4,8 @@
 // layers that are not tensor-core shaped (mainConv1, Cin = 1) and as the on-device cross-check of each tcgen05
 // kernel (pv_selftest), and (b) the layout glue between the PR trunk and the valid-conv tail.
 // Reference semantics: Keras Conv3D inside TFA WeightNormalization (modelsTF.py:191-197), tf.pad REFLECT (:157-158).
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 #include "wgrad_reduce.cuh"
 #include "rows.h"
@@ -485,6 +487,20 @@ __global__ void pr_to_g_reflect_bwd_kernel(const float* __restrict__ gg0, RowGeo
     reinterpret_cast<float4*>(ga)[dst * C4 + c] = s;
 }
 
+// (hi, lo) fp32 rows -> packed fp16 pair rows [ fp16(hi) x 32 | fp16(PACK_SCALE * lo) x 32 ]; one thread per 4 channels of a row
+__global__ void pack_rows_kernel(const float* __restrict__ hi, const float* __restrict__ lo, float* __restrict__ pack, long long n4) {
+    pdl_grid_wait();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const long long row = i >> 3; const int q = (int)(i & 7);
+    const float4 h = __ldg(reinterpret_cast<const float4*>(hi) + i), l = __ldg(reinterpret_cast<const float4*>(lo) + i);
+    const __half2 h0 = __floats2half2_rn(h.x, h.y), h1 = __floats2half2_rn(h.z, h.w);
+    const __half2 l0 = __floats2half2_rn(l.x * PACK_SCALE, l.y * PACK_SCALE), l1 = __floats2half2_rn(l.z * PACK_SCALE, l.w * PACK_SCALE);
+    uint2* dst = reinterpret_cast<uint2*>(pack + row * 32);
+    dst[q] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    dst[8 + q] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+
 // sr[b, s*h+i, s*w+j] = (U[row(b,0,h,w)][i*s+j] + resid[b,h,w,i*s+j]) * std + mean
 __global__ void tail_rows_kernel(const float* __restrict__ u, RowGeom g, int uc, const float* __restrict__ resid, long long n,
                                  int P, int s, float mean, float stdv, int clip_round, float* __restrict__ sr) {
@@ -516,6 +532,14 @@ __global__ void tail_bwd_rows_kernel(const float* __restrict__ dsr, long long n,
 }
 
 }  // namespace
+
+int launch_pack_rows(const float* hi, const float* lo, float* pack, long long n32, cudaStream_t st) {
+    const long long n4 = n32 * 8;
+    PV_TIMED("pack_rows", st, 0.0, (double)n32 * 384.0);
+    PV_CUDA(launch_pdl_simple(pack_rows_kernel, cdiv(n4, 256), 256, 0, st, hi, lo, pack, n4));
+    PV_LAUNCH_CHECK();
+    return 0;
+}
 
 int launch_tail_rows(const float* u, RowGeom g, int uc, const float* resid, int B, int P, int scale, float mean, float stdv,
                      int clip_round, float* sr, cudaStream_t st) {

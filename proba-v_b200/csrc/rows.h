@@ -39,6 +39,14 @@ __host__ __device__ inline bool row_valid(const RowGeom& g, int r /* row inside 
     return t >= 0 && t < g.nt && h < g.nh && w < g.nw;
 }
 
+// Packed fp16 pair rows (error-compensated engine, the ONE correction pass of a compensated convolution): a 128-byte row holds 64 halves,
+//   activations  [ fp16(x_hi[0..31]) | fp16(PACK_SCALE * x_lo[0..31]) ]        weights (per output channel and tap)  [ fp16(PACK_SCALE * w_lo) | fp16(w_hi) ]
+// so that one K = 64 dot product of the two rows is PACK_SCALE * (x_hi w_lo + x_lo w_hi): both correction products of
+// x w ~= x_hi w_hi + x_lo w_hi + x_hi w_lo in one kind::f16 MMA chain with the descriptors of the fp32 rows (same 128-byte rows, same
+// 32-byte K steps).  hi = tf32(v) has 11 significant bits and is exact in fp16 (values are O(1) after normalisation); |lo| <= 2^-12 |v| is
+// scaled by 2^12 into fp16's normal range (Ootomo & Yokota's scaling), so the corrections keep 11 bits: 2^-23 of the product.
+constexpr float PACK_SCALE = 4096.0f;
+
 constexpr int ROW_TAIL = 2048;   // rows allocated (and zero) after the last patch of every row buffer
 constexpr int MAX_TAPS = 27;
 constexpr int MAX_SLABS = 8;
@@ -58,6 +66,9 @@ struct RowConvP {
     const float* residual2;            // two more addends of the same shape (conv3_tc only): the error-compensated forward chains
     const float* residual3;            //   its partial passes and the hi / lo halves of the skip connection through them
     float* y_lo;                       // conv3_tc only: when set, y receives hi = tf32(v) and y_lo the remainder v - hi
+    float* y_pack;                     // conv3_tc only: when set, also the PACKED fp16 pair row of (hi, lo) (see PACK_SCALE)
+    int f16_pack;                      // conv3_tc only: x and w are packed fp16 pair rows; the kernel issues kind::f16 MMAs (K = 16) over the
+                                       //   64-element rows, which yields PACK_SCALE * (x_hi w_lo + x_lo w_hi), and scales the sum back
     const float* relumask;             // [rows][n]: output multiplied by (relumask > 0), or nullptr
     float* y; int n;                   // output rows, channels per output row
     int B;
@@ -111,7 +122,7 @@ int launch_resfront_bwd_data_tc(const float* gd, const float* w_dec, const float
 int launch_resfront_fwd_x3_tc(const float* x_hi, const float* x_lo, const float* weT_exp_hi, const float* weT_exp_lo,
                               const float* weT_dec_hi, const float* weT_dec_lo, const float* bias_e, const float* bias_d,
                               float* d_hi, float* d_lo, uint32_t* relu_bits, uint32_t* relu_bits_t, const RowGeom& g, int B, double flops,
-                              cudaStream_t st);
+                              cudaStream_t st, int pack_out = 0);   // pack_out: d_lo receives the packed fp16 pair rows of (hi, lo)
 int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* weT_exp, const float* w_dec, const float* bias_e,
                                   float* dw_dec, float* dw_exp, float* db_exp, float* db_dec, const RowGeom& g, int B,
                                   float* partials, size_t partial_floats, double flops, cudaStream_t st, ReduceQueue* rq = nullptr,
@@ -134,6 +145,8 @@ int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom 
 int launch_skip2d_fwd_tail(const float* mn, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
                            const float* b3, int B, int S, int C, float* q1, float* q2, float* q3, const float* u, RowGeom ug, int uc,
                            int scale, float mean, float stdv, int clip_round, float* sr, cudaStream_t st);
+// (hi, lo) fp32 row arrays -> packed fp16 pair rows (n32 = number of 32-channel rows)
+int launch_pack_rows(const float* hi, const float* lo, float* pack, long long n32, cudaStream_t st);
 // tail on the row layouts: sr = (depth_to_space(U[:, :, :9]) + depth_to_space(resid)) * std + mean [clip, round]; and its adjoint
 int launch_tail_rows(const float* u, RowGeom g, int uc, const float* resid, int B, int P, int scale, float mean, float stdv,
                      int clip_round, float* sr, cudaStream_t st);

@@ -129,6 +129,19 @@ __device__ __forceinline__ void umma_ss_tf32_lohi(uint32_t d_tmem, uint32_t a_lo
         "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// kind::f16 twin of umma_ss_tf32_lohi (fp16 / bf16 operands, K = 16 per MMA, fp32 accumulate)
+__device__ __forceinline__ void umma_ss_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // A operand read from TMEM ([128 lanes x K columns]), B from smem
 template <bool TF32>
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
