@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(ConvP p) {
 
 // ------------------------------------------------------------------------------------------ wgrad_vec
 template <int BN>
-__global__ void __launch_bounds__(256) wgrad_vec_kernel(WgradP p, int m_per_cta) {
+__global__ void __launch_bounds__(256) wgrad_vec_kernel(WgradP p, int m_per_cta, float* __restrict__ part) {
     constexpr int BKO = 64, BMC = 32, TXN = BN / 4, TYN = 256 / TXN, TK = BKO / TYN;
     __shared__ __align__(16) float At[BMC][BKO + 4];
     __shared__ __align__(16) float Ys[BMC][BN];
@@ -232,6 +232,17 @@ __global__ void __launch_bounds__(256) wgrad_vec_kernel(WgradP p, int m_per_cta)
         }
         __syncthreads();
     }
+    if (part) {     // deterministic: this split's partial sums, one writer per element; summed in split order by wgrad_sum_kernel
+        float* mine = part + (size_t)blockIdx.z * (size_t)(Ktot + 1) * p.cout;
+#pragma unroll
+        for (int i = 0; i < TK; ++i) {
+            const int k = k0 + ty * TK + i;
+            if (k >= Ktot) continue;
+            *reinterpret_cast<float4*>(mine + (size_t)k * p.cout + n0 + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+        if (do_bias) *reinterpret_cast<float4*>(mine + (size_t)Ktot * p.cout + n0 + tx * 4) = make_float4(bsum[0], bsum[1], bsum[2], bsum[3]);
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < TK; ++i) {
         const int k = k0 + ty * TK + i;
@@ -244,8 +255,20 @@ __global__ void __launch_bounds__(256) wgrad_vec_kernel(WgradP p, int m_per_cta)
         for (int j = 0; j < 4; ++j) atomicAdd(p.db + n0 + tx * 4 + j, bsum[j]);
 }
 
+// dw[k][n] (+ db[n] from row Ktot) = sum over the splits, in split order
+__global__ void __launch_bounds__(256) wgrad_sum_kernel(const float* __restrict__ part, int nsplit, int Ktot, int cout, float* __restrict__ dw,
+                                                        float* __restrict__ db) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int n_all = (Ktot + 1) * cout;
+    if (idx >= n_all) return;
+    float s = 0.f;
+    for (int z = 0; z < nsplit; ++z) s += part[(size_t)z * n_all + idx];
+    if (idx < Ktot * cout) dw[idx] += s;
+    else if (db) db[idx - Ktot * cout] += s;
+}
+
 // ------------------------------------------------------------------------------------------ wgrad_direct
-__global__ void __launch_bounds__(256) wgrad_direct_kernel(WgradP p, int m_per_cta) {
+__global__ void __launch_bounds__(256) wgrad_direct_kernel(WgradP p, int m_per_cta, float* __restrict__ part) {
     const long long M = (long long)p.B * p.Ho * p.Wo * p.To;
     const int Ktot = p.kh * p.kw * p.kt * p.cin;
     const int idx = blockIdx.x * 256 + threadIdx.x;          // (k, n) pair, n fastest; k == Ktot rows -> bias
@@ -257,7 +280,10 @@ __global__ void __launch_bounds__(256) wgrad_direct_kernel(WgradP p, int m_per_c
     const int dt = tap % p.kt, dw = (tap / p.kt) % p.kw, dh = tap / (p.kt * p.kw);
     long long mlo = (long long)blockIdx.y * m_per_cta;
     long long mhi = mlo + m_per_cta; if (mhi > M) mhi = M;
-    if (mlo >= mhi) return;
+    if (mlo >= mhi) {
+        if (part && (isw || isb)) part[(size_t)blockIdx.y * (size_t)(Ktot + 1) * p.cout + idx] = 0.f;
+        return;
+    }
     // CTA-uniform incremental decode of the voxel index
     long long t = mlo;
     int to = (int)(t % p.To); t /= p.To;
@@ -278,6 +304,7 @@ __global__ void __launch_bounds__(256) wgrad_direct_kernel(WgradP p, int m_per_c
         }
         if (++to == p.To) { to = 0; if (++wo == p.Wo) { wo = 0; if (++ho == p.Ho) { ho = 0; ++b; } } }
     }
+    if (part) { if (isw || isb) part[(size_t)blockIdx.y * (size_t)(Ktot + 1) * p.cout + idx] = acc; return; }
     if (isw) atomicAdd(p.dw + idx, acc);
     else if (isb) atomicAdd(p.db + n, acc);
 }
@@ -321,15 +348,26 @@ int launch_wgrad(const WgradP& p, cudaStream_t st) {
         per = ((per + 31) / 32) * 32;
         msplit = cdiv(M, per);
         dim3 grid(kt, nt, msplit);
-        if (BN == 64) wgrad_vec_kernel<64><<<grid, 256, 0, st>>>(p, (int)per);
-        else wgrad_vec_kernel<32><<<grid, 256, 0, st>>>(p, (int)per);
+        const size_t need = (size_t)msplit * (Ktot + 1) * p.cout;
+        float* part = (p.partials && p.partial_floats >= need) ? p.partials : nullptr;
+        if (part && !p.db) PV_CUDA(cudaMemsetAsync(part, 0, need * sizeof(float), st));       // bias rows are only written when db is set
+        if (BN == 64) wgrad_vec_kernel<64><<<grid, 256, 0, st>>>(p, (int)per, part);
+        else wgrad_vec_kernel<32><<<grid, 256, 0, st>>>(p, (int)per, part);
+        PV_LAUNCH_CHECK();
+        if (part) wgrad_sum_kernel<<<cdiv((long long)(Ktot + 1) * p.cout, 256), 256, 0, st>>>(part, msplit, Ktot, p.cout, p.dw, p.db);
     } else {
         const int nb = cdiv((long long)(Ktot + 1) * p.cout, 256);
         int msplit = 148 * 8 / nb; if (msplit < 1) msplit = 1;
         if (msplit > M) msplit = (int)M;
         const long long per = (M + msplit - 1) / msplit;
-        dim3 grid(nb, cdiv(M, per));
-        wgrad_direct_kernel<<<grid, 256, 0, st>>>(p, (int)per);
+        const int nsplit = cdiv(M, per);
+        dim3 grid(nb, nsplit);
+        const size_t need = (size_t)nsplit * (Ktot + 1) * p.cout;
+        float* part = (p.partials && p.partial_floats >= need) ? p.partials : nullptr;
+        if (part && !p.db) PV_CUDA(cudaMemsetAsync(part, 0, need * sizeof(float), st));
+        wgrad_direct_kernel<<<grid, 256, 0, st>>>(p, (int)per, part);
+        PV_LAUNCH_CHECK();
+        if (part) wgrad_sum_kernel<<<cdiv((long long)(Ktot + 1) * p.cout, 256), 256, 0, st>>>(part, nsplit, Ktot, p.cout, p.dw, p.db);
     }
     PV_LAUNCH_CHECK();
     return 0;

@@ -255,6 +255,7 @@ int conv_wgrad(pv_trainer* t, int li, const float* in, const float* gout, const 
     p.cin = L.cin_s; p.cout = L.cout_s; p.kh = L.k[0]; p.kw = L.k[1]; p.kt = L.k[2];
     p.ph = L.pad[0]; p.pw = L.pad[1]; p.pt = L.pad[2];
     p.cin_r = L.cin; p.cout_r = L.cout; p.tag = nullptr;
+    p.partials = t->dense_partials; p.partial_floats = t->dense_partials ? WGRAD_PARTIAL_FLOATS : 0;   // fixed-order split reduction
     return launch_wgrad(p, st);
 }
 
@@ -834,6 +835,12 @@ int pv_trainer_create(pv_model* m, int opt_kind, float learning_rate, int loss_k
         pv_trainer_destroy(t);
         return set_error(PV_ERR_CUDA, "cudaMalloc of the trainer arenas failed");
     }
+    // split-reduction scratch of the CUDA-core weight-gradient kernels (the dense engine, and the 2-D skip path's fallback): makes the
+    // exact engines bit-reproducible
+    if (cudaMalloc(&t->dense_partials, WGRAD_PARTIAL_FLOATS * sizeof(float)) != cudaSuccess) {
+        pv_trainer_destroy(t);
+        return set_error(PV_ERR_CUDA, "cudaMalloc of the weight-gradient split scratch failed");
+    }
     if (m->rows) {
         t->wg_partial_floats = (size_t)148 * (9 * 4096 + 1024);
         // deferred reductions: one private region per conv3 layer (R norm convs + reducers + upscale), per fused block,
@@ -866,7 +873,7 @@ void pv_trainer_destroy(pv_trainer* t) {
     cudaSetDevice(t->m->device);
     cudaFree(t->grads); cudaFree(t->dweff); cudaFree(t->dbias_s); cudaFree(t->m1); cudaFree(t->m2);
     cudaFree(t->sr); cudaFree(t->dsr); cudaFree(t->loss_ps); cudaFree(t->cpsnr_ps); cudaFree(t->best); cudaFree(t->cnt);
-    cudaFree(t->out2); cudaFree(t->s_lr); cudaFree(t->s_hr); cudaFree(t->s_mask); cudaFree(t->wg_partials);
+    cudaFree(t->out2); cudaFree(t->s_lr); cudaFree(t->s_hr); cudaFree(t->s_mask); cudaFree(t->wg_partials); cudaFree(t->dense_partials);
     delete t;
 }
 

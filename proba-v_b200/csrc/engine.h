@@ -167,6 +167,7 @@ struct pv_trainer {
     float *s_lr = nullptr, *s_hr = nullptr;
     uint8_t* s_mask = nullptr;
     int s_cap = 0;
+    float* dense_partials = nullptr;   // split scratch of the CUDA-core wgrad kernels (kernels.h WGRAD_PARTIAL_FLOATS): fixed-order reduction
     float* wg_partials = nullptr;      // per-CTA partial weight gradients of the tensor-core wgrad kernels: the first
     size_t wg_partial_floats = 0;      // wg_partial_floats are the immediate-mode scratch, the rest of the arena is carved per layer
     pv::ReduceQueue rq;                // by the deferred reduction queue (one reduction launch per backward pass)

@@ -880,9 +880,10 @@ static int tc_forward_x3(pv_model* m, int B, float* sr, bool tr, int clip_round,
             in_hi = P[tail[k - 1].out]; in_pack = P[tail[k - 1].out + "_pack"];
         }
         const Layer& L = m->layers[m->li("convReducer_" + std::to_string(k + 1))];
-        // a reducer's output feeds the next conv directly (packed rows) or through a reflect-pad copy (hi + lo): write both
-        PV_TRY(conv_rows_x3(m, L, valid, in_hi, in_pack, ts.ig, P[ts.out], P[ts.out + "_lo"], P[ts.out + "_pack"], ts.og, nullptr, nullptr, yp, B,
-                            "reducer_fwd_x3", st));
+        // a reducer's output feeds the next conv directly (packed rows) or through a reflect-pad copy (which needs the fp32 lo half)
+        const bool next_copies = k + 1 < tail.size() && tail[k + 1].copy;
+        PV_TRY(conv_rows_x3(m, L, valid, in_hi, in_pack, ts.ig, P[ts.out], next_copies ? P[ts.out + "_lo"] : nullptr, P[ts.out + "_pack"], ts.og, nullptr,
+                            nullptr, yp, B, "reducer_fwd_x3", st));
     }
     PV_TRY(conv_rows_x3(m, m->layers[m->li("upscaleConv1")], valid, P[tail.back().out], P[tail.back().out + "_pack"], tail.back().og, P["U"], nullptr, nullptr,
                         ug, nullptr, nullptr, yp, B, "upscale_fwd_x3", st));

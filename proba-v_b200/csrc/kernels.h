@@ -34,7 +34,13 @@ struct WgradP {
     int cin, cout, kh, kw, kt, ph, pw, pt;
     int cin_r, cout_r;
     const char* tag;
+    // Deterministic mode: the row range is split over CTAs; each split stores its partial sums into
+    // partials[split][(k | bias row)][n] and a second kernel adds the splits in a FIXED order, so the exact (fp32) engine is
+    // bit-reproducible (round 1 accumulated the splits with atomicAdd).  nullptr / too small: the atomic path.
+    float* partials = nullptr;
+    size_t partial_floats = 0;
 };
+constexpr size_t WGRAD_PARTIAL_FLOATS = (size_t)148 * 4 * 64 * 64 + (size_t)148 * 8 * 256 + 4096;   // covers every split geometry of launch_wgrad
 
 int launch_conv(const ConvP& p, cudaStream_t st);
 int launch_wgrad(const WgradP& p, cudaStream_t st);

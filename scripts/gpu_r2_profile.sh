@@ -22,6 +22,9 @@ PY
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $((2 * L)) -c $L --csv --log-file gpurun_out/launches_r02_${PREC}.csv \
       python scripts/profile_fwd.py $PREC 3 > gpurun_out/ncu_ll_${PREC}.log 2>&1; echo "launch list rc=$?"
 done
-# --set full of the dominant kernel classes (second step)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rowconv3_tc|resfront_fwd_x3|resfront_bwd_weight|resfront_pipe" -s 60 -c 14 -f -o gpurun_out/prof_r02_x3_hot \
-    python scripts/profile_fwd.py tf32x3 2 > gpurun_out/ncu_full_x3.log 2>&1; echo "full x3 rc=$?"; tail -2 gpurun_out/ncu_full_x3.log
+# --set full of the dominant kernel classes of the tf32x3 step: the compensated conv's two passes (4 launches = blocks 5, 6 of the second step),
+# then one launch each of the fused forward, the fused weight-gradient and the split-weight backward-data kernels
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:rowconv3_tc -s 90 -c 4 -f -o gpurun_out/prof_r02_x3_conv3 \
+    python scripts/profile_fwd.py tf32x3 2 > gpurun_out/ncu_full_x3a.log 2>&1; echo "full conv3 rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"resfront" -s 40 -c 3 -f -o gpurun_out/prof_r02_x3_resfront \
+    python scripts/profile_fwd.py tf32x3 2 > gpurun_out/ncu_full_x3b.log 2>&1; echo "full resfront rc=$?"

@@ -292,7 +292,7 @@ def test_pytorch_twin_matches_the_trainer_and_steps_with_torch_optim(small_cfg):
     d = tempfile.mkdtemp(prefix="pv_")
     t = pb.ModelTrainer(m2, L.shiftCompensatedL1Loss, L.shiftCompensatedcPSNR, pb.Nadam(5e-4), d + "/ckpt", d + "/log")
     lossv, _ = t.forward_backward(lr, hr, mask)
-    assert abs(float(loss) - lossv) <= 1e-6 * abs(lossv)
+    assert abs(float(loss.detach()) - lossv) <= 1e-6 * abs(lossv)
     assert torch.equal(net.theta.grad, t.grad_view())                                  # same kernels, fixed-order reductions: bit-identical
     # a torch optimizer updates the engine's arena in place, and the next forward sees it
     opt = torch.optim.SGD(net.parameters(), lr=1e-4)
