@@ -361,8 +361,9 @@ def run_b200(args, cfg):
     notes = {
         "resfront_bwd_weight": "fused expand/decay weight gradients: E^T and gE^T recomputed transposed in TMEM (not counted as algorithmic "
                                "flops), TS-mode N=32 MMAs at 39 cycles each; MMA-issue floor 82 us per launch, see DESIGN.md section 4",
-        "norm_fwd_x3": "error-compensated conv3 forward: three passes (x_lo w_hi, x_hi w_lo, x_hi w_hi) of 36 M128xN96xK8 MMAs per 126 rows, "
-                       "i.e. 3x the algorithmic MMAs by construction (the price of the 1e-3 gradient bar)",
+        "norm_fwd_x3": "error-compensated conv3 forward: pass C = both correction products (x_lo w_hi + x_hi w_lo) as ONE kind::f16 chain over packed "
+                       "fp16 pair rows (K = 64 per tap), pass M = x_hi w_hi in tf32; 36 M128xN96 MMAs per 126 rows each, i.e. 3x the algorithmic "
+                       "MACs by construction (the price of the 1e-3 gradient bar); executed flops count pass C's fp16 MACs too",
         "resfront_fwd_x3": "error-compensated fused expand/ReLU/decay forward: three MMAs per product, expanded tensor as hi | lo in TMEM",
         "norm_wgrad": "conv3 weight gradient as M128xN96xK8 MMAs (80 cycles each, 75 % of the M slots useful): floor 64 us per launch",
         "norm_fwd": "conv3 forward as 36 M128xN96xK8 MMAs per 126 rows: floor 47 us per launch",
