@@ -399,7 +399,9 @@ static int trainer_fwd_loss(pv_trainer* t, const float* lr, const float* hr, con
     if (!lr || !hr || !mask || !out_dev || B <= 0) return set_error(PV_ERR_BAD_ARG, "step: null buffer or B=%d", B);
     pv_model* m = t->m;
     PV_TRY(trainer_ensure(t, B));
-    PV_TRY(model_forward(m, lr, B, t->sr, true, 0, st));
+    // the training pool (which keeps every activation for the backward pass) only when gradients follow: evaluation runs on the
+    // inference pool's ping-pong buffers (a validation batch must not grow the training pool)
+    PV_TRY(model_forward(m, lr, B, t->sr, backward, 0, st));
     const int HW = m->P * m->cfg.scale;
     PV_TRY(shift_loss_device(t->loss_kind, hr, mask, t->sr, B, HW, HW, 3, grad_scale, t->loss_ps, t->best, t->cnt,
                              t->cpsnr_ps, out_dev, backward ? t->dsr : nullptr, nullptr, st));

@@ -22,6 +22,24 @@ logging.basicConfig(format="%(asctime)s - %(message)s", level=logging.INFO)
 logger = logging.getLogger("probav_b200")
 
 
+class _nvtx:
+    """NVTX range around a step when PV_NVTX=1 (torch.cuda.nvtx; a no-op otherwise)."""
+    _on = os.environ.get("PV_NVTX", "0") == "1"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if self._on:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if self._on:
+            import torch
+            torch.cuda.nvtx.range_pop()
+
+
 class Mean:
     """tf.keras.metrics.Mean: running mean, count-weighted by update calls (trainClass.py:43-46)."""
 
@@ -198,10 +216,11 @@ class ModelTrainer:
         sync=False (device tensors only) skips the per-step host read the reference's logging forces and returns the
         device tensor [loss, cPSNR] of this rank's shard instead."""
         rank, ws = parallel.world()
-        if ws == 1:
-            out = self._run(lib().pv_train_step_host, lib().pv_train_step, patchLR, patchHR, maskHR)
-        else:
-            out = self._dp_step(patchLR, patchHR, maskHR, global_batch)
+        with _nvtx("pv.trainStep"):       # PV_NVTX=1: NVTX ranges for Nsight timelines (SURVEY section 5, tracing)
+            if ws == 1:
+                out = self._run(lib().pv_train_step_host, lib().pv_train_step, patchLR, patchHR, maskHR)
+            else:
+                out = self._dp_step(patchLR, patchHR, maskHR, global_batch)
         if not sync and _buf.is_cuda_tensor(out):
             return out
         lossv, psnrv = float(out[0]), float(out[1])
@@ -251,7 +270,8 @@ class ModelTrainer:
 
     def testStep(self, patchLR, patchHR, maskHR):
         """trainClass.py:137-143."""
-        out = self._run(lib().pv_eval_step_host, lib().pv_eval_step, patchLR, patchHR, maskHR)
+        with _nvtx("pv.testStep"):
+            out = self._run(lib().pv_eval_step_host, lib().pv_eval_step, patchLR, patchHR, maskHR)
         lossv, psnrv = float(out[0]), float(out[1])
         self.testLoss(lossv)
         self.testPSNR(psnrv)
@@ -372,7 +392,21 @@ class ModelTrainer:
                     if k >= valSteps:
                         break
                     vsel = np.sort(vidx)
-                    self.testStep(Xv[vsel], yv[vsel], mv[vsel])
+                    if ws == 1:
+                        self.testStep(Xv[vsel], yv[vsel], mv[vsel])
+                    else:
+                        # data parallel: every rank scores its shard of the validation batch and the sums are all-reduced (each rank
+                        # used to evaluate the whole global batch: world-size times the work and the activation memory)
+                        lo, hi = parallel.shard_bounds(len(vsel), rank, ws)
+                        sub = vsel[lo:hi]
+                        lv = pv_ = 0.0
+                        if len(sub):
+                            o = self._run(lib().pv_eval_step_host, lib().pv_eval_step, Xv[sub], yv[sub], mv[sub])
+                            lv, pv_ = float(o[0]), float(o[1])
+                        import torch
+                        gl, gp = parallel.reduce_metrics(lv, pv_, len(sub), device=torch.device(f"cuda:{self._model.device}"))
+                        self.testLoss(gl)
+                        self.testPSNR(gp)
                 self._scalar("Test loss", self.testLoss.result(), globalStep)
                 self._scalar("Test PSNR", self.testPSNR.result(), globalStep)
                 if rank == 0:
