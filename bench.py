@@ -2,13 +2,16 @@
 """bench.py -- headline benchmark of the PROBA-V 3D-WDSR hot path on B200 (BASELINE.json: train patches/s,
 fwd+bwd+shift-L1(+Nadam, +cPSNR metric) on cfg/p16t9c85r12, batch 128 per GPU, synthetic PROBA-V-shaped data).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision tf32x3|tf32|fp32] [--scaling weak|strong]
 
 One "step" = ModelTrainer.trainStep (reference models/trainClass.py:124-135) on one batch.  Prints ONE JSON line
 (rank 0).  `value` = whole-job patches/s with the batch resident in HBM; `e2e` = the same through the public API
-with pinned HOST buffers (H2D of the batch + D2H of loss/cPSNR inside the timed region).  `roofline` describes the
-dominant kernel class, timed live with CUDA events through pv_timing_*; `cpu_baseline` is the oracle (a PyTorch-CPU
-restatement of the TF reference, which cannot be installed here) timed on this box's host cores.
+with pinned HOST buffers (H2D of the batch + D2H of loss/cPSNR inside the timed region).  The headline precision is `tf32x3`, the
+error-compensated tensor-core engine whose gradients meet the 1e-3 bar at batch 128; the faster single-pass tf32 engine is measured in
+the same run and reported beside it (`single_pass_tf32`).  `roofline` describes the dominant kernel class, timed live with CUDA
+events through pv_timing_*, with algorithmic AND executed flops and a tf32 peak measured on the spot; `scene_infer` is BASELINE
+configs[3] including the shift-cPSNR scoring; `cpu_baseline` is the oracle (a PyTorch-CPU restatement of the TF reference, which
+cannot be installed here) timed on this box's host cores on full 128-patch steps.
 Weak scaling for N > 1 (default): per-rank batch fixed, the flat gradient arena all-reduced over NCCL in two buckets overlapped with
 the backward pass; `--scaling strong` keeps the GLOBAL batch at the cfg's batch_size instead.
 """
