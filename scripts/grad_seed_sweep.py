@@ -1,0 +1,40 @@
+"""Is the batch-128 gradient parity of the tensor-core engines a property of ONE fixture?  For several (weight seed, data seed) pairs:
+fp64-oracle gradients of a full cfg/p16t9c85r12 batch (CPU, chunked as in tests/golden/make_grad_b128_golden.py) against the engines'
+(per tensor max |error| / max |gradient|; worst and median over the 132 tensors).  python scripts/grad_seed_sweep.py [seed pairs ...]"""
+import os, sys, tempfile, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import probav_b200 as pb
+from probav_b200 import synth
+from oracle.losses import OracleLosses
+from oracle.step import loss_and_grads
+from oracle.wdsr import OracleWDSR, init_params
+
+FULL = dict(scale=3, numFilters=32, kernelSize=(3, 3, 3), numResBlocks=12, expRate=8, decayRate=0.8, numImgLR=9, patchSizeLR=16, isGrayScale=True)
+NIR = (8075.2045, 3160.7272)
+pairs = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]] or [(200, 201), (300, 301), (400, 401)]
+torch.set_num_threads(os.cpu_count() or 1)
+om = OracleWDSR(NIR[0], NIR[1], 6, **FULL)
+ol = OracleLosses((48, 48, 1))
+for sw, sd in pairs:
+    p = init_params(om.specs, seed=sw, dtype=torch.float64)
+    lr, hr, mask = synth.make_batch(128, seed=sd, hr_zero_under_mask=False)
+    t0 = time.time()
+    ref, loss = None, 0.0
+    for s in range(0, 128, 16):
+        sl = slice(s, s + 16)
+        l, g, _, _ = loss_and_grads(om, ol, p, torch.from_numpy(lr[sl]).double(), torch.from_numpy(hr[sl]).double(), torch.from_numpy(mask[sl]))
+        loss += float(l) / 8
+        ref = {k: v / 8 for k, v in g.items()} if ref is None else {k: ref[k] + g[k] / 8 for k in ref}
+    line = f"seeds ({sw}, {sd}): oracle loss {loss:.4f} [{time.time() - t0:.0f} s CPU]"
+    for prec in ("tf32x3", "tf32"):
+        m = pb.WDSRConv3D("n", "NIR", NIR[0], NIR[1], 6).build(**FULL, precision=prec)
+        m.set_weights({k: v.numpy().astype(np.float32) for k, v in p.items()})
+        L = pb.Losses((48, 48, 1)); d = tempfile.mkdtemp()
+        t = pb.ModelTrainer(m, L.shiftCompensatedL1Loss, L.shiftCompensatedcPSNR, pb.Nadam(5e-4), d + "/c", d + "/l")
+        lossv, _ = t.forward_backward(lr, hr, mask)
+        got = t.get_grads()
+        errs = sorted(float(np.abs(got[k] - v.numpy()).max() / np.abs(v.numpy()).max()) for k, v in ref.items() if np.abs(v.numpy()).max() > 0)
+        line += f" | {prec}: loss rel {abs(lossv - loss) / loss:.1e}, gradients worst {errs[-1]:.2e} median {errs[len(errs) // 2]:.2e} over 1e-3: {sum(e > 1e-3 for e in errs)}/{len(errs)}"
+        t.close(); m.close()
+    print(line, flush=True)
