@@ -85,8 +85,13 @@ __device__ __forceinline__ TileInfo tile_info(const Conv3Args& a, int tile, int 
     return ti;
 }
 
-// F16: the operands are packed fp16 pair rows (rows.h): kind::f16 MMAs, K = 16 per step over the same 128-byte rows, and the
-// accumulator is PACK_SCALE times the two correction products of a compensated convolution (scaled back in the epilogue).
+// F16 (the error-compensated convolution in ONE launch): the operands are packed fp16 pair rows (rows.h), activations
+// [hi | 2^12 lo], weights [2^12 w_lo | w_hi].  Per tap the MMA thread issues kind::f16 MMAs (K = 16 per step over the same 128-byte rows)
+// into TWO accumulators: the MAIN product x_hi w_hi = the first half of the activation row against the second half of the weight row
+// (2 steps), and both CORRECTIONS x_hi w_lo + x_lo w_hi = the whole rows against each other (4 steps, 2^12-scaled).  hi = tf32(v) has 11
+// significant bits and is exact in fp16, so the main product loses nothing against kind::tf32 while taking half the accumulation steps
+// (tcgen05 truncates the accumulator once per step), and the corrections never touch the full-size sum.  The epilogue adds
+// main + 2^-12 corrections (+ bias + skip connection) in fp32, round to nearest.
 template <bool F16>
 __global__ void __launch_bounds__(C3_THREADS, 1)
 rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const Conv3Args a) {
@@ -111,7 +116,8 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         fence_mbar_init();
     }
     if (threadIdx.x < 32) s_bias[threadIdx.x] = a.bias ? a.bias[threadIdx.x] : 0.f;
-    if (warp == 1) tmem_alloc<256>(smem_u32(&tmem_slot));
+    constexpr uint32_t ACC_COLS = F16 ? 192u : 96u;               // F16: main accumulator | correction accumulator
+    if (warp == 1) tmem_alloc<(F16 ? 512 : 256)>(smem_u32(&tmem_slot));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -169,7 +175,7 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 if (tile + 1 == t_hi) nnext = 3;
                 mbar_wait(BAR(TEMPTY + acc), aph ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem + acc * 96;
+                const uint32_t d_tmem = tmem + acc * ACC_COLS;
 #pragma unroll
                 for (int s = 0; s < 3; ++s) {
                     const uint32_t stg = s == 0 ? s0 : (s == 1 ? s1 : s2);
@@ -179,9 +185,15 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
 #pragma unroll
                     for (int dh = 0; dh < 3; ++dh) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            if (F16) umma_ss_f16_lohi(d_tmem, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
-                            else umma_ss_tf32_lohi(d_tmem, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
+                        for (int ks = 0; ks < 4; ++ks) {
+                            if (F16) {
+                                // corrections: whole rows; main: activation K-steps 0, 1 (hi) against weight K-steps 2, 3 (w_hi)
+                                umma_ss_f16_lohi(d_tmem + 96, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
+                                if (ks < 2) umma_ss_f16_lohi(d_tmem, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 4 + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
+                            } else {
+                                umma_ss_tf32_lohi(d_tmem, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
+                            }
+                        }
                     }
                     // release the slabs the next tile does not inherit: as many (oldest first) as it loads itself
                     if (s < (int)nnext) umma_commit(BAR(EMPTY + stg));
@@ -229,10 +241,26 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             mbar_wait(BAR(TFULL + acc), aph);
             tc_fence_after();
             uint32_t v0[32], v1[32], v2[32];
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * 96;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
             tmem_ld32(taddr, v0);
             tmem_ld32(taddr + 32, v1);
             tmem_ld32(taddr + 64, v2);
+            if (F16) {                                                    // + 2^-12 x the correction accumulator, one third at a time
+                constexpr float CS = 1.0f / PACK_SCALE;
+                uint32_t vc[32];
+                tmem_ld32(taddr + 96, vc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v0[c] = __float_as_uint(fmaf(__uint_as_float(vc[c]), CS, __uint_as_float(v0[c])));
+                tmem_ld32(taddr + 128, vc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v1[c] = __float_as_uint(fmaf(__uint_as_float(vc[c]), CS, __uint_as_float(v1[c])));
+                tmem_ld32(taddr + 160, vc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v2[c] = __float_as_uint(fmaf(__uint_as_float(vc[c]), CS, __uint_as_float(v2[c])));
+            }
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
@@ -257,7 +285,7 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                 const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c]), 1);
                 o[c] = __uint_as_float(v1[c]) + (lane > 0 ? left : 0.f) + (lane < 31 ? right : 0.f);
             }
-            constexpr float ACC_SCALE = F16 ? 1.0f / PACK_SCALE : 1.0f;
+
             if (lane == 0 && q > 0) {
 #pragma unroll
                 for (int g4 = 0; g4 < 8; ++g4) {
@@ -280,8 +308,7 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             for (int g4 = 0; g4 < 8; ++g4) {
                 float* e = o + 4 * g4;
                 const float4 bq = reinterpret_cast<const float4*>(s_bias)[g4];
-                if (F16) { e[0] = fmaf(e[0], ACC_SCALE, bq.x); e[1] = fmaf(e[1], ACC_SCALE, bq.y); e[2] = fmaf(e[2], ACC_SCALE, bq.z); e[3] = fmaf(e[3], ACC_SCALE, bq.w); }
-                else { e[0] += bq.x; e[1] += bq.y; e[2] += bq.z; e[3] += bq.w; }
+                e[0] += bq.x; e[1] += bq.y; e[2] += bq.z; e[3] += bq.w;
                 if (a.residual) { e[0] += pre[g4].x; e[1] += pre[g4].y; e[2] += pre[g4].z; e[3] += pre[g4].w; }
                 if (a.relu) {
 #pragma unroll
@@ -308,8 +335,10 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     float pk[32];
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
+                        // the packed hi half is fp16(hi); where that differs from hi (|v| below fp16's normal range) the difference moves into lo
                         const __half2 h = __floats2half2_rn(o[2 * c], o[2 * c + 1]);
-                        const __half2 l = __floats2half2_rn(lo[2 * c] * PACK_SCALE, lo[2 * c + 1] * PACK_SCALE);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn((lo[2 * c] + (o[2 * c] - hf.x)) * PACK_SCALE, (lo[2 * c + 1] + (o[2 * c + 1] - hf.y)) * PACK_SCALE);
                         pk[c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
                         pk[16 + c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l));
                     }
@@ -322,7 +351,7 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc<256>(tmem);
+    if (warp == 1) tmem_dealloc<(F16 ? 512 : 256)>(tmem);
 }
 
 }  // namespace
@@ -375,8 +404,8 @@ int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = a.B * a.chunks * a.nt;
     const int grid = ntiles < sms ? ntiles : sms;
-    // executed flops: a packed fp16 pass runs K = 64 per tap (both correction products) in the same number of MMAs
-    PV_TIMED(p.tag ? p.tag : "rowconv3_tc", st, p.flops, 0.0, (p.f16_pack ? 2.0 : 1.0) * 2.0 * (double)ntiles * 128.0 * 96.0 * 288.0);
+    // executed flops: the compensated launch runs the main product (K = 32 per tap) and both corrections (K = 64 per tap)
+    PV_TIMED(p.tag ? p.tag : "rowconv3_tc", st, p.flops, 0.0, (p.f16_pack ? 3.0 : 1.0) * 2.0 * (double)ntiles * 128.0 * 96.0 * 288.0);
     static size_t attr[16] = {}, attr_h[16] = {};
     if (p.f16_pack) {
         PV_CUDA(ensure_dyn_smem(rowconv3_tc_kernel<true>, smem, attr_h));

@@ -153,15 +153,13 @@ int dgrad_rows(pv_model* m, const Layer& L, const Taps& tp /* negated offsets */
     return m->use_tc ? launch_rowconv_tc(p, st) : launch_rowconv_simt(p, st);
 }
 
-// Error-compensated forward convolution (precision 4), x w ~= x_hi w_hi + (x_lo w_hi + x_hi w_lo), in TWO passes of the conv3 kernel chained
-// through the fp32 partial buffer `yp` (same geometry as the output):
-//   pass C (kind::f16, K = 64 per tap over packed fp16 pair rows, rows.h):  yp = x_lo w_hi + x_hi w_lo + bias (+ res_hi + res_lo)
-//   pass M (kind::tf32):                                                   v  = act(x_hi w_hi + yp)  ->  y_hi = tf32(v), y_lo = v - y_hi, y_pack
-// Both correction products ride in ONE launch because a packed row holds [hi | scaled lo] for the activations and [scaled lo | hi] for the
-// weights (round 2's first version ran them as two tf32 passes: two 108 KB weight sets do not fit in shared memory at once).
+// Error-compensated forward convolution (precision 4), x w ~= x_hi w_hi + (x_lo w_hi + x_hi w_lo), in ONE launch of the conv3 kernel over
+// packed fp16 pair rows (rows.h): the main product and the two corrections accumulate in separate TMEM accumulators (conv3_tc.cu, F16),
+//   v = act(x_hi w_hi + 2^-12 (2^12 x_lo w_hi + x_hi 2^12 w_lo) + bias (+ res_hi + res_lo))  ->  y_hi = tf32(v), y_lo = v - y_hi, y_pack.
+// (Round 2's earlier versions: three tf32 passes, then a packed correction pass + a tf32 main pass chained through an fp32 partial buffer.)
 // y_lo / y_pack nullable; y_lo == y_pack == nullptr stores v itself (un-rounded fp32: the upscale conv, whose output feeds the CUDA-core tail).
-int conv_rows_x3(pv_model* m, const Layer& L, const Taps& tp, const float* x_hi, const float* x_pack, const RowGeom& ig, float* y_hi, float* y_lo,
-                 float* y_pack, const RowGeom& og, const float* res_hi, const float* res_lo, float* yp, int B, const char* tag, cudaStream_t st) {
+int conv_rows_x3(pv_model* m, const Layer& L, const Taps& tp, const float* x_pack, const RowGeom& ig, float* y_hi, float* y_lo,
+                 float* y_pack, const RowGeom& og, const float* res_hi, const float* res_lo, int B, const char* tag, cudaStream_t st) {
     RowConvP p;
     memset(&p, 0, sizeof p);
     p.xc = 32; p.n = L.cout_s; p.B = B;
@@ -170,14 +168,9 @@ int conv_rows_x3(pv_model* m, const Layer& L, const Taps& tp, const float* x_hi,
     const int Kflat = L.taps() * L.cin_s;
     for (int i = 0; i < tp.n; ++i) { p.off[i] = tp.off[i]; p.c0[i] = tp.c0[i]; p.wr0[i] = 0; p.wc0[i] = 32 * tp.chunk[i]; }
     p.w_rows = L.cout_s; p.w_cols = Kflat; p.w_kmajor = 1;
-    p.flops = 0.0;                       // the algorithmic flops are booked once, on the main pass
     p.tag = tag;
-    // pass C: both correction products + bias (+ skip connection)
-    p.x = x_pack; p.w = m->weffT_pack + L.weff_off; p.f16_pack = 1; p.y = yp; p.bias = m->bias_s + L.bias_s_off;
+    p.x = x_pack; p.w = m->weffT_pack + L.weff_off; p.f16_pack = 1; p.bias = m->bias_s + L.bias_s_off;
     p.residual = res_hi; p.residual2 = res_hi ? res_lo : nullptr;
-    PV_TRY(launch_rowconv_tc(p, st));
-    // pass M: + x_hi * w_hi, activation, split
-    p.x = x_hi; p.w = m->weffT + L.weff_off; p.f16_pack = 0; p.bias = nullptr; p.residual = yp; p.residual2 = nullptr;
     p.relu = L.relu; p.y = y_hi; p.y_lo = y_lo; p.y_pack = y_pack;
     p.flops = 2.0 * B * L.Ho * L.Wo * L.To * L.taps() * L.cin * L.cout;
     return launch_rowconv_tc(p, st);
@@ -460,7 +453,8 @@ struct SplitBuf {
             std::vector<__half> pk(2 * n);
             for (size_t r = 0; r < n / 32; ++r)
                 for (int c = 0; c < 32; ++c) {
-                    const __half hh = __float2half_rn(a[r * 32 + c]), ll = __float2half_rn(b[r * 32 + c] * PACK_SCALE);
+                    const __half hh = __float2half_rn(a[r * 32 + c]);                  // lo' = v - fp16(hi): hi16 + lo' = v exactly
+                    const __half ll = __float2half_rn((h[r * 32 + c] - __half2float(hh)) * PACK_SCALE);
                     pk[r * 64 + (pack_mode == 1 ? c : 32 + c)] = hh;
                     pk[r * 64 + (pack_mode == 1 ? 32 + c : c)] = ll;
                 }
@@ -520,10 +514,10 @@ static int selftest_x3(std::string& rep) {
         for (int co = 0; co < 32; ++co) for (int k = 0; k < 864; ++k) wt[(size_t)k * 32 + co] = wk[(size_t)co * 864 + k];
         for (auto& v : bb) v = rnd(0.5f);
         PV_TRY(W3.upload(wk, 2));
-        float *wt_d, *b_d, *y0, *yh, *yl, *yp;
+        float *wt_d, *b_d, *y0, *yh, *yl;
         PV_CUDA(cudaMalloc(&wt_d, wt.size() * 4)); PV_CUDA(cudaMalloc(&b_d, 128));
         PV_CUDA(cudaMemcpy(wt_d, wt.data(), wt.size() * 4, cudaMemcpyHostToDevice)); PV_CUDA(cudaMemcpy(b_d, bb.data(), 128, cudaMemcpyHostToDevice));
-        for (float** p : {&y0, &yh, &yl, &yp}) { PV_CUDA(cudaMalloc(p, rows * 128)); PV_CUDA(cudaMemset(*p, 0, rows * 128)); }
+        for (float** p : {&y0, &yh, &yl}) { PV_CUDA(cudaMalloc(p, rows * 128)); PV_CUDA(cudaMemset(*p, 0, rows * 128)); }
         const Taps tp = conv3_taps(pr.plane, pr.pw, true, +1);
         RowConvP q;
         memset(&q, 0, sizeof q);
@@ -538,7 +532,7 @@ static int selftest_x3(std::string& rep) {
         L.Ho = L.Wo = 22; L.To = 9;
         float* ypk;
         PV_CUDA(cudaMalloc(&ypk, rows * 128)); PV_CUDA(cudaMemset(ypk, 0, rows * 128));
-        if (!rc) rc = conv_rows_x3(&fm, L, tp, X.hi, X.pack, pr, yh, yl, ypk, pr, RES.hi, RES.lo, yp, B, "selftest_x3", 0);
+        if (!rc) rc = conv_rows_x3(&fm, L, tp, X.pack, pr, yh, yl, ypk, pr, RES.hi, RES.lo, B, "selftest_x3", 0);
         if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest x3 conv: %s", cudaGetErrorString(cudaGetLastError()));
         if (rc) { rep += std::string("x3 conv3 same fwd                  FAIL : ") + last_error() + "\n"; ++fails; }
         else {
@@ -552,15 +546,16 @@ static int selftest_x3(std::string& rep) {
             for (size_t r = 0; r < rows; ++r)
                 for (int c = 0; c < 32; ++c) {
                     const float dh = __half2float(pk[r * 64 + c]), dl = __half2float(pk[r * 64 + 32 + c]) / PACK_SCALE;
-                    // (values below fp16's normal range, 6e-5, keep fewer bits: absolute floors)
-                    if (std::fabs(dh - hh[r * 32 + c]) > 6e-8f || std::fabs(dl - ll[r * 32 + c]) > 1e-3f * std::fabs(ll[r * 32 + c]) + 2e-11f) ++bad;
+                    // hi16 + lo' = hi + lo to fp16's 11 bits of the lo half (values below fp16's normal range, 6e-5, keep fewer bits: absolute floors)
+                    const float v = hh[r * 32 + c] + ll[r * 32 + c], lo2 = v - dh;
+                    if (std::fabs(dh - hh[r * 32 + c]) > 6e-8f || std::fabs(dl - lo2) > 1e-3f * std::fabs(lo2) + 2e-11f) ++bad;
                 }
             char line[256];
             snprintf(line, sizeof line, "%-34s %s %zu mismatching elements of %zu\n", "x3 conv3: packed fp16 pair output", bad == 0 ? "PASS" : "FAIL", bad, rows * 32);
             rep += line;
             fails += bad == 0 ? 0 : 1;
         }
-        for (float* p : {wt_d, b_d, y0, yh, yl, yp, ypk}) cudaFree(p);
+        for (float* p : {wt_d, b_d, y0, yh, yl, ypk}) cudaFree(p);
     }
     // ---------------- fused expand -> ReLU -> decay forward
     {
@@ -599,7 +594,11 @@ static int selftest_x3(std::string& rep) {
                 std::vector<__half> pk(rows * 64);
                 std::vector<float> ll(rows * 32);
                 cudaMemcpy(pk.data(), dl, rows * 128, cudaMemcpyDeviceToHost);
-                for (size_t r = 0; r < rows; ++r) for (int c = 0; c < 32; ++c) ll[r * 32 + c] = __half2float(pk[r * 64 + 32 + c]) / PACK_SCALE;
+                std::vector<float> hv(rows * 32);
+                cudaMemcpy(hv.data(), dh, rows * 128, cudaMemcpyDeviceToHost);
+                for (size_t r = 0; r < rows; ++r)                                      // v = hi16 + lo'; the comparison wants v - hi
+                    for (int c = 0; c < 32; ++c)
+                        ll[r * 32 + c] = (__half2float(pk[r * 64 + c]) - hv[r * 32 + c]) + __half2float(pk[r * 64 + 32 + c]) / PACK_SCALE;
                 cudaMemcpy(dl, ll.data(), rows * 128, cudaMemcpyHostToDevice);
             }
             if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest x3 resfront: %s", cudaGetErrorString(cudaGetLastError()));
@@ -775,7 +774,7 @@ int tc_build_plan(pv_model* m) {
             P.add(ts.out, rows_per(ts.og, F), rows_extra(ts.og, F));
         }
         P.add("U", rows_per(ug, F), rows_extra(ug, F));
-        if (m->x3) {                    // remainders (v - tf32(v)) of the tensors a compensated forward product reads, + the partial-pass buffer
+        if (m->x3) {                    // remainders (v - tf32(v)) of the tensors a compensated forward product reads; Yp: the split-weight data gradient's partial pass
             size_t yp_per = rows_per(pr, F), yp_extra = rows_extra(pr, F);
             P.add("a_lo0", rows_per(pr, F), rows_extra(pr, F));
             P.add("a_lo1", rows_per(pr, F), rows_extra(pr, F));
@@ -848,7 +847,6 @@ static int tc_forward_x3(pv_model* m, int B, float* sr, bool tr, int clip_round,
     const Taps same = conv3_taps(pr.plane, pr.pw, true, +1);
     const std::vector<TailStep> tail = tail_plan(m);
     const RowGeom ug = g_dims(1, m->P, m->P);
-    float* const yp = P["Yp"];
     auto alo = [&](int i) { return P[(i & 1) ? "a_lo1" : "a_lo0"]; };
     const Layer& L0 = m->layers[m->li("mainConv1")];
     PV_TRY(launch_first_conv_pr(P["xn"], m->weff + L0.weff_off, m->bias_s + L0.bias_s_off, B, m->S, m->T, P[m->A(0, tr)], pr, st, alo(0)));
@@ -860,13 +858,13 @@ static int tc_forward_x3(pv_model* m, int B, float* sr, bool tr, int clip_round,
                                          m->weffT_lo + Ld.weff_off, m->bias_s + Le.bias_s_off, m->bias_s + Ld.bias_s_off, P[m->D(i, tr)], P["D_pack"],
                                          tr ? reinterpret_cast<uint32_t*>(P["M" + std::to_string(i)]) : nullptr,
                                          tr ? reinterpret_cast<uint32_t*>(P["MT" + std::to_string(i)]) : nullptr, pr, B, fl, st, 1));
-        PV_TRY(conv_rows_x3(m, m->layers[e + 2], same, P[m->D(i, tr)], P["D_pack"], pr, P[m->A(i + 1, tr)], alo(i + 1), nullptr, pr, P[m->A(i, tr)], alo(i),
-                            yp, B, "norm_fwd_x3", st));
+        PV_TRY(conv_rows_x3(m, m->layers[e + 2], same, P["D_pack"], pr, P[m->A(i + 1, tr)], alo(i + 1), nullptr, pr, P[m->A(i, tr)], alo(i), B,
+                            "norm_fwd_x3", st));
     }
     const Taps valid = conv3_taps(576, 24, false, +1);
     for (size_t k = 0; k < tail.size(); ++k) {
         const TailStep& ts = tail[k];
-        const float *in_hi, *in_pack;
+        const float* in_pack;
         if (k == 0 || ts.copy) {
             // re-layout (+ reflect pad) of the hi and lo halves, then the packed pair rows of the padded tensor (padding rows pack to zero)
             const float* src_hi = k == 0 ? P[m->A(m->R, tr)] : P[tail[k - 1].out];
@@ -875,18 +873,18 @@ static int tc_forward_x3(pv_model* m, int B, float* sr, bool tr, int clip_round,
             PV_TRY(launch_pr_to_g_reflect(src_hi, sg, P[ts.in], ts.ig, B, F, st, ts.pad));
             PV_TRY(launch_pr_to_g_reflect(src_lo, sg, P[ts.in + "_lo"], ts.ig, B, F, st, ts.pad));
             PV_TRY(launch_pack_rows(P[ts.in], P[ts.in + "_lo"], P[ts.in + "_pack"], ts.ig.lead + (long long)B * ts.ig.pstride + ROW_TAIL, st));
-            in_hi = P[ts.in]; in_pack = P[ts.in + "_pack"];
+            in_pack = P[ts.in + "_pack"];
         } else {
-            in_hi = P[tail[k - 1].out]; in_pack = P[tail[k - 1].out + "_pack"];
+            in_pack = P[tail[k - 1].out + "_pack"];
         }
         const Layer& L = m->layers[m->li("convReducer_" + std::to_string(k + 1))];
         // a reducer's output feeds the next conv directly (packed rows) or through a reflect-pad copy (which needs the fp32 lo half)
         const bool next_copies = k + 1 < tail.size() && tail[k + 1].copy;
-        PV_TRY(conv_rows_x3(m, L, valid, in_hi, in_pack, ts.ig, P[ts.out], next_copies ? P[ts.out + "_lo"] : nullptr, P[ts.out + "_pack"], ts.og, nullptr,
-                            nullptr, yp, B, "reducer_fwd_x3", st));
+        PV_TRY(conv_rows_x3(m, L, valid, in_pack, ts.ig, P[ts.out], next_copies ? P[ts.out + "_lo"] : nullptr, P[ts.out + "_pack"], ts.og, nullptr,
+                            nullptr, B, "reducer_fwd_x3", st));
     }
-    PV_TRY(conv_rows_x3(m, m->layers[m->li("upscaleConv1")], valid, P[tail.back().out], P[tail.back().out + "_pack"], tail.back().og, P["U"], nullptr, nullptr,
-                        ug, nullptr, nullptr, yp, B, "upscale_fwd_x3", st));
+    PV_TRY(conv_rows_x3(m, m->layers[m->li("upscaleConv1")], valid, P[tail.back().out + "_pack"], tail.back().og, P["U"], nullptr, nullptr, ug, nullptr,
+                        nullptr, B, "upscale_fwd_x3", st));
     return tc_forward_tail(m, B, sr, tr, clip_round, st);
 }
 

@@ -176,8 +176,9 @@ __global__ void __launch_bounds__(128) wn_prep_kernel(const WnLayer* __restrict_
                 // packed fp16 pair row of (co, tap): [ fp16(PACK_SCALE * w_lo) x 32 | fp16(w_hi) x 32 ] (rows.h) in the 128 bytes
                 // the 32 fp32 K-values of weffT occupy
                 __half* row = reinterpret_cast<__half*>(weffT_pack + L.weffT_off + (long long)co * (L.taps * L.cin_s) + (long long)rt * L.cin_s);
-                row[ci] = __float2half_rn((wf - w) * PACK_SCALE);
-                row[32 + ci] = __float2half_rn(w);
+                const __half w16 = __float2half_rn(w);                 // == w unless |w| is below fp16's normal range; the lo half absorbs that
+                row[ci] = __float2half_rn((wf - __half2float(w16)) * PACK_SCALE);
+                row[32 + ci] = w16;
             }
         }
     }

@@ -266,7 +266,8 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const __half2 h2 = __floats2half2_rn(hi[2 * c], hi[2 * c + 1]);
-                    const __half2 l2 = __floats2half2_rn(lo[2 * c] * PACK_SCALE, lo[2 * c + 1] * PACK_SCALE);
+                    const float2 hf = __half22float2(h2);                 // lo' = lo + (hi - fp16(hi)), rows.h
+                    const __half2 l2 = __floats2half2_rn((lo[2 * c] + (hi[2 * c] - hf.x)) * PACK_SCALE, (lo[2 * c + 1] + (hi[2 * c + 1] - hf.y)) * PACK_SCALE);
                     pk[c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h2));
                     pk[16 + c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l2));
                 }

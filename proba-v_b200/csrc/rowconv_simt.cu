@@ -495,7 +495,10 @@ __global__ void pack_rows_kernel(const float* __restrict__ hi, const float* __re
     const long long row = i >> 3; const int q = (int)(i & 7);
     const float4 h = __ldg(reinterpret_cast<const float4*>(hi) + i), l = __ldg(reinterpret_cast<const float4*>(lo) + i);
     const __half2 h0 = __floats2half2_rn(h.x, h.y), h1 = __floats2half2_rn(h.z, h.w);
-    const __half2 l0 = __floats2half2_rn(l.x * PACK_SCALE, l.y * PACK_SCALE), l1 = __floats2half2_rn(l.z * PACK_SCALE, l.w * PACK_SCALE);
+    // lo' = lo + (hi - fp16(hi)): the packed pair always sums to hi + lo (rows.h)
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn((l.x + (h.x - f0.x)) * PACK_SCALE, (l.y + (h.y - f0.y)) * PACK_SCALE);
+    const __half2 l1 = __floats2half2_rn((l.z + (h.z - f1.x)) * PACK_SCALE, (l.w + (h.w - f1.y)) * PACK_SCALE);
     uint2* dst = reinterpret_cast<uint2*>(pack + row * 32);
     dst[q] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
     dst[8 + q] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));

@@ -43,8 +43,10 @@ __host__ __device__ inline bool row_valid(const RowGeom& g, int r /* row inside 
 //   activations  [ fp16(x_hi[0..31]) | fp16(PACK_SCALE * x_lo[0..31]) ]        weights (per output channel and tap)  [ fp16(PACK_SCALE * w_lo) | fp16(w_hi) ]
 // so that one K = 64 dot product of the two rows is PACK_SCALE * (x_hi w_lo + x_lo w_hi): both correction products of
 // x w ~= x_hi w_hi + x_lo w_hi + x_hi w_lo in one kind::f16 MMA chain with the descriptors of the fp32 rows (same 128-byte rows, same
-// 32-byte K steps).  hi = tf32(v) has 11 significant bits and is exact in fp16 (values are O(1) after normalisation); |lo| <= 2^-12 |v| is
-// scaled by 2^12 into fp16's normal range (Ootomo & Yokota's scaling), so the corrections keep 11 bits: 2^-23 of the product.
+// 32-byte K steps), and the hi halves alone (K steps 0, 1 of an activation row against K steps 2, 3 of a weight row) give the main product.
+// hi = tf32(v) has 11 significant bits and is exact in fp16 for |v| in fp16's normal range (values are O(1) after normalisation); where
+// fp16(hi) != hi the packed lo half absorbs the difference (lo' = v - fp16(hi)), so hi16 + lo' = v always.  |lo'| <= 2^-12 |v| is scaled
+// by 2^12 into fp16's normal range (Ootomo & Yokota's scaling), so the corrections keep 11 bits: 2^-23 of the product.
 constexpr float PACK_SCALE = 4096.0f;
 
 constexpr int ROW_TAIL = 2048;   // rows allocated (and zero) after the last patch of every row buffer
@@ -67,8 +69,8 @@ struct RowConvP {
     const float* residual3;            //   its partial passes and the hi / lo halves of the skip connection through them
     float* y_lo;                       // conv3_tc only: when set, y receives hi = tf32(v) and y_lo the remainder v - hi
     float* y_pack;                     // conv3_tc only: when set, also the PACKED fp16 pair row of (hi, lo) (see PACK_SCALE)
-    int f16_pack;                      // conv3_tc only: x and w are packed fp16 pair rows; the kernel issues kind::f16 MMAs (K = 16) over the
-                                       //   64-element rows, which yields PACK_SCALE * (x_hi w_lo + x_lo w_hi), and scales the sum back
+    int f16_pack;                      // conv3_tc only: x and w are packed fp16 pair rows; the kernel computes the whole compensated product
+                                       //   x_hi w_hi + x_lo w_hi + x_hi w_lo from them with kind::f16 MMAs (main and correction accumulators)
     const float* relumask;             // [rows][n]: output multiplied by (relumask > 0), or nullptr
     float* y; int n;                   // output rows, channels per output row
     int B;
