@@ -92,9 +92,17 @@ __device__ __forceinline__ TileInfo tile_info(const Conv3Args& a, int tile, int 
 // significant bits and is exact in fp16, so the main product loses nothing against kind::tf32 while taking half the accumulation steps
 // (tcgen05 truncates the accumulator once per step), and the corrections never touch the full-size sum.  The epilogue adds
 // main + 2^-12 corrections (+ bias + skip connection) in fp32, round to nearest.
-template <bool F16>
+//
+// MODE 2 (the split-weight data gradient in ONE launch): gradients are not O(1), so both operands are bf16 PAIRS (fp32's exponent range,
+// 16 significant bits, no scaling): gradient rows [bf16(g) | bf16(g - bf16(g))], weight rows [bf16(w) | bf16(w - bf16(w))] in the data
+// gradient's layout.  Per tap: main accumulator g_a w_a (2 steps), second accumulator g_b w_a + g_a w_b (4 steps); same epilogue with
+// scale 1.  What is dropped is 2^-16 of each weight (the single-pass engine drops 2^-12, which is the systematic error the split
+// removes) and 2^-16 of each gradient (tf32 operands keep 2^-12).  (kind::f16 does NOT take bf16 gradients against fp16 weights:
+// mixed 16-bit operand formats raise an illegal-instruction fault on sm_100a, tried in round 2.)
+template <int MODE>
 __global__ void __launch_bounds__(C3_THREADS, 1)
 rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const Conv3Args a) {
+    constexpr bool F16 = MODE != 0;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * C3_STAGES + 5];
     __shared__ uint32_t tmem_slot;
@@ -151,7 +159,8 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         if (elect_one_sync()) {
             constexpr uint64_t HI = smem_desc_hi(16, 1024, 2);          // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
             constexpr uint32_t HI32 = (uint32_t)(HI >> 32), LO32 = (uint32_t)HI;
-            constexpr uint32_t IDESC = instr_desc(F16 ? 0 : 2, 128, 96, 0, 0);    // tf32 (or fp16) operands -> f32, M = 128, N = 96 (three dw taps)
+            // tf32 (MODE 1: fp16, MODE 2: bf16) operands -> f32, M = 128, N = 96 (three dw taps)
+            constexpr uint32_t IDESC = instr_desc(MODE == 0 ? 2 : (MODE == 2 ? 1 : 0), 128, 96, 0, 0);
             const uint32_t dh_inc = (uint32_t)a.pw * 8u;                // one image line further into the slab (16-byte units)
             mbar_wait(BAR(WBAR), 0);
             tc_fence_after();
@@ -186,7 +195,11 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     for (int dh = 0; dh < 3; ++dh) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            if (F16) {
+                            if (MODE == 2) {
+                                // K-steps 0, 1 of a row = the first halves (g_a, w_a), 2, 3 = the remainders: main g_a w_a; second g_b w_a + g_a w_b
+                                if (ks < 2) umma_ss_f16_lohi(d_tmem, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
+                                umma_ss_f16_lohi(d_tmem + 96, a_lo + dh * dh_inc + 2 * ((ks + 2) & 3), b_lo + (uint32_t)(dh * 3) * 256u + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
+                            } else if (F16) {
                                 // corrections: whole rows; main: activation K-steps 0, 1 (hi) against weight K-steps 2, 3 (w_hi)
                                 umma_ss_f16_lohi(d_tmem + 96, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
                                 if (ks < 2) umma_ss_f16_lohi(d_tmem, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 4 + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
@@ -240,50 +253,80 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             }
             mbar_wait(BAR(TFULL + acc), aph);
             tc_fence_after();
-            uint32_t v0[32], v1[32], v2[32];
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
-            tmem_ld32(taddr, v0);
-            tmem_ld32(taddr + 32, v1);
-            tmem_ld32(taddr + 64, v2);
-            if (F16) {                                                    // + 2^-12 x the correction accumulator, one third at a time
-                constexpr float CS = 1.0f / PACK_SCALE;
-                uint32_t vc[32];
-                tmem_ld32(taddr + 96, vc);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 32; ++c) v0[c] = __float_as_uint(fmaf(__uint_as_float(vc[c]), CS, __uint_as_float(v0[c])));
+            // cross-warp halo: the last lane's Q_0 row goes to the next warp's lane 0, the first lane's Q_2 row to the previous warp's lane 31
+            float (*xb)[2][32] = xch[grp][(tl >> 1) & 1];
+            float o[32];
+            if (F16) {
+                // main + 2^-12 x correction accumulator, one dw third at a time (middle, left, right) so that only one third of each
+                // accumulator is live next to the running sum: the kernel sits at its 168-register cap
+                constexpr float CS = MODE == 2 ? 1.0f : 1.0f / PACK_SCALE;
+                uint32_t vm[32], vc[32];
+                tmem_ld32(taddr + 32, vm);
                 tmem_ld32(taddr + 128, vc);
                 tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 32; ++c) v1[c] = __float_as_uint(fmaf(__uint_as_float(vc[c]), CS, __uint_as_float(v1[c])));
-                tmem_ld32(taddr + 160, vc);
+                for (int c = 0; c < 32; ++c) o[c] = fmaf(__uint_as_float(vc[c]), CS, __uint_as_float(vm[c]));
+                tmem_ld32(taddr, vm);
+                tmem_ld32(taddr + 96, vc);
                 tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < 32; ++c) v2[c] = __float_as_uint(fmaf(__uint_as_float(vc[c]), CS, __uint_as_float(v2[c])));
-            }
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(TEMPTY + acc));
-            // cross-warp halo: the last lane's Q_0 row goes to the next warp's lane 0, the first lane's Q_2 row to the previous warp's lane 31
-            float (*xb)[2][32] = xch[grp][(tl >> 1) & 1];
-            if (lane == 31) {
+                for (int c = 0; c < 32; ++c) {
+                    const float t = fmaf(__uint_as_float(vc[c]), CS, __uint_as_float(vm[c]));
+                    vm[c] = __float_as_uint(t);
+                    const float left = __shfl_up_sync(0xffffffffu, t, 1);
+                    o[c] += lane > 0 ? left : 0.f;
+                }
+                if (lane == 31) {
 #pragma unroll
-                for (int g4 = 0; g4 < 8; ++g4)
-                    reinterpret_cast<float4*>(xb[q][0])[g4] = make_float4(__uint_as_float(v0[4 * g4]), __uint_as_float(v0[4 * g4 + 1]), __uint_as_float(v0[4 * g4 + 2]), __uint_as_float(v0[4 * g4 + 3]));
-            }
-            if (lane == 0) {
+                    for (int g4 = 0; g4 < 8; ++g4)
+                        reinterpret_cast<float4*>(xb[q][0])[g4] = make_float4(__uint_as_float(vm[4 * g4]), __uint_as_float(vm[4 * g4 + 1]), __uint_as_float(vm[4 * g4 + 2]), __uint_as_float(vm[4 * g4 + 3]));
+                }
+                tmem_ld32(taddr + 64, vm);
+                tmem_ld32(taddr + 160, vc);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(TEMPTY + acc));
 #pragma unroll
-                for (int g4 = 0; g4 < 8; ++g4)
-                    reinterpret_cast<float4*>(xb[q][1])[g4] = make_float4(__uint_as_float(v2[4 * g4]), __uint_as_float(v2[4 * g4 + 1]), __uint_as_float(v2[4 * g4 + 2]), __uint_as_float(v2[4 * g4 + 3]));
-            }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-            float o[32];
+                for (int c = 0; c < 32; ++c) {
+                    const float t = fmaf(__uint_as_float(vc[c]), CS, __uint_as_float(vm[c]));
+                    vm[c] = __float_as_uint(t);
+                    const float right = __shfl_down_sync(0xffffffffu, t, 1);
+                    o[c] += lane < 31 ? right : 0.f;
+                }
+                if (lane == 0) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[c]), 1);
-                const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c]), 1);
-                o[c] = __uint_as_float(v1[c]) + (lane > 0 ? left : 0.f) + (lane < 31 ? right : 0.f);
+                    for (int g4 = 0; g4 < 8; ++g4)
+                        reinterpret_cast<float4*>(xb[q][1])[g4] = make_float4(__uint_as_float(vm[4 * g4]), __uint_as_float(vm[4 * g4 + 1]), __uint_as_float(vm[4 * g4 + 2]), __uint_as_float(vm[4 * g4 + 3]));
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+            } else {
+                uint32_t v0[32], v1[32], v2[32];
+                tmem_ld32(taddr, v0);
+                tmem_ld32(taddr + 32, v1);
+                tmem_ld32(taddr + 64, v2);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(BAR(TEMPTY + acc));
+                if (lane == 31) {
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4)
+                        reinterpret_cast<float4*>(xb[q][0])[g4] = make_float4(__uint_as_float(v0[4 * g4]), __uint_as_float(v0[4 * g4 + 1]), __uint_as_float(v0[4 * g4 + 2]), __uint_as_float(v0[4 * g4 + 3]));
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4)
+                        reinterpret_cast<float4*>(xb[q][1])[g4] = make_float4(__uint_as_float(v2[4 * g4]), __uint_as_float(v2[4 * g4 + 1]), __uint_as_float(v2[4 * g4 + 2]), __uint_as_float(v2[4 * g4 + 3]));
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[c]), 1);
+                    const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[c]), 1);
+                    o[c] = __uint_as_float(v1[c]) + (lane > 0 ? left : 0.f) + (lane < 31 ? right : 0.f);
+                }
             }
 
             if (lane == 0 && q > 0) {
@@ -406,13 +449,16 @@ int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st) {
     const int grid = ntiles < sms ? ntiles : sms;
     // executed flops: the compensated launch runs the main product (K = 32 per tap) and both corrections (K = 64 per tap)
     PV_TIMED(p.tag ? p.tag : "rowconv3_tc", st, p.flops, 0.0, (p.f16_pack ? 3.0 : 1.0) * 2.0 * (double)ntiles * 128.0 * 96.0 * 288.0);
-    static size_t attr[16] = {}, attr_h[16] = {};
-    if (p.f16_pack) {
-        PV_CUDA(ensure_dyn_smem(rowconv3_tc_kernel<true>, smem, attr_h));
-        PV_CUDA(launch_pdl(rowconv3_tc_kernel<true>, grid, C3_THREADS, smem, st, tm_x, tm_w, a));
+    static size_t attr[16] = {}, attr_h[16] = {}, attr_g[16] = {};
+    if (p.f16_pack == 2) {
+        PV_CUDA(ensure_dyn_smem(rowconv3_tc_kernel<2>, smem, attr_g));
+        PV_CUDA(launch_pdl(rowconv3_tc_kernel<2>, grid, C3_THREADS, smem, st, tm_x, tm_w, a));
+    } else if (p.f16_pack) {
+        PV_CUDA(ensure_dyn_smem(rowconv3_tc_kernel<1>, smem, attr_h));
+        PV_CUDA(launch_pdl(rowconv3_tc_kernel<1>, grid, C3_THREADS, smem, st, tm_x, tm_w, a));
     } else {
-        PV_CUDA(ensure_dyn_smem(rowconv3_tc_kernel<false>, smem, attr));
-        PV_CUDA(launch_pdl(rowconv3_tc_kernel<false>, grid, C3_THREADS, smem, st, tm_x, tm_w, a));
+        PV_CUDA(ensure_dyn_smem(rowconv3_tc_kernel<0>, smem, attr));
+        PV_CUDA(launch_pdl(rowconv3_tc_kernel<0>, grid, C3_THREADS, smem, st, tm_x, tm_w, a));
     }
     PV_LAUNCH_CHECK();
     return 0;

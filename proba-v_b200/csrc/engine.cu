@@ -262,7 +262,7 @@ int conv_wgrad(pv_trainer* t, int li, const float* in, const float* gout, const 
 int refresh_weights(pv_model* m, cudaStream_t st) {
     if (!m->weff_dirty) return 0;
     PV_TRY(launch_wn_prep(m->wn_tab, (int)m->layers.size(), m->wn_blocks, m->params, m->weff, m->weffT, m->bias_s, m->scale, st,
-                          m->weff_lo, m->weffT_lo, m->weffT_pack));
+                          m->weff_lo, m->weffT_lo, m->weffT_pack, m->weff_pack));
     m->weff_dirty = false;
     return 0;
 }
@@ -543,11 +543,13 @@ int pv_model_create(const pv_cfg* cfg, int device, pv_model** out) {
     cudaMemset(m->bias_s, 0, m->nbias_s * sizeof(float));
     if (m->x3) {
         if (cudaMalloc(&m->weff_lo, m->nweff * sizeof(float)) != cudaSuccess || cudaMalloc(&m->weffT_lo, m->nweff * sizeof(float)) != cudaSuccess ||
-            cudaMalloc(&m->weffT_pack, m->nweff * sizeof(float)) != cudaSuccess)
+            cudaMalloc(&m->weffT_pack, m->nweff * sizeof(float)) != cudaSuccess ||
+            cudaMalloc(&m->weff_pack, m->nweff * sizeof(float)) != cudaSuccess)
             return fail(set_error(PV_ERR_CUDA, "cudaMalloc of the weight remainder arenas failed"));
         cudaMemset(m->weff_lo, 0, m->nweff * sizeof(float));
         cudaMemset(m->weffT_lo, 0, m->nweff * sizeof(float));
         cudaMemset(m->weffT_pack, 0, m->nweff * sizeof(float));
+        cudaMemset(m->weff_pack, 0, m->nweff * sizeof(float));
     }
     std::vector<WnLayer> tab(m->layers.size());
     int blocks = 0;
@@ -578,7 +580,7 @@ void pv_model_destroy(pv_model* m) {
     m->pool_infer.release();
     m->pool_train.release();
     cudaFree(m->params); cudaFree(m->weff); cudaFree(m->weffT); cudaFree(m->bias_s); cudaFree(m->scale); cudaFree(m->wn_tab);
-    cudaFree(m->weff_lo); cudaFree(m->weffT_lo); cudaFree(m->weffT_pack);
+    cudaFree(m->weff_lo); cudaFree(m->weffT_lo); cudaFree(m->weffT_pack); cudaFree(m->weff_pack);
     cudaFree(m->stage_lr); cudaFree(m->stage_sr); cudaFree(m->stage_scene);
     m->scene_pipe.release();
     delete m;

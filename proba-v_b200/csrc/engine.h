@@ -137,6 +137,7 @@ struct pv_model {
     bool x3 = false;                   // precision 4: error-compensated tensor-core engine.  Every forward product is
                                        // x_hi w_hi + x_lo w_hi + x_hi w_lo (hi = tf32(v), lo = v - hi), data gradients use w_hi + w_lo
     float *weff_lo = nullptr, *weffT_lo = nullptr;   // w - tf32(w) in the layouts of weff / weffT
+    float* weff_pack = nullptr;                      // bf16 pair rows [w_a | w - w_a] indexed like weff (data gradient: rows (tap, ci), K = co)
     float* weffT_pack = nullptr;                     // packed fp16 pair rows of the 3x3x3 layers (rows.h), indexed like weffT
     float *stage_lr = nullptr, *stage_sr = nullptr, *stage_scene = nullptr;   // host-API staging
     size_t stage_lr_n = 0, stage_sr_n = 0, stage_scene_n = 0;

@@ -7,6 +7,7 @@
 //   -> reflect pad -> G0 [G] -> convReducer_1..3 (+ReLU) -> G1..G3 -> upscaleConv1 -> U [G] -> tail (+ 2-D skip path)
 // Backward: every data-gradient kernel masks its output with the ReLU of the layer it flows into, so the stored
 // tensors are dL/d(pre-activation) and the weight-gradient kernels need no mask.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cmath>
 #include <cstring>
@@ -114,9 +115,10 @@ int conv_rows(pv_model* m, const Layer& L, const Taps& tp, const float* x, int x
 }
 
 // data gradient of layer L: gx = conv^T(gz) (+ residual), multiplied by (relumask > 0), masked to the valid extent of `xg`
+// gz_pack (precision 4, nullable): gz as bf16 pair rows -> the split-weight product in one launch (conv3_tc.cu MODE 2)
 int dgrad_rows(pv_model* m, const Layer& L, const Taps& tp /* negated offsets */, int nchunk_out /* cout_s / 32 */,
                const float* gz, const RowGeom& zg, float* gx, const RowGeom& xg, const float* residual, const float* relumask,
-               int B, const char* tag, cudaStream_t st) {
+               int B, const char* tag, cudaStream_t st, const float* gz_pack = nullptr) {
     RowConvP p;
     memset(&p, 0, sizeof p);
     p.x = gz; p.xc = L.cout_s; p.y = gx; p.n = L.cin_s; p.B = B;
@@ -139,6 +141,10 @@ int dgrad_rows(pv_model* m, const Layer& L, const Taps& tp /* negated offsets */
     p.round_tf32 = m->use_tc ? 1 : 0;
     p.flops = 2.0 * B * L.Ho * L.Wo * L.To * L.taps() * L.cin * L.cout;
     p.tag = tag;
+    if (m->x3 && gz_pack && rowconv3_tc_supported(p)) {
+        p.x = gz_pack; p.w = m->weff_pack + L.weff_off; p.f16_pack = 2;
+        return launch_rowconv_tc(p, st);
+    }
     if (m->x3) {
         // precision 4: gx = gz * (w_hi + w_lo).  The weight rounding is the one systematic error of the data-gradient chain
         // (profiles/r02_tf32_numerics_study.md); the lo pass goes first into the fp32 partial buffer, then rides as the residual.
@@ -444,12 +450,23 @@ static float host_tf32(float v) {
 }
 struct SplitBuf {
     float *full = nullptr, *hi = nullptr, *lo = nullptr, *pack = nullptr;
-    // pack_mode 1: activation rows [fp16(hi) | fp16(PACK_SCALE lo)], 2: weight rows [fp16(PACK_SCALE lo) | fp16(hi)] per 32 values (rows.h)
+    // pack_mode 1: activation rows [fp16(hi) | fp16(PACK_SCALE lo)], 2: weight rows [fp16(PACK_SCALE lo) | fp16(hi)] per 32 values (rows.h),
+    // 3: bf16 pair rows [bf16(v) | bf16(v - bf16(v))] (gradients and the data gradient's weights)
     int upload(const std::vector<float>& h, int pack_mode = 0) {
         const size_t n = h.size();
         std::vector<float> a(n), b(n);
         for (size_t i = 0; i < n; ++i) { a[i] = host_tf32(h[i]); b[i] = h[i] - a[i]; }
-        if (pack_mode) {
+        if (pack_mode == 3) {
+            std::vector<__nv_bfloat16> pk(2 * n);
+            for (size_t r = 0; r < n / 32; ++r)
+                for (int c = 0; c < 32; ++c) {
+                    const __nv_bfloat16 hh = __float2bfloat16_rn(h[r * 32 + c]);
+                    pk[r * 64 + c] = hh;
+                    pk[r * 64 + 32 + c] = __float2bfloat16_rn(h[r * 32 + c] - __bfloat162float(hh));
+                }
+            PV_CUDA(cudaMalloc(&pack, n * 4));
+            PV_CUDA(cudaMemcpy(pack, pk.data(), n * 4, cudaMemcpyHostToDevice));
+        } else if (pack_mode) {
             std::vector<__half> pk(2 * n);
             for (size_t r = 0; r < n / 32; ++r)
                 for (int c = 0; c < 32; ++c) {
@@ -554,6 +571,25 @@ static int selftest_x3(std::string& rep) {
             snprintf(line, sizeof line, "%-34s %s %zu mismatching elements of %zu\n", "x3 conv3: packed fp16 pair output", bad == 0 ? "PASS" : "FAIL", bad, rows * 32);
             rep += line;
             fails += bad == 0 ? 0 : 1;
+        }
+        // ---------------- the same lattice as a split-weight data gradient in one launch: bf16 pair rows x fp16 pair weights (conv3_tc.cu MODE 2)
+        {
+            SplitBuf GZ;
+            rows_rand(h, 1e-4f);                           // gradient-sized values: far below fp16's normal range, fine in bf16
+            PV_TRY(GZ.upload(h, 3));
+            q.x = GZ.full; q.bias = nullptr; q.residual = nullptr;
+            PV_CUDA(cudaMemset(y0, 0, rows * 128)); PV_CUDA(cudaMemset(yh, 0, rows * 128));
+            rc = launch_rowconv_simt(q, 0);
+            RowConvP g = q;
+            SplitBuf WB;
+            PV_TRY(WB.upload(wk, 3));
+            g.x = GZ.pack; g.w = WB.pack; g.w_rows = 32; g.w_cols = 864; g.w_kmajor = 1; g.f16_pack = 2; g.y = yh; g.round_tf32 = 0;
+            for (int i = 0; i < 27; ++i) { g.wr0[i] = 0; g.wc0[i] = 32 * i; }
+            if (!rc) rc = launch_rowconv_tc(g, 0);
+            if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest x3 dgrad: %s", cudaGetErrorString(cudaGetLastError()));
+            if (rc) { rep += std::string("x3 conv3 split-weight dgrad        FAIL : ") + last_error() + "\n"; ++fails; }
+            else fails += compare("x3 conv3 split-weight dgrad", y0, yh, nullptr, rows * 32, 5e-5);     // 16 bits of each operand
+            GZ.release(); WB.release();
         }
         for (float* p : {wt_d, b_d, y0, yh, yl, ypk}) cudaFree(p);
     }
@@ -799,6 +835,7 @@ int tc_build_plan(pv_model* m) {
             P.add("g_a0", rows_per(pr, F), rows_extra(pr, F));
             P.add("g_a1", rows_per(pr, F), rows_extra(pr, F));
             P.add("g_D", rows_per(pr, F), rows_extra(pr, F));
+            if (m->x3) P.add("g_pack", rows_per(pr, F), rows_extra(pr, F));      // bf16 pair rows of the block-input gradient (conv3_tc.cu MODE 2)
             if (!m->use_tc) P.add("g_E", rows_per(pr, EX), rows_extra(pr, EX));
             for (const TailStep& ts : tail) {
                 if (ts.copy) P.add("g_" + ts.in, rows_per(ts.ig, F), rows_extra(ts.ig, F));
@@ -1008,7 +1045,9 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int st
         const float* G = P["g_a" + std::to_string((i + 1) & 1)];
         float* gin = P["g_a" + std::to_string(i & 1)];
         PV_TRY(wgrad_rows(t, Ln, same, P[m->D(i, true)], F, pr, G, pr, B, "norm_wgrad", st));
-        PV_TRY(dgrad_rows(m, Ln, same_T, 1, G, pr, P["g_D"], pr, nullptr, nullptr, B, "norm_dgrad", st));
+        // (precision 4: block i + 1's backward-data kernel left G as bf16 pair rows too; the last block's G comes from the tail)
+        PV_TRY(dgrad_rows(m, Ln, same_T, 1, G, pr, P["g_D"], pr, nullptr, nullptr, B, "norm_dgrad", st,
+                          (m->x3 && i + 1 < R) ? P["g_pack"] : nullptr));
         if (m->use_tc) {                // expand/decay backward on chip: E and gZ are recomputed in TMEM, never stored
             const double fl = 2.0 * B * Le.Ho * Le.Wo * Le.To * ((double)Le.cin * Le.cout + (double)Ld.cin * Ld.cout);
             PV_TRY(launch_resfront_bwd_weight_tc(P[m->A(i, true)], P["g_D"], m->weffT + Le.weff_off, m->weff + Ld.weff_off,
@@ -1019,7 +1058,8 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int st
             PV_TRY(launch_resfront_bwd_data_tc(P["g_D"], m->weff + Ld.weff_off, m->weff + Le.weff_off,
                                                reinterpret_cast<const uint32_t*>(P["M" + std::to_string(i)]), G,
                                                i == 0 ? P[m->A(0, true)] : nullptr, gin, pr, B, 1, fl, st,
-                                               m->x3 ? m->weff_lo + Ld.weff_off : nullptr, m->x3 ? m->weff_lo + Le.weff_off : nullptr));
+                                               m->x3 ? m->weff_lo + Ld.weff_off : nullptr, m->x3 ? m->weff_lo + Le.weff_off : nullptr,
+                                               (m->x3 && i > 0) ? P["g_pack"] : nullptr));
             continue;
         }
         PV_TRY(wgrad_rows(t, Ld, wide, P[m->E(i, true)], EX, pr, P["g_D"], pr, B, "dec_wgrad", st));

@@ -5,6 +5,7 @@
 //   weight norm     : TFA WeightNormalization kernel = g * v/||v||, all layers in one launch, + backward
 //   optimizers      : Keras Nadam / Adam / SGD over the flat parameter arena (train.py:77-83)
 //   scene geometry  : reflect-pad-3 + unfold(22, stride 16) and the n x n stitch (dataGenerator.py:108-121; test.py:149-160)
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "kernels.h"
@@ -143,7 +144,8 @@ __global__ void __launch_bounds__(128) wn_prep_kernel(const WnLayer* __restrict_
                                                       const float* __restrict__ params, float* __restrict__ weff,
                                                       float* __restrict__ weffT, float* __restrict__ bias_s,
                                                       float* __restrict__ scale, float* __restrict__ weff_lo,
-                                                      float* __restrict__ weffT_lo, float* __restrict__ weffT_pack) {
+                                                      float* __restrict__ weffT_lo, float* __restrict__ weffT_pack,
+                                                      float* __restrict__ weff_pack) {
     pdl_grid_wait();
     __shared__ float red[4];
     int co;
@@ -177,8 +179,15 @@ __global__ void __launch_bounds__(128) wn_prep_kernel(const WnLayer* __restrict_
                 // the 32 fp32 K-values of weffT occupy
                 __half* row = reinterpret_cast<__half*>(weffT_pack + L.weffT_off + (long long)co * (L.taps * L.cin_s) + (long long)rt * L.cin_s);
                 const __half w16 = __float2half_rn(w);                 // == w unless |w| is below fp16's normal range; the lo half absorbs that
-                row[ci] = __float2half_rn((wf - __half2float(w16)) * PACK_SCALE);
+                const __half l16 = __float2half_rn((wf - __half2float(w16)) * PACK_SCALE);
+                row[ci] = l16;
                 row[32 + ci] = w16;
+                if (weff_pack && L.cout_s == 32) {     // the data gradient's bf16 pair, row (tap, ci), K = co (the layout of weff): [w_a | w - w_a]
+                    __nv_bfloat16* rowd = reinterpret_cast<__nv_bfloat16*>(weff_pack + L.weff_off + ((long long)rt * L.cin_s + ci) * L.cout_s);
+                    const __nv_bfloat16 wa = __float2bfloat16_rn(wf);
+                    rowd[co] = wa;
+                    rowd[32 + co] = __float2bfloat16_rn(wf - __bfloat162float(wa));
+                }
             }
         }
     }
@@ -332,9 +341,9 @@ int launch_tail_bwd(const float* dsr, int B, int P, int scale, float stdv, float
 }
 
 int launch_wn_prep(const WnLayer* tab, int nlayers, int nblocks, const float* params, float* weff, float* weffT,
-                   float* bias_s, float* scale, cudaStream_t st, float* weff_lo, float* weffT_lo, float* weffT_pack) {
+                   float* bias_s, float* scale, cudaStream_t st, float* weff_lo, float* weffT_lo, float* weffT_pack, float* weff_pack) {
     PV_TIMED("wn_prep", st);
-    PV_CUDA(launch_pdl_simple(wn_prep_kernel, nblocks, 128, 0, st, tab, nlayers, params, weff, weffT, bias_s, scale, weff_lo, weffT_lo, weffT_pack));
+    PV_CUDA(launch_pdl_simple(wn_prep_kernel, nblocks, 128, 0, st, tab, nlayers, params, weff, weffT, bias_s, scale, weff_lo, weffT_lo, weffT_pack, weff_pack));
     PV_LAUNCH_CHECK();
     return 0;
 }

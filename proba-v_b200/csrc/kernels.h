@@ -69,7 +69,8 @@ struct WnLayer {
 // weff_lo / weffT_lo (nullable, row engine): w - tf32(w) in the layouts of weff / weffT (error-compensated forward, precision 4)
 int launch_wn_prep(const WnLayer* table_dev, int nlayers, int nblocks, const float* params, float* weff, float* weffT,
                    float* bias_s, float* scale, cudaStream_t st, float* weff_lo = nullptr, float* weffT_lo = nullptr,
-                   float* weffT_pack = nullptr);   // packed fp16 pair rows of the 3x3x3 layers' weights (rows.h PACK_SCALE)
+                   float* weffT_pack = nullptr,    // packed fp16 pair rows of the 3x3x3 layers' weights (rows.h PACK_SCALE), forward layout
+                   float* weff_pack = nullptr);    // bf16 pair rows [w_a | w - w_a] in the data gradient's layout (rows (tap, ci), K = co)
 int launch_wn_bwd(const WnLayer* table_dev, int nlayers, int nblocks, const float* params, const float* scale,
                   const float* dweff, const float* dbias_s, float* grads, cudaStream_t st, int block0 = 0);   // blocks [block0, block0 + nblocks): a layer sub-range
 int launch_g_from_v(const WnLayer* table_dev, int nlayers, int nblocks, float* params, cudaStream_t st);

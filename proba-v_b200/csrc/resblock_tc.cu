@@ -12,6 +12,8 @@
 //
 // Layouts as in rows.h (PR rows, 32 channels, 128 B per row); weights are the effective (weight-normalised, tf32)
 // matrices prepared by wn_prep: weT_exp [256][32], weT_dec [32][256] (both K contiguous).
+#include <cuda_bf16.h>
+
 #include "rowio.cuh"
 #include "rows.h"
 #include "tc_common.cuh"
@@ -72,7 +74,8 @@ struct ResPipeArgs {
     const float* residual;             // bwd: G rows
     const float* relumask;             // bwd: rows or nullptr
     float* out;                        // rows [.. x 32]
-    int round_tf32;
+    float* out_pack;                   // bwd, nullable: the same rows as bf16 pairs [bf16(v) | bf16(v - bf16(v))] of the un-rounded result
+    int round_tf32;                    //   (what the next block's single-launch 3x3x3 data gradient reads, conv3_tc.cu MODE 2)
 };
 
 // WSPLIT (backward-data of the error-compensated engine, precision 4): both weight matrices come as hi + lo (hi = tf32(w),
@@ -321,10 +324,24 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                         }
                     }
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
+                    for (int e = 0; e < 4; ++e)
                         if (!valid) o[e] = 0.f;
-                        if (a.round_tf32) o[e] = rna_tf32(o[e]);
+                }
+                if (MODE == 1 && a.out_pack) {
+                    float pk[32];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(out_row[2 * c], out_row[2 * c + 1]);
+                        const float2 hf = __bfloat1622float2(h);
+                        const __nv_bfloat162 l = __floats2bfloat162_rn(out_row[2 * c] - hf.x, out_row[2 * c + 1] - hf.y);
+                        pk[c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+                        pk[16 + c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l));
                     }
+                    rowio_store_rows(a.out_pack + orow_w * 32, pk, rowmask, sc);
+                }
+                if (a.round_tf32) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) out_row[c] = rna_tf32(out_row[c]);
                 }
                 rowio_store_rows(a.out + orow_w * 32, out_row, rowmask, sc);
             }
@@ -595,10 +612,11 @@ int launch_resfront_fwd_tc(const float* x, const float* weT_exp, const float* we
 // gA = ((gD Wd^T) .* relu_bits) We + G  (.* relumask).  w_dec [256][32] (= weff of decConv), w_exp [32][256] (= weff of expConv)
 int launch_resfront_bwd_data_tc(const float* gd, const float* w_dec, const float* w_exp, const uint32_t* relu_bits,
                                 const float* residual, const float* relumask, float* ga, const RowGeom& g,
-                                int B, int round_tf32, double flops, cudaStream_t st, const float* w_dec_lo, const float* w_exp_lo) {
+                                int B, int round_tf32, double flops, cudaStream_t st, const float* w_dec_lo, const float* w_exp_lo, float* ga_pack) {
     ResPipeArgs a;
     memset(&a, 0, sizeof a);
     a.B = B; a.g = g; a.mask = const_cast<uint32_t*>(relu_bits); a.residual = residual; a.relumask = relumask; a.out = ga; a.round_tf32 = round_tf32;
+    a.out_pack = ga_pack;
     if (w_dec_lo || w_exp_lo) return launch_respipe<1, true>(gd, w_dec, w_exp, a, "resfront_bwd_data_w2", flops, st, w_dec_lo, w_exp_lo);
     return launch_respipe<1>(gd, w_dec, w_exp, a, "resfront_bwd_data", flops, st);
 }

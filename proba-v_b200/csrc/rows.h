@@ -69,8 +69,9 @@ struct RowConvP {
     const float* residual3;            //   its partial passes and the hi / lo halves of the skip connection through them
     float* y_lo;                       // conv3_tc only: when set, y receives hi = tf32(v) and y_lo the remainder v - hi
     float* y_pack;                     // conv3_tc only: when set, also the PACKED fp16 pair row of (hi, lo) (see PACK_SCALE)
-    int f16_pack;                      // conv3_tc only: x and w are packed fp16 pair rows; the kernel computes the whole compensated product
-                                       //   x_hi w_hi + x_lo w_hi + x_hi w_lo from them with kind::f16 MMAs (main and correction accumulators)
+    int f16_pack;                      // conv3_tc only: 1 = x and w are packed fp16 pair rows; the kernel computes the whole compensated product
+                                       //   x_hi w_hi + x_lo w_hi + x_hi w_lo from them with kind::f16 MMAs (main and correction accumulators);
+                                       //   2 = x and w are bf16 pair rows [a | v - a], unscaled (a gradient and the weights): x w to 16 bits each
     const float* relumask;             // [rows][n]: output multiplied by (relumask > 0), or nullptr
     float* y; int n;                   // output rows, channels per output row
     int B;
@@ -119,7 +120,8 @@ int launch_resfront_fwd_tc(const float* x, const float* weT_exp, const float* we
 int launch_resfront_bwd_data_tc(const float* gd, const float* w_dec, const float* w_exp, const uint32_t* relu_bits,
                                 const float* residual, const float* relumask, float* ga, const RowGeom& g,
                                 int B, int round_tf32, double flops, cudaStream_t st,
-                                const float* w_dec_lo = nullptr, const float* w_exp_lo = nullptr);   // lo halves: two MMAs per product
+                                const float* w_dec_lo = nullptr, const float* w_exp_lo = nullptr,    // lo halves: two MMAs per product
+                                float* ga_pack = nullptr);     // also the un-rounded result as bf16 pair rows (conv3_tc MODE 2's input)
 // error-compensated forward (resblock_x3_tc.cu): operands and result as (hi, lo) row arrays, three MMAs per product
 int launch_resfront_fwd_x3_tc(const float* x_hi, const float* x_lo, const float* weT_exp_hi, const float* weT_exp_lo,
                               const float* weT_dec_hi, const float* weT_dec_lo, const float* bias_e, const float* bias_d,

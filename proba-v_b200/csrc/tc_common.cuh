@@ -195,9 +195,12 @@ __device__ __forceinline__ uint64_t smem_desc(uint64_t hi_template, uint32_t sme
 }
 // instruction descriptor (kind::tf32 / kind::f16, fp32 accumulate):
 // c_format=1 (F32) [4,6) | a_format [7,10) | b_format [10,13) | a_major [15] | b_major [16] | N>>3 [17,23) | M>>4 [24,29)
-__host__ __device__ constexpr uint32_t instr_desc(int fmt /*0 f16, 1 bf16, 2 tf32*/, int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn_major << 15) |
+__host__ __device__ constexpr uint32_t instr_desc2(int a_fmt, int b_fmt /*0 f16, 1 bf16, 2 tf32*/, int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
            ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t instr_desc(int fmt, int M, int N, int a_mn_major, int b_mn_major) {
+    return instr_desc2(fmt, fmt, M, N, a_mn_major, b_mn_major);
 }
 
 }  // namespace tc
