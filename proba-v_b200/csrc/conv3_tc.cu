@@ -23,6 +23,7 @@
 //
 // Warp roles as in conv_tc.cu: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer (one elected thread), warps 2-5 and
 // 6-9 two epilogue groups draining alternate tiles (TMEM accumulator double buffer, 2 x 96 columns).
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "rowio.cuh"
@@ -53,8 +54,8 @@ struct Conv3Args {
     int slab_lo[3];                    // first row of temporal slab dtI relative to the tile's lane-0 row
     int pw;                            // rows per image line: dh view stride inside a slab
     int tap_wr[MAX_TAPS], tap_wc[MAX_TAPS];
-    const float* bias; const float* residual; const float* residual2; const float* residual3; const float* relumask; float* y; float* y_lo;
-    float* y_pack;                     // packed fp16 pair rows of (hi, lo) (rows.h PACK_SCALE), nullable
+    const float* bias; const float* residual; const float* residual2; const float* relumask; float* y; float* y_lo;
+    float* y_pack;                     // MODE 1: packed fp16 pair rows of (hi, lo) (rows.h PACK_SCALE); MODE 2: bf16 pair rows; nullable
     int relu, round_tf32;
 };
 
@@ -239,15 +240,9 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             const float* pre_src = a.residual ? a.residual : a.relumask;
             float4 pre[8];
             if (pre_src) rowio_ldg_chunks(pre_src + orow_w * 32, rowmask, pre);
-            if (a.residual2) {                                            // further addends (compensated forward): summed chunk-wise,
-                float4 t2[8];                                             // hi + lo of the skip connection first, then the partial pass
+            if (MODE == 1 && a.residual2) {                               // the lo half of the skip connection (compensated forward)
+                float4 t2[8];
                 rowio_ldg_chunks(a.residual2 + orow_w * 32, rowmask, t2);
-                if (a.residual3) {
-                    float4 t3[8];
-                    rowio_ldg_chunks(a.residual3 + orow_w * 32, rowmask, t3);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { t2[i].x += t3[i].x; t2[i].y += t3[i].y; t2[i].z += t3[i].z; t2[i].w += t3[i].w; }
-                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { pre[i].x += t2[i].x; pre[i].y += t2[i].y; pre[i].z += t2[i].z; pre[i].w += t2[i].w; }
             }
@@ -363,12 +358,30 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                     e[2] = mq.z > 0.f ? e[2] : 0.f; e[3] = mq.w > 0.f ? e[3] : 0.f;
                 }
                 if (!valid) { e[0] = e[1] = e[2] = e[3] = 0.f; }
-                if (a.round_tf32) {
+                if (a.round_tf32 && !(MODE == 2 && a.y_pack)) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) e[k] = rna_tf32(e[k]);
                 }
             }
-            if (a.y_lo || a.y_pack) {                                     // hi / lo split of the fp32 result (hi is tf32-exact)
+            if (MODE == 2) {
+                if (a.y_pack) {                                           // the un-rounded gradient as a bf16 pair row for the next data gradient
+                    float pk[32];
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * c], o[2 * c + 1]);
+                        const float2 hf = __bfloat1622float2(h);
+                        const __nv_bfloat162 l = __floats2bfloat162_rn(o[2 * c] - hf.x, o[2 * c + 1] - hf.y);
+                        pk[c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+                        pk[16 + c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&l));
+                    }
+                    rowio_store_rows(a.y_pack + orow_w * 32, pk, rowmask, sc);
+                    if (a.round_tf32) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) o[c] = rna_tf32(o[c]);
+                    }
+                }
+                rowio_store_rows(a.y + orow_w * 32, o, rowmask, sc);
+            } else if (MODE == 1 && (a.y_lo || a.y_pack)) {               // hi / lo split of the fp32 result (hi is tf32-exact)
                 float lo[32];
 #pragma unroll
                 for (int c = 0; c < 32; ++c) { const float hi = rna_tf32(o[c]); lo[c] = o[c] - hi; o[c] = hi; }
@@ -417,9 +430,10 @@ int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st) {
     const int pw = p.off[3] - p.off[0];
     a.B = p.B; a.in_lead = p.in_lead; a.in_pstride = p.in_pstride; a.og = og; a.pw = pw;
     a.bias = p.bias; a.residual = p.residual; a.relumask = p.relumask; a.y = p.y; a.relu = p.relu; a.round_tf32 = p.round_tf32;
-    a.residual2 = p.residual2; a.residual3 = p.residual3; a.y_lo = p.y_lo; a.y_pack = p.y_pack;
-    if ((p.residual2 || p.residual3) && !p.residual) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: residual2/3 need residual");
-    if (p.residual3 && !p.residual2) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: residual3 needs residual2");
+    a.residual2 = p.residual2; a.y_lo = p.y_lo; a.y_pack = p.y_pack;
+    if (p.residual2 && !p.residual) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: residual2 needs residual");
+    if ((p.residual2 || p.y_lo) && p.f16_pack != 1) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: residual2 / y_lo belong to the compensated forward (f16_pack = 1)");
+    if (p.y_pack && !p.f16_pack) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: y_pack needs one of the pair-row modes");
     a.slab_rows = ((128 + 2 * pw + 7) / 8) * 8;
     // lane l of a tile accumulates Q[rho = r0 + l]; its A rows for group g are rho + base_g + 1 with base_g = off[3g]
     for (int s = 0; s < 3; ++s) a.slab_lo[s] = p.off[9 * s] + 1;

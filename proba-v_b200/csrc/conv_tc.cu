@@ -275,7 +275,7 @@ rowconv_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 int launch_rowconv_tc(const RowConvP& p, cudaStream_t st) {
     static const bool force_n32 = getenv("PV_CONV3_N32") != nullptr;
     if (!force_n32 && rowconv3_tc_supported(p)) return launch_rowconv3_tc(p, st);
-    if (p.residual2 || p.residual3 || p.y_lo || p.y_pack || p.f16_pack) return set_error(PV_ERR_BAD_ARG, "rowconv_tc: extra addends / split output need the conv3 kernel");
+    if (p.residual2 || p.y_lo || p.y_pack || p.f16_pack) return set_error(PV_ERR_BAD_ARG, "rowconv_tc: extra addends / split output need the conv3 kernel");
     if (p.kc != 32 || (p.n != 32 && p.n != 256) || p.ntap < 1 || p.ntap > MAX_TAPS || !p.w_kmajor)
         return set_error(PV_ERR_BAD_ARG, "rowconv_tc: unsupported shape kc=%d n=%d ntap=%d kmajor=%d", p.kc, p.n, p.ntap, p.w_kmajor);
     if (p.og.row0 % 128) return set_error(PV_ERR_BAD_ARG, "rowconv_tc: row0 must be a multiple of 128");

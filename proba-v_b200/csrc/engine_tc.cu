@@ -118,7 +118,7 @@ int conv_rows(pv_model* m, const Layer& L, const Taps& tp, const float* x, int x
 // gz_pack (precision 4, nullable): gz as bf16 pair rows -> the split-weight product in one launch (conv3_tc.cu MODE 2)
 int dgrad_rows(pv_model* m, const Layer& L, const Taps& tp /* negated offsets */, int nchunk_out /* cout_s / 32 */,
                const float* gz, const RowGeom& zg, float* gx, const RowGeom& xg, const float* residual, const float* relumask,
-               int B, const char* tag, cudaStream_t st, const float* gz_pack = nullptr) {
+               int B, const char* tag, cudaStream_t st, const float* gz_pack = nullptr, float* gx_pack = nullptr) {
     RowConvP p;
     memset(&p, 0, sizeof p);
     p.x = gz; p.xc = L.cout_s; p.y = gx; p.n = L.cin_s; p.B = B;
@@ -142,20 +142,12 @@ int dgrad_rows(pv_model* m, const Layer& L, const Taps& tp /* negated offsets */
     p.flops = 2.0 * B * L.Ho * L.Wo * L.To * L.taps() * L.cin * L.cout;
     p.tag = tag;
     if (m->x3 && gz_pack && rowconv3_tc_supported(p)) {
-        p.x = gz_pack; p.w = m->weff_pack + L.weff_off; p.f16_pack = 2;
+        p.x = gz_pack; p.w = m->weff_pack + L.weff_off; p.f16_pack = 2; p.y_pack = gx_pack;      // gx_pack: gx as bf16 pair rows for the next one
         return launch_rowconv_tc(p, st);
     }
-    if (m->x3) {
-        // precision 4: gx = gz * (w_hi + w_lo).  The weight rounding is the one systematic error of the data-gradient chain
-        // (profiles/r02_tf32_numerics_study.md); the lo pass goes first into the fp32 partial buffer, then rides as the residual.
-        if (residual) return set_error(PV_ERR_BAD_ARG, "dgrad_rows: the split-weight data gradient has no residual slot left");
-        float* yp = m->pool_train["Yp"];
-        RowConvP q = p;
-        q.w = m->weff_lo + L.weff_off; q.relumask = nullptr; q.round_tf32 = 0; q.y = yp; q.flops = 0.0;
-        PV_TRY(launch_rowconv_tc(q, st));
-        p.residual = yp;
-        return launch_rowconv_tc(p, st);
-    }
+    // precision 4 runs every 3x3x3 data gradient with split weights (the weight rounding is the one systematic error of the data-gradient
+    // chain, profiles/r02_tf32_numerics_study.md); the pointwise ones live in the fused block kernels
+    if (m->x3) return set_error(PV_ERR_BAD_ARG, "dgrad_rows: the error-compensated engine needs bf16 pair rows of the gradient and a 3x3x3 lattice");
     return m->use_tc ? launch_rowconv_tc(p, st) : launch_rowconv_simt(p, st);
 }
 
@@ -810,8 +802,7 @@ int tc_build_plan(pv_model* m) {
             P.add(ts.out, rows_per(ts.og, F), rows_extra(ts.og, F));
         }
         P.add("U", rows_per(ug, F), rows_extra(ug, F));
-        if (m->x3) {                    // remainders (v - tf32(v)) of the tensors a compensated forward product reads; Yp: the split-weight data gradient's partial pass
-            size_t yp_per = rows_per(pr, F), yp_extra = rows_extra(pr, F);
+        if (m->x3) {                    // remainders (v - tf32(v)) of the tensors a compensated forward product reads, and their packed pair rows
             P.add("a_lo0", rows_per(pr, F), rows_extra(pr, F));
             P.add("a_lo1", rows_per(pr, F), rows_extra(pr, F));
             P.add("D_pack", rows_per(pr, F), rows_extra(pr, F));         // packed fp16 pair rows (rows.h): what a compensated conv3 reads
@@ -822,10 +813,7 @@ int tc_build_plan(pv_model* m) {
                 }
                 P.add(ts.out + "_lo", rows_per(ts.og, F), rows_extra(ts.og, F));
                 P.add(ts.out + "_pack", rows_per(ts.og, F), rows_extra(ts.og, F));
-                yp_per = std::max(yp_per, std::max(rows_per(ts.ig, F), rows_per(ts.og, F)));
-                yp_extra = std::max(yp_extra, std::max(rows_extra(ts.ig, F), rows_extra(ts.og, F)));
             }
-            P.add("Yp", yp_per, yp_extra);
         }
         for (int i = 0; i < c.scale; ++i) {
             const Layer& L = m->layers[m->li("residConv" + std::to_string(i + 1))];
@@ -840,7 +828,9 @@ int tc_build_plan(pv_model* m) {
             for (const TailStep& ts : tail) {
                 if (ts.copy) P.add("g_" + ts.in, rows_per(ts.ig, F), rows_extra(ts.ig, F));
                 P.add("g_" + ts.out, rows_per(ts.og, F), rows_extra(ts.og, F));
+                if (m->x3) P.add("g_" + ts.out + "_pack", rows_per(ts.og, F), rows_extra(ts.og, F));
             }
+            if (m->x3) P.add("g_U_pack", rows_per(ug, F), rows_extra(ug, F));
             P.add("g_U", rows_per(ug, F), rows_extra(ug, F));
             P.add("g_tail", (size_t)m->P * m->P * c.scale * c.scale);
             for (int i = 0; i + 1 < c.scale; ++i) {
@@ -997,7 +987,9 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int st
     t->rq.reset(t->wg_partial_floats);        // deferred partial reductions of this pass: one launch per bucket, before wn_bwd
     PV_CUDA(cudaMemsetAsync(t->dweff, 0, m->nweff * sizeof(float), st));
     PV_CUDA(cudaMemsetAsync(t->dbias_s, 0, m->nbias_s * sizeof(float), st));
-    PV_TRY(launch_tail_bwd_rows(g_sr, B, m->P, c.scale, c.std, P["g_U"], ug, F, P["g_tail"], st, m->use_tc ? 1 : 0));
+    // precision 4: every gradient a 3x3x3 data gradient reads also exists as bf16 pair rows ("..._pack"), written by its producer
+    auto gpack = [&](const std::string& name) -> float* { return m->x3 ? P[name + "_pack"] : nullptr; };
+    PV_TRY(launch_tail_bwd_rows(g_sr, B, m->P, c.scale, c.std, P["g_U"], ug, F, P["g_tail"], st, m->use_tc ? 1 : 0, gpack("g_U")));
     if (c.scale == 3 && skip2d_supported(m->S, c.scale * c.scale) &&
         skip2d_partial_floats(B, m->S, c.scale * c.scale) <= t->wg_partial_floats) {   // ---- 2-D skip path: one fused kernel + a fixed-order reduction
         const Layer &R1 = m->layers[m->li("residConv1")], &R2 = m->layers[m->li("residConv2")], &R3 = m->layers[m->li("residConv3")];
@@ -1022,20 +1014,22 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int st
         const Layer& U = m->layers[m->li("upscaleConv1")];
         const TailStep& last = tail.back();
         PV_TRY(wgrad_rows(t, U, valid, P[last.out], F, last.og, P["g_U"], ug, B, "upscale_wgrad", st));
-        PV_TRY(dgrad_rows(m, U, valid_T, 1, P["g_U"], ug, P["g_" + last.out], last.og, nullptr, P[last.out], B, "upscale_dgrad", st));
+        PV_TRY(dgrad_rows(m, U, valid_T, 1, P["g_U"], ug, P["g_" + last.out], last.og, nullptr, P[last.out], B, "upscale_dgrad", st,
+                          gpack("g_U"), gpack("g_" + last.out)));
         for (int k = (int)tail.size() - 1; k >= 0; --k) {
             const TailStep& ts = tail[k];
             const Layer& L = m->layers[m->li("convReducer_" + std::to_string(k + 1))];
             PV_TRY(wgrad_rows(t, L, valid, P[ts.in], F, ts.ig, P["g_" + ts.out], ts.og, B, "reducer_wgrad", st));
             // the input is the previous reducer's ReLU output itself (mask here) or a padded copy of it (mask in the pad adjoint)
+            // (a padded copy's gradient goes through the pad adjoint next, which reads fp32 rows: no pair rows of it)
             PV_TRY(dgrad_rows(m, L, valid_T, 1, P["g_" + ts.out], ts.og, P["g_" + ts.in], ts.ig, nullptr, (k > 0 && !ts.copy) ? P[ts.in] : nullptr,
-                              B, "reducer_dgrad", st));
+                              B, "reducer_dgrad", st, gpack("g_" + ts.out), ts.copy ? nullptr : gpack("g_" + ts.in)));
             if (k > 0 && ts.copy)
                 PV_TRY(launch_pr_to_g_reflect_bwd(P["g_" + ts.in], ts.ig, P["g_" + tail[k - 1].out], tail[k - 1].og, B, F, st, ts.pad, P[tail[k - 1].out],
-                                                  m->use_tc ? 1 : 0));
+                                                  m->use_tc ? 1 : 0, gpack("g_" + tail[k - 1].out)));
         }
         PV_TRY(launch_pr_to_g_reflect_bwd(P["g_" + tail[0].in], tail[0].ig, P["g_a" + std::to_string(R & 1)], pr, B, F, st, tail[0].pad, nullptr,
-                                          m->use_tc ? 1 : 0));
+                                          m->use_tc ? 1 : 0, m->x3 ? P["g_pack"] : nullptr));
     }
     }   // stage != 1
     const int i_hi = stage == 1 ? isplit - 1 : R - 1, i_lo = stage == 0 ? isplit : 0;
@@ -1045,9 +1039,9 @@ int tc_backward(pv_trainer* t, const float* g_sr, int B, cudaStream_t st, int st
         const float* G = P["g_a" + std::to_string((i + 1) & 1)];
         float* gin = P["g_a" + std::to_string(i & 1)];
         PV_TRY(wgrad_rows(t, Ln, same, P[m->D(i, true)], F, pr, G, pr, B, "norm_wgrad", st));
-        // (precision 4: block i + 1's backward-data kernel left G as bf16 pair rows too; the last block's G comes from the tail)
+        // (precision 4: block i + 1's backward-data kernel, or the tail's pad adjoint, left G as bf16 pair rows too)
         PV_TRY(dgrad_rows(m, Ln, same_T, 1, G, pr, P["g_D"], pr, nullptr, nullptr, B, "norm_dgrad", st,
-                          (m->x3 && i + 1 < R) ? P["g_pack"] : nullptr));
+                          m->x3 ? P["g_pack"] : nullptr));
         if (m->use_tc) {                // expand/decay backward on chip: E and gZ are recomputed in TMEM, never stored
             const double fl = 2.0 * B * Le.Ho * Le.Wo * Le.To * ((double)Le.cin * Le.cout + (double)Ld.cin * Ld.cout);
             PV_TRY(launch_resfront_bwd_weight_tc(P[m->A(i, true)], P["g_D"], m->weffT + Le.weff_off, m->weff + Ld.weff_off,

@@ -4,6 +4,7 @@
 // layers that are not tensor-core shaped (mainConv1, Cin = 1) and as the on-device cross-check of each tcgen05
 // kernel (pv_selftest), and (b) the layout glue between the PR trunk and the valid-conv tail.
 // Reference semantics: Keras Conv3D inside TFA WeightNormalization (modelsTF.py:191-197), tf.pad REFLECT (:157-158).
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include <cstdlib>
@@ -456,10 +457,21 @@ __device__ __forceinline__ int preimages(int i, int n, int p, int (&o)[3]) {
     return c;
 }
 
+// channels 4q .. 4q+3 of 32-channel row `row` as a bf16 pair [bf16(v) x 32 | bf16(v - bf16(v)) x 32] (128 bytes per row)
+__device__ __forceinline__ void store_bf16_pair4(float* pack, long long row, int q, float4 v) {
+    const __nv_bfloat162 a0 = __floats2bfloat162_rn(v.x, v.y), a1 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f0 = __bfloat1622float2(a0), f1 = __bfloat1622float2(a1);
+    const __nv_bfloat162 b0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), b1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+    uint2* dst = reinterpret_cast<uint2*>(pack + row * 32);
+    dst[q] = make_uint2(*reinterpret_cast<const uint32_t*>(&a0), *reinterpret_cast<const uint32_t*>(&a1));
+    dst[8 + q] = make_uint2(*reinterpret_cast<const uint32_t*>(&b0), *reinterpret_cast<const uint32_t*>(&b1));
+}
+
 // adjoint of the kernel above; `relumask` (nullable, same rows as ga): the result is multiplied by (relumask > 0), i.e. the
 // gradient flows into the ReLU output the padded tensor was made from (convReducePad_2/3 of the T = 13 graph)
 __global__ void pr_to_g_reflect_bwd_kernel(const float* __restrict__ gg0, RowGeom gg, float* __restrict__ ga, RowGeom pr,
-                                           long long n, int C4, int pad, const float* __restrict__ relumask, int round_tf32) {
+                                           long long n, int C4, int pad, const float* __restrict__ relumask, int round_tf32,
+                                           float* __restrict__ ga_pack) {
     pdl_grid_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -483,6 +495,7 @@ __global__ void pr_to_g_reflect_bwd_kernel(const float* __restrict__ gg0, RowGeo
     }
     // the result only feeds kind::tf32 MMAs, which TRUNCATE a raw fp32 operand (a -2.4e-4 relative bias on the whole upstream
     // gradient chain, profiles/r02_tf32_numerics_study.md): store it rounded to nearest instead
+    if (ga_pack) store_bf16_pair4(ga_pack, dst, c, s);       // C4 == 8: the un-rounded result as a bf16 pair row (conv3_tc.cu MODE 2)
     if (round_tf32) { s.x = to_tf32(s.x); s.y = to_tf32(s.y); s.z = to_tf32(s.z); s.w = to_tf32(s.w); }
     reinterpret_cast<float4*>(ga)[dst * C4 + c] = s;
 }
@@ -521,7 +534,8 @@ __global__ void tail_rows_kernel(const float* __restrict__ u, RowGeom g, int uc,
 }
 
 __global__ void tail_bwd_rows_kernel(const float* __restrict__ dsr, long long n, int P, int s, float stdv,
-                                     float* __restrict__ gu, RowGeom g, int uc, float* __restrict__ dtail, int round_tf32) {
+                                     float* __restrict__ gu, RowGeom g, int uc, float* __restrict__ dtail, int round_tf32,
+                                     float* __restrict__ gu_pack) {
     pdl_grid_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // index into [B,P,P,s*s]
     if (i >= n) return;
@@ -531,7 +545,14 @@ __global__ void tail_bwd_rows_kernel(const float* __restrict__ dsr, long long n,
     const int PS = P * s;
     const float v = __ldg(dsr + (b * PS + h * s + c / s) * PS + w * s + c % s) * stdv;
     dtail[i] = v;
-    gu[(g.lead + b * g.pstride + (long long)g.t0 * g.plane + h * g.pw + w) * uc + c] = round_tf32 ? to_tf32(v) : v;   // MMA operand: see pr_to_g_reflect_bwd_kernel
+    const long long row = g.lead + b * g.pstride + (long long)g.t0 * g.plane + h * g.pw + w;
+    gu[row * uc + c] = round_tf32 ? to_tf32(v) : v;   // MMA operand: see pr_to_g_reflect_bwd_kernel
+    if (gu_pack) {                                    // uc == 32: bf16 pair row, channels >= s * s stay zero
+        __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(gu_pack + row * 32);
+        const __nv_bfloat16 a = __float2bfloat16_rn(v);
+        pk[c] = a;
+        pk[32 + c] = __float2bfloat16_rn(v - __bfloat162float(a));
+    }
 }
 
 }  // namespace
@@ -553,10 +574,12 @@ int launch_tail_rows(const float* u, RowGeom g, int uc, const float* resid, int 
     return 0;
 }
 
-int launch_tail_bwd_rows(const float* dsr, int B, int P, int scale, float stdv, float* gu, RowGeom g, int uc, float* dtail, cudaStream_t st, int round_tf32) {
+int launch_tail_bwd_rows(const float* dsr, int B, int P, int scale, float stdv, float* gu, RowGeom g, int uc, float* dtail, cudaStream_t st, int round_tf32,
+                         float* gu_pack) {
+    if (gu_pack && uc != 32) return set_error(PV_ERR_BAD_ARG, "tail_bwd: bf16 pair rows need 32-channel rows");
     const long long n = (long long)B * P * P * scale * scale;
     PV_TIMED("tail_bwd", st, 0.0, (double)n * 12.0);
-    PV_CUDA(launch_pdl_simple(tail_bwd_rows_kernel, cdiv(n, 256), 256, 0, st, dsr, n, P, scale, stdv, gu, g, uc, dtail, round_tf32));
+    PV_CUDA(launch_pdl_simple(tail_bwd_rows_kernel, cdiv(n, 256), 256, 0, st, dsr, n, P, scale, stdv, gu, g, uc, dtail, round_tf32, gu_pack));
     PV_LAUNCH_CHECK();
     return 0;
 }
@@ -648,12 +671,13 @@ int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, in
 }
 
 int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st, int pad,
-                               const float* relumask, int round_tf32) {
+                               const float* relumask, int round_tf32, float* ga_pack) {
+    if (ga_pack && C != 32) return set_error(PV_ERR_BAD_ARG, "pr_to_g_reflect_bwd: bf16 pair rows need 32-channel rows");
     if (pad < 0 || pad > 1 || gg.nh != pr.nh + 2 * pad || gg.nw != pr.nw + 2 * pad || gg.nt != pr.nt)
         return set_error(PV_ERR_BAD_ARG, "pr_to_g_reflect_bwd: geometry mismatch");
     const long long n = (long long)B * pr.nt * pr.nh * pr.nw * (C / 4);
     PV_TIMED("pr_to_g_reflect_bwd", st);
-    PV_CUDA(launch_pdl_simple(pr_to_g_reflect_bwd_kernel, cdiv(n, 256), 256, 0, st, gg0, gg, ga, pr, n, C / 4, pad, relumask, round_tf32));
+    PV_CUDA(launch_pdl_simple(pr_to_g_reflect_bwd_kernel, cdiv(n, 256), 256, 0, st, gg0, gg, ga, pr, n, C / 4, pad, relumask, round_tf32, ga_pack));
     PV_LAUNCH_CHECK();
     return 0;
 }

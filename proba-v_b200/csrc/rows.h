@@ -65,10 +65,10 @@ struct RowConvP {
     int wr0[MAX_TAPS], wc0[MAX_TAPS];
     const float* bias;                 // [n] or nullptr
     const float* residual;             // [rows][n] same rows as y, or nullptr
-    const float* residual2;            // two more addends of the same shape (conv3_tc only): the error-compensated forward chains
-    const float* residual3;            //   its partial passes and the hi / lo halves of the skip connection through them
-    float* y_lo;                       // conv3_tc only: when set, y receives hi = tf32(v) and y_lo the remainder v - hi
-    float* y_pack;                     // conv3_tc only: when set, also the PACKED fp16 pair row of (hi, lo) (see PACK_SCALE)
+    const float* residual2;            // conv3_tc, f16_pack = 1 only: a second addend of the same shape (the lo half of the skip connection)
+    float* y_lo;                       // conv3_tc, f16_pack = 1 only: when set, y receives hi = tf32(v) and y_lo the remainder v - hi
+    float* y_pack;                     // conv3_tc only: when set, also the result as a pair row: f16_pack = 1: fp16 pair of (hi, lo)
+                                       //   (see PACK_SCALE); f16_pack = 2: bf16 pair of the un-rounded result
     int f16_pack;                      // conv3_tc only: 1 = x and w are packed fp16 pair rows; the kernel computes the whole compensated product
                                        //   x_hi w_hi + x_lo w_hi + x_hi w_lo from them with kind::f16 MMAs (main and correction accumulators);
                                        //   2 = x and w are bf16 pair rows [a | v - a], unscaled (a gradient and the weights): x w to 16 bits each
@@ -143,7 +143,7 @@ int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, i
 int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st, int pad = 1);
 // round_tf32: store the result rounded to nearest tf32 (it only feeds tensor-core MMAs, which would truncate it)
 int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st, int pad = 1,
-                               const float* relumask = nullptr, int round_tf32 = 0);
+                               const float* relumask = nullptr, int round_tf32 = 0, float* ga_pack = nullptr);   // ga_pack: also as bf16 pair rows
 
 // low-frequency skip path (three 3x3 Conv2D) with the graph's tail fused in (skip2d.cu); u / ug / uc describe the upscale conv's rows
 int launch_skip2d_fwd_tail(const float* mn, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
@@ -155,6 +155,6 @@ int launch_pack_rows(const float* hi, const float* lo, float* pack, long long n3
 int launch_tail_rows(const float* u, RowGeom g, int uc, const float* resid, int B, int P, int scale, float mean, float stdv,
                      int clip_round, float* sr, cudaStream_t st);
 int launch_tail_bwd_rows(const float* dsr, int B, int P, int scale, float stdv, float* gu, RowGeom g, int uc, float* dtail, cudaStream_t st,
-                         int round_tf32 = 0);
+                         int round_tf32 = 0, float* gu_pack = nullptr);
 
 }  // namespace pv
