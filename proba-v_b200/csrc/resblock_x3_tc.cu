@@ -42,7 +42,7 @@ struct ResX3Args {
     uint32_t* mask_t;                  // [tile][4 row blocks][256 channels]: bit k = row k of the 32-row block (for the weight-gradient kernel)
     float* out_hi;                     // D rows: tf32(D)
     float* out_lo;                     //         D - tf32(D), or (pack_out) the packed fp16 pair rows of (hi, lo): what the
-    int pack_out;                      //         compensated 3x3x3 convolution's correction pass reads (rows.h PACK_SCALE)
+    int pack_out;                      //         compensated 3x3x3 convolution reads (rows.h PACK_SCALE)
 };
 
 __device__ __forceinline__ uint32_t tf32_rn_bits(uint32_t bits) { return (bits + 0x1000u) & 0xffffe000u; }

@@ -39,7 +39,7 @@ __host__ __device__ inline bool row_valid(const RowGeom& g, int r /* row inside 
     return t >= 0 && t < g.nt && h < g.nh && w < g.nw;
 }
 
-// Packed fp16 pair rows (error-compensated engine, the ONE correction pass of a compensated convolution): a 128-byte row holds 64 halves,
+// Packed fp16 pair rows (error-compensated engine: what a compensated 3x3x3 convolution reads): a 128-byte row holds 64 halves,
 //   activations  [ fp16(x_hi[0..31]) | fp16(PACK_SCALE * x_lo[0..31]) ]        weights (per output channel and tap)  [ fp16(PACK_SCALE * w_lo) | fp16(w_hi) ]
 // so that one K = 64 dot product of the two rows is PACK_SCALE * (x_hi w_lo + x_lo w_hi): both correction products of
 // x w ~= x_hi w_hi + x_lo w_hi + x_hi w_lo in one kind::f16 MMA chain with the descriptors of the fp32 rows (same 128-byte rows, same
@@ -47,6 +47,8 @@ __host__ __device__ inline bool row_valid(const RowGeom& g, int r /* row inside 
 // hi = tf32(v) has 11 significant bits and is exact in fp16 for |v| in fp16's normal range (values are O(1) after normalisation); where
 // fp16(hi) != hi the packed lo half absorbs the difference (lo' = v - fp16(hi)), so hi16 + lo' = v always.  |lo'| <= 2^-12 |v| is scaled
 // by 2^12 into fp16's normal range (Ootomo & Yokota's scaling), so the corrections keep 11 bits: 2^-23 of the product.
+// The backward pass uses bf16 pair rows instead, [ bf16(g) x 32 | bf16(g - bf16(g)) x 32 ], unscaled (gradients are far below fp16's range),
+// for the gradient rows and for the weights of the split-weight 3x3x3 data gradients (conv3_tc.cu MODE 2).
 constexpr float PACK_SCALE = 4096.0f;
 
 constexpr int ROW_TAIL = 2048;   // rows allocated (and zero) after the last patch of every row buffer
