@@ -100,10 +100,13 @@ __device__ __forceinline__ TileInfo tile_info(const Conv3Args& a, int tile, int 
 // scale 1.  What is dropped is 2^-16 of each weight (the single-pass engine drops 2^-12, which is the systematic error the split
 // removes) and 2^-16 of each gradient (tf32 operands keep 2^-12).  (kind::f16 does NOT take bf16 gradients against fp16 weights:
 // mixed 16-bit operand formats raise an illegal-instruction fault on sm_100a, tried in round 2.)
+//
+// MODE 3 (inference of the single-pass engine): the main product alone from the hi halves of fp16 pair rows -- the values are tf32-exact, so
+// the result is the kind::tf32 kernel's, with 2 instead of 4 MMAs per tap row (the kernel is bound by the operand fetch from shared memory).
 template <int MODE>
 __global__ void __launch_bounds__(C3_THREADS, 1)
 rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const Conv3Args a) {
-    constexpr bool F16 = MODE != 0;
+    constexpr bool F16 = MODE == 1 || MODE == 2;                  // pair-row modes with two accumulators
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * C3_STAGES + 5];
     __shared__ uint32_t tmem_slot;
@@ -161,7 +164,7 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             constexpr uint64_t HI = smem_desc_hi(16, 1024, 2);          // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
             constexpr uint32_t HI32 = (uint32_t)(HI >> 32), LO32 = (uint32_t)HI;
             // tf32 (MODE 1: fp16, MODE 2: bf16) operands -> f32, M = 128, N = 96 (three dw taps)
-            constexpr uint32_t IDESC = instr_desc(MODE == 0 ? 2 : (MODE == 2 ? 1 : 0), 128, 96, 0, 0);
+            constexpr uint32_t IDESC = instr_desc(MODE == 0 ? 2 : (MODE == 2 ? 1 : 0), 128, 96, 0, 0);   // MODE 1, 3: fp16
             const uint32_t dh_inc = (uint32_t)a.pw * 8u;                // one image line further into the slab (16-byte units)
             mbar_wait(BAR(WBAR), 0);
             tc_fence_after();
@@ -200,6 +203,8 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
                                 // K-steps 0, 1 of a row = the first halves (g_a, w_a), 2, 3 = the remainders: main g_a w_a; second g_b w_a + g_a w_b
                                 if (ks < 2) umma_ss_f16_lohi(d_tmem, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
                                 umma_ss_f16_lohi(d_tmem + 96, a_lo + dh * dh_inc + 2 * ((ks + 2) & 3), b_lo + (uint32_t)(dh * 3) * 256u + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
+                            } else if (MODE == 3) {
+                                if (ks < 2) umma_ss_f16_lohi(d_tmem, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 4 + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
                             } else if (F16) {
                                 // corrections: whole rows; main: activation K-steps 0, 1 (hi) against weight K-steps 2, 3 (w_hi)
                                 umma_ss_f16_lohi(d_tmem + 96, a_lo + dh * dh_inc + 2 * ks, b_lo + (uint32_t)(dh * 3) * 256u + 2 * ks, HI32, IDESC, (s | dh | ks) ? 1u : 0u);
@@ -433,7 +438,7 @@ int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st) {
     a.residual2 = p.residual2; a.y_lo = p.y_lo; a.y_pack = p.y_pack;
     if (p.residual2 && !p.residual) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: residual2 needs residual");
     if ((p.residual2 || p.y_lo) && p.f16_pack != 1) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: residual2 / y_lo belong to the compensated forward (f16_pack = 1)");
-    if (p.y_pack && !p.f16_pack) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: y_pack needs one of the pair-row modes");
+    if (p.y_pack && p.f16_pack != 1 && p.f16_pack != 2) return set_error(PV_ERR_BAD_ARG, "rowconv3_tc: y_pack needs one of the pair-row modes");
     a.slab_rows = ((128 + 2 * pw + 7) / 8) * 8;
     // lane l of a tile accumulates Q[rho = r0 + l]; its A rows for group g are rho + base_g + 1 with base_g = off[3g]
     for (int s = 0; s < 3; ++s) a.slab_lo[s] = p.off[9 * s] + 1;
@@ -462,9 +467,12 @@ int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st) {
     const int ntiles = a.B * a.chunks * a.nt;
     const int grid = ntiles < sms ? ntiles : sms;
     // executed flops: the compensated launch runs the main product (K = 32 per tap) and both corrections (K = 64 per tap)
-    PV_TIMED(p.tag ? p.tag : "rowconv3_tc", st, p.flops, 0.0, (p.f16_pack ? 3.0 : 1.0) * 2.0 * (double)ntiles * 128.0 * 96.0 * 288.0);
-    static size_t attr[16] = {}, attr_h[16] = {}, attr_g[16] = {};
-    if (p.f16_pack == 2) {
+    PV_TIMED(p.tag ? p.tag : "rowconv3_tc", st, p.flops, 0.0, ((p.f16_pack == 1 || p.f16_pack == 2) ? 3.0 : 1.0) * 2.0 * (double)ntiles * 128.0 * 96.0 * 288.0);
+    static size_t attr[16] = {}, attr_h[16] = {}, attr_g[16] = {}, attr_s[16] = {};
+    if (p.f16_pack == 3) {
+        PV_CUDA(ensure_dyn_smem(rowconv3_tc_kernel<3>, smem, attr_s));
+        PV_CUDA(launch_pdl(rowconv3_tc_kernel<3>, grid, C3_THREADS, smem, st, tm_x, tm_w, a));
+    } else if (p.f16_pack == 2) {
         PV_CUDA(ensure_dyn_smem(rowconv3_tc_kernel<2>, smem, attr_g));
         PV_CUDA(launch_pdl(rowconv3_tc_kernel<2>, grid, C3_THREADS, smem, st, tm_x, tm_w, a));
     } else if (p.f16_pack) {

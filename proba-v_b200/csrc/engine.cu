@@ -550,6 +550,10 @@ int pv_model_create(const pv_cfg* cfg, int device, pv_model** out) {
         cudaMemset(m->weffT_lo, 0, m->nweff * sizeof(float));
         cudaMemset(m->weffT_pack, 0, m->nweff * sizeof(float));
         cudaMemset(m->weff_pack, 0, m->nweff * sizeof(float));
+    } else if (m->use_tc) {             // single-pass tensor-core engine: fp16 copies of the 3x3x3 weights for the inference convs (conv3_tc.cu MODE 3)
+        if (cudaMalloc(&m->weffT_pack, m->nweff * sizeof(float)) != cudaSuccess)
+            return fail(set_error(PV_ERR_CUDA, "cudaMalloc of the fp16 weight arena failed"));
+        cudaMemset(m->weffT_pack, 0, m->nweff * sizeof(float));
     }
     std::vector<WnLayer> tab(m->layers.size());
     int blocks = 0;

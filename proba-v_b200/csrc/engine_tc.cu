@@ -92,8 +92,9 @@ Taps chunk_taps(int kin) {
 }
 
 // forward convolution of layer L:  y = act(conv(x) + bias) (+ residual), masked to the valid extent of `og`
+// x_f16: x holds fp16 pair rows (hi halves used): the 3x3x3 lattice runs as conv3_tc.cu MODE 3 against the fp16 weight copies
 int conv_rows(pv_model* m, const Layer& L, const Taps& tp, const float* x, int xc, const RowGeom& ig, float* y, const RowGeom& og,
-              const float* residual, int B, const char* tag, cudaStream_t st, bool round_out = true) {
+              const float* residual, int B, const char* tag, cudaStream_t st, bool round_out = true, bool x_f16 = false) {
     RowConvP p;
     memset(&p, 0, sizeof p);
     p.x = x; p.xc = xc; p.y = y; p.n = L.cout_s; p.B = B;
@@ -111,6 +112,10 @@ int conv_rows(pv_model* m, const Layer& L, const Taps& tp, const float* x, int x
     p.round_tf32 = (m->use_tc && round_out) ? 1 : 0;      // outputs that only feed MMAs are stored round-to-nearest tf32
     p.flops = 2.0 * B * L.Ho * L.Wo * L.To * L.taps() * L.cin * L.cout;
     p.tag = tag;
+    if (x_f16) {
+        if (!m->use_tc || !m->weffT_pack || !rowconv3_tc_supported(p)) return set_error(PV_ERR_BAD_ARG, "conv_rows: fp16 rows need the 3x3x3 tensor-core kernel");
+        p.w = m->weffT_pack + L.weff_off; p.f16_pack = 3;
+    }
     return m->use_tc ? launch_rowconv_tc(p, st) : launch_rowconv_simt(p, st);
 }
 
@@ -564,6 +569,26 @@ static int selftest_x3(std::string& rep) {
             rep += line;
             fails += bad == 0 ? 0 : 1;
         }
+        // ---------------- the inference form (conv3_tc.cu MODE 3): hi halves of the fp16 pair rows only = the single-pass product of the tf32 values
+        {
+            float* wth_d;
+            std::vector<float> wth(864 * 32);
+            for (int co = 0; co < 32; ++co) for (int k = 0; k < 864; ++k) wth[(size_t)k * 32 + co] = host_tf32(wk[(size_t)co * 864 + k]);
+            PV_CUDA(cudaMalloc(&wth_d, wth.size() * 4));
+            PV_CUDA(cudaMemcpy(wth_d, wth.data(), wth.size() * 4, cudaMemcpyHostToDevice));
+            RowConvP r0 = q;
+            r0.x = X.hi; r0.w = wth_d; r0.residual = RES.hi;
+            PV_CUDA(cudaMemset(y0, 0, rows * 128)); PV_CUDA(cudaMemset(yh, 0, rows * 128));
+            rc = launch_rowconv_simt(r0, 0);
+            RowConvP g = q;
+            g.x = X.pack; g.w = W3.pack; g.w_rows = 32; g.w_cols = 864; g.w_kmajor = 1; g.f16_pack = 3; g.residual = RES.hi; g.y = yh; g.round_tf32 = 0;
+            for (int i = 0; i < 27; ++i) { g.wr0[i] = 0; g.wc0[i] = 32 * i; }
+            if (!rc) rc = launch_rowconv_tc(g, 0);
+            if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest fp16-row conv: %s", cudaGetErrorString(cudaGetLastError()));
+            if (rc) { rep += std::string("conv3 fp16 rows (inference)        FAIL : ") + last_error() + "\n"; ++fails; }
+            else fails += compare("conv3 fp16 rows (inference)", y0, yh, nullptr, rows * 32, 2e-6);      // same tf32 values, fp32 accumulation order differs
+            cudaFree(wth_d);
+        }
         // ---------------- the same lattice as a split-weight data gradient in one launch: bf16 pair rows x fp16 pair weights (conv3_tc.cu MODE 2)
         {
             SplitBuf GZ;
@@ -932,6 +957,11 @@ int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip
     if (m->x3) return tc_forward_x3(m, B, sr, tr, clip_round, st);
     PV_TRY(launch_first_conv_pr(P["xn"], m->weff + L0.weff_off, m->bias_s + L0.bias_s_off, B, m->S, m->T, P[m->A(0, tr)], pr, st, nullptr,
                                 m->use_tc ? 1 : 0));
+    // Inference on the tensor cores: the decay output only feeds the block's 3x3x3 conv, so the fused kernel stores it as fp16 rows
+    // (tf32-exact values are fp16-exact) and the conv runs K = 16 MMAs over them: half the operand fetch of the tf32 form, same result.
+    // (Training keeps fp32 rows: the weight-gradient kernels read D as a tf32 operand.)  PV_INFER_TF32_ROWS=1 keeps the tf32 form (A/B).
+    static const bool infer_tf32_rows = getenv("PV_INFER_TF32_ROWS") != nullptr;
+    const bool f16_rows = !tr && m->use_tc && m->weffT_pack && !infer_tf32_rows;
     for (int i = 0; i < m->R; ++i) {                                   // ResConv3D, modelsTF.py:177-189
         const int e = m->li("expConv_" + std::to_string(i));
         const Layer &Le = m->layers[e], &Ld = m->layers[e + 1];
@@ -939,12 +969,12 @@ int tc_forward(pv_model* m, const float* lr, int B, float* sr, bool tr, int clip
             const double fl = 2.0 * B * Le.Ho * Le.Wo * Le.To * ((double)Le.cin * Le.cout + (double)Ld.cin * Ld.cout);
             PV_TRY(launch_resfront_fwd_tc(P[m->A(i, tr)], m->weffT + Le.weff_off, m->weffT + Ld.weff_off, m->bias_s + Le.bias_s_off,
                                           m->bias_s + Ld.bias_s_off, P[m->D(i, tr)],
-                                          tr ? reinterpret_cast<uint32_t*>(P["M" + std::to_string(i)]) : nullptr, pr, B, 1, fl, st));
+                                          tr ? reinterpret_cast<uint32_t*>(P["M" + std::to_string(i)]) : nullptr, pr, B, 1, fl, st, f16_rows ? 1 : 0));
         } else {
             PV_TRY(conv_rows(m, Le, one, P[m->A(i, tr)], F, pr, P[m->E(i, tr)], pr, nullptr, B, "exp_fwd", st));
             PV_TRY(conv_rows(m, Ld, wide, P[m->E(i, tr)], EX, pr, P[m->D(i, tr)], pr, nullptr, B, "dec_fwd", st));
         }
-        PV_TRY(conv_rows(m, m->layers[e + 2], same, P[m->D(i, tr)], F, pr, P[m->A(i + 1, tr)], pr, P[m->A(i, tr)], B, "norm_fwd", st));
+        PV_TRY(conv_rows(m, m->layers[e + 2], same, P[m->D(i, tr)], F, pr, P[m->A(i + 1, tr)], pr, P[m->A(i, tr)], B, "norm_fwd", st, true, f16_rows));
     }
     // ConvReduceAndUpscale (T = 9: modelsTF.py:152-164, reflect pad H,W by 1 before reducer 1), v2 (T = 7: :166-175, no pad),
     // v3 (T = 13: :123-150, reflect pad before reducers 1-3): valid 3x3x3 + ReLU reducers, then the upscale conv

@@ -174,7 +174,9 @@ __global__ void __launch_bounds__(128) wn_prep_kernel(const WnLayer* __restrict_
         if (weff_lo && L.mode == 1) {       // error-compensated engine: the remainder of the tf32 rounding, same two layouts
             weff_lo[L.weff_off + ((long long)rt * L.cin_s + ci) * L.cout_s + co] = wf - w;
             weffT_lo[L.weffT_off + (long long)co * (L.taps * L.cin_s) + (long long)rt * L.cin_s + ci] = wf - w;
-            if (weffT_pack && L.taps == 27 && L.cin_s == 32) {
+        }
+        {
+            if (weffT_pack && L.mode == 1 && L.taps == 27 && L.cin_s == 32) {     // (also the single-pass engine: its inference convs read the hi halves)
                 // packed fp16 pair row of (co, tap): [ fp16(PACK_SCALE * w_lo) x 32 | fp16(w_hi) x 32 ] (rows.h) in the 128 bytes
                 // the 32 fp32 K-values of weffT occupy
                 __half* row = reinterpret_cast<__half*>(weffT_pack + L.weffT_off + (long long)co * (L.taps * L.cin_s) + (long long)rt * L.cin_s);

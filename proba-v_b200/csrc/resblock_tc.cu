@@ -13,6 +13,7 @@
 // Layouts as in rows.h (PR rows, 32 channels, 128 B per row); weights are the effective (weight-normalised, tf32)
 // matrices prepared by wn_prep: weT_exp [256][32], weT_dec [32][256] (both K contiguous).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "rowio.cuh"
 #include "rows.h"
@@ -76,6 +77,7 @@ struct ResPipeArgs {
     float* out;                        // rows [.. x 32]
     float* out_pack;                   // bwd, nullable: the same rows as bf16 pairs [bf16(v) | bf16(v - bf16(v))] of the un-rounded result
     int round_tf32;                    //   (what the next block's single-launch 3x3x3 data gradient reads, conv3_tc.cu MODE 2)
+    int out_f16;                       // inference fwd: `out` receives fp16 pair rows [fp16(tf32(D)) x 32 | 0] instead of fp32 rows (conv3_tc.cu MODE 3)
 };
 
 // WSPLIT (backward-data of the error-compensated engine, precision 4): both weight matrices come as hi + lo (hi = tf32(w),
@@ -343,6 +345,15 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
 #pragma unroll
                     for (int c = 0; c < 32; ++c) out_row[c] = rna_tf32(out_row[c]);
                 }
+                if (MODE == 2 && a.out_f16) {                 // tf32-exact values are fp16-exact inside fp16's normal range
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const __half2 h = __floats2half2_rn(out_row[2 * c], out_row[2 * c + 1]);
+                        out_row[c] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+                    }
+#pragma unroll
+                    for (int c = 16; c < 32; ++c) out_row[c] = 0.f;
+                }
                 rowio_store_rows(a.out + orow_w * 32, out_row, rowmask, sc);
             }
         }
@@ -601,10 +612,12 @@ static int launch_respipe(const float* t, const float* w1, const float* w2, cons
 // D = decConv(relu(expConv(X))) on PR rows.  weT_exp [256][32], weT_dec [32][256], biases padded to 256 / 32.
 // relu_bits (nullable): [rows][8] uint32, bit (c % 32) of word c / 32 = (E[row][c] > 0), consumed by the backward-data kernel.
 int launch_resfront_fwd_tc(const float* x, const float* weT_exp, const float* weT_dec, const float* bias_e, const float* bias_d,
-                           float* d, uint32_t* relu_bits, const RowGeom& g, int B, int round_tf32, double flops, cudaStream_t st) {
+                           float* d, uint32_t* relu_bits, const RowGeom& g, int B, int round_tf32, double flops, cudaStream_t st, int out_f16) {
     ResPipeArgs a;
     memset(&a, 0, sizeof a);
     a.B = B; a.g = g; a.bias1 = bias_e; a.bias2 = bias_d; a.mask = relu_bits; a.out = d; a.round_tf32 = round_tf32;
+    if (out_f16 && (relu_bits || !round_tf32)) return set_error(PV_ERR_BAD_ARG, "resfront_fwd: fp16 rows are an inference output of tf32-rounded values");
+    a.out_f16 = out_f16;
     if (!relu_bits) return launch_respipe<2>(x, weT_exp, weT_dec, a, "resfront_fwd_infer", flops, st);
     return launch_respipe<0>(x, weT_exp, weT_dec, a, "resfront_fwd", flops, st);
 }

@@ -73,7 +73,8 @@ struct RowConvP {
                                        //   (see PACK_SCALE); f16_pack = 2: bf16 pair of the un-rounded result
     int f16_pack;                      // conv3_tc only: 1 = x and w are packed fp16 pair rows; the kernel computes the whole compensated product
                                        //   x_hi w_hi + x_lo w_hi + x_hi w_lo from them with kind::f16 MMAs (main and correction accumulators);
-                                       //   2 = x and w are bf16 pair rows [a | v - a], unscaled (a gradient and the weights): x w to 16 bits each
+                                       //   2 = x and w are bf16 pair rows [a | v - a], unscaled (a gradient and the weights): x w to 16 bits each;
+                                       //   3 = fp16 pair rows, hi halves only: the single-pass product with K = 16 MMAs (inference)
     const float* relumask;             // [rows][n]: output multiplied by (relumask > 0), or nullptr
     float* y; int n;                   // output rows, channels per output row
     int B;
@@ -118,7 +119,8 @@ int launch_rowconv3_tc(const RowConvP& p, cudaStream_t st);
 // fused expConv + ReLU + decConv of one residual block (resblock_tc.cu); the expanded tensor stays in TMEM.
 // relu_bits: [rows][8] uint32 ReLU bit mask written by the forward (nullable) and consumed by the backward-data kernel.
 int launch_resfront_fwd_tc(const float* x, const float* weT_exp, const float* weT_dec, const float* bias_e, const float* bias_d,
-                           float* d, uint32_t* relu_bits, const RowGeom& g, int B, int round_tf32, double flops, cudaStream_t st);
+                           float* d, uint32_t* relu_bits, const RowGeom& g, int B, int round_tf32, double flops, cudaStream_t st,
+                           int out_f16 = 0);      // inference: d receives fp16 pair rows [fp16(tf32(D)) | 0] (what conv3_tc MODE 3 reads)
 int launch_resfront_bwd_data_tc(const float* gd, const float* w_dec, const float* w_exp, const uint32_t* relu_bits,
                                 const float* residual, const float* relumask, float* ga, const RowGeom& g,
                                 int B, int round_tf32, double flops, cudaStream_t st,
