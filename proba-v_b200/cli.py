@@ -68,6 +68,20 @@ def _dirs(config: dict, cfg_path: str, band: str):
             os.path.join(config["model_out"], f"logs_{basename}", band))
 
 
+def _build_model(config, band, precision, preferred):
+    """--precision auto: the tensor-core engine `preferred` when it runs this graph (32 filters, 7 / 9 / 13 LR frames), else the dense
+    fp32 CUDA-core engine, which builds every graph the reference can (both are GPU engines: there is no CPU path)."""
+    from . import build_from_config
+    from ._lib import PvError
+    if precision != "auto":
+        return build_from_config(config, band=band, precision=precision)
+    try:
+        return build_from_config(config, band=band, precision=preferred)
+    except (PvError, ValueError) as e:
+        logger.info(f"[ INFO ] {preferred} engine does not run this graph ({e}); using the dense fp32 engine")
+        return build_from_config(config, band=band, precision="fp32")
+
+
 def train_parser() -> argparse.ArgumentParser:
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg", default="cfg/yourcfg.cfg", type=str)
@@ -76,7 +90,8 @@ def train_parser() -> argparse.ArgumentParser:
     ap.add_argument("--synthetic", type=int, default=0, help="train on N seeded synthetic patches instead of the .npy files")
     ap.add_argument("--max-steps", type=int, default=None)
     ap.add_argument("--eval-step", type=int, default=1000)
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3", "fp32", "fp32_rows"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "tf32", "tf32x3", "fp32", "fp32_rows"],
+                    help="auto = tf32x3 (error-compensated tensor cores: gradients inside the 1e-3 bar) where the row engine runs the graph, else fp32")
     return ap
 
 
@@ -101,7 +116,7 @@ def train_main(argv=None):
         y_train_mask, y_val_mask = ~np.ma.getmaskarray(y_train), ~np.ma.getmaskarray(y_val)          # True = clear (train.py:43-44)
         X_train, X_val, y_train, y_val = (np.asarray(np.ma.getdata(a), np.float32) for a in (X_train, X_val, y_train, y_val))
     logger.info("[ INFO ] Building model...")
-    model = build_from_config(config, band=opt.band, precision=opt.precision)
+    model = _build_model(config, opt.band, opt.precision, "tf32x3")
     target = config["scale"] * config["patch_size"]
     loss = Losses(targetShape=(target, target, 1))
     basename, ckptDir, logDir = _dirs(config, opt.cfg, opt.band)
@@ -126,7 +141,8 @@ def test_parser() -> argparse.ArgumentParser:
     ap.add_argument("--band", type=str, default="RED")
     ap.add_argument("--totest", type=str, default="TEST")
     ap.add_argument("--synthetic", type=int, default=0, help="predict N seeded synthetic 128x128 scenes instead of the .npy file")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "tf32x3", "fp32", "fp32_rows"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "tf32", "tf32x3", "fp32", "fp32_rows"],
+                    help="auto = tf32 (single-pass tensor cores: SR inside the 1e-3 bar) where the row engine runs the graph, else fp32")
     return ap
 
 
@@ -134,7 +150,7 @@ def test_main(argv=None):
     from . import build_from_config, evaluate, parseConfig, synth
     opt = test_parser().parse_args(argv)
     config = parseConfig(opt.cfg)
-    model = build_from_config(config, band=opt.band, precision=opt.precision)
+    model = _build_model(config, opt.band, opt.precision, "tf32")
     basename, ckptDir, _ = _dirs(config, opt.cfg, opt.band)
     try:
         info = model.restore_checkpoint(ckptDir)          # ckpt.restore(ckptMngr.latest_checkpoint), test.py:58-67

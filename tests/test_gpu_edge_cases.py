@@ -330,3 +330,22 @@ def test_64_filter_graph_with_sobel_l1_loss(small_cfg):
     worst = max(rel_err(grads[k], v.numpy()) for k, v in g.items() if np.abs(v.numpy()).max() > 0)
     print(f"F=64, sobel_l1_mix: worst gradient rel err {worst:.2e}")
     assert worst < 4e-3          # 3-patch batch with a sign-based loss: see test_forward_backward_with_raw_hr
+
+
+def test_cli_auto_precision_picks_the_engine_that_runs_the_graph():
+    """train.py / test.py --precision auto: the error-compensated (train) or single-pass (predict) tensor-core engine for the graphs the row
+    engine runs, the dense fp32 CUDA-core engine for the others (64 filters = BASELINE configs[4], 19 LR frames)."""
+    import probav_b200 as pb
+    from probav_b200 import cli
+    from probav_b200.models import PRECISION
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    base = pb.parseConfig(os.path.join(root, "cfg", "p16t9c85r12.cfg"))
+    base["num_res_blocks"] = 2
+    for cfg_over, preferred, want in (({}, "tf32x3", "tf32x3"), ({}, "tf32", "tf32"), ({"num_filters": 64}, "tf32x3", "fp32"),
+                                      ({"num_low_res_imgs": 19}, "tf32", "fp32")):
+        m = cli._build_model(dict(base, **cfg_over), "NIR", "auto", preferred)
+        assert m.cfg.precision == PRECISION[want], (cfg_over, preferred)
+        m.close()
+    m = cli._build_model(base, "NIR", "fp32_rows", "tf32x3")          # an explicit choice is taken as is
+    assert m.cfg.precision == PRECISION["fp32_rows"]
+    m.close()
