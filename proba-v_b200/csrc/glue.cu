@@ -176,15 +176,16 @@ __global__ void __launch_bounds__(128) wn_prep_kernel(const WnLayer* __restrict_
             weffT_lo[L.weffT_off + (long long)co * (L.taps * L.cin_s) + (long long)rt * L.cin_s + ci] = wf - w;
         }
         {
-            if (weffT_pack && L.mode == 1 && L.taps == 27 && L.cin_s == 32) {     // (also the single-pass engine: its inference convs read the hi halves)
-                // packed fp16 pair row of (co, tap): [ fp16(PACK_SCALE * w_lo) x 32 | fp16(w_hi) x 32 ] (rows.h) in the 128 bytes
-                // the 32 fp32 K-values of weffT occupy
-                __half* row = reinterpret_cast<__half*>(weffT_pack + L.weffT_off + (long long)co * (L.taps * L.cin_s) + (long long)rt * L.cin_s);
+            if (weffT_pack && L.mode == 1 && L.cin_s % 32 == 0) {     // (also the single-pass engine: its inference convs read the hi halves)
+                // packed fp16 pair row of (co, tap, 32-channel chunk of ci): [ fp16(PACK_SCALE * w_lo) x 32 | fp16(w_hi) x 32 ] (rows.h) in the
+                // 128 bytes the 32 fp32 K-values of weffT occupy (3x3x3 layers: one chunk per tap; decay layer: 8 chunks)
+                __half* row = reinterpret_cast<__half*>(weffT_pack + L.weffT_off + (long long)co * (L.taps * L.cin_s) + (long long)rt * L.cin_s + (ci / 32) * 32);
+                const int cw = ci % 32;
                 const __half w16 = __float2half_rn(w);                 // == w unless |w| is below fp16's normal range; the lo half absorbs that
                 const __half l16 = __float2half_rn((wf - __half2float(w16)) * PACK_SCALE);
-                row[ci] = l16;
-                row[32 + ci] = w16;
-                if (weff_pack && L.cout_s == 32) {     // the data gradient's bf16 pair, row (tap, ci), K = co (the layout of weff): [w_a | w - w_a]
+                row[cw] = l16;
+                row[32 + cw] = w16;
+                if (weff_pack && L.taps == 27 && L.cin_s == 32 && L.cout_s == 32) {     // the data gradient's bf16 pair, row (tap, ci), K = co (the layout of weff): [w_a | w - w_a]
                     __nv_bfloat16* rowd = reinterpret_cast<__nv_bfloat16*>(weff_pack + L.weff_off + ((long long)rt * L.cin_s + ci) * L.cout_s);
                     const __nv_bfloat16 wa = __float2bfloat16_rn(wf);
                     rowd[co] = wa;

@@ -47,7 +47,12 @@ struct ResX3Args {
 
 __device__ __forceinline__ uint32_t tf32_rn_bits(uint32_t bits) { return (bits + 0x1000u) & 0xffffe000u; }
 
-template <int TRAIN>
+// PACKD: the decay GEMM runs in kind::f16 on fp16 PAIRS.  The epilogue packs the activated quarter as [fp16(v) x 64 | fp16(2^12 (v - fp16(v))) x 64]
+// in place over its accumulator (two 16-bit values per TMEM column: 64 columns instead of the 128 of the tf32 pair), the decay weights
+// arrive as the fp16 pair rows of rows.h (tm_w2h then maps that array; tm_w2l is unused), and MMA2 is 12 K = 16 MMAs per quarter instead of
+// 24 K = 8 ones: E16 Wd_hi into the main accumulator, Elo16 Wd_hi + E16 2^12 Wd_lo into the correction accumulator (scaled back by 2^-12
+// in the final epilogue).  Half the tcgen05.st traffic and half the TMEM operand reads of MMA2.
+template <int TRAIN, bool PACKD>
 __global__ void __launch_bounds__(RX_THREADS, 1)
 resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
                        const __grid_constant__ CUtensorMap tm_w1h, const __grid_constant__ CUtensorMap tm_w1l,
@@ -86,12 +91,12 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
         if (elect_one_sync()) {
             tma_prefetch_desc(&tm_xh);
             tma_prefetch_desc(&tm_xl);
-            mbar_arrive_expect_tx(BAR(WBAR), 131072);
+            mbar_arrive_expect_tx(BAR(WBAR), PACKD ? 98304 : 131072);
             tma_load_2d(w1h_smem, &tm_w1h, BAR(WBAR), 0, 0);
             tma_load_2d(w1l_smem, &tm_w1l, BAR(WBAR), 0, 0);
             for (int j = 0; j < 8; ++j) {
                 tma_load_2d(w2h_smem + j * 4096, &tm_w2h, BAR(WBAR), 32 * j, 0);
-                tma_load_2d(w2l_smem + j * 4096, &tm_w2l, BAR(WBAR), 32 * j, 0);
+                if (!PACKD) tma_load_2d(w2l_smem + j * 4096, &tm_w2l, BAR(WBAR), 32 * j, 0);
             }
             pdl_wait();
             pdl_trigger();
@@ -142,7 +147,21 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                     // fp32 accumulator at every accumulation step (one ulp of the ACCUMULATOR, whatever the addend's size), so chaining the tiny
                     // corrections behind the main sum cost 64 extra truncations of the full-size value (D carried a -4.4e-6 scale error,
                     // profiles/r02_tf32_numerics_study.md); the correction accumulator is 2^-11 of the size and its truncations are harmless.
-                    const uint32_t d = tmem + 384 + 32 * db, dc = tmem + 448 + 32 * db, eh = tmem + eb * 128, el = eh + 64;
+                    const uint32_t d = tmem + 384 + 32 * db, dc = tmem + 448 + 32 * db, eh = tmem + eb * 128, el = eh + (PACKD ? 32 : 64);
+                    if (PACKD) {
+                        constexpr uint32_t IDESC2H = instr_desc(0, 128, 32, 0, 0);      // fp16 operands
+#pragma unroll
+                        for (int jl = 0; jl < 2; ++jl) {                // the quarter's two 32-channel chunks: 16 TMEM columns each
+                            const uint64_t bp = smem_desc(HI, w2h_smem + (uint32_t)(2 * q + jl) * 4096);     // row = [2^12 w_lo x 32 | w_hi x 32]
+#pragma unroll
+                            for (int t = 0; t < 2; ++t) {
+                                const uint32_t ac = (uint32_t)(jl * 16 + t * 8);
+                                umma_ts<false>(d, eh + ac, bp + 2 * (2 + t), IDESC2H, (q > 0 || jl > 0 || t > 0) ? 1u : 0u);
+                                umma_ts<false>(dc, el + ac, bp + 2 * (2 + t), IDESC2H, (q > 0 || jl > 0 || t > 0) ? 1u : 0u);
+                                umma_ts<false>(dc, eh + ac, bp + 2 * t, IDESC2H, 1u);
+                            }
+                        }
+                    } else
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint32_t off = (uint32_t)(2 * q + (ks >> 2)) * 4096;
@@ -179,13 +198,14 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                 mbar_wait(BAR(EFULL + grp * 4 + q), tph);
                 tc_fence_after();
                 uint32_t va[32], vb[32];
+                uint32_t ph[PACKD ? 32 : 1], pl[PACKD ? 32 : 1];      // PACKD: the quarter as fp16 pairs, two channels per word
                 tmem_ld32(hb, va);
                 tmem_ld32(hb + 32, vb);
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     if (c == 0) tmem_ld_wait();               // both loads are complete after the first wait
                     uint32_t (&cur)[32] = c ? vb : va;
-                    uint32_t lo[32];
+                    uint32_t lo[PACKD ? 1 : 32];
                     uint32_t sg[4] = {0u, 0u, 0u, 0u};
                     uint32_t colbits = 0u;                    // TRAIN: lane e keeps the row bit-vector of channel e of this chunk
                     const float4* be4 = reinterpret_cast<const float4*>(s_b1 + q * 64 + c * 32);
@@ -200,13 +220,29 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                             // (bits(v) - 1) has its sign bit set exactly when v == 0, i.e. when the pre-activation is <= 0
                             // (tf.nn.relu's gradient convention)
                             if (TRAIN) sg[e4 >> 1] = __funnelshift_l(x - 1u, sg[e4 >> 1], 1);
-                            const uint32_t h = tf32_rn_bits(x);
-                            cur[e4 * 4 + e] = h;
-                            lo[e4 * 4 + e] = __float_as_uint(v - __uint_as_float(h));
+                            if constexpr (PACKD) {
+                                cur[e4 * 4 + e] = x;
+                            } else {
+                                const uint32_t h = tf32_rn_bits(x);
+                                cur[e4 * 4 + e] = h;
+                                lo[e4 * 4 + e] = __float_as_uint(v - __uint_as_float(h));
+                            }
                         }
                     }
-                    tmem_st32(hb + c * 32, cur);
-                    tmem_st32(hb + 64 + c * 32, lo);
+                    if constexpr (PACKD) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {        // channels 2k, 2k + 1 of this chunk -> one word each of the hi and lo halves
+                            const float v0 = __uint_as_float(cur[2 * k]), v1 = __uint_as_float(cur[2 * k + 1]);
+                            const __half2 h2 = __floats2half2_rn(v0, v1);
+                            const float2 hf = __half22float2(h2);
+                            const __half2 l2 = __floats2half2_rn((v0 - hf.x) * PACK_SCALE, (v1 - hf.y) * PACK_SCALE);
+                            ph[c * 16 + k] = *reinterpret_cast<const uint32_t*>(&h2);
+                            pl[c * 16 + k] = *reinterpret_cast<const uint32_t*>(&l2);
+                        }
+                    } else {
+                        tmem_st32(hb + c * 32, cur);
+                        tmem_st32(hb + 64 + c * 32, lo);
+                    }
                     if (TRAIN) {                              // word q * 2 + c of the row's mask (static register indexing under the rolled loop)
                         const uint32_t word = ~((sg[0] << 24) | ((sg[1] & 0xffu) << 16) | ((sg[2] & 0xffu) << 8) | (sg[3] & 0xffu));
                         // 32 x 32 bit-matrix transpose across the warp (lane = row, bit 31 - e = channel e  ->  lane = channel, bit k = row k):
@@ -224,6 +260,10 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                         // transposed copy: one coalesced 128-byte store per (32 rows x 32 channels)
                         if (a.mask_t) a.mask_t[((size_t)tile * 4 + q4) * 256 + q * 64 + c * 32 + lane] = colbits;
                     }
+                }
+                if constexpr (PACKD) {
+                    tmem_st32(hb, ph);                        // in place over the accumulator (both halves of it are in registers)
+                    tmem_st32(hb + 32, pl);
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -246,7 +286,8 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(DFREE + db));
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(vc[c]));   // main + corrections, rounded to nearest
+            for (int c = 0; c < 32; ++c)              // main + corrections (PACKD: 2^12-scaled), rounded to nearest
+                v[c] = __float_as_uint(PACKD ? fmaf(__uint_as_float(vc[c]), 1.0f / PACK_SCALE, __uint_as_float(v[c])) : __uint_as_float(v[c]) + __uint_as_float(vc[c]));
             float hi[32], lo[32];
 #pragma unroll
             for (int g4 = 0; g4 < 8; ++g4) {
@@ -293,7 +334,7 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
 int launch_resfront_fwd_x3_tc(const float* x_hi, const float* x_lo, const float* weT_exp_hi, const float* weT_exp_lo,
                               const float* weT_dec_hi, const float* weT_dec_lo, const float* bias_e, const float* bias_d,
                               float* d_hi, float* d_lo, uint32_t* relu_bits, uint32_t* relu_bits_t, const RowGeom& g, int B, double flops,
-                              cudaStream_t st, int pack_out) {
+                              cudaStream_t st, int pack_out, const float* weT_dec_pack) {
     ResX3Args a;
     memset(&a, 0, sizeof a);
     a.B = B; a.g = g; a.bias1 = bias_e; a.bias2 = bias_d; a.mask = relu_bits; a.mask_t = relu_bits_t; a.out_hi = d_hi; a.out_lo = d_lo; a.pack_out = pack_out;
@@ -304,7 +345,7 @@ int launch_resfront_fwd_x3_tc(const float* x_hi, const float* x_lo, const float*
     PV_TRY(make_tmap_2d(&tm_xl, x_lo, rows, 32, 128, 32, 0));
     PV_TRY(make_tmap_2d(&tm_w1h, weT_exp_hi, 256, 32, 256, 32, 0));
     PV_TRY(make_tmap_2d(&tm_w1l, weT_exp_lo, 256, 32, 256, 32, 0));
-    PV_TRY(make_tmap_2d(&tm_w2h, weT_dec_hi, 32, 256, 32, 32, 0));
+    PV_TRY(make_tmap_2d(&tm_w2h, weT_dec_pack ? weT_dec_pack : weT_dec_hi, 32, 256, 32, 32, 0));
     PV_TRY(make_tmap_2d(&tm_w2l, weT_dec_lo, 32, 256, 32, 32, 0));
     const size_t smem = 1024 + 131072 + 2 * 32768 + 8 * ROWIO_SCRATCH_BYTES;
     int dev = 0, sms = 148;
@@ -314,15 +355,14 @@ int launch_resfront_fwd_x3_tc(const float* x_hi, const float* x_lo, const float*
     const int grid = ntiles < sms ? ntiles : sms;
     // executed: three MMAs per product on the padded 32 x 256 shapes, both GEMMs
     PV_TIMED(relu_bits ? "resfront_fwd_x3" : "resfront_fwd_x3_infer", st, flops, 0.0, 3.0 * 2.0 * 2.0 * (double)ntiles * 128.0 * 32.0 * 256.0);
-    if (relu_bits) {
-        static size_t attr[16] = {};
-        PV_CUDA(ensure_dyn_smem(resfront_fwd_x3_kernel<1>, smem, attr));
-        PV_CUDA(launch_pdl(resfront_fwd_x3_kernel<1>, grid, RX_THREADS, smem, st, tm_xh, tm_xl, tm_w1h, tm_w1l, tm_w2h, tm_w2l, a));
-    } else {
-        static size_t attr[16] = {};
-        PV_CUDA(ensure_dyn_smem(resfront_fwd_x3_kernel<0>, smem, attr));
-        PV_CUDA(launch_pdl(resfront_fwd_x3_kernel<0>, grid, RX_THREADS, smem, st, tm_xh, tm_xl, tm_w1h, tm_w1l, tm_w2h, tm_w2l, a));
-    }
+    static size_t attr[4][16] = {};
+    auto go = [&](auto kern, size_t (&at)[16]) -> int {
+        PV_CUDA(ensure_dyn_smem(kern, smem, at));
+        PV_CUDA(launch_pdl(kern, grid, RX_THREADS, smem, st, tm_xh, tm_xl, tm_w1h, tm_w1l, tm_w2h, tm_w2l, a));
+        return 0;
+    };
+    if (relu_bits) PV_TRY(weT_dec_pack ? go(resfront_fwd_x3_kernel<1, true>, attr[0]) : go(resfront_fwd_x3_kernel<1, false>, attr[1]));
+    else PV_TRY(weT_dec_pack ? go(resfront_fwd_x3_kernel<0, true>, attr[2]) : go(resfront_fwd_x3_kernel<0, false>, attr[3]));
     PV_LAUNCH_CHECK();
     return 0;
 }
