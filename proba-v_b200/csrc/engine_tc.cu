@@ -639,11 +639,9 @@ static int selftest_x3(std::string& rep) {
         pd.in_lead = pr.lead; pd.in_pstride = pr.pstride; pd.og = pr; pd.ntap = 8; pd.kc = 32;
         for (int j = 0; j < 8; ++j) { pd.c0[j] = 32 * j; pd.wr0[j] = 32 * j; }
         if (!rc) rc = launch_rowconv_simt(pd, 0);
-        for (int v4 = 0; v4 < 4 && !rc; ++v4) {           // (inference | training) x (decay GEMM on tf32 pairs | on fp16 pairs in TMEM)
-            const int variant = v4 & 1, packd = v4 >> 1;
+        for (int variant = 0; variant < 2 && !rc; ++variant) {
             PV_CUDA(cudaMemset(dh, 0, rows * 128)); PV_CUDA(cudaMemset(dl, 0, rows * 128));
-            rc = launch_resfront_fwd_x3_tc(X.hi, X.lo, WE.hi, WE.lo, WD.hi, WD.lo, be_d, bd_d, dh, dl, variant ? bits : nullptr, variant ? bits_t : nullptr, pr, B, 0.0, 0, variant,
-                                           packd ? WD.pack : nullptr);
+            rc = launch_resfront_fwd_x3_tc(X.hi, X.lo, WE.hi, WE.lo, WD.pack, be_d, bd_d, dh, dl, variant ? bits : nullptr, variant ? bits_t : nullptr, pr, B, 0.0, 0, variant);
             if (!rc && variant) {       // the training variant writes packed fp16 pair rows: decode the lo half back to fp32 for the comparison
                 if (cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest x3 resfront: %s", cudaGetErrorString(cudaGetLastError()));
                 std::vector<__half> pk(rows * 64);
@@ -657,8 +655,7 @@ static int selftest_x3(std::string& rep) {
                 cudaMemcpy(dl, ll.data(), rows * 128, cudaMemcpyHostToDevice);
             }
             if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = set_error(PV_ERR_CUDA, "selftest x3 resfront: %s", cudaGetErrorString(cudaGetLastError()));
-            if (!rc) fails += compare(packd ? (variant ? "x3 fused fwd, fp16 decay (train)" : "x3 fused fwd, fp16 decay (infer)")
-                                            : (variant ? "x3 fused exp->relu->dec (train)" : "x3 fused exp->relu->dec (infer)"), d0, dh, dl, rows * 32, 2e-5);
+            if (!rc) fails += compare(variant ? "x3 fused exp->relu->dec (train)" : "x3 fused exp->relu->dec (infer)", d0, dh, dl, rows * 32, 2e-5);
         }
         if (!rc) {      // the ReLU bit mask against the fp32 expanded tensor (bit 31 - e of word c / 32 <=> E[row][c] > 0)
             std::vector<float> Eh(rows * 256);
@@ -903,18 +900,16 @@ static int tc_forward_x3(pv_model* m, int B, float* sr, bool tr, int clip_round,
     const std::vector<TailStep> tail = tail_plan(m);
     const RowGeom ug = g_dims(1, m->P, m->P);
     auto alo = [&](int i) { return P[(i & 1) ? "a_lo1" : "a_lo0"]; };
-    static const bool x3_tf32_decay = getenv("PV_X3_TF32_DECAY") != nullptr;       // A/B: the decay GEMM on tf32 pairs (previous version)
     const Layer& L0 = m->layers[m->li("mainConv1")];
     PV_TRY(launch_first_conv_pr(P["xn"], m->weff + L0.weff_off, m->bias_s + L0.bias_s_off, B, m->S, m->T, P[m->A(0, tr)], pr, st, alo(0)));
     for (int i = 0; i < m->R; ++i) {                                   // ResConv3D, modelsTF.py:177-189
         const int e = m->li("expConv_" + std::to_string(i));
         const Layer &Le = m->layers[e], &Ld = m->layers[e + 1];
         const double fl = 2.0 * B * Le.Ho * Le.Wo * Le.To * ((double)Le.cin * Le.cout + (double)Ld.cin * Ld.cout);
-        PV_TRY(launch_resfront_fwd_x3_tc(P[m->A(i, tr)], alo(i), m->weffT + Le.weff_off, m->weffT_lo + Le.weff_off, m->weffT + Ld.weff_off,
-                                         m->weffT_lo + Ld.weff_off, m->bias_s + Le.bias_s_off, m->bias_s + Ld.bias_s_off, P[m->D(i, tr)], P["D_pack"],
+        PV_TRY(launch_resfront_fwd_x3_tc(P[m->A(i, tr)], alo(i), m->weffT + Le.weff_off, m->weffT_lo + Le.weff_off, m->weffT_pack + Ld.weff_off,
+                                         m->bias_s + Le.bias_s_off, m->bias_s + Ld.bias_s_off, P[m->D(i, tr)], P["D_pack"],
                                          tr ? reinterpret_cast<uint32_t*>(P["M" + std::to_string(i)]) : nullptr,
-                                         tr ? reinterpret_cast<uint32_t*>(P["MT" + std::to_string(i)]) : nullptr, pr, B, fl, st, 1,
-                                         x3_tf32_decay ? nullptr : m->weffT_pack + Ld.weff_off));
+                                         tr ? reinterpret_cast<uint32_t*>(P["MT" + std::to_string(i)]) : nullptr, pr, B, fl, st, 1));
         PV_TRY(conv_rows_x3(m, m->layers[e + 2], same, P["D_pack"], pr, P[m->A(i + 1, tr)], alo(i + 1), nullptr, pr, P[m->A(i, tr)], alo(i), B,
                             "norm_fwd_x3", st));
     }

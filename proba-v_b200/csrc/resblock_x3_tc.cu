@@ -8,15 +8,13 @@
 // truncated to tf32 by the tensor core: 2^-21 overall), and every product is
 //        x w  ~=  x_hi w_hi + x_lo w_hi + x_hi w_lo                     (three kind::tf32 MMAs into one fp32 accumulator).
 //
-// Per 128-row tile and per QUARTER q of the 256 expanded channels (64 channels; the E_hi | E_lo pair of a quarter takes
-// 128 TMEM columns, so three unit buffers + two output accumulators fit the 512 columns):
-//     MMA1 (SS, N = 64)  E_q = X_hi We_hi,q^T + X_lo We_hi,q^T + X_hi We_lo,q^T            12 MMAs
-//     epilogue           v = relu(E_q + be);  ReLU bit mask;  E_hi <- tf32(v) in place,  E_lo <- v - tf32(v) next to it
-//     MMA2 (TS, N = 32)  D += E_hi Wd_hi,q^T + E_lo Wd_hi,q^T + E_hi Wd_lo,q^T             24 MMAs
-//     final              D + bd -> (hi, lo) -> two row arrays
-// Pipelining as in resblock_tc.cu: the MMA thread issues MMA1 of unit u+1 before MMA2 of unit u; tcgen05 operations execute in
-// issue order, which is what makes re-using a unit buffer three units later safe.  Two epilogue groups of four warps take
-// alternate tiles.  mbarrier rule (profiles/r01_next_round_notes.md): a parity wait is only correct if the waiter sees EVERY
+// Per 128-row tile and per QUARTER q of the 256 expanded channels (64 channels; three unit buffers + 2 x 2 output accumulators):
+//     MMA1 (SS, kind::tf32, N = 64)  E_q = X_hi We_hi,q^T + X_lo We_hi,q^T + X_hi We_lo,q^T              12 MMAs
+//     epilogue   v = relu(E_q + be);  ReLU bit mask;  fp16 pair [fp16(v) | fp16(2^12 (v - fp16(v)))] in place, 2 values per TMEM column
+//     MMA2 (TS, kind::f16, N = 32)   D += E16 Wd_hi,q^T;   Dc += Elo16 Wd_hi,q^T + E16 (2^12 Wd_lo,q)^T     12 MMAs
+//     final      D + 2^-12 Dc + bd -> (hi, lo) -> two row arrays (the lo array as packed fp16 pair rows when a 3x3x3 conv reads it)
+// Pipelining: the MMA thread issues MMA1 ahead of MMA2 (see the issue order there); tcgen05 operations execute in issue order,
+// which is what makes re-using a unit buffer three units later safe.  Two epilogue groups of four warps take alternate tiles.  mbarrier rule (profiles/r01_next_round_notes.md): a parity wait is only correct if the waiter sees EVERY
 // phase of its barrier, so the "E ready" barriers are indexed by (group, quarter): one waiting group, consecutive phases.
 #include <cuda_fp16.h>
 
@@ -32,6 +30,7 @@ int make_tmap_2d(CUtensorMap* m, const float* base, long long rows, int cols, in
 namespace {
 
 constexpr int RX_THREADS = 320;
+constexpr int RX_STAGES = 3;
 
 struct ResX3Args {
     int B, tiles_per_patch;
@@ -47,31 +46,32 @@ struct ResX3Args {
 
 __device__ __forceinline__ uint32_t tf32_rn_bits(uint32_t bits) { return (bits + 0x1000u) & 0xffffe000u; }
 
-// PACKD: the decay GEMM runs in kind::f16 on fp16 PAIRS.  The epilogue packs the activated quarter as [fp16(v) x 64 | fp16(2^12 (v - fp16(v))) x 64]
-// in place over its accumulator (two 16-bit values per TMEM column: 64 columns instead of the 128 of the tf32 pair), the decay weights
-// arrive as the fp16 pair rows of rows.h (tm_w2h then maps that array; tm_w2l is unused), and MMA2 is 12 K = 16 MMAs per quarter instead of
-// 24 K = 8 ones: E16 Wd_hi into the main accumulator, Elo16 Wd_hi + E16 2^12 Wd_lo into the correction accumulator (scaled back by 2^-12
-// in the final epilogue).  Half the tcgen05.st traffic and half the TMEM operand reads of MMA2.
-template <int TRAIN, bool PACKD>
+// The decay GEMM runs in kind::f16 on fp16 PAIRS: the epilogue packs the activated quarter as [fp16(v) x 64 | fp16(2^12 (v - fp16(v))) x 64]
+// in place over its accumulator (two 16-bit values per TMEM column, the even channel in the low half: 64 columns), the decay weights
+// arrive as the fp16 pair rows of rows.h, and MMA2 is 12 K = 16 MMAs per quarter: E16 Wd_hi into the main accumulator,
+// Elo16 Wd_hi + E16 2^12 Wd_lo into the correction accumulator (scaled back by 2^-12 in the final epilogue).
+// ILV: issue order of the quarter units (see the MMA thread).
+template <int TRAIN, bool ILV>
 __global__ void __launch_bounds__(RX_THREADS, 1)
 resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
                        const __grid_constant__ CUtensorMap tm_w1h, const __grid_constant__ CUtensorMap tm_w1l,
-                       const __grid_constant__ CUtensorMap tm_w2h, const __grid_constant__ CUtensorMap tm_w2l, const ResX3Args a) {
+                       const __grid_constant__ CUtensorMap tm_w2p, const ResX3Args a) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[20];
+    __shared__ __align__(8) uint64_t bars[22];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float s_b1[256];
     __shared__ __align__(16) float s_b2[32];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t w1h_smem = base, w1l_smem = base + 32768;            // [256 rows x 128 B] each
-    const uint32_t w2h_smem = base + 65536, w2l_smem = base + 98304;    // 8 K-chunks x [32 rows x 128 B] each
-    const uint32_t x_smem = base + 131072;                              // 2 stages x { X_hi, X_lo } x [128 rows x 128 B]
-    uint8_t* const io_scratch = smem_raw + (base - smem_u32(smem_raw)) + 131072 + 2 * 32768;   // 8 epilogue warps x 2 KB (rowio.cuh)
+    const uint32_t w2p_smem = base + 65536;                             // 8 K-chunks x [32 rows x 128 B]: fp16 pair rows [2^12 w_lo x 32 | w_hi x 32]
+    const uint32_t x_smem = base + 98304;                               // RX_STAGES x { X_hi, X_lo } x [128 rows x 128 B]
+    uint8_t* const io_scratch = smem_raw + (base - smem_u32(smem_raw)) + 98304 + RX_STAGES * 32768;   // 8 epilogue warps x 2 KB (rowio.cuh)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto BAR = [&](int i) { return smem_u32(&bars[i]); };
-    const int FULL = 0, EMPTY = 2, WBAR = 4, EFULL = 5, EREADY = 13, DFULL = 16, DFREE = 18;
+    const int FULL = 0, EMPTY = 3, WBAR = 6, EFULL = 7, EREADY = 15, DFULL = 18, DFREE = 20;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); mbar_init(BAR(DFULL + i), 1); mbar_init(BAR(DFREE + i), 4); }
+        for (int i = 0; i < RX_STAGES; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(DFULL + i), 1); mbar_init(BAR(DFREE + i), 4); }
         for (int i = 0; i < 8; ++i) mbar_init(BAR(EFULL + i), 1);
         for (int i = 0; i < 3; ++i) mbar_init(BAR(EREADY + i), 4);
         mbar_init(BAR(WBAR), 1);
@@ -91,20 +91,17 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
         if (elect_one_sync()) {
             tma_prefetch_desc(&tm_xh);
             tma_prefetch_desc(&tm_xl);
-            mbar_arrive_expect_tx(BAR(WBAR), PACKD ? 98304 : 131072);
+            mbar_arrive_expect_tx(BAR(WBAR), 98304);
             tma_load_2d(w1h_smem, &tm_w1h, BAR(WBAR), 0, 0);
             tma_load_2d(w1l_smem, &tm_w1l, BAR(WBAR), 0, 0);
-            for (int j = 0; j < 8; ++j) {
-                tma_load_2d(w2h_smem + j * 4096, &tm_w2h, BAR(WBAR), 32 * j, 0);
-                if (!PACKD) tma_load_2d(w2l_smem + j * 4096, &tm_w2l, BAR(WBAR), 32 * j, 0);
-            }
+            for (int j = 0; j < 8; ++j) tma_load_2d(w2p_smem + j * 4096, &tm_w2p, BAR(WBAR), 32 * j, 0);
             pdl_wait();
             pdl_trigger();
             for (int tl = 0; tl < my_tiles; ++tl) {
                 const int tile = blockIdx.x + tl * gridDim.x;
                 const int b = tile / a.tiles_per_patch, j = tile % a.tiles_per_patch;
                 const long long row0 = a.g.lead + (long long)b * a.g.pstride + a.g.row0 + j * 128;
-                const uint32_t stg = tl & 1, ph = (tl >> 1) & 1;
+                const uint32_t stg = tl % RX_STAGES, ph = (tl / RX_STAGES) & 1;
                 mbar_wait(BAR(EMPTY + stg), ph ^ 1);
                 mbar_arrive_expect_tx(BAR(FULL + stg), 32768);
                 tma_load_2d(x_smem + stg * 32768, &tm_xh, BAR(FULL + stg), 0, (int)row0);
@@ -116,14 +113,28 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
             constexpr uint64_t HI = smem_desc_hi(16, 1024, 2);
             constexpr uint32_t HI32 = (uint32_t)(HI >> 32), LO32 = (uint32_t)HI;
             constexpr uint32_t IDESC1 = instr_desc(2, 128, 64, 0, 0);
-            constexpr uint32_t IDESC2 = instr_desc(2, 128, 32, 0, 0);
+            constexpr uint32_t IDESC2 = instr_desc(0, 128, 32, 0, 0);       // fp16 operands (A from TMEM), N = 32
             mbar_wait(BAR(WBAR), 0);
             tc_fence_after();
+            // Issue order of the quarter units.  Sequential (ILV = false): tile after tile, MMA1 one unit ahead of MMA2; the epilogue group of
+            // the NEXT tile then gets its first unit only while this tile's last quarter is in the epilogue (ncu: 20 % of the stall samples sit
+            // on that wait).  Interleaved (ILV = true): the units of a PAIR of tiles alternate (A0 B0 A1 B1 ... A3 B3, A = even tile = epilogue
+            // group 0, B = odd tile = group 1) with MMA1 two units ahead: each group finds its next unit computed while its own current unit
+            // and the other group's occupy the other two buffers.  Both tiles of a pair are then in flight at once, hence three X stages.
             const int U = 4 * my_tiles;
-            for (int u = 0; u <= U; ++u) {
-                if (u < U) {                        // MMA1 of unit u
-                    const int tl = u >> 2, q = u & 3;
-                    const uint32_t stg = tl & 1, ph = (tl >> 1) & 1, eb = u % 3;
+            constexpr int LA = ILV ? 2 : 1;
+            auto unit_of = [&](int n, int& tl, int& q) {
+                if (ILV) {
+                    const int p = n >> 3, r = n & 7;
+                    if (2 * p + 1 < my_tiles) { tl = 2 * p + (r & 1); q = r >> 1; }
+                    else { tl = 2 * p; q = r; }                 // the last, unpaired tile: its four units in a row
+                } else { tl = n >> 2; q = n & 3; }
+            };
+            for (int n = 0; n < U + LA; ++n) {
+                if (n < U) {                        // MMA1 of unit n
+                    int tl, q;
+                    unit_of(n, tl, q);
+                    const uint32_t stg = tl % RX_STAGES, ph = (tl / RX_STAGES) & 1, eb = n % 3;
                     if (q == 0) { mbar_wait(BAR(FULL + stg), ph); tc_fence_after(); }
                     const uint32_t xh = ((x_smem + stg * 32768) >> 4) | LO32, xl = ((x_smem + stg * 32768 + 16384) >> 4) | LO32;
                     const uint32_t wh = ((w1h_smem + q * 8192) >> 4) | LO32, wl = ((w1l_smem + q * 8192) >> 4) | LO32;
@@ -137,38 +148,29 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                     if (q == 3) umma_commit(BAR(EMPTY + stg));
                     umma_commit(BAR(EFULL + (tl & 1) * 4 + q));
                 }
-                if (u >= 1) {                       // MMA2 of unit u - 1
-                    const int v = u - 1, tl = v >> 2, q = v & 3;
+                if (n >= LA) {                      // MMA2 of unit n - LA
+                    const int v = n - LA;
+                    int tl, q;
+                    unit_of(v, tl, q);
                     const uint32_t eb = v % 3, db = tl & 1;
                     mbar_wait(BAR(EREADY + eb), (v / 3) & 1);
                     tc_fence_after();
                     if (q == 0) { mbar_wait(BAR(DFREE + db), ((tl >> 1) & 1) ^ 1); tc_fence_after(); }
-                    // Two accumulators per tile: the 32-step main chain E_hi Wd_hi and the 64-step correction chain.  tcgen05 truncates the
-                    // fp32 accumulator at every accumulation step (one ulp of the ACCUMULATOR, whatever the addend's size), so chaining the tiny
-                    // corrections behind the main sum cost 64 extra truncations of the full-size value (D carried a -4.4e-6 scale error,
-                    // profiles/r02_tf32_numerics_study.md); the correction accumulator is 2^-11 of the size and its truncations are harmless.
-                    const uint32_t d = tmem + 384 + 32 * db, dc = tmem + 448 + 32 * db, eh = tmem + eb * 128, el = eh + (PACKD ? 32 : 64);
-                    if (PACKD) {
-                        constexpr uint32_t IDESC2H = instr_desc(0, 128, 32, 0, 0);      // fp16 operands
+                    // Two accumulators per tile: the main chain E16 Wd_hi and the correction chain.  tcgen05 truncates the fp32 accumulator at
+                    // every accumulation step (one ulp of the ACCUMULATOR, whatever the addend's size), so chaining the tiny corrections behind
+                    // the main sum would cost a truncation of the full-size value per correction step (profiles/r02_tf32_numerics_study.md);
+                    // the correction accumulator is 2^-11 of the size (before its 2^12 scale) and its truncations are harmless.
+                    const uint32_t d = tmem + 384 + 32 * db, dc = tmem + 448 + 32 * db, eh = tmem + eb * 128, el = eh + 32;
 #pragma unroll
-                        for (int jl = 0; jl < 2; ++jl) {                // the quarter's two 32-channel chunks: 16 TMEM columns each
-                            const uint64_t bp = smem_desc(HI, w2h_smem + (uint32_t)(2 * q + jl) * 4096);     // row = [2^12 w_lo x 32 | w_hi x 32]
+                    for (int jl = 0; jl < 2; ++jl) {                // the quarter's two 32-channel chunks: 16 TMEM columns each
+                        const uint64_t bp = smem_desc(HI, w2p_smem + (uint32_t)(2 * q + jl) * 4096);     // row = [2^12 w_lo x 32 | w_hi x 32]
 #pragma unroll
-                            for (int t = 0; t < 2; ++t) {
-                                const uint32_t ac = (uint32_t)(jl * 16 + t * 8);
-                                umma_ts<false>(d, eh + ac, bp + 2 * (2 + t), IDESC2H, (q > 0 || jl > 0 || t > 0) ? 1u : 0u);
-                                umma_ts<false>(dc, el + ac, bp + 2 * (2 + t), IDESC2H, (q > 0 || jl > 0 || t > 0) ? 1u : 0u);
-                                umma_ts<false>(dc, eh + ac, bp + 2 * t, IDESC2H, 1u);
-                            }
+                        for (int t = 0; t < 2; ++t) {
+                            const uint32_t ac = (uint32_t)(jl * 16 + t * 8);
+                            umma_ts<false>(d, eh + ac, bp + 2 * (2 + t), IDESC2, (q > 0 || jl > 0 || t > 0) ? 1u : 0u);
+                            umma_ts<false>(dc, el + ac, bp + 2 * (2 + t), IDESC2, (q > 0 || jl > 0 || t > 0) ? 1u : 0u);
+                            umma_ts<false>(dc, eh + ac, bp + 2 * t, IDESC2, 1u);
                         }
-                    } else
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        const uint32_t off = (uint32_t)(2 * q + (ks >> 2)) * 4096;
-                        const uint64_t bh = smem_desc(HI, w2h_smem + off) + 2 * (ks & 3), bl = smem_desc(HI, w2l_smem + off) + 2 * (ks & 3);
-                        umma_ts<true>(d, eh + ks * 8, bh, IDESC2, (q > 0 || ks > 0) ? 1u : 0u);
-                        umma_ts<true>(dc, el + ks * 8, bh, IDESC2, (q > 0 || ks > 0) ? 1u : 0u);
-                        umma_ts<true>(dc, eh + ks * 8, bl, IDESC2, 1u);
                     }
                     if (q == 3) umma_commit(BAR(DFULL + db));
                 }
@@ -193,19 +195,19 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
             uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll 1
             for (int q = 0; q < 4; ++q) {                     // rolled: the unrolled body thrashes the instruction cache
-                const int u = 4 * tl + q;
+                // position of this unit in the MMA thread's issue order (unit_of there)
+                const int u = !ILV ? 4 * tl + q : ((tl | 1) < my_tiles ? 8 * (tl >> 1) + 2 * q + (tl & 1) : 8 * (tl >> 1) + q);
                 const uint32_t eb = u % 3, hb = lane_base + eb * 128;
                 mbar_wait(BAR(EFULL + grp * 4 + q), tph);
                 tc_fence_after();
                 uint32_t va[32], vb[32];
-                uint32_t ph[PACKD ? 32 : 1], pl[PACKD ? 32 : 1];      // PACKD: the quarter as fp16 pairs, two channels per word
+                uint32_t ph[32], pl[32];                      // the quarter as fp16 pairs, two channels per word
                 tmem_ld32(hb, va);
                 tmem_ld32(hb + 32, vb);
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     if (c == 0) tmem_ld_wait();               // both loads are complete after the first wait
                     uint32_t (&cur)[32] = c ? vb : va;
-                    uint32_t lo[PACKD ? 1 : 32];
                     uint32_t sg[4] = {0u, 0u, 0u, 0u};
                     uint32_t colbits = 0u;                    // TRAIN: lane e keeps the row bit-vector of channel e of this chunk
                     const float4* be4 = reinterpret_cast<const float4*>(s_b1 + q * 64 + c * 32);
@@ -220,16 +222,10 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                             // (bits(v) - 1) has its sign bit set exactly when v == 0, i.e. when the pre-activation is <= 0
                             // (tf.nn.relu's gradient convention)
                             if (TRAIN) sg[e4 >> 1] = __funnelshift_l(x - 1u, sg[e4 >> 1], 1);
-                            if constexpr (PACKD) {
-                                cur[e4 * 4 + e] = x;
-                            } else {
-                                const uint32_t h = tf32_rn_bits(x);
-                                cur[e4 * 4 + e] = h;
-                                lo[e4 * 4 + e] = __float_as_uint(v - __uint_as_float(h));
-                            }
+                            cur[e4 * 4 + e] = x;
                         }
                     }
-                    if constexpr (PACKD) {
+                    {
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {        // channels 2k, 2k + 1 of this chunk -> one word each of the hi and lo halves
                             const float v0 = __uint_as_float(cur[2 * k]), v1 = __uint_as_float(cur[2 * k + 1]);
@@ -239,9 +235,6 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                             ph[c * 16 + k] = *reinterpret_cast<const uint32_t*>(&h2);
                             pl[c * 16 + k] = *reinterpret_cast<const uint32_t*>(&l2);
                         }
-                    } else {
-                        tmem_st32(hb + c * 32, cur);
-                        tmem_st32(hb + 64 + c * 32, lo);
                     }
                     if (TRAIN) {                              // word q * 2 + c of the row's mask (static register indexing under the rolled loop)
                         const uint32_t word = ~((sg[0] << 24) | ((sg[1] & 0xffu) << 16) | ((sg[2] & 0xffu) << 8) | (sg[3] & 0xffu));
@@ -261,10 +254,8 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                         if (a.mask_t) a.mask_t[((size_t)tile * 4 + q4) * 256 + q * 64 + c * 32 + lane] = colbits;
                     }
                 }
-                if constexpr (PACKD) {
-                    tmem_st32(hb, ph);                        // in place over the accumulator (both halves of it are in registers)
-                    tmem_st32(hb + 32, pl);
-                }
+                tmem_st32(hb, ph);                            // in place over the accumulator (both halves of it are in registers)
+                tmem_st32(hb + 32, pl);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -286,8 +277,8 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(DFREE + db));
 #pragma unroll
-            for (int c = 0; c < 32; ++c)              // main + corrections (PACKD: 2^12-scaled), rounded to nearest
-                v[c] = __float_as_uint(PACKD ? fmaf(__uint_as_float(vc[c]), 1.0f / PACK_SCALE, __uint_as_float(v[c])) : __uint_as_float(v[c]) + __uint_as_float(vc[c]));
+            for (int c = 0; c < 32; ++c)              // main + 2^-12 corrections, rounded to nearest
+                v[c] = __float_as_uint(fmaf(__uint_as_float(vc[c]), 1.0f / PACK_SCALE, __uint_as_float(v[c])));
             float hi[32], lo[32];
 #pragma unroll
             for (int g4 = 0; g4 < 8; ++g4) {
@@ -326,43 +317,44 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
 }  // namespace
 
 // (D_hi, D_lo) = split(decConv(relu(expConv(X_hi + X_lo)))) on PR rows with compensated products.
-//   weT_exp_* [256][32], weT_dec_* [32][256] (K contiguous; hi = tf32(w), lo = w - hi), biases padded to 256 / 32.
+//   weT_exp_* [256][32] (K contiguous; hi = tf32(w), lo = w - hi), weT_dec_pack [32][256] as fp16 pair rows per 32-channel chunk
+//   (rows.h: [2^12 w_lo x 32 | w_hi x 32]), biases padded to 256 / 32.
 //   relu_bits (nullable): [rows][8] uint32 in resblock_tc.cu's format (consumed by the backward-data kernel).
 //   relu_bits_t (nullable): the same bits transposed, [tile][4][256] uint32 with bit k = row 32 * block + k of the tile, for the
 //   weight-gradient kernel (whose threads own channels): it must use the FORWARD's mask -- its own single-pass recomputation of E
 //   disagrees with the compensated forward on ~1e-4 of the elements, which alone is a ~1e-2 error on dWe (sqrt law).
 int launch_resfront_fwd_x3_tc(const float* x_hi, const float* x_lo, const float* weT_exp_hi, const float* weT_exp_lo,
-                              const float* weT_dec_hi, const float* weT_dec_lo, const float* bias_e, const float* bias_d,
+                              const float* weT_dec_pack, const float* bias_e, const float* bias_d,
                               float* d_hi, float* d_lo, uint32_t* relu_bits, uint32_t* relu_bits_t, const RowGeom& g, int B, double flops,
-                              cudaStream_t st, int pack_out, const float* weT_dec_pack) {
+                              cudaStream_t st, int pack_out) {
     ResX3Args a;
     memset(&a, 0, sizeof a);
     a.B = B; a.g = g; a.bias1 = bias_e; a.bias2 = bias_d; a.mask = relu_bits; a.mask_t = relu_bits_t; a.out_hi = d_hi; a.out_lo = d_lo; a.pack_out = pack_out;
     a.tiles_per_patch = cdiv(g.nrows, 128);
     const long long rows = g.lead + (long long)B * g.pstride + ROW_TAIL;
-    CUtensorMap tm_xh, tm_xl, tm_w1h, tm_w1l, tm_w2h, tm_w2l;
+    CUtensorMap tm_xh, tm_xl, tm_w1h, tm_w1l, tm_w2p;
     PV_TRY(make_tmap_2d(&tm_xh, x_hi, rows, 32, 128, 32, 0));
     PV_TRY(make_tmap_2d(&tm_xl, x_lo, rows, 32, 128, 32, 0));
     PV_TRY(make_tmap_2d(&tm_w1h, weT_exp_hi, 256, 32, 256, 32, 0));
     PV_TRY(make_tmap_2d(&tm_w1l, weT_exp_lo, 256, 32, 256, 32, 0));
-    PV_TRY(make_tmap_2d(&tm_w2h, weT_dec_pack ? weT_dec_pack : weT_dec_hi, 32, 256, 32, 32, 0));
-    PV_TRY(make_tmap_2d(&tm_w2l, weT_dec_lo, 32, 256, 32, 32, 0));
-    const size_t smem = 1024 + 131072 + 2 * 32768 + 8 * ROWIO_SCRATCH_BYTES;
+    PV_TRY(make_tmap_2d(&tm_w2p, weT_dec_pack, 32, 256, 32, 32, 0));
+    const size_t smem = 1024 + 98304 + RX_STAGES * 32768 + 8 * ROWIO_SCRATCH_BYTES;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int ntiles = a.B * a.tiles_per_patch;
     const int grid = ntiles < sms ? ntiles : sms;
-    // executed: three MMAs per product on the padded 32 x 256 shapes, both GEMMs
+    // executed: three products per GEMM on the padded 32 x 256 shapes
     PV_TIMED(relu_bits ? "resfront_fwd_x3" : "resfront_fwd_x3_infer", st, flops, 0.0, 3.0 * 2.0 * 2.0 * (double)ntiles * 128.0 * 32.0 * 256.0);
+    static const bool sequential = getenv("PV_X3_SEQUENTIAL") != nullptr;     // A/B: the previous issue order
     static size_t attr[4][16] = {};
     auto go = [&](auto kern, size_t (&at)[16]) -> int {
         PV_CUDA(ensure_dyn_smem(kern, smem, at));
-        PV_CUDA(launch_pdl(kern, grid, RX_THREADS, smem, st, tm_xh, tm_xl, tm_w1h, tm_w1l, tm_w2h, tm_w2l, a));
+        PV_CUDA(launch_pdl(kern, grid, RX_THREADS, smem, st, tm_xh, tm_xl, tm_w1h, tm_w1l, tm_w2p, a));
         return 0;
     };
-    if (relu_bits) PV_TRY(weT_dec_pack ? go(resfront_fwd_x3_kernel<1, true>, attr[0]) : go(resfront_fwd_x3_kernel<1, false>, attr[1]));
-    else PV_TRY(weT_dec_pack ? go(resfront_fwd_x3_kernel<0, true>, attr[2]) : go(resfront_fwd_x3_kernel<0, false>, attr[3]));
+    if (relu_bits) PV_TRY(sequential ? go(resfront_fwd_x3_kernel<1, false>, attr[0]) : go(resfront_fwd_x3_kernel<1, true>, attr[1]));
+    else PV_TRY(sequential ? go(resfront_fwd_x3_kernel<0, false>, attr[2]) : go(resfront_fwd_x3_kernel<0, true>, attr[3]));
     PV_LAUNCH_CHECK();
     return 0;
 }

@@ -128,10 +128,9 @@ int launch_resfront_bwd_data_tc(const float* gd, const float* w_dec, const float
                                 float* ga_pack = nullptr);     // also the un-rounded result as bf16 pair rows (conv3_tc MODE 2's input)
 // error-compensated forward (resblock_x3_tc.cu): operands and result as (hi, lo) row arrays, three MMAs per product
 int launch_resfront_fwd_x3_tc(const float* x_hi, const float* x_lo, const float* weT_exp_hi, const float* weT_exp_lo,
-                              const float* weT_dec_hi, const float* weT_dec_lo, const float* bias_e, const float* bias_d,
+                              const float* weT_dec_pack /* fp16 pair rows of the decay weights */, const float* bias_e, const float* bias_d,
                               float* d_hi, float* d_lo, uint32_t* relu_bits, uint32_t* relu_bits_t, const RowGeom& g, int B, double flops,
-                              cudaStream_t st, int pack_out = 0,
-                              const float* weT_dec_pack = nullptr);   // decay weights as fp16 pair rows: the decay GEMM runs in kind::f16 on fp16 pairs in TMEM   // pack_out: d_lo receives the packed fp16 pair rows of (hi, lo)
+                              cudaStream_t st, int pack_out = 0);
 int launch_resfront_bwd_weight_tc(const float* x, const float* gd, const float* weT_exp, const float* w_dec, const float* bias_e,
                                   float* dw_dec, float* dw_exp, float* db_exp, float* db_dec, const RowGeom& g, int B,
                                   float* partials, size_t partial_floats, double flops, cudaStream_t st, ReduceQueue* rq = nullptr,
