@@ -528,10 +528,21 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
                     const float x = fmaxf(__uint_as_float(e[k]) + be, 0.f);
                     // tf.nn.relu's gradient convention: 0 at E == 0.  With the forward's mask the value and the mask may disagree
                     // on elements within rounding distance of zero; the mask is what the data path used, so it decides gZ.
-                    const bool pos = FWD_MASK ? ((mt[c] >> k) & 1u) != 0u : x > 0.f;
-                    zs[k & 3] += pos ? __uint_as_float(v[k]) : 0.f;        // bias gradient from the unrounded value
                     e[k] = tf32_bump(__float_as_uint(x));
-                    v[k] = pos ? tf32_bump(v[k]) : 0u;
+                    if (FWD_MASK) {
+                        // one predicate per element from the mask word (LOP3 with an immediate), shared by both selects; left to itself the
+                        // compiler builds an all-ones / zero word per element instead (shift left, arithmetic shift right, AND: +2 instructions)
+                        uint32_t vb;
+                        float zt;
+                        asm("{\n.reg .pred p;\n.reg .b32 t;\nand.b32 t, %2, %3;\nsetp.ne.u32 p, t, 0;\nselp.b32 %0, %4, 0, p;\nselp.f32 %1, %5, 0f00000000, p;\n}\n"
+                            : "=r"(vb), "=f"(zt) : "r"(mt[c]), "r"(1u << k), "r"(tf32_bump(v[k])), "f"(__uint_as_float(v[k])));
+                        zs[k & 3] += zt;                                   // bias gradient from the unrounded value
+                        v[k] = vb;
+                    } else {
+                        const bool pos = x > 0.f;
+                        zs[k & 3] += pos ? __uint_as_float(v[k]) : 0.f;
+                        v[k] = pos ? tf32_bump(v[k]) : 0u;
+                    }
                 }
                 tmem_st32(lane_base + eb * 128 + c * 32, e);
                 tmem_st32(lane_base + eb * 128 + 64 + c * 32, v);
