@@ -42,6 +42,23 @@ __device__ __forceinline__ float rna_tf32(float x) {
 // forward kernel's run time).  Non-finite inputs are not preserved (an Inf would become a NaN pattern).
 __device__ __forceinline__ uint32_t tf32_bump(uint32_t bits) { return bits + 0x1000u; }
 
+// cur[e] = (bits & (0x80000000 >> e)) ? tf32_bump(cur[e]) : 0 for e = E .. 31, as LOP3-with-predicate (immediate mask) + add + select.
+// Left to itself the compiler builds an all-ones / zero word per element (shift left, arithmetic shift right, AND): one instruction
+// more on a 3-instruction path.
+template <int E>
+struct MaskedBump {
+    static __device__ __forceinline__ void run(uint32_t (&cur)[32], uint32_t bits) {
+        uint32_t r = tf32_bump(cur[E]);
+        asm("{\n.reg .pred p;\n.reg .b32 t;\nand.b32 t, %1, %2;\nsetp.ne.u32 p, t, 0;\nselp.b32 %0, %0, 0, p;\n}\n" : "+r"(r) : "r"(bits), "n"(0x80000000u >> E));
+        cur[E] = r;
+        MaskedBump<E + 1>::run(cur, bits);
+    }
+};
+template <>
+struct MaskedBump<32> {
+    static __device__ __forceinline__ void run(uint32_t (&)[32], uint32_t) {}
+};
+
 // ----------------------------------------------------------------------------------------------------------------
 // Forward and backward-data share one kernel (MODE 0 = training forward, 1 = backward-data, 2 = inference forward: the same
 // as 0 without the ReLU bit mask, i.e. 3 instead of 5 instructions per expanded element in the epilogue): both are
@@ -63,7 +80,11 @@ constexpr int RP_THREADS = 320;
 // parity wait cannot tell from "already complete", so the "H ready" barriers are then indexed by u mod 6: every barrier has
 // ONE waiting group and consecutive phases.  (The accumulator barriers are safe: tcgen05 commits arrive in issue order.)
 constexpr int respipe_groups(int mode) { return mode == 1 ? 3 : 2; }
-constexpr int respipe_threads(int g) { return 64 + 128 * g; }
+// three groups: 512 threads = {producer, MMA, two idle warps} + 12 epilogue warps.  The first warpgroup hands its registers back
+// (setmaxnreg.dec 40) and the epilogue warps take 152 (4 x 32 x 40 + 12 x 32 x 152 = 63 488 <= 65 536, and per scheduler
+// 40 + 3 x 152 <= 512): three warps per scheduler without the spills a plain 448-thread launch has at its 128-register cap.
+constexpr int respipe_threads(int g) { return g == 3 ? 512 : 64 + 128 * g; }
+constexpr int respipe_first_epi_warp(int g) { return g == 3 ? 4 : 2; }
 constexpr int respipe_nef(int g) { return g == 2 ? 3 : 2 * g; }       // number of "H ready" (EFULL) barriers
 
 struct ResPipeArgs {
@@ -88,7 +109,7 @@ __global__ void __launch_bounds__(respipe_threads(respipe_groups(MODE)), 1)
 resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant__ CUtensorMap tm_w1,
                      const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w1l,
                      const __grid_constant__ CUtensorMap tm_w2l, const ResPipeArgs a) {
-    constexpr int RPG = respipe_groups(MODE), RPP_THREADS = respipe_threads(RPG), NEF = respipe_nef(RPG);
+    constexpr int RPG = respipe_groups(MODE), RPP_THREADS = respipe_threads(RPG), NEF = respipe_nef(RPG), EW0 = respipe_first_epi_warp(RPG);
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[14 + NEF];
     __shared__ uint32_t tmem_slot;
@@ -123,7 +144,9 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
     const int ntiles = a.B * a.tiles_per_patch;
     const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    if (warp == 0) {
+    if (warp < EW0) {
+      if (RPG == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");       // the whole first warpgroup (two of its warps are idle)
+      if (warp == 0) {
         if (elect_one_sync()) {
             tma_prefetch_desc(&tm_t);
             mbar_arrive_expect_tx(BAR(WBAR), WBYTES);
@@ -189,9 +212,11 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                 }
             }
         }
+      }
     } else {
+        if (RPG == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
         const int q = warp & 3;
-        const int grp = (warp - 2) >> 2;
+        const int grp = (warp - EW0) >> 2;
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         pdl_wait();
         // bwd: the ReLU bits are needed by the very first chunk of a tile, so they are fetched one tile ahead (the row-wide
@@ -217,7 +242,7 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
             // the warp's 32 rows are contiguous in global memory: row-wide traffic goes through the coalescing helpers (rowio.cuh)
             const uint32_t rowmask = __ballot_sync(0xffffffffu, in_patch);
             const long long orow_w = orow - lane;
-            uint8_t* const sc = io_scratch + (warp - 2) * ROWIO_SCRATCH_BYTES;
+            uint8_t* const sc = io_scratch + (warp - EW0) * ROWIO_SCRATCH_BYTES;
             if (MODE == 1) {
                 mlo = nlo; mhi = nhi;
                 if (tl + RPG < my_tiles) { const uint4* mp = mask_row(tl + RPG); nlo = __ldg(mp); nhi = __ldg(mp + 1); }
