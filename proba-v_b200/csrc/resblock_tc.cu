@@ -474,8 +474,11 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
             constexpr uint32_t IDESC2 = instr_desc(2, 128, 32, 0, 1);     // TS: A from TMEM, B MN-major, N = 32
             mbar_wait(BAR(WBAR), 0);
             tc_fence_after();
+            // the SS MMAs run TWO units ahead of the TS MMAs: the units alternate between the epilogue groups, so while group A's unit
+            // u - 2 and group B's unit u - 1 are in the epilogue, A's next unit u is already computed in the third buffer (one ahead, each
+            // group waited for its next unit's SS MMAs after every unit)
             const int U = 4 * my_tiles;
-            for (int u = 0; u <= U; ++u) {
+            for (int u = 0; u < U + 2; ++u) {
                 if (u < U) {                        // the two SS MMAs of unit u = (tile, h, s)
                     const int tl = u >> 2, h = (u >> 1) & 1, sub = u & 1;
                     const uint32_t stg = tl & 1, ph = (tl >> 1) & 1, sa = st_smem + stg * 65536, eb = u % 3;
@@ -488,8 +491,8 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
                     for (int ks = 0; ks < 4; ++ks) umma_ss_tf32_lohi(tmem + eb * 128 + 64, w2 + 2 * ks, g_lo + 2 * ks, HI32, IDESC1, ks > 0);
                     umma_commit(BAR(EFULL + eb));
                 }
-                if (u >= 1) {                       // the two TS MMAs of unit u - 1
-                    const int v = u - 1, tl = v >> 2, h = (v >> 1) & 1, sub = v & 1;
+                if (u >= 2) {                       // the two TS MMAs of unit u - 2
+                    const int v = u - 2, tl = v >> 2, h = (v >> 1) & 1, sub = v & 1;
                     const uint32_t stg = tl & 1, sa = st_smem + stg * 65536, eb = v % 3;
                     mbar_wait(BAR(EREADY + eb), (v / 3) & 1);
                     tc_fence_after();
