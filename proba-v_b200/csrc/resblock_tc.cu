@@ -42,23 +42,6 @@ __device__ __forceinline__ float rna_tf32(float x) {
 // forward kernel's run time).  Non-finite inputs are not preserved (an Inf would become a NaN pattern).
 __device__ __forceinline__ uint32_t tf32_bump(uint32_t bits) { return bits + 0x1000u; }
 
-// cur[e] = (bits & (0x80000000 >> e)) ? tf32_bump(cur[e]) : 0 for e = E .. 31, as LOP3-with-predicate (immediate mask) + add + select.
-// Left to itself the compiler builds an all-ones / zero word per element (shift left, arithmetic shift right, AND): one instruction
-// more on a 3-instruction path.
-template <int E>
-struct MaskedBump {
-    static __device__ __forceinline__ void run(uint32_t (&cur)[32], uint32_t bits) {
-        uint32_t r = tf32_bump(cur[E]);
-        asm("{\n.reg .pred p;\n.reg .b32 t;\nand.b32 t, %1, %2;\nsetp.ne.u32 p, t, 0;\nselp.b32 %0, %0, 0, p;\n}\n" : "+r"(r) : "r"(bits), "n"(0x80000000u >> E));
-        cur[E] = r;
-        MaskedBump<E + 1>::run(cur, bits);
-    }
-};
-template <>
-struct MaskedBump<32> {
-    static __device__ __forceinline__ void run(uint32_t (&)[32], uint32_t) {}
-};
-
 // ----------------------------------------------------------------------------------------------------------------
 // Forward and backward-data share one kernel (MODE 0 = training forward, 1 = backward-data, 2 = inference forward: the same
 // as 0 without the ReLU bit mask, i.e. 3 instead of 5 instructions per expanded element in the epilogue): both are
@@ -81,8 +64,9 @@ constexpr int RP_THREADS = 320;
 // ONE waiting group and consecutive phases.  (The accumulator barriers are safe: tcgen05 commits arrive in issue order.)
 constexpr int respipe_groups(int mode) { return mode == 1 ? 3 : 2; }
 // three groups: 512 threads = {producer, MMA, two idle warps} + 12 epilogue warps.  The first warpgroup hands its registers back
-// (setmaxnreg.dec 40) and the epilogue warps take 152 (4 x 32 x 40 + 12 x 32 x 152 = 63 488 <= 65 536, and per scheduler
-// 40 + 3 x 152 <= 512): three warps per scheduler without the spills a plain 448-thread launch has at its 128-register cap.
+// (setmaxnreg.dec 56) and the epilogue warps take 152 (4 x 32 x 56 + 12 x 32 x 152 = 65 536, and per scheduler 56 + 3 x 152 = 512
+// registers per lane): three warps per scheduler without the spills a plain 448-thread launch has at its 128-register cap.  The role
+// split has to happen at warpgroup level (setmaxnreg is a warpgroup-wide instruction, and ptxas budgets each side of the branch).
 constexpr int respipe_threads(int g) { return g == 3 ? 512 : 64 + 128 * g; }
 constexpr int respipe_first_epi_warp(int g) { return g == 3 ? 4 : 2; }
 constexpr int respipe_nef(int g) { return g == 2 ? 3 : 2 * g; }       // number of "H ready" (EFULL) barriers
@@ -402,7 +386,9 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
 //       three unit buffers (384 columns) + the four accumulators (128 columns) fill TMEM exactly.  As in the forward
 //       kernel the MMA thread issues the two SS MMAs of unit u+1 before the two TS MMAs of unit u, and two epilogue
 //       groups of four warps take alternate units.
-constexpr int RBW_THREADS = 64 + 128 * RESBW_GROUPS;
+// three groups: 512 threads = {producer, MMA, two idle warps} + 12 epilogue warps with setmaxnreg (see respipe_threads)
+constexpr int RBW_EW0 = RESBW_GROUPS == 3 ? 4 : 2;          // first epilogue warp
+constexpr int RBW_THREADS = 32 * RBW_EW0 + 128 * RESBW_GROUPS;
 struct ResBwdWeightArgs {
     int B, tiles_per_patch;
     RowGeom g;
@@ -445,7 +431,9 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
     const int t_lo = (int)((long long)ntiles * blockIdx.x / gridDim.x), t_hi = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
     const int my_tiles = t_hi - t_lo;
 
-    if (warp == 0) {
+    if (warp < RBW_EW0) {
+      if (RESBW_GROUPS == 3) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");       // the whole first warpgroup (two of its warps are idle)
+      if (warp == 0) {
         if (elect_one_sync()) {
             mbar_arrive_expect_tx(BAR(WBAR), 65536);
             tma_load_2d(weT_smem, &tm_weT, BAR(WBAR), 0, 0);
@@ -509,9 +497,11 @@ resfront_bwd_weight_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
             }
             umma_commit(BAR(DONE));
         }
+      }
     } else {
+        if (RESBW_GROUPS == 3) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
         const int q = warp & 3;
-        const int grp = (warp - 2) >> 2;
+        const int grp = (warp - RBW_EW0) >> 2;
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         float dbe0 = 0.f, dbe1 = 0.f, dbd = 0.f;
         const int U = 4 * my_tiles;
