@@ -2,12 +2,13 @@
 // models/modelsTF.py:159-163,185-188 and their Conv3DBackpropInputV2) as an implicit GEMM whose MMA N dimension is
 // widened from 32 to 96 by folding the three dw taps into N.
 //
-// Why: on sm_100a an M128 x N x K8 kind::tf32 MMA with both operands in shared memory costs 32 + N/2 cycles
-// (probes/umma_rate.cu -- the 4 KB A-operand fetch is not overlapped with the math), so with N = 32 the tensor pipe
-// idles two thirds of the time.  Taps that differ only in dw read the SAME activation rows shifted by one row, so
+// Why: on sm_100a an M128 x N x K8 kind::tf32 MMA with both operands in shared memory costs max(N/2, 32 + N/4) cycles
+// (probes/umma_rate.cu, profiles/r02_umma_rate_probe.log: the operands stream from shared memory at 128 B/cycle, 4 KB of A per
+// MMA whatever N is), so with N = 32 the A fetch alone paces the tensor pipe.  Taps that differ only in dw read the SAME activation
+// rows shifted by one row, so
 //     Q_j[rho] = sum_{g=(dt,dh)} X[rho + base_g + 1] . W[g, dw = j]          j = 0,1,2      (one N = 96 MMA chain, 9 groups)
 //     out[r]   = Q_0[r - 1] + Q_1[r] + Q_2[r + 1]
-// i.e. 36 MMAs of 80 cycles per 128-row tile instead of 108 MMAs of 54 cycles.  The row shift of the two outer thirds
+// i.e. 36 MMAs of 56 cycles per 128-row tile instead of 108 MMAs of 40 cycles.  The row shift of the two outer thirds
 // is done by the epilogue: TMEM lanes are rows, so it is a lane shift -- warp shuffles inside a warp, a 1 KB shared
 // memory exchange across the four warps of a TMEM lane quarter group; the tile's first/last lanes are halo.
 //
@@ -22,7 +23,11 @@
 // three fresh slabs per tile.
 //
 // Warp roles as in conv_tc.cu: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer (one elected thread), warps 2-5 and
-// 6-9 two epilogue groups draining alternate tiles (TMEM accumulator double buffer, 2 x 96 columns).
+// 6-9 two epilogue groups draining alternate tiles (TMEM accumulator double buffer, 2 x 96 columns; 2 x 192 in the pair-row modes).
+//
+// Modes (template parameter, RowConvP::f16_pack): 0 = kind::tf32 on fp32 rows (single-pass engine: forward, data gradient);
+// 1 = the error-compensated forward in one launch on fp16 pair rows (main + correction accumulators); 2 = the split-weight data
+// gradient in one launch on bf16 pair rows; 3 = kind::f16 on the hi halves of fp16 pair rows (inference).  See the kernel's comment.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
