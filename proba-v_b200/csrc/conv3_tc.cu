@@ -173,7 +173,7 @@ rowconv3_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
             const uint32_t dh_inc = (uint32_t)a.pw * 8u;                // one image line further into the slab (16-byte units)
             mbar_wait(BAR(WBAR), 0);
             tc_fence_after();
-            // The issuing thread must stay ahead of the tensor pipe (an N = 96 MMA retires every ~80 cycles), so the per-tile
+            // The issuing thread must stay ahead of the tensor pipe (an N = 96 MMA retires every ~56 cycles), so the per-tile
             // bookkeeping is incremental: (c, b, t) counters instead of divisions, ring stages and barrier parities in registers.
             TileInfo ti = tile_info(a, t_lo, t_lo);
             int tb = ti.b, tt = ti.t;

@@ -11,8 +11,8 @@
 //          A operand whose four 32-channel atoms are 128 B apart, i.e. overlapping views of the same rows (LBO = 128).
 //          The three dh taps ride on the OTHER operand: dW[dt,dh,dw] = sum_r' x[r' + off(dt,0,dw)] * gz[r' - dh*pw], so
 //          B is three 32-channel atoms of the gz tile one image line (pw rows) apart (LBO = pw * 128 B) and N = 96.
-//          An M128 x N32 x K8 tf32 MMA costs 32 + N/2 cycles (probes/umma_rate.cu: the 4 KB A fetch is not overlapped),
-//          so one N = 96 MMA (80 cycles) replaces three N = 32 MMAs (163 cycles).  Three dt groups -> three [128 x 96]
+//          An M128 x N x K8 tf32 MMA costs max(N/2, 32 + N/4) cycles (probes/umma_rate.cu, profiles/r02_umma_rate_probe.log: the 4 KB
+//          A fetch paces small N), so one N = 96 MMA (56 cycles) replaces three N = 32 MMAs (120 cycles).  Three dt groups -> three [128 x 96]
 //          accumulators = 288 TMEM columns.  Tiles run 2*pw rows past the patch's row range so that every gz row meets
 //          every dh (gz is zero outside its valid extent, rows.h invariant).
 //   wide x (decConv: x = E, 256 channels): 2 groups of 4 channel atoms (LBO = box stride), N = 32 (gz = gD)
