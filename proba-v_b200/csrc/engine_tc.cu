@@ -832,10 +832,7 @@ int tc_build_plan(pv_model* m) {
             P.add("a_lo1", rows_per(pr, F), rows_extra(pr, F));
             P.add("D_pack", rows_per(pr, F), rows_extra(pr, F));         // packed fp16 pair rows (rows.h): what a compensated conv3 reads
             for (const TailStep& ts : tail) {
-                if (ts.copy) {
-                    P.add(ts.in + "_lo", rows_per(ts.ig, F), rows_extra(ts.ig, F));
-                    P.add(ts.in + "_pack", rows_per(ts.ig, F), rows_extra(ts.ig, F));
-                }
+                if (ts.copy) P.add(ts.in + "_pack", rows_per(ts.ig, F), rows_extra(ts.ig, F));
                 P.add(ts.out + "_lo", rows_per(ts.og, F), rows_extra(ts.og, F));
                 P.add(ts.out + "_pack", rows_per(ts.og, F), rows_extra(ts.og, F));
             }
@@ -918,13 +915,12 @@ static int tc_forward_x3(pv_model* m, int B, float* sr, bool tr, int clip_round,
         const TailStep& ts = tail[k];
         const float* in_pack;
         if (k == 0 || ts.copy) {
-            // re-layout (+ reflect pad) of the hi and lo halves, then the packed pair rows of the padded tensor (padding rows pack to zero)
+            // re-layout (+ reflect pad) of the (hi, lo) pair in one launch: hi rows for the backward pass, packed pair rows for the conv
+            // (rows the copy does not write stay zero in both)
             const float* src_hi = k == 0 ? P[m->A(m->R, tr)] : P[tail[k - 1].out];
             const float* src_lo = k == 0 ? alo(m->R) : P[tail[k - 1].out + "_lo"];
             const RowGeom sg = k == 0 ? pr : tail[k - 1].og;
-            PV_TRY(launch_pr_to_g_reflect(src_hi, sg, P[ts.in], ts.ig, B, F, st, ts.pad));
-            PV_TRY(launch_pr_to_g_reflect(src_lo, sg, P[ts.in + "_lo"], ts.ig, B, F, st, ts.pad));
-            PV_TRY(launch_pack_rows(P[ts.in], P[ts.in + "_lo"], P[ts.in + "_pack"], ts.ig.lead + (long long)B * ts.ig.pstride + ROW_TAIL, st));
+            PV_TRY(launch_pr_to_g_reflect(src_hi, sg, P[ts.in], ts.ig, B, F, st, ts.pad, src_lo, P[ts.in + "_pack"]));
             in_pack = P[ts.in + "_pack"];
         } else {
             in_pack = P[tail[k - 1].out + "_pack"];

@@ -192,7 +192,6 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
             const long long orow_w = orow - lane;
             uint8_t* const sc = io_scratch + (warp - 2) * ROWIO_SCRATCH_BYTES;
             const uint32_t tph = (tl >> 1) & 1;               // this group's (tl >> 1)-th tile: every barrier below sees consecutive phases
-            uint32_t mw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll 1
             for (int q = 0; q < 4; ++q) {                     // rolled: the unrolled body thrashes the instruction cache
                 // position of this unit in the MMA thread's issue order (unit_of there)
@@ -202,6 +201,7 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                 tc_fence_after();
                 uint32_t va[32], vb[32];
                 uint32_t ph[32], pl[32];                      // the quarter as fp16 pairs, two channels per word
+                uint32_t wq[2] = {0u, 0u};                    // TRAIN: this quarter's two words of the row's ReLU mask
                 tmem_ld32(hb, va);
                 tmem_ld32(hb + 32, vb);
 #pragma unroll
@@ -248,23 +248,20 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                             // lanes with bit j clear keep their low halves and take the partner's low halves shifted up; the others mirror it
                             colbits = (lane & j) ? ((colbits & ~msk) | ((other >> j) & msk)) : ((colbits & msk) | ((other << j) & ~msk));
                         }
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) if (k == q * 2 + c) mw[k] = word;
+                        wq[c] = word;
                         // transposed copy: one coalesced 128-byte store per (32 rows x 32 channels)
                         if (a.mask_t) a.mask_t[((size_t)tile * 4 + q4) * 256 + q * 64 + c * 32 + lane] = colbits;
                     }
                 }
+                // words 2q, 2q + 1 of the row-major mask (one 8-byte store per quarter: collecting the tile's eight words in registers
+                // under the rolled q loop costs a 16-compare select chain per quarter)
+                if (TRAIN && a.mask && in_patch) reinterpret_cast<uint2*>(a.mask + orow * 8)[q] = make_uint2(wq[0], wq[1]);
                 tmem_st32(hb, ph);                            // in place over the accumulator (both halves of it are in registers)
                 tmem_st32(hb + 32, pl);
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(BAR(EREADY + eb));
-            }
-            if (TRAIN && a.mask && in_patch) {
-                uint4* mp = reinterpret_cast<uint4*>(a.mask + orow * 8);
-                mp[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-                mp[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
             }
             const uint32_t db = tl & 1;                       // == grp
             mbar_wait(BAR(DFULL + db), tph);

@@ -435,8 +435,11 @@ __device__ __forceinline__ int refl(int i, int n) { return i < 0 ? -i : (i >= n 
 
 // `pad` = reflect padding per side on H and W (tf.pad REFLECT, modelsTF.py:125-135,157): 1, or 0 for a plain re-layout
 // (ConvReduceAndUpscalev2 pads nothing, modelsTF.py:166-175).  The source may be a PR or a G buffer.
+// a_lo / g_pack (error-compensated engine, C4 == 8): the source is a (hi, lo) pair of row arrays; g0 receives the hi rows (what the
+// backward pass reads) and g_pack the packed fp16 pair rows of (hi, lo) (what the compensated 3x3x3 convolution reads, rows.h) --
+// one launch instead of two copies and a packing pass.
 __global__ void pr_to_g_reflect_kernel(const float* __restrict__ a, RowGeom pr, float* __restrict__ g0, RowGeom gg,
-                                       long long n, int C4, int pad) {
+                                       long long n, int C4, int pad, const float* __restrict__ a_lo, float* __restrict__ g_pack) {
     pdl_grid_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -446,7 +449,19 @@ __global__ void pr_to_g_reflect_kernel(const float* __restrict__ a, RowGeom pr, 
     const int t = (int)(r % gg.nt); const long long b = r / gg.nt;
     const long long src = pr.lead + b * pr.pstride + (long long)(pr.t0 + t) * pr.plane + refl(h - pad, pr.nh) * pr.pw + refl(w - pad, pr.nw);
     const long long dst = gg.lead + b * gg.pstride + (long long)(gg.t0 + t) * gg.plane + h * gg.pw + w;
-    reinterpret_cast<float4*>(g0)[dst * C4 + c] = __ldg(reinterpret_cast<const float4*>(a) + src * C4 + c);
+    const float4 vh = __ldg(reinterpret_cast<const float4*>(a) + src * C4 + c);
+    reinterpret_cast<float4*>(g0)[dst * C4 + c] = vh;
+    if (g_pack) {
+        const float4 l = __ldg(reinterpret_cast<const float4*>(a_lo) + src * C4 + c);
+        const __half2 h0 = __floats2half2_rn(vh.x, vh.y), h1 = __floats2half2_rn(vh.z, vh.w);
+        // lo' = lo + (hi - fp16(hi)): the packed pair always sums to hi + lo (rows.h)
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn((l.x + (vh.x - f0.x)) * PACK_SCALE, (l.y + (vh.y - f0.y)) * PACK_SCALE);
+        const __half2 l1 = __floats2half2_rn((l.z + (vh.z - f1.x)) * PACK_SCALE, (l.w + (vh.w - f1.y)) * PACK_SCALE);
+        uint2* pk = reinterpret_cast<uint2*>(g_pack + dst * 32);
+        pk[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        pk[8 + c] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+    }
 }
 
 __device__ __forceinline__ int preimages(int i, int n, int p, int (&o)[3]) {
@@ -500,23 +515,6 @@ __global__ void pr_to_g_reflect_bwd_kernel(const float* __restrict__ gg0, RowGeo
     reinterpret_cast<float4*>(ga)[dst * C4 + c] = s;
 }
 
-// (hi, lo) fp32 rows -> packed fp16 pair rows [ fp16(hi) x 32 | fp16(PACK_SCALE * lo) x 32 ]; one thread per 4 channels of a row
-__global__ void pack_rows_kernel(const float* __restrict__ hi, const float* __restrict__ lo, float* __restrict__ pack, long long n4) {
-    pdl_grid_wait();
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n4) return;
-    const long long row = i >> 3; const int q = (int)(i & 7);
-    const float4 h = __ldg(reinterpret_cast<const float4*>(hi) + i), l = __ldg(reinterpret_cast<const float4*>(lo) + i);
-    const __half2 h0 = __floats2half2_rn(h.x, h.y), h1 = __floats2half2_rn(h.z, h.w);
-    // lo' = lo + (hi - fp16(hi)): the packed pair always sums to hi + lo (rows.h)
-    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-    const __half2 l0 = __floats2half2_rn((l.x + (h.x - f0.x)) * PACK_SCALE, (l.y + (h.y - f0.y)) * PACK_SCALE);
-    const __half2 l1 = __floats2half2_rn((l.z + (h.z - f1.x)) * PACK_SCALE, (l.w + (h.w - f1.y)) * PACK_SCALE);
-    uint2* dst = reinterpret_cast<uint2*>(pack + row * 32);
-    dst[q] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-    dst[8 + q] = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
-}
-
 // sr[b, s*h+i, s*w+j] = (U[row(b,0,h,w)][i*s+j] + resid[b,h,w,i*s+j]) * std + mean
 __global__ void tail_rows_kernel(const float* __restrict__ u, RowGeom g, int uc, const float* __restrict__ resid, long long n,
                                  int P, int s, float mean, float stdv, int clip_round, float* __restrict__ sr) {
@@ -556,14 +554,6 @@ __global__ void tail_bwd_rows_kernel(const float* __restrict__ dsr, long long n,
 }
 
 }  // namespace
-
-int launch_pack_rows(const float* hi, const float* lo, float* pack, long long n32, cudaStream_t st) {
-    const long long n4 = n32 * 8;
-    PV_TIMED("pack_rows", st, 0.0, (double)n32 * 384.0);
-    PV_CUDA(launch_pdl_simple(pack_rows_kernel, cdiv(n4, 256), 256, 0, st, hi, lo, pack, n4));
-    PV_LAUNCH_CHECK();
-    return 0;
-}
 
 int launch_tail_rows(const float* u, RowGeom g, int uc, const float* resid, int B, int P, int scale, float mean, float stdv,
                      int clip_round, float* sr, cudaStream_t st) {
@@ -660,12 +650,13 @@ int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, i
     return 0;
 }
 
-int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st, int pad) {
+int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st, int pad, const float* a_lo, float* g_pack) {
+    if ((a_lo != nullptr) != (g_pack != nullptr) || (g_pack && C != 32)) return set_error(PV_ERR_BAD_ARG, "pr_to_g_reflect: pair rows need the lo source and 32-channel rows");
     if (pad < 0 || pad > 1 || gg.nh != pr.nh + 2 * pad || gg.nw != pr.nw + 2 * pad || gg.nt != pr.nt)
         return set_error(PV_ERR_BAD_ARG, "pr_to_g_reflect: %dx%dx%d + pad %d does not give %dx%dx%d", pr.nh, pr.nw, pr.nt, pad, gg.nh, gg.nw, gg.nt);
     const long long n = (long long)B * gg.nt * gg.nh * gg.nw * (C / 4);
     PV_TIMED("pr_to_g_reflect", st);
-    PV_CUDA(launch_pdl_simple(pr_to_g_reflect_kernel, cdiv(n, 256), 256, 0, st, a, pr, g0, gg, n, C / 4, pad));
+    PV_CUDA(launch_pdl_simple(pr_to_g_reflect_kernel, cdiv(n, 256), 256, 0, st, a, pr, g0, gg, n, C / 4, pad, a_lo, g_pack));
     PV_LAUNCH_CHECK();
     return 0;
 }

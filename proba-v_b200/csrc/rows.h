@@ -144,7 +144,8 @@ int launch_first_conv_pr_wgrad(const float* xn, const float* gz, int B, int S, i
                                float* partials, size_t partial_floats, cudaStream_t st, ReduceQueue* rq = nullptr);
 // PR (or G) tensor -> G layout with the reducer's reflect padding (tf.pad REFLECT by `pad` = 0 or 1 on H and W), and its
 // adjoint (optionally multiplied by (relumask > 0): the padded tensor was a ReLU output)
-int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st, int pad = 1);
+int launch_pr_to_g_reflect(const float* a, RowGeom pr, float* g0, RowGeom gg, int B, int C, cudaStream_t st, int pad = 1,
+                           const float* a_lo = nullptr, float* g_pack = nullptr);   // (hi, lo) source -> hi rows + packed fp16 pair rows
 // round_tf32: store the result rounded to nearest tf32 (it only feeds tensor-core MMAs, which would truncate it)
 int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom pr, int B, int C, cudaStream_t st, int pad = 1,
                                const float* relumask = nullptr, int round_tf32 = 0, float* ga_pack = nullptr);   // ga_pack: also as bf16 pair rows
@@ -153,8 +154,6 @@ int launch_pr_to_g_reflect_bwd(const float* gg0, RowGeom gg, float* ga, RowGeom 
 int launch_skip2d_fwd_tail(const float* mn, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
                            const float* b3, int B, int S, int C, float* q1, float* q2, float* q3, const float* u, RowGeom ug, int uc,
                            int scale, float mean, float stdv, int clip_round, float* sr, cudaStream_t st);
-// (hi, lo) fp32 row arrays -> packed fp16 pair rows (n32 = number of 32-channel rows)
-int launch_pack_rows(const float* hi, const float* lo, float* pack, long long n32, cudaStream_t st);
 // tail on the row layouts: sr = (depth_to_space(U[:, :, :9]) + depth_to_space(resid)) * std + mean [clip, round]; and its adjoint
 int launch_tail_rows(const float* u, RowGeom g, int uc, const float* resid, int B, int P, int scale, float mean, float stdv,
                      int clip_round, float* sr, cudaStream_t st);
