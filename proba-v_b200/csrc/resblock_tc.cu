@@ -97,7 +97,6 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[14 + NEF];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(16) float s_b1[256];
     __shared__ __align__(16) float s_b2[32];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     constexpr uint32_t WBYTES = WSPLIT ? 131072u : 65536u;
@@ -106,6 +105,11 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
     const uint32_t w1l_smem = base + 65536, w2l_smem = base + 98304;     // WSPLIT: the lo halves, same layouts
     const uint32_t t_smem = base + WBYTES;          // 3 stages x [128 rows x 128 B]
     uint8_t* const io_scratch = smem_raw + (base - smem_u32(smem_raw)) + WBYTES + 3 * 16384;   // 8 epilogue warps x 2 KB (rowio.cuh)
+    // Forward (MODE 0 / 2): the expand bias rides in MMA1 as one more K = 8 step, A = a [128 x 8] tile whose columns 0 and 1 are ones,
+    // B = a [256 x 8] tile whose columns 0 / 1 are tf32(be) / be - tf32(be) -- one MMA per unit instead of an FADD per expanded element in
+    // an epilogue that is bound by its instruction stream.  Both tiles are K-major SWIZZLE_128B like the operands.
+    constexpr uint32_t SCRATCH_BYTES = 4 * RPG * ROWIO_SCRATCH_BYTES;
+    const uint32_t ones_smem = base + WBYTES + 3 * 16384 + SCRATCH_BYTES, biasb_smem = ones_smem + 16384;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto BAR = [&](int i) { return smem_u32(&bars[i]); };
     const int FULL = 0, EMPTY = 3, WBAR = 6, EFULL = 7, EREADY = 7 + NEF, DFULL = 10 + NEF, DFREE = 12 + NEF;
@@ -117,8 +121,18 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
         fence_mbar_init();
     }
     if (MODE != 1) {
-        for (int i = threadIdx.x; i < 256; i += RPP_THREADS) s_b1[i] = a.bias1[i];
         if (threadIdx.x < 32) s_b2[threadIdx.x] = a.bias2[threadIdx.x];
+        uint8_t* const ones_p = smem_raw + (ones_smem - smem_u32(smem_raw));
+        for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += RPP_THREADS) reinterpret_cast<uint4*>(ones_p)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        // logical 16-byte chunk 0 of row r sits at physical chunk (r & 7) (SWIZZLE_128B: chunk index ^= row & 7)
+        for (int r = threadIdx.x; r < 128; r += RPP_THREADS)
+            *reinterpret_cast<float2*>(ones_p + r * 128 + ((r & 7) << 4)) = make_float2(1.f, 1.f);
+        for (int n = threadIdx.x; n < 256; n += RPP_THREADS) {
+            const float b = a.bias1[n], bh = rna_tf32(b);
+            *reinterpret_cast<float2*>(ones_p + 16384 + n * 128 + ((n & 7) << 4)) = make_float2(bh, b - bh);
+        }
+        fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core's async-proxy reads
     }
     if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
     tc_fence_before();
@@ -169,6 +183,8 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                     const uint32_t t_lo = ((t_smem + stg * 16384) >> 4) | LO32, w_lo = ((w1_smem + h * 16384) >> 4) | LO32;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) umma_ss_tf32_lohi(tmem + eb * 128, t_lo + 2 * ks, w_lo + 2 * ks, HI32, IDESC1, ks > 0);
+                    if (MODE != 1)                  // + ones . [be_hi | be_lo]^T
+                        umma_ss_tf32_lohi(tmem + eb * 128, (ones_smem >> 4) | LO32, ((biasb_smem + h * 16384) >> 4) | LO32, HI32, IDESC1, 1u);
                     if (WSPLIT) {
                         const uint32_t wl_lo = ((w1l_smem + h * 16384) >> 4) | LO32;
 #pragma unroll
@@ -255,31 +271,21 @@ resfront_pipe_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_cons
                     if (MODE == 0) {
                         // four independent 8-element sign chains (one serial 32-long funnel-shift chain would pace the warp)
                         uint32_t sg[4] = {0u, 0u, 0u, 0u};
-                        const float4* be4 = reinterpret_cast<const float4*>(s_b1 + h * 128 + c * 32);
 #pragma unroll
                         for (int e4 = 0; e4 < 8; ++e4) {
-                            const float4 bq = be4[e4];
-                            const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 // x = relu(y) >= +0; (bits(x) - 1) has its sign bit set exactly when x == 0, i.e. when y <= 0,
-                                // which is tf.nn.relu's gradient convention (0 at y == 0)
-                                const uint32_t x = __float_as_uint(fmaxf(__uint_as_float(cur[e4 * 4 + e]) + bb[e], 0.f));
+                                // which is tf.nn.relu's gradient convention (0 at y == 0).  (The bias is already in the accumulator.)
+                                const uint32_t x = __float_as_uint(fmaxf(__uint_as_float(cur[e4 * 4 + e]), 0.f));
                                 sg[e4 >> 1] = __funnelshift_l(x - 1u, sg[e4 >> 1], 1);
                                 cur[e4 * 4 + e] = tf32_bump(x);
                             }
                         }
                         wd[c] = ~((sg[0] << 24) | ((sg[1] & 0xffu) << 16) | ((sg[2] & 0xffu) << 8) | (sg[3] & 0xffu));
                     } else if (MODE == 2) {
-                        const float4* be4 = reinterpret_cast<const float4*>(s_b1 + h * 128 + c * 32);
 #pragma unroll
-                        for (int e4 = 0; e4 < 8; ++e4) {
-                            const float4 bq = be4[e4];
-                            const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                cur[e4 * 4 + e] = tf32_bump(__float_as_uint(fmaxf(__uint_as_float(cur[e4 * 4 + e]) + bb[e], 0.f)));
-                        }
+                        for (int e = 0; e < 32; ++e) cur[e] = tf32_bump(__float_as_uint(fmaxf(__uint_as_float(cur[e]), 0.f)));
                     } else {
                         const uint32_t bits = wd[c];
 #pragma unroll
@@ -622,7 +628,8 @@ static int launch_respipe(const float* t, const float* w1, const float* w2, cons
         PV_TRY(make_tmap_2d(&tm_w1l, w1_lo, 256, 32, 256, 32, 0));
         PV_TRY(make_tmap_2d(&tm_w2l, w2_lo, 32, 256, 32, 32, 0));
     }
-    const size_t smem = 1024 + (WSPLIT ? 131072 : 65536) + 3 * 16384 + 4 * respipe_groups(MODE) * ROWIO_SCRATCH_BYTES;
+    const size_t smem = 1024 + (WSPLIT ? 131072 : 65536) + 3 * 16384 + 4 * respipe_groups(MODE) * ROWIO_SCRATCH_BYTES +
+                        (MODE != 1 ? 16384 + 32768 : 0);        // forward: the ones / bias tiles of the bias MMA
     static size_t attr[16] = {};
     PV_CUDA(ensure_dyn_smem(resfront_pipe_kernel<MODE, WSPLIT>, smem, attr));
     int dev = 0, sms = 148;
