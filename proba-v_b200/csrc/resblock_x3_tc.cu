@@ -42,6 +42,8 @@ struct ResX3Args {
     float* out_hi;                     // D rows: tf32(D)
     float* out_lo;                     //         D - tf32(D), or (pack_out) the packed fp16 pair rows of (hi, lo): what the
     int pack_out;                      //         compensated 3x3x3 convolution reads (rows.h PACK_SCALE)
+    int bias_mma;                      // the expand bias rides in MMA1 (ones tile x bias tile, one more K = 8 step) instead of an FADD per element
+    uint32_t bias_lbo, bias_sbo;       // byte strides of the two un-swizzled tiles (K-adjacent core matrices, 8-row groups)
 };
 
 __device__ __forceinline__ uint32_t tf32_rn_bits(uint32_t bits) { return (bits + 0x1000u) & 0xffffe000u; }
@@ -51,7 +53,7 @@ __device__ __forceinline__ uint32_t tf32_rn_bits(uint32_t bits) { return (bits +
 // arrive as the fp16 pair rows of rows.h, and MMA2 is 12 K = 16 MMAs per quarter: E16 Wd_hi into the main accumulator,
 // Elo16 Wd_hi + E16 2^12 Wd_lo into the correction accumulator (scaled back by 2^-12 in the final epilogue).
 // ILV: issue order of the quarter units (see the MMA thread).
-template <int TRAIN, bool ILV>
+template <int TRAIN, bool ILV, bool BMMA>
 __global__ void __launch_bounds__(RX_THREADS, 1)
 resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_constant__ CUtensorMap tm_xl,
                        const __grid_constant__ CUtensorMap tm_w1h, const __grid_constant__ CUtensorMap tm_w1l,
@@ -59,13 +61,16 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[22];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(16) float s_b1[256];
+    __shared__ __align__(16) float s_b1[256];        // (only without bias_mma)
     __shared__ __align__(16) float s_b2[32];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t w1h_smem = base, w1l_smem = base + 32768;            // [256 rows x 128 B] each
     const uint32_t w2p_smem = base + 65536;                             // 8 K-chunks x [32 rows x 128 B]: fp16 pair rows [2^12 w_lo x 32 | w_hi x 32]
     const uint32_t x_smem = base + 98304;                               // RX_STAGES x { X_hi, X_lo } x [128 rows x 128 B]
     uint8_t* const io_scratch = smem_raw + (base - smem_u32(smem_raw)) + 98304 + RX_STAGES * 32768;   // 8 epilogue warps x 2 KB (rowio.cuh)
+    // bias_mma: A = [128 x 8] tile with ones in columns 0, 1; B = [256 x 8] tile with tf32(be) / be - tf32(be) in columns 0 / 1.  Shared memory
+    // is nearly full, so both are UN-SWIZZLED K-major tiles (core matrix = 8 rows x 16 bytes): 4 KB + 8 KB instead of 16 KB + 32 KB.
+    const uint32_t ones_smem = base + 98304 + RX_STAGES * 32768 + 8 * ROWIO_SCRATCH_BYTES, biasb_smem = ones_smem + 4096;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto BAR = [&](int i) { return smem_u32(&bars[i]); };
     const int FULL = 0, EMPTY = 3, WBAR = 6, EFULL = 7, EREADY = 15, DFULL = 18, DFREE = 20;
@@ -78,6 +83,19 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
         fence_mbar_init();
     }
     for (int i = threadIdx.x; i < 256; i += RX_THREADS) s_b1[i] = a.bias1[i];
+    if (BMMA) {
+        uint8_t* const tp = smem_raw + (ones_smem - smem_u32(smem_raw));
+        // element (row r, k) of a tile: (r / 8) * sbo + (k / 4) * lbo + (r % 8) * 16 + (k % 4) * 4
+        for (int i = threadIdx.x; i < (4096 + 8192) / 16; i += RX_THREADS) reinterpret_cast<uint4*>(tp)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        for (int r = threadIdx.x; r < 128; r += RX_THREADS)
+            *reinterpret_cast<float2*>(tp + (r >> 3) * a.bias_sbo + (r & 7) * 16) = make_float2(1.f, 1.f);
+        for (int n = threadIdx.x; n < 256; n += RX_THREADS) {
+            const float b = a.bias1[n], bh = __uint_as_float(tf32_rn_bits(__float_as_uint(b)));
+            *reinterpret_cast<float2*>(tp + 4096 + (n >> 3) * a.bias_sbo + (n & 7) * 16) = make_float2(bh, b - bh);
+        }
+        fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core's async-proxy reads
+    }
     if (threadIdx.x < 32) s_b2[threadIdx.x] = a.bias2[threadIdx.x];
     if (warp == 1) tmem_alloc<512>(smem_u32(&tmem_slot));
     tc_fence_before();
@@ -145,6 +163,11 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                     for (int ks = 0; ks < 4; ++ks) umma_ss_tf32_lohi(d, xl + 2 * ks, wh + 2 * ks, HI32, IDESC1, 1u);
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) umma_ss_tf32_lohi(d, xh + 2 * ks, wl + 2 * ks, HI32, IDESC1, 1u);
+                    if (BMMA) {                     // + ones . [be_hi | be_lo]^T of this quarter's 64 channels (un-swizzled descriptors)
+                        const uint64_t hn = smem_desc_hi(a.bias_lbo, a.bias_sbo, 0);
+                        const uint32_t hn32 = (uint32_t)(hn >> 32), ln32 = (uint32_t)hn;
+                        umma_ss_tf32_lohi(d, (ones_smem >> 4) | ln32, ((biasb_smem + (uint32_t)q * 8u * a.bias_sbo) >> 4) | ln32, hn32, IDESC1, 1u);
+                    }
                     if (q == 3) umma_commit(BAR(EMPTY + stg));
                     umma_commit(BAR(EFULL + (tl & 1) * 4 + q));
                 }
@@ -217,7 +240,7 @@ resfront_fwd_x3_kernel(const __grid_constant__ CUtensorMap tm_xh, const __grid_c
                         const float bb[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float v = fmaxf(__uint_as_float(cur[e4 * 4 + e]) + bb[e], 0.f);
+                            const float v = fmaxf(BMMA ? __uint_as_float(cur[e4 * 4 + e]) : __uint_as_float(cur[e4 * 4 + e]) + bb[e], 0.f);
                             const uint32_t x = __float_as_uint(v);
                             // (bits(v) - 1) has its sign bit set exactly when v == 0, i.e. when the pre-activation is <= 0
                             // (tf.nn.relu's gradient convention)
@@ -335,7 +358,14 @@ int launch_resfront_fwd_x3_tc(const float* x_hi, const float* x_lo, const float*
     PV_TRY(make_tmap_2d(&tm_w1h, weT_exp_hi, 256, 32, 256, 32, 0));
     PV_TRY(make_tmap_2d(&tm_w1l, weT_exp_lo, 256, 32, 256, 32, 0));
     PV_TRY(make_tmap_2d(&tm_w2p, weT_dec_pack, 32, 256, 32, 32, 0));
-    const size_t smem = 1024 + 98304 + RX_STAGES * 32768 + 8 * ROWIO_SCRATCH_BYTES;
+    const size_t smem = 1024 + 98304 + RX_STAGES * 32768 + 8 * ROWIO_SCRATCH_BYTES + 4096 + 8192;
+    {   // PV_X3_BIAS_MMA=0 keeps the per-element bias add (A/B); PV_X3_BIAS_DESC=lbo,sbo overrides the tile strides (bring-up)
+        static const char* off = getenv("PV_X3_BIAS_MMA");
+        static const char* ds = getenv("PV_X3_BIAS_DESC");
+        a.bias_mma = !(off && off[0] == '0');
+        a.bias_lbo = 128; a.bias_sbo = 256;
+        if (ds) { unsigned l = 0, s2 = 0; if (sscanf(ds, "%u,%u", &l, &s2) == 2) { a.bias_lbo = l; a.bias_sbo = s2; } }
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -344,14 +374,23 @@ int launch_resfront_fwd_x3_tc(const float* x_hi, const float* x_lo, const float*
     // executed: three products per GEMM on the padded 32 x 256 shapes
     PV_TIMED(relu_bits ? "resfront_fwd_x3" : "resfront_fwd_x3_infer", st, flops, 0.0, 3.0 * 2.0 * 2.0 * (double)ntiles * 128.0 * 32.0 * 256.0);
     static const bool sequential = getenv("PV_X3_SEQUENTIAL") != nullptr;     // A/B: the previous issue order
-    static size_t attr[4][16] = {};
+    static size_t attr[8][16] = {};
     auto go = [&](auto kern, size_t (&at)[16]) -> int {
         PV_CUDA(ensure_dyn_smem(kern, smem, at));
         PV_CUDA(launch_pdl(kern, grid, RX_THREADS, smem, st, tm_xh, tm_xl, tm_w1h, tm_w1l, tm_w2p, a));
         return 0;
     };
-    if (relu_bits) PV_TRY(sequential ? go(resfront_fwd_x3_kernel<1, false>, attr[0]) : go(resfront_fwd_x3_kernel<1, true>, attr[1]));
-    else PV_TRY(sequential ? go(resfront_fwd_x3_kernel<0, false>, attr[2]) : go(resfront_fwd_x3_kernel<0, true>, attr[3]));
+    const int variant = (relu_bits ? 4 : 0) | (sequential ? 0 : 2) | (a.bias_mma ? 1 : 0);
+    switch (variant) {
+        case 0: PV_TRY(go(resfront_fwd_x3_kernel<0, false, false>, attr[0])); break;
+        case 1: PV_TRY(go(resfront_fwd_x3_kernel<0, false, true>, attr[1])); break;
+        case 2: PV_TRY(go(resfront_fwd_x3_kernel<0, true, false>, attr[2])); break;
+        case 3: PV_TRY(go(resfront_fwd_x3_kernel<0, true, true>, attr[3])); break;
+        case 4: PV_TRY(go(resfront_fwd_x3_kernel<1, false, false>, attr[4])); break;
+        case 5: PV_TRY(go(resfront_fwd_x3_kernel<1, false, true>, attr[5])); break;
+        case 6: PV_TRY(go(resfront_fwd_x3_kernel<1, true, false>, attr[6])); break;
+        default: PV_TRY(go(resfront_fwd_x3_kernel<1, true, true>, attr[7])); break;
+    }
     PV_LAUNCH_CHECK();
     return 0;
 }
