@@ -363,14 +363,16 @@ def run_b200(args, cfg):
     gflop_per_patch0 = TRAIN_GFLOP_PER_PATCH if os.path.splitext(os.path.basename(args.cfg))[0] == "p16t9c85r12" else sum(v["flops"] for v in rep.values()) / 2 / B / 1e9
     notes = {
         "resfront_bwd_weight": "fused expand/decay weight gradients: E^T and gE^T recomputed transposed in TMEM (not counted as algorithmic "
-                               "flops), TS-mode N=32 MMAs at 39 cycles each; MMA-issue floor 82 us per launch, see DESIGN.md section 4",
-        "norm_fwd_x3": "error-compensated conv3 forward: pass C = both correction products (x_lo w_hi + x_hi w_lo) as ONE kind::f16 chain over packed "
-                       "fp16 pair rows (K = 64 per tap), pass M = x_hi w_hi in tf32; 36 M128xN96 MMAs per 126 rows each, i.e. 3x the algorithmic "
-                       "MACs by construction (the price of the 1e-3 gradient bar); executed flops count pass C's fp16 MACs too",
-        "resfront_fwd_x3": "error-compensated fused expand/ReLU/decay forward: three MMAs per product, expanded tensor as hi | lo in TMEM",
-        "norm_wgrad": "conv3 weight gradient as M128xN96xK8 MMAs (80 cycles each, 75 % of the M slots useful): floor 64 us per launch",
-        "norm_fwd": "conv3 forward as 36 M128xN96xK8 MMAs per 126 rows: floor 47 us per launch",
-        "norm_dgrad": "conv3 data gradient as 36 M128xN96xK8 MMAs per 126 rows: floor 47 us per launch",
+                               "flops); MMA floor 47 us per launch, bound by the epilogue's instruction stream, see DESIGN.md section 4",
+        "norm_fwd_x3": "error-compensated conv3 forward in ONE launch over packed fp16 pair rows: main product x_hi w_hi (K = 32 per tap) and both "
+                       "corrections (K = 64 per tap) as kind::f16 MMAs into two TMEM accumulators, i.e. 3x the algorithmic MACs by construction "
+                       "(the price of the 1e-3 gradient bar); the executed flops are fp16 MACs",
+        "resfront_fwd_x3": "error-compensated fused expand/ReLU/decay forward: three tf32 MMAs per expand product (+ the bias as a 13th MMA), the "
+                           "expanded tensor as fp16 pairs in TMEM, decay GEMM in kind::f16; bound by the epilogue's instruction stream (ncu: "
+                           "tensor pipe 36 %, issue slots 48 %), DESIGN.md sections 4 and 7",
+        "norm_wgrad": "conv3 weight gradient as M128xN96xK8 MMAs (56 cycles each, 75 % of the M slots useful): floor 45 us per launch",
+        "norm_fwd": "conv3 forward as 36 M128xN96xK8 MMAs per 126 rows: floor 32 us per launch",
+        "norm_dgrad": "conv3 data gradient: 36 M128xN96xK8 tf32 MMAs per 126 rows (floor 32 us), or in tf32x3 54 K16 bf16 MMAs over pair rows (floor 57 us)",
     }
     roofline = {"kernel": top[0], "bound": "tensor", "achieved": ach, "peak": peaks["tensor_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tensor_sustained"], "traffic": traffic, "peak_source": peaks["source"] + ", bf16 sustained",
@@ -382,9 +384,9 @@ def run_b200(args, cfg):
                 "executed_frac_of_measured_tf32_peak": top[1]["exec_flops"] / (top[1]["ms"] * 1e-3) / 1e12 / tf32_peak["tf32_tflops_sustained"],
                 "whole_step": {"algorithmic_tflops": value * gflop_per_patch0 / 1e3 / ws, "frac_of_bf16_sustained": value * gflop_per_patch0 / 1e3 / ws / peaks["tensor_sustained"],
                                "frac_of_measured_tf32_peak": value * gflop_per_patch0 / 1e3 / ws / tf32_peak["tf32_tflops_sustained"]},
-                "note": "kind::tf32 MMAs run at half the bf16 rate, and an M128xNxK8 tf32 MMA costs 32 + N/2 cycles (the A-operand fetch "
-                        "is not overlapped; profiles/r01_umma_rate_probe.log), so N <= 96 GEMMs cannot exceed 60 % of the tf32 pipe. "
-                        + notes.get(top[0], ""),
+                "note": "kind::tf32 MMAs run at 0.45 of the bf16 rate here (measured), and an M128xNxK8 MMA from shared memory costs "
+                        "max(N/2, 32 + N/4) cycles (operands stream at 128 B/cycle; profiles/r02_umma_rate_probe.log), so the 32-channel GEMMs of "
+                        "this graph reach 50 - 86 % of the math rate at best. " + notes.get(top[0], ""),
                 "avg_launch_ms": top[1]["ms"] / top[1]["launches"], "share_of_step": top[1]["ms"] / tot_ms}
     sl = rep.get("shift_loss_patch")
     roof_loss = None
