@@ -228,3 +228,29 @@ def test_predict_helpers_with_a_stub_model():
     imgs = np.arange(64 * 4).reshape(64, 2, 2, 1).astype(np.float64)
     rec = pb.reconstruct_from_patches(imgs)
     assert rec.shape == (16, 16, 1) and np.array_equal(rec[2:4, 4:6], imgs[1 * 8 + 2])   # row-major: block (i=1, j=2)
+
+
+def test_cli_auto_precision_falls_back_to_the_dense_engine(monkeypatch):
+    """--precision auto (cli._build_model): the preferred tensor-core engine when model creation accepts the graph, the dense fp32 engine
+    when it rejects it; an explicit precision is passed through untouched (and its error is NOT swallowed).  No GPU: build_from_config is
+    replaced by a stand-in that rejects 64-filter graphs on the row engines like pv_model_create does."""
+    import probav_b200 as pb
+    from probav_b200 import cli
+    from probav_b200._lib import PvError
+    calls = []
+
+    def fake_build(config, band="NIR", precision="fp32", **kw):
+        calls.append(precision)
+        if precision != "fp32" and config["num_filters"] != 32:
+            raise PvError("[pv_status -2] the row engine runs 32-filter graphs")
+        return ("model", precision)
+
+    monkeypatch.setattr(pb, "build_from_config", fake_build)
+    assert cli._build_model({"num_filters": 32}, "NIR", "auto", "tf32x3") == ("model", "tf32x3")
+    assert cli._build_model({"num_filters": 64}, "NIR", "auto", "tf32x3") == ("model", "fp32")
+    assert calls == ["tf32x3", "tf32x3", "fp32"]
+    assert cli._build_model({"num_filters": 32}, "RED", "tf32", "tf32x3") == ("model", "tf32")
+    with pytest.raises(PvError):
+        cli._build_model({"num_filters": 64}, "NIR", "tf32x3", "tf32x3")
+    a, b = cli.train_parser().parse_args([]), cli.test_parser().parse_args([])
+    assert a.precision == "auto" and b.precision == "auto"
