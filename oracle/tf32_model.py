@@ -12,6 +12,7 @@ forward pass AND in both backward products, exactly where the CUDA kernels round
     "rn"    round-to-nearest-away to tf32 (10 explicit mantissa bits)   -- cvt.rna.tf32.f32 / the half-ulp bump
     "tr"    truncation to tf32                                           -- what tcgen05 kind::tf32 does to a raw fp32 operand
     "x2"    hi + lo split, hi = tr(x), lo = tr(x - hi): two MMAs per product, ~21 mantissa bits
+    "f16p"  the packed fp16 pair row of the final engine (hi = fp16(tf32(x)), lo scaled by 2^12): ~22 bits;  "bf16x2" the bf16 pair (16 bits)
     "none"  exact (fp32 CUDA-core engine)
 `act_b` / `wt_b` (default: the same as act / wt) are the quantisers the BACKWARD products apply to the saved activation /
 the weights; `stream` says whether the residual stream A_i (forward) and its gradient (backward) are rounded at every block boundary
@@ -64,7 +65,15 @@ def q_bf16(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.float32).to(torch.bfloat16).to(x.dtype)
 
 
-Q = {"rn": q_rn, "tr": q_tr, "x2": q_x2, "none": lambda x: x, "bf16": q_bf16, "bf16x2": q_bf16x2}
+def q_f16p(x: torch.Tensor) -> torch.Tensor:
+    """the packed fp16 pair row of csrc/rows.h: fp16(tf32(x)) + fp16(2^12 (x - fp16(tf32(x)))) / 2^12 (~22 mantissa bits for O(1) values)."""
+    x32 = x.to(torch.float32)
+    hi = q_rn(x32).to(torch.float16).to(torch.float32)
+    lo = ((x32 - hi) * 4096.0).to(torch.float16).to(torch.float32) / 4096.0
+    return (hi.double() + lo.double()).to(x.dtype)
+
+
+Q = {"rn": q_rn, "tr": q_tr, "x2": q_x2, "none": lambda x: x, "bf16": q_bf16, "bf16x2": q_bf16x2, "f16p": q_f16p}
 
 
 class _QConv(torch.autograd.Function):
